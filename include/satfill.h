@@ -1,0 +1,164 @@
+/* satfill.h -- C-ABI of libsatfill.so, the B200 (sm_100a) implementation of the Laplace / Poisson fill path of
+ * ebiederstadt/satellite-approximation (lib/approx).
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++ / torch / Eigen types.  The C++ `approx`
+ * shim (cpp/include/approx/*.h), the pybind11 module `satellite_approximation._core` and the ctypes binding
+ * (satellite_approximation_b200/_capi.py) all sit on exactly these entry points.  Each entry point names the
+ * reference interface it replaces (paths relative to the reference repository root).
+ *
+ * Conventions
+ *   * Images are `double`, masks are one byte per pixel (non-zero = invalid), like the reference's
+ *     utils::MatX<f64> / MatX<bool> (lib/utils/include/utils/types.h:31).
+ *   * Every host image / mask argument carries explicit ELEMENT strides (row_stride, col_stride).  The reference's
+ *     MatX is column-major (row_stride = 1, col_stride = rows); numpy C-order is (cols, 1).  One of the two strides
+ *     must be 1 and the other >= the extent it jumps over.
+ *   * Integer outputs are always in row-major raster order of (row, col), which is how the reference scans
+ *     (laplace.cpp:34-40, poisson.cpp:169-176).
+ *   * Host-pointer entry points own all device memory and copies; `sa_scene_*` entry points keep a scene resident
+ *     in HBM so that a caller (bench.py) can time the solve alone.
+ *   * Every function returns an sa_status; sa_last_error(ctx) holds a message for the last non-zero one.
+ *   * A context is the unit of thread-safety: one host thread per context at a time.
+ */
+#ifndef SATFILL_H
+#define SATFILL_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SATFILL_ABI_VERSION 1
+
+typedef enum sa_status {
+    SA_OK = 0,
+    SA_EMPTY_MASK = 1,     /* no invalid pixel: nothing done (laplace.cpp:41-44 logs and returns)                 */
+    SA_NOT_CONVERGED = 2,  /* max_iterations reached first (Eigen::NoConvergence, poisson.cpp:263-269)            */
+    SA_SIZE_MISMATCH = 3,  /* laplace.cpp:124-127 throws; poisson.cpp:154-157 logs and returns                    */
+    SA_BAD_ARGUMENT = 4,
+    SA_CUDA_ERROR = 5,
+    SA_NCCL_ERROR = 6,
+    SA_OUT_OF_MEMORY = 7
+} sa_status;
+
+typedef struct sa_ctx sa_ctx;
+typedef struct sa_scene sa_scene;
+
+typedef enum sa_problem {
+    SA_LAPLACE = 0, /* laplace.cpp:31-120: unknowns = invalid pixels not on the image border, diagonal 4, x0 = 0   */
+    SA_POISSON = 1  /* poisson.cpp:145-290: unknowns = invalid pixels, diagonal = #in-image neighbours, x0 = g     */
+} sa_problem;
+
+typedef enum sa_precond {
+    SA_PRECOND_JACOBI = 0,   /* Eigen's DiagonalPreconditioner (BasicPreconditioners.h:39-86), matrix-free        */
+    SA_PRECOND_MULTIGRID = 1 /* symmetric V-cycle on the masked grid (DESIGN.md "Multigrid")                       */
+} sa_precond;
+
+/* Solver knobs.  The reference exposes tolerance / max_iterations on Poisson only (poisson.h:45-46); Laplace runs
+ * Eigen defaults (epsilon, 2N; laplace.cpp:113-114, IterativeSolverBase.h:251,367-368).  Zero-initialise, then
+ * call sa_default_options(). */
+typedef struct sa_options {
+    double tolerance;       /* stop when |b_U - A_UU x|_2 <= tolerance * |b_U|_2 on the reduced system          */
+    int64_t max_iterations; /* <= 0: reference default (Laplace 2n, Poisson n/2 with n = unknowns)              */
+    int32_t precond;        /* sa_precond                                                                        */
+    int32_t check_every;    /* host polls the device-side convergence flags every this many iterations          */
+    int32_t mg_levels;      /* multigrid: maximum number of levels (<= 0: automatic)                             */
+    int32_t mg_smooth;      /* multigrid: pre = post smoothing sweeps                                            */
+    int32_t profile;        /* != 0: time every solver kernel with CUDA events (sa_stats.kernel_ms)              */
+    int32_t reserved[3];
+} sa_options;
+
+/* Per-band solve record (superset of approx::PerfInfo, poisson.h:12-21). */
+typedef struct sa_stats {
+    int64_t unknowns;       /* PerfInfo::region_size                                                            */
+    int64_t iterations;     /* PerfInfo::iterations                                                             */
+    int64_t max_iterations; /* PerfInfo::max_iterations actually applied                                        */
+    double tolerance;       /* PerfInfo::tolerance                                                              */
+    double error;           /* PerfInfo::error: sqrt(|r|^2 / |b|^2) at exit                                     */
+    double solve_ms;        /* PerfInfo::solve_time: device time of the solve loop for the whole batch          */
+    double setup_ms;        /* device time of mask indexing + right-hand side                                   */
+    int32_t status;         /* sa_status of this band                                                           */
+    int32_t active_tiles;   /* tiles of the block-sparse layout that contain an unknown                         */
+    /* sa_options.profile: summed CUDA-event durations and launch counts of the solver kernels of the whole batch,
+     * by class: 0 = CG direction (p update + p.Ap), 1 = CG update (x, r, norms), 2 = multigrid smoother,
+     * 3 = multigrid transfer (residual + restriction, prolongation + correction) */
+    double kernel_ms[4];
+    int64_t kernel_launches[4];
+} sa_stats;
+
+/* ---- context ------------------------------------------------------------------------------------------------ */
+
+/* device: CUDA ordinal.  stream: a cudaStream_t the library should launch on (e.g. torch's current stream), or NULL
+ * for a stream the context creates and owns. */
+int sa_create(sa_ctx** out, int device, void* stream);
+void sa_destroy(sa_ctx* ctx);
+const char* sa_last_error(const sa_ctx* ctx);
+int sa_abi_version(void);
+void sa_default_options(sa_options* opts, int problem);
+/* number of kernels of this library launched through ctx since creation (bench.py's gpu_launches) */
+int64_t sa_kernel_launches(const sa_ctx* ctx);
+
+/* ---- integer path, host pointers ----------------------------------------------------------------------------- */
+
+/* Replaces the invalid-pixel scan + bounding box of solve_matrix (laplace.cpp:33-52).
+ * out_pixels: capacity `capacity` (row, col) int64 pairs, may be NULL to only count.  bbox = {min_row, max_row,
+ * min_col, max_col}; for an empty mask {rows, -1, cols, -1}. */
+int sa_mask_scan(sa_ctx* ctx, const uint8_t* mask, int64_t rows, int64_t cols, int64_t row_stride, int64_t col_stride,
+    int64_t* out_pixels, int64_t capacity, int64_t* out_count, int64_t bbox[4]);
+
+/* Replaces the unknown numbering of blend_images_poisson (poisson.cpp:162-177): numbering[col + row*cols] = k, the
+ * number of invalid pixels strictly before (row, col) in raster order, or -1 for valid pixels. */
+int sa_unknown_numbering(sa_ctx* ctx, const uint8_t* mask, int64_t rows, int64_t cols, int64_t row_stride,
+    int64_t col_stride, int32_t* numbering, int64_t* out_count);
+
+/* Replaces approx::find_connected_components (laplace.h:11-20, declared but never defined in the reference;
+ * contract: tests/approximation.h:55-75 + SURVEY.md 8a A3).  4-connectivity, background 0, labels 1..K by first
+ * pixel in raster order.  labels is a dense row-major rows x cols table. */
+int sa_label_components(sa_ctx* ctx, const uint8_t* mask, int64_t rows, int64_t cols, int64_t row_stride,
+    int64_t col_stride, int32_t* labels, int32_t* out_num_labels);
+
+/* ---- float path, host pointers -------------------------------------------------------------------------------- */
+
+/* Replaces approx::fill_missing_portion_smooth_boundary (laplace.h:28, laplace.cpp:122-132) for `nbands` images
+ * sharing one mask (apply_laplace, laplace.cpp:152-162, calls it once per channel and re-assembles each time).
+ * images[b] is modified in place at invalid pixels only.  The element-count check of laplace.cpp:124-127 is made by
+ * the caller-side shim (one rows x cols here covers image and mask); stats: nbands entries or NULL.
+ * Laplace unknowns are the invalid pixels that are not on the image border: border pixels are Dirichlet data and come
+ * back unchanged (laplace.cpp:98-100). */
+int sa_laplace_fill(sa_ctx* ctx, double* const* images, int nbands, const uint8_t* mask, int64_t rows, int64_t cols,
+    int64_t row_stride, int64_t col_stride, const sa_options* opts, sa_stats* stats);
+
+/* Replaces approx::blend_images_poisson, mask overload (poisson.h:41-46, poisson.cpp:145-290).  inputs[b] is
+ * modified in place at invalid pixels only, and only if every band converged (poisson.cpp:263-269). */
+int sa_poisson_blend(sa_ctx* ctx, double* const* inputs, const double* const* replacements, int nbands,
+    const uint8_t* mask, int64_t rows, int64_t cols, int64_t row_stride, int64_t col_stride, const sa_options* opts,
+    sa_stats* stats);
+
+/* ---- device-resident scenes ------------------------------------------------------------------------------------ */
+
+/* A scene = one mask + nbands images (+ nbands guidance images for SA_POISSON) + solver work vectors, all in HBM,
+ * in the library's layout: row-major with the unit-stride axis of the source as the fast axis (the 5-point operator
+ * is transpose-invariant, so a column-major source is solved as its transpose without a transposition). */
+int sa_scene_create(sa_ctx* ctx, int problem, int64_t rows, int64_t cols, int nbands, sa_scene** out);
+void sa_scene_destroy(sa_scene* scene);
+/* src_on_device != 0: `src` is a device pointer (same strides convention).  Uploads are asynchronous on the
+ * context's stream when the host memory is pinned. */
+int sa_scene_set_mask(sa_scene* scene, const uint8_t* src, int64_t row_stride, int64_t col_stride, int src_on_device);
+int sa_scene_set_band(sa_scene* scene, int band, const double* src, int64_t row_stride, int64_t col_stride,
+    int src_on_device);
+int sa_scene_set_guidance(sa_scene* scene, int band, const double* src, int64_t row_stride, int64_t col_stride,
+    int src_on_device);
+/* Mask indexing + tile list + right-hand side + solve + write-back into the resident bands. */
+int sa_scene_solve(sa_scene* scene, const sa_options* opts, sa_stats* stats);
+int sa_scene_get_band(sa_scene* scene, int band, double* dst, int64_t row_stride, int64_t col_stride, int dst_on_device);
+/* After a solve (or any call that indexed the mask): unknowns of the linear system, tiles of the block-sparse layout
+ * that hold one, and tiles in total.  Any pointer may be NULL. */
+int sa_scene_info(const sa_scene* scene, int64_t* unknowns, int32_t* active_tiles, int32_t* total_tiles);
+/* Blocks until everything queued on the context's stream has finished. */
+int sa_synchronize(sa_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SATFILL_H */

@@ -1,0 +1,452 @@
+"""satellite_approximation_b200 -- the Laplace / Poisson fill path of ebiederstadt/satellite-approximation on B200.
+
+Host-side mirror of the reference's Python module ``satellite_approximation`` (``src/main.cpp:49-58``,
+``src/satellite_approximation/__init__.py``) for the fill path, plus the declared-but-undefined
+``find_connected_components`` (``lib/approx/include/approx/laplace.h:11-20``).  Same function names, argument names,
+defaults, dtype rules and error behaviour; the arithmetic runs in ``lib/libsatfill.so`` (hand-written CUDA for
+sm_100a) through the C-ABI in ``include/satfill.h``.  There is no CPU fallback: importing works without a GPU, calling
+does not.
+
+    from satellite_approximation_b200 import filling_missing_portions_smooth_boundaries, blend_images_poisson
+    filled = filling_missing_portions_smooth_boundaries(img_f64, mask_bool)
+    bands  = blend_images_poisson([f0, f1], [g0, g1], mask_bool, tolerance=1e-6)
+
+Device-resident use (no PCIe traffic inside the solve; what ``bench.py`` times as ``value``)::
+
+    ctx = Context(device=0)
+    scene = ctx.scene(LAPLACE, rows, cols, nbands)
+    scene.set_mask(mask); scene.set_band(0, img); stats = scene.solve(tolerance=1e-6); out = scene.get_band(0)
+"""
+from __future__ import annotations
+
+import ctypes as C
+import enum
+import logging
+import threading
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _capi
+from ._capi import (  # noqa: F401  (re-exported)
+    SA_EMPTY_MASK,
+    SA_LAPLACE as LAPLACE,
+    SA_NOT_CONVERGED,
+    SA_OK,
+    SA_POISSON as POISSON,
+    SA_PRECOND_JACOBI as JACOBI,
+    SA_PRECOND_MULTIGRID as MULTIGRID,
+    SatfillError,
+)
+
+__all__ = [
+    "LogLevel", "set_log_level", "filling_missing_portions_smooth_boundaries", "blend_images_poisson",
+    "find_connected_components", "ConnectedComponents", "mask_scan", "unknown_numbering", "valid_neighbours",
+    "Context", "Scene", "SolveStats", "default_context", "set_solver_defaults", "last_perf_info",
+    "LAPLACE", "POISSON", "JACOBI", "MULTIGRID", "SatfillError",
+]  # fmt: skip
+
+_log = logging.getLogger("satellite_approximation_b200")
+
+
+class LogLevel(enum.IntEnum):
+    """spdlog levels exported by the reference module (src/main.cpp:24-29)."""
+
+    Debug = 1
+    Info = 2
+    Warn = 3
+    Error = 4
+    Critical = 5
+
+
+_PY_LEVEL = {
+    LogLevel.Debug: logging.DEBUG, LogLevel.Info: logging.INFO, LogLevel.Warn: logging.WARNING,
+    LogLevel.Error: logging.ERROR, LogLevel.Critical: logging.CRITICAL,
+}  # fmt: skip
+
+
+def set_log_level(level: LogLevel) -> None:
+    """src/main.cpp:30-34.  Unlike the reference nothing is created on disk at import time."""
+    _log.setLevel(_PY_LEVEL[LogLevel(level)])
+    _log.info("Logging set to level: %s", LogLevel(level).name)
+
+
+class SolveStats(dict):
+    """Per-band solve record: superset of approx::PerfInfo (poisson.h:12-21)."""
+
+    __getattr__ = dict.__getitem__
+
+
+# Solver knobs the reference does not expose on its Python surface.  `None` = the reference's own behaviour
+# (Laplace: Eigen defaults, epsilon tolerance / 2N iterations, laplace.cpp:113-114).
+_defaults = {"laplace_tolerance": None, "laplace_max_iterations": None, "precond": JACOBI, "check_every": 32}
+_last_perf: list[SolveStats] = []
+
+
+def set_solver_defaults(**kw) -> None:
+    """laplace_tolerance, laplace_max_iterations, precond (JACOBI | MULTIGRID), check_every."""
+    for k, v in kw.items():
+        if k not in _defaults:
+            raise TypeError(f"unknown solver default {k!r}")
+        _defaults[k] = v
+
+
+def last_perf_info() -> list[SolveStats]:
+    """Records of the most recent fill (the reference appends PerfInfo to a hard-coded CSV, poisson.cpp:287-289)."""
+    return list(_last_perf)
+
+
+def _ptr(a) -> int:
+    return a.ctypes.data if isinstance(a, np.ndarray) else int(a.data_ptr())
+
+
+def _describe(a, dtype_np, what: str):
+    """(pointer, rows, cols, row_stride, col_stride, on_device) of a numpy array or a CUDA torch tensor."""
+    if isinstance(a, np.ndarray):
+        if a.dtype != dtype_np:
+            raise TypeError(f"{what}: expected dtype {np.dtype(dtype_np)}, got {a.dtype}")
+        rs, cs = _capi.element_strides(a)
+        return a.ctypes.data, a.shape[0], a.shape[1], rs, cs, 0
+    import torch  # device buffers are torch tensors: torch is the plumbing for device memory and streams
+
+    if not isinstance(a, torch.Tensor) or a.dim() != 2:
+        raise TypeError(f"{what}: expected a 2-D numpy array or torch tensor")
+    want = (torch.float64,) if np.dtype(dtype_np) == np.float64 else (torch.uint8, torch.bool)
+    if a.dtype not in want:
+        raise TypeError(f"{what}: expected {want}, got {a.dtype}")
+    return a.data_ptr(), a.shape[0], a.shape[1], a.stride(0), a.stride(1), 1 if a.is_cuda else 0
+
+
+class Context:
+    """One sa_ctx: a device, a stream and the scene cache of the host-pointer entry points."""
+
+    def __init__(self, device: int = 0, stream: Optional[int] = None):
+        self._lib = _capi.load()
+        h = C.c_void_p()
+        st = self._lib.sa_create(C.byref(h), int(device), C.c_void_p(stream) if stream else None)
+        if st != SA_OK:
+            raise SatfillError(st, f"sa_create(device={device}) failed: no usable CUDA device (no CPU fallback)")
+        self._h = h
+        self.device = int(device)
+        self._lock = threading.Lock()
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self._lib.sa_destroy(self._h)
+            self._h = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, st: int, ok=(SA_OK,)):
+        if st not in ok:
+            raise SatfillError(st, self._lib.sa_last_error(self._h).decode())
+        return st
+
+    @property
+    def kernel_launches(self) -> int:
+        return int(self._lib.sa_kernel_launches(self._h))
+
+    def synchronize(self) -> None:
+        self._check(self._lib.sa_synchronize(self._h))
+
+    def options(self, problem: int, tolerance=None, max_iterations=None, precond=None, check_every=None,
+                mg_levels=None, mg_smooth=None, profile=None) -> _capi.Options:  # fmt: skip
+        o = _capi.Options()
+        self._lib.sa_default_options(C.byref(o), problem)
+        if tolerance is not None:
+            o.tolerance = float(tolerance)
+        if max_iterations is not None:
+            o.max_iterations = int(max_iterations)
+        if precond is not None:
+            o.precond = int(precond)
+        if check_every is not None:
+            o.check_every = int(check_every)
+        if mg_levels is not None:
+            o.mg_levels = int(mg_levels)
+        if mg_smooth is not None:
+            o.mg_smooth = int(mg_smooth)
+        if profile is not None:
+            o.profile = int(bool(profile))
+        return o
+
+    # ---- integer path -----------------------------------------------------------------------------------------
+    def mask_scan(self, mask: np.ndarray):
+        """laplace.cpp:33-52: (pixels[n, 2] int64 in row-major raster order, bbox = [min_row, max_row, min_col, max_col])."""
+        m = _mask_u8(mask)
+        rs, cs = _capi.element_strides(m)
+        n = C.c_int64()
+        bbox = (C.c_int64 * 4)()
+        self._check(self._lib.sa_mask_scan(self._h, m.ctypes.data, m.shape[0], m.shape[1], rs, cs, None, 0,
+                                           C.byref(n), bbox))  # fmt: skip
+        px = np.empty((n.value, 2), np.int64)
+        if n.value:
+            self._check(self._lib.sa_mask_scan(self._h, m.ctypes.data, m.shape[0], m.shape[1], rs, cs, px.ctypes.data,
+                                               n.value, C.byref(n), bbox))  # fmt: skip
+        return px, np.array(list(bbox), np.int64)
+
+    def unknown_numbering(self, mask: np.ndarray):
+        """poisson.cpp:162-177: (numbering[rows, cols] int32 with -1 at valid pixels, n)."""
+        m = _mask_u8(mask)
+        rs, cs = _capi.element_strides(m)
+        num = np.empty(m.shape, np.int32)
+        n = C.c_int64()
+        self._check(self._lib.sa_unknown_numbering(self._h, m.ctypes.data, m.shape[0], m.shape[1], rs, cs,
+                                                   num.ctypes.data, C.byref(n)))  # fmt: skip
+        return num, int(n.value)
+
+    def label_components(self, mask: np.ndarray):
+        """laplace.h:11-20 contract: (labels[rows, cols] int32, K)."""
+        m = _mask_u8(mask)
+        rs, cs = _capi.element_strides(m)
+        lab = np.empty(m.shape, np.int32)
+        k = C.c_int32()
+        self._check(self._lib.sa_label_components(self._h, m.ctypes.data, m.shape[0], m.shape[1], rs, cs,
+                                                  lab.ctypes.data, C.byref(k)))  # fmt: skip
+        return lab, int(k.value)
+
+    # ---- float path, host buffers -------------------------------------------------------------------------------
+    def laplace_fill(self, images: Sequence[np.ndarray], mask: np.ndarray, **opts):
+        """In place on `images` (float64, all one layout, same shape as mask).  Returns per-band SolveStats."""
+        m = _mask_u8(mask)
+        rows, cols = m.shape
+        rs, cs = _capi.element_strides(m)
+        for a in images:
+            if a.dtype != np.float64 or a.shape != m.shape or _capi.element_strides(a) != (rs, cs):
+                raise ValueError("laplace_fill: images must be float64 with the shape and memory layout of the mask")
+        nb = len(images)
+        ptrs = (C.c_void_p * nb)(*[a.ctypes.data for a in images])
+        stats = (_capi.Stats * nb)()
+        o = self.options(LAPLACE, **opts)
+        with self._lock:
+            st = self._lib.sa_laplace_fill(self._h, ptrs, nb, m.ctypes.data, rows, cols, rs, cs, C.byref(o), stats)
+        self._check(st, ok=(SA_OK, SA_EMPTY_MASK, SA_NOT_CONVERGED))
+        return [SolveStats(s.as_dict()) for s in stats]
+
+    def poisson_blend(self, inputs: Sequence[np.ndarray], replacements: Sequence[np.ndarray], mask: np.ndarray,
+                      **opts):  # fmt: skip
+        m = _mask_u8(mask)
+        rows, cols = m.shape
+        rs, cs = _capi.element_strides(m)
+        for a in list(inputs) + list(replacements):
+            if a.dtype != np.float64 or a.shape != m.shape or _capi.element_strides(a) != (rs, cs):
+                raise ValueError("poisson_blend: images must be float64 with the shape and memory layout of the mask")
+        nb = len(inputs)
+        pin = (C.c_void_p * nb)(*[a.ctypes.data for a in inputs])
+        prp = (C.c_void_p * nb)(*[a.ctypes.data for a in replacements])
+        stats = (_capi.Stats * nb)()
+        o = self.options(POISSON, **opts)
+        with self._lock:
+            st = self._lib.sa_poisson_blend(self._h, pin, prp, nb, m.ctypes.data, rows, cols, rs, cs, C.byref(o), stats)
+        self._check(st, ok=(SA_OK, SA_EMPTY_MASK, SA_NOT_CONVERGED))
+        return [SolveStats(s.as_dict()) for s in stats]
+
+    def scene(self, problem: int, rows: int, cols: int, nbands: int = 1) -> "Scene":
+        return Scene(self, problem, rows, cols, nbands)
+
+
+class Scene:
+    """A mask + nbands images (+ guidance) resident in HBM (sa_scene_*)."""
+
+    def __init__(self, ctx: Context, problem: int, rows: int, cols: int, nbands: int):
+        self.ctx, self.problem, self.rows, self.cols, self.nbands = ctx, problem, rows, cols, nbands
+        h = C.c_void_p()
+        ctx._check(ctx._lib.sa_scene_create(ctx._h, problem, rows, cols, nbands, C.byref(h)))
+        self._h = h
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) and getattr(self.ctx, "_h", None):
+            self.ctx._lib.sa_scene_destroy(self._h)
+        self._h = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _shape_ok(self, rows, cols):
+        if (rows, cols) != (self.rows, self.cols):
+            raise ValueError(f"expected shape {(self.rows, self.cols)}, got {(rows, cols)}")
+
+    def set_mask(self, mask) -> None:
+        if isinstance(mask, np.ndarray):
+            mask = _mask_u8(mask)
+        p, r, c, rs, cs, dev = _describe(mask, np.uint8, "mask")
+        self._shape_ok(r, c)
+        self.ctx._check(self.ctx._lib.sa_scene_set_mask(self._h, p, rs, cs, dev))
+
+    def set_band(self, band: int, image) -> None:
+        p, r, c, rs, cs, dev = _describe(image, np.float64, "image")
+        self._shape_ok(r, c)
+        self.ctx._check(self.ctx._lib.sa_scene_set_band(self._h, band, p, rs, cs, dev))
+
+    def set_guidance(self, band: int, image) -> None:
+        p, r, c, rs, cs, dev = _describe(image, np.float64, "guidance")
+        self._shape_ok(r, c)
+        self.ctx._check(self.ctx._lib.sa_scene_set_guidance(self._h, band, p, rs, cs, dev))
+
+    def solve(self, raise_on_failure: bool = False, **opts) -> list[SolveStats]:
+        stats = (_capi.Stats * self.nbands)()
+        o = self.ctx.options(self.problem, **opts)
+        st = self.ctx._lib.sa_scene_solve(self._h, C.byref(o), stats)
+        self.ctx._check(st, ok=(SA_OK,) if raise_on_failure else (SA_OK, SA_EMPTY_MASK, SA_NOT_CONVERGED))
+        return [SolveStats(s.as_dict()) for s in stats]
+
+    def get_band(self, band: int, out=None, order: str = "C"):
+        if out is None:
+            out = np.empty((self.rows, self.cols), np.float64, order=order)
+        p, r, c, rs, cs, dev = _describe(out, np.float64, "out")
+        self._shape_ok(r, c)
+        self.ctx._check(self.ctx._lib.sa_scene_get_band(self._h, band, p, rs, cs, dev))
+        return out
+
+    def info(self) -> dict:
+        n, a, t = C.c_int64(), C.c_int32(), C.c_int32()
+        self.ctx._lib.sa_scene_info(self._h, C.byref(n), C.byref(a), C.byref(t))
+        return {"unknowns": n.value, "active_tiles": a.value, "total_tiles": t.value}
+
+
+_default_ctx: Optional[Context] = None
+_ctx_lock = threading.Lock()
+
+
+def default_context() -> Context:
+    """The process-wide context the module-level functions use (device 0 unless LOCAL_RANK says otherwise)."""
+    global _default_ctx
+    with _ctx_lock:
+        if _default_ctx is None:
+            import os
+
+            _default_ctx = Context(int(os.environ.get("SATFILL_DEVICE", os.environ.get("LOCAL_RANK", "0"))))
+        return _default_ctx
+
+
+def _mask_u8(mask: np.ndarray) -> np.ndarray:
+    if not isinstance(mask, np.ndarray) or mask.ndim != 2:
+        raise TypeError("mask: expected a 2-D numpy array")
+    if mask.dtype == np.bool_:
+        mask = mask.view(np.uint8)
+    elif mask.dtype != np.uint8:
+        raise TypeError(f"mask: expected bool or uint8, got {mask.dtype}")
+    if not _capi.is_dense_2d(mask):
+        mask = np.ascontiguousarray(mask)
+    return mask
+
+
+# ---- the reference's Python surface ---------------------------------------------------------------------------------
+
+
+def filling_missing_portions_smooth_boundaries(input_image: np.ndarray, invalid_pixels: np.ndarray) -> np.ndarray:
+    """Laplace (harmonic) fill of the invalid pixels -- src/main.cpp:49-54 -> laplace.cpp:122-132.
+
+    Both arguments are ``noconvert`` in the reference: ``input_image`` must be a 2-D float64 array and
+    ``invalid_pixels`` a 2-D bool array (any strides), otherwise TypeError.  Returns a NEW Fortran-ordered float64
+    array; the argument is not modified.  Raises RuntimeError when the element counts differ (laplace.cpp:124-127).
+    """
+    if not (isinstance(input_image, np.ndarray) and input_image.ndim == 2 and input_image.dtype == np.float64):
+        raise TypeError("filling_missing_portions_smooth_boundaries(): input_image must be a 2-D float64 numpy array")
+    if not (isinstance(invalid_pixels, np.ndarray) and invalid_pixels.ndim == 2 and invalid_pixels.dtype == np.bool_):
+        raise TypeError("filling_missing_portions_smooth_boundaries(): invalid_pixels must be a 2-D bool numpy array")
+    if input_image.size != invalid_pixels.size:
+        raise RuntimeError("Input image and mask need to be the same size")  # laplace.cpp:124-127
+    out = np.array(input_image, dtype=np.float64, order="F", copy=True)  # the pybind11 caster copies (MatX is col-major)
+    if invalid_pixels.shape != out.shape:
+        # same element count, different shape: the reference indexes the mask with the image's (row, col)
+        raise RuntimeError("Input image and mask need to be the same shape")
+    mask = np.asfortranarray(invalid_pixels)
+    global _last_perf
+    _last_perf = default_context().laplace_fill(
+        [out], mask, tolerance=_defaults["laplace_tolerance"], max_iterations=_defaults["laplace_max_iterations"],
+        precond=_defaults["precond"], check_every=_defaults["check_every"],
+    )  # fmt: skip
+    if _last_perf and _last_perf[0]["status"] == SA_EMPTY_MASK:
+        _log.info("No invalid pixels: nothing to do")  # laplace.cpp:41-44
+    return out
+
+
+def blend_images_poisson(input_image: Sequence[np.ndarray], replacement_image: Sequence[np.ndarray],
+                         invalid_mask: np.ndarray, tolerance: float = 1e-6,
+                         max_iterations: Optional[int] = None) -> list[np.ndarray]:  # fmt: skip
+    """Poisson (seamless-cloning) blend, mask overload -- src/main.cpp:55-58 -> poisson.cpp:292-303, 145-290.
+
+    Returns a list of new Fortran-ordered float64 arrays.  Like the reference, a size mismatch or a band that does not
+    converge within ``max_iterations`` (default: unknowns / 2) is logged and the inputs come back unchanged
+    (poisson.cpp:154-157, 263-269).
+    """
+    outs = [np.array(a, dtype=np.float64, order="F", copy=True) for a in input_image]
+    reps = [np.asfortranarray(np.asarray(a, dtype=np.float64)) for a in replacement_image]
+    mask = np.asfortranarray(np.asarray(invalid_mask).astype(np.bool_, copy=False))
+    if any(a.ndim != 2 for a in outs + reps) or mask.ndim != 2:
+        raise TypeError("blend_images_poisson(): expected lists of 2-D arrays and a 2-D mask")
+    if not outs:
+        return outs
+    if len(outs) != len(reps) or any(a.shape != outs[0].shape for a in outs + reps):
+        _log.error("Input and replacement images must have the same dimensions")  # poisson.cpp:154-157
+        return outs
+    if mask.shape != outs[0].shape:
+        _log.error("Invalid mask must match the image dimensions")  # poisson.cpp:158-160 logs; continuing would read
+        return outs  # out of bounds in the reference (App. B4): return the inputs unchanged instead
+    global _last_perf
+    work = [a.copy(order="F") for a in outs]
+    _last_perf = default_context().poisson_blend(
+        work, reps, mask, tolerance=tolerance, max_iterations=max_iterations, precond=_defaults["precond"],
+        check_every=_defaults["check_every"],
+    )  # fmt: skip
+    if any(s["status"] == SA_NOT_CONVERGED for s in _last_perf):
+        _log.error("Failed to solve the linear system (no convergence)")  # poisson.cpp:263-269
+        return outs
+    return work
+
+
+class ConnectedComponents:
+    """approx::ConnectedComponents (laplace.h:11-14): `matrix` (labels, 0 = valid) and `region_map` label -> pixels."""
+
+    def __init__(self, matrix: np.ndarray, num_labels: int):
+        self.matrix = matrix
+        self.num_labels = num_labels
+        self._region_map = None
+
+    @property
+    def region_map(self) -> dict[int, np.ndarray]:
+        """label -> int64[n, 2] (row, col) in row-major raster order.  Built lazily from `matrix` (host bookkeeping)."""
+        if self._region_map is None:
+            flat = self.matrix.ravel(order="C")
+            idx = np.flatnonzero(flat)
+            order = np.argsort(flat[idx], kind="stable")
+            idx = idx[order]
+            labels = flat[idx]
+            cols = self.matrix.shape[1]
+            rc = np.stack([idx // cols, idx % cols], axis=1).astype(np.int64)
+            cuts = np.flatnonzero(np.diff(labels)) + 1
+            parts = np.split(rc, cuts)
+            self._region_map = {int(labels[s]): p for s, p in zip(np.concatenate([[0], cuts]), parts)} if len(idx) else {}
+        return self._region_map
+
+
+def find_connected_components(invalid: np.ndarray) -> ConnectedComponents:
+    """approx::find_connected_components (laplace.h:20; contract tests/approximation.h:55-75)."""
+    if not (isinstance(invalid, np.ndarray) and invalid.ndim == 2 and invalid.dtype in (np.bool_, np.uint8)):
+        raise TypeError("find_connected_components(): expected a 2-D bool array")
+    lab, k = default_context().label_components(invalid)
+    return ConnectedComponents(lab, k)
+
+
+def mask_scan(mask: np.ndarray):
+    return default_context().mask_scan(mask)
+
+
+def unknown_numbering(mask: np.ndarray):
+    return default_context().unknown_numbering(mask)
+
+
+def valid_neighbours(rows: int, cols: int, row: int, col: int) -> list[tuple[int, int]]:
+    """approx::valid_neighbours (utils.h:35-50): in-image 4-neighbours in the order (-1,0) (+1,0) (0,-1) (0,+1).
+
+    Pure index arithmetic on two integers (API value type); tests/approximation.h:9-33 pins the counts.
+    """
+    cand = [(row - 1, col), (row + 1, col), (row, col - 1), (row, col + 1)]
+    return [(r, c) for r, c in cand if 0 <= r < rows and 0 <= c < cols]

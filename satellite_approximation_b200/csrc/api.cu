@@ -1,0 +1,572 @@
+// C-ABI of libsatfill.so (include/satfill.h): contexts, device-resident scenes and the host-pointer entry points that
+// the C++ `approx` shim, the pybind11 module and the ctypes binding call.  No compute happens on the host: every
+// entry point either moves bytes or launches kernels of this library, and fails with SA_CUDA_ERROR when there is no
+// usable device.
+#include "common.cuh"
+
+#include <cstring>
+#include <new>
+
+using namespace satfill;
+
+namespace {
+
+enum Layout { LAYOUT_BAD = 0, LAYOUT_ROW_MAJOR = 1, LAYOUT_COL_MAJOR = 2 };
+
+Layout classify(int64_t rows, int64_t cols, int64_t rs, int64_t cs)
+{
+    bool row_major = (cs == 1 || cols <= 1) && (rs >= cols || rows <= 1);
+    bool col_major = (rs == 1 || rows <= 1) && (cs >= rows || cols <= 1);
+    if (row_major)
+        return LAYOUT_ROW_MAJOR;
+    if (col_major)
+        return LAYOUT_COL_MAJOR;
+    return LAYOUT_BAD;
+}
+
+int check_ctx(sa_ctx* ctx)
+{
+    if (!ctx)
+        return SA_BAD_ARGUMENT;
+    cudaError_t e = cudaSetDevice(ctx->device);
+    if (e != cudaSuccess)
+        return fail(ctx, SA_CUDA_ERROR, std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+    return SA_OK;
+}
+
+// Upload a host mask (any of the two layouts) as a dense row-major rows x cols device table (pitch = cols).
+int upload_mask_row_major(sa_ctx* ctx, const uint8_t* mask, int64_t rows, int64_t cols, int64_t rs, int64_t cs,
+    uint8_t** d_out)
+{
+    *d_out = nullptr;
+    Layout lay = classify(rows, cols, rs, cs);
+    if (lay == LAYOUT_BAD)
+        return fail(ctx, SA_BAD_ARGUMENT, "mask strides: one of row_stride / col_stride must be 1");
+    if (rows == 0 || cols == 0)
+        return SA_OK;
+    uint8_t* d = nullptr;
+    SA_CUDA(ctx, cudaMallocAsync(&d, (size_t)(rows * cols), ctx->stream));
+    if (lay == LAYOUT_ROW_MAJOR) {
+        SA_CUDA(ctx, cudaMemcpy2DAsync(d, (size_t)cols, mask, (size_t)(rows > 1 ? rs : cols), (size_t)cols, (size_t)rows,
+                         cudaMemcpyHostToDevice, ctx->stream));
+    } else {
+        uint8_t* t = nullptr;  // cols x rows, row-major = the column-major source as it lies in memory
+        SA_CUDA(ctx, cudaMallocAsync(&t, (size_t)(rows * cols), ctx->stream));
+        SA_CUDA(ctx, cudaMemcpy2DAsync(t, (size_t)rows, mask, (size_t)(cols > 1 ? cs : rows), (size_t)rows, (size_t)cols,
+                         cudaMemcpyHostToDevice, ctx->stream));
+        SA_TRY(transpose_u8(ctx, t, cols, rows, rows, d, cols));
+        SA_CUDA(ctx, cudaFreeAsync(t, ctx->stream));
+    }
+    *d_out = d;
+    return SA_OK;
+}
+
+int scene_alloc(sa_scene* s, bool transposed)
+{
+    sa_ctx* ctx = s->ctx;
+    s->transposed = transposed;
+    s->rows = transposed ? s->user_cols : s->user_rows;
+    s->cols = transposed ? s->user_rows : s->user_cols;
+    s->pitch = round_up(s->cols + 1, TILE_W);
+    s->rows_p = round_up(s->rows, TILE_H);
+    if (s->rows_p == 0)
+        s->rows_p = TILE_H;
+    s->plane = (s->rows_p + 2) * s->pitch;
+    s->tiles_x = (int)(s->pitch / TILE_W);
+    s->tiles_y = (int)(s->rows_p / TILE_H);
+    size_t vec = (size_t)s->plane * s->nbands * sizeof(double);
+    SA_CUDA(ctx, cudaMalloc(&s->u, vec));
+    SA_CUDA(ctx, cudaMalloc(&s->r, vec));
+    SA_CUDA(ctx, cudaMalloc(&s->p[0], vec));
+    SA_CUDA(ctx, cudaMalloc(&s->p[1], vec));
+    SA_CUDA(ctx, cudaMemsetAsync(s->u, 0, vec, ctx->stream));
+    if (s->problem == SA_POISSON) {
+        SA_CUDA(ctx, cudaMalloc(&s->g, vec));
+        SA_CUDA(ctx, cudaMemsetAsync(s->g, 0, vec, ctx->stream));
+    }
+    SA_CUDA(ctx, cudaMalloc(&s->mask, (size_t)s->plane));
+    SA_CUDA(ctx, cudaMalloc(&s->umask, (size_t)s->plane));
+    SA_CUDA(ctx, cudaMemsetAsync(s->mask, 0, (size_t)s->plane, ctx->stream));
+    SA_CUDA(ctx, cudaMemsetAsync(s->umask, 0, (size_t)s->plane, ctx->stream));
+    SA_CUDA(ctx, cudaMalloc(&s->tile_list, sizeof(int32_t) * 2 * (size_t)s->tiles_x * s->tiles_y));
+    SA_CUDA(ctx, cudaMalloc(&s->d_counters, sizeof(int32_t) * 4));
+    SA_CUDA(ctx, cudaMalloc(&s->d_count64, sizeof(unsigned long long)));
+    SA_CUDA(ctx, cudaMalloc(&s->scal, sizeof(BandScalars) * s->nbands));
+    s->oriented = true;
+    return SA_OK;
+}
+
+// Decide / check the resident orientation of a scene from the strides of a source or destination buffer.
+int scene_orient(sa_scene* s, int64_t rs, int64_t cs)
+{
+    Layout lay = classify(s->user_rows, s->user_cols, rs, cs);
+    if (lay == LAYOUT_BAD)
+        return fail(s->ctx, SA_BAD_ARGUMENT, "strides: one of row_stride / col_stride must be 1");
+    bool transposed = lay == LAYOUT_COL_MAJOR;
+    if (!s->oriented)
+        return scene_alloc(s, transposed);
+    if (transposed != s->transposed) {
+        // a buffer that is valid in both layouts (a single row or column) is fine
+        Layout alt = transposed ? LAYOUT_ROW_MAJOR : LAYOUT_COL_MAJOR;
+        bool both = (alt == LAYOUT_ROW_MAJOR)
+            ? ((cs == 1 || s->user_cols <= 1) && (rs >= s->user_cols || s->user_rows <= 1))
+            : ((rs == 1 || s->user_rows <= 1) && (cs >= s->user_rows || s->user_cols <= 1));
+        if (!both)
+            return fail(s->ctx, SA_BAD_ARGUMENT, "all buffers of one scene must share one memory layout");
+    }
+    return SA_OK;
+}
+
+// source pitch (elements) along the resident slow axis
+int64_t slow_stride(const sa_scene* s, int64_t rs, int64_t cs)
+{
+    int64_t st = s->transposed ? cs : rs;
+    return s->rows > 1 ? st : s->cols;
+}
+
+template <typename T>
+int copy_in(sa_scene* s, T* dst0, const T* src, int64_t rs, int64_t cs, int on_device, int64_t row_lo, int64_t row_hi)
+{
+    sa_ctx* ctx = s->ctx;
+    if (row_hi <= row_lo || s->cols == 0)
+        return SA_OK;
+    int64_t sp = slow_stride(s, rs, cs);
+    SA_CUDA(ctx, cudaMemcpy2DAsync(dst0 + row_lo * s->pitch, (size_t)s->pitch * sizeof(T), src + row_lo * sp,
+                     (size_t)sp * sizeof(T), (size_t)s->cols * sizeof(T), (size_t)(row_hi - row_lo),
+                     on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
+    return SA_OK;
+}
+
+template <typename T>
+int copy_out(sa_scene* s, const T* src0, T* dst, int64_t rs, int64_t cs, int on_device, int64_t row_lo, int64_t row_hi)
+{
+    sa_ctx* ctx = s->ctx;
+    if (row_hi <= row_lo || s->cols == 0)
+        return SA_OK;
+    int64_t dp = slow_stride(s, rs, cs);
+    SA_CUDA(ctx, cudaMemcpy2DAsync(dst + row_lo * dp, (size_t)dp * sizeof(T), src0 + row_lo * s->pitch,
+                     (size_t)s->pitch * sizeof(T), (size_t)s->cols * sizeof(T), (size_t)(row_hi - row_lo),
+                     on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, ctx->stream));
+    return SA_OK;
+}
+
+void scene_free(sa_scene* s)
+{
+    if (!s)
+        return;
+    if (s->ctx)
+        cudaSetDevice(s->ctx->device);
+    free_hierarchy(s);
+    cudaFree(s->u);
+    cudaFree(s->g);
+    cudaFree(s->r);
+    cudaFree(s->p[0]);
+    cudaFree(s->p[1]);
+    cudaFree(s->z);
+    cudaFree(s->mask);
+    cudaFree(s->umask);
+    cudaFree(s->tile_list);
+    cudaFree(s->d_counters);
+    cudaFree(s->d_count64);
+    cudaFree(s->scal);
+    delete s;
+}
+
+}  // namespace
+
+// The context caches the scene of the last host-pointer fill so that repeated calls on same-shaped inputs do not
+// re-allocate HBM.
+struct sa_ctx_cache {
+    sa_scene* scene = nullptr;
+};
+static sa_ctx_cache* cache_of(sa_ctx* ctx);
+
+struct sa_ctx_full : sa_ctx {
+    sa_ctx_cache cache;
+};
+static sa_ctx_cache* cache_of(sa_ctx* ctx) { return &static_cast<sa_ctx_full*>(ctx)->cache; }
+
+extern "C" {
+
+int sa_abi_version(void) { return SATFILL_ABI_VERSION; }
+
+int sa_create(sa_ctx** out, int device, void* stream)
+{
+    if (!out)
+        return SA_BAD_ARGUMENT;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || device < 0 || device >= count)
+        return SA_CUDA_ERROR;  // no CPU fallback: the library is unusable without a device
+    if (cudaSetDevice(device) != cudaSuccess)
+        return SA_CUDA_ERROR;
+    sa_ctx_full* ctx = new (std::nothrow) sa_ctx_full();
+    if (!ctx)
+        return SA_OUT_OF_MEMORY;
+    ctx->device = device;
+    if (stream) {
+        ctx->stream = (cudaStream_t)stream;
+    } else {
+        if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+            delete ctx;
+            return SA_CUDA_ERROR;
+        }
+        ctx->owns_stream = true;
+    }
+    cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+    ctx->pinned_bytes = 1 << 20;
+    if (cudaMallocHost(&ctx->pinned, ctx->pinned_bytes) != cudaSuccess) {
+        if (ctx->owns_stream)
+            cudaStreamDestroy(ctx->stream);
+        delete ctx;
+        return SA_OUT_OF_MEMORY;
+    }
+    for (auto& ev : ctx->ev)
+        cudaEventCreate(&ev);
+    *out = ctx;
+    return SA_OK;
+}
+
+void sa_destroy(sa_ctx* ctx)
+{
+    if (!ctx)
+        return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    scene_free(cache_of(ctx)->scene);
+    for (auto& ev : ctx->ev)
+        if (ev)
+            cudaEventDestroy(ev);
+    for (auto& ev : ctx->ev_pool)
+        cudaEventDestroy(ev);
+    if (ctx->pinned)
+        cudaFreeHost(ctx->pinned);
+    if (ctx->owns_stream)
+        cudaStreamDestroy(ctx->stream);
+    delete static_cast<sa_ctx_full*>(ctx);
+}
+
+const char* sa_last_error(const sa_ctx* ctx) { return ctx ? ctx->error.c_str() : "null context"; }
+
+int64_t sa_kernel_launches(const sa_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+void sa_default_options(sa_options* o, int problem)
+{
+    if (!o)
+        return;
+    std::memset(o, 0, sizeof(*o));
+    // Laplace: Eigen's default tolerance is machine epsilon (IterativeSolverBase.h:367-368); Poisson: 1e-6 (poisson.h:45)
+    o->tolerance = problem == SA_POISSON ? 1e-6 : DBL_EPSILON;
+    o->max_iterations = 0;
+    o->precond = SA_PRECOND_JACOBI;
+    o->check_every = 32;
+    o->mg_levels = 0;
+    o->mg_smooth = 2;
+}
+
+int sa_synchronize(sa_ctx* ctx)
+{
+    SA_TRY(check_ctx(ctx));
+    SA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SA_OK;
+}
+
+/* ---- integer path ------------------------------------------------------------------------------------------- */
+
+int sa_mask_scan(sa_ctx* ctx, const uint8_t* mask, int64_t rows, int64_t cols, int64_t row_stride, int64_t col_stride,
+    int64_t* out_pixels, int64_t capacity, int64_t* out_count, int64_t bbox[4])
+{
+    SA_TRY(check_ctx(ctx));
+    if (rows < 0 || cols < 0 || (rows * cols > 0 && !mask))
+        return fail(ctx, SA_BAD_ARGUMENT, "mask_scan: bad arguments");
+    uint8_t* d_mask = nullptr;
+    SA_TRY(upload_mask_row_major(ctx, mask, rows, cols, row_stride, col_stride, &d_mask));
+    int64_t* d_pixels = nullptr;
+    if (!out_pixels)
+        capacity = 0;
+    if (capacity > rows * cols)
+        capacity = rows * cols;
+    if (capacity > 0)
+        SA_CUDA(ctx, cudaMallocAsync(&d_pixels, (size_t)capacity * 2 * sizeof(int64_t), ctx->stream));
+    int64_t count = 0;
+    int st = device_numbering(ctx, d_mask, rows, cols, cols, nullptr, d_pixels, capacity, &count, bbox);
+    if (st == SA_OK && d_pixels) {
+        int64_t ncopy = count < capacity ? count : capacity;
+        if (ncopy > 0) {
+            SA_CUDA(ctx, cudaMemcpyAsync(out_pixels, d_pixels, (size_t)ncopy * 2 * sizeof(int64_t), cudaMemcpyDeviceToHost,
+                             ctx->stream));
+        }
+    }
+    if (d_pixels)
+        cudaFreeAsync(d_pixels, ctx->stream);
+    if (d_mask)
+        cudaFreeAsync(d_mask, ctx->stream);
+    SA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (out_count)
+        *out_count = count;
+    return st;
+}
+
+int sa_unknown_numbering(sa_ctx* ctx, const uint8_t* mask, int64_t rows, int64_t cols, int64_t row_stride,
+    int64_t col_stride, int32_t* numbering, int64_t* out_count)
+{
+    SA_TRY(check_ctx(ctx));
+    if (rows < 0 || cols < 0 || (rows * cols > 0 && (!mask || !numbering)))
+        return fail(ctx, SA_BAD_ARGUMENT, "unknown_numbering: bad arguments");
+    if (rows * cols > (int64_t)INT32_MAX)  // the reference stores the count in a 32-bit int (poisson.cpp:177)
+        return fail(ctx, SA_BAD_ARGUMENT, "unknown_numbering: rows * cols must fit 32 bits");
+    uint8_t* d_mask = nullptr;
+    SA_TRY(upload_mask_row_major(ctx, mask, rows, cols, row_stride, col_stride, &d_mask));
+    int32_t* d_num = nullptr;
+    int64_t count = 0;
+    int st = SA_OK;
+    if (rows * cols > 0) {
+        SA_CUDA(ctx, cudaMallocAsync(&d_num, (size_t)(rows * cols) * sizeof(int32_t), ctx->stream));
+        st = device_numbering(ctx, d_mask, rows, cols, cols, d_num, nullptr, 0, &count, nullptr);
+        if (st == SA_OK) {
+            SA_CUDA(ctx, cudaMemcpyAsync(numbering, d_num, (size_t)(rows * cols) * sizeof(int32_t), cudaMemcpyDeviceToHost,
+                             ctx->stream));
+        }
+        cudaFreeAsync(d_num, ctx->stream);
+        cudaFreeAsync(d_mask, ctx->stream);
+    }
+    SA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (out_count)
+        *out_count = count;
+    return st;
+}
+
+int sa_label_components(sa_ctx* ctx, const uint8_t* mask, int64_t rows, int64_t cols, int64_t row_stride,
+    int64_t col_stride, int32_t* labels, int32_t* out_num_labels)
+{
+    SA_TRY(check_ctx(ctx));
+    if (rows < 0 || cols < 0 || (rows * cols > 0 && (!mask || !labels)))
+        return fail(ctx, SA_BAD_ARGUMENT, "label_components: bad arguments");
+    if (out_num_labels)
+        *out_num_labels = 0;
+    if (rows * cols == 0)
+        return SA_OK;
+    if (rows * cols > (int64_t)INT32_MAX)
+        return fail(ctx, SA_BAD_ARGUMENT, "label_components: rows * cols must fit a 32-bit label table");
+    uint8_t* d_mask = nullptr;
+    SA_TRY(upload_mask_row_major(ctx, mask, rows, cols, row_stride, col_stride, &d_mask));
+    int32_t* d_lab = nullptr;
+    SA_CUDA(ctx, cudaMallocAsync(&d_lab, (size_t)(rows * cols) * sizeof(int32_t), ctx->stream));
+    int32_t K = 0;
+    int st = device_label_components(ctx, d_mask, rows, cols, cols, d_lab, &K);
+    if (st == SA_OK) {
+        SA_CUDA(ctx, cudaMemcpyAsync(labels, d_lab, (size_t)(rows * cols) * sizeof(int32_t), cudaMemcpyDeviceToHost,
+                         ctx->stream));
+    }
+    cudaFreeAsync(d_lab, ctx->stream);
+    cudaFreeAsync(d_mask, ctx->stream);
+    SA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (out_num_labels)
+        *out_num_labels = K;
+    return st;
+}
+
+/* ---- scenes --------------------------------------------------------------------------------------------------- */
+
+int sa_scene_create(sa_ctx* ctx, int problem, int64_t rows, int64_t cols, int nbands, sa_scene** out)
+{
+    SA_TRY(check_ctx(ctx));
+    if (!out || rows < 0 || cols < 0 || nbands < 1 || (problem != SA_LAPLACE && problem != SA_POISSON))
+        return fail(ctx, SA_BAD_ARGUMENT, "scene_create: bad arguments");
+    if ((rows + 64) * (cols + 64) > (int64_t)INT32_MAX * 2)
+        return fail(ctx, SA_BAD_ARGUMENT, "scene_create: scene too large for one device plane");
+    sa_scene* s = new (std::nothrow) sa_scene();
+    if (!s)
+        return fail(ctx, SA_OUT_OF_MEMORY, "scene_create: host allocation failed");
+    s->ctx = ctx;
+    s->problem = problem;
+    s->user_rows = rows;
+    s->user_cols = cols;
+    s->nbands = nbands;
+    *out = s;
+    return SA_OK;
+}
+
+void sa_scene_destroy(sa_scene* scene)
+{
+    if (scene && scene->ctx)
+        cudaStreamSynchronize(scene->ctx->stream);
+    scene_free(scene);
+}
+
+int sa_scene_set_mask(sa_scene* s, const uint8_t* src, int64_t row_stride, int64_t col_stride, int src_on_device)
+{
+    if (!s)
+        return SA_BAD_ARGUMENT;
+    SA_TRY(check_ctx(s->ctx));
+    SA_TRY(scene_orient(s, row_stride, col_stride));
+    SA_TRY(copy_in<uint8_t>(s, s->mask0(s->mask), src, row_stride, col_stride, src_on_device, 0, s->rows));
+    s->mask_set = true;
+    s->indexed = false;
+    return SA_OK;
+}
+
+int sa_scene_set_band(sa_scene* s, int band, const double* src, int64_t row_stride, int64_t col_stride,
+    int src_on_device)
+{
+    if (!s)
+        return SA_BAD_ARGUMENT;
+    SA_TRY(check_ctx(s->ctx));
+    if (band < 0 || band >= s->nbands)
+        return fail(s->ctx, SA_BAD_ARGUMENT, "scene_set_band: band out of range");
+    SA_TRY(scene_orient(s, row_stride, col_stride));
+    return copy_in<double>(s, s->plane0(s->u, band), src, row_stride, col_stride, src_on_device, 0, s->rows);
+}
+
+int sa_scene_set_guidance(sa_scene* s, int band, const double* src, int64_t row_stride, int64_t col_stride,
+    int src_on_device)
+{
+    if (!s)
+        return SA_BAD_ARGUMENT;
+    SA_TRY(check_ctx(s->ctx));
+    if (s->problem != SA_POISSON)
+        return fail(s->ctx, SA_BAD_ARGUMENT, "scene_set_guidance: not a Poisson scene");
+    if (band < 0 || band >= s->nbands)
+        return fail(s->ctx, SA_BAD_ARGUMENT, "scene_set_guidance: band out of range");
+    SA_TRY(scene_orient(s, row_stride, col_stride));
+    return copy_in<double>(s, s->plane0(s->g, band), src, row_stride, col_stride, src_on_device, 0, s->rows);
+}
+
+int sa_scene_solve(sa_scene* s, const sa_options* opts, sa_stats* stats)
+{
+    if (!s)
+        return SA_BAD_ARGUMENT;
+    SA_TRY(check_ctx(s->ctx));
+    if (!s->mask_set)
+        return fail(s->ctx, SA_BAD_ARGUMENT, "scene_solve: no mask set");
+    sa_options o;
+    if (opts)
+        o = *opts;
+    else
+        sa_default_options(&o, s->problem);
+    if (!(o.tolerance > 0.0))
+        o.tolerance = s->problem == SA_POISSON ? 1e-6 : DBL_EPSILON;
+    return solve_scene(s, o, stats);
+}
+
+int sa_scene_get_band(sa_scene* s, int band, double* dst, int64_t row_stride, int64_t col_stride, int dst_on_device)
+{
+    if (!s)
+        return SA_BAD_ARGUMENT;
+    SA_TRY(check_ctx(s->ctx));
+    if (!s->oriented || band < 0 || band >= s->nbands)
+        return fail(s->ctx, SA_BAD_ARGUMENT, "scene_get_band: band out of range or empty scene");
+    SA_TRY(scene_orient(s, row_stride, col_stride));
+    SA_TRY(copy_out<double>(s, s->plane0(s->u, band), dst, row_stride, col_stride, dst_on_device, 0, s->rows));
+    if (!dst_on_device)
+        SA_CUDA(s->ctx, cudaStreamSynchronize(s->ctx->stream));
+    return SA_OK;
+}
+
+int sa_scene_info(const sa_scene* s, int64_t* unknowns, int32_t* active_tiles, int32_t* total_tiles)
+{
+    if (!s)
+        return SA_BAD_ARGUMENT;
+    if (unknowns)
+        *unknowns = s->n_unknowns;
+    if (active_tiles)
+        *active_tiles = s->n_active_tiles;
+    if (total_tiles)
+        *total_tiles = s->tiles_x * s->tiles_y;
+    return SA_OK;
+}
+
+/* ---- float path, host pointers ---------------------------------------------------------------------------------- */
+
+static int host_fill(sa_ctx* ctx, int problem, double* const* images, const double* const* guidance, int nbands,
+    const uint8_t* mask, int64_t rows, int64_t cols, int64_t rs, int64_t cs, const sa_options* opts, sa_stats* stats)
+{
+    SA_TRY(check_ctx(ctx));
+    if (nbands < 1 || rows < 0 || cols < 0 || !images || (problem == SA_POISSON && !guidance))
+        return fail(ctx, SA_BAD_ARGUMENT, "fill: bad arguments");
+    if (rows * cols == 0) {
+        if (stats)
+            for (int b = 0; b < nbands; ++b) {
+                stats[b] = sa_stats {};
+                stats[b].status = SA_EMPTY_MASK;
+            }
+        return SA_EMPTY_MASK;
+    }
+    if (!mask)
+        return fail(ctx, SA_BAD_ARGUMENT, "fill: null mask");
+    Layout lay = classify(rows, cols, rs, cs);
+    if (lay == LAYOUT_BAD)
+        return fail(ctx, SA_BAD_ARGUMENT, "strides: one of row_stride / col_stride must be 1");
+    sa_ctx_cache* cache = cache_of(ctx);
+    sa_scene* s = cache->scene;
+    bool transposed = lay == LAYOUT_COL_MAJOR;
+    if (s && (s->problem != problem || s->user_rows != rows || s->user_cols != cols || s->nbands != nbands
+                 || s->transposed != transposed)) {
+        cudaStreamSynchronize(ctx->stream);
+        scene_free(s);
+        s = cache->scene = nullptr;
+    }
+    if (!s) {
+        SA_TRY(sa_scene_create(ctx, problem, rows, cols, nbands, &s));
+        int st = scene_alloc(s, transposed);
+        if (st != SA_OK) {
+            scene_free(s);
+            return st;
+        }
+        cache->scene = s;
+    }
+    // 1. mask -> unknown set and active tiles; only the band of rows that holds active tiles (plus one known row on
+    //    either side for the boundary values) has to cross PCIe.
+    SA_TRY(copy_in<uint8_t>(s, s->mask0(s->mask), mask, rs, cs, 0, 0, s->rows));
+    s->mask_set = true;
+    s->indexed = false;
+    SA_TRY(ensure_indexed(s));
+    sa_options o;
+    if (opts)
+        o = *opts;
+    else
+        sa_default_options(&o, problem);
+    if (!(o.tolerance > 0.0))
+        o.tolerance = problem == SA_POISSON ? 1e-6 : DBL_EPSILON;
+    if (s->n_unknowns == 0)
+        return solve_scene(s, o, stats);  // fills stats, returns SA_EMPTY_MASK
+    int32_t* h_cnt = (int32_t*)ctx->pinned;
+    SA_CUDA(ctx, cudaMemcpyAsync(h_cnt, s->d_counters, 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    SA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    int64_t row_lo = (int64_t)(h_cnt[1] / s->tiles_x) * TILE_H - 1;
+    int64_t row_hi = (int64_t)(h_cnt[2] / s->tiles_x + 1) * TILE_H + 1;
+    if (row_lo < 0)
+        row_lo = 0;
+    if (row_hi > s->rows)
+        row_hi = s->rows;
+    for (int b = 0; b < nbands; ++b) {
+        SA_TRY(copy_in<double>(s, s->plane0(s->u, b), images[b], rs, cs, 0, row_lo, row_hi));
+        if (problem == SA_POISSON)
+            SA_TRY(copy_in<double>(s, s->plane0(s->g, b), guidance[b], rs, cs, 0, row_lo, row_hi));
+    }
+    int st = solve_scene(s, o, stats);
+    // Laplace never looks at the solver status (laplace.cpp:113-119); Poisson writes nothing unless every band
+    // converged (poisson.cpp:263-269).
+    if (st == SA_OK || (problem == SA_LAPLACE && st == SA_NOT_CONVERGED)) {
+        for (int b = 0; b < nbands; ++b)
+            SA_TRY(copy_out<double>(s, s->plane0(s->u, b), images[b], rs, cs, 0, row_lo, row_hi));
+        SA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return st;
+}
+
+int sa_laplace_fill(sa_ctx* ctx, double* const* images, int nbands, const uint8_t* mask, int64_t rows, int64_t cols,
+    int64_t row_stride, int64_t col_stride, const sa_options* opts, sa_stats* stats)
+{
+    return host_fill(ctx, SA_LAPLACE, images, nullptr, nbands, mask, rows, cols, row_stride, col_stride, opts, stats);
+}
+
+int sa_poisson_blend(sa_ctx* ctx, double* const* inputs, const double* const* replacements, int nbands,
+    const uint8_t* mask, int64_t rows, int64_t cols, int64_t row_stride, int64_t col_stride, const sa_options* opts,
+    sa_stats* stats)
+{
+    return host_fill(ctx, SA_POISSON, inputs, replacements, nbands, mask, rows, cols, row_stride, col_stride, opts, stats);
+}
+
+}  // extern "C"

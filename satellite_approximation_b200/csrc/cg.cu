@@ -1,0 +1,472 @@
+// Matrix-free preconditioned conjugate gradient on the block-sparse masked grid.  Replaces the Eigen sparse assembly
+// and solve of the reference (laplace.cpp:58-114, poisson.cpp:179-270 -> Eigen ConjugateGradient.h:30-85 with
+// DiagonalPreconditioner, BasicPreconditioners.h:39-86).
+//
+// The system, for p in the unknown set U:
+//     d_p x_p - sum_{q in N4(p) & U} x_q = b_p,      d_p = number of in-image 4-neighbours of p (4 in the interior)
+//     b_p = [Poisson: sum_{q in N4(p)} (g_p - g_q)] + sum_{q in N4(p) \ U} f_q
+// x lives in the image plane itself (known cells keep f, unknown cells hold the iterate); r, p are planes that are
+// zero outside U.  One CG iteration is two kernels over the active tiles of all bands (DESIGN.md "CG kernels"):
+//     k_direction:  beta = rz_k / rz_{k-1};  p' = z + beta p  (ping-pong buffer; z = r/d for Jacobi);  pq = p'.Ap'
+//     k_update:     alpha = rz_k / pq;  x += alpha p';  r -= alpha A p'  (A p' recomputed from the staged tile);
+//                   rr = |r|^2,  rz = r.(r/d)
+// 65 B per unknown per iteration instead of the 89 B of the textbook five-pass formulation: A p is never stored.
+// All scalars stay on the device (BandScalars); the host only polls the `done` flags every check_every iterations.
+#include "common.cuh"
+
+namespace satfill {
+
+__device__ __forceinline__ double inv_diag(int64_t r, int64_t c, int64_t rows, int64_t cols)
+{
+    // in-image neighbour count: poisson.cpp:187-190 (valid_neighbours, utils.h:35-50); 4 for every Laplace unknown.
+    int d = (r > 0) + (r < rows - 1) + (c > 0) + (c < cols - 1);
+    // Eigen's DiagonalPreconditioner uses 1 for a zero diagonal (BasicPreconditioners.h:66-70)
+    return d == 4 ? 0.25 : (d == 3 ? (1.0 / 3.0) : (d == 2 ? 0.5 : 1.0));
+}
+__device__ __forceinline__ double diag_of(int64_t r, int64_t c, int64_t rows, int64_t cols)
+{
+    return (double)((r > 0) + (r < rows - 1) + (c > 0) + (c < cols - 1));
+}
+
+__device__ __forceinline__ double block_sum(double v, double* s_red /* 8 doubles */)
+{
+    for (int o = 16; o; o >>= 1)
+        v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();  // protect s_red reuse
+    if (threadIdx.x == 0)
+        s_red[threadIdx.y] = v;
+    __syncthreads();
+    double t = 0.0;
+    if (threadIdx.y == 0) {
+        t = threadIdx.x < CG_BLOCK_Y ? s_red[threadIdx.x] : 0.0;
+        for (int o = 4; o; o >>= 1)
+            t += __shfl_xor_sync(0xffffffffu, t, o);
+    }
+    return t;  // valid in thread (0, 0)
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Set-up: initial iterate, residual, right-hand-side norm.
+// ---------------------------------------------------------------------------------------------------------------
+
+// x0: Laplace solve() starts from zero (IterativeSolverBase.h:357-360); Poisson from the replacement image
+// (poisson.cpp:239, 257).
+template <bool POISSON>
+__global__ void __launch_bounds__(256) k_init_guess(Level lv, double* __restrict__ u, const double* __restrict__ g)
+{
+    int tile = lv.tile_list[blockIdx.x];
+    int64_t r0 = (int64_t)(tile / lv.tiles_x) * TILE_H, c0 = (int64_t)(tile % lv.tiles_x) * TILE_W;
+    int64_t boff = (int64_t)blockIdx.y * lv.plane;
+#pragma unroll
+    for (int j = 0; j < ROWS_PER_THREAD; ++j) {
+        int64_t idx = (r0 + threadIdx.y + j * CG_BLOCK_Y) * lv.pitch + c0 + threadIdx.x;
+        if (lv.umask[idx])
+            u[boff + idx] = POISSON ? g[boff + idx] : 0.0;
+    }
+}
+
+// r = b - A x0 and |b|^2, |r|^2, r.(r/d) in one pass over u (and g): laplace.cpp:71-94 / poisson.cpp:241-251 for b,
+// ConjugateGradient.h:38-61 for the rest.
+template <bool POISSON>
+__global__ void __launch_bounds__(256) k_residual(Level lv, const double* __restrict__ u, const double* __restrict__ g,
+    double* __restrict__ rvec, BandScalars* __restrict__ scal)
+{
+    __shared__ double s_red[CG_BLOCK_Y];
+    int tile = lv.tile_list[blockIdx.x];
+    int64_t r0 = (int64_t)(tile / lv.tiles_x) * TILE_H, c0 = (int64_t)(tile % lv.tiles_x) * TILE_W;
+    int64_t boff = (int64_t)blockIdx.y * lv.plane;
+    const double* ub = u + boff;
+    const double* gb = POISSON ? g + boff : nullptr;
+    double b2 = 0.0, r2 = 0.0, rz = 0.0;
+#pragma unroll
+    for (int j = 0; j < ROWS_PER_THREAD; ++j) {
+        int64_t r = r0 + threadIdx.y + j * CG_BLOCK_Y, c = c0 + threadIdx.x;
+        int64_t idx = r * lv.pitch + c;
+        double res = 0.0;
+        if (lv.umask[idx]) {
+            double d = diag_of(r, c, lv.rows, lv.cols);
+            double un = ub[idx - lv.pitch], us = ub[idx + lv.pitch], uw = ub[idx - 1], ue = ub[idx + 1];
+            double kn = lv.umask[idx - lv.pitch] ? 0.0 : un, ks = lv.umask[idx + lv.pitch] ? 0.0 : us;
+            double kw = lv.umask[idx - 1] ? 0.0 : uw, ke = lv.umask[idx + 1] ? 0.0 : ue;
+            double div = 0.0;
+            if (POISSON)  // sum over in-image neighbours of (g_p - g_q); g is zero outside the image
+                div = d * gb[idx] - (gb[idx - lv.pitch] + gb[idx + lv.pitch] + gb[idx - 1] + gb[idx + 1]);
+            double b = div + (kn + ks + kw + ke);
+            res = div + (un + us + uw + ue) - d * ub[idx];
+            b2 += b * b;
+            r2 += res * res;
+            rz += res * res * inv_diag(r, c, lv.rows, lv.cols);
+        }
+        rvec[boff + idx] = res;
+    }
+    double t;
+    t = block_sum(b2, s_red);
+    if (threadIdx.x == 0 && threadIdx.y == 0 && t != 0.0)
+        atomicAdd(&scal[blockIdx.y].bnorm2, t);
+    t = block_sum(r2, s_red);
+    if (threadIdx.x == 0 && threadIdx.y == 0 && t != 0.0)
+        atomicAdd(&scal[blockIdx.y].rr[0], t);
+    t = block_sum(rz, s_red);
+    if (threadIdx.x == 0 && threadIdx.y == 0 && t != 0.0)
+        atomicAdd(&scal[blockIdx.y].rz[0], t);
+}
+
+__global__ void k_finalize_setup(BandScalars* scal, int nbands, double tol)
+{
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nbands)
+        return;
+    BandScalars& s = scal[b];
+    if (s.bnorm2 == 0.0) {  // ConjugateGradient.h:43-49
+        s.zero_rhs = 1;
+        s.done = 1;
+        s.iters = 0;
+        s.rr_exit = 0.0;
+        return;
+    }
+    double thr = tol * tol * s.bnorm2;  // ConjugateGradient.h:50-51
+    s.thr = thr < DBL_MIN ? DBL_MIN : thr;
+    if (s.rr[0] < s.thr) {  // ConjugateGradient.h:52-57
+        s.done = 1;
+        s.iters = 0;
+        s.rr_exit = s.rr[0];
+    }
+}
+
+// Zero right-hand side: Eigen returns x = 0 whatever the guess was (ConjugateGradient.h:43-49).
+__global__ void __launch_bounds__(256) k_zero_unknowns(Level lv, double* __restrict__ u,
+    const BandScalars* __restrict__ scal)
+{
+    if (!scal[blockIdx.y].zero_rhs)
+        return;
+    int tile = lv.tile_list[blockIdx.x];
+    int64_t r0 = (int64_t)(tile / lv.tiles_x) * TILE_H, c0 = (int64_t)(tile % lv.tiles_x) * TILE_W;
+    int64_t boff = (int64_t)blockIdx.y * lv.plane;
+#pragma unroll
+    for (int j = 0; j < ROWS_PER_THREAD; ++j) {
+        int64_t idx = (r0 + threadIdx.y + j * CG_BLOCK_Y) * lv.pitch + c0 + threadIdx.x;
+        if (lv.umask[idx])
+            u[boff + idx] = 0.0;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// The two kernels of one CG iteration.
+// ---------------------------------------------------------------------------------------------------------------
+
+// Stage the 34 x 34 neighbourhood of a tile in shared memory.  `f(idx, r, c)` yields the value of the staged vector
+// at plane offset idx; it is evaluated for the 32 x 32 interior (coalesced 256 B rows) and the 4 x 32 halo cells.
+constexpr int SP = TILE_W + 3;  // padded row length of the staged tile (odd multiple keeps 8-byte banks spread)
+
+template <typename F>
+__device__ __forceinline__ void stage_tile(double (*sp)[SP], int64_t r0, int64_t c0, int64_t pitch, F f)
+{
+#pragma unroll
+    for (int j = 0; j < ROWS_PER_THREAD; ++j) {
+        int lr = threadIdx.y + j * CG_BLOCK_Y;
+        int64_t r = r0 + lr, c = c0 + threadIdx.x;
+        sp[lr + 1][threadIdx.x + 1] = f(r * pitch + c, r, c, true);
+    }
+    int t = threadIdx.y * CG_BLOCK_X + threadIdx.x;
+    if (t < 128) {
+        int e = t >> 5, i = t & 31;
+        int lr, lc;
+        if (e == 0) { lr = -1; lc = i; }
+        else if (e == 1) { lr = TILE_H; lc = i; }
+        else if (e == 2) { lr = i; lc = -1; }
+        else { lr = i; lc = TILE_W; }
+        int64_t r = r0 + lr, c = c0 + lc;
+        sp[lr + 1][lc + 1] = f(r * pitch + c, r, c, false);
+    }
+}
+
+// k_direction: p' = z + beta p, pq = p'.Ap'.   JACOBI: z = r / d computed on the fly (zin = r).  Otherwise zin = z.
+template <bool JACOBI>
+__global__ void __launch_bounds__(256) k_direction(Level lv, const double* __restrict__ zin,
+    const double* __restrict__ p_old, double* __restrict__ p_new, BandScalars* __restrict__ scal, int k)
+{
+    __shared__ double sp[TILE_H + 2][SP];
+    __shared__ double s_red[CG_BLOCK_Y];
+    BandScalars& sc = scal[blockIdx.y];
+    if (sc.done)
+        return;
+    int slot = k & 3;
+    bool lead = blockIdx.x == 0 && threadIdx.x == 0 && threadIdx.y == 0;
+    if (k > 0 && sc.rr[slot] < sc.thr) {  // ConjugateGradient.h:72-73 (strict <), tested one launch later
+        if (lead) {
+            sc.rr_exit = sc.rr[slot];
+            sc.iters = k - 1;
+            __threadfence();
+            sc.done = 1;
+        }
+        return;
+    }
+    double beta = k > 0 ? sc.rz[slot] / sc.rz[(k - 1) & 3] : 0.0;  // ConjugateGradient.h:77-79
+    if (lead) {  // recycle the slot two iterations ahead
+        int z2 = (k + 2) & 3;
+        sc.rz[z2] = 0.0;
+        sc.rr[z2] = 0.0;
+        sc.pq[z2] = 0.0;
+    }
+    int tile = lv.tile_list[blockIdx.x];
+    int64_t r0 = (int64_t)(tile / lv.tiles_x) * TILE_H, c0 = (int64_t)(tile % lv.tiles_x) * TILE_W;
+    int64_t boff = (int64_t)blockIdx.y * lv.plane;
+    const double* zb = zin + boff;
+    const double* pb = p_old + boff;
+    double* pn = p_new + boff;
+    int64_t rows = lv.rows, cols = lv.cols;
+    stage_tile(sp, r0, c0, lv.pitch, [&](int64_t idx, int64_t r, int64_t c, bool interior) {
+        double z = zb[idx];
+        if (JACOBI)
+            z *= inv_diag(r, c, rows, cols);
+        double v = z + beta * pb[idx];  // ConjugateGradient.h:80
+        if (interior)
+            pn[idx] = v;
+        return v;
+    });
+    __syncthreads();
+    double acc = 0.0;
+#pragma unroll
+    for (int j = 0; j < ROWS_PER_THREAD; ++j) {
+        int lr = threadIdx.y + j * CG_BLOCK_Y + 1, lc = threadIdx.x + 1;
+        double pc = sp[lr][lc];
+        double d = diag_of(r0 + lr - 1, c0 + lc - 1, rows, cols);
+        double q = d * pc - (sp[lr - 1][lc] + sp[lr + 1][lc] + sp[lr][lc - 1] + sp[lr][lc + 1]);
+        acc += pc * q;  // p is zero outside U, so no mask is needed here
+    }
+    double t = block_sum(acc, s_red);
+    if (threadIdx.x == 0 && threadIdx.y == 0 && t != 0.0)
+        atomicAdd(&sc.pq[slot], t);
+}
+
+// k_update: alpha = rz / pq; x += alpha p; r -= alpha A p; new |r|^2 and (JACOBI) r.(r/d) into slot k+1.
+template <bool JACOBI>
+__global__ void __launch_bounds__(256) k_update(Level lv, double* __restrict__ u, const double* __restrict__ p,
+    double* __restrict__ rvec, BandScalars* __restrict__ scal, int k)
+{
+    __shared__ double sp[TILE_H + 2][SP];
+    __shared__ double s_red[CG_BLOCK_Y];
+    BandScalars& sc = scal[blockIdx.y];
+    if (sc.done)
+        return;
+    int slot = k & 3, next = (k + 1) & 3;
+    double alpha = sc.rz[slot] / sc.pq[slot];  // ConjugateGradient.h:68
+    int tile = lv.tile_list[blockIdx.x];
+    int64_t r0 = (int64_t)(tile / lv.tiles_x) * TILE_H, c0 = (int64_t)(tile % lv.tiles_x) * TILE_W;
+    int64_t boff = (int64_t)blockIdx.y * lv.plane;
+    const double* pb = p + boff;
+    double* ub = u + boff;
+    double* rb = rvec + boff;
+    int64_t rows = lv.rows, cols = lv.cols;
+    stage_tile(sp, r0, c0, lv.pitch, [&](int64_t idx, int64_t, int64_t, bool) { return pb[idx]; });
+    __syncthreads();
+    double r2 = 0.0, rz = 0.0;
+#pragma unroll
+    for (int j = 0; j < ROWS_PER_THREAD; ++j) {
+        int lr = threadIdx.y + j * CG_BLOCK_Y + 1, lc = threadIdx.x + 1;
+        int64_t r = r0 + lr - 1, c = c0 + lc - 1;
+        int64_t idx = r * lv.pitch + c;
+        if (lv.umask[idx]) {
+            double pc = sp[lr][lc];
+            double d = diag_of(r, c, rows, cols);
+            double q = d * pc - (sp[lr - 1][lc] + sp[lr + 1][lc] + sp[lr][lc - 1] + sp[lr][lc + 1]);
+            ub[idx] += alpha * pc;                // ConjugateGradient.h:69
+            double rn = rb[idx] - alpha * q;      // ConjugateGradient.h:70
+            rb[idx] = rn;
+            r2 += rn * rn;
+            if (JACOBI)
+                rz += rn * rn * inv_diag(r, c, rows, cols);
+        }
+    }
+    double t = block_sum(r2, s_red);
+    if (threadIdx.x == 0 && threadIdx.y == 0 && t != 0.0)
+        atomicAdd(&sc.rr[next], t);
+    if (JACOBI) {
+        t = block_sum(rz, s_red);
+        if (threadIdx.x == 0 && threadIdx.y == 0 && t != 0.0)
+            atomicAdd(&sc.rz[next], t);
+    }
+}
+
+__global__ void k_final_check(BandScalars* scal, int nbands, int k_end)
+{
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nbands)
+        return;
+    BandScalars& s = scal[b];
+    if (s.done)
+        return;
+    double rr = s.rr[k_end & 3];
+    s.rr_exit = rr;
+    if (k_end > 0 && rr < s.thr) {
+        s.iters = k_end - 1;
+        s.done = 1;
+    } else {
+        s.iters = k_end;  // ran out of iterations (ConjugateGradient.h:65)
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Host driver
+// ---------------------------------------------------------------------------------------------------------------
+static Level fine_level(const sa_scene* s)
+{
+    Level lv {};
+    lv.rows = s->rows;
+    lv.cols = s->cols;
+    lv.pitch = s->pitch;
+    lv.plane = s->plane;
+    lv.tiles_x = s->tiles_x;
+    lv.tiles_y = s->tiles_y;
+    lv.n_tiles = s->n_active_tiles;
+    lv.umask = s->mask0(s->umask);
+    lv.tile_list = s->tile_list;
+    return lv;
+}
+
+int ensure_indexed(sa_scene* s)
+{
+    sa_ctx* ctx = s->ctx;
+    if (s->indexed)
+        return SA_OK;
+    SA_TRY(index_scene(s));
+    // work vectors must be zero outside the unknown set (and in tiles that are never visited)
+    size_t bytes = (size_t)s->plane * s->nbands * sizeof(double);
+    SA_CUDA(ctx, cudaMemsetAsync(s->r, 0, bytes, ctx->stream));
+    SA_CUDA(ctx, cudaMemsetAsync(s->p[0], 0, bytes, ctx->stream));
+    SA_CUDA(ctx, cudaMemsetAsync(s->p[1], 0, bytes, ctx->stream));
+    if (s->z)
+        SA_CUDA(ctx, cudaMemsetAsync(s->z, 0, bytes, ctx->stream));
+    s->hierarchy_built = false;
+    return SA_OK;
+}
+
+int solve_scene(sa_scene* s, const sa_options& o, sa_stats* stats)
+{
+    sa_ctx* ctx = s->ctx;
+    const int nb = s->nbands;
+    const bool poisson = s->problem == SA_POISSON;
+    const bool mg = o.precond == SA_PRECOND_MULTIGRID;
+    SA_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
+    SA_TRY(ensure_indexed(s));
+    const int64_t n = s->n_unknowns;
+    // reference defaults: Laplace 2N (IterativeSolverBase.h:251), Poisson n/2 (poisson.cpp:207)
+    int64_t max_it = o.max_iterations > 0 ? o.max_iterations : (poisson ? n / 2 : 2 * n);
+    if (max_it > (int64_t)1 << 30)
+        max_it = (int64_t)1 << 30;
+    if (stats) {
+        for (int b = 0; b < nb; ++b) {
+            stats[b] = sa_stats {};
+            stats[b].unknowns = n;
+            stats[b].max_iterations = max_it;
+            stats[b].tolerance = o.tolerance;
+            stats[b].active_tiles = s->n_active_tiles;
+        }
+    }
+    if (n == 0) {  // laplace.cpp:41-44: nothing to do
+        if (stats)
+            for (int b = 0; b < nb; ++b)
+                stats[b].status = SA_EMPTY_MASK;
+        return SA_EMPTY_MASK;
+    }
+    if (mg) {
+        if (!s->z) {
+            size_t bytes = (size_t)s->plane * nb * sizeof(double);
+            SA_CUDA(ctx, cudaMalloc(&s->z, bytes));
+            SA_CUDA(ctx, cudaMemsetAsync(s->z, 0, bytes, ctx->stream));
+        }
+        if (!s->hierarchy_built)
+            SA_TRY(build_hierarchy(s, o));
+    }
+
+    Level lv = fine_level(s);
+    dim3 grid((unsigned)lv.n_tiles, (unsigned)nb), block(CG_BLOCK_X, CG_BLOCK_Y);
+    double* u0 = s->plane0(s->u, 0);
+    double* g0 = poisson ? s->plane0(s->g, 0) : nullptr;
+    double* r0 = s->plane0(s->r, 0);
+    double* pbuf[2] = { s->plane0(s->p[0], 0), s->plane0(s->p[1], 0) };
+    double* z0 = s->z ? s->plane0(s->z, 0) : nullptr;
+
+    SA_CUDA(ctx, cudaMemsetAsync(s->scal, 0, sizeof(BandScalars) * nb, ctx->stream));
+    if (poisson) {
+        SA_LAUNCH(ctx, k_init_guess<true>, grid, block, 0, lv, u0, g0);
+        SA_LAUNCH(ctx, k_residual<true>, grid, block, 0, lv, u0, g0, r0, s->scal);
+    } else {
+        SA_LAUNCH(ctx, k_init_guess<false>, grid, block, 0, lv, u0, g0);
+        SA_LAUNCH(ctx, k_residual<false>, grid, block, 0, lv, u0, g0, r0, s->scal);
+    }
+    SA_LAUNCH(ctx, k_finalize_setup, (nb + 63) / 64, 64, 0, s->scal, nb, o.tolerance);
+    SA_CUDA(ctx, cudaGetLastError());
+    SA_CUDA(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
+
+    KernelTimer kt;
+    kt.ctx = ctx;
+    kt.on = o.profile != 0;
+    BandScalars* h_scal = (BandScalars*)ctx->pinned;
+    const int check = o.check_every > 0 ? o.check_every : 32;
+    int64_t k = 0;
+    bool all_done = false;
+    while (k < max_it && !all_done) {
+        int64_t k_stop = k + check < max_it ? k + check : max_it;
+        for (; k < k_stop; ++k) {
+            int ki = (int)(k & 0x3fffffff);  // only k == 0 and k & 3 matter to the kernels; iters is re-based below
+            const double* pin = pbuf[k & 1];
+            double* pout = pbuf[(k + 1) & 1];
+            if (mg) {
+                SA_TRY(apply_vcycle(s, o, kt));  // z = M^-1 r, rz[slot] accumulated by its last kernel
+                kt.begin(KC_DIRECTION);
+                SA_LAUNCH(ctx, k_direction<false>, grid, block, 0, lv, z0, pin, pout, s->scal, ki);
+                kt.end();
+                kt.begin(KC_UPDATE);
+                SA_LAUNCH(ctx, k_update<false>, grid, block, 0, lv, u0, pout, r0, s->scal, ki);
+                kt.end();
+            } else {
+                kt.begin(KC_DIRECTION);
+                SA_LAUNCH(ctx, k_direction<true>, grid, block, 0, lv, r0, pin, pout, s->scal, ki);
+                kt.end();
+                kt.begin(KC_UPDATE);
+                SA_LAUNCH(ctx, k_update<true>, grid, block, 0, lv, u0, pout, r0, s->scal, ki);
+                kt.end();
+            }
+        }
+        SA_CUDA(ctx, cudaGetLastError());
+        SA_CUDA(ctx, cudaMemcpyAsync(h_scal, s->scal, sizeof(BandScalars) * nb, cudaMemcpyDeviceToHost, ctx->stream));
+        SA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        kt.flush();
+        all_done = true;
+        for (int b = 0; b < nb; ++b)
+            all_done = all_done && h_scal[b].done;
+    }
+    SA_LAUNCH(ctx, k_final_check, (nb + 63) / 64, 64, 0, s->scal, nb, (int)(k & 0x3fffffff));
+    SA_LAUNCH(ctx, k_zero_unknowns, grid, block, 0, lv, u0, s->scal);
+    SA_CUDA(ctx, cudaGetLastError());
+    SA_CUDA(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
+    SA_CUDA(ctx, cudaMemcpyAsync(h_scal, s->scal, sizeof(BandScalars) * nb, cudaMemcpyDeviceToHost, ctx->stream));
+    SA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    float setup_ms = 0.f, solve_ms = 0.f;
+    cudaEventElapsedTime(&setup_ms, ctx->ev[0], ctx->ev[1]);
+    cudaEventElapsedTime(&solve_ms, ctx->ev[1], ctx->ev[2]);
+    int status = SA_OK;
+    for (int b = 0; b < nb; ++b) {
+        const BandScalars& sc = h_scal[b];
+        int st = sc.done ? SA_OK : SA_NOT_CONVERGED;
+        if (stats) {
+            stats[b].iterations = sc.iters;
+            stats[b].error = sc.bnorm2 > 0.0 ? sqrt(sc.rr_exit / sc.bnorm2) : 0.0;
+            stats[b].solve_ms = solve_ms;
+            stats[b].setup_ms = setup_ms;
+            stats[b].status = st;
+            for (int c = 0; c < KC_COUNT; ++c) {
+                stats[b].kernel_ms[c] = kt.ms[c];
+                stats[b].kernel_launches[c] = kt.n[c];
+            }
+        }
+        if (st != SA_OK)
+            status = st;
+    }
+    if (status == SA_NOT_CONVERGED)
+        fail(ctx, status, "conjugate gradient reached max_iterations before the tolerance");
+    return status;
+}
+
+}  // namespace satfill

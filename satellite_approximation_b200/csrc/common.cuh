@@ -1,0 +1,233 @@
+// Shared declarations of libsatfill.so (sm_100a only).  See include/satfill.h for the C-ABI and DESIGN.md for the
+// layout.  Every image-shaped quantity of a scene is a row-major "plane": (rows_p + 2) x pitch elements per band,
+// rows_p = rows rounded up to the 32-row tile, pitch = (cols + 1) rounded up to the 32-column tile, so that there is
+// at least one zero column after the last image column, plus one zero guard row above and below.  Pointers address
+// element (0, 0); the guards sit at negative / past-the-end offsets.  With the solver's convention that every work
+// vector is ZERO at cells that are not unknowns, the 5-point operator needs no bounds checks and no neighbour-mask
+// look-ups: a neighbour that is known, outside the image or in the padding simply contributes 0.
+// Only the tiles listed in `tile_list` (tiles holding at least one unknown) are ever touched by solver kernels.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cfloat>
+#include <climits>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/satfill.h"
+
+namespace satfill {
+
+constexpr int TILE_W = 32;
+constexpr int TILE_H = 32;
+constexpr int CG_BLOCK_X = 32;
+constexpr int CG_BLOCK_Y = 8;
+constexpr int ROWS_PER_THREAD = TILE_H / CG_BLOCK_Y;
+constexpr int MAX_LEVELS = 12;
+
+// Per-band CG scalars, device resident.  Slot s = iteration & 3 (a ring of four so that the slot two iterations
+// ahead can be zeroed while the current and previous ones are still being read; DESIGN.md "Reductions").
+struct BandScalars {
+    double rz[4];   // r.z entering iteration k
+    double rr[4];   // |r|^2 entering iteration k
+    double pq[4];   // p.Ap of iteration k
+    double bnorm2;  // |b_U|^2
+    double thr;     // max(tol^2 |b|^2, DBL_MIN)      (ConjugateGradient.h:50-51)
+    double rr_exit; // |r|^2 when the band stopped
+    int done;       // sticky: band has met thr (or had a zero right-hand side)
+    int iters;      // Eigen-style iteration count at exit (ConjugateGradient.h:65-82)
+    int zero_rhs;   // ConjugateGradient.h:43-49: x is set to zero
+    int pad;
+};
+
+// One grid level of a scene (level 0 = the image; levels >= 1 = multigrid coarse grids).  Passed to kernels by value.
+struct Level {
+    int64_t rows, cols;   // logical extent
+    int64_t pitch;        // elements per plane row
+    int64_t plane;        // elements per band plane including the two guard rows
+    int tiles_x, tiles_y;
+    int n_tiles;          // active tiles
+    const uint8_t* umask; // 1 = unknown of the linear system; addressed like a plane (pitch bytes per row)
+    const int32_t* tile_list;
+};
+
+}  // namespace satfill
+
+struct sa_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool owns_stream = false;
+    int64_t launches = 0;
+    std::string error;
+    int sm_count = 148;
+    // pinned host scratch for polling convergence flags / small read-backs
+    void* pinned = nullptr;
+    size_t pinned_bytes = 0;
+    cudaEvent_t ev[4] = { nullptr, nullptr, nullptr, nullptr };
+    std::vector<cudaEvent_t> ev_pool;  // per-kernel timing (sa_options.profile)
+};
+
+struct sa_level_store {
+    satfill::Level lv {};
+    uint8_t* umask_alloc = nullptr;    // base of the allocation (guard row included)
+    int32_t* tile_list = nullptr;
+    double* x = nullptr;               // coarse levels: correction; nbands planes (allocation base)
+    double* b = nullptr;               // coarse levels: restricted residual
+    double* t = nullptr;               // scratch (second smoothing buffer)
+    int64_t n_unknowns = 0;
+};
+
+struct sa_scene {
+    sa_ctx* ctx = nullptr;
+    int problem = SA_LAPLACE;
+    int64_t user_rows = 0, user_cols = 0;  // as given to sa_scene_create
+    bool transposed = false;               // the resident layout is the transpose of the user's (row, col) grid
+    bool oriented = false;
+    int64_t rows = 0, cols = 0;            // resident extents (fast axis = cols)
+    int nbands = 0;
+    int64_t pitch = 0;
+    int64_t rows_p = 0;
+    int64_t plane = 0;                     // (rows_p + 2) * pitch
+    int tiles_x = 0, tiles_y = 0;
+    // allocation bases (nbands planes each); the *0 accessors below skip the first guard row
+    double* u = nullptr;   // image; unknown pixels hold the iterate x
+    double* g = nullptr;   // guidance (SA_POISSON only)
+    double* r = nullptr;
+    double* p[2] = { nullptr, nullptr };
+    double* z = nullptr;   // multigrid only: preconditioned residual
+    uint8_t* mask = nullptr;   // normalised 0/1 invalid mask (allocation base)
+    uint8_t* umask = nullptr;  // unknown set (allocation base)
+    int32_t* tile_list = nullptr;
+    int32_t* d_counters = nullptr;
+    unsigned long long* d_count64 = nullptr;
+    satfill::BandScalars* scal = nullptr;
+    int n_active_tiles = 0;
+    int64_t n_unknowns = 0;
+    bool mask_set = false;
+    bool indexed = false;
+    std::vector<sa_level_store> coarse;  // multigrid hierarchy below level 0
+    bool hierarchy_built = false;
+
+    double* plane0(double* base, int band) const { return base + (int64_t)band * plane + pitch; }
+    uint8_t* mask0(uint8_t* base) const { return base + pitch; }
+};
+
+namespace satfill {
+
+inline int fail(sa_ctx* ctx, int status, const std::string& msg)
+{
+    if (ctx)
+        ctx->error = msg;
+    return status;
+}
+
+#define SA_CUDA(ctx, expr)                                                                                       \
+    do {                                                                                                         \
+        cudaError_t e__ = (expr);                                                                                \
+        if (e__ != cudaSuccess) {                                                                                \
+            return satfill::fail((ctx), e__ == cudaErrorMemoryAllocation ? SA_OUT_OF_MEMORY : SA_CUDA_ERROR,     \
+                std::string(#expr) + ": " + cudaGetErrorString(e__));                                            \
+        }                                                                                                        \
+    } while (0)
+
+#define SA_TRY(expr)             \
+    do {                         \
+        int st__ = (expr);       \
+        if (st__ != SA_OK)       \
+            return st__;         \
+    } while (0)
+
+// Every kernel of the library is launched through this macro so that sa_kernel_launches() is exact.
+#define SA_LAUNCH(ctx, kernel, grid, block, smem, ...)                     \
+    do {                                                                   \
+        kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);   \
+        (ctx)->launches += 1;                                              \
+    } while (0)
+
+inline int64_t round_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
+
+// Kernel classes reported in sa_stats.kernel_ms / kernel_launches when sa_options.profile is set.
+enum KernelClass { KC_DIRECTION = 0, KC_UPDATE = 1, KC_SMOOTH = 2, KC_TRANSFER = 3, KC_COUNT = 4 };
+
+// Brackets individual launches with CUDA events on the launching stream; the pairs are resolved after the next
+// stream synchronisation (flush).  Off unless profiling was requested: the events cost ~1 us of launch gap each.
+struct KernelTimer {
+    sa_ctx* ctx = nullptr;
+    bool on = false;
+    size_t used = 0;
+    struct Pending { int cls; size_t e0; };
+    std::vector<Pending> pending;
+    double ms[KC_COUNT] = { 0, 0, 0, 0 };
+    int64_t n[KC_COUNT] = { 0, 0, 0, 0 };
+
+    cudaEvent_t take()
+    {
+        if (used == ctx->ev_pool.size()) {
+            cudaEvent_t e;
+            cudaEventCreate(&e);
+            ctx->ev_pool.push_back(e);
+        }
+        return ctx->ev_pool[used++];
+    }
+    void begin(int cls)
+    {
+        if (!on)
+            return;
+        pending.push_back({ cls, used });
+        cudaEventRecord(take(), ctx->stream);
+    }
+    void end()
+    {
+        if (!on)
+            return;
+        cudaEventRecord(take(), ctx->stream);
+    }
+    void flush()  // call after a stream synchronisation
+    {
+        for (const Pending& p : pending) {
+            float t = 0.f;
+            if (cudaEventElapsedTime(&t, ctx->ev_pool[p.e0], ctx->ev_pool[p.e0 + 1]) == cudaSuccess) {
+                ms[p.cls] += t;
+                n[p.cls] += 1;
+            }
+        }
+        pending.clear();
+        used = 0;
+    }
+};
+
+// ---- mask_index.cu ---------------------------------------------------------------------------------------------
+int transpose_u8(sa_ctx* ctx, const uint8_t* src, int64_t src_rows, int64_t src_cols, int64_t src_pitch, uint8_t* dst,
+    int64_t dst_pitch);
+int transpose_i32(sa_ctx* ctx, const int32_t* src, int64_t src_rows, int64_t src_cols, int64_t src_pitch, int32_t* dst,
+    int64_t dst_pitch);
+// normalise to 0/1, build umask + active tile list + unknown count for a scene
+int index_scene(sa_scene* s);
+// raster-order numbering / pixel list / bbox of a device mask (pitch bytes per row, non-zero = invalid)
+int device_numbering(sa_ctx* ctx, const uint8_t* mask, int64_t rows, int64_t cols, int64_t pitch, int32_t* numbering,
+    int64_t* out_pixels, int64_t capacity, int64_t* out_count, int64_t bbox[4]);
+// flags[n_tiles] -> raster-ordered list of the flagged tiles; d_n_active (device, 4 ints) receives
+// {count, first tile, last tile}
+int compact_tile_flags(sa_ctx* ctx, const int32_t* flags, int n_tiles, int32_t* tile_list, int32_t* d_n_active);
+// exclusive scan helper shared with ccl.cu: in place over `n` 64-bit counters, total written to *total
+int device_scan_u64(sa_ctx* ctx, unsigned long long* data, int64_t n, unsigned long long* total);
+
+// ---- ccl.cu ----------------------------------------------------------------------------------------------------
+int device_label_components(sa_ctx* ctx, const uint8_t* mask, int64_t rows, int64_t cols, int64_t pitch,
+    int32_t* labels /* dense rows x cols, device */, int32_t* out_num_labels);
+
+// ---- cg.cu -----------------------------------------------------------------------------------------------------
+// index the mask if it changed and clear the work vectors (they must be zero outside the unknown set)
+int ensure_indexed(sa_scene* s);
+int solve_scene(sa_scene* s, const sa_options& o, sa_stats* stats);
+
+// ---- mg.cu -----------------------------------------------------------------------------------------------------
+int build_hierarchy(sa_scene* s, const sa_options& o);
+void free_hierarchy(sa_scene* s);
+// z = M^{-1} r for every band that is not done (one symmetric V-cycle)
+int apply_vcycle(sa_scene* s, const sa_options& o, KernelTimer& kt);
+
+}  // namespace satfill

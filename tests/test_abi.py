@@ -1,0 +1,74 @@
+"""CPU: the C-ABI library loads and exports exactly what include/satfill.h declares (no compute calls)."""
+from __future__ import annotations
+
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "satfill.h")
+
+
+def header_symbols() -> list[str]:
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(sa_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_matches_binding_list():
+    from satellite_approximation_b200 import _capi
+
+    assert header_symbols() == sorted(_capi.EXPORTS)
+
+
+def test_library_exports_every_declared_symbol():
+    from satellite_approximation_b200 import _capi
+
+    if not os.path.exists(_capi.LIB_PATH):
+        import __graft_entry__ as g
+
+        g.build()
+    lib = ctypes.CDLL(_capi.LIB_PATH)
+    for name in header_symbols():
+        assert hasattr(lib, name), f"{name} declared in include/satfill.h but not exported"
+    out = subprocess.run(["nm", "-D", "--defined-only", _capi.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    exported = {line.split()[-1] for line in out.splitlines() if " T " in line}
+    assert set(header_symbols()) <= exported
+    assert lib.sa_abi_version() == 1
+
+
+def test_struct_layouts_match_header():
+    from satellite_approximation_b200 import _capi
+
+    assert ctypes.sizeof(_capi.Options) == 8 + 8 + 4 * 4 + 16
+    assert ctypes.sizeof(_capi.Stats) == 8 * 3 + 8 * 4 + 4 * 2 + 8 * 4 + 8 * 4
+    lib = _capi.load()
+    o = _capi.Options()
+    lib.sa_default_options(ctypes.byref(o), _capi.SA_POISSON)
+    assert o.tolerance == 1e-6 and o.max_iterations == 0 and o.precond == _capi.SA_PRECOND_JACOBI
+    lib.sa_default_options(ctypes.byref(o), _capi.SA_LAPLACE)
+    assert o.tolerance == 2.220446049250313e-16  # Eigen default (IterativeSolverBase.h:367-368)
+
+
+def test_no_device_fails_loudly():
+    """Without a GPU the product must refuse to run rather than fall back to anything on the CPU."""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    import satellite_approximation_b200 as sab
+
+    with pytest.raises(sab.SatfillError):
+        sab.Context(0)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "satellite_approximation_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                text = open(os.path.join(dirpath, fn)).read()
+                assert "import oracle" not in text and "liboracle" not in text and "libref_eigen" not in text, fn

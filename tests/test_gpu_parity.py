@@ -1,0 +1,264 @@
+"""GPU: parity of the CUDA path (through the C-ABI) against the oracle, the reference-generated golden vectors and
+size-independent properties.  Integer outputs must be bit-exact; filled pixels must be within 1e-4 relative max-abs of
+the CONVERGED reference solve (BASELINE.json north_star), measured as max|x - x_ref| / max|x_ref| over the unknowns."""
+from __future__ import annotations
+
+import numpy as np
+import pytest
+from conftest import rel_max_abs
+
+import satellite_approximation_b200 as sab
+from satellite_approximation_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+PARITY_TOL = 1e-4  # BASELINE.json: "filled pixels within 1e-4 relative max-abs difference"
+
+
+# ---- integer path: bit-exact ---------------------------------------------------------------------------------------
+def _masks():
+    rng = np.random.default_rng(7)
+    out = [
+        np.zeros((10, 10), bool),
+        np.ones((7, 9), bool),
+        np.zeros((1, 1), bool),
+        np.ones((1, 1), bool),
+        np.ones((1, 70), bool),
+        np.ones((70, 1), bool),
+        rng.random((33, 65)) < 0.5,
+        rng.random((257, 130)) < 0.3,
+        rng.random((64, 64)) < 0.6,  # near the 4-connectivity percolation threshold: long winding components
+        synth.blob_mask(300, 413, cover=0.35, sigma=6.0, seed=3, clear_border=False),
+    ]
+    spiral = np.zeros((41, 41), bool)  # a single snake: worst case for label propagation
+    for i in range(0, 41, 2):
+        spiral[i, :] = True
+        spiral[min(i + 1, 40), 40 if (i // 2) % 2 == 0 else 0] = True
+    out.append(spiral)
+    return out
+
+
+@pytest.mark.parametrize("order", ["C", "F"])
+def test_integer_path_bit_exact(ctx, port, order):
+    for m in _masks():
+        mm = np.asfortranarray(m) if order == "F" else np.ascontiguousarray(m)
+        px, bbox = ctx.mask_scan(mm)
+        wpx, wbbox = port.mask_scan(mm)
+        assert np.array_equal(px, wpx) and np.array_equal(bbox, wbbox), m.shape
+        num, n = ctx.unknown_numbering(mm)
+        wnum, wn = port.unknown_numbering(mm)
+        assert n == wn and np.array_equal(num, wnum), m.shape
+        lab, k = ctx.label_components(mm)
+        wlab, wk = port.label_components(mm)
+        assert k == wk and np.array_equal(lab, wlab), m.shape
+
+
+def test_connected_components_reference_kat(ctx):
+    """tests/approximation.h:55-75."""
+    m = np.zeros((10, 10), bool)
+    cc = sab.find_connected_components(m)
+    assert not cc.matrix.any() and cc.region_map == {}
+    m[1:3, 1:3] = True
+    m[5:9, 5:7] = True
+    cc = sab.find_connected_components(m)
+    assert len(cc.region_map) == 2 and len(cc.region_map[1]) == 4 and len(cc.region_map[2]) == 8
+
+
+def test_integer_path_c1_mask(ctx, port, c1_scene):
+    m = np.asfortranarray(c1_scene["full_mask"])  # the layout the reference's MatX<bool> has
+    px, bbox = ctx.mask_scan(m)
+    wpx, wbbox = port.mask_scan(m)
+    assert len(px) == 633573 and np.array_equal(px, wpx) and np.array_equal(bbox, wbbox)
+    num, n = ctx.unknown_numbering(m)
+    wnum, _ = port.unknown_numbering(m)
+    assert n == 633573 and np.array_equal(num, wnum)
+    lab, k = ctx.label_components(m)
+    wlab, wk = port.label_components(m)
+    assert k == wk == 7 and np.array_equal(lab, wlab)  # 7 components
+
+
+def test_integer_path_large_properties(ctx):
+    """Full-tile size (10980^2): too big for the oracle in a test; checked through properties of the contract."""
+    from scipy.ndimage import label
+
+    rows = cols = 4096
+    m = synth.blob_mask(rows, cols, cover=0.3, sigma=12.0, seed=11)
+    num, n = ctx.unknown_numbering(m)
+    assert n == int(m.sum())
+    assert np.array_equal(num[m], np.arange(n, dtype=np.int32))  # raster order
+    assert (num[~m] == -1).all()
+    lab, k = ctx.label_components(m)
+    want, wk = label(m)
+    assert k == wk and np.array_equal(lab, want)
+
+
+# ---- float path -------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("i", [0, 1, 2])
+@pytest.mark.parametrize("order", ["C", "F"])
+def test_laplace_vs_golden(ctx, small_cases, i, order):
+    img, mask, want = small_cases[f"lap{i}_img"], small_cases[f"lap{i}_mask"], small_cases[f"lap{i}_out"]
+    work = np.array(img, order=order, copy=True)
+    st = ctx.laplace_fill([work], np.array(mask, order=order), tolerance=1e-12)
+    assert st[0]["status"] == sab.SA_OK
+    assert rel_max_abs(work, want, mask) < 1e-8
+    assert np.array_equal(work[~mask], img[~mask])  # known pixels bit-identical (laplace.cpp:117-119)
+
+
+@pytest.mark.parametrize("i", [0, 1])
+def test_poisson_vs_golden(ctx, small_cases, i):
+    f, g, mask, want = (small_cases[f"poi{i}_{k}"] for k in ("f", "g", "mask", "out"))
+    out = sab.blend_images_poisson(list(f), list(g), mask, tolerance=1e-13, max_iterations=100000)
+    for b in range(len(f)):
+        assert out[b].flags.f_contiguous
+        assert rel_max_abs(out[b], want[b], mask) < 1e-8
+        assert np.array_equal(out[b][~mask], f[b][~mask])
+
+
+def test_c1_crop_vs_reference_eigen(ctx, c1_scene):
+    """Real Sentinel-2 data (B04/B08 crop of test_data/2019-05-22), converged Eigen solves as golden."""
+    mask = c1_scene["crop_mask"]
+    img = c1_scene["crop_b04"].astype(np.float64)
+    sab.set_solver_defaults(laplace_tolerance=1e-9)
+    try:
+        out = sab.filling_missing_portions_smooth_boundaries(np.asfortranarray(img), np.asfortranarray(mask))
+    finally:
+        sab.set_solver_defaults(laplace_tolerance=None)
+    want = c1_scene["laplace_unknowns"]
+    assert np.max(np.abs(out[mask] - want)) / np.max(np.abs(want)) < PARITY_TOL
+    assert np.array_equal(out[~mask], img[~mask])
+    f = [c1_scene["crop_b04"].astype(np.float64), c1_scene["crop_b08"].astype(np.float64)]
+    g = [synth.second_date(f[1], seed=0), synth.second_date(f[0], seed=1)]
+    outs = sab.blend_images_poisson(f, g, mask, tolerance=1e-9, max_iterations=10**6)
+    for b in range(2):
+        wantp = c1_scene["poisson_unknowns"][b]
+        assert np.max(np.abs(outs[b][mask] - wantp)) / np.max(np.abs(wantp)) < PARITY_TOL
+
+
+def test_reference_default_tolerances(ctx, port):
+    """Laplace at the reference's defaults (epsilon, 2N iterations) and Poisson at 1e-6 / n/2 (poisson.h:45-46)."""
+    img = synth.smooth_band(70, 90, seed=3)
+    mask = synth.blob_mask(70, 90, cover=0.4, sigma=4.0, seed=4)
+    want, _ = port.laplace_fill(img, mask, mode=0)
+    got = sab.filling_missing_portions_smooth_boundaries(img, mask)
+    assert got.flags.f_contiguous and rel_max_abs(got, want, mask) < 1e-9
+    g = synth.second_date(img, seed=5)
+    wantp, wst = port.poisson_blend([img], [g], mask, tol=1e-6)
+    gotp = sab.blend_images_poisson([img], [g], mask)
+    st = sab.last_perf_info()[0]
+    assert st["status"] == sab.SA_OK and st["error"] <= 1e-6
+    # same algorithm, same stop rule: the iteration count matches Eigen's to within reduction-order rounding
+    assert abs(st["iterations"] - wst[0].iterations) <= 2
+    assert rel_max_abs(gotp[0], wantp[0], mask) < 1e-5
+
+
+def test_laplace_border_semantics(ctx, port):
+    """Masks touching the image border: border pixels are Dirichlet data and come back unchanged;
+    the interior solves the as-assembled system exactly = the oracle's reduced mode."""
+    img = synth.smooth_band(60, 75, seed=8)
+    mask = synth.blob_mask(60, 75, cover=0.45, sigma=5.0, seed=9, clear_border=False)
+    assert mask[0].any() or mask[-1].any() or mask[:, 0].any() or mask[:, -1].any()
+    want, _ = port.laplace_fill(img, mask, mode=1, tol=1e-13)
+    work = img.copy()
+    ctx.laplace_fill([work], mask, tolerance=1e-12)
+    assert rel_max_abs(work, want, mask) < 1e-8
+    ring = np.zeros_like(mask)
+    ring[0, :] = ring[-1, :] = ring[:, 0] = ring[:, -1] = True
+    assert np.array_equal(work[ring], img[ring])
+
+
+def test_empty_mask_is_a_no_op(ctx):
+    img = synth.smooth_band(20, 20, seed=1)
+    work = img.copy()
+    st = ctx.laplace_fill([work], np.zeros((20, 20), bool))
+    assert st[0]["status"] == sab.SA_EMPTY_MASK and np.array_equal(work, img)  # laplace.cpp:41-44
+    out = sab.blend_images_poisson([img], [img + 1], np.zeros((20, 20), bool))
+    assert np.array_equal(out[0], img)
+
+
+def test_poisson_not_converged_returns_inputs(ctx):
+    f = synth.smooth_band(64, 64, seed=2)
+    g = synth.second_date(f, seed=1)
+    mask = synth.blob_mask(64, 64, cover=0.5, sigma=6.0, seed=4)
+    out = sab.blend_images_poisson([f], [g], mask, tolerance=1e-12, max_iterations=3)
+    assert sab.last_perf_info()[0]["status"] == sab.SA_NOT_CONVERGED
+    assert np.array_equal(out[0], f)  # poisson.cpp:263-269
+
+
+def test_poisson_zero_rhs_gives_zero(ctx):
+    """ConjugateGradient.h:43-49: b == 0 -> x = 0 whatever the guess."""
+    f = np.zeros((20, 24))
+    g = np.full((20, 24), 5.0)  # constant guidance: zero divergence; known neighbours are 0
+    mask = np.zeros((20, 24), bool)
+    mask[5:10, 6:12] = True
+    out = sab.blend_images_poisson([f], [g], mask)
+    assert (out[0][mask] == 0).all()
+
+
+@pytest.mark.parametrize("kind", [0, 1, 2])
+def test_harmonic_fixed_point_full_c1_mask(ctx, c1_scene, kind):
+    """Config-1 size without an oracle run: a discrete-harmonic image is a fixed point of the Laplace fill, so the
+    fill of the real 633k-pixel mask must reproduce it (size-independent property)."""
+    mask = c1_scene["full_mask"].copy()
+    mask[0, :] = mask[-1, :] = False
+    mask[:, 0] = mask[:, -1] = False
+    f = synth.harmonic_field(*mask.shape, kind)
+    work = f.copy()
+    work[mask] = -12345.0
+    st = ctx.laplace_fill([work], mask, tolerance=1e-10)
+    assert st[0]["status"] == sab.SA_OK and st[0]["unknowns"] == 633332
+    assert rel_max_abs(work, f, mask) < PARITY_TOL
+    assert np.array_equal(work[~mask], f[~mask])
+
+
+def test_poisson_identity_and_linearity(ctx):
+    rows, cols = 200, 260
+    f = synth.smooth_band(rows, cols, seed=2)
+    mask = synth.blob_mask(rows, cols, cover=0.4, sigma=6.0, seed=4, clear_border=False)
+    mask[0, :] = False
+    for g in (f, f + 123.0):  # replacement == input (+ const) must give back the input
+        out = sab.blend_images_poisson([f], [g], mask, tolerance=1e-11, max_iterations=10**6)
+        assert rel_max_abs(out[0], f, mask) < 1e-7
+    # linearity in (f, g): blend(a f1 + b f2, a g1 + b g2) = a blend(f1, g1) + b blend(f2, g2)
+    f2 = synth.smooth_band(rows, cols, seed=12)
+    g1, g2 = synth.second_date(f, seed=5), synth.second_date(f2, seed=6)
+    o = sab.blend_images_poisson([f, f2, 2 * f - 3 * f2], [g1, g2, 2 * g1 - 3 * g2], mask, tolerance=1e-11,
+                                 max_iterations=10**6)  # fmt: skip
+    assert rel_max_abs(o[2], 2 * o[0] - 3 * o[1], mask) < 1e-7
+
+
+def test_multiband_matches_single_band(ctx):
+    rows, cols = 150, 170
+    mask = synth.blob_mask(rows, cols, cover=0.35, sigma=5.0, seed=21)
+    bands = [synth.smooth_band(rows, cols, seed=30 + b) for b in range(5)]
+    multi = [b.copy() for b in bands]
+    ctx.laplace_fill(multi, mask, tolerance=1e-11)
+    for b in range(5):
+        single = [bands[b].copy()]
+        ctx.laplace_fill(single, mask, tolerance=1e-11)
+        assert rel_max_abs(multi[b], single[0], mask) < 1e-9
+
+
+def test_resident_scene_device_buffers(ctx, port):
+    """sa_scene_* with device-resident inputs (what bench.py times as `value`)."""
+    import torch
+
+    rows, cols = 130, 200
+    img = synth.smooth_band(rows, cols, seed=3)
+    mask = synth.blob_mask(rows, cols, cover=0.4, sigma=5.0, seed=4)
+    want, _ = port.laplace_fill(img, mask, mode=1, tol=1e-13)
+    sc = ctx.scene(sab.LAPLACE, rows, cols, 2)
+    sc.set_mask(torch.from_numpy(mask.view(np.uint8)).cuda())
+    d_img = torch.from_numpy(img).cuda()
+    sc.set_band(0, d_img)
+    sc.set_band(1, d_img * 2.0)
+    st = sc.solve(tolerance=1e-12)
+    assert all(s["status"] == sab.SA_OK for s in st) and st[0]["unknowns"] == int(mask.sum())
+    out = torch.empty_like(d_img)
+    sc.get_band(1, out)
+    ctx.synchronize()
+    assert rel_max_abs(out.cpu().numpy() / 2.0, want, mask) < 1e-8
+    assert rel_max_abs(sc.get_band(0), want, mask) < 1e-8
+    # solving again from the filled state must reproduce the same answer (x0 is reset, known pixels untouched)
+    st2 = sc.solve(tolerance=1e-12)
+    assert st2[0]["iterations"] == st[0]["iterations"]
+    sc.close()

@@ -1,0 +1,60 @@
+"""CPU: host-side mirror of the reference's Python surface -- dtype rules and error behaviour that are decided before
+any device work (src/main.cpp:49-58, laplace.cpp:124-127, poisson.cpp:154-160)."""
+from __future__ import annotations
+
+import numpy as np
+import pytest
+
+import satellite_approximation_b200 as sab
+
+
+def test_exports_match_reference_module():
+    for name in ("LogLevel", "set_log_level", "filling_missing_portions_smooth_boundaries", "blend_images_poisson"):
+        assert hasattr(sab, name)
+    assert [m.name for m in sab.LogLevel] == ["Debug", "Info", "Warn", "Error", "Critical"]  # src/main.cpp:24-29
+    sab.set_log_level(sab.LogLevel.Warn)
+
+
+def test_laplace_noconvert_dtype_rules():
+    img = np.zeros((4, 5), np.float64)
+    mask = np.zeros((4, 5), bool)
+    with pytest.raises(TypeError):
+        sab.filling_missing_portions_smooth_boundaries(img.astype(np.float32), mask)  # noconvert: no silent cast
+    with pytest.raises(TypeError):
+        sab.filling_missing_portions_smooth_boundaries(img, mask.astype(np.uint8))
+    with pytest.raises(TypeError):
+        sab.filling_missing_portions_smooth_boundaries(img[0], mask)
+
+
+def test_laplace_size_mismatch_raises_runtime_error():
+    with pytest.raises(RuntimeError):  # laplace.cpp:124-127
+        sab.filling_missing_portions_smooth_boundaries(np.zeros((4, 5)), np.zeros((4, 6), bool))
+
+
+def test_poisson_size_mismatch_returns_inputs_unchanged():
+    f = [np.arange(20.0).reshape(4, 5)]
+    g = [np.zeros((4, 6))]
+    out = sab.blend_images_poisson(f, g, np.zeros((4, 5), bool))  # poisson.cpp:154-157: log and return
+    assert len(out) == 1 and np.array_equal(out[0], f[0]) and out[0].flags.f_contiguous
+    out = sab.blend_images_poisson(f, [np.zeros((4, 5))], np.zeros((5, 4), bool))
+    assert np.array_equal(out[0], f[0])
+    assert sab.blend_images_poisson([], [], np.zeros((0, 0), bool)) == []
+
+
+def test_region_map_from_labels():
+    lab = np.array([[1, 0, 2], [1, 0, 2], [0, 0, 2]], np.int32)
+    cc = sab.ConnectedComponents(lab, 2)
+    rm = cc.region_map
+    assert set(rm) == {1, 2}
+    assert rm[1].tolist() == [[0, 0], [1, 0]] and rm[2].tolist() == [[0, 2], [1, 2], [2, 2]]
+    assert sab.ConnectedComponents(np.zeros((3, 3), np.int32), 0).region_map == {}
+
+
+def test_stride_helpers():
+    from satellite_approximation_b200 import _capi
+
+    a = np.zeros((6, 8))
+    assert _capi.is_dense_2d(a) and _capi.is_dense_2d(np.asfortranarray(a))
+    assert _capi.is_dense_2d(a[:, :5]) and _capi.is_dense_2d(a[1:4])
+    assert not _capi.is_dense_2d(a[::2, ::2])
+    assert _capi.element_strides(np.asfortranarray(a)) == (1, 6)
