@@ -163,6 +163,7 @@ void scene_free(sa_scene* s)
     cudaFree(s->p[0]);
     cudaFree(s->p[1]);
     cudaFree(s->z);
+    cudaFree(s->t);
     cudaFree(s->mask);
     cudaFree(s->umask);
     cudaFree(s->tile_list);

@@ -13,37 +13,9 @@
 // 65 B per unknown per iteration instead of the 89 B of the textbook five-pass formulation: A p is never stored.
 // All scalars stay on the device (BandScalars); the host only polls the `done` flags every check_every iterations.
 #include "common.cuh"
+#include "tile.cuh"
 
 namespace satfill {
-
-__device__ __forceinline__ double inv_diag(int64_t r, int64_t c, int64_t rows, int64_t cols)
-{
-    // in-image neighbour count: poisson.cpp:187-190 (valid_neighbours, utils.h:35-50); 4 for every Laplace unknown.
-    int d = (r > 0) + (r < rows - 1) + (c > 0) + (c < cols - 1);
-    // Eigen's DiagonalPreconditioner uses 1 for a zero diagonal (BasicPreconditioners.h:66-70)
-    return d == 4 ? 0.25 : (d == 3 ? (1.0 / 3.0) : (d == 2 ? 0.5 : 1.0));
-}
-__device__ __forceinline__ double diag_of(int64_t r, int64_t c, int64_t rows, int64_t cols)
-{
-    return (double)((r > 0) + (r < rows - 1) + (c > 0) + (c < cols - 1));
-}
-
-__device__ __forceinline__ double block_sum(double v, double* s_red /* 8 doubles */)
-{
-    for (int o = 16; o; o >>= 1)
-        v += __shfl_xor_sync(0xffffffffu, v, o);
-    __syncthreads();  // protect s_red reuse
-    if (threadIdx.x == 0)
-        s_red[threadIdx.y] = v;
-    __syncthreads();
-    double t = 0.0;
-    if (threadIdx.y == 0) {
-        t = threadIdx.x < CG_BLOCK_Y ? s_red[threadIdx.x] : 0.0;
-        for (int o = 4; o; o >>= 1)
-            t += __shfl_xor_sync(0xffffffffu, t, o);
-    }
-    return t;  // valid in thread (0, 0)
-}
 
 // ---------------------------------------------------------------------------------------------------------------
 // Set-up: initial iterate, residual, right-hand-side norm.
@@ -111,12 +83,14 @@ __global__ void __launch_bounds__(256) k_residual(Level lv, const double* __rest
         atomicAdd(&scal[blockIdx.y].rz[0], t);
 }
 
-__global__ void k_finalize_setup(BandScalars* scal, int nbands, double tol)
+__global__ void k_finalize_setup(BandScalars* scal, int nbands, double tol, int mg)
 {
     int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= nbands)
         return;
     BandScalars& s = scal[b];
+    if (mg)
+        s.rz[0] = 0.0;  // r.z of iteration 0 comes from the first V-cycle, not from the Jacobi scaling
     if (s.bnorm2 == 0.0) {  // ConjugateGradient.h:43-49
         s.zero_rhs = 1;
         s.done = 1;
@@ -153,32 +127,6 @@ __global__ void __launch_bounds__(256) k_zero_unknowns(Level lv, double* __restr
 // ---------------------------------------------------------------------------------------------------------------
 // The two kernels of one CG iteration.
 // ---------------------------------------------------------------------------------------------------------------
-
-// Stage the 34 x 34 neighbourhood of a tile in shared memory.  `f(idx, r, c)` yields the value of the staged vector
-// at plane offset idx; it is evaluated for the 32 x 32 interior (coalesced 256 B rows) and the 4 x 32 halo cells.
-constexpr int SP = TILE_W + 3;  // padded row length of the staged tile (odd multiple keeps 8-byte banks spread)
-
-template <typename F>
-__device__ __forceinline__ void stage_tile(double (*sp)[SP], int64_t r0, int64_t c0, int64_t pitch, F f)
-{
-#pragma unroll
-    for (int j = 0; j < ROWS_PER_THREAD; ++j) {
-        int lr = threadIdx.y + j * CG_BLOCK_Y;
-        int64_t r = r0 + lr, c = c0 + threadIdx.x;
-        sp[lr + 1][threadIdx.x + 1] = f(r * pitch + c, r, c, true);
-    }
-    int t = threadIdx.y * CG_BLOCK_X + threadIdx.x;
-    if (t < 128) {
-        int e = t >> 5, i = t & 31;
-        int lr, lc;
-        if (e == 0) { lr = -1; lc = i; }
-        else if (e == 1) { lr = TILE_H; lc = i; }
-        else if (e == 2) { lr = i; lc = -1; }
-        else { lr = i; lc = TILE_W; }
-        int64_t r = r0 + lr, c = c0 + lc;
-        sp[lr + 1][lc + 1] = f(r * pitch + c, r, c, false);
-    }
-}
 
 // k_direction: p' = z + beta p, pq = p'.Ap'.   JACOBI: z = r / d computed on the fly (zin = r).  Otherwise zin = z.
 template <bool JACOBI>
@@ -309,7 +257,7 @@ __global__ void k_final_check(BandScalars* scal, int nbands, int k_end)
 // ---------------------------------------------------------------------------------------------------------------
 // Host driver
 // ---------------------------------------------------------------------------------------------------------------
-static Level fine_level(const sa_scene* s)
+Level fine_level(const sa_scene* s)
 {
     Level lv {};
     lv.rows = s->rows;
@@ -321,6 +269,7 @@ static Level fine_level(const sa_scene* s)
     lv.n_tiles = s->n_active_tiles;
     lv.umask = s->mask0(s->umask);
     lv.tile_list = s->tile_list;
+    lv.fixed_diag = s->problem == SA_LAPLACE;
     return lv;
 }
 
@@ -337,6 +286,8 @@ int ensure_indexed(sa_scene* s)
     SA_CUDA(ctx, cudaMemsetAsync(s->p[1], 0, bytes, ctx->stream));
     if (s->z)
         SA_CUDA(ctx, cudaMemsetAsync(s->z, 0, bytes, ctx->stream));
+    if (s->t)
+        SA_CUDA(ctx, cudaMemsetAsync(s->t, 0, bytes, ctx->stream));
     s->hierarchy_built = false;
     return SA_OK;
 }
@@ -373,7 +324,9 @@ int solve_scene(sa_scene* s, const sa_options& o, sa_stats* stats)
         if (!s->z) {
             size_t bytes = (size_t)s->plane * nb * sizeof(double);
             SA_CUDA(ctx, cudaMalloc(&s->z, bytes));
+            SA_CUDA(ctx, cudaMalloc(&s->t, bytes));
             SA_CUDA(ctx, cudaMemsetAsync(s->z, 0, bytes, ctx->stream));
+            SA_CUDA(ctx, cudaMemsetAsync(s->t, 0, bytes, ctx->stream));
         }
         if (!s->hierarchy_built)
             SA_TRY(build_hierarchy(s, o));
@@ -385,7 +338,6 @@ int solve_scene(sa_scene* s, const sa_options& o, sa_stats* stats)
     double* g0 = poisson ? s->plane0(s->g, 0) : nullptr;
     double* r0 = s->plane0(s->r, 0);
     double* pbuf[2] = { s->plane0(s->p[0], 0), s->plane0(s->p[1], 0) };
-    double* z0 = s->z ? s->plane0(s->z, 0) : nullptr;
 
     SA_CUDA(ctx, cudaMemsetAsync(s->scal, 0, sizeof(BandScalars) * nb, ctx->stream));
     if (poisson) {
@@ -395,7 +347,7 @@ int solve_scene(sa_scene* s, const sa_options& o, sa_stats* stats)
         SA_LAUNCH(ctx, k_init_guess<false>, grid, block, 0, lv, u0, g0);
         SA_LAUNCH(ctx, k_residual<false>, grid, block, 0, lv, u0, g0, r0, s->scal);
     }
-    SA_LAUNCH(ctx, k_finalize_setup, (nb + 63) / 64, 64, 0, s->scal, nb, o.tolerance);
+    SA_LAUNCH(ctx, k_finalize_setup, (nb + 63) / 64, 64, 0, s->scal, nb, o.tolerance, mg ? 1 : 0);
     SA_CUDA(ctx, cudaGetLastError());
     SA_CUDA(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
 
@@ -413,9 +365,9 @@ int solve_scene(sa_scene* s, const sa_options& o, sa_stats* stats)
             const double* pin = pbuf[k & 1];
             double* pout = pbuf[(k + 1) & 1];
             if (mg) {
-                SA_TRY(apply_vcycle(s, o, kt));  // z = M^-1 r, rz[slot] accumulated by its last kernel
+                SA_TRY(apply_vcycle(s, o, kt, ki & 3));  // z = M^-1 r, rz[slot] accumulated by its last kernel
                 kt.begin(KC_DIRECTION);
-                SA_LAUNCH(ctx, k_direction<false>, grid, block, 0, lv, z0, pin, pout, s->scal, ki);
+                SA_LAUNCH(ctx, k_direction<false>, grid, block, 0, lv, s->plane0(s->z, 0), pin, pout, s->scal, ki);
                 kt.end();
                 kt.begin(KC_UPDATE);
                 SA_LAUNCH(ctx, k_update<false>, grid, block, 0, lv, u0, pout, r0, s->scal, ki);

@@ -52,6 +52,7 @@ struct Level {
     int n_tiles;          // active tiles
     const uint8_t* umask; // 1 = unknown of the linear system; addressed like a plane (pitch bytes per row)
     const int32_t* tile_list;
+    int fixed_diag;       // != 0: the diagonal is 4 everywhere (Laplace: unknowns never touch the image border)
 };
 
 }  // namespace satfill
@@ -73,7 +74,9 @@ struct sa_ctx {
 struct sa_level_store {
     satfill::Level lv {};
     uint8_t* umask_alloc = nullptr;    // base of the allocation (guard row included)
-    int32_t* tile_list = nullptr;
+    int32_t* tile_list = nullptr;      // 2 * tiles entries: list, then per-tile flags
+    int32_t* d_counters = nullptr;     // {active tiles, first, last, -}
+    int64_t rows_p = 0;
     double* x = nullptr;               // coarse levels: correction; nbands planes (allocation base)
     double* b = nullptr;               // coarse levels: restricted residual
     double* t = nullptr;               // scratch (second smoothing buffer)
@@ -98,6 +101,7 @@ struct sa_scene {
     double* r = nullptr;
     double* p[2] = { nullptr, nullptr };
     double* z = nullptr;   // multigrid only: preconditioned residual
+    double* t = nullptr;   // multigrid only: fine-level scratch (smoother ping-pong, residual)
     uint8_t* mask = nullptr;   // normalised 0/1 invalid mask (allocation base)
     uint8_t* umask = nullptr;  // unknown set (allocation base)
     int32_t* tile_list = nullptr;
@@ -223,11 +227,12 @@ int device_label_components(sa_ctx* ctx, const uint8_t* mask, int64_t rows, int6
 // index the mask if it changed and clear the work vectors (they must be zero outside the unknown set)
 int ensure_indexed(sa_scene* s);
 int solve_scene(sa_scene* s, const sa_options& o, sa_stats* stats);
+Level fine_level(const sa_scene* s);
 
 // ---- mg.cu -----------------------------------------------------------------------------------------------------
 int build_hierarchy(sa_scene* s, const sa_options& o);
 void free_hierarchy(sa_scene* s);
-// z = M^{-1} r for every band that is not done (one symmetric V-cycle)
-int apply_vcycle(sa_scene* s, const sa_options& o, KernelTimer& kt);
+// z = M^{-1} r for every band that is not done (one symmetric V-cycle); r.z is accumulated into rz[rz_slot]
+int apply_vcycle(sa_scene* s, const sa_options& o, KernelTimer& kt, int rz_slot);
 
 }  // namespace satfill
