@@ -250,6 +250,7 @@ def run_b200(args, w):
     e0.record(stream)
     kms = [0.0] * 4
     kn = [0] * 4
+    ku = [0] * 4
     iters = []
     for _ in range(args.steps):
         st = step()
@@ -257,6 +258,7 @@ def run_b200(args, w):
         for c in range(4):
             kms[c] += st[0]["kernel_ms"][c]
             kn[c] += st[0]["kernel_launches"][c]
+            ku[c] += st[0]["kernel_units"][c]
     e1.record(stream)
     barrier()
     clocks = sampler.stop()
@@ -285,20 +287,25 @@ def run_b200(args, w):
     peak, peak_src = peaks()
     roof = None
     if kn[dom] > 0 and kms[dom] > 0:
-        units = scene_level_units(st, dom, unknowns * nb)
+        # per launch: algorithmic bytes = bytes/unknown x (unknown-bands the launches of this class processed / launches)
+        units = ku[dom] / kn[dom]
         achieved = bytes_per_unknown[dom] * units / (kms[dom] / kn[dom] * 1e-3) / 1e9
         roof = {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                 "avg_launch_ms": kms[dom] / kn[dom], "launches": kn[dom],
                 "share_of_step": kms[dom] / ms if ms > 0 else None,
                 "algorithmic_bytes_per_launch": bytes_per_unknown[dom] * units,
-                "all_kernels_ms": {names[c]: kms[c] for c in range(4)}}  # fmt: skip
+                "bytes_per_unknown": bytes_per_unknown[dom],
+                "all_kernels": {names[c]: {"ms": kms[c], "launches": kn[c],
+                                           "GBps": (bytes_per_unknown[c] * ku[c] / (kms[c] * 1e-3) / 1e9) if kms[c] else None}
+                                for c in range(4)}}  # fmt: skip
 
-    # ---- end to end through the host-pointer C-ABI entry point
+    # ---- end to end through the host-pointer C-ABI entry point (the resident scene is released first: the host-pointer
+    # entry point keeps its own scene, and two 13-band scenes with solver work space do not fit one GPU together)
+    scene.close()
     e2e = None
     if not args.no_e2e:
         e2e = run_e2e(args, w, ctx, sab, mask, bands, guides, world, dev, barrier)
-    scene.close()
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -323,13 +330,6 @@ def run_b200(args, w):
         dist.destroy_process_group()
 
 
-def scene_level_units(st, cls, fine_units):
-    """Units (unknown-bands) one launch of a kernel class processes.  CG kernels always run on the fine grid; multigrid
-    launches run on all levels, so their per-launch average is fine_units * sum_l 4^-l / levels -- computed by the
-    library from the real per-level unknown counts would be better; DESIGN.md states the approximation."""
-    return fine_units
-
-
 def run_e2e(args, w, ctx, sab, mask, bands, guides, world, dev, barrier):
     import torch
 
@@ -338,7 +338,6 @@ def run_e2e(args, w, ctx, sab, mask, bands, guides, world, dev, barrier):
     h_mask = torch.empty((rows, cols), dtype=torch.uint8).pin_memory()
     h_mask.copy_(mask)
     h_bands = [torch.empty((rows, cols), dtype=torch.float64).pin_memory() for _ in range(nb)]
-    h_orig = []
     for b in range(nb):
         h_bands[b].copy_(bands[b])
     h_guides = None
@@ -347,6 +346,11 @@ def run_e2e(args, w, ctx, sab, mask, bands, guides, world, dev, barrier):
         for b in range(nb):
             h_guides[b].copy_(guides[b])
     torch.cuda.synchronize()
+    bands.clear()  # free the device copies: the e2e call starts from host memory
+    if guides:
+        guides.clear()
+    del mask
+    torch.cuda.empty_cache()
     np_mask = h_mask.numpy()
     np_bands = [t.numpy() for t in h_bands]
     np_guides = [t.numpy() for t in h_guides] if poisson else None

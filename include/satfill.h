@@ -85,6 +85,9 @@ typedef struct sa_stats {
      * 3 = multigrid transfer (residual + restriction, prolongation + correction) */
     double kernel_ms[4];
     int64_t kernel_launches[4];
+    /* unknowns x bands summed over the launches of each class (a multigrid launch on level l counts the unknowns of
+     * level l): algorithmic bytes of a class = bytes per unknown x kernel_units */
+    int64_t kernel_units[4];
 } sa_stats;
 
 /* ---- context ------------------------------------------------------------------------------------------------ */

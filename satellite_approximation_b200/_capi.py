@@ -64,12 +64,14 @@ class Stats(C.Structure):
         ("active_tiles", C.c_int32),
         ("kernel_ms", C.c_double * 4),
         ("kernel_launches", C.c_int64 * 4),
+        ("kernel_units", C.c_int64 * 4),
     ]
 
     def as_dict(self) -> dict:
         d = {name: getattr(self, name) for name, _ in self._fields_}
         d["kernel_ms"] = list(self.kernel_ms)
         d["kernel_launches"] = list(self.kernel_launches)
+        d["kernel_units"] = list(self.kernel_units)
         return d
 
 

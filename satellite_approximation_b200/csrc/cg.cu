@@ -54,7 +54,6 @@ __global__ void __launch_bounds__(256) k_residual(Level lv, const double* __rest
     for (int j = 0; j < ROWS_PER_THREAD; ++j) {
         int64_t r = r0 + threadIdx.y + j * CG_BLOCK_Y, c = c0 + threadIdx.x;
         int64_t idx = r * lv.pitch + c;
-        double res = 0.0;
         if (lv.umask[idx]) {
             double d = diag_of(r, c, lv.rows, lv.cols);
             double un = ub[idx - lv.pitch], us = ub[idx + lv.pitch], uw = ub[idx - 1], ue = ub[idx + 1];
@@ -64,12 +63,12 @@ __global__ void __launch_bounds__(256) k_residual(Level lv, const double* __rest
             if (POISSON)  // sum over in-image neighbours of (g_p - g_q); g is zero outside the image
                 div = d * gb[idx] - (gb[idx - lv.pitch] + gb[idx + lv.pitch] + gb[idx - 1] + gb[idx + 1]);
             double b = div + (kn + ks + kw + ke);
-            res = div + (un + us + uw + ue) - d * ub[idx];
+            double res = div + (un + us + uw + ue) - d * ub[idx];
             b2 += b * b;
             r2 += res * res;
             rz += res * res * inv_diag(r, c, lv.rows, lv.cols);
+            rvec[boff + idx] = res;
         }
-        rvec[boff + idx] = res;
     }
     double t;
     t = block_sum(b2, s_red);
@@ -163,7 +162,7 @@ __global__ void __launch_bounds__(256) k_direction(Level lv, const double* __res
     const double* pb = p_old + boff;
     double* pn = p_new + boff;
     int64_t rows = lv.rows, cols = lv.cols;
-    stage_tile(sp, r0, c0, lv.pitch, [&](int64_t idx, int64_t r, int64_t c, bool interior) {
+    stage_tile(sp, lv.umask, r0, c0, lv.pitch, [&](int64_t idx, int64_t r, int64_t c, bool interior) {
         double z = zb[idx];
         if (JACOBI)
             z *= inv_diag(r, c, rows, cols);
@@ -206,7 +205,7 @@ __global__ void __launch_bounds__(256) k_update(Level lv, double* __restrict__ u
     double* ub = u + boff;
     double* rb = rvec + boff;
     int64_t rows = lv.rows, cols = lv.cols;
-    stage_tile(sp, r0, c0, lv.pitch, [&](int64_t idx, int64_t, int64_t, bool) { return pb[idx]; });
+    stage_tile(sp, lv.umask, r0, c0, lv.pitch, [&](int64_t idx, int64_t, int64_t, bool) { return pb[idx]; });
     __syncthreads();
     double r2 = 0.0, rz = 0.0;
 #pragma unroll
@@ -366,17 +365,17 @@ int solve_scene(sa_scene* s, const sa_options& o, sa_stats* stats)
             double* pout = pbuf[(k + 1) & 1];
             if (mg) {
                 SA_TRY(apply_vcycle(s, o, kt, ki & 3));  // z = M^-1 r, rz[slot] accumulated by its last kernel
-                kt.begin(KC_DIRECTION);
+                kt.begin(KC_DIRECTION, n * nb);
                 SA_LAUNCH(ctx, k_direction<false>, grid, block, 0, lv, s->plane0(s->z, 0), pin, pout, s->scal, ki);
                 kt.end();
-                kt.begin(KC_UPDATE);
+                kt.begin(KC_UPDATE, n * nb);
                 SA_LAUNCH(ctx, k_update<false>, grid, block, 0, lv, u0, pout, r0, s->scal, ki);
                 kt.end();
             } else {
-                kt.begin(KC_DIRECTION);
+                kt.begin(KC_DIRECTION, n * nb);
                 SA_LAUNCH(ctx, k_direction<true>, grid, block, 0, lv, r0, pin, pout, s->scal, ki);
                 kt.end();
-                kt.begin(KC_UPDATE);
+                kt.begin(KC_UPDATE, n * nb);
                 SA_LAUNCH(ctx, k_update<true>, grid, block, 0, lv, u0, pout, r0, s->scal, ki);
                 kt.end();
             }
@@ -411,6 +410,7 @@ int solve_scene(sa_scene* s, const sa_options& o, sa_stats* stats)
             for (int c = 0; c < KC_COUNT; ++c) {
                 stats[b].kernel_ms[c] = kt.ms[c];
                 stats[b].kernel_launches[c] = kt.n[c];
+                stats[b].kernel_units[c] = kt.units[c];
             }
         }
         if (st != SA_OK)

@@ -166,6 +166,7 @@ struct KernelTimer {
     std::vector<Pending> pending;
     double ms[KC_COUNT] = { 0, 0, 0, 0 };
     int64_t n[KC_COUNT] = { 0, 0, 0, 0 };
+    int64_t units[KC_COUNT] = { 0, 0, 0, 0 };
 
     cudaEvent_t take()
     {
@@ -176,10 +177,11 @@ struct KernelTimer {
         }
         return ctx->ev_pool[used++];
     }
-    void begin(int cls)
+    void begin(int cls, int64_t launch_units = 0)
     {
         if (!on)
             return;
+        units[cls] += launch_units;
         pending.push_back({ cls, used });
         cudaEventRecord(take(), ctx->stream);
     }

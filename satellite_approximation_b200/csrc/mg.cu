@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(256) k_mg_smooth(Level lv, const double* __res
     double* xo = x_out + boff;
     if (!FIRST) {
         const double* xi = x_in + boff;
-        stage_tile(sp, r0, c0, lv.pitch, [&](int64_t idx, int64_t, int64_t, bool) { return xi[idx]; });
+        stage_tile(sp, lv.umask, r0, c0, lv.pitch, [&](int64_t idx, int64_t, int64_t, bool) { return xi[idx]; });
         __syncthreads();
     }
     double acc = 0.0;
@@ -218,7 +218,7 @@ __global__ void __launch_bounds__(256) k_mg_residual(Level lv, const double* __r
     int64_t r0 = (int64_t)(tile / lv.tiles_x) * TILE_H, c0 = (int64_t)(tile % lv.tiles_x) * TILE_W;
     int64_t boff = (int64_t)blockIdx.y * lv.plane;
     const double* xb = x + boff;
-    stage_tile(sp, r0, c0, lv.pitch, [&](int64_t idx, int64_t, int64_t, bool) { return xb[idx]; });
+    stage_tile(sp, lv.umask, r0, c0, lv.pitch, [&](int64_t idx, int64_t, int64_t, bool) { return xb[idx]; });
     __syncthreads();
 #pragma unroll
     for (int j = 0; j < ROWS_PER_THREAD; ++j) {
@@ -293,6 +293,7 @@ namespace {
 
 struct LevelVecs {
     Level lv;
+    int64_t units;  // unknowns x bands of the level
     double* x;  // iterate (level 0: z)
     double* b;  // right-hand side (level 0: the CG residual r)
     double* t;  // scratch
@@ -306,11 +307,11 @@ int apply_vcycle(sa_scene* s, const sa_options& o, KernelTimer& kt, int rz_slot)
     const int nb = s->nbands;
     const int nu = o.mg_smooth > 0 ? o.mg_smooth : 2;
     std::vector<LevelVecs> L;
-    L.push_back({ fine_level(s), s->plane0(s->z, 0), s->plane0(s->r, 0), s->plane0(s->t, 0) });
+    L.push_back({ fine_level(s), s->n_unknowns * nb, s->plane0(s->z, 0), s->plane0(s->r, 0), s->plane0(s->t, 0) });
     for (sa_level_store& c : s->coarse) {
         if (c.lv.n_tiles == 0)
             break;
-        L.push_back({ c.lv, c.x + c.lv.pitch, c.b + c.lv.pitch, c.t + c.lv.pitch });
+        L.push_back({ c.lv, c.n_unknowns * nb, c.x + c.lv.pitch, c.b + c.lv.pitch, c.t + c.lv.pitch });
     }
     const int nl = (int)L.size();
     dim3 block(CG_BLOCK_X, CG_BLOCK_Y);
@@ -327,7 +328,7 @@ int apply_vcycle(sa_scene* s, const sa_options& o, KernelTimer& kt, int rz_slot)
         if (from_zero) {
             // sweep 1 writes without reading an iterate: choose its target so that the last sweep writes V.x
             double* target = (writes % 2 == 1) ? V.x : V.t;
-            kt.begin(KC_SMOOTH);
+            kt.begin(KC_SMOOTH, V.units);
             if (sweeps == 1 && rz_slot >= 0)
                 SA_LAUNCH(ctx, (k_mg_smooth<true, true>), grid, block, 0, V.lv, nullptr, V.b, target, scal, rz_slot);
             else
@@ -339,7 +340,7 @@ int apply_vcycle(sa_scene* s, const sa_options& o, KernelTimer& kt, int rz_slot)
         }
         for (int k = 0; k < writes; ++k) {
             bool last = k == writes - 1;
-            kt.begin(KC_SMOOTH);
+            kt.begin(KC_SMOOTH, V.units);
             if (last && rz_slot >= 0)
                 SA_LAUNCH(ctx, (k_mg_smooth<false, true>), grid, block, 0, V.lv, cur, V.b, oth, scal, rz_slot);
             else
@@ -362,10 +363,10 @@ int apply_vcycle(sa_scene* s, const sa_options& o, KernelTimer& kt, int rz_slot)
         LevelVecs& F = L[l];
         LevelVecs& C = L[l + 1];
         dim3 gf((unsigned)F.lv.n_tiles, (unsigned)nb), gc((unsigned)C.lv.n_tiles, (unsigned)nb);
-        kt.begin(KC_TRANSFER);
+        kt.begin(KC_TRANSFER, F.units);
         SA_LAUNCH(ctx, k_mg_residual, gf, block, 0, F.lv, F.x, F.b, F.t, scal);
         kt.end();
-        kt.begin(KC_TRANSFER);
+        kt.begin(KC_TRANSFER, C.units);
         SA_LAUNCH(ctx, k_mg_restrict, gc, block, 0, C.lv, F.lv, F.t, C.b, scal);
         kt.end();
     }
@@ -380,7 +381,7 @@ int apply_vcycle(sa_scene* s, const sa_options& o, KernelTimer& kt, int rz_slot)
         LevelVecs& F = L[l];
         LevelVecs& C = L[l + 1];
         dim3 gf((unsigned)F.lv.n_tiles, (unsigned)nb);
-        kt.begin(KC_TRANSFER);
+        kt.begin(KC_TRANSFER, F.units);
         SA_LAUNCH(ctx, k_mg_prolong, gf, block, 0, F.lv, C.lv, F.x, C.x, scal);
         kt.end();
         SA_TRY(smooth(l, nu, false, l == 0 ? rz_slot : -1));
