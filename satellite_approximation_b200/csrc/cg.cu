@@ -235,6 +235,21 @@ __global__ void __launch_bounds__(256) k_update(Level lv, double* __restrict__ u
     }
 }
 
+// Multigrid loop: test the stop rule right after the update of iteration k - 1 (one thread per band), so that a band
+// that has converged does not pay for another V-cycle before k_direction would notice.
+__global__ void k_check_converged(BandScalars* scal, int nbands, int k)
+{
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nbands)
+        return;
+    BandScalars& s = scal[b];
+    if (!s.done && s.rr[k & 3] < s.thr) {  // ConjugateGradient.h:72-73
+        s.rr_exit = s.rr[k & 3];
+        s.iters = k - 1;
+        s.done = 1;
+    }
+}
+
 __global__ void k_final_check(BandScalars* scal, int nbands, int k_end)
 {
     int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -354,9 +369,12 @@ int solve_scene(sa_scene* s, const sa_options& o, sa_stats* stats)
     kt.ctx = ctx;
     kt.on = o.profile != 0;
     BandScalars* h_scal = (BandScalars*)ctx->pinned;
-    const int check = o.check_every > 0 ? o.check_every : 32;
+    // Jacobi iterations are short (two kernels): poll the flags every 32.  A multigrid iteration is a whole V-cycle:
+    // poll every iteration, which also keeps the profile's per-class unit counts exact.
+    const int check = o.check_every > 0 ? o.check_every : (mg ? 1 : 32);
     int64_t k = 0;
     bool all_done = false;
+    int live = nb;  // bands not done at the last poll
     while (k < max_it && !all_done) {
         int64_t k_stop = k + check < max_it ? k + check : max_it;
         for (; k < k_stop; ++k) {
@@ -364,18 +382,19 @@ int solve_scene(sa_scene* s, const sa_options& o, sa_stats* stats)
             const double* pin = pbuf[k & 1];
             double* pout = pbuf[(k + 1) & 1];
             if (mg) {
-                SA_TRY(apply_vcycle(s, o, kt, ki & 3));  // z = M^-1 r, rz[slot] accumulated by its last kernel
-                kt.begin(KC_DIRECTION, n * nb);
+                SA_TRY(apply_vcycle(s, o, kt, ki & 3, live));  // z = M^-1 r, rz[slot] accumulated by its last kernel
+                kt.begin(KC_DIRECTION, n * live);
                 SA_LAUNCH(ctx, k_direction<false>, grid, block, 0, lv, s->plane0(s->z, 0), pin, pout, s->scal, ki);
                 kt.end();
-                kt.begin(KC_UPDATE, n * nb);
+                kt.begin(KC_UPDATE, n * live);
                 SA_LAUNCH(ctx, k_update<false>, grid, block, 0, lv, u0, pout, r0, s->scal, ki);
                 kt.end();
+                SA_LAUNCH(ctx, k_check_converged, (nb + 63) / 64, 64, 0, s->scal, nb, ki + 1);
             } else {
-                kt.begin(KC_DIRECTION, n * nb);
+                kt.begin(KC_DIRECTION, n * live);
                 SA_LAUNCH(ctx, k_direction<true>, grid, block, 0, lv, r0, pin, pout, s->scal, ki);
                 kt.end();
-                kt.begin(KC_UPDATE, n * nb);
+                kt.begin(KC_UPDATE, n * live);
                 SA_LAUNCH(ctx, k_update<true>, grid, block, 0, lv, u0, pout, r0, s->scal, ki);
                 kt.end();
             }
@@ -384,9 +403,10 @@ int solve_scene(sa_scene* s, const sa_options& o, sa_stats* stats)
         SA_CUDA(ctx, cudaMemcpyAsync(h_scal, s->scal, sizeof(BandScalars) * nb, cudaMemcpyDeviceToHost, ctx->stream));
         SA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         kt.flush();
-        all_done = true;
+        live = 0;
         for (int b = 0; b < nb; ++b)
-            all_done = all_done && h_scal[b].done;
+            live += h_scal[b].done ? 0 : 1;
+        all_done = live == 0;
     }
     SA_LAUNCH(ctx, k_final_check, (nb + 63) / 64, 64, 0, s->scal, nb, (int)(k & 0x3fffffff));
     SA_LAUNCH(ctx, k_zero_unknowns, grid, block, 0, lv, u0, s->scal);

@@ -235,6 +235,6 @@ Level fine_level(const sa_scene* s);
 int build_hierarchy(sa_scene* s, const sa_options& o);
 void free_hierarchy(sa_scene* s);
 // z = M^{-1} r for every band that is not done (one symmetric V-cycle); r.z is accumulated into rz[rz_slot]
-int apply_vcycle(sa_scene* s, const sa_options& o, KernelTimer& kt, int rz_slot);
+int apply_vcycle(sa_scene* s, const sa_options& o, KernelTimer& kt, int rz_slot, int live_bands);
 
 }  // namespace satfill

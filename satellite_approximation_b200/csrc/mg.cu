@@ -301,17 +301,17 @@ struct LevelVecs {
 
 }  // namespace
 
-int apply_vcycle(sa_scene* s, const sa_options& o, KernelTimer& kt, int rz_slot)
+int apply_vcycle(sa_scene* s, const sa_options& o, KernelTimer& kt, int rz_slot, int live_bands)
 {
     sa_ctx* ctx = s->ctx;
     const int nb = s->nbands;
     const int nu = o.mg_smooth > 0 ? o.mg_smooth : 2;
     std::vector<LevelVecs> L;
-    L.push_back({ fine_level(s), s->n_unknowns * nb, s->plane0(s->z, 0), s->plane0(s->r, 0), s->plane0(s->t, 0) });
+    L.push_back({ fine_level(s), s->n_unknowns * live_bands, s->plane0(s->z, 0), s->plane0(s->r, 0), s->plane0(s->t, 0) });
     for (sa_level_store& c : s->coarse) {
         if (c.lv.n_tiles == 0)
             break;
-        L.push_back({ c.lv, c.n_unknowns * nb, c.x + c.lv.pitch, c.b + c.lv.pitch, c.t + c.lv.pitch });
+        L.push_back({ c.lv, c.n_unknowns * live_bands, c.x + c.lv.pitch, c.b + c.lv.pitch, c.t + c.lv.pitch });
     }
     const int nl = (int)L.size();
     dim3 block(CG_BLOCK_X, CG_BLOCK_Y);
