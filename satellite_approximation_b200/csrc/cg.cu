@@ -24,7 +24,7 @@ namespace satfill {
 // x0: Laplace solve() starts from zero (IterativeSolverBase.h:357-360); Poisson from the replacement image
 // (poisson.cpp:239, 257).
 template <bool POISSON>
-__global__ void __launch_bounds__(256) k_init_guess(Level lv, double* __restrict__ u, const double* __restrict__ g)
+__global__ void __launch_bounds__(CG_THREADS) k_init_guess(Level lv, double* __restrict__ u, const double* __restrict__ g)
 {
     int tile = lv.tile_list[blockIdx.x];
     int64_t r0 = (int64_t)(tile / lv.tiles_x) * TILE_H, c0 = (int64_t)(tile % lv.tiles_x) * TILE_W;
@@ -40,7 +40,7 @@ __global__ void __launch_bounds__(256) k_init_guess(Level lv, double* __restrict
 // r = b - A x0 and |b|^2, |r|^2, r.(r/d) in one pass over u (and g): laplace.cpp:71-94 / poisson.cpp:241-251 for b,
 // ConjugateGradient.h:38-61 for the rest.
 template <bool POISSON>
-__global__ void __launch_bounds__(256) k_residual(Level lv, const double* __restrict__ u, const double* __restrict__ g,
+__global__ void __launch_bounds__(CG_THREADS) k_residual(Level lv, const double* __restrict__ u, const double* __restrict__ g,
     double* __restrict__ rvec, BandScalars* __restrict__ scal)
 {
     __shared__ double s_red[CG_BLOCK_Y];
@@ -107,7 +107,7 @@ __global__ void k_finalize_setup(BandScalars* scal, int nbands, double tol, int 
 }
 
 // Zero right-hand side: Eigen returns x = 0 whatever the guess was (ConjugateGradient.h:43-49).
-__global__ void __launch_bounds__(256) k_zero_unknowns(Level lv, double* __restrict__ u,
+__global__ void __launch_bounds__(CG_THREADS) k_zero_unknowns(Level lv, double* __restrict__ u,
     const BandScalars* __restrict__ scal)
 {
     if (!scal[blockIdx.y].zero_rhs)
@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(256) k_zero_unknowns(Level lv, double* __restr
 
 // k_direction: p' = z + beta p, pq = p'.Ap'.   JACOBI: z = r / d computed on the fly (zin = r).  Otherwise zin = z.
 template <bool JACOBI>
-__global__ void __launch_bounds__(256) k_direction(Level lv, const double* __restrict__ zin,
+__global__ void __launch_bounds__(CG_THREADS) k_direction(Level lv, const double* __restrict__ zin,
     const double* __restrict__ p_old, double* __restrict__ p_new, BandScalars* __restrict__ scal, int k)
 {
     __shared__ double sp[TILE_H + 2][SP];
@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(256) k_direction(Level lv, const double* __res
 
 // k_update: alpha = rz / pq; x += alpha p; r -= alpha A p; new |r|^2 and (JACOBI) r.(r/d) into slot k+1.
 template <bool JACOBI>
-__global__ void __launch_bounds__(256) k_update(Level lv, double* __restrict__ u, const double* __restrict__ p,
+__global__ void __launch_bounds__(CG_THREADS) k_update(Level lv, double* __restrict__ u, const double* __restrict__ p,
     double* __restrict__ rvec, BandScalars* __restrict__ scal, int k)
 {
     __shared__ double sp[TILE_H + 2][SP];

@@ -57,11 +57,11 @@ int transpose_i32(sa_ctx* ctx, const int32_t* s, int64_t r, int64_t c, int64_t s
 // to 0/1 in place on the way.  Each CTA records whether its tile holds an unknown; a single-CTA ballot scan then
 // lists the active tiles in raster order (reproducible work order, neighbouring CTAs touch neighbouring memory).
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_build_unknown_set(uint8_t* __restrict__ mask, uint8_t* __restrict__ umask,
+__global__ void __launch_bounds__(CG_THREADS) k_build_unknown_set(uint8_t* __restrict__ mask, uint8_t* __restrict__ umask,
     int64_t rows, int64_t cols, int64_t pitch, int tiles_x, int laplace, int32_t* __restrict__ tile_flags,
     unsigned long long* __restrict__ count64)
 {
-    __shared__ int warp_cnt[8];
+    __shared__ int warp_cnt[CG_BLOCK_Y];
     int tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x;
     int64_t c = (int64_t)tx * TILE_W + threadIdx.x;
     int cnt = 0;
@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(256) k_build_unknown_set(uint8_t* __restrict__
     __syncthreads();
     if (threadIdx.x == 0 && threadIdx.y == 0) {
         int total = 0;
-        for (int w = 0; w < 8; ++w)
+        for (int w = 0; w < CG_BLOCK_Y; ++w)
             total += warp_cnt[w];
         tile_flags[blockIdx.x] = total > 0;
         if (total > 0)

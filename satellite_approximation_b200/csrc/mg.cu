@@ -29,11 +29,11 @@ __device__ __forceinline__ double lv_diag(const Level& lv, int64_t r, int64_t c)
 // ---- hierarchy construction -------------------------------------------------------------------------------------
 
 // coarse umask(I, J) = fine umask(2I, 2J); per-tile activity flags and unknown count.  One CTA per coarse tile.
-__global__ void __launch_bounds__(256) k_coarsen_mask(const uint8_t* __restrict__ fmask, int64_t fpitch,
+__global__ void __launch_bounds__(CG_THREADS) k_coarsen_mask(const uint8_t* __restrict__ fmask, int64_t fpitch,
     uint8_t* __restrict__ cmask, int64_t crows, int64_t ccols, int64_t cpitch, int tiles_x,
     int32_t* __restrict__ tile_flags, unsigned long long* __restrict__ count64)
 {
-    __shared__ int warp_cnt[8];
+    __shared__ int warp_cnt[CG_BLOCK_Y];
     int tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x;
     int64_t c = (int64_t)tx * TILE_W + threadIdx.x;
     int cnt = 0;
@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(256) k_coarsen_mask(const uint8_t* __restrict_
     __syncthreads();
     if (threadIdx.x == 0 && threadIdx.y == 0) {
         int total = 0;
-        for (int w = 0; w < 8; ++w)
+        for (int w = 0; w < CG_BLOCK_Y; ++w)
             total += warp_cnt[w];
         tile_flags[blockIdx.x] = total > 0;
         if (total > 0)
@@ -161,7 +161,7 @@ int build_hierarchy(sa_scene* s, const sa_options& o)
 // else : x_out = x_in + omega * (b - A x_in) / d.
 // DOT  : additionally accumulate b . x_out into rz[slot] (level 0, last post-smoothing sweep: b is the CG residual).
 template <bool FIRST, bool DOT>
-__global__ void __launch_bounds__(256) k_mg_smooth(Level lv, const double* __restrict__ x_in,
+__global__ void __launch_bounds__(CG_THREADS) k_mg_smooth(Level lv, const double* __restrict__ x_in,
     const double* __restrict__ b, double* __restrict__ x_out, BandScalars* __restrict__ scal, int slot)
 {
     __shared__ double sp[TILE_H + 2][SP];
@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(256) k_mg_smooth(Level lv, const double* __res
 }
 
 // t = b - A x on the unknowns of the level
-__global__ void __launch_bounds__(256) k_mg_residual(Level lv, const double* __restrict__ x,
+__global__ void __launch_bounds__(CG_THREADS) k_mg_residual(Level lv, const double* __restrict__ x,
     const double* __restrict__ b, double* __restrict__ t, const BandScalars* __restrict__ scal)
 {
     __shared__ double sp[TILE_H + 2][SP];
@@ -236,7 +236,7 @@ __global__ void __launch_bounds__(256) k_mg_residual(Level lv, const double* __r
 
 // b_c(I, J) = sum_{di, dj in -1..1} w(di) w(dj) t_f(2I + di, 2J + dj),  w = (1/2, 1, 1/2)  (= P^T t_f).
 // Runs over the active tiles of the COARSE level.
-__global__ void __launch_bounds__(256) k_mg_restrict(Level lc, Level lf, const double* __restrict__ tf,
+__global__ void __launch_bounds__(CG_THREADS) k_mg_restrict(Level lc, Level lf, const double* __restrict__ tf,
     double* __restrict__ bc, const BandScalars* __restrict__ scal)
 {
     if (scal[blockIdx.y].done)
@@ -261,7 +261,7 @@ __global__ void __launch_bounds__(256) k_mg_restrict(Level lc, Level lf, const d
 }
 
 // x_f += P e_c (bilinear), on the unknowns of the fine level.  Runs over the active tiles of the FINE level.
-__global__ void __launch_bounds__(256) k_mg_prolong(Level lf, Level lc, double* __restrict__ xf,
+__global__ void __launch_bounds__(CG_THREADS) k_mg_prolong(Level lf, Level lc, double* __restrict__ xf,
     const double* __restrict__ ec, const BandScalars* __restrict__ scal)
 {
     if (scal[blockIdx.y].done)

@@ -28,7 +28,7 @@ __device__ __forceinline__ double block_sum(double v, double* s_red /* 8 doubles
     double t = 0.0;
     if (threadIdx.y == 0) {
         t = threadIdx.x < CG_BLOCK_Y ? s_red[threadIdx.x] : 0.0;
-        for (int o = 4; o; o >>= 1)
+        for (int o = CG_BLOCK_Y / 2; o; o >>= 1)
             t += __shfl_xor_sync(0xffffffffu, t, o);
     }
     return t;  // valid in thread (0, 0)
@@ -49,16 +49,18 @@ __device__ __forceinline__ void stage_tile(double (*sp)[SP], const uint8_t* __re
 #pragma unroll
     for (int j = 0; j < ROWS_PER_THREAD; ++j)
         m[j] = umask[(r0 + threadIdx.y + j * CG_BLOCK_Y) * pitch + c0 + threadIdx.x];
+    // 4 x 32 halo cells: edge e = 0 top, 1 bottom, 2 left, 3 right; HALO_PER_THREAD of them per thread
+    constexpr int HALO_PER_THREAD = (128 + CG_THREADS - 1) / CG_THREADS;
     int t = threadIdx.y * CG_BLOCK_X + threadIdx.x;
-    int hr = 0, hc = 0;
-    uint8_t hm = 0;
-    if (t < 128) {
-        int e = t >> 5, i = t & 31;
-        if (e == 0) { hr = -1; hc = i; }
-        else if (e == 1) { hr = TILE_H; hc = i; }
-        else if (e == 2) { hr = i; hc = -1; }
-        else { hr = i; hc = TILE_W; }
-        hm = umask[(r0 + hr) * pitch + c0 + hc];
+    int hr[HALO_PER_THREAD], hc[HALO_PER_THREAD];
+    uint8_t hm[HALO_PER_THREAD];
+#pragma unroll
+    for (int k = 0; k < HALO_PER_THREAD; ++k) {
+        int h = t + k * CG_THREADS;
+        int e = h >> 5, i = h & 31;
+        hr[k] = e == 0 ? -1 : (e == 1 ? TILE_H : i);
+        hc[k] = e == 2 ? -1 : (e == 3 ? TILE_W : i);
+        hm[k] = h < 128 ? umask[(r0 + hr[k]) * pitch + c0 + hc[k]] : 0;
     }
 #pragma unroll
     for (int j = 0; j < ROWS_PER_THREAD; ++j) {
@@ -66,9 +68,12 @@ __device__ __forceinline__ void stage_tile(double (*sp)[SP], const uint8_t* __re
         int64_t r = r0 + lr, c = c0 + threadIdx.x;
         sp[lr + 1][threadIdx.x + 1] = m[j] ? f(r * pitch + c, r, c, true) : 0.0;
     }
-    if (t < 128) {
-        int64_t r = r0 + hr, c = c0 + hc;
-        sp[hr + 1][hc + 1] = hm ? f(r * pitch + c, r, c, false) : 0.0;
+#pragma unroll
+    for (int k = 0; k < HALO_PER_THREAD; ++k) {
+        if (t + k * CG_THREADS < 128) {
+            int64_t r = r0 + hr[k], c = c0 + hc[k];
+            sp[hr[k] + 1][hc[k] + 1] = hm[k] ? f(r * pitch + c, r, c, false) : 0.0;
+        }
     }
 }
 
