@@ -248,14 +248,15 @@ def run_b200(args, w):
     launches0 = ctx.kernel_launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
-    kms = [0.0] * 4
-    kn = [0] * 4
-    ku = [0] * 4
+    NK = 6
+    kms = [0.0] * NK
+    kn = [0] * NK
+    ku = [0] * NK
     iters = []
     for _ in range(args.steps):
         st = step()
         iters.append(max(s["iterations"] for s in st))
-        for c in range(4):
+        for c in range(NK):
             kms[c] += st[0]["kernel_ms"][c]
             kn[c] += st[0]["kernel_launches"][c]
             ku[c] += st[0]["kernel_units"][c]
@@ -277,13 +278,15 @@ def run_b200(args, w):
     value = total_units * args.steps / (ms_max * 1e-3)
 
     # ---- roofline of the dominant kernel (by accumulated event time inside the timed region)
-    names = ["cg_direction (k_direction)", "cg_update (k_update)", "mg_smooth (k_smooth)", "mg_transfer"]
+    names = ["cg_direction (k_direction)", "cg_update (k_update)", "mg_sweep (k_mg_smooth)",
+             "mg_transfer (k_mg_residual/restrict/prolong)", "mg_down (k_mg_down)", "mg_up (k_mg_up)"]
     # algorithmic bytes per fine-grid unknown and launch (DESIGN.md "Algorithmic bytes"):
     #   direction: R z|r 8 + R p 8 + W p 8 + R mask 1 = 25; update: R p 8 + R x 8 + R r 8 + W x 8 + W r 8 + R mask 1 = 41
     #   smoother sweep (level l holds ~ n / 4^l unknowns; summed over the launches of all levels it is counted with
     #   the unknowns of the level it ran on): R x 8 + R b 8 + W x 8 + R mask 1 = 25
-    bytes_per_unknown = [25.0, 41.0, 25.0, 19.0]
-    dom = max(range(4), key=lambda c: kms[c])
+    #   fused descent: R b 8 + W x 8 + W coarse b 8/4 = 18; fused ascent: R x 8 + R b 8 + R coarse e 8/4 + W x 8 = 26
+    bytes_per_unknown = [25.0, 41.0, 25.0, 19.0, 18.0, 26.0]
+    dom = max(range(NK), key=lambda c: kms[c])
     peak, peak_src = peaks()
     roof = None
     if kn[dom] > 0 and kms[dom] > 0:
@@ -298,7 +301,7 @@ def run_b200(args, w):
                 "bytes_per_unknown": bytes_per_unknown[dom],
                 "all_kernels": {names[c]: {"ms": kms[c], "launches": kn[c],
                                            "GBps": (bytes_per_unknown[c] * ku[c] / (kms[c] * 1e-3) / 1e9) if kms[c] else None}
-                                for c in range(4)}}  # fmt: skip
+                                for c in range(NK)}}  # fmt: skip
 
     # ---- end to end through the host-pointer C-ABI entry point (the resident scene is released first: the host-pointer
     # entry point keeps its own scene, and two 13-band scenes with solver work space do not fit one GPU together)

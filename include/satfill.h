@@ -62,11 +62,13 @@ typedef struct sa_options {
     double tolerance;       /* stop when |b_U - A_UU x|_2 <= tolerance * |b_U|_2 on the reduced system          */
     int64_t max_iterations; /* <= 0: reference default (Laplace 2n, Poisson n/2 with n = unknowns)              */
     int32_t precond;        /* sa_precond                                                                        */
-    int32_t check_every;    /* host polls the device-side convergence flags every this many iterations          */
+    int32_t check_every;    /* host polls the device-side convergence flags every this many iterations; <= 0:
+                             * automatic (32 for Jacobi, 1 for multigrid)                                         */
     int32_t mg_levels;      /* multigrid: maximum number of levels (<= 0: automatic)                             */
     int32_t mg_smooth;      /* multigrid: pre = post smoothing sweeps                                            */
     int32_t profile;        /* != 0: time every solver kernel with CUDA events (sa_stats.kernel_ms)              */
-    int32_t reserved[3];
+    int32_t mg_unfused;     /* != 0: run the V-cycle one sweep per kernel (reference path of the fused kernels)  */
+    int32_t reserved[2];
 } sa_options;
 
 /* Per-band solve record (superset of approx::PerfInfo, poisson.h:12-21). */
@@ -81,13 +83,14 @@ typedef struct sa_stats {
     int32_t status;         /* sa_status of this band                                                           */
     int32_t active_tiles;   /* tiles of the block-sparse layout that contain an unknown                         */
     /* sa_options.profile: summed CUDA-event durations and launch counts of the solver kernels of the whole batch,
-     * by class: 0 = CG direction (p update + p.Ap), 1 = CG update (x, r, norms), 2 = multigrid smoother,
-     * 3 = multigrid transfer (residual + restriction, prolongation + correction) */
-    double kernel_ms[4];
-    int64_t kernel_launches[4];
+     * by class: 0 = CG direction (p update + p.Ap), 1 = CG update (x, r, norms), 2 = multigrid single sweeps,
+     * 3 = multigrid single transfers (residual, restriction, prolongation), 4 = fused multigrid descent
+     * (pre-smoothing + residual + restriction), 5 = fused multigrid ascent (prolongation + post-smoothing) */
+    double kernel_ms[6];
+    int64_t kernel_launches[6];
     /* unknowns x bands summed over the launches of each class (a multigrid launch on level l counts the unknowns of
      * level l): algorithmic bytes of a class = bytes per unknown x kernel_units */
-    int64_t kernel_units[4];
+    int64_t kernel_units[6];
 } sa_stats;
 
 /* ---- context ------------------------------------------------------------------------------------------------ */

@@ -79,7 +79,7 @@ class SolveStats(dict):
 
 # Solver knobs the reference does not expose on its Python surface.  `None` = the reference's own behaviour
 # (Laplace: Eigen defaults, epsilon tolerance / 2N iterations, laplace.cpp:113-114).
-_defaults = {"laplace_tolerance": None, "laplace_max_iterations": None, "precond": JACOBI, "check_every": 32}
+_defaults = {"laplace_tolerance": None, "laplace_max_iterations": None, "precond": JACOBI, "check_every": None}
 _last_perf: list[SolveStats] = []
 
 
@@ -154,7 +154,7 @@ class Context:
         self._check(self._lib.sa_synchronize(self._h))
 
     def options(self, problem: int, tolerance=None, max_iterations=None, precond=None, check_every=None,
-                mg_levels=None, mg_smooth=None, profile=None) -> _capi.Options:  # fmt: skip
+                mg_levels=None, mg_smooth=None, profile=None, mg_unfused=None) -> _capi.Options:  # fmt: skip
         o = _capi.Options()
         self._lib.sa_default_options(C.byref(o), problem)
         if tolerance is not None:
@@ -171,6 +171,8 @@ class Context:
             o.mg_smooth = int(mg_smooth)
         if profile is not None:
             o.profile = int(bool(profile))
+        if mg_unfused is not None:
+            o.mg_unfused = int(bool(mg_unfused))
         return o
 
     # ---- integer path -----------------------------------------------------------------------------------------

@@ -47,7 +47,8 @@ class Options(C.Structure):
         ("mg_levels", C.c_int32),
         ("mg_smooth", C.c_int32),
         ("profile", C.c_int32),
-        ("reserved", C.c_int32 * 3),
+        ("mg_unfused", C.c_int32),
+        ("reserved", C.c_int32 * 2),
     ]
 
 
@@ -62,9 +63,9 @@ class Stats(C.Structure):
         ("setup_ms", C.c_double),
         ("status", C.c_int32),
         ("active_tiles", C.c_int32),
-        ("kernel_ms", C.c_double * 4),
-        ("kernel_launches", C.c_int64 * 4),
-        ("kernel_units", C.c_int64 * 4),
+        ("kernel_ms", C.c_double * 6),
+        ("kernel_launches", C.c_int64 * 6),
+        ("kernel_units", C.c_int64 * 6),
     ]
 
     def as_dict(self) -> dict:

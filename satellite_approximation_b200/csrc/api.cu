@@ -89,6 +89,11 @@ int scene_alloc(sa_scene* s, bool transposed)
     SA_CUDA(ctx, cudaMemsetAsync(s->mask, 0, (size_t)s->plane, ctx->stream));
     SA_CUDA(ctx, cudaMemsetAsync(s->umask, 0, (size_t)s->plane, ctx->stream));
     SA_CUDA(ctx, cudaMalloc(&s->tile_list, sizeof(int32_t) * 2 * (size_t)s->tiles_x * s->tiles_y));
+    {
+        size_t words = (size_t)(s->tiles_x + 2) * (s->tiles_y + 2) * 32;
+        SA_CUDA(ctx, cudaMalloc(&s->tbits, words * sizeof(uint32_t)));
+        SA_CUDA(ctx, cudaMemsetAsync(s->tbits, 0, words * sizeof(uint32_t), ctx->stream));
+    }
     SA_CUDA(ctx, cudaMalloc(&s->d_counters, sizeof(int32_t) * 4));
     SA_CUDA(ctx, cudaMalloc(&s->d_count64, sizeof(unsigned long long)));
     SA_CUDA(ctx, cudaMalloc(&s->scal, sizeof(BandScalars) * s->nbands));
@@ -167,6 +172,7 @@ void scene_free(sa_scene* s)
     cudaFree(s->mask);
     cudaFree(s->umask);
     cudaFree(s->tile_list);
+    cudaFree(s->tbits);
     cudaFree(s->d_counters);
     cudaFree(s->d_count64);
     cudaFree(s->scal);
@@ -261,7 +267,7 @@ void sa_default_options(sa_options* o, int problem)
     o->tolerance = problem == SA_POISSON ? 1e-6 : DBL_EPSILON;
     o->max_iterations = 0;
     o->precond = SA_PRECOND_JACOBI;
-    o->check_every = 32;
+    o->check_every = 0;
     o->mg_levels = 0;
     o->mg_smooth = 2;
 }

@@ -284,6 +284,8 @@ Level fine_level(const sa_scene* s)
     lv.umask = s->mask0(s->umask);
     lv.tile_list = s->tile_list;
     lv.fixed_diag = s->problem == SA_LAPLACE;
+    lv.tbits = s->tbits;
+    lv.tb_stride = s->tiles_x + 2;
     return lv;
 }
 

@@ -60,6 +60,11 @@ struct Level {
     const uint8_t* umask; // 1 = unknown of the linear system; addressed like a plane (pitch bytes per row)
     const int32_t* tile_list;
     int fixed_diag;       // != 0: the diagonal is 4 everywhere (Laplace: unknowns never touch the image border)
+    // The same unknown set as one 32-bit word per tile row: word [((ty + 1) * tb_stride + tx + 1) * 32 + row], bit = col.
+    // A ring of all-zero tiles surrounds the grid, so neighbourhoods of any tile can be read without bounds checks.
+    // 128 B per tile: small enough to stay resident in L2 across kernels (15 MB for a 10980^2 scene).
+    const uint32_t* tbits;
+    int tb_stride;        // tiles_x + 2
 };
 
 }  // namespace satfill
@@ -83,6 +88,7 @@ struct sa_level_store {
     uint8_t* umask_alloc = nullptr;    // base of the allocation (guard row included)
     int32_t* tile_list = nullptr;      // 2 * tiles entries: list, then per-tile flags
     int32_t* d_counters = nullptr;     // {active tiles, first, last, -}
+    uint32_t* tbits = nullptr;
     int64_t rows_p = 0;
     double* x = nullptr;               // coarse levels: correction; nbands planes (allocation base)
     double* b = nullptr;               // coarse levels: restricted residual
@@ -112,6 +118,7 @@ struct sa_scene {
     uint8_t* mask = nullptr;   // normalised 0/1 invalid mask (allocation base)
     uint8_t* umask = nullptr;  // unknown set (allocation base)
     int32_t* tile_list = nullptr;
+    uint32_t* tbits = nullptr;  // tile-row bit masks of umask (Level::tbits)
     int32_t* d_counters = nullptr;
     unsigned long long* d_count64 = nullptr;
     satfill::BandScalars* scal = nullptr;
@@ -161,7 +168,7 @@ inline int fail(sa_ctx* ctx, int status, const std::string& msg)
 inline int64_t round_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
 
 // Kernel classes reported in sa_stats.kernel_ms / kernel_launches when sa_options.profile is set.
-enum KernelClass { KC_DIRECTION = 0, KC_UPDATE = 1, KC_SMOOTH = 2, KC_TRANSFER = 3, KC_COUNT = 4 };
+enum KernelClass { KC_DIRECTION = 0, KC_UPDATE = 1, KC_SMOOTH = 2, KC_TRANSFER = 3, KC_MG_DOWN = 4, KC_MG_UP = 5, KC_COUNT = 6 };
 
 // Brackets individual launches with CUDA events on the launching stream; the pairs are resolved after the next
 // stream synchronisation (flush).  Off unless profiling was requested: the events cost ~1 us of launch gap each.
@@ -171,9 +178,9 @@ struct KernelTimer {
     size_t used = 0;
     struct Pending { int cls; size_t e0; };
     std::vector<Pending> pending;
-    double ms[KC_COUNT] = { 0, 0, 0, 0 };
-    int64_t n[KC_COUNT] = { 0, 0, 0, 0 };
-    int64_t units[KC_COUNT] = { 0, 0, 0, 0 };
+    double ms[KC_COUNT] = {};
+    int64_t n[KC_COUNT] = {};
+    int64_t units[KC_COUNT] = {};
 
     cudaEvent_t take()
     {
@@ -237,6 +244,12 @@ int device_label_components(sa_ctx* ctx, const uint8_t* mask, int64_t rows, int6
 int ensure_indexed(sa_scene* s);
 int solve_scene(sa_scene* s, const sa_options& o, sa_stats* stats);
 Level fine_level(const sa_scene* s);
+
+// ---- mg_fused.cu -------------------------------------------------------------------------------------------------
+int launch_mg_down(sa_ctx* ctx, const Level& lf, const Level& lc, int nbands, const double* b, double* x_out, double* bc,
+    const BandScalars* scal);
+int launch_mg_up(sa_ctx* ctx, const Level& lf, const Level& lc, int nbands, const double* x_in, const double* b,
+    const double* ec, double* x_out, BandScalars* scal, int rz_slot);
 
 // ---- mg.cu -----------------------------------------------------------------------------------------------------
 int build_hierarchy(sa_scene* s, const sa_options& o);

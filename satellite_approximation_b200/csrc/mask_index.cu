@@ -59,7 +59,7 @@ int transpose_i32(sa_ctx* ctx, const int32_t* s, int64_t r, int64_t c, int64_t s
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(CG_THREADS) k_build_unknown_set(uint8_t* __restrict__ mask, uint8_t* __restrict__ umask,
     int64_t rows, int64_t cols, int64_t pitch, int tiles_x, int laplace, int32_t* __restrict__ tile_flags,
-    unsigned long long* __restrict__ count64)
+    unsigned long long* __restrict__ count64, uint32_t* __restrict__ tbits)
 {
     __shared__ int warp_cnt[CG_BLOCK_Y];
     int tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x;
@@ -78,6 +78,9 @@ __global__ void __launch_bounds__(CG_THREADS) k_build_unknown_set(uint8_t* __res
         mask[r * pitch + c] = m;
         umask[r * pitch + c] = um;
         cnt += um;
+        unsigned word = __ballot_sync(0xffffffffu, um);
+        if (threadIdx.x == 0)
+            tbits[((size_t)(ty + 1) * (tiles_x + 2) + tx + 1) * 32 + threadIdx.y + j * CG_BLOCK_Y] = word;
     }
     for (int o = 16; o; o >>= 1)
         cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
@@ -150,7 +153,7 @@ int index_scene(sa_scene* s)
     SA_CUDA(ctx, cudaMemsetAsync(s->d_count64, 0, sizeof(unsigned long long), ctx->stream));
     dim3 block(CG_BLOCK_X, CG_BLOCK_Y);
     SA_LAUNCH(ctx, k_build_unknown_set, n_tiles, block, 0, s->mask0(s->mask), s->mask0(s->umask), s->rows, s->cols,
-        s->pitch, s->tiles_x, s->problem == SA_LAPLACE ? 1 : 0, flags, s->d_count64);
+        s->pitch, s->tiles_x, s->problem == SA_LAPLACE ? 1 : 0, flags, s->d_count64, s->tbits);
     SA_CUDA(ctx, cudaGetLastError());
     SA_TRY(compact_tile_flags(ctx, flags, n_tiles, s->tile_list, s->d_counters));
     struct readback {

@@ -31,7 +31,7 @@ __device__ __forceinline__ double lv_diag(const Level& lv, int64_t r, int64_t c)
 // coarse umask(I, J) = fine umask(2I, 2J); per-tile activity flags and unknown count.  One CTA per coarse tile.
 __global__ void __launch_bounds__(CG_THREADS) k_coarsen_mask(const uint8_t* __restrict__ fmask, int64_t fpitch,
     uint8_t* __restrict__ cmask, int64_t crows, int64_t ccols, int64_t cpitch, int tiles_x,
-    int32_t* __restrict__ tile_flags, unsigned long long* __restrict__ count64)
+    int32_t* __restrict__ tile_flags, unsigned long long* __restrict__ count64, uint32_t* __restrict__ tbits)
 {
     __shared__ int warp_cnt[CG_BLOCK_Y];
     int tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x;
@@ -45,6 +45,9 @@ __global__ void __launch_bounds__(CG_THREADS) k_coarsen_mask(const uint8_t* __re
             m = fmask[2 * r * fpitch + 2 * c];
         cmask[r * cpitch + c] = m;
         cnt += m;
+        unsigned word = __ballot_sync(0xffffffffu, m);
+        if (threadIdx.x == 0)
+            tbits[((size_t)(ty + 1) * (tiles_x + 2) + tx + 1) * 32 + threadIdx.y + j * CG_BLOCK_Y] = word;
     }
     for (int o = 16; o; o >>= 1)
         cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
@@ -67,6 +70,7 @@ void free_hierarchy(sa_scene* s)
         cudaFree(L.umask_alloc);
         cudaFree(L.tile_list);
         cudaFree(L.d_counters);
+        cudaFree(L.tbits);
         cudaFree(L.x);
         cudaFree(L.b);
         cudaFree(L.t);
@@ -104,8 +108,13 @@ static int alloc_hierarchy(sa_scene* s, const sa_options& o)
         SA_CUDA(ctx, cudaMalloc(&L.x, vec));
         SA_CUDA(ctx, cudaMalloc(&L.b, vec));
         SA_CUDA(ctx, cudaMalloc(&L.t, vec));
+        size_t words = (size_t)(L.lv.tiles_x + 2) * (L.lv.tiles_y + 2) * 32;
+        SA_CUDA(ctx, cudaMalloc(&L.tbits, words * sizeof(uint32_t)));
+        SA_CUDA(ctx, cudaMemsetAsync(L.tbits, 0, words * sizeof(uint32_t), ctx->stream));
         L.lv.umask = L.umask_alloc + L.lv.pitch;
         L.lv.tile_list = L.tile_list;
+        L.lv.tbits = L.tbits;
+        L.lv.tb_stride = L.lv.tiles_x + 2;
         s->coarse.push_back(L);
         rows = crows;
         cols = ccols;
@@ -128,7 +137,7 @@ int build_hierarchy(sa_scene* s, const sa_options& o)
         SA_CUDA(ctx, cudaMemsetAsync(L.d_counters, 0, sizeof(int32_t) * 4 + sizeof(unsigned long long), ctx->stream));
         uint8_t* cmask = L.umask_alloc + L.lv.pitch;
         SA_LAUNCH(ctx, k_coarsen_mask, n_tiles, block, 0, fmask, fpitch, cmask, L.lv.rows, L.lv.cols, L.lv.pitch,
-            L.lv.tiles_x, flags, count64);
+            L.lv.tiles_x, flags, count64, L.tbits);
         SA_TRY(compact_tile_flags(ctx, flags, n_tiles, L.tile_list, L.d_counters));
         size_t vec = (size_t)L.lv.plane * s->nbands * sizeof(double);
         SA_CUDA(ctx, cudaMemsetAsync(L.x, 0, vec, ctx->stream));
@@ -357,8 +366,15 @@ int apply_vcycle(sa_scene* s, const sa_options& o, KernelTimer& kt, int rz_slot,
         return SA_OK;
     };
 
+    const bool fused = nu == 2 && !o.mg_unfused;
     // descend
     for (int l = 0; l < nl - 1; ++l) {
+        if (fused) {
+            kt.begin(KC_MG_DOWN, L[l].units);
+            SA_TRY(launch_mg_down(ctx, L[l].lv, L[l + 1].lv, nb, L[l].b, L[l].x, L[l + 1].b, scal));
+            kt.end();
+            continue;
+        }
         SA_TRY(smooth(l, nu, true, -1));
         LevelVecs& F = L[l];
         LevelVecs& C = L[l + 1];
@@ -380,6 +396,15 @@ int apply_vcycle(sa_scene* s, const sa_options& o, KernelTimer& kt, int rz_slot,
     for (int l = nl - 2; l >= 0; --l) {
         LevelVecs& F = L[l];
         LevelVecs& C = L[l + 1];
+        if (fused) {
+            kt.begin(KC_MG_UP, F.units);
+            SA_TRY(launch_mg_up(ctx, F.lv, C.lv, nb, F.x, F.b, C.x, F.t, scal, l == 0 ? rz_slot : -1));
+            kt.end();
+            double* tmp = F.x;  // the result sits in t: swap the level's buffers
+            F.x = F.t;
+            F.t = tmp;
+            continue;
+        }
         dim3 gf((unsigned)F.lv.n_tiles, (unsigned)nb);
         kt.begin(KC_TRANSFER, F.units);
         SA_LAUNCH(ctx, k_mg_prolong, gf, block, 0, F.lv, C.lv, F.x, C.x, scal);

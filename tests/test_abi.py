@@ -44,7 +44,7 @@ def test_struct_layouts_match_header():
     from satellite_approximation_b200 import _capi
 
     assert ctypes.sizeof(_capi.Options) == 8 + 8 + 4 * 4 + 16
-    assert ctypes.sizeof(_capi.Stats) == 8 * 3 + 8 * 4 + 4 * 2 + 8 * 4 + 8 * 4 + 8 * 4
+    assert ctypes.sizeof(_capi.Stats) == 8 * 3 + 8 * 4 + 4 * 2 + 3 * 8 * 6
     lib = _capi.load()
     o = _capi.Options()
     lib.sa_default_options(ctypes.byref(o), _capi.SA_POISSON)
