@@ -162,15 +162,21 @@ __global__ void __launch_bounds__(CG_THREADS) k_direction(Level lv, const double
     const double* pb = p_old + boff;
     double* pn = p_new + boff;
     int64_t rows = lv.rows, cols = lv.cols;
-    stage_tile(sp, lv.umask, r0, c0, lv.pitch, [&](int64_t idx, int64_t r, int64_t c, bool interior) {
-        double z = zb[idx];
-        if (JACOBI)
-            z *= inv_diag(r, c, rows, cols);
-        double v = z + beta * pb[idx];  // ConjugateGradient.h:80
-        if (interior)
-            pn[idx] = v;
-        return v;
-    });
+    stage_tile<2>(
+        sp, lv.umask, r0, c0, lv.pitch,
+        [&](int64_t idx, double* v) {
+            v[0] = zb[idx];
+            v[1] = pb[idx];
+        },
+        [&](const double* v, int64_t idx, int64_t r, int64_t c, bool interior) {
+            double z = v[0];
+            if (JACOBI)
+                z *= inv_diag(r, c, rows, cols);
+            double pv = z + beta * v[1];  // ConjugateGradient.h:80
+            if (interior)
+                pn[idx] = pv;
+            return pv;
+        });
     __syncthreads();
     double acc = 0.0;
 #pragma unroll
@@ -205,21 +211,35 @@ __global__ void __launch_bounds__(CG_THREADS) k_update(Level lv, double* __restr
     double* ub = u + boff;
     double* rb = rvec + boff;
     int64_t rows = lv.rows, cols = lv.cols;
-    stage_tile(sp, lv.umask, r0, c0, lv.pitch, [&](int64_t idx, int64_t, int64_t, bool) { return pb[idx]; });
+    // x and r of the thread's own cells: issued before the staging of p so that all loads are in flight together
+    const int64_t base = (r0 + threadIdx.y) * lv.pitch + c0 + threadIdx.x;
+    const int64_t rstep = (int64_t)CG_BLOCK_Y * lv.pitch;
+    uint8_t m[ROWS_PER_THREAD];
+    double xv[ROWS_PER_THREAD], rv[ROWS_PER_THREAD];
+#pragma unroll
+    for (int j = 0; j < ROWS_PER_THREAD; ++j)
+        m[j] = lv.umask[base + j * rstep];
+#pragma unroll
+    for (int j = 0; j < ROWS_PER_THREAD; ++j) {
+        xv[j] = m[j] ? ub[base + j * rstep] : 0.0;
+        rv[j] = m[j] ? rb[base + j * rstep] : 0.0;
+    }
+    stage_tile<1>(
+        sp, lv.umask, r0, c0, lv.pitch, [&](int64_t idx, double* v) { v[0] = pb[idx]; },
+        [&](const double* v, int64_t, int64_t, int64_t, bool) { return v[0]; });
     __syncthreads();
     double r2 = 0.0, rz = 0.0;
 #pragma unroll
     for (int j = 0; j < ROWS_PER_THREAD; ++j) {
         int lr = threadIdx.y + j * CG_BLOCK_Y + 1, lc = threadIdx.x + 1;
-        int64_t r = r0 + lr - 1, c = c0 + lc - 1;
-        int64_t idx = r * lv.pitch + c;
-        if (lv.umask[idx]) {
+        if (m[j]) {
+            int64_t r = r0 + lr - 1, c = c0 + lc - 1;
             double pc = sp[lr][lc];
             double d = diag_of(r, c, rows, cols);
             double q = d * pc - (sp[lr - 1][lc] + sp[lr + 1][lc] + sp[lr][lc - 1] + sp[lr][lc + 1]);
-            ub[idx] += alpha * pc;                // ConjugateGradient.h:69
-            double rn = rb[idx] - alpha * q;      // ConjugateGradient.h:70
-            rb[idx] = rn;
+            ub[base + j * rstep] = xv[j] + alpha * pc;  // ConjugateGradient.h:69
+            double rn = rv[j] - alpha * q;               // ConjugateGradient.h:70
+            rb[base + j * rstep] = rn;
             r2 += rn * rn;
             if (JACOBI)
                 rz += rn * rn * inv_diag(r, c, rows, cols);

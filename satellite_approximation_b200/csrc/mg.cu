@@ -184,7 +184,9 @@ __global__ void __launch_bounds__(CG_THREADS) k_mg_smooth(Level lv, const double
     double* xo = x_out + boff;
     if (!FIRST) {
         const double* xi = x_in + boff;
-        stage_tile(sp, lv.umask, r0, c0, lv.pitch, [&](int64_t idx, int64_t, int64_t, bool) { return xi[idx]; });
+        stage_tile<1>(
+            sp, lv.umask, r0, c0, lv.pitch, [&](int64_t idx, double* v) { v[0] = xi[idx]; },
+            [&](const double* v, int64_t, int64_t, int64_t, bool) { return v[0]; });
         __syncthreads();
     }
     double acc = 0.0;
@@ -227,7 +229,9 @@ __global__ void __launch_bounds__(CG_THREADS) k_mg_residual(Level lv, const doub
     int64_t r0 = (int64_t)(tile / lv.tiles_x) * TILE_H, c0 = (int64_t)(tile % lv.tiles_x) * TILE_W;
     int64_t boff = (int64_t)blockIdx.y * lv.plane;
     const double* xb = x + boff;
-    stage_tile(sp, lv.umask, r0, c0, lv.pitch, [&](int64_t idx, int64_t, int64_t, bool) { return xb[idx]; });
+    stage_tile<1>(
+        sp, lv.umask, r0, c0, lv.pitch, [&](int64_t idx, double* v) { v[0] = xb[idx]; },
+        [&](const double* v, int64_t, int64_t, int64_t, bool) { return v[0]; });
     __syncthreads();
 #pragma unroll
     for (int j = 0; j < ROWS_PER_THREAD; ++j) {

@@ -74,21 +74,28 @@ __global__ void __launch_bounds__(FTHREADS) k_mg_down(Level lf, Level lc, const 
     load_region_mask<H>(lf, ty, tx, mrow, t);
     __syncthreads();
     const int64_t gc = c0 - H + x;  // global column of this thread
-    const double* bb = b + (int64_t)blockIdx.y * lf.plane + (r0 - H) * lf.pitch + gc;
-    if (x < W) {
+    {
+        // all loads of the thread are issued back to back (predicated, no branches) before any of them is used
+        constexpr int NK = (W + FY - 1) / FY;
+        const double* bp = b + (int64_t)blockIdx.y * lf.plane + (r0 - H + y) * lf.pitch + gc;
+        const int64_t step = (int64_t)FY * lf.pitch;
+        double v[NK];
 #pragma unroll
-        for (int k = 0; k < (W + FY - 1) / FY; ++k) {
+        for (int k = 0; k < NK; ++k) {
             int row = y + k * FY;
-            if (row < W) {
-                double v = 0.0, x1 = 0.0;
-                if ((mrow[row] >> x) & 1) {
+            bool on = x < W && row < W && ((mrow[row < W ? row : 0] >> x) & 1);
+            v[k] = on ? bp[k * step] : 0.0;
+        }
+        if (x < W) {
+#pragma unroll
+            for (int k = 0; k < NK; ++k) {
+                int row = y + k * FY;
+                if (row < W) {
                     double d, inv;
                     diag_pair<FIXED>(lf, r0 - H + row, gc, d, inv);
-                    v = bb[row * lf.pitch];
-                    x1 = FW * inv * v;
+                    B[row * S + x] = v[k];
+                    X1[row * S + x] = FW * inv * v[k];
                 }
-                B[row * S + x] = v;
-                X1[row * S + x] = x1;
             }
         }
     }
@@ -186,24 +193,35 @@ __global__ void __launch_bounds__(FTHREADS) k_mg_up(Level lf, Level lc, const do
     __syncthreads();
     const int64_t gc = c0 - H + x;
     const int64_t boff = (int64_t)blockIdx.y * lf.plane + (r0 - H) * lf.pitch + gc;
-    const double* xi = x_in + boff;
-    const double* bb = b + boff;
-    if (x < W) {  // x + P e on the 36 x 36 region, b on the inner 34 x 34
-        const int ej = x >> 1, oj = x & 1;  // c0 - 2 is even: parity of the local index = global parity
+    {
+        // x + P e on the 36 x 36 region, b on the inner 34 x 34; loads first (predicated, back to back), then use
+        constexpr int NK = W / FY;
+        const double* xp = x_in + boff + (int64_t)y * lf.pitch;
+        const double* bp = b + boff + (int64_t)y * lf.pitch;
+        const int64_t step = (int64_t)FY * lf.pitch;
+        double xv[NK], bv[NK];
 #pragma unroll
-        for (int k = 0; k < W / FY; ++k) {
+        for (int k = 0; k < NK; ++k) {
             int row = y + k * FY;
-            double v = 0.0, bv = 0.0;
-            if ((mrow[row] >> x) & 1) {
-                const double* p = E + (row >> 1) * ES + ej;
-                int oi = (row & 1) * ES;
-                double pe = 0.25 * ((p[0] + p[oj]) + (p[oi] + p[oi + oj]));  // bilinear, branch free
-                v = xi[row * lf.pitch] + pe;
-                if (row >= 1 && row < W - 1 && x >= 1 && x < W - 1)
-                    bv = bb[row * lf.pitch];
+            bool on = x < W && ((mrow[row] >> x) & 1);
+            bool inner = on && row >= 1 && row < W - 1 && x >= 1 && x < W - 1;
+            xv[k] = on ? xp[k * step] : 0.0;
+            bv[k] = inner ? bp[k * step] : 0.0;
+        }
+        if (x < W) {
+            const int ej = x >> 1, oj = x & 1;  // c0 - 2 is even: parity of the local index = global parity
+#pragma unroll
+            for (int k = 0; k < NK; ++k) {
+                int row = y + k * FY;
+                double v = 0.0;
+                if ((mrow[row] >> x) & 1) {
+                    const double* p = E + (row >> 1) * ES + ej;
+                    int oi = (row & 1) * ES;
+                    v = xv[k] + 0.25 * ((p[0] + p[oj]) + (p[oi] + p[oi + oj]));  // bilinear, branch free
+                }
+                X[row * S + x] = v;
+                Bv[row * S + x] = bv[k];
             }
-            X[row * S + x] = v;
-            Bv[row * S + x] = bv;
         }
     }
     __syncthreads();

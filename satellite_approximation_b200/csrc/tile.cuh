@@ -34,26 +34,28 @@ __device__ __forceinline__ double block_sum(double v, double* s_red /* 8 doubles
     return t;  // valid in thread (0, 0)
 }
 
-// Stage the 34 x 34 neighbourhood of a tile in shared memory.  `f(idx, r, c, interior)` yields the value of the staged
-// vector at plane offset idx; it is evaluated for the 32 x 32 interior (coalesced 256 B rows) and the 4 x 32 halo
-// cells, but ONLY at cells of the unknown set: every staged vector is zero elsewhere by construction, so the loads
-// of known cells are predicated off and their 32-byte sectors never leave HBM (tiles are ~50 % known cells on
-// cloud-like masks).  The mask bytes are read first so that the predicated loads can all be in flight together.
+// Stage the 34 x 34 neighbourhood of a tile in shared memory.  For each staged cell, `load(idx, v)` reads NV values
+// (plane offset idx) and `combine(v, idx, r, c, interior)` turns them into the staged value.  The 32 x 32 interior is
+// read as coalesced 256 B rows, plus 4 x 32 halo cells -- but ONLY at cells of the unknown set: every staged vector is
+// zero elsewhere by construction, so the loads of known cells are predicated off and their 32-byte sectors never
+// leave HBM (tiles are ~50 % known cells on cloud-like masks).  The schedule is: all mask bytes, then ALL loads of the
+// thread back to back (predicated, branch free), then the combines -- a load that sits in the same branch as its use
+// serialises the thread on one HBM round trip per cell.
 constexpr int SP = TILE_W + 3;  // padded row length of the staged tile (odd multiple keeps 8-byte banks spread)
 
-template <typename F>
+template <int NV, typename FL, typename FC>
 __device__ __forceinline__ void stage_tile(double (*sp)[SP], const uint8_t* __restrict__ umask, int64_t r0, int64_t c0,
-    int64_t pitch, F f)
+    int64_t pitch, FL load, FC combine)
 {
-    uint8_t m[ROWS_PER_THREAD];
-#pragma unroll
-    for (int j = 0; j < ROWS_PER_THREAD; ++j)
-        m[j] = umask[(r0 + threadIdx.y + j * CG_BLOCK_Y) * pitch + c0 + threadIdx.x];
     // 4 x 32 halo cells: edge e = 0 top, 1 bottom, 2 left, 3 right; HALO_PER_THREAD of them per thread
     constexpr int HALO_PER_THREAD = (128 + CG_THREADS - 1) / CG_THREADS;
-    int t = threadIdx.y * CG_BLOCK_X + threadIdx.x;
+    const int t = threadIdx.y * CG_BLOCK_X + threadIdx.x;
+    uint8_t m[ROWS_PER_THREAD], hm[HALO_PER_THREAD];
     int hr[HALO_PER_THREAD], hc[HALO_PER_THREAD];
-    uint8_t hm[HALO_PER_THREAD];
+    const int64_t base = (r0 + threadIdx.y) * pitch + c0 + threadIdx.x;
+#pragma unroll
+    for (int j = 0; j < ROWS_PER_THREAD; ++j)
+        m[j] = umask[base + (int64_t)j * CG_BLOCK_Y * pitch];
 #pragma unroll
     for (int k = 0; k < HALO_PER_THREAD; ++k) {
         int h = t + k * CG_THREADS;
@@ -62,18 +64,34 @@ __device__ __forceinline__ void stage_tile(double (*sp)[SP], const uint8_t* __re
         hc[k] = e == 2 ? -1 : (e == 3 ? TILE_W : i);
         hm[k] = h < 128 ? umask[(r0 + hr[k]) * pitch + c0 + hc[k]] : 0;
     }
+    double v[ROWS_PER_THREAD][NV], hv[HALO_PER_THREAD][NV];
 #pragma unroll
     for (int j = 0; j < ROWS_PER_THREAD; ++j) {
-        int lr = threadIdx.y + j * CG_BLOCK_Y;
-        int64_t r = r0 + lr, c = c0 + threadIdx.x;
-        sp[lr + 1][threadIdx.x + 1] = m[j] ? f(r * pitch + c, r, c, true) : 0.0;
+#pragma unroll
+        for (int q = 0; q < NV; ++q)
+            v[j][q] = 0.0;
+        if (m[j])
+            load(base + (int64_t)j * CG_BLOCK_Y * pitch, v[j]);
     }
 #pragma unroll
     for (int k = 0; k < HALO_PER_THREAD; ++k) {
-        if (t + k * CG_THREADS < 128) {
-            int64_t r = r0 + hr[k], c = c0 + hc[k];
-            sp[hr[k] + 1][hc[k] + 1] = hm[k] ? f(r * pitch + c, r, c, false) : 0.0;
-        }
+#pragma unroll
+        for (int q = 0; q < NV; ++q)
+            hv[k][q] = 0.0;
+        if (hm[k])
+            load((r0 + hr[k]) * pitch + c0 + hc[k], hv[k]);
+    }
+#pragma unroll
+    for (int j = 0; j < ROWS_PER_THREAD; ++j) {
+        int lr = threadIdx.y + j * CG_BLOCK_Y;
+        sp[lr + 1][threadIdx.x + 1] =
+            m[j] ? combine(v[j], base + (int64_t)j * CG_BLOCK_Y * pitch, r0 + lr, c0 + threadIdx.x, true) : 0.0;
+    }
+#pragma unroll
+    for (int k = 0; k < HALO_PER_THREAD; ++k) {
+        if (t + k * CG_THREADS < 128)
+            sp[hr[k] + 1][hc[k] + 1] =
+                hm[k] ? combine(hv[k], (r0 + hr[k]) * pitch + c0 + hc[k], r0 + hr[k], c0 + hc[k], false) : 0.0;
     }
 }
 
