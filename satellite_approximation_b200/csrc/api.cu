@@ -91,8 +91,9 @@ int scene_alloc(sa_scene* s, bool transposed)
     SA_CUDA(ctx, cudaMalloc(&s->tile_list, sizeof(int32_t) * 2 * (size_t)s->tiles_x * s->tiles_y));
     {
         size_t words = (size_t)(s->tiles_x + 2) * (s->tiles_y + 2) * 32;
-        SA_CUDA(ctx, cudaMalloc(&s->tbits, words * sizeof(uint32_t)));
-        SA_CUDA(ctx, cudaMemsetAsync(s->tbits, 0, words * sizeof(uint32_t), ctx->stream));
+        s->tb_words = words;
+        SA_CUDA(ctx, cudaMalloc(&s->tbits, 2 * words * sizeof(uint32_t)));
+        SA_CUDA(ctx, cudaMemsetAsync(s->tbits, 0, 2 * words * sizeof(uint32_t), ctx->stream));
     }
     SA_CUDA(ctx, cudaMalloc(&s->d_counters, sizeof(int32_t) * 4));
     SA_CUDA(ctx, cudaMalloc(&s->d_count64, sizeof(unsigned long long)));

@@ -305,6 +305,7 @@ Level fine_level(const sa_scene* s)
     lv.tile_list = s->tile_list;
     lv.fixed_diag = s->problem == SA_LAPLACE;
     lv.tbits = s->tbits;
+    lv.tbitsT = s->tbits + s->tb_words;
     lv.tb_stride = s->tiles_x + 2;
     return lv;
 }

@@ -64,6 +64,7 @@ struct Level {
     // A ring of all-zero tiles surrounds the grid, so neighbourhoods of any tile can be read without bounds checks.
     // 128 B per tile: small enough to stay resident in L2 across kernels (15 MB for a 10980^2 scene).
     const uint32_t* tbits;
+    const uint32_t* tbitsT;  // transposed: word index = column of the tile, bit = row (column masks for the fused kernels)
     int tb_stride;        // tiles_x + 2
 };
 
@@ -88,7 +89,8 @@ struct sa_level_store {
     uint8_t* umask_alloc = nullptr;    // base of the allocation (guard row included)
     int32_t* tile_list = nullptr;      // 2 * tiles entries: list, then per-tile flags
     int32_t* d_counters = nullptr;     // {active tiles, first, last, -}
-    uint32_t* tbits = nullptr;
+    uint32_t* tbits = nullptr;  // row words, then (at +tb_words) the transposed column words
+    size_t tb_words = 0;
     int64_t rows_p = 0;
     double* x = nullptr;               // coarse levels: correction; nbands planes (allocation base)
     double* b = nullptr;               // coarse levels: restricted residual
@@ -118,7 +120,8 @@ struct sa_scene {
     uint8_t* mask = nullptr;   // normalised 0/1 invalid mask (allocation base)
     uint8_t* umask = nullptr;  // unknown set (allocation base)
     int32_t* tile_list = nullptr;
-    uint32_t* tbits = nullptr;  // tile-row bit masks of umask (Level::tbits)
+    uint32_t* tbits = nullptr;  // tile-row bit masks of umask (Level::tbits), then the transposed words (Level::tbitsT)
+    size_t tb_words = 0;
     int32_t* d_counters = nullptr;
     unsigned long long* d_count64 = nullptr;
     satfill::BandScalars* scal = nullptr;

@@ -59,9 +59,14 @@ int transpose_i32(sa_ctx* ctx, const int32_t* s, int64_t r, int64_t c, int64_t s
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(CG_THREADS) k_build_unknown_set(uint8_t* __restrict__ mask, uint8_t* __restrict__ umask,
     int64_t rows, int64_t cols, int64_t pitch, int tiles_x, int laplace, int32_t* __restrict__ tile_flags,
-    unsigned long long* __restrict__ count64, uint32_t* __restrict__ tbits)
+    unsigned long long* __restrict__ count64, uint32_t* __restrict__ tbits, uint32_t* __restrict__ tbitsT)
 {
     __shared__ int warp_cnt[CG_BLOCK_Y];
+    __shared__ unsigned scol[TILE_W];
+    if (threadIdx.y == 0)
+        scol[threadIdx.x] = 0;
+    __syncthreads();
+    unsigned colbits = 0;
     int tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x;
     int64_t c = (int64_t)tx * TILE_W + threadIdx.x;
     int cnt = 0;
@@ -81,12 +86,16 @@ __global__ void __launch_bounds__(CG_THREADS) k_build_unknown_set(uint8_t* __res
         unsigned word = __ballot_sync(0xffffffffu, um);
         if (threadIdx.x == 0)
             tbits[((size_t)(ty + 1) * (tiles_x + 2) + tx + 1) * 32 + threadIdx.y + j * CG_BLOCK_Y] = word;
+        colbits |= (unsigned)um << (threadIdx.y + j * CG_BLOCK_Y);
     }
+    atomicOr(&scol[threadIdx.x], colbits);
     for (int o = 16; o; o >>= 1)
         cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
     if (threadIdx.x == 0)
         warp_cnt[threadIdx.y] = cnt;
     __syncthreads();
+    if (threadIdx.y == 0)
+        tbitsT[((size_t)(ty + 1) * (tiles_x + 2) + tx + 1) * 32 + threadIdx.x] = scol[threadIdx.x];
     if (threadIdx.x == 0 && threadIdx.y == 0) {
         int total = 0;
         for (int w = 0; w < CG_BLOCK_Y; ++w)
@@ -153,7 +162,7 @@ int index_scene(sa_scene* s)
     SA_CUDA(ctx, cudaMemsetAsync(s->d_count64, 0, sizeof(unsigned long long), ctx->stream));
     dim3 block(CG_BLOCK_X, CG_BLOCK_Y);
     SA_LAUNCH(ctx, k_build_unknown_set, n_tiles, block, 0, s->mask0(s->mask), s->mask0(s->umask), s->rows, s->cols,
-        s->pitch, s->tiles_x, s->problem == SA_LAPLACE ? 1 : 0, flags, s->d_count64, s->tbits);
+        s->pitch, s->tiles_x, s->problem == SA_LAPLACE ? 1 : 0, flags, s->d_count64, s->tbits, s->tbits + s->tb_words);
     SA_CUDA(ctx, cudaGetLastError());
     SA_TRY(compact_tile_flags(ctx, flags, n_tiles, s->tile_list, s->d_counters));
     struct readback {

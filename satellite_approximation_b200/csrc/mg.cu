@@ -31,9 +31,15 @@ __device__ __forceinline__ double lv_diag(const Level& lv, int64_t r, int64_t c)
 // coarse umask(I, J) = fine umask(2I, 2J); per-tile activity flags and unknown count.  One CTA per coarse tile.
 __global__ void __launch_bounds__(CG_THREADS) k_coarsen_mask(const uint8_t* __restrict__ fmask, int64_t fpitch,
     uint8_t* __restrict__ cmask, int64_t crows, int64_t ccols, int64_t cpitch, int tiles_x,
-    int32_t* __restrict__ tile_flags, unsigned long long* __restrict__ count64, uint32_t* __restrict__ tbits)
+    int32_t* __restrict__ tile_flags, unsigned long long* __restrict__ count64, uint32_t* __restrict__ tbits,
+    uint32_t* __restrict__ tbitsT)
 {
     __shared__ int warp_cnt[CG_BLOCK_Y];
+    __shared__ unsigned scol[TILE_W];
+    if (threadIdx.y == 0)
+        scol[threadIdx.x] = 0;
+    __syncthreads();
+    unsigned colbits = 0;
     int tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x;
     int64_t c = (int64_t)tx * TILE_W + threadIdx.x;
     int cnt = 0;
@@ -48,12 +54,16 @@ __global__ void __launch_bounds__(CG_THREADS) k_coarsen_mask(const uint8_t* __re
         unsigned word = __ballot_sync(0xffffffffu, m);
         if (threadIdx.x == 0)
             tbits[((size_t)(ty + 1) * (tiles_x + 2) + tx + 1) * 32 + threadIdx.y + j * CG_BLOCK_Y] = word;
+        colbits |= (unsigned)m << (threadIdx.y + j * CG_BLOCK_Y);
     }
+    atomicOr(&scol[threadIdx.x], colbits);
     for (int o = 16; o; o >>= 1)
         cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
     if (threadIdx.x == 0)
         warp_cnt[threadIdx.y] = cnt;
     __syncthreads();
+    if (threadIdx.y == 0)
+        tbitsT[((size_t)(ty + 1) * (tiles_x + 2) + tx + 1) * 32 + threadIdx.x] = scol[threadIdx.x];
     if (threadIdx.x == 0 && threadIdx.y == 0) {
         int total = 0;
         for (int w = 0; w < CG_BLOCK_Y; ++w)
@@ -109,11 +119,13 @@ static int alloc_hierarchy(sa_scene* s, const sa_options& o)
         SA_CUDA(ctx, cudaMalloc(&L.b, vec));
         SA_CUDA(ctx, cudaMalloc(&L.t, vec));
         size_t words = (size_t)(L.lv.tiles_x + 2) * (L.lv.tiles_y + 2) * 32;
-        SA_CUDA(ctx, cudaMalloc(&L.tbits, words * sizeof(uint32_t)));
-        SA_CUDA(ctx, cudaMemsetAsync(L.tbits, 0, words * sizeof(uint32_t), ctx->stream));
+        L.tb_words = words;
+        SA_CUDA(ctx, cudaMalloc(&L.tbits, 2 * words * sizeof(uint32_t)));
+        SA_CUDA(ctx, cudaMemsetAsync(L.tbits, 0, 2 * words * sizeof(uint32_t), ctx->stream));
         L.lv.umask = L.umask_alloc + L.lv.pitch;
         L.lv.tile_list = L.tile_list;
         L.lv.tbits = L.tbits;
+        L.lv.tbitsT = L.tbits + words;
         L.lv.tb_stride = L.lv.tiles_x + 2;
         s->coarse.push_back(L);
         rows = crows;
@@ -137,7 +149,7 @@ int build_hierarchy(sa_scene* s, const sa_options& o)
         SA_CUDA(ctx, cudaMemsetAsync(L.d_counters, 0, sizeof(int32_t) * 4 + sizeof(unsigned long long), ctx->stream));
         uint8_t* cmask = L.umask_alloc + L.lv.pitch;
         SA_LAUNCH(ctx, k_coarsen_mask, n_tiles, block, 0, fmask, fpitch, cmask, L.lv.rows, L.lv.cols, L.lv.pitch,
-            L.lv.tiles_x, flags, count64, L.tbits);
+            L.lv.tiles_x, flags, count64, L.tbits, L.tbits + L.tb_words);
         SA_TRY(compact_tile_flags(ctx, flags, n_tiles, L.tile_list, L.d_counters));
         size_t vec = (size_t)L.lv.plane * s->nbands * sizeof(double);
         SA_CUDA(ctx, cudaMemsetAsync(L.x, 0, vec, ctx->stream));

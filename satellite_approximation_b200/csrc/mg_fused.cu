@@ -15,10 +15,16 @@
 // The unknown set comes from the per-tile bit masks (Level::tbits, L2 resident), so loads of known cells are
 // predicated off and no bounds checks are needed.
 //
-// Thread mapping: 40 x 4 threads; thread (x, y) owns column x of the staged region and rows y, y + 4, ...  All shared
-// memory addresses are then a per-thread base plus compile-time offsets -- the first version of these kernels walked
-// the regions with a linear index (div / mod per cell) and was instruction-issue bound at ~1 TB/s (profiles/).
-// Rows of the region without any unknown are skipped by the whole CTA.
+// Thread mapping: 40 x 4 threads; thread (x, y) owns column x of the staged region and a CONTIGUOUS run of rows
+// [RG y, RG y + RG).  Consequences, each of which removed instructions from what was an issue-bound kernel
+// (profiles/r1_fused_v1_*: 62 % issue utilisation at 18 % DRAM utilisation):
+//   * shared-memory addresses are a per-thread base plus compile-time offsets (no div / mod per cell);
+//   * the unknown set of the thread's column is ONE 64-bit register (Level::tbitsT, three L2-resident words), tested
+//     with a compile-time bit index -- no mask array in shared memory, no barrier before the global loads;
+//   * the north / centre / south values of the 5-point stencil slide through registers down the column: 4 shared
+//     loads per cell instead of 6;
+//   * all global loads of a thread are issued back to back before the first use, and cells are processed branch
+//     free (results of known cells are discarded by a select), so the unrolled body schedules as one block.
 #include "common.cuh"
 #include "tile.cuh"
 
@@ -27,31 +33,30 @@ namespace satfill {
 constexpr double FW = 0.8;  // damped-Jacobi weight, same as mg.cu
 constexpr int FX = 40, FY = 4, FTHREADS = FX * FY;
 
-// Row masks of the (32 + 2H)^2 neighbourhood of tile (ty, tx): bit (col + H) of mrow[row + H] <=> cell
-// (r0 + row, c0 + col) is an unknown, for row, col in [-H, 32 + H).
+// Unknown set of column x of the (32 + 2H)^2 neighbourhood of tile (ty, tx): bit (row + H) <=> cell
+// (r0 + row, c0 - H + x) is an unknown, row in [-H, 32 + H).
 template <int H>
-__device__ __forceinline__ void load_region_mask(const Level& lv, int ty, int tx, unsigned long long* mrow, int t)
+__device__ __forceinline__ unsigned long long region_col_mask(const Level& lv, int ty, int tx, int x)
 {
-    for (int row = t; row < TILE_H + 2 * H; row += FTHREADS) {
-        int gr = row - H;
-        int tyy = ty + (gr < 0 ? -1 : (gr >= TILE_H ? 1 : 0));
-        const uint32_t* w = lv.tbits + ((size_t)(tyy + 1) * lv.tb_stride + (tx + 1)) * 32 + (gr & 31);
-        unsigned long long C = w[0], L = w[-32], R = w[32];
-        mrow[row] = (L >> (32 - H)) | (C << H) | ((R & ((1ull << H) - 1)) << (32 + H));
-    }
+    int gc = x - H;
+    int txx = tx + (gc < 0 ? -1 : (gc >= TILE_W ? 1 : 0));
+    const uint32_t* w = lv.tbitsT + ((size_t)(ty + 1) * lv.tb_stride + (txx + 1)) * 32 + (gc & 31);
+    const size_t vs = (size_t)lv.tb_stride * 32;
+    unsigned long long C = w[0], N = *(w - vs), Sx = w[vs];
+    return (N >> (32 - H)) | (C << H) | ((Sx & ((1ull << H) - 1)) << (32 + H));
 }
 
-// diagonal and its inverse; FIXED: Laplace (every unknown has four in-image neighbours)
+// diagonal and omega / diagonal; FIXED: Laplace (every unknown has four in-image neighbours)
 template <bool FIXED>
-__device__ __forceinline__ void diag_pair(const Level& lv, int64_t r, int64_t c, double& d, double& inv)
+__device__ __forceinline__ void diag_pair(const Level& lv, int64_t r, int64_t c, double& d, double& winv)
 {
     if (FIXED) {
         d = 4.0;
-        inv = 0.25;
+        winv = FW * 0.25;
     } else {
         int n = (r > 0) + (r < lv.rows - 1) + (c > 0) + (c < lv.cols - 1);
         d = n < 1 ? 1.0 : (double)n;
-        inv = n == 4 ? 0.25 : (n == 3 ? (1.0 / 3.0) : (n == 2 ? 0.5 : 1.0));
+        winv = FW * (n == 4 ? 0.25 : (n == 3 ? (1.0 / 3.0) : (n == 2 ? 0.5 : 1.0)));
     }
 }
 
@@ -61,95 +66,86 @@ __global__ void __launch_bounds__(FTHREADS) k_mg_down(Level lf, Level lc, const 
 {
     constexpr int H = 3, W = TILE_W + 2 * H;  // 38
     constexpr int S = W + 1;                  // shared row stride
-    __shared__ unsigned long long mrow[W];
-    __shared__ double B[W * S];
-    __shared__ double X1[W * S];  // sweep 1; later reused for the residual
-    __shared__ double X2[W * S];  // sweep 2, stored at the 38-grid position of the cell
+    constexpr int RG = (W + FY - 1) / FY;     // 10 rows per thread
+    constexpr int RA = RG * FY + 1;           // allocated rows: the sliding window reads one row past the last
+    __shared__ double B[RA * S];
+    __shared__ double X1[RA * S];  // sweep 1; later reused for the residual
+    __shared__ double X2[RA * S];  // sweep 2
     if (scal[blockIdx.y].done)
         return;
     const int x = threadIdx.x, y = threadIdx.y, t = y * FX + x;
     const int tile = lf.tile_list[blockIdx.x];
     const int ty = tile / lf.tiles_x, tx = tile % lf.tiles_x;
     const int64_t r0 = (int64_t)ty * TILE_H, c0 = (int64_t)tx * TILE_W;
-    load_region_mask<H>(lf, ty, tx, mrow, t);
-    __syncthreads();
-    const int64_t gc = c0 - H + x;  // global column of this thread
+    const int row0 = RG * y;
+    const unsigned long long cm = x < W ? region_col_mask<H>(lf, ty, tx, x) : 0ull;
+    const unsigned my = (unsigned)(cm >> row0);  // bit k <=> (row0 + k, x) is an unknown; rows >= W have no bits
+    const int64_t gr = r0 - H + row0, gc = c0 - H + x;
+    const int sbase = row0 * S + x;
     {
-        // all loads of the thread are issued back to back (predicated, no branches) before any of them is used
-        constexpr int NK = (W + FY - 1) / FY;
-        const double* bp = b + (int64_t)blockIdx.y * lf.plane + (r0 - H + y) * lf.pitch + gc;
-        const int64_t step = (int64_t)FY * lf.pitch;
-        double v[NK];
+        const double* bp = b + (int64_t)blockIdx.y * lf.plane + gr * lf.pitch + gc;
+        double v[RG];
 #pragma unroll
-        for (int k = 0; k < NK; ++k) {
-            int row = y + k * FY;
-            bool on = x < W && row < W && ((mrow[row < W ? row : 0] >> x) & 1);
-            v[k] = on ? bp[k * step] : 0.0;
-        }
+        for (int k = 0; k < RG; ++k)
+            v[k] = ((my >> k) & 1) ? bp[k * lf.pitch] : 0.0;
         if (x < W) {
 #pragma unroll
-            for (int k = 0; k < NK; ++k) {
-                int row = y + k * FY;
-                if (row < W) {
-                    double d, inv;
-                    diag_pair<FIXED>(lf, r0 - H + row, gc, d, inv);
-                    B[row * S + x] = v[k];
-                    X1[row * S + x] = FW * inv * v[k];
-                }
+            for (int k = 0; k < RG; ++k) {
+                double d, winv;
+                diag_pair<FIXED>(lf, gr + k, gc, d, winv);
+                B[sbase + k * S] = v[k];
+                X1[sbase + k * S] = winv * v[k];  // one damped-Jacobi sweep from zero
             }
         }
     }
     __syncthreads();
-    if (x >= 1 && x < W - 1) {  // sweep 2 on the 36 x 36 region
+    if (x >= 1 && x < W - 1) {  // sweep 2 on rows / columns 1 .. 36
+        const double* p = X1 + sbase;
+        double n = y > 0 ? p[-S] : 0.0, c = p[0];
 #pragma unroll
-        for (int k = 0; k < (W + FY - 1) / FY; ++k) {
-            int row = y + k * FY;
-            if (row >= 1 && row < W - 1) {
-                unsigned long long m = mrow[row];
-                double x2 = 0.0;
-                if ((m >> x) & 1) {
-                    double d, inv;
-                    diag_pair<FIXED>(lf, r0 - H + row, gc, d, inv);
-                    const double* p = X1 + row * S + x;
-                    double xc = p[0];
-                    double ax = d * xc - ((p[-S] + p[S]) + (p[-1] + p[1]));
-                    x2 = xc + FW * inv * (B[row * S + x] - ax);
-                }
-                X2[row * S + x] = x2;
-            }
+        for (int k = 0; k < RG; ++k) {
+            double sv = p[(k + 1) * S];
+            double d, winv;
+            diag_pair<FIXED>(lf, gr + k, gc, d, winv);
+            double ax = d * c - ((n + sv) + (p[k * S - 1] + p[k * S + 1]));
+            double x2 = c + winv * (B[sbase + k * S] - ax);
+            bool on = ((my >> k) & 1) && row0 + k >= 1 && row0 + k < W - 1;
+            X2[sbase + k * S] = on ? x2 : 0.0;
+            n = c;
+            c = sv;
         }
     }
     __syncthreads();
-    double* R = X1;  // residual on the 34 x 34 region (X1 is dead)
-    double* xo = x_out + (int64_t)blockIdx.y * lf.plane + (r0 - H) * lf.pitch + gc;
+    double* R = X1;  // residual on rows / columns 2 .. 35 (X1 is dead)
     if (x >= 2 && x < W - 2) {
+        const double* p = X2 + sbase;
+        double* xo = x_out + (int64_t)blockIdx.y * lf.plane + gr * lf.pitch + gc;
+        const bool own_col = x >= H && x < H + TILE_W;
+        double n = y > 0 ? p[-S] : 0.0, c = p[0];
 #pragma unroll
-        for (int k = 0; k < (W + FY - 1) / FY; ++k) {
-            int row = y + k * FY;
-            if (row >= 2 && row < W - 2) {
-                double res = 0.0;
-                if ((mrow[row] >> x) & 1) {
-                    double d, inv;
-                    diag_pair<FIXED>(lf, r0 - H + row, gc, d, inv);
-                    const double* p = X2 + row * S + x;
-                    double xc = p[0];
-                    double ax = d * xc - ((p[-S] + p[S]) + (p[-1] + p[1]));
-                    res = B[row * S + x] - ax;
-                    if (row >= H && row < H + TILE_H && x >= H && x < H + TILE_W)
-                        xo[row * lf.pitch] = xc;  // the CTA's own tile
-                }
-                R[row * S + x] = res;
-            }
+        for (int k = 0; k < RG; ++k) {
+            double sv = p[(k + 1) * S];
+            double d, winv;
+            diag_pair<FIXED>(lf, gr + k, gc, d, winv);
+            double ax = d * c - ((n + sv) + (p[k * S - 1] + p[k * S + 1]));
+            double res = B[sbase + k * S] - ax;
+            int row = row0 + k;
+            bool on = ((my >> k) & 1) && row >= 2 && row < W - 2;
+            R[sbase + k * S] = on ? res : 0.0;
+            if (on && own_col && row >= H && row < H + TILE_H)
+                xo[k * lf.pitch] = c;  // the CTA's own tile
+            n = c;
+            c = sv;
         }
     }
     __syncthreads();
-    // restriction: coarse cell (ci, cj) of this tile sits on fine tile cell (2 ci, 2 cj) = 38-grid (2 ci + 3, 2 cj + 3)
+    // restriction: coarse cell (ci, cj) of this tile sits on fine tile cell (2 ci, 2 cj) = region (2 ci + 3, 2 cj + 3)
     double* bco = bc + (int64_t)blockIdx.y * lc.plane + (r0 >> 1) * lc.pitch + (c0 >> 1);
+    const uint32_t* rowbits = lf.tbits + ((size_t)(ty + 1) * lf.tb_stride + (tx + 1)) * 32;
     for (int i = t; i < (TILE_H / 2) * (TILE_W / 2); i += FTHREADS) {
         int ci = i >> 4, cj = i & 15;
-        int a = 2 * ci + H, c = 2 * cj + H;
-        if ((mrow[a] >> c) & 1) {  // mask injection: coarse unknown <=> fine (2I, 2J) unknown
-            const double* p = R + a * S + c;
+        if ((rowbits[2 * ci] >> (2 * cj)) & 1) {  // mask injection: coarse unknown <=> fine (2I, 2J) unknown
+            const double* p = R + (2 * ci + H) * S + 2 * cj + H;
             double up = 0.5 * p[-S - 1] + p[-S] + 0.5 * p[-S + 1];
             double mid = 0.5 * p[-1] + p[0] + 0.5 * p[1];
             double dn = 0.5 * p[S - 1] + p[S] + 0.5 * p[S + 1];
@@ -165,12 +161,12 @@ __global__ void __launch_bounds__(FTHREADS) k_mg_up(Level lf, Level lc, const do
 {
     constexpr int H = 2, W = TILE_W + 2 * H;  // 36
     constexpr int S = W + 1;
-    constexpr int EW = W / 2 + 1;  // 19 coarse cells cover the region
+    constexpr int RG = W / FY;        // 9 rows per thread
+    constexpr int RA = RG * FY + 1;
+    constexpr int EW = W / 2 + 1;     // 19 coarse cells cover the region
     constexpr int ES = EW + 2;
-    __shared__ unsigned long long mrow[W];
-    __shared__ double X[W * S];
-    __shared__ double Bv[W * S];
-    __shared__ double X3[W * S];
+    __shared__ double X[RA * S];
+    __shared__ double X3[RA * S];
     __shared__ double E[EW * ES];
     __shared__ double s_red[FTHREADS / 32];
     if (scal[blockIdx.y].done)
@@ -179,9 +175,24 @@ __global__ void __launch_bounds__(FTHREADS) k_mg_up(Level lf, Level lc, const do
     const int tile = lf.tile_list[blockIdx.x];
     const int ty = tile / lf.tiles_x, tx = tile % lf.tiles_x;
     const int64_t r0 = (int64_t)ty * TILE_H, c0 = (int64_t)tx * TILE_W;
-    load_region_mask<H>(lf, ty, tx, mrow, t);
-    // the coarse correction under the region: coarse rows r0/2 - 1 .. r0/2 + 17 (zero outside the coarse grid)
+    const int row0 = RG * y;
+    const unsigned long long cm = x < W ? region_col_mask<H>(lf, ty, tx, x) : 0ull;
+    const unsigned my = (unsigned)(cm >> row0);
+    const int64_t gr = r0 - H + row0, gc = c0 - H + x;
+    const int sbase = row0 * S + x;
+    const int64_t goff = (int64_t)blockIdx.y * lf.plane + gr * lf.pitch + gc;
+    // global loads first: x on the 36 x 36 region, b on the inner 34 x 34, the coarse correction under the region
+    double xv[RG], bv[RG];
     {
+        const double* xp = x_in + goff;
+        const double* bp = b + goff;
+        const bool inner_col = x >= 1 && x < W - 1;
+#pragma unroll
+        for (int k = 0; k < RG; ++k) {
+            bool on = (my >> k) & 1;
+            xv[k] = on ? xp[k * lf.pitch] : 0.0;
+            bv[k] = (on && inner_col && row0 + k >= 1 && row0 + k < W - 1) ? bp[k * lf.pitch] : 0.0;
+        }
         const double* e = ec + (int64_t)blockIdx.y * lc.plane;
         const int64_t I0 = (r0 >> 1) - 1, J0 = (c0 >> 1) - 1;
         for (int i = t; i < EW * EW; i += FTHREADS) {
@@ -191,77 +202,55 @@ __global__ void __launch_bounds__(FTHREADS) k_mg_up(Level lf, Level lc, const do
         }
     }
     __syncthreads();
-    const int64_t gc = c0 - H + x;
-    const int64_t boff = (int64_t)blockIdx.y * lf.plane + (r0 - H) * lf.pitch + gc;
-    {
-        // x + P e on the 36 x 36 region, b on the inner 34 x 34; loads first (predicated, back to back), then use
-        constexpr int NK = W / FY;
-        const double* xp = x_in + boff + (int64_t)y * lf.pitch;
-        const double* bp = b + boff + (int64_t)y * lf.pitch;
-        const int64_t step = (int64_t)FY * lf.pitch;
-        double xv[NK], bv[NK];
+    if (x < W) {  // X = x + P e (bilinear; r0 - 2 and c0 - 2 are even, so local parity = global parity)
+        const int ej = x >> 1, oj = x & 1;
 #pragma unroll
-        for (int k = 0; k < NK; ++k) {
-            int row = y + k * FY;
-            bool on = x < W && ((mrow[row] >> x) & 1);
-            bool inner = on && row >= 1 && row < W - 1 && x >= 1 && x < W - 1;
-            xv[k] = on ? xp[k * step] : 0.0;
-            bv[k] = inner ? bp[k * step] : 0.0;
-        }
-        if (x < W) {
-            const int ej = x >> 1, oj = x & 1;  // c0 - 2 is even: parity of the local index = global parity
-#pragma unroll
-            for (int k = 0; k < NK; ++k) {
-                int row = y + k * FY;
-                double v = 0.0;
-                if ((mrow[row] >> x) & 1) {
-                    const double* p = E + (row >> 1) * ES + ej;
-                    int oi = (row & 1) * ES;
-                    v = xv[k] + 0.25 * ((p[0] + p[oj]) + (p[oi] + p[oi + oj]));  // bilinear, branch free
-                }
-                X[row * S + x] = v;
-                Bv[row * S + x] = bv[k];
-            }
+        for (int k = 0; k < RG; ++k) {
+            int row = row0 + k;
+            const double* p = E + (row >> 1) * ES + ej;
+            int oi = (row & 1) * ES;
+            double pe = 0.25 * ((p[0] + p[oj]) + (p[oi] + p[oi + oj]));
+            X[sbase + k * S] = ((my >> k) & 1) ? xv[k] + pe : 0.0;
         }
     }
     __syncthreads();
-    if (x >= 1 && x < W - 1) {  // post-smoothing sweep 1 on the 34 x 34 region
+    if (x >= 1 && x < W - 1) {  // post-smoothing sweep 1 on rows / columns 1 .. 34
+        const double* p = X + sbase;
+        double n = y > 0 ? p[-S] : 0.0, c = p[0];
 #pragma unroll
-        for (int k = 0; k < W / FY; ++k) {
-            int row = y + k * FY;
-            if (row >= 1 && row < W - 1) {
-                double x3 = 0.0;
-                if ((mrow[row] >> x) & 1) {
-                    double d, inv;
-                    diag_pair<FIXED>(lf, r0 - H + row, gc, d, inv);
-                    const double* p = X + row * S + x;
-                    double xc = p[0];
-                    double ax = d * xc - ((p[-S] + p[S]) + (p[-1] + p[1]));
-                    x3 = xc + FW * inv * (Bv[row * S + x] - ax);
-                }
-                X3[row * S + x] = x3;
-            }
+        for (int k = 0; k < RG; ++k) {
+            double sv = p[(k + 1) * S];
+            double d, winv;
+            diag_pair<FIXED>(lf, gr + k, gc, d, winv);
+            double ax = d * c - ((n + sv) + (p[k * S - 1] + p[k * S + 1]));
+            double x3 = c + winv * (bv[k] - ax);
+            bool on = ((my >> k) & 1) && row0 + k >= 1 && row0 + k < W - 1;
+            X3[sbase + k * S] = on ? x3 : 0.0;
+            n = c;
+            c = sv;
         }
     }
     __syncthreads();
-    double* xo = x_out + boff;
     double acc = 0.0;
     if (x >= H && x < H + TILE_W) {  // sweep 2 on the tile itself
+        const double* p = X3 + sbase;
+        double* xo = x_out + goff;
+        double n = y > 0 ? p[-S] : 0.0, c = p[0];
 #pragma unroll
-        for (int k = 0; k < TILE_H / FY; ++k) {
-            int row = H + y + k * FY;
-            if ((mrow[row] >> x) & 1) {
-                double d, inv;
-                diag_pair<FIXED>(lf, r0 - H + row, gc, d, inv);
-                const double* p = X3 + row * S + x;
-                double xc = p[0];
-                double ax = d * xc - ((p[-S] + p[S]) + (p[-1] + p[1]));
-                double bv = Bv[row * S + x];
-                double x4 = xc + FW * inv * (bv - ax);
-                xo[row * lf.pitch] = x4;
+        for (int k = 0; k < RG; ++k) {
+            double sv = p[(k + 1) * S];
+            double d, winv;
+            diag_pair<FIXED>(lf, gr + k, gc, d, winv);
+            double ax = d * c - ((n + sv) + (p[k * S - 1] + p[k * S + 1]));
+            double x4 = c + winv * (bv[k] - ax);
+            int row = row0 + k;
+            if (((my >> k) & 1) && row >= H && row < H + TILE_H) {
+                xo[k * lf.pitch] = x4;
                 if (DOT)
-                    acc += bv * x4;
+                    acc += bv[k] * x4;
             }
+            n = c;
+            c = sv;
         }
     }
     if (DOT) {
@@ -271,11 +260,11 @@ __global__ void __launch_bounds__(FTHREADS) k_mg_up(Level lf, Level lc, const do
             s_red[t >> 5] = acc;
         __syncthreads();
         if (t == 0) {
-            double s = 0.0;
+            double sum = 0.0;
             for (int w = 0; w < FTHREADS / 32; ++w)
-                s += s_red[w];
-            if (s != 0.0)
-                atomicAdd(&scal[blockIdx.y].rz[slot], s);
+                sum += s_red[w];
+            if (sum != 0.0)
+                atomicAdd(&scal[blockIdx.y].rz[slot], sum);
         }
     }
 }
