@@ -61,14 +61,13 @@ __device__ __forceinline__ void diag_pair(const Level& lv, int64_t r, int64_t c,
 }
 
 template <bool FIXED>
-__global__ void __launch_bounds__(FTHREADS) k_mg_down(Level lf, Level lc, const double* __restrict__ b,
+__global__ void __launch_bounds__(FTHREADS, 8) k_mg_down(Level lf, Level lc, const double* __restrict__ b,
     double* __restrict__ x_out, double* __restrict__ bc, const BandScalars* __restrict__ scal)
 {
     constexpr int H = 3, W = TILE_W + 2 * H;  // 38
     constexpr int S = W + 1;                  // shared row stride
     constexpr int RG = (W + FY - 1) / FY;     // 10 rows per thread
     constexpr int RA = RG * FY + 1;           // allocated rows: the sliding window reads one row past the last
-    __shared__ double B[RA * S];
     __shared__ double X1[RA * S];  // sweep 1; later reused for the residual
     __shared__ double X2[RA * S];  // sweep 2
     if (scal[blockIdx.y].done)
@@ -82,9 +81,9 @@ __global__ void __launch_bounds__(FTHREADS) k_mg_down(Level lf, Level lc, const 
     const unsigned my = (unsigned)(cm >> row0);  // bit k <=> (row0 + k, x) is an unknown; rows >= W have no bits
     const int64_t gr = r0 - H + row0, gc = c0 - H + x;
     const int sbase = row0 * S + x;
+    double v[RG];  // the right-hand side of the thread's own cells stays in registers (it is only used pointwise)
     {
         const double* bp = b + (int64_t)blockIdx.y * lf.plane + gr * lf.pitch + gc;
-        double v[RG];
 #pragma unroll
         for (int k = 0; k < RG; ++k)
             v[k] = ((my >> k) & 1) ? bp[k * lf.pitch] : 0.0;
@@ -93,7 +92,6 @@ __global__ void __launch_bounds__(FTHREADS) k_mg_down(Level lf, Level lc, const 
             for (int k = 0; k < RG; ++k) {
                 double d, winv;
                 diag_pair<FIXED>(lf, gr + k, gc, d, winv);
-                B[sbase + k * S] = v[k];
                 X1[sbase + k * S] = winv * v[k];  // one damped-Jacobi sweep from zero
             }
         }
@@ -108,7 +106,7 @@ __global__ void __launch_bounds__(FTHREADS) k_mg_down(Level lf, Level lc, const 
             double d, winv;
             diag_pair<FIXED>(lf, gr + k, gc, d, winv);
             double ax = d * c - ((n + sv) + (p[k * S - 1] + p[k * S + 1]));
-            double x2 = c + winv * (B[sbase + k * S] - ax);
+            double x2 = c + winv * (v[k] - ax);
             bool on = ((my >> k) & 1) && row0 + k >= 1 && row0 + k < W - 1;
             X2[sbase + k * S] = on ? x2 : 0.0;
             n = c;
@@ -128,7 +126,7 @@ __global__ void __launch_bounds__(FTHREADS) k_mg_down(Level lf, Level lc, const 
             double d, winv;
             diag_pair<FIXED>(lf, gr + k, gc, d, winv);
             double ax = d * c - ((n + sv) + (p[k * S - 1] + p[k * S + 1]));
-            double res = B[sbase + k * S] - ax;
+            double res = v[k] - ax;
             int row = row0 + k;
             bool on = ((my >> k) & 1) && row >= 2 && row < W - 2;
             R[sbase + k * S] = on ? res : 0.0;
@@ -155,7 +153,7 @@ __global__ void __launch_bounds__(FTHREADS) k_mg_down(Level lf, Level lc, const 
 }
 
 template <bool FIXED, bool DOT>
-__global__ void __launch_bounds__(FTHREADS) k_mg_up(Level lf, Level lc, const double* __restrict__ x_in,
+__global__ void __launch_bounds__(FTHREADS, 8) k_mg_up(Level lf, Level lc, const double* __restrict__ x_in,
     const double* __restrict__ b, const double* __restrict__ ec, double* __restrict__ x_out,
     BandScalars* __restrict__ scal, int slot)
 {
