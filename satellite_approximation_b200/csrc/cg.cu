@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(CG_THREADS) k_zero_unknowns(Level lv, double* 
 
 // k_direction: p' = z + beta p, pq = p'.Ap'.   JACOBI: z = r / d computed on the fly (zin = r).  Otherwise zin = z.
 template <bool JACOBI>
-__global__ void __launch_bounds__(CG_THREADS, 10) k_direction(Level lv, const double* __restrict__ zin,
+__global__ void __launch_bounds__(CG_THREADS, 8) k_direction(Level lv, const double* __restrict__ zin,
     const double* __restrict__ p_old, double* __restrict__ p_new, BandScalars* __restrict__ scal, int k)
 {
     __shared__ double sp[TILE_H + 2][SP];
@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(CG_THREADS, 10) k_direction(Level lv, const do
 
 // k_update: alpha = rz / pq; x += alpha p; r -= alpha A p; new |r|^2 and (JACOBI) r.(r/d) into slot k+1.
 template <bool JACOBI>
-__global__ void __launch_bounds__(CG_THREADS, 10) k_update(Level lv, double* __restrict__ u, const double* __restrict__ p,
+__global__ void __launch_bounds__(CG_THREADS, 8) k_update(Level lv, double* __restrict__ u, const double* __restrict__ p,
     double* __restrict__ rvec, BandScalars* __restrict__ scal, int k)
 {
     __shared__ double sp[TILE_H + 2][SP];

@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(FTHREADS, 8) k_mg_down(Level lf, Level lc, con
 }
 
 template <bool FIXED, bool DOT>
-__global__ void __launch_bounds__(FTHREADS, 8) k_mg_up(Level lf, Level lc, const double* __restrict__ x_in,
+__global__ void __launch_bounds__(FTHREADS) k_mg_up(Level lf, Level lc, const double* __restrict__ x_in,
     const double* __restrict__ b, const double* __restrict__ ec, double* __restrict__ x_out,
     BandScalars* __restrict__ scal, int slot)
 {
