@@ -1,0 +1,152 @@
+// Host-side C++ shim: the reference's `approx` API (laplace.h:20,28; poisson.h:41-52) implemented by calls into the
+// C-ABI of libsatfill.so.  No arithmetic happens here -- Eigen is only the container type of the signatures.
+#include <approx/laplace.h>
+#include <approx/poisson.h>
+
+#include <satfill.h>
+
+#include <cstdio>
+#include <fstream>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+
+namespace approx {
+namespace {
+
+struct Ctx {
+    sa_ctx* h = nullptr;
+    std::mutex lock;  // a context serves one host thread at a time
+    Ctx()
+    {
+        int device = 0;
+        if (const char* e = std::getenv("SATFILL_DEVICE"))
+            device = std::atoi(e);
+        if (sa_create(&h, device, nullptr) != SA_OK)
+            throw std::runtime_error("satfill: no usable CUDA device (there is no CPU fallback)");
+    }
+    ~Ctx() { sa_destroy(h); }
+};
+
+Ctx& ctx()
+{
+    static Ctx c;
+    return c;
+}
+
+LaplaceOptions g_laplace;
+PerfInfo g_perf;
+
+static_assert(sizeof(bool) == 1, "MatX<bool> is passed to the C-ABI as a byte mask");
+
+}  // namespace
+
+void set_laplace_options(LaplaceOptions const& options) { g_laplace = options; }
+PerfInfo const& last_perf_info() { return g_perf; }
+
+void PerfInfo::write(fs::path const& output) const
+{
+    std::ofstream f(output, std::ios::app);
+    f << region_size << ',' << tolerance << ',' << max_iterations << ',' << iterations << ',' << error << ','
+      << solve_time << '\n';
+}
+
+void fill_missing_portion_smooth_boundary(MatX<f64>& input_image, MatX<bool> const& invalid_pixels)
+{
+    if (input_image.size() != invalid_pixels.size())  // laplace.cpp:124-127
+        throw std::runtime_error("Input image and mask need to be the same size");
+    if (input_image.rows() != invalid_pixels.rows())
+        throw std::runtime_error("Input image and mask need to be the same shape");
+    Ctx& c = ctx();
+    std::lock_guard<std::mutex> guard(c.lock);
+    sa_options o;
+    sa_default_options(&o, SA_LAPLACE);
+    if (g_laplace.tolerance > 0)
+        o.tolerance = g_laplace.tolerance;
+    if (g_laplace.max_iterations > 0)
+        o.max_iterations = g_laplace.max_iterations;
+    o.precond = g_laplace.multigrid ? SA_PRECOND_MULTIGRID : SA_PRECOND_JACOBI;
+    double* band = input_image.data();
+    sa_stats st {};
+    // MatX is column-major: row stride 1, column stride rows
+    int rc = sa_laplace_fill(c.h, &band, 1, reinterpret_cast<const uint8_t*>(invalid_pixels.data()), input_image.rows(),
+        input_image.cols(), 1, input_image.rows(), &o, &st);
+    if (rc != SA_OK && rc != SA_EMPTY_MASK && rc != SA_NOT_CONVERGED)  // the reference never checks info() here
+        throw std::runtime_error(std::string("satfill: ") + sa_last_error(c.h));
+}
+
+void blend_images_poisson(MultiChannelImage& input_images, MultiChannelImage const& replacement_images,
+    MatX<bool> const& invalid_mask, f64 tolerance, std::optional<int> max_iterations)
+{
+    if (input_images.images.empty())
+        return;
+    if (input_images.images.size() != replacement_images.images.size() || input_images.rows() != replacement_images.rows()
+        || input_images.cols() != replacement_images.cols()) {  // poisson.cpp:154-157: log and return
+        std::fprintf(stderr, "[approx] Input and replacement images must have the same dimensions\n");
+        return;
+    }
+    if (invalid_mask.rows() != input_images.rows() || invalid_mask.cols() != input_images.cols()) {
+        // poisson.cpp:158-160 logs and continues (out-of-bounds reads); return instead
+        std::fprintf(stderr, "[approx] Invalid mask must match the image dimensions\n");
+        return;
+    }
+    Ctx& c = ctx();
+    std::lock_guard<std::mutex> guard(c.lock);
+    const int nb = (int)input_images.images.size();
+    std::vector<double*> in(nb);
+    std::vector<const double*> rep(nb);
+    for (int b = 0; b < nb; ++b) {
+        in[b] = input_images.images[b].data();
+        rep[b] = replacement_images.images[b].data();
+    }
+    sa_options o;
+    sa_default_options(&o, SA_POISSON);
+    o.tolerance = tolerance;
+    o.max_iterations = max_iterations ? *max_iterations : 0;  // 0 -> n / 2 (poisson.cpp:207)
+    std::vector<sa_stats> st(nb);
+    int rc = sa_poisson_blend(c.h, in.data(), rep.data(), nb, reinterpret_cast<const uint8_t*>(invalid_mask.data()),
+        input_images.rows(), input_images.cols(), 1, input_images.rows(), &o, st.data());
+    const sa_stats& last = st[nb - 1];  // the reference keeps the last band's numbers (poisson.cpp:259-261)
+    g_perf = PerfInfo { (long)last.unknowns, last.tolerance, (long)last.max_iterations, (long)last.iterations, last.error,
+        last.solve_ms * 1e-3 };
+    if (rc == SA_NOT_CONVERGED)  // poisson.cpp:263-269: nothing was written
+        std::fprintf(stderr, "[approx] Failed to solve the linear system: no convergence\n");
+    else if (rc != SA_OK && rc != SA_EMPTY_MASK)
+        std::fprintf(stderr, "[approx] %s\n", sa_last_error(c.h));
+}
+
+std::vector<MatX<f64>> blend_images_poisson(std::vector<MatX<f64>> const& input_images,
+    std::vector<MatX<f64>> const& replacement_images, MatX<bool> const& invalid_mask, f64 tolerance,
+    std::optional<int> max_iterations)
+{
+    MultiChannelImage input(input_images);  // poisson.cpp:292-303
+    MultiChannelImage replacement(replacement_images);
+    blend_images_poisson(input, replacement, invalid_mask, tolerance, max_iterations);
+    return input.images;
+}
+
+ConnectedComponents find_connected_components(MatX<bool> const& invalid)
+{
+    ConnectedComponents out;
+    const Eigen::Index rows = invalid.rows(), cols = invalid.cols();
+    out.matrix = MatX<int>::Zero(rows, cols);
+    if (rows == 0 || cols == 0)
+        return out;
+    Ctx& c = ctx();
+    std::lock_guard<std::mutex> guard(c.lock);
+    std::vector<int32_t> labels((size_t)rows * cols);  // dense row-major table from the device
+    int32_t k = 0;
+    int rc = sa_label_components(c.h, reinterpret_cast<const uint8_t*>(invalid.data()), rows, cols, 1, rows, labels.data(), &k);
+    if (rc != SA_OK)
+        throw std::runtime_error(std::string("satfill: ") + sa_last_error(c.h));
+    for (Eigen::Index r = 0; r < rows; ++r)  // container bookkeeping only: raster order = the contract's order
+        for (Eigen::Index col = 0; col < cols; ++col) {
+            int l = labels[(size_t)r * cols + col];
+            out.matrix(r, col) = l;
+            if (l)
+                out.region_map[l].push_back({ r, col });
+        }
+    return out;
+}
+
+}  // namespace approx

@@ -1,0 +1,41 @@
+// satellite_approximation._core -- the fill-path functions of the reference's pybind11 module (src/main.cpp:16-58)
+// bound to the B200 implementation.  Same names, argument names, noconvert rules and defaults.
+#include <pybind11/eigen.h>
+#include <pybind11/pybind11.h>
+#include <pybind11/stl.h>
+
+#include <approx/laplace.h>
+#include <approx/poisson.h>
+
+namespace py = pybind11;
+using namespace py::literals;
+
+enum class LogLevel { Debug = 1, Info = 2, Warn = 3, Error = 4, Critical = 5 };  // spdlog values (src/main.cpp:24-29)
+
+PYBIND11_MODULE(_core, m)
+{
+    m.doc() = "Data processing for sentinel satellite imagery (Laplace / Poisson fill path on B200)";
+    py::enum_<LogLevel>(m, "LogLevel")
+        .value("Debug", LogLevel::Debug)
+        .value("Info", LogLevel::Info)
+        .value("Warn", LogLevel::Warn)
+        .value("Error", LogLevel::Error)
+        .value("Critical", LogLevel::Critical);
+    m.def("set_log_level", [](LogLevel) {});
+    m.def(
+        "filling_missing_portions_smooth_boundaries",
+        [](MatX<f64>& input_image, MatX<bool> const& invalid_pixels) {
+            py::gil_scoped_release release;
+            approx::fill_missing_portion_smooth_boundary(input_image, invalid_pixels);
+            return input_image;
+        },
+        py::arg("input_image").noconvert(), py::arg("invalid_pixels").noconvert());
+    m.def("blend_images_poisson",
+        py::overload_cast<std::vector<MatX<f64>> const&, std::vector<MatX<f64>> const&, MatX<bool> const&, f64,
+            std::optional<int>>(&approx::blend_images_poisson),
+        "input_image"_a, "replacement_image"_a, "invalid_mask"_a, "tolerance"_a = 1e-6, "max_iterations"_a = std::nullopt,
+        py::call_guard<py::gil_scoped_release>());
+    m.def("set_laplace_options", [](double tolerance, long max_iterations, bool multigrid) {
+        approx::set_laplace_options({ tolerance, max_iterations, multigrid });
+    }, "tolerance"_a = 0.0, "max_iterations"_a = 0, "multigrid"_a = false);
+}
