@@ -61,6 +61,7 @@ def parse_args():
     ap.add_argument("--bands", type=int)
     ap.add_argument("--tol", type=float, default=1e-6)
     ap.add_argument("--precond", default=os.environ.get("SATFILL_PRECOND", "multigrid"), choices=["jacobi", "multigrid"])
+    ap.add_argument("--mg-variant", default=os.environ.get("SATFILL_MG_VARIANT", "rb32"), choices=["rb32", "jacobi64"])
     ap.add_argument("--check-every", type=int, default=0)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -231,7 +232,8 @@ def run_b200(args, w):
         scene.set_band(b, bands[b])
         if poisson:
             scene.set_guidance(b, guides[b])
-    opts = dict(tolerance=args.tol, precond=precond, profile=True)
+    variant = sab.MG_RB32 if args.mg_variant == "rb32" else sab.MG_JACOBI64
+    opts = dict(tolerance=args.tol, precond=precond, profile=True, mg_variant=variant)
     if args.check_every:
         opts["check_every"] = args.check_every
 
@@ -248,7 +250,7 @@ def run_b200(args, w):
     launches0 = ctx.kernel_launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
-    NK = 6
+    NK = 8
     kms = [0.0] * NK
     kn = [0] * NK
     ku = [0] * NK
@@ -278,14 +280,22 @@ def run_b200(args, w):
     value = total_units * args.steps / (ms_max * 1e-3)
 
     # ---- roofline of the dominant kernel (by accumulated event time inside the timed region)
-    names = ["cg_direction (k_direction)", "cg_update (k_update)", "mg_sweep (k_mg_smooth)",
-             "mg_transfer (k_mg_residual/restrict/prolong)", "mg_down (k_mg_down)", "mg_up (k_mg_up)"]
-    # algorithmic bytes per fine-grid unknown and launch (DESIGN.md "Algorithmic bytes"):
-    #   direction: R z|r 8 + R p 8 + W p 8 + R mask 1 = 25; update: R p 8 + R x 8 + R r 8 + W x 8 + W r 8 + R mask 1 = 41
-    #   smoother sweep (level l holds ~ n / 4^l unknowns; summed over the launches of all levels it is counted with
-    #   the unknowns of the level it ran on): R x 8 + R b 8 + W x 8 + R mask 1 = 25
-    #   fused descent: R b 8 + W x 8 + W coarse b 8/4 = 18; fused ascent: R x 8 + R b 8 + R coarse e 8/4 + W x 8 = 26
-    bytes_per_unknown = [25.0, 41.0, 25.0, 19.0, 18.0, 26.0]
+    rb = args.precond == "multigrid" and args.mg_variant == "rb32"
+    names = ["cg_direction (k_direction)", "cg_update (k_update)", "mg_sweep (k_mg_smooth / k_rb_coarsest)",
+             "mg_transfer (k_mg_residual/restrict/prolong)",
+             "mg_down level 0 (k_rb_down)" if rb else "mg_down level 0 (k_mg_down)",
+             "mg_up level 0 (k_rb_up)" if rb else "mg_up level 0 (k_mg_up)",
+             "mg_down coarse levels", "mg_up coarse levels"]
+    # algorithmic bytes per unknown of the level the launch runs on, fp64 CG vectors:
+    #   direction: R z 8 (4: the float cycle's z) + R p 8 + W p 8 + R mask 1;  update: R p, x, r 24 + W x, r 16 + mask 1
+    #   single smoother sweep: R x 8 + R b 8 + W x 8 + R mask 1 = 25;  single transfers ~19
+    #   double Jacobi cycle: down R b 8 + W x 8 + W b_c 8/4 = 18;  up R x 8 + R b 8 + R e_c 8/4 + W x 8 = 26
+    #   float red-black cycle: down R b 4 (level 0: the double residual, 8) + W x_red 4/2 + W b_c 4/4 = 7 (11);
+    #                          up R x_red 4/2 + R b 4 (8) + R e_c 4/4 + W x 4 = 11 (15)
+    if rb:
+        bytes_per_unknown = [21.0, 41.0, 9.0, 19.0, 11.0, 15.0, 7.0, 11.0]
+    else:
+        bytes_per_unknown = [25.0, 41.0, 25.0, 19.0, 18.0, 26.0, 18.0, 26.0]
     dom = max(range(NK), key=lambda c: kms[c])
     peak, peak_src = peaks()
     roof = None
@@ -319,9 +329,12 @@ def run_b200(args, w):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_max / max(args.steps, 1), "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64" + (" (CG iterate, residual, operator and dot products; float inside the multigrid preconditioner)" if rb else ""),
+            "data": "synthetic",
             "config": {"workload": w["desc"], "problem": w["problem"], "rows": rows, "cols": cols, "bands": nb,
                        "unknowns_per_band": unknowns, "tolerance": args.tol, "precond": args.precond,
+                       "mg_variant": args.mg_variant if args.precond == "multigrid" else None,
                        "cg_iterations": iters, "converged": ok, "worst_rel_residual": worst_err,
                        "l2": "inputs larger than L2 (no flush needed)" if rows * cols * 8 * nb > 2.6e8 else
                              "scene fits L2; mask re-upload + re-index between steps, no explicit flush",
@@ -358,7 +371,8 @@ def run_e2e(args, w, ctx, sab, mask, bands, guides, world, dev, barrier):
     np_bands = [t.numpy() for t in h_bands]
     np_guides = [t.numpy() for t in h_guides] if poisson else None
     precond = sab.MULTIGRID if args.precond == "multigrid" else sab.JACOBI
-    opts = dict(tolerance=args.tol, precond=precond)
+    opts = dict(tolerance=args.tol, precond=precond,
+                mg_variant=sab.MG_RB32 if args.mg_variant == "rb32" else sab.MG_JACOBI64)
 
     def call():
         # the filled pixels of the previous call are overwritten by the solver's own x0, so re-running on the same

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define SATFILL_ABI_VERSION 1
+#define SATFILL_ABI_VERSION 2
 
 typedef enum sa_status {
     SA_OK = 0,
@@ -55,6 +55,11 @@ typedef enum sa_precond {
     SA_PRECOND_MULTIGRID = 1 /* symmetric V-cycle on the masked grid (DESIGN.md "Multigrid")                       */
 } sa_precond;
 
+typedef enum sa_mg_variant {
+    SA_MG_RB32 = 0,    /* red-black Gauss-Seidel V(1,1), float arithmetic inside the preconditioner (mg_rb.cu)      */
+    SA_MG_JACOBI64 = 1 /* damped-Jacobi V(nu,nu), double (mg_fused.cu / mg.cu)                                      */
+} sa_mg_variant;
+
 /* Solver knobs.  The reference exposes tolerance / max_iterations on Poisson only (poisson.h:45-46); Laplace runs
  * Eigen defaults (epsilon, 2N; laplace.cpp:113-114, IterativeSolverBase.h:251,367-368).  Zero-initialise, then
  * call sa_default_options(). */
@@ -68,7 +73,8 @@ typedef struct sa_options {
     int32_t mg_smooth;      /* multigrid: pre = post smoothing sweeps                                            */
     int32_t profile;        /* != 0: time every solver kernel with CUDA events (sa_stats.kernel_ms)              */
     int32_t mg_unfused;     /* != 0: run the V-cycle one sweep per kernel (reference path of the fused kernels)  */
-    int32_t reserved[2];
+    int32_t mg_variant;     /* sa_mg_variant; CG itself (iterate, residual, operator, dot products) is always double */
+    int32_t reserved[1];
 } sa_options;
 
 /* Per-band solve record (superset of approx::PerfInfo, poisson.h:12-21). */
@@ -85,12 +91,13 @@ typedef struct sa_stats {
     /* sa_options.profile: summed CUDA-event durations and launch counts of the solver kernels of the whole batch,
      * by class: 0 = CG direction (p update + p.Ap), 1 = CG update (x, r, norms), 2 = multigrid single sweeps,
      * 3 = multigrid single transfers (residual, restriction, prolongation), 4 = fused multigrid descent
-     * (pre-smoothing + residual + restriction), 5 = fused multigrid ascent (prolongation + post-smoothing) */
-    double kernel_ms[6];
-    int64_t kernel_launches[6];
+     * (pre-smoothing + residual + restriction) on level 0, 5 = fused multigrid ascent (prolongation + post-smoothing)
+     * on level 0, 6 / 7 = the same two on the coarse levels */
+    double kernel_ms[8];
+    int64_t kernel_launches[8];
     /* unknowns x bands summed over the launches of each class (a multigrid launch on level l counts the unknowns of
      * level l): algorithmic bytes of a class = bytes per unknown x kernel_units */
-    int64_t kernel_units[6];
+    int64_t kernel_units[8];
 } sa_stats;
 
 /* ---- context ------------------------------------------------------------------------------------------------ */
@@ -161,6 +168,11 @@ int sa_scene_get_band(sa_scene* scene, int band, double* dst, int64_t row_stride
 /* After a solve (or any call that indexed the mask): unknowns of the linear system, tiles of the block-sparse layout
  * that hold one, and tiles in total.  Any pointer may be NULL. */
 int sa_scene_info(const sa_scene* scene, int64_t* unknowns, int32_t* active_tiles, int32_t* total_tiles);
+/* Diagnostic hook for the parity tests: z = M^-1 r, one application of the multigrid preconditioner selected by `opts`
+ * to band 0 of a scene whose mask is set.  r and z are host rows x cols tables (same strides); r is taken at the
+ * unknown cells only, z is zero elsewhere.  Not used by the fill path itself. */
+int sa_scene_precondition(sa_scene* scene, const sa_options* opts, const double* r, double* z, int64_t row_stride,
+    int64_t col_stride);
 /* Blocks until everything queued on the context's stream has finished. */
 int sa_synchronize(sa_ctx* ctx);
 

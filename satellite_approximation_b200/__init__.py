@@ -36,6 +36,8 @@ from ._capi import (  # noqa: F401  (re-exported)
     SA_POISSON as POISSON,
     SA_PRECOND_JACOBI as JACOBI,
     SA_PRECOND_MULTIGRID as MULTIGRID,
+    SA_MG_RB32 as MG_RB32,
+    SA_MG_JACOBI64 as MG_JACOBI64,
     SatfillError,
 )
 
@@ -43,7 +45,7 @@ __all__ = [
     "LogLevel", "set_log_level", "filling_missing_portions_smooth_boundaries", "blend_images_poisson",
     "find_connected_components", "ConnectedComponents", "mask_scan", "unknown_numbering", "valid_neighbours",
     "Context", "Scene", "SolveStats", "default_context", "set_solver_defaults", "last_perf_info",
-    "LAPLACE", "POISSON", "JACOBI", "MULTIGRID", "SatfillError",
+    "LAPLACE", "POISSON", "JACOBI", "MULTIGRID", "MG_RB32", "MG_JACOBI64", "SatfillError",
 ]  # fmt: skip
 
 _log = logging.getLogger("satellite_approximation_b200")
@@ -154,7 +156,7 @@ class Context:
         self._check(self._lib.sa_synchronize(self._h))
 
     def options(self, problem: int, tolerance=None, max_iterations=None, precond=None, check_every=None,
-                mg_levels=None, mg_smooth=None, profile=None, mg_unfused=None) -> _capi.Options:  # fmt: skip
+                mg_levels=None, mg_smooth=None, profile=None, mg_unfused=None, mg_variant=None) -> _capi.Options:  # fmt: skip
         o = _capi.Options()
         self._lib.sa_default_options(C.byref(o), problem)
         if tolerance is not None:
@@ -173,6 +175,8 @@ class Context:
             o.profile = int(bool(profile))
         if mg_unfused is not None:
             o.mg_unfused = int(bool(mg_unfused))
+        if mg_variant is not None:
+            o.mg_variant = int(mg_variant)
         return o
 
     # ---- integer path -----------------------------------------------------------------------------------------
@@ -305,6 +309,15 @@ class Scene:
         self._shape_ok(r, c)
         self.ctx._check(self.ctx._lib.sa_scene_get_band(self._h, band, p, rs, cs, dev))
         return out
+
+    def precondition(self, r: np.ndarray, **opts) -> np.ndarray:
+        """z = M^-1 r: one application of the multigrid preconditioner (diagnostic hook of the parity tests)."""
+        r = np.ascontiguousarray(r, np.float64)
+        self._shape_ok(*r.shape)
+        z = np.empty_like(r)
+        o = self.ctx.options(self.problem, **opts)
+        self.ctx._check(self.ctx._lib.sa_scene_precondition(self._h, C.byref(o), r.ctypes.data, z.ctypes.data, r.shape[1], 1))
+        return z
 
     def info(self) -> dict:
         n, a, t = C.c_int64(), C.c_int32(), C.c_int32()

@@ -13,10 +13,12 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libsatfill.so")
+ABI_VERSION = 2  # SATFILL_ABI_VERSION of include/satfill.h
 
 SA_OK, SA_EMPTY_MASK, SA_NOT_CONVERGED, SA_SIZE_MISMATCH, SA_BAD_ARGUMENT, SA_CUDA_ERROR, SA_NCCL_ERROR, SA_OOM = range(8)
 SA_LAPLACE, SA_POISSON = 0, 1
 SA_PRECOND_JACOBI, SA_PRECOND_MULTIGRID = 0, 1
+SA_MG_RB32, SA_MG_JACOBI64 = 0, 1
 
 STATUS_NAMES = {
     0: "SA_OK", 1: "SA_EMPTY_MASK", 2: "SA_NOT_CONVERGED", 3: "SA_SIZE_MISMATCH", 4: "SA_BAD_ARGUMENT",
@@ -28,7 +30,7 @@ EXPORTS = [
     "sa_create", "sa_destroy", "sa_last_error", "sa_abi_version", "sa_default_options", "sa_kernel_launches",
     "sa_mask_scan", "sa_unknown_numbering", "sa_label_components", "sa_laplace_fill", "sa_poisson_blend",
     "sa_scene_create", "sa_scene_destroy", "sa_scene_set_mask", "sa_scene_set_band", "sa_scene_set_guidance",
-    "sa_scene_solve", "sa_scene_get_band", "sa_scene_info", "sa_synchronize",
+    "sa_scene_solve", "sa_scene_get_band", "sa_scene_info", "sa_scene_precondition", "sa_synchronize",
 ]  # fmt: skip
 
 
@@ -48,7 +50,8 @@ class Options(C.Structure):
         ("mg_smooth", C.c_int32),
         ("profile", C.c_int32),
         ("mg_unfused", C.c_int32),
-        ("reserved", C.c_int32 * 2),
+        ("mg_variant", C.c_int32),
+        ("reserved", C.c_int32 * 1),
     ]
 
 
@@ -63,9 +66,9 @@ class Stats(C.Structure):
         ("setup_ms", C.c_double),
         ("status", C.c_int32),
         ("active_tiles", C.c_int32),
-        ("kernel_ms", C.c_double * 6),
-        ("kernel_launches", C.c_int64 * 6),
-        ("kernel_units", C.c_int64 * 6),
+        ("kernel_ms", C.c_double * 8),
+        ("kernel_launches", C.c_int64 * 8),
+        ("kernel_units", C.c_int64 * 8),
     ]
 
     def as_dict(self) -> dict:
@@ -131,10 +134,12 @@ def load() -> C.CDLL:
     L.sa_scene_get_band.argtypes = [_vp, C.c_int, _vp, _i64, _i64, C.c_int]
     L.sa_scene_info.restype = C.c_int
     L.sa_scene_info.argtypes = [_vp, C.POINTER(_i64), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+    L.sa_scene_precondition.restype = C.c_int
+    L.sa_scene_precondition.argtypes = [_vp, C.POINTER(Options), _vp, _vp, _i64, _i64]
     L.sa_synchronize.restype = C.c_int
     L.sa_synchronize.argtypes = [_vp]
-    if L.sa_abi_version() != 1:
-        raise ImportError(f"{LIB_PATH}: ABI version {L.sa_abi_version()} != 1")
+    if L.sa_abi_version() != ABI_VERSION:
+        raise ImportError(f"{LIB_PATH}: ABI version {L.sa_abi_version()} != {ABI_VERSION}")
     _lib = L
     return L
 

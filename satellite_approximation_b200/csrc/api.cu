@@ -472,6 +472,31 @@ int sa_scene_get_band(sa_scene* s, int band, double* dst, int64_t row_stride, in
     return SA_OK;
 }
 
+int sa_scene_precondition(sa_scene* s, const sa_options* opts, const double* r, double* z, int64_t row_stride,
+    int64_t col_stride)
+{
+    if (!s)
+        return SA_BAD_ARGUMENT;
+    SA_TRY(check_ctx(s->ctx));
+    if (!s->mask_set || !r || !z)
+        return fail(s->ctx, SA_BAD_ARGUMENT, "scene_precondition: no mask set or null buffers");
+    SA_TRY(scene_orient(s, row_stride, col_stride));
+    sa_options o;
+    if (opts)
+        o = *opts;
+    else
+        sa_default_options(&o, s->problem);
+    o.precond = SA_PRECOND_MULTIGRID;
+    SA_TRY(ensure_indexed(s));
+    SA_TRY(copy_in<double>(s, s->plane0(s->r, 0), r, row_stride, col_stride, 0, 0, s->rows));
+    SA_TRY(precondition_scene(s, o));
+    SA_TRY(copy_out<double>(s, s->plane0(s->p[0], 0), z, row_stride, col_stride, 0, 0, s->rows));
+    SA_CUDA(s->ctx, cudaStreamSynchronize(s->ctx->stream));
+    // the work vectors must be zero outside the unknown set and consistent for the next solve: re-clear them
+    s->indexed = false;
+    return SA_OK;
+}
+
 int sa_scene_info(const sa_scene* s, int64_t* unknowns, int32_t* active_tiles, int32_t* total_tiles)
 {
     if (!s)

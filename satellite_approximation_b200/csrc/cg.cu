@@ -128,8 +128,8 @@ __global__ void __launch_bounds__(CG_THREADS) k_zero_unknowns(Level lv, double* 
 // ---------------------------------------------------------------------------------------------------------------
 
 // k_direction: p' = z + beta p, pq = p'.Ap'.   JACOBI: z = r / d computed on the fly (zin = r).  Otherwise zin = z.
-template <bool JACOBI>
-__global__ void __launch_bounds__(CG_THREADS, 8) k_direction(Level lv, const double* __restrict__ zin,
+template <bool JACOBI, typename ZT>
+__global__ void __launch_bounds__(CG_THREADS, 8) k_direction(Level lv, const ZT* __restrict__ zin,
     const double* __restrict__ p_old, double* __restrict__ p_new, BandScalars* __restrict__ scal, int k)
 {
     __shared__ double sp[TILE_H + 2][SP];
@@ -158,14 +158,14 @@ __global__ void __launch_bounds__(CG_THREADS, 8) k_direction(Level lv, const dou
     int tile = lv.tile_list[blockIdx.x];
     int64_t r0 = (int64_t)(tile / lv.tiles_x) * TILE_H, c0 = (int64_t)(tile % lv.tiles_x) * TILE_W;
     int64_t boff = (int64_t)blockIdx.y * lv.plane;
-    const double* zb = zin + boff;
+    const ZT* zb = zin + boff;
     const double* pb = p_old + boff;
     double* pn = p_new + boff;
     int64_t rows = lv.rows, cols = lv.cols;
     stage_tile<2>(
         sp, lv.umask, r0, c0, lv.pitch,
         [&](int64_t idx, double* v) {
-            v[0] = zb[idx];
+            v[0] = (double)zb[idx];
             v[1] = pb[idx];
         },
         [&](const double* v, int64_t idx, int64_t r, int64_t c, bool interior) {
@@ -329,12 +329,69 @@ int ensure_indexed(sa_scene* s)
     return SA_OK;
 }
 
+// ---- diagnostic: one application of the preconditioner (sa_scene_precondition) ---------------------------------------
+__global__ void __launch_bounds__(256) k_mask_plane(double* __restrict__ v, const uint8_t* __restrict__ umask, int64_t n)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        if (!umask[i])
+            v[i] = 0.0;
+}
+
+template <typename ZT>
+__global__ void __launch_bounds__(256) k_widen_plane(const ZT* __restrict__ z, const uint8_t* __restrict__ umask,
+    double* __restrict__ out, int64_t n)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = umask[i] ? (double)z[i] : 0.0;
+}
+
+static int ensure_multigrid(sa_scene* s, const sa_options& o)
+{
+    sa_ctx* ctx = s->ctx;
+    if (!s->z) {
+        size_t bytes = (size_t)s->plane * s->nbands * sizeof(double);
+        SA_CUDA(ctx, cudaMalloc(&s->z, bytes));
+        SA_CUDA(ctx, cudaMalloc(&s->t, bytes));
+        SA_CUDA(ctx, cudaMemsetAsync(s->z, 0, bytes, ctx->stream));
+        SA_CUDA(ctx, cudaMemsetAsync(s->t, 0, bytes, ctx->stream));
+    }
+    if (!s->hierarchy_built)
+        SA_TRY(build_hierarchy(s, o));
+    return SA_OK;
+}
+
+int precondition_scene(sa_scene* s, const sa_options& o)
+{
+    sa_ctx* ctx = s->ctx;
+    SA_TRY(ensure_multigrid(s, o));
+    const int64_t n = (int64_t)s->rows_p * s->pitch;  // the plane without its guard rows
+    const uint8_t* um = s->mask0(s->umask);
+    SA_LAUNCH(ctx, k_mask_plane, 1024, 256, 0, s->plane0(s->r, 0), um, n);
+    SA_CUDA(ctx, cudaMemsetAsync(s->scal, 0, sizeof(BandScalars) * s->nbands, ctx->stream));
+    if (s->n_unknowns == 0) {
+        SA_CUDA(ctx, cudaMemsetAsync(s->p[0], 0, (size_t)s->plane * sizeof(double), ctx->stream));
+        return SA_OK;
+    }
+    KernelTimer kt;
+    kt.ctx = ctx;
+    if (o.mg_variant == SA_MG_RB32) {
+        SA_TRY(apply_vcycle_rb(s, o, kt, 0, s->nbands));
+        SA_LAUNCH(ctx, k_widen_plane<float>, 1024, 256, 0, (const float*)s->z + s->pitch, um, s->plane0(s->p[0], 0), n);
+    } else {
+        SA_TRY(apply_vcycle(s, o, kt, 0, s->nbands));
+        SA_LAUNCH(ctx, k_widen_plane<double>, 1024, 256, 0, s->plane0(s->z, 0), um, s->plane0(s->p[0], 0), n);
+    }
+    SA_CUDA(ctx, cudaGetLastError());
+    return SA_OK;
+}
+
 int solve_scene(sa_scene* s, const sa_options& o, sa_stats* stats)
 {
     sa_ctx* ctx = s->ctx;
     const int nb = s->nbands;
     const bool poisson = s->problem == SA_POISSON;
     const bool mg = o.precond == SA_PRECOND_MULTIGRID;
+    const bool rb = mg && o.mg_variant == SA_MG_RB32;
     SA_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
     SA_TRY(ensure_indexed(s));
     const int64_t n = s->n_unknowns;
@@ -357,17 +414,8 @@ int solve_scene(sa_scene* s, const sa_options& o, sa_stats* stats)
                 stats[b].status = SA_EMPTY_MASK;
         return SA_EMPTY_MASK;
     }
-    if (mg) {
-        if (!s->z) {
-            size_t bytes = (size_t)s->plane * nb * sizeof(double);
-            SA_CUDA(ctx, cudaMalloc(&s->z, bytes));
-            SA_CUDA(ctx, cudaMalloc(&s->t, bytes));
-            SA_CUDA(ctx, cudaMemsetAsync(s->z, 0, bytes, ctx->stream));
-            SA_CUDA(ctx, cudaMemsetAsync(s->t, 0, bytes, ctx->stream));
-        }
-        if (!s->hierarchy_built)
-            SA_TRY(build_hierarchy(s, o));
-    }
+    if (mg)
+        SA_TRY(ensure_multigrid(s, o));
 
     Level lv = fine_level(s);
     dim3 grid((unsigned)lv.n_tiles, (unsigned)nb), block(CG_BLOCK_X, CG_BLOCK_Y);
@@ -405,17 +453,26 @@ int solve_scene(sa_scene* s, const sa_options& o, sa_stats* stats)
             const double* pin = pbuf[k & 1];
             double* pout = pbuf[(k + 1) & 1];
             if (mg) {
-                SA_TRY(apply_vcycle(s, o, kt, ki & 3, live));  // z = M^-1 r, rz[slot] accumulated by its last kernel
-                kt.begin(KC_DIRECTION, n * live);
-                SA_LAUNCH(ctx, k_direction<false>, grid, block, 0, lv, s->plane0(s->z, 0), pin, pout, s->scal, ki);
-                kt.end();
+                // z = M^-1 r, rz[slot] accumulated by the cycle's last kernel
+                if (rb) {
+                    SA_TRY(apply_vcycle_rb(s, o, kt, ki & 3, live));
+                    kt.begin(KC_DIRECTION, n * live);
+                    SA_LAUNCH(ctx, (k_direction<false, float>), grid, block, 0, lv, (const float*)s->z + s->pitch, pin, pout,
+                        s->scal, ki);
+                    kt.end();
+                } else {
+                    SA_TRY(apply_vcycle(s, o, kt, ki & 3, live));
+                    kt.begin(KC_DIRECTION, n * live);
+                    SA_LAUNCH(ctx, (k_direction<false, double>), grid, block, 0, lv, s->plane0(s->z, 0), pin, pout, s->scal, ki);
+                    kt.end();
+                }
                 kt.begin(KC_UPDATE, n * live);
                 SA_LAUNCH(ctx, k_update<false>, grid, block, 0, lv, u0, pout, r0, s->scal, ki);
                 kt.end();
                 SA_LAUNCH(ctx, k_check_converged, (nb + 63) / 64, 64, 0, s->scal, nb, ki + 1);
             } else {
                 kt.begin(KC_DIRECTION, n * live);
-                SA_LAUNCH(ctx, k_direction<true>, grid, block, 0, lv, r0, pin, pout, s->scal, ki);
+                SA_LAUNCH(ctx, (k_direction<true, double>), grid, block, 0, lv, r0, pin, pout, s->scal, ki);
                 kt.end();
                 kt.begin(KC_UPDATE, n * live);
                 SA_LAUNCH(ctx, k_update<true>, grid, block, 0, lv, u0, pout, r0, s->scal, ki);

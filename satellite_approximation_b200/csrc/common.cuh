@@ -171,7 +171,10 @@ inline int fail(sa_ctx* ctx, int status, const std::string& msg)
 inline int64_t round_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
 
 // Kernel classes reported in sa_stats.kernel_ms / kernel_launches when sa_options.profile is set.
-enum KernelClass { KC_DIRECTION = 0, KC_UPDATE = 1, KC_SMOOTH = 2, KC_TRANSFER = 3, KC_MG_DOWN = 4, KC_MG_UP = 5, KC_COUNT = 6 };
+enum KernelClass {
+    KC_DIRECTION = 0, KC_UPDATE = 1, KC_SMOOTH = 2, KC_TRANSFER = 3, KC_MG_DOWN = 4, KC_MG_UP = 5, KC_MG_DOWN_COARSE = 6,
+    KC_MG_UP_COARSE = 7, KC_COUNT = 8
+};
 
 // Brackets individual launches with CUDA events on the launching stream; the pairs are resolved after the next
 // stream synchronisation (flush).  Off unless profiling was requested: the events cost ~1 us of launch gap each.
@@ -247,6 +250,8 @@ int device_label_components(sa_ctx* ctx, const uint8_t* mask, int64_t rows, int6
 int ensure_indexed(sa_scene* s);
 int solve_scene(sa_scene* s, const sa_options& o, sa_stats* stats);
 Level fine_level(const sa_scene* s);
+// z = M^-1 r on band 0: r is taken from s->r (masked here), the result is left as doubles in s->p[0]
+int precondition_scene(sa_scene* s, const sa_options& o);
 
 // ---- mg_fused.cu -------------------------------------------------------------------------------------------------
 int launch_mg_down(sa_ctx* ctx, const Level& lf, const Level& lc, int nbands, const double* b, double* x_out, double* bc,
@@ -259,5 +264,9 @@ int build_hierarchy(sa_scene* s, const sa_options& o);
 void free_hierarchy(sa_scene* s);
 // z = M^{-1} r for every band that is not done (one symmetric V-cycle); r.z is accumulated into rz[rz_slot]
 int apply_vcycle(sa_scene* s, const sa_options& o, KernelTimer& kt, int rz_slot, int live_bands);
+
+// ---- mg_rb.cu ---------------------------------------------------------------------------------------------------
+// the same for the red-black float cycle: z is a FLOAT plane in s->z
+int apply_vcycle_rb(sa_scene* s, const sa_options& o, KernelTimer& kt, int rz_slot, int live_bands);
 
 }  // namespace satfill

@@ -386,7 +386,7 @@ int apply_vcycle(sa_scene* s, const sa_options& o, KernelTimer& kt, int rz_slot,
     // descend
     for (int l = 0; l < nl - 1; ++l) {
         if (fused) {
-            kt.begin(KC_MG_DOWN, L[l].units);
+            kt.begin(l == 0 ? KC_MG_DOWN : KC_MG_DOWN_COARSE, L[l].units);
             SA_TRY(launch_mg_down(ctx, L[l].lv, L[l + 1].lv, nb, L[l].b, L[l].x, L[l + 1].b, scal));
             kt.end();
             continue;
@@ -413,7 +413,7 @@ int apply_vcycle(sa_scene* s, const sa_options& o, KernelTimer& kt, int rz_slot,
         LevelVecs& F = L[l];
         LevelVecs& C = L[l + 1];
         if (fused) {
-            kt.begin(KC_MG_UP, F.units);
+            kt.begin(l == 0 ? KC_MG_UP : KC_MG_UP_COARSE, F.units);
             SA_TRY(launch_mg_up(ctx, F.lv, C.lv, nb, F.x, F.b, C.x, F.t, scal, l == 0 ? rz_slot : -1));
             kt.end();
             double* tmp = F.x;  // the result sits in t: swap the level's buffers

@@ -95,4 +95,17 @@ __device__ __forceinline__ void stage_tile(double (*sp)[SP], const uint8_t* __re
     }
 }
 
+// Unknown set of column x of the (32 + 2H)^2 neighbourhood of tile (ty, tx): bit (row + H) <=> cell
+// (r0 + row, c0 - H + x) is an unknown, row in [-H, 32 + H).
+template <int H>
+__device__ __forceinline__ unsigned long long region_col_mask(const Level& lv, int ty, int tx, int x)
+{
+    int gc = x - H;
+    int txx = tx + (gc < 0 ? -1 : (gc >= TILE_W ? 1 : 0));
+    const uint32_t* w = lv.tbitsT + ((size_t)(ty + 1) * lv.tb_stride + (txx + 1)) * 32 + (gc & 31);
+    const size_t vs = (size_t)lv.tb_stride * 32;
+    unsigned long long C = w[0], N = *(w - vs), Sx = w[vs];
+    return (N >> (32 - H)) | (C << H) | ((Sx & ((1ull << H) - 1)) << (32 + H));
+}
+
 }  // namespace satfill

@@ -37,14 +37,14 @@ def test_library_exports_every_declared_symbol():
     out = subprocess.run(["nm", "-D", "--defined-only", _capi.LIB_PATH], capture_output=True, text=True, check=True).stdout
     exported = {line.split()[-1] for line in out.splitlines() if " T " in line}
     assert set(header_symbols()) <= exported
-    assert lib.sa_abi_version() == 1
+    assert lib.sa_abi_version() == 2
 
 
 def test_struct_layouts_match_header():
     from satellite_approximation_b200 import _capi
 
     assert ctypes.sizeof(_capi.Options) == 8 + 8 + 4 * 4 + 16
-    assert ctypes.sizeof(_capi.Stats) == 8 * 3 + 8 * 4 + 4 * 2 + 3 * 8 * 6
+    assert ctypes.sizeof(_capi.Stats) == 8 * 3 + 8 * 4 + 4 * 2 + 3 * 8 * 8
     lib = _capi.load()
     o = _capi.Options()
     lib.sa_default_options(ctypes.byref(o), _capi.SA_POISSON)

@@ -343,13 +343,86 @@ def test_fused_multigrid_kernels_match_single_sweep_kernels(ctx):
         for unfused in (True, False):
             work = [x.copy() for x in f]
             if problem == sab.LAPLACE:
-                st = ctx.laplace_fill(work, mask, tolerance=1e-11, precond=sab.MULTIGRID, mg_unfused=unfused)
+                st = ctx.laplace_fill(work, mask, tolerance=1e-11, precond=sab.MULTIGRID, mg_unfused=unfused,
+                                      mg_variant=sab.MG_JACOBI64)  # fmt: skip
             else:
                 st = ctx.poisson_blend(work, g, mask, tolerance=1e-11, max_iterations=1000, precond=sab.MULTIGRID,
-                                       mg_unfused=unfused)  # fmt: skip
+                                       mg_unfused=unfused, mg_variant=sab.MG_JACOBI64)  # fmt: skip
             assert all(s["status"] == sab.SA_OK for s in st)
             outs.append(work)
             stats.append(st)
         for b in range(2):
             assert abs(stats[0][b]["iterations"] - stats[1][b]["iterations"]) <= 1
             assert rel_max_abs(outs[0][b], outs[1][b], mask) < 1e-9
+
+
+# ---- the red-black float V-cycle (mg_rb.cu), the default preconditioner ------------------------------------------------
+def _prototype():
+    import importlib.util
+    import os
+
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "mg_prototype.py")
+    spec = importlib.util.spec_from_file_location("mg_prototype", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+@pytest.mark.parametrize("shape", [(96, 128), (391, 517), (40, 33)])
+def test_rb_preconditioner_matches_numpy_prototype_and_is_symmetric(ctx, shape):
+    """One application z = M^-1 r of the CUDA V-cycle against the numpy statement of the same algorithm
+    (tools/mg_prototype.py: red-black Gauss-Seidel V(1,1), float, mask injection, full weighting / bilinear), and
+    <u, M^-1 v> = <v, M^-1 u>: CG needs a symmetric preconditioner."""
+    proto = _prototype()
+    rows, cols = shape
+    mask = synth.blob_mask(rows, cols, cover=0.45, sigma=7.0, seed=5)  # border cleared: Laplace unknowns = mask
+    rng = np.random.default_rng(3)
+    sc = ctx.scene(sab.LAPLACE, rows, cols, 1)
+    sc.set_mask(mask)
+    mg = proto.MG(mask, smoother="rb1", dtype=np.float32, coarse_sweeps=32)
+    zs, rs = [], []
+    for _ in range(2):
+        r = np.where(mask, rng.standard_normal(shape), 0.0)
+        z = sc.precondition(r, mg_variant=sab.MG_RB32)
+        want = mg.apply(r)
+        assert not z[~mask].any()
+        assert np.max(np.abs(z - want)) < 2e-5 * np.max(np.abs(want)), shape
+        zs.append(z)
+        rs.append(r)
+    a, b = float((rs[0] * zs[1]).sum()), float((rs[1] * zs[0]).sum())
+    assert abs(a - b) < 1e-4 * max(abs(a), abs(b), 1e-30)
+    assert float((rs[0] * zs[0]).sum()) > 0  # positive definite
+    sc.close()
+
+
+@pytest.mark.parametrize("variant", ["rb32", "jacobi64"])
+def test_multigrid_variants_reach_the_same_fill(ctx, variant):
+    """The preconditioner only changes the path of CG, not its fixed point: both variants meet a tight tolerance and
+    agree with the Jacobi-preconditioned solve; the float cycle does not limit the attainable accuracy."""
+    rows, cols = 300, 413
+    f = [synth.smooth_band(rows, cols, seed=2), synth.smooth_band(rows, cols, seed=9)]
+    mask = synth.blob_mask(rows, cols, cover=0.4, sigma=8.0, seed=4)
+    ref = [x.copy() for x in f]
+    ctx.laplace_fill(ref, mask, tolerance=1e-13, precond=sab.JACOBI)
+    work = [x.copy() for x in f]
+    v = sab.MG_RB32 if variant == "rb32" else sab.MG_JACOBI64
+    st = ctx.laplace_fill(work, mask, tolerance=1e-12, precond=sab.MULTIGRID, mg_variant=v)
+    assert all(s["status"] == sab.SA_OK and s["error"] <= 1e-12 for s in st)
+    assert max(s["iterations"] for s in st) < 40
+    for b in range(2):
+        assert rel_max_abs(work[b], ref[b], mask) < 1e-9
+        assert np.array_equal(work[b][~mask], f[b][~mask])
+
+
+def test_rb_multigrid_tiny_and_degenerate_scenes(ctx, port):
+    """Scenes too small for a coarse level (the coarsest-level kernel is the whole cycle), single rows / columns."""
+    for shape in ((3, 3), (5, 4), (1, 40), (40, 1), (7, 70)):
+        img = synth.smooth_band(*shape, seed=4)
+        mask = np.ones(shape, bool)
+        mask[0, 0] = False  # one known pixel: without it the Poisson system is singular
+        g = img * 0.5 + 3.0
+        want, _ = port.poisson_blend([img], [g], mask, tol=1e-12, max_it=100000)
+        work = [img.copy()]
+        st = ctx.poisson_blend(work, [g], mask, tolerance=1e-12, max_iterations=100000, precond=sab.MULTIGRID)
+        if np.isfinite(want[0]).all() and st[0]["status"] == sab.SA_OK:
+            assert rel_max_abs(work[0], want[0], mask) < 1e-6, shape
