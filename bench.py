@@ -62,6 +62,7 @@ def parse_args():
     ap.add_argument("--tol", type=float, default=1e-6)
     ap.add_argument("--precond", default=os.environ.get("SATFILL_PRECOND", "multigrid"), choices=["jacobi", "multigrid"])
     ap.add_argument("--mg-variant", default=os.environ.get("SATFILL_MG_VARIANT", "rb32"), choices=["rb32", "jacobi64"])
+    ap.add_argument("--cg-variant", type=int, default=int(os.environ.get("SATFILL_CG_VARIANT", "0")), choices=[0, 1])
     ap.add_argument("--check-every", type=int, default=0)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -233,7 +234,7 @@ def run_b200(args, w):
         if poisson:
             scene.set_guidance(b, guides[b])
     variant = sab.MG_RB32 if args.mg_variant == "rb32" else sab.MG_JACOBI64
-    opts = dict(tolerance=args.tol, precond=precond, profile=True, mg_variant=variant)
+    opts = dict(tolerance=args.tol, precond=precond, profile=True, mg_variant=variant, cg_variant=args.cg_variant)
     if args.check_every:
         opts["check_every"] = args.check_every
 
@@ -335,7 +336,7 @@ def run_b200(args, w):
             "config": {"workload": w["desc"], "problem": w["problem"], "rows": rows, "cols": cols, "bands": nb,
                        "unknowns_per_band": unknowns, "tolerance": args.tol, "precond": args.precond,
                        "mg_variant": args.mg_variant if args.precond == "multigrid" else None,
-                       "cg_iterations": iters, "converged": ok, "worst_rel_residual": worst_err,
+                       "cg_iterations": iters, "cg_iterations_per_band": [s["iterations"] for s in st], "converged": ok, "worst_rel_residual": worst_err,
                        "l2": "inputs larger than L2 (no flush needed)" if rows * cols * 8 * nb > 2.6e8 else
                              "scene fits L2; mask re-upload + re-index between steps, no explicit flush",
                        "parallelism": f"{world} independent scene(s), one per GPU, no collective"},
@@ -371,7 +372,7 @@ def run_e2e(args, w, ctx, sab, mask, bands, guides, world, dev, barrier):
     np_bands = [t.numpy() for t in h_bands]
     np_guides = [t.numpy() for t in h_guides] if poisson else None
     precond = sab.MULTIGRID if args.precond == "multigrid" else sab.JACOBI
-    opts = dict(tolerance=args.tol, precond=precond,
+    opts = dict(tolerance=args.tol, precond=precond, cg_variant=args.cg_variant,
                 mg_variant=sab.MG_RB32 if args.mg_variant == "rb32" else sab.MG_JACOBI64)
 
     def call():

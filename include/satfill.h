@@ -2,7 +2,7 @@
  * ebiederstadt/satellite-approximation (lib/approx).
  *
  * This is the drop-in boundary: plain pointers and sizes, no C++ / torch / Eigen types.  The C++ `approx`
- * shim (cpp/include/approx/*.h), the pybind11 module `satellite_approximation._core` and the ctypes binding
+ * shim (cpp/include/approx/ headers), the pybind11 module `satellite_approximation._core` and the ctypes binding
  * (satellite_approximation_b200/_capi.py) all sit on exactly these entry points.  Each entry point names the
  * reference interface it replaces (paths relative to the reference repository root).
  *
@@ -74,7 +74,7 @@ typedef struct sa_options {
     int32_t profile;        /* != 0: time every solver kernel with CUDA events (sa_stats.kernel_ms)              */
     int32_t mg_unfused;     /* != 0: run the V-cycle one sweep per kernel (reference path of the fused kernels)  */
     int32_t mg_variant;     /* sa_mg_variant; CG itself (iterate, residual, operator, dot products) is always double */
-    int32_t reserved[1];
+    int32_t cg_variant;     /* 0: strip kernels (cg_strip.cu); 1: first-generation staged-tile kernels (cg.cu)          */
 } sa_options;
 
 /* Per-band solve record (superset of approx::PerfInfo, poisson.h:12-21). */

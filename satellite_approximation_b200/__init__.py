@@ -156,7 +156,7 @@ class Context:
         self._check(self._lib.sa_synchronize(self._h))
 
     def options(self, problem: int, tolerance=None, max_iterations=None, precond=None, check_every=None,
-                mg_levels=None, mg_smooth=None, profile=None, mg_unfused=None, mg_variant=None) -> _capi.Options:  # fmt: skip
+                mg_levels=None, mg_smooth=None, profile=None, mg_unfused=None, mg_variant=None, cg_variant=None) -> _capi.Options:  # fmt: skip
         o = _capi.Options()
         self._lib.sa_default_options(C.byref(o), problem)
         if tolerance is not None:
@@ -177,6 +177,8 @@ class Context:
             o.mg_unfused = int(bool(mg_unfused))
         if mg_variant is not None:
             o.mg_variant = int(mg_variant)
+        if cg_variant is not None:
+            o.cg_variant = int(cg_variant)
         return o
 
     # ---- integer path -----------------------------------------------------------------------------------------

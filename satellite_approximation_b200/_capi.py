@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libsatfill.so")
+LIB_PATH = os.environ.get("SATFILL_LIB") or os.path.join(_HERE, "lib", "libsatfill.so")  # SATFILL_LIB: tuning builds
 ABI_VERSION = 2  # SATFILL_ABI_VERSION of include/satfill.h
 
 SA_OK, SA_EMPTY_MASK, SA_NOT_CONVERGED, SA_SIZE_MISMATCH, SA_BAD_ARGUMENT, SA_CUDA_ERROR, SA_NCCL_ERROR, SA_OOM = range(8)
@@ -51,7 +51,7 @@ class Options(C.Structure):
         ("profile", C.c_int32),
         ("mg_unfused", C.c_int32),
         ("mg_variant", C.c_int32),
-        ("reserved", C.c_int32 * 1),
+        ("cg_variant", C.c_int32),
     ]
 
 

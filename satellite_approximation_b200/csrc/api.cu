@@ -88,7 +88,7 @@ int scene_alloc(sa_scene* s, bool transposed)
     SA_CUDA(ctx, cudaMalloc(&s->umask, (size_t)s->plane));
     SA_CUDA(ctx, cudaMemsetAsync(s->mask, 0, (size_t)s->plane, ctx->stream));
     SA_CUDA(ctx, cudaMemsetAsync(s->umask, 0, (size_t)s->plane, ctx->stream));
-    SA_CUDA(ctx, cudaMalloc(&s->tile_list, sizeof(int32_t) * 2 * (size_t)s->tiles_x * s->tiles_y));
+    SA_CUDA(ctx, cudaMalloc(&s->tile_list, sizeof(int32_t) * 3 * (size_t)s->tiles_x * s->tiles_y));
     {
         size_t words = (size_t)(s->tiles_x + 2) * (s->tiles_y + 2) * 32;
         s->tb_words = words;
@@ -382,7 +382,7 @@ int sa_scene_create(sa_ctx* ctx, int problem, int64_t rows, int64_t cols, int nb
     SA_TRY(check_ctx(ctx));
     if (!out || rows < 0 || cols < 0 || nbands < 1 || (problem != SA_LAPLACE && problem != SA_POISSON))
         return fail(ctx, SA_BAD_ARGUMENT, "scene_create: bad arguments");
-    if ((rows + 64) * (cols + 64) > (int64_t)INT32_MAX * 2)
+    if ((rows + 64) * (cols + 64) > (int64_t)INT32_MAX * 2 || rows > (1 << 20) || cols > (1 << 20))
         return fail(ctx, SA_BAD_ARGUMENT, "scene_create: scene too large for one device plane");
     sa_scene* s = new (std::nothrow) sa_scene();
     if (!s)

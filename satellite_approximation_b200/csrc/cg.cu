@@ -41,7 +41,7 @@ __global__ void __launch_bounds__(CG_THREADS) k_init_guess(Level lv, double* __r
 // ConjugateGradient.h:38-61 for the rest.
 template <bool POISSON>
 __global__ void __launch_bounds__(CG_THREADS) k_residual(Level lv, const double* __restrict__ u, const double* __restrict__ g,
-    double* __restrict__ rvec, BandScalars* __restrict__ scal)
+    double* __restrict__ rvec, float* __restrict__ rf, BandScalars* __restrict__ scal)
 {
     __shared__ double s_red[CG_BLOCK_Y];
     int tile = lv.tile_list[blockIdx.x];
@@ -68,6 +68,8 @@ __global__ void __launch_bounds__(CG_THREADS) k_residual(Level lv, const double*
             r2 += res * res;
             rz += res * res * inv_diag(r, c, lv.rows, lv.cols);
             rvec[boff + idx] = res;
+            if (rf)
+                rf[boff + idx] = (float)res;
         }
     }
     double t;
@@ -193,9 +195,10 @@ __global__ void __launch_bounds__(CG_THREADS, 8) k_direction(Level lv, const ZT*
 }
 
 // k_update: alpha = rz / pq; x += alpha p; r -= alpha A p; new |r|^2 and (JACOBI) r.(r/d) into slot k+1.
-template <bool JACOBI>
+// RF: also write the residual as float for the red-black cycle (mg_rb.cu), which then never reads a double.
+template <bool JACOBI, bool RF>
 __global__ void __launch_bounds__(CG_THREADS, 8) k_update(Level lv, double* __restrict__ u, const double* __restrict__ p,
-    double* __restrict__ rvec, BandScalars* __restrict__ scal, int k)
+    double* __restrict__ rvec, float* __restrict__ rf, BandScalars* __restrict__ scal, int k)
 {
     __shared__ double sp[TILE_H + 2][SP];
     __shared__ double s_red[CG_BLOCK_Y];
@@ -240,6 +243,8 @@ __global__ void __launch_bounds__(CG_THREADS, 8) k_update(Level lv, double* __re
             ub[base + j * rstep] = xv[j] + alpha * pc;  // ConjugateGradient.h:69
             double rn = rv[j] - alpha * q;               // ConjugateGradient.h:70
             rb[base + j * rstep] = rn;
+            if (RF)
+                rf[boff + base + j * rstep] = (float)rn;
             r2 += rn * rn;
             if (JACOBI)
                 rz += rn * rn * inv_diag(r, c, rows, cols);
@@ -303,6 +308,7 @@ Level fine_level(const sa_scene* s)
     lv.n_tiles = s->n_active_tiles;
     lv.umask = s->mask0(s->umask);
     lv.tile_list = s->tile_list;
+    lv.tile_yx = s->tile_list + 2 * (size_t)s->tiles_x * s->tiles_y;
     lv.fixed_diag = s->problem == SA_LAPLACE;
     lv.tbits = s->tbits;
     lv.tbitsT = s->tbits + s->tb_words;
@@ -335,6 +341,12 @@ __global__ void __launch_bounds__(256) k_mask_plane(double* __restrict__ v, cons
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
         if (!umask[i])
             v[i] = 0.0;
+}
+
+__global__ void __launch_bounds__(256) k_narrow_plane(const double* __restrict__ v, float* __restrict__ out, int64_t n)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = (float)v[i];
 }
 
 template <typename ZT>
@@ -375,8 +387,9 @@ int precondition_scene(sa_scene* s, const sa_options& o)
     KernelTimer kt;
     kt.ctx = ctx;
     if (o.mg_variant == SA_MG_RB32) {
+        SA_LAUNCH(ctx, k_narrow_plane, 1024, 256, 0, s->plane0(s->r, 0), s->rb_rf(), n);
         SA_TRY(apply_vcycle_rb(s, o, kt, 0, s->nbands));
-        SA_LAUNCH(ctx, k_widen_plane<float>, 1024, 256, 0, (const float*)s->z + s->pitch, um, s->plane0(s->p[0], 0), n);
+        SA_LAUNCH(ctx, k_widen_plane<float>, 1024, 256, 0, s->rb_z(), um, s->plane0(s->p[0], 0), n);
     } else {
         SA_TRY(apply_vcycle(s, o, kt, 0, s->nbands));
         SA_LAUNCH(ctx, k_widen_plane<double>, 1024, 256, 0, s->plane0(s->z, 0), um, s->plane0(s->p[0], 0), n);
@@ -392,6 +405,7 @@ int solve_scene(sa_scene* s, const sa_options& o, sa_stats* stats)
     const bool poisson = s->problem == SA_POISSON;
     const bool mg = o.precond == SA_PRECOND_MULTIGRID;
     const bool rb = mg && o.mg_variant == SA_MG_RB32;
+    const bool strip = o.cg_variant == 0;
     SA_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
     SA_TRY(ensure_indexed(s));
     const int64_t n = s->n_unknowns;
@@ -427,10 +441,10 @@ int solve_scene(sa_scene* s, const sa_options& o, sa_stats* stats)
     SA_CUDA(ctx, cudaMemsetAsync(s->scal, 0, sizeof(BandScalars) * nb, ctx->stream));
     if (poisson) {
         SA_LAUNCH(ctx, k_init_guess<true>, grid, block, 0, lv, u0, g0);
-        SA_LAUNCH(ctx, k_residual<true>, grid, block, 0, lv, u0, g0, r0, s->scal);
+        SA_LAUNCH(ctx, k_residual<true>, grid, block, 0, lv, u0, g0, r0, rb ? s->rb_rf() : nullptr, s->scal);
     } else {
         SA_LAUNCH(ctx, k_init_guess<false>, grid, block, 0, lv, u0, g0);
-        SA_LAUNCH(ctx, k_residual<false>, grid, block, 0, lv, u0, g0, r0, s->scal);
+        SA_LAUNCH(ctx, k_residual<false>, grid, block, 0, lv, u0, g0, r0, rb ? s->rb_rf() : nullptr, s->scal);
     }
     SA_LAUNCH(ctx, k_finalize_setup, (nb + 63) / 64, 64, 0, s->scal, nb, o.tolerance, mg ? 1 : 0);
     SA_CUDA(ctx, cudaGetLastError());
@@ -454,28 +468,44 @@ int solve_scene(sa_scene* s, const sa_options& o, sa_stats* stats)
             double* pout = pbuf[(k + 1) & 1];
             if (mg) {
                 // z = M^-1 r, rz[slot] accumulated by the cycle's last kernel
+                const void* z;
                 if (rb) {
                     SA_TRY(apply_vcycle_rb(s, o, kt, ki & 3, live));
-                    kt.begin(KC_DIRECTION, n * live);
-                    SA_LAUNCH(ctx, (k_direction<false, float>), grid, block, 0, lv, (const float*)s->z + s->pitch, pin, pout,
-                        s->scal, ki);
-                    kt.end();
+                    z = s->rb_z();
                 } else {
                     SA_TRY(apply_vcycle(s, o, kt, ki & 3, live));
-                    kt.begin(KC_DIRECTION, n * live);
-                    SA_LAUNCH(ctx, (k_direction<false, double>), grid, block, 0, lv, s->plane0(s->z, 0), pin, pout, s->scal, ki);
-                    kt.end();
+                    z = s->plane0(s->z, 0);
                 }
+                float* rf = rb ? s->rb_rf() : nullptr;
+                kt.begin(KC_DIRECTION, n * live);
+                if (strip)
+                    SA_TRY(launch_direction2(ctx, lv, nb, false, z, rb, pin, pout, s->scal, ki));
+                else if (rb)
+                    SA_LAUNCH(ctx, (k_direction<false, float>), grid, block, 0, lv, (const float*)z, pin, pout, s->scal, ki);
+                else
+                    SA_LAUNCH(ctx, (k_direction<false, double>), grid, block, 0, lv, (const double*)z, pin, pout, s->scal, ki);
+                kt.end();
                 kt.begin(KC_UPDATE, n * live);
-                SA_LAUNCH(ctx, k_update<false>, grid, block, 0, lv, u0, pout, r0, s->scal, ki);
+                if (strip)
+                    SA_TRY(launch_update2(ctx, lv, nb, false, u0, pout, r0, rf, s->scal, ki));
+                else if (rb)
+                    SA_LAUNCH(ctx, (k_update<false, true>), grid, block, 0, lv, u0, pout, r0, rf, s->scal, ki);
+                else
+                    SA_LAUNCH(ctx, (k_update<false, false>), grid, block, 0, lv, u0, pout, r0, nullptr, s->scal, ki);
                 kt.end();
                 SA_LAUNCH(ctx, k_check_converged, (nb + 63) / 64, 64, 0, s->scal, nb, ki + 1);
             } else {
                 kt.begin(KC_DIRECTION, n * live);
-                SA_LAUNCH(ctx, (k_direction<true, double>), grid, block, 0, lv, r0, pin, pout, s->scal, ki);
+                if (strip)
+                    SA_TRY(launch_direction2(ctx, lv, nb, true, r0, false, pin, pout, s->scal, ki));
+                else
+                    SA_LAUNCH(ctx, (k_direction<true, double>), grid, block, 0, lv, r0, pin, pout, s->scal, ki);
                 kt.end();
                 kt.begin(KC_UPDATE, n * live);
-                SA_LAUNCH(ctx, k_update<true>, grid, block, 0, lv, u0, pout, r0, s->scal, ki);
+                if (strip)
+                    SA_TRY(launch_update2(ctx, lv, nb, true, u0, pout, r0, nullptr, s->scal, ki));
+                else
+                    SA_LAUNCH(ctx, (k_update<true, false>), grid, block, 0, lv, u0, pout, r0, nullptr, s->scal, ki);
                 kt.end();
             }
         }

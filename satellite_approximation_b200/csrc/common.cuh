@@ -59,6 +59,7 @@ struct Level {
     int n_tiles;          // active tiles
     const uint8_t* umask; // 1 = unknown of the linear system; addressed like a plane (pitch bytes per row)
     const int32_t* tile_list;
+    const int32_t* tile_yx;  // the same list as packed tile coordinates (ty << 16 | tx): no division in the kernels
     int fixed_diag;       // != 0: the diagonal is 4 everywhere (Laplace: unknowns never touch the image border)
     // The same unknown set as one 32-bit word per tile row: word [((ty + 1) * tb_stride + tx + 1) * 32 + row], bit = col.
     // A ring of all-zero tiles surrounds the grid, so neighbourhoods of any tile can be read without bounds checks.
@@ -87,7 +88,7 @@ struct sa_ctx {
 struct sa_level_store {
     satfill::Level lv {};
     uint8_t* umask_alloc = nullptr;    // base of the allocation (guard row included)
-    int32_t* tile_list = nullptr;      // 2 * tiles entries: list, then per-tile flags
+    int32_t* tile_list = nullptr;      // 3 * tiles entries: list, per-tile flags, packed (ty, tx) list
     int32_t* d_counters = nullptr;     // {active tiles, first, last, -}
     uint32_t* tbits = nullptr;  // row words, then (at +tb_words) the transposed column words
     size_t tb_words = 0;
@@ -133,6 +134,10 @@ struct sa_scene {
     bool hierarchy_built = false;
 
     double* plane0(double* base, int band) const { return base + (int64_t)band * plane + pitch; }
+    // float planes of the red-black cycle (mg_rb.cu) inside the z allocation: z itself, then the float copy of the
+    // CG residual that k_update / k_residual write for it
+    float* rb_z() const { return (float*)z + pitch; }
+    float* rb_rf() const { return (float*)z + (int64_t)plane * nbands + pitch; }
     uint8_t* mask0(uint8_t* base) const { return base + pitch; }
 };
 
@@ -237,7 +242,8 @@ int device_numbering(sa_ctx* ctx, const uint8_t* mask, int64_t rows, int64_t col
     int64_t* out_pixels, int64_t capacity, int64_t* out_count, int64_t bbox[4]);
 // flags[n_tiles] -> raster-ordered list of the flagged tiles; d_n_active (device, 4 ints) receives
 // {count, first tile, last tile}
-int compact_tile_flags(sa_ctx* ctx, const int32_t* flags, int n_tiles, int32_t* tile_list, int32_t* d_n_active);
+int compact_tile_flags(sa_ctx* ctx, const int32_t* flags, int n_tiles, int tiles_x, int32_t* tile_list, int32_t* tile_yx,
+    int32_t* d_n_active);
 // exclusive scan helper shared with ccl.cu: in place over `n` 64-bit counters, total written to *total
 int device_scan_u64(sa_ctx* ctx, unsigned long long* data, int64_t n, unsigned long long* total);
 
@@ -252,6 +258,12 @@ int solve_scene(sa_scene* s, const sa_options& o, sa_stats* stats);
 Level fine_level(const sa_scene* s);
 // z = M^-1 r on band 0: r is taken from s->r (masked here), the result is left as doubles in s->p[0]
 int precondition_scene(sa_scene* s, const sa_options& o);
+
+// ---- cg_strip.cu: the two kernels of a CG iteration, shared-memory-free generation ---------------------------------
+int launch_direction2(sa_ctx* ctx, const Level& lv, int nbands, bool jacobi, const void* zin, bool z_is_float,
+    const double* p_old, double* p_new, BandScalars* scal, int k);
+int launch_update2(sa_ctx* ctx, const Level& lv, int nbands, bool jacobi, double* u, const double* p, double* r, float* rf,
+    BandScalars* scal, int k);
 
 // ---- mg_fused.cu -------------------------------------------------------------------------------------------------
 int launch_mg_down(sa_ctx* ctx, const Level& lf, const Level& lc, int nbands, const double* b, double* x_out, double* bc,

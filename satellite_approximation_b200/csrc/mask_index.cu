@@ -106,8 +106,8 @@ __global__ void __launch_bounds__(CG_THREADS) k_build_unknown_set(uint8_t* __res
     }
 }
 
-__global__ void __launch_bounds__(1024) k_compact_flags(const int32_t* __restrict__ flags, int n_tiles,
-    int32_t* __restrict__ tile_list, int32_t* __restrict__ n_active)
+__global__ void __launch_bounds__(1024) k_compact_flags(const int32_t* __restrict__ flags, int n_tiles, int tiles_x,
+    int32_t* __restrict__ tile_list, int32_t* __restrict__ tile_yx, int32_t* __restrict__ n_active)
 {
     // single CTA, raster order: running offset + block-wide ballot scan
     __shared__ int warp_tot[32];
@@ -127,8 +127,10 @@ __global__ void __launch_bounds__(1024) k_compact_flags(const int32_t* __restric
         int woff = 0;
         for (int w = 0; w < warp; ++w)
             woff += warp_tot[w];
-        if (f)
+        if (f) {
             tile_list[base + woff + pre] = i;
+            tile_yx[base + woff + pre] = ((i / tiles_x) << 16) | (i % tiles_x);
+        }
         __syncthreads();
         if (threadIdx.x == 0) {
             int t = 0;
@@ -146,9 +148,10 @@ __global__ void __launch_bounds__(1024) k_compact_flags(const int32_t* __restric
 }
 
 // Shared by the fine level (index_scene) and the multigrid coarse levels: flags -> raster-ordered list + count.
-int compact_tile_flags(sa_ctx* ctx, const int32_t* flags, int n_tiles, int32_t* tile_list, int32_t* d_n_active)
+int compact_tile_flags(sa_ctx* ctx, const int32_t* flags, int n_tiles, int tiles_x, int32_t* tile_list, int32_t* tile_yx,
+    int32_t* d_n_active)
 {
-    SA_LAUNCH(ctx, k_compact_flags, 1, 1024, 0, flags, n_tiles, tile_list, d_n_active);
+    SA_LAUNCH(ctx, k_compact_flags, 1, 1024, 0, flags, n_tiles, tiles_x, tile_list, tile_yx, d_n_active);
     SA_CUDA(ctx, cudaGetLastError());
     return SA_OK;
 }
@@ -157,14 +160,14 @@ int index_scene(sa_scene* s)
 {
     sa_ctx* ctx = s->ctx;
     int n_tiles = s->tiles_x * s->tiles_y;
-    int32_t* flags = s->tile_list + n_tiles;  // tile_list is allocated with 2 * n_tiles entries
+    int32_t* flags = s->tile_list + n_tiles;  // tile_list is allocated with 3 * n_tiles entries
     SA_CUDA(ctx, cudaMemsetAsync(s->d_counters, 0, 4 * sizeof(int32_t), ctx->stream));
     SA_CUDA(ctx, cudaMemsetAsync(s->d_count64, 0, sizeof(unsigned long long), ctx->stream));
     dim3 block(CG_BLOCK_X, CG_BLOCK_Y);
     SA_LAUNCH(ctx, k_build_unknown_set, n_tiles, block, 0, s->mask0(s->mask), s->mask0(s->umask), s->rows, s->cols,
         s->pitch, s->tiles_x, s->problem == SA_LAPLACE ? 1 : 0, flags, s->d_count64, s->tbits, s->tbits + s->tb_words);
     SA_CUDA(ctx, cudaGetLastError());
-    SA_TRY(compact_tile_flags(ctx, flags, n_tiles, s->tile_list, s->d_counters));
+    SA_TRY(compact_tile_flags(ctx, flags, n_tiles, s->tiles_x, s->tile_list, s->tile_list + 2 * n_tiles, s->d_counters));
     struct readback {
         int32_t counters[4];
         unsigned long long n;

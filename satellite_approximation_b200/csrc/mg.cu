@@ -113,7 +113,7 @@ static int alloc_hierarchy(sa_scene* s, const sa_options& o)
         size_t vec = (size_t)L.lv.plane * s->nbands * sizeof(double);
         SA_CUDA(ctx, cudaMalloc(&L.umask_alloc, (size_t)L.lv.plane));
         SA_CUDA(ctx, cudaMemsetAsync(L.umask_alloc, 0, (size_t)L.lv.plane, ctx->stream));
-        SA_CUDA(ctx, cudaMalloc(&L.tile_list, sizeof(int32_t) * 2 * (size_t)L.lv.tiles_x * L.lv.tiles_y));
+        SA_CUDA(ctx, cudaMalloc(&L.tile_list, sizeof(int32_t) * 3 * (size_t)L.lv.tiles_x * L.lv.tiles_y));
         SA_CUDA(ctx, cudaMalloc(&L.d_counters, sizeof(int32_t) * 4 + sizeof(unsigned long long)));
         SA_CUDA(ctx, cudaMalloc(&L.x, vec));
         SA_CUDA(ctx, cudaMalloc(&L.b, vec));
@@ -124,6 +124,7 @@ static int alloc_hierarchy(sa_scene* s, const sa_options& o)
         SA_CUDA(ctx, cudaMemsetAsync(L.tbits, 0, 2 * words * sizeof(uint32_t), ctx->stream));
         L.lv.umask = L.umask_alloc + L.lv.pitch;
         L.lv.tile_list = L.tile_list;
+        L.lv.tile_yx = L.tile_list + 2 * (size_t)L.lv.tiles_x * L.lv.tiles_y;
         L.lv.tbits = L.tbits;
         L.lv.tbitsT = L.tbits + words;
         L.lv.tb_stride = L.lv.tiles_x + 2;
@@ -150,7 +151,7 @@ int build_hierarchy(sa_scene* s, const sa_options& o)
         uint8_t* cmask = L.umask_alloc + L.lv.pitch;
         SA_LAUNCH(ctx, k_coarsen_mask, n_tiles, block, 0, fmask, fpitch, cmask, L.lv.rows, L.lv.cols, L.lv.pitch,
             L.lv.tiles_x, flags, count64, L.tbits, L.tbits + L.tb_words);
-        SA_TRY(compact_tile_flags(ctx, flags, n_tiles, L.tile_list, L.d_counters));
+        SA_TRY(compact_tile_flags(ctx, flags, n_tiles, L.lv.tiles_x, L.tile_list, L.tile_list + 2 * n_tiles, L.d_counters));
         size_t vec = (size_t)L.lv.plane * s->nbands * sizeof(double);
         SA_CUDA(ctx, cudaMemsetAsync(L.x, 0, vec, ctx->stream));
         SA_CUDA(ctx, cudaMemsetAsync(L.b, 0, vec, ctx->stream));

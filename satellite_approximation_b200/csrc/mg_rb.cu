@@ -32,9 +32,17 @@ namespace satfill {
 
 namespace {
 
-constexpr int RB_HP = 20;  // threads per row group (half columns, padded): lane-linear shared-memory addressing
-constexpr int RB_RG = 4;   // rows per thread
-constexpr int RB_S = 21;   // row stride of the colour-split arrays: RB_RG * RB_S = 84 = 20 (mod 32) => bank = thread id
+constexpr int RB_HP = 20;  // threads per row group (half columns): lane-linear shared-memory addressing
+#ifndef SATFILL_RB_DOWN_RG
+#define SATFILL_RB_DOWN_RG 4
+#endif
+#ifndef SATFILL_RB_UP_RG
+#define SATFILL_RB_UP_RG 6
+#endif
+// rows per thread: even, so that the row parity is the parity of the unrolled row index
+constexpr int RB_DOWN_RG = SATFILL_RB_DOWN_RG, RB_UP_RG = SATFILL_RB_UP_RG;
+// row stride S of the colour-split arrays with RG * S = 20 (mod 32): shared-memory bank = thread id + constant
+__host__ __device__ constexpr int rb_stride(int rg) { return rg == 4 ? 21 : (rg == 6 ? 30 : (rg == 10 ? 34 : (rg == 12 ? 23 : -1))); }
 constexpr unsigned long long EVEN_ROWS = 0x5555555555555555ull;
 
 template <bool FIXED>
@@ -46,86 +54,123 @@ __device__ __forceinline__ float rb_winv(const Level& lv, int64_t r, int64_t c)
     return n == 4 ? 0.25f : (n == 3 ? (1.0f / 3.0f) : (n == 2 ? 0.5f : 1.0f));
 }
 
-// red / black unknown bits of the thread's half column: bit i <=> region row i
+// red / black unknown bits of the thread's half column (frame columns 2h, 2h + 1): bit i <=> frame row i
 template <int H>
 __device__ __forceinline__ void colour_masks(const Level& lv, int ty, int tx, int h, unsigned long long& red,
     unsigned long long& black)
 {
-    constexpr int W = TILE_W + 2 * H;
-    unsigned long long cm0 = 2 * h < W ? region_col_mask<H>(lv, ty, tx, 2 * h) : 0ull;
-    unsigned long long cm1 = 2 * h + 1 < W ? region_col_mask<H>(lv, ty, tx, 2 * h + 1) : 0ull;
+    unsigned long long cm0 = region_col_mask<H>(lv, ty, tx, 2 * h);
+    unsigned long long cm1 = region_col_mask<H>(lv, ty, tx, 2 * h + 1);
     red = (cm0 & EVEN_ROWS) | (cm1 & ~EVEN_ROWS);
     black = (cm1 & EVEN_ROWS) | (cm0 & ~EVEN_ROWS);
+}
+
+// bit k <=> frame row row0 + k lies in [lo, hi)
+template <int RG>
+__device__ __forceinline__ unsigned rb_rows(int row0, int lo, int hi)
+{
+    return (unsigned)((((1ull << hi) - 1) & ~((1ull << lo) - 1)) >> row0) & ((1u << RG) - 1);
+}
+// bit k <=> the column of the thread's red (black) cell in row row0 + k lies in [lo, hi); red cells sit in column
+// 2h + (k & 1), black cells in column 2h + 1 - (k & 1)
+template <int RG>
+__device__ __forceinline__ unsigned rb_cols(int h, int lo, int hi, bool red)
+{
+    constexpr unsigned KM = (1u << RG) - 1, EV = 0x55555555u & KM, OD = 0xAAAAAAAAu & KM;
+    bool c0 = 2 * h >= lo && 2 * h < hi, c1 = 2 * h + 1 >= lo && 2 * h + 1 < hi;
+    return red ? ((c0 ? EV : 0u) | (c1 ? OD : 0u)) : ((c1 ? EV : 0u) | (c0 ? OD : 0u));
+}
+
+// predicated read-only loads: one instruction, no branch; 0 when the predicate is off
+__device__ __forceinline__ float ldg_if(const float* p, unsigned pred)
+{
+    float v;
+    asm("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\tmov.f32 %0, 0f00000000;\n\t@q ld.global.nc.f32 %0, [%1];\n\t}"
+        : "=f"(v)
+        : "l"(p), "r"(pred));
+    return v;
+}
+__device__ __forceinline__ float2 ldg2_if(const float* p, unsigned pred)
+{
+    float2 v;
+    asm("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %3, 0;\n\tmov.f32 %0, 0f00000000;\n\tmov.f32 %1, 0f00000000;\n\t"
+        "@q ld.global.nc.v2.f32 {%0, %1}, [%2];\n\t}"
+        : "=f"(v.x), "=f"(v.y)
+        : "l"(p), "r"(pred));
+    return v;
 }
 
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------------------------
-// descent: pre-smoothing from zero, residual, restriction
+// descent: pre-smoothing from zero, residual, restriction.  The dependence region has a halo of 3 cells; it is
+// framed with a halo of 4 (40 x 40, outer ring unused) so that a half column is an 8-byte aligned pair of cells.
 // ---------------------------------------------------------------------------------------------------------------
-template <bool FIXED, typename BT>
-__global__ void __launch_bounds__(RB_HP * 10) k_rb_down(Level lf, Level lc, const BT* __restrict__ b,
+constexpr int RB_DOWN_NG = (TILE_W + 8 + RB_DOWN_RG - 1) / RB_DOWN_RG;
+constexpr int RB_UP_NG = (TILE_W + 4 + RB_UP_RG - 1) / RB_UP_RG;
+
+template <bool FIXED>
+__global__ void __launch_bounds__(RB_HP * RB_DOWN_NG) k_rb_down(Level lf, Level lc, const float* __restrict__ b,
     float* __restrict__ xr, float* __restrict__ bc, const BandScalars* __restrict__ scal)
 {
-    constexpr int H = 3, W = TILE_W + 2 * H;  // 38
-    constexpr int NG = (W + RB_RG - 1) / RB_RG;  // 10 row groups
+    constexpr int H = 4, W = TILE_W + 2 * H;  // frame 40 x 40; cells used: frame rows / columns 1 .. 38
+    constexpr int RG = RB_DOWN_RG, NG = RB_DOWN_NG, S = rb_stride(RG);
+    static_assert(S > 0 && (RG * S) % 32 == 20 && RG % 2 == 0, "unsupported rows per thread");
     constexpr int THREADS = RB_HP * NG;
-    constexpr int ROWS = NG * RB_RG + 2;  // one spare row above and below: the sliding window needs no bounds checks
-    __shared__ float R[ROWS * RB_S];
-    __shared__ float B[ROWS * RB_S];
+    constexpr int ROWS = NG * RG + 2;  // one spare row above and below: the sliding window needs no bounds checks
+    constexpr unsigned KM = (1u << RG) - 1;
+    __shared__ float R[ROWS * S];
+    __shared__ float B[ROWS * S];
     if (scal[blockIdx.y].done)
         return;
-    const int t = threadIdx.x, h = t % RB_HP, y = t / RB_HP;
-    const int tile = lf.tile_list[blockIdx.x];
-    const int ty = tile / lf.tiles_x, tx = tile % lf.tiles_x;
-    const int64_t r0 = (int64_t)ty * TILE_H, c0 = (int64_t)tx * TILE_W;
-    const int row0 = RB_RG * y;
+    const int t = threadIdx.x, y = t / RB_HP, h = t - y * RB_HP;
+    const int yx = lf.tile_yx[blockIdx.x];
+    const int ty = yx >> 16, tx = yx & 0xffff;
+    const int row0 = RG * y;
+    const int pitch = (int)lf.pitch, pitch2 = pitch >> 1;
     unsigned long long redm, blkm;
     colour_masks<H>(lf, ty, tx, h, redm, blkm);
-    const unsigned rm = (unsigned)(redm >> row0) & 15u, bm = (unsigned)(blkm >> row0) & 15u;
-    const int64_t gr = r0 - H + row0, gc = c0 - H + 2 * h;  // global position of (row0, column 2h)
-    // ---- global loads: the right-hand side at the thread's 2 x 4 cells
-    float bred[RB_RG], bblk[RB_RG];
+    const unsigned rm = (unsigned)(redm >> row0) & KM & rb_rows<RG>(row0, 1, W - 1) & rb_cols<RG>(h, 1, W - 1, true);
+    const unsigned bm = (unsigned)(blkm >> row0) & KM & rb_rows<RG>(row0, 2, W - 2) & rb_cols<RG>(h, 2, W - 2, false);
+    const int64_t gr = (int64_t)ty * TILE_H - H, gc = (int64_t)tx * TILE_W - H;  // global position of the frame origin
+    const int toff = row0 * pitch + 2 * h;                                       // the thread's (row0, column 2h) in it
+    // ---- global loads: the right-hand side at the thread's RG x 2 cells, one aligned pair per row
+    float bred[RG], bblk[RG];
     {
-        const BT* bp = b + (int64_t)blockIdx.y * lf.plane + gr * lf.pitch + gc;
-        BT vr[RB_RG], vb[RB_RG];
+        const float* bp = b + (int64_t)blockIdx.y * lf.plane + gr * lf.pitch + gc;
+        const unsigned ld = rm | bm;
 #pragma unroll
-        for (int k = 0; k < RB_RG; ++k) {
-            vr[k] = ((rm >> k) & 1) ? bp[k * lf.pitch + (k & 1)] : BT(0);
-            vb[k] = ((bm >> k) & 1) ? bp[k * lf.pitch + 1 - (k & 1)] : BT(0);
-        }
-#pragma unroll
-        for (int k = 0; k < RB_RG; ++k) {
-            bred[k] = (float)vr[k];
-            bblk[k] = (float)vb[k];
+        for (int k = 0; k < RG; ++k) {
+            float2 v = ldg2_if(bp + (toff + k * pitch), (ld >> k) & 1);
+            bred[k] = (k & 1) ? v.y : v.x;
+            bblk[k] = (k & 1) ? v.x : v.y;
         }
     }
-    const int sb = (row0 + 1) * RB_S + h;  // shared index of (row0, h)
+    const int sb = (row0 + 1) * S + h;  // shared index of (row0, h)
     // ---- red half-sweep from zero: x = b / d (pointwise); the tile's own red cells go to HBM colour-split
     {
-        float* xo = xr + (int64_t)blockIdx.y * (lf.plane >> 1) + gr * (lf.pitch >> 1);
+        float* xo = xr + (int64_t)blockIdx.y * (lf.plane >> 1) + gr * pitch2 + (gc >> 1);
+        const int toff2 = row0 * pitch2 + h;
+        const unsigned own = rm & rb_rows<RG>(row0, H, H + TILE_H) & rb_cols<RG>(h, H, H + TILE_W, true);
 #pragma unroll
-        for (int k = 0; k < RB_RG; ++k) {
-            const int row = row0 + k, col = 2 * h + (k & 1);
-            float v = rb_winv<FIXED>(lf, gr + k, gc + (k & 1)) * bred[k];
-            R[sb + k * RB_S] = v;
-            if (((rm >> k) & 1) && row >= H && row < H + TILE_H && col >= H && col < H + TILE_W)
-                xo[k * (lf.pitch >> 1) + ((gc + (k & 1)) >> 1)] = v;
+        for (int k = 0; k < RG; ++k) {
+            float v = rb_winv<FIXED>(lf, gr + row0 + k, gc + 2 * h + (k & 1)) * (((rm >> k) & 1) ? bred[k] : 0.f);
+            R[sb + k * S] = v;
+            if ((own >> k) & 1)
+                xo[toff2 + k * pitch2] = v;
         }
     }
     __syncthreads();
-    // ---- black half-sweep on rows / columns 1 .. W-2
+    // ---- black half-sweep on frame rows / columns 2 .. 37
     {
         const float* p = R + sb;
-        float n = p[-RB_S], c = p[0];
+        float n = p[-S], c = p[0];
 #pragma unroll
-        for (int k = 0; k < RB_RG; ++k) {
-            const int row = row0 + k, col = 2 * h + 1 - (k & 1);
-            float s = p[(k + 1) * RB_S];
-            float side = p[k * RB_S + ((k & 1) ? -1 : 1)];
-            float v = rb_winv<FIXED>(lf, gr + k, gc + 1 - (k & 1)) * (bblk[k] + ((n + s) + (c + side)));
-            bool on = ((bm >> k) & 1) && row >= 1 && row < W - 1 && col >= 1 && col < W - 1;
-            B[sb + k * RB_S] = on ? v : 0.f;
+        for (int k = 0; k < RG; ++k) {
+            float s = p[(k + 1) * S];
+            float side = p[k * S + ((k & 1) ? -1 : 1)];
+            float v = rb_winv<FIXED>(lf, gr + row0 + k, gc + 2 * h + 1 - (k & 1)) * (bblk[k] + ((n + s) + (c + side)));
+            B[sb + k * S] = ((bm >> k) & 1) ? v : 0.f;
             n = c;
             c = s;
         }
@@ -133,32 +178,32 @@ __global__ void __launch_bounds__(RB_HP * 10) k_rb_down(Level lf, Level lc, cons
     __syncthreads();
     // ---- residual: zero at black cells; at a red cell b - d x + sum(black neighbours) = sum(black neighbours)
     {
+        const unsigned on = rm & rb_rows<RG>(row0, 3, W - 3) & rb_cols<RG>(h, 3, W - 3, true);
         const float* p = B + sb;
-        float n = p[-RB_S], c = p[0];
+        float n = p[-S], c = p[0];
 #pragma unroll
-        for (int k = 0; k < RB_RG; ++k) {
-            const int row = row0 + k, col = 2 * h + (k & 1);
-            float s = p[(k + 1) * RB_S];
-            float side = p[k * RB_S + ((k & 1) ? 1 : -1)];
+        for (int k = 0; k < RG; ++k) {
+            float s = p[(k + 1) * S];
+            float side = p[k * S + ((k & 1) ? 1 : -1)];
             float v = (n + s) + (c + side);
-            bool on = ((rm >> k) & 1) && row >= 2 && row < W - 2 && col >= 2 && col < W - 2;
-            R[sb + k * RB_S] = on ? v : 0.f;  // R is dead as an iterate: reuse it for the residual
+            R[sb + k * S] = ((on >> k) & 1) ? v : 0.f;  // R is dead as an iterate: reuse it for the residual
             n = c;
             c = s;
         }
     }
     __syncthreads();
-    // ---- full-weighting restriction: coarse (ci, cj) <-> tile cell (2ci, 2cj) = region (2ci + 3, 2cj + 3), a red
-    //      cell in an odd row (half column cj + 1); its diagonal neighbours are the red cells of the rows above and
+    // ---- full-weighting restriction: coarse (ci, cj) <-> tile cell (2ci, 2cj) = frame (2ci + 4, 2cj + 4), a red
+    //      cell in an even row (half column cj + 2); its diagonal neighbours are the red cells of the rows above and
     //      below in half columns cj + 1 and cj + 2; its edge neighbours are black (zero residual).
     {
-        float* bco = bc + (int64_t)blockIdx.y * lc.plane + (r0 >> 1) * lc.pitch + (c0 >> 1);
+        float* bco = bc + (int64_t)blockIdx.y * lc.plane + (int64_t)(ty * (TILE_H / 2)) * lc.pitch + tx * (TILE_W / 2);
+        const int cpitch = (int)lc.pitch;
         const uint32_t* rowbits = lf.tbits + ((size_t)(ty + 1) * lf.tb_stride + (tx + 1)) * 32;
         for (int i = t; i < (TILE_H / 2) * (TILE_W / 2); i += THREADS) {
             int ci = i >> 4, cj = i & 15;
             if ((rowbits[2 * ci] >> (2 * cj)) & 1) {  // mask injection: coarse unknown <=> fine (2I, 2J) unknown
-                const float* p = R + (2 * ci + H + 1) * RB_S + cj + 1;
-                bco[ci * lc.pitch + cj] = p[0] + 0.25f * ((p[-RB_S] + p[-RB_S + 1]) + (p[RB_S] + p[RB_S + 1]));
+                const float* p = R + (2 * ci + H + 1) * S + cj + 2;
+                bco[ci * cpitch + cj] = p[0] + 0.25f * ((p[-S - 1] + p[-S]) + (p[S - 1] + p[S]));
             }
         }
     }
@@ -167,127 +212,135 @@ __global__ void __launch_bounds__(RB_HP * 10) k_rb_down(Level lf, Level lc, cons
 // ---------------------------------------------------------------------------------------------------------------
 // ascent: prolongation + correction (red cells only), post-smoothing black then red, (level 0) r.z
 // ---------------------------------------------------------------------------------------------------------------
-template <bool FIXED, typename BT, bool DOT>
-__global__ void __launch_bounds__(RB_HP * 9) k_rb_up(Level lf, Level lc, const float* __restrict__ xr,
-    const BT* __restrict__ b, const float* __restrict__ ec, float* __restrict__ x_out, BandScalars* __restrict__ scal,
+template <bool FIXED, bool DOT>
+__global__ void __launch_bounds__(RB_HP * RB_UP_NG) k_rb_up(Level lf, Level lc, const float* __restrict__ xr,
+    const float* __restrict__ b, const float* __restrict__ ec, float* __restrict__ x_out, BandScalars* __restrict__ scal,
     int slot)
 {
     constexpr int H = 2, W = TILE_W + 2 * H;  // 36
-    constexpr int NG = W / RB_RG;             // 9 row groups
+    constexpr int RG = RB_UP_RG, NG = RB_UP_NG, S = rb_stride(RG);
+    static_assert(S > 0 && (RG * S) % 32 == 20 && RG % 2 == 0, "unsupported rows per thread");
     constexpr int THREADS = RB_HP * NG;
-    constexpr int ROWS = NG * RB_RG + 2;
-    constexpr int EW = W / 2 + 1, ES = EW + 2;  // 19 x 19 coarse cells cover the region
-    __shared__ float R[ROWS * RB_S];
-    __shared__ float B[ROWS * RB_S];
-    __shared__ float E[EW * ES];
-    __shared__ double s_red[(THREADS + 31) / 32];
+    constexpr int ROWS = NG * RG + 2;
+    constexpr int EW = W / 2 + 1, ES = RB_HP + 1;  // 19 x 19 coarse cells cover the region
+    constexpr int EROWS = (NG * RG) / 2 + 2;
+    constexpr unsigned KM = (1u << RG) - 1;
+    __shared__ float R[ROWS * S];
+    __shared__ float B[ROWS * S];
+    __shared__ float E[EROWS * ES];
+    __shared__ float s_acc[DOT ? THREADS : 1];
     if (scal[blockIdx.y].done)
         return;
-    const int t = threadIdx.x, h = t % RB_HP, y = t / RB_HP;
-    const int tile = lf.tile_list[blockIdx.x];
-    const int ty = tile / lf.tiles_x, tx = tile % lf.tiles_x;
-    const int64_t r0 = (int64_t)ty * TILE_H, c0 = (int64_t)tx * TILE_W;
-    const int row0 = RB_RG * y;
-    unsigned long long redm, blkm;
-    colour_masks<H>(lf, ty, tx, h, redm, blkm);
-    const unsigned rm = (unsigned)(redm >> row0) & 15u, bm = (unsigned)(blkm >> row0) & 15u;
-    const int64_t gr = r0 - H + row0, gc = c0 - H + 2 * h;
+    const int t = threadIdx.x, y = t / RB_HP, h = t - y * RB_HP;
+    const int yx = lf.tile_yx[blockIdx.x];
+    const int ty = yx >> 16, tx = yx & 0xffff;
+    const int row0 = RG * y;
+    const int pitch = (int)lf.pitch, pitch2 = pitch >> 1;
+    unsigned long long redm = 0, blkm = 0;
+    if (h < W / 2)
+        colour_masks<H>(lf, ty, tx, h, redm, blkm);
+    const unsigned rm = (unsigned)(redm >> row0) & KM;
+    const unsigned on_blk = (unsigned)(blkm >> row0) & KM & rb_rows<RG>(row0, 1, W - 1) & rb_cols<RG>(h, 1, W - 1, false);
+    const unsigned own_rows = rb_rows<RG>(row0, H, H + TILE_H);
+    const unsigned own_red = rm & own_rows & rb_cols<RG>(h, H, H + TILE_W, true);
+    const unsigned own_blk = on_blk & own_rows & rb_cols<RG>(h, H, H + TILE_W, false);
+    const int64_t gr = (int64_t)ty * TILE_H - H, gc = (int64_t)tx * TILE_W - H;
+    const int toff = row0 * pitch + 2 * h;
     const int64_t goff = (int64_t)blockIdx.y * lf.plane + gr * lf.pitch + gc;
     // ---- global loads first: red x on the whole region, b where an update needs it, the coarse correction
-    float xv[RB_RG], bred[RB_RG], bblk[RB_RG];
+    float xv[RG], bred[RG], bblk[RG];
     {
-        const float* xp = xr + (int64_t)blockIdx.y * (lf.plane >> 1) + gr * (lf.pitch >> 1);
-        const BT* bp = b + goff;
-        BT vr[RB_RG], vb[RB_RG];
+        const float* xp = xr + (int64_t)blockIdx.y * (lf.plane >> 1) + gr * pitch2 + (gc >> 1);
+        const float* bp = b + goff;
+        const int toff2 = row0 * pitch2 + h;
+        const unsigned ld = own_red | on_blk;
 #pragma unroll
-        for (int k = 0; k < RB_RG; ++k) {
-            const int row = row0 + k, cr = 2 * h + (k & 1), cb = 2 * h + 1 - (k & 1);
-            bool red = (rm >> k) & 1, blk = (bm >> k) & 1;
-            xv[k] = red ? xp[k * (lf.pitch >> 1) + ((gc + (k & 1)) >> 1)] : 0.f;
-            vr[k] = (red && row >= H && row < H + TILE_H && cr >= H && cr < H + TILE_W) ? bp[k * lf.pitch + (k & 1)] : BT(0);
-            vb[k] = (blk && row >= 1 && row < W - 1 && cb >= 1 && cb < W - 1) ? bp[k * lf.pitch + 1 - (k & 1)] : BT(0);
+        for (int k = 0; k < RG; ++k) {
+            xv[k] = ldg_if(xp + (toff2 + k * pitch2), (rm >> k) & 1);
+            float2 v = ldg2_if(bp + (toff + k * pitch), (ld >> k) & 1);
+            bred[k] = (k & 1) ? v.y : v.x;
+            bblk[k] = (k & 1) ? v.x : v.y;
         }
-        const float* e = ec + (int64_t)blockIdx.y * lc.plane;
-        const int64_t I0 = (r0 >> 1) - 1, J0 = (c0 >> 1) - 1;
-        for (int i = t; i < EW * EW; i += THREADS) {
-            int ei = i / EW, ej = i - ei * EW;
-            int64_t I = I0 + ei, J = J0 + ej;
-            E[ei * ES + ej] = (I >= 0 && I < lc.rows && J >= 0 && J < lc.cols) ? e[I * lc.pitch + J] : 0.f;
-        }
+        const int cpitch = (int)lc.pitch;
+        const int I0 = ty * (TILE_H / 2) - 1, J = tx * (TILE_W / 2) - 1 + h;
+        const float* e = ec + (int64_t)blockIdx.y * lc.plane + (int64_t)I0 * lc.pitch + J;
+        const bool jok = h < EW && J >= 0 && J < lc.cols;
 #pragma unroll
-        for (int k = 0; k < RB_RG; ++k) {
-            bred[k] = (float)vr[k];
-            bblk[k] = (float)vb[k];
+        for (int q = 0; q < (EW + NG - 1) / NG; ++q) {
+            int ei = y + q * NG;
+            if (ei < EW && h < EW)
+                E[ei * ES + h] = ldg_if(e + ei * cpitch, jok && I0 + ei >= 0 && I0 + ei < lc.rows);
         }
     }
     __syncthreads();
-    const int sb = (row0 + 1) * RB_S + h;
+    const int sb = (row0 + 1) * S + h;
     // ---- R = x + P e at red cells (bilinear; region row / column parity = global parity).  Even rows: the red cell
     //      sits on a coarse point; odd rows: in the middle of four.
     if (h < W / 2) {
+        const float* p = E + (row0 >> 1) * ES + h;
 #pragma unroll
-        for (int k = 0; k < RB_RG; ++k) {
-            const float* p = E + ((row0 + k) >> 1) * ES + h;
-            float pe = (k & 1) ? 0.25f * ((p[0] + p[1]) + (p[ES] + p[ES + 1])) : p[0];
-            R[sb + k * RB_S] = ((rm >> k) & 1) ? xv[k] + pe : 0.f;
+        for (int k = 0; k < RG; ++k) {
+            const float* q = p + (k >> 1) * ES;
+            float pe = (k & 1) ? 0.25f * ((q[0] + q[1]) + (q[ES] + q[ES + 1])) : q[0];
+            R[sb + k * S] = ((rm >> k) & 1) ? xv[k] + pe : 0.f;
         }
     }
     __syncthreads();
-    double acc = 0.0;
-    float* xo = x_out + goff;
+    float acc = 0.f;
+    float vblk[RG];
     // ---- black half-sweep on rows / columns 1 .. W-2; the tile's own black cells are final
     {
         const float* p = R + sb;
-        float n = p[-RB_S], c = p[0];
+        float n = p[-S], c = p[0];
 #pragma unroll
-        for (int k = 0; k < RB_RG; ++k) {
-            const int row = row0 + k, col = 2 * h + 1 - (k & 1);
-            float s = p[(k + 1) * RB_S];
-            float side = p[k * RB_S + ((k & 1) ? -1 : 1)];
-            float v = rb_winv<FIXED>(lf, gr + k, gc + 1 - (k & 1)) * (bblk[k] + ((n + s) + (c + side)));
-            bool on = ((bm >> k) & 1) && row >= 1 && row < W - 1 && col >= 1 && col < W - 1;
-            B[sb + k * RB_S] = on ? v : 0.f;
-            if (on && row >= H && row < H + TILE_H && col >= H && col < H + TILE_W) {
-                xo[k * lf.pitch + 1 - (k & 1)] = v;
-                if (DOT)
-                    acc += (double)bblk[k] * (double)v;
-            }
+        for (int k = 0; k < RG; ++k) {
+            float s = p[(k + 1) * S];
+            float side = p[k * S + ((k & 1) ? -1 : 1)];
+            float v = rb_winv<FIXED>(lf, gr + row0 + k, gc + 2 * h + 1 - (k & 1)) * (bblk[k] + ((n + s) + (c + side)));
+            v = ((on_blk >> k) & 1) ? v : 0.f;
+            B[sb + k * S] = v;
+            vblk[k] = v;
+            if (DOT)
+                acc += ((own_blk >> k) & 1) ? bblk[k] * v : 0.f;
             n = c;
             c = s;
         }
     }
     __syncthreads();
-    // ---- red half-sweep on the tile itself
+    // ---- red half-sweep on the tile itself; both cells of the half column leave as one aligned pair (a cell that
+    //      is not an unknown is written as the zero it already holds)
     {
+        float* xo = x_out + goff;
+        const unsigned st = own_red | own_blk;
         const float* p = B + sb;
-        float n = p[-RB_S], c = p[0];
+        float n = p[-S], c = p[0];
 #pragma unroll
-        for (int k = 0; k < RB_RG; ++k) {
-            const int row = row0 + k, col = 2 * h + (k & 1);
-            float s = p[(k + 1) * RB_S];
-            float side = p[k * RB_S + ((k & 1) ? 1 : -1)];
-            float v = rb_winv<FIXED>(lf, gr + k, gc + (k & 1)) * (bred[k] + ((n + s) + (c + side)));
-            if (((rm >> k) & 1) && row >= H && row < H + TILE_H && col >= H && col < H + TILE_W) {
-                xo[k * lf.pitch + (k & 1)] = v;
-                if (DOT)
-                    acc += (double)bred[k] * (double)v;
-            }
+        for (int k = 0; k < RG; ++k) {
+            float s = p[(k + 1) * S];
+            float side = p[k * S + ((k & 1) ? 1 : -1)];
+            float v = rb_winv<FIXED>(lf, gr + row0 + k, gc + 2 * h + (k & 1)) * (bred[k] + ((n + s) + (c + side)));
+            v = ((own_red >> k) & 1) ? v : 0.f;
+            if (DOT)
+                acc += bred[k] * v;
+            if ((st >> k) & 1)
+                *reinterpret_cast<float2*>(xo + (toff + k * pitch)) = (k & 1) ? make_float2(vblk[k], v) : make_float2(v, vblk[k]);
             n = c;
             c = s;
         }
     }
     if (DOT) {
-        for (int o = 16; o; o >>= 1)
-            acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        if ((t & 31) == 0)
-            s_red[t >> 5] = acc;
+        // per-thread partial sums (a dozen products) in float, everything above that in double.  The CTA is not a whole
+        // number of warps, so the partial sums go through shared memory and the (always complete) first warp adds them.
+        s_acc[t] = acc;
         __syncthreads();
-        if (t == 0) {
-            double sum = 0.0;
-            for (int w = 0; w < (THREADS + 31) / 32; ++w)
-                sum += s_red[w];
-            if (sum != 0.0)
-                atomicAdd(&scal[blockIdx.y].rz[slot], sum);
+        if (t < 32) {
+            double a = 0.0;
+            for (int i = t; i < THREADS; i += 32)
+                a += (double)s_acc[i];
+            for (int o = 16; o; o >>= 1)
+                a += __shfl_xor_sync(0xffffffffu, a, o);
+            if (t == 0 && a != 0.0)
+                atomicAdd(&scal[blockIdx.y].rz[slot], a);
         }
     }
 }
@@ -297,15 +350,15 @@ __global__ void __launch_bounds__(RB_HP * 9) k_rb_up(Level lf, Level lc, const f
 // global memory, one CTA per band over the active tiles of the level (a handful; usually one).  Global writes of a
 // CTA are visible to its own threads after __syncthreads().
 // ---------------------------------------------------------------------------------------------------------------
-template <bool FIXED, typename BT, bool DOT>
-__global__ void __launch_bounds__(1024) k_rb_coarsest(Level lv, const BT* __restrict__ b, float* __restrict__ x,
+template <bool FIXED, bool DOT>
+__global__ void __launch_bounds__(1024) k_rb_coarsest(Level lv, const float* __restrict__ b, float* __restrict__ x,
     BandScalars* __restrict__ scal, int slot, int sweeps)
 {
     __shared__ double s_red[32];
     if (scal[blockIdx.x].done)
         return;
     const int t = threadIdx.x, lr = t >> 5, lc = t & 31;
-    const BT* bb = b + (int64_t)blockIdx.x * lv.plane;
+    const float* bb = b + (int64_t)blockIdx.x * lv.plane;
     float* xb = x + (int64_t)blockIdx.x * lv.plane;
     for (int ti = 0; ti < lv.n_tiles; ++ti) {  // zero start
         int tile = lv.tile_list[ti];
@@ -323,7 +376,7 @@ __global__ void __launch_bounds__(1024) k_rb_coarsest(Level lv, const BT* __rest
             int64_t idx = r * lv.pitch + c;
             if (((r + c) & 1) == colour && lv.umask[idx]) {
                 float nb = (xb[idx - lv.pitch] + xb[idx + lv.pitch]) + (xb[idx - 1] + xb[idx + 1]);
-                xb[idx] = rb_winv<FIXED>(lv, r, c) * ((float)bb[idx] + nb);
+                xb[idx] = rb_winv<FIXED>(lv, r, c) * (bb[idx] + nb);
             }
         }
         __syncthreads();
@@ -359,40 +412,39 @@ namespace {
 struct RBLevel {
     Level lv;
     int64_t units;
-    const void* b;  // level 0: the CG residual (double); coarse levels: float
+    float* b;  // level 0: the float copy of the CG residual
     float* x;       // full plane (level 0: z)
     float* xr;      // colour-split half plane
 };
 
-template <typename BT>
 int launch_down(sa_ctx* ctx, const RBLevel& F, const RBLevel& C, int nb, const BandScalars* scal)
 {
     dim3 grid((unsigned)F.lv.n_tiles, (unsigned)nb);
     if (F.lv.fixed_diag)
-        SA_LAUNCH(ctx, (k_rb_down<true, BT>), grid, RB_HP * 10, 0, F.lv, C.lv, (const BT*)F.b, F.xr, (float*)C.b, scal);
+        SA_LAUNCH(ctx, k_rb_down<true>, grid, RB_HP * RB_DOWN_NG, 0, F.lv, C.lv, F.b, F.xr, C.b, scal);
     else
-        SA_LAUNCH(ctx, (k_rb_down<false, BT>), grid, RB_HP * 10, 0, F.lv, C.lv, (const BT*)F.b, F.xr, (float*)C.b, scal);
+        SA_LAUNCH(ctx, k_rb_down<false>, grid, RB_HP * RB_DOWN_NG, 0, F.lv, C.lv, F.b, F.xr, C.b, scal);
     return SA_OK;
 }
 
-template <typename BT, bool DOT>
+template <bool DOT>
 int launch_up(sa_ctx* ctx, const RBLevel& F, const RBLevel& C, int nb, BandScalars* scal, int slot)
 {
     dim3 grid((unsigned)F.lv.n_tiles, (unsigned)nb);
     if (F.lv.fixed_diag)
-        SA_LAUNCH(ctx, (k_rb_up<true, BT, DOT>), grid, RB_HP * 9, 0, F.lv, C.lv, F.xr, (const BT*)F.b, C.x, F.x, scal, slot);
+        SA_LAUNCH(ctx, (k_rb_up<true, DOT>), grid, RB_HP * RB_UP_NG, 0, F.lv, C.lv, F.xr, F.b, C.x, F.x, scal, slot);
     else
-        SA_LAUNCH(ctx, (k_rb_up<false, BT, DOT>), grid, RB_HP * 9, 0, F.lv, C.lv, F.xr, (const BT*)F.b, C.x, F.x, scal, slot);
+        SA_LAUNCH(ctx, (k_rb_up<false, DOT>), grid, RB_HP * RB_UP_NG, 0, F.lv, C.lv, F.xr, F.b, C.x, F.x, scal, slot);
     return SA_OK;
 }
 
-template <typename BT, bool DOT>
+template <bool DOT>
 int launch_coarsest(sa_ctx* ctx, const RBLevel& L, int nb, BandScalars* scal, int slot, int sweeps)
 {
     if (L.lv.fixed_diag)
-        SA_LAUNCH(ctx, (k_rb_coarsest<true, BT, DOT>), nb, 1024, 0, L.lv, (const BT*)L.b, L.x, scal, slot, sweeps);
+        SA_LAUNCH(ctx, (k_rb_coarsest<true, DOT>), nb, 1024, 0, L.lv, L.b, L.x, scal, slot, sweeps);
     else
-        SA_LAUNCH(ctx, (k_rb_coarsest<false, BT, DOT>), nb, 1024, 0, L.lv, (const BT*)L.b, L.x, scal, slot, sweeps);
+        SA_LAUNCH(ctx, (k_rb_coarsest<false, DOT>), nb, 1024, 0, L.lv, L.b, L.x, scal, slot, sweeps);
     return SA_OK;
 }
 
@@ -405,7 +457,7 @@ int apply_vcycle_rb(sa_scene* s, const sa_options& o, KernelTimer& kt, int rz_sl
     sa_ctx* ctx = s->ctx;
     const int nb = s->nbands;
     std::vector<RBLevel> L;
-    L.push_back({ fine_level(s), s->n_unknowns * live_bands, s->plane0(s->r, 0), (float*)s->z + s->pitch,
+    L.push_back({ fine_level(s), s->n_unknowns * live_bands, s->rb_rf(), s->rb_z(),
         (float*)s->t + (s->pitch >> 1) });
     for (sa_level_store& c : s->coarse) {
         if (c.lv.n_tiles == 0)
@@ -418,28 +470,25 @@ int apply_vcycle_rb(sa_scene* s, const sa_options& o, KernelTimer& kt, int rz_sl
     const int coarse_sweeps = 16;
     if (nl == 1) {
         kt.begin(KC_SMOOTH, L[0].units);
-        SA_TRY((launch_coarsest<double, true>(ctx, L[0], nb, scal, rz_slot, coarse_sweeps)));
+        SA_TRY((launch_coarsest<true>(ctx, L[0], nb, scal, rz_slot, coarse_sweeps)));
         kt.end();
         SA_CUDA(ctx, cudaGetLastError());
         return SA_OK;
     }
     for (int l = 0; l < nl - 1; ++l) {
         kt.begin(l == 0 ? KC_MG_DOWN : KC_MG_DOWN_COARSE, L[l].units);
-        if (l == 0)
-            SA_TRY(launch_down<double>(ctx, L[l], L[l + 1], nb, scal));
-        else
-            SA_TRY(launch_down<float>(ctx, L[l], L[l + 1], nb, scal));
+        SA_TRY(launch_down(ctx, L[l], L[l + 1], nb, scal));
         kt.end();
     }
     kt.begin(KC_SMOOTH, L[nl - 1].units);
-    SA_TRY((launch_coarsest<float, false>(ctx, L[nl - 1], nb, scal, 0, coarse_sweeps)));
+    SA_TRY((launch_coarsest<false>(ctx, L[nl - 1], nb, scal, 0, coarse_sweeps)));
     kt.end();
     for (int l = nl - 2; l >= 0; --l) {
         kt.begin(l == 0 ? KC_MG_UP : KC_MG_UP_COARSE, L[l].units);
         if (l == 0)
-            SA_TRY((launch_up<double, true>(ctx, L[l], L[l + 1], nb, scal, rz_slot)));
+            SA_TRY((launch_up<true>(ctx, L[l], L[l + 1], nb, scal, rz_slot)));
         else
-            SA_TRY((launch_up<float, false>(ctx, L[l], L[l + 1], nb, scal, 0)));
+            SA_TRY((launch_up<false>(ctx, L[l], L[l + 1], nb, scal, 0)));
         kt.end();
     }
     SA_CUDA(ctx, cudaGetLastError());
