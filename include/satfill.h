@@ -102,8 +102,9 @@ typedef struct sa_stats {
 
 /* ---- context ------------------------------------------------------------------------------------------------ */
 
-/* device: CUDA ordinal.  stream: a cudaStream_t the library should launch on (e.g. torch's current stream), or NULL
- * for a stream the context creates and owns. */
+/* device: CUDA ordinal.  stream: a cudaStream_t the library should launch on, or NULL for a (non-blocking) stream the
+ * context creates and owns.  The legacy default stream has handle 0 = NULL: a caller that produces device inputs on
+ * the default stream must synchronise before handing them over, or pass an explicit stream. */
 int sa_create(sa_ctx** out, int device, void* stream);
 void sa_destroy(sa_ctx* ctx);
 const char* sa_last_error(const sa_ctx* ctx);

@@ -15,6 +15,8 @@
 #include "common.cuh"
 #include "tile.cuh"
 
+#include <cstdlib>
+
 namespace satfill {
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -528,6 +530,11 @@ int solve_scene(sa_scene* s, const sa_options& o, sa_stats* stats)
     cudaEventElapsedTime(&setup_ms, ctx->ev[0], ctx->ev[1]);
     cudaEventElapsedTime(&solve_ms, ctx->ev[1], ctx->ev[2]);
     int status = SA_OK;
+    if (std::getenv("SATFILL_DEBUG"))
+        for (int b = 0; b < nb; ++b)
+            std::fprintf(stderr, "[satfill] band %d: bnorm2 %.6e thr %.3e rr_exit %.3e iters %d done %d zero_rhs %d rz %.3e %.3e %.3e %.3e\n",
+                b, h_scal[b].bnorm2, h_scal[b].thr, h_scal[b].rr_exit, h_scal[b].iters, h_scal[b].done, h_scal[b].zero_rhs,
+                h_scal[b].rz[0], h_scal[b].rz[1], h_scal[b].rz[2], h_scal[b].rz[3]);
     for (int b = 0; b < nb; ++b) {
         const BandScalars& sc = h_scal[b];
         int st = sc.done ? SA_OK : SA_NOT_CONVERGED;

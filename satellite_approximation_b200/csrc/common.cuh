@@ -67,6 +67,9 @@ struct Level {
     const uint32_t* tbits;
     const uint32_t* tbitsT;  // transposed: word index = column of the tile, bit = row (column masks for the fused kernels)
     int tb_stride;        // tiles_x + 2
+    // coarse levels of the red-black cycle: 1 / diagonal of the boundary-corrected coarse operator (mg.cu), a float plane
+    // shared by all bands; nullptr on level 0 (diagonal = neighbour count)
+    const float* winv;
 };
 
 }  // namespace satfill
@@ -96,6 +99,7 @@ struct sa_level_store {
     double* x = nullptr;               // coarse levels: correction; nbands planes (allocation base)
     double* b = nullptr;               // coarse levels: restricted residual
     double* t = nullptr;               // scratch (second smoothing buffer)
+    float* winv = nullptr;             // Level::winv (allocation base, guard row included)
     int64_t n_unknowns = 0;
 };
 

@@ -29,10 +29,20 @@ __device__ __forceinline__ double lv_diag(const Level& lv, int64_t r, int64_t c)
 // ---- hierarchy construction -------------------------------------------------------------------------------------
 
 // coarse umask(I, J) = fine umask(2I, 2J); per-tile activity flags and unknown count.  One CTA per coarse tile.
+//
+// It also writes 1 / d of the coarse operator the red-black cycle uses (Level::winv).  Re-discretising the 5-point
+// operator on the injected mask puts every Dirichlet boundary on a coarse grid point, i.e. up to one fine cell too far
+// out; measured on cloud-like masks that mismatch costs almost half of the convergence rate (tools/mg_prototype.py:
+// 11 -> 8 CG iterations).  The correction keeps the operator symmetric (only the diagonal changes): the diagonal is the
+// sum of the conductances of the four arms of the coarse cell, in units of a regular coarse arm --
+//     the fine cell half way along the arm is an unknown: 1 (whether the arm ends on a coarse unknown or on a boundary
+//                                                           a full coarse spacing away);
+//     it is known: the boundary sits at half the spacing -> 2;
+//     it lies outside the image (Poisson only: no neighbour there, poisson.cpp:187-190), or the arm's end does: 0.
 __global__ void __launch_bounds__(CG_THREADS) k_coarsen_mask(const uint8_t* __restrict__ fmask, int64_t fpitch,
-    uint8_t* __restrict__ cmask, int64_t crows, int64_t ccols, int64_t cpitch, int tiles_x,
-    int32_t* __restrict__ tile_flags, unsigned long long* __restrict__ count64, uint32_t* __restrict__ tbits,
-    uint32_t* __restrict__ tbitsT)
+    int64_t frows, int64_t fcols, int fixed, uint8_t* __restrict__ cmask, int64_t crows, int64_t ccols, int64_t cpitch,
+    int tiles_x, int32_t* __restrict__ tile_flags, unsigned long long* __restrict__ count64, uint32_t* __restrict__ tbits,
+    uint32_t* __restrict__ tbitsT, float* __restrict__ winv)
 {
     __shared__ int warp_cnt[CG_BLOCK_Y];
     __shared__ unsigned scol[TILE_W];
@@ -50,6 +60,27 @@ __global__ void __launch_bounds__(CG_THREADS) k_coarsen_mask(const uint8_t* __re
         if (r < crows && c < ccols)
             m = fmask[2 * r * fpitch + 2 * c];
         cmask[r * cpitch + c] = m;
+        {
+            float d = 0.f;
+            if (m) {
+                const int64_t fr = 2 * r, fc = 2 * c;
+                const int dr[4] = { -1, 1, 0, 0 }, dc[4] = { 0, 0, -1, 1 };
+#pragma unroll
+                for (int a = 0; a < 4; ++a) {
+                    int64_t mr = fr + dr[a], mc = fc + dc[a], er = fr + 2 * dr[a], ec = fc + 2 * dc[a];
+                    bool mid_in = mr >= 0 && mr < frows && mc >= 0 && mc < fcols;
+                    bool end_in = er >= 0 && er < frows && ec >= 0 && ec < fcols;
+                    if (!mid_in)
+                        d += fixed ? 2.f : 0.f;
+                    else if (!fmask[mr * fpitch + mc])
+                        d += 2.f;
+                    else
+                        d += (end_in || fixed) ? 1.f : 0.f;
+                }
+                d = d < 1.f ? 1.f : d;
+            }
+            winv[r * cpitch + c] = m ? 1.f / d : 0.f;
+        }
         cnt += m;
         unsigned word = __ballot_sync(0xffffffffu, m);
         if (threadIdx.x == 0)
@@ -84,6 +115,7 @@ void free_hierarchy(sa_scene* s)
         cudaFree(L.x);
         cudaFree(L.b);
         cudaFree(L.t);
+        cudaFree(L.winv);
     }
     s->coarse.clear();
     s->hierarchy_built = false;
@@ -118,6 +150,8 @@ static int alloc_hierarchy(sa_scene* s, const sa_options& o)
         SA_CUDA(ctx, cudaMalloc(&L.x, vec));
         SA_CUDA(ctx, cudaMalloc(&L.b, vec));
         SA_CUDA(ctx, cudaMalloc(&L.t, vec));
+        SA_CUDA(ctx, cudaMalloc(&L.winv, (size_t)L.lv.plane * sizeof(float)));
+        SA_CUDA(ctx, cudaMemsetAsync(L.winv, 0, (size_t)L.lv.plane * sizeof(float), ctx->stream));
         size_t words = (size_t)(L.lv.tiles_x + 2) * (L.lv.tiles_y + 2) * 32;
         L.tb_words = words;
         SA_CUDA(ctx, cudaMalloc(&L.tbits, 2 * words * sizeof(uint32_t)));
@@ -128,6 +162,7 @@ static int alloc_hierarchy(sa_scene* s, const sa_options& o)
         L.lv.tbits = L.tbits;
         L.lv.tbitsT = L.tbits + words;
         L.lv.tb_stride = L.lv.tiles_x + 2;
+        L.lv.winv = L.winv + L.lv.pitch;
         s->coarse.push_back(L);
         rows = crows;
         cols = ccols;
@@ -141,7 +176,7 @@ int build_hierarchy(sa_scene* s, const sa_options& o)
     if (s->coarse.empty())
         SA_TRY(alloc_hierarchy(s, o));
     const uint8_t* fmask = s->mask0(s->umask);
-    int64_t fpitch = s->pitch;
+    int64_t fpitch = s->pitch, frows = s->rows, fcols = s->cols;
     dim3 block(CG_BLOCK_X, CG_BLOCK_Y);
     for (sa_level_store& L : s->coarse) {
         int n_tiles = L.lv.tiles_x * L.lv.tiles_y;
@@ -149,8 +184,8 @@ int build_hierarchy(sa_scene* s, const sa_options& o)
         unsigned long long* count64 = reinterpret_cast<unsigned long long*>(L.d_counters + 4);
         SA_CUDA(ctx, cudaMemsetAsync(L.d_counters, 0, sizeof(int32_t) * 4 + sizeof(unsigned long long), ctx->stream));
         uint8_t* cmask = L.umask_alloc + L.lv.pitch;
-        SA_LAUNCH(ctx, k_coarsen_mask, n_tiles, block, 0, fmask, fpitch, cmask, L.lv.rows, L.lv.cols, L.lv.pitch,
-            L.lv.tiles_x, flags, count64, L.tbits, L.tbits + L.tb_words);
+        SA_LAUNCH(ctx, k_coarsen_mask, n_tiles, block, 0, fmask, fpitch, frows, fcols, L.lv.fixed_diag, cmask, L.lv.rows,
+            L.lv.cols, L.lv.pitch, L.lv.tiles_x, flags, count64, L.tbits, L.tbits + L.tb_words, L.winv + L.lv.pitch);
         SA_TRY(compact_tile_flags(ctx, flags, n_tiles, L.lv.tiles_x, L.tile_list, L.tile_list + 2 * n_tiles, L.d_counters));
         size_t vec = (size_t)L.lv.plane * s->nbands * sizeof(double);
         SA_CUDA(ctx, cudaMemsetAsync(L.x, 0, vec, ctx->stream));
@@ -158,6 +193,8 @@ int build_hierarchy(sa_scene* s, const sa_options& o)
         SA_CUDA(ctx, cudaMemsetAsync(L.t, 0, vec, ctx->stream));
         fmask = cmask;
         fpitch = L.lv.pitch;
+        frows = L.lv.rows;
+        fcols = L.lv.cols;
     }
     SA_CUDA(ctx, cudaGetLastError());
     // one read-back for all levels

@@ -34,7 +34,7 @@ namespace {
 
 constexpr int RB_HP = 20;  // threads per row group (half columns): lane-linear shared-memory addressing
 #ifndef SATFILL_RB_DOWN_RG
-#define SATFILL_RB_DOWN_RG 4
+#define SATFILL_RB_DOWN_RG 10
 #endif
 #ifndef SATFILL_RB_UP_RG
 #define SATFILL_RB_UP_RG 6
@@ -109,7 +109,8 @@ __device__ __forceinline__ float2 ldg2_if(const float* p, unsigned pred)
 constexpr int RB_DOWN_NG = (TILE_W + 8 + RB_DOWN_RG - 1) / RB_DOWN_RG;
 constexpr int RB_UP_NG = (TILE_W + 4 + RB_UP_RG - 1) / RB_UP_RG;
 
-template <bool FIXED>
+// WINV: the level carries its own 1 / diagonal plane (coarse levels, Level::winv)
+template <bool FIXED, bool WINV>
 __global__ void __launch_bounds__(RB_HP * RB_DOWN_NG) k_rb_down(Level lf, Level lc, const float* __restrict__ b,
     float* __restrict__ xr, float* __restrict__ bc, const BandScalars* __restrict__ scal)
 {
@@ -135,15 +136,24 @@ __global__ void __launch_bounds__(RB_HP * RB_DOWN_NG) k_rb_down(Level lf, Level 
     const int64_t gr = (int64_t)ty * TILE_H - H, gc = (int64_t)tx * TILE_W - H;  // global position of the frame origin
     const int toff = row0 * pitch + 2 * h;                                       // the thread's (row0, column 2h) in it
     // ---- global loads: the right-hand side at the thread's RG x 2 cells, one aligned pair per row
-    float bred[RG], bblk[RG];
+    float bred[RG], bblk[RG], wred[RG], wblk[RG];
     {
         const float* bp = b + (int64_t)blockIdx.y * lf.plane + gr * lf.pitch + gc;
+        const float* wp = WINV ? lf.winv + gr * lf.pitch + gc : nullptr;
         const unsigned ld = rm | bm;
 #pragma unroll
         for (int k = 0; k < RG; ++k) {
             float2 v = ldg2_if(bp + (toff + k * pitch), (ld >> k) & 1);
             bred[k] = (k & 1) ? v.y : v.x;
             bblk[k] = (k & 1) ? v.x : v.y;
+            if (WINV) {
+                float2 w = ldg2_if(wp + (toff + k * pitch), (ld >> k) & 1);
+                wred[k] = (k & 1) ? w.y : w.x;
+                wblk[k] = (k & 1) ? w.x : w.y;
+            } else {
+                wred[k] = rb_winv<FIXED>(lf, gr + row0 + k, gc + 2 * h + (k & 1));
+                wblk[k] = rb_winv<FIXED>(lf, gr + row0 + k, gc + 2 * h + 1 - (k & 1));
+            }
         }
     }
     const int sb = (row0 + 1) * S + h;  // shared index of (row0, h)
@@ -154,7 +164,7 @@ __global__ void __launch_bounds__(RB_HP * RB_DOWN_NG) k_rb_down(Level lf, Level 
         const unsigned own = rm & rb_rows<RG>(row0, H, H + TILE_H) & rb_cols<RG>(h, H, H + TILE_W, true);
 #pragma unroll
         for (int k = 0; k < RG; ++k) {
-            float v = rb_winv<FIXED>(lf, gr + row0 + k, gc + 2 * h + (k & 1)) * (((rm >> k) & 1) ? bred[k] : 0.f);
+            float v = wred[k] * (((rm >> k) & 1) ? bred[k] : 0.f);
             R[sb + k * S] = v;
             if ((own >> k) & 1)
                 xo[toff2 + k * pitch2] = v;
@@ -169,7 +179,7 @@ __global__ void __launch_bounds__(RB_HP * RB_DOWN_NG) k_rb_down(Level lf, Level 
         for (int k = 0; k < RG; ++k) {
             float s = p[(k + 1) * S];
             float side = p[k * S + ((k & 1) ? -1 : 1)];
-            float v = rb_winv<FIXED>(lf, gr + row0 + k, gc + 2 * h + 1 - (k & 1)) * (bblk[k] + ((n + s) + (c + side)));
+            float v = wblk[k] * (bblk[k] + ((n + s) + (c + side)));
             B[sb + k * S] = ((bm >> k) & 1) ? v : 0.f;
             n = c;
             c = s;
@@ -212,7 +222,7 @@ __global__ void __launch_bounds__(RB_HP * RB_DOWN_NG) k_rb_down(Level lf, Level 
 // ---------------------------------------------------------------------------------------------------------------
 // ascent: prolongation + correction (red cells only), post-smoothing black then red, (level 0) r.z
 // ---------------------------------------------------------------------------------------------------------------
-template <bool FIXED, bool DOT>
+template <bool FIXED, bool DOT, bool WINV>
 __global__ void __launch_bounds__(RB_HP * RB_UP_NG) k_rb_up(Level lf, Level lc, const float* __restrict__ xr,
     const float* __restrict__ b, const float* __restrict__ ec, float* __restrict__ x_out, BandScalars* __restrict__ scal,
     int slot)
@@ -248,10 +258,11 @@ __global__ void __launch_bounds__(RB_HP * RB_UP_NG) k_rb_up(Level lf, Level lc, 
     const int toff = row0 * pitch + 2 * h;
     const int64_t goff = (int64_t)blockIdx.y * lf.plane + gr * lf.pitch + gc;
     // ---- global loads first: red x on the whole region, b where an update needs it, the coarse correction
-    float xv[RG], bred[RG], bblk[RG];
+    float xv[RG], bred[RG], bblk[RG], wred[RG], wblk[RG];
     {
         const float* xp = xr + (int64_t)blockIdx.y * (lf.plane >> 1) + gr * pitch2 + (gc >> 1);
         const float* bp = b + goff;
+        const float* wp = WINV ? lf.winv + gr * lf.pitch + gc : nullptr;
         const int toff2 = row0 * pitch2 + h;
         const unsigned ld = own_red | on_blk;
 #pragma unroll
@@ -260,6 +271,14 @@ __global__ void __launch_bounds__(RB_HP * RB_UP_NG) k_rb_up(Level lf, Level lc, 
             float2 v = ldg2_if(bp + (toff + k * pitch), (ld >> k) & 1);
             bred[k] = (k & 1) ? v.y : v.x;
             bblk[k] = (k & 1) ? v.x : v.y;
+            if (WINV) {
+                float2 w = ldg2_if(wp + (toff + k * pitch), (ld >> k) & 1);
+                wred[k] = (k & 1) ? w.y : w.x;
+                wblk[k] = (k & 1) ? w.x : w.y;
+            } else {
+                wred[k] = rb_winv<FIXED>(lf, gr + row0 + k, gc + 2 * h + (k & 1));
+                wblk[k] = rb_winv<FIXED>(lf, gr + row0 + k, gc + 2 * h + 1 - (k & 1));
+            }
         }
         const int cpitch = (int)lc.pitch;
         const int I0 = ty * (TILE_H / 2) - 1, J = tx * (TILE_W / 2) - 1 + h;
@@ -296,7 +315,7 @@ __global__ void __launch_bounds__(RB_HP * RB_UP_NG) k_rb_up(Level lf, Level lc, 
         for (int k = 0; k < RG; ++k) {
             float s = p[(k + 1) * S];
             float side = p[k * S + ((k & 1) ? -1 : 1)];
-            float v = rb_winv<FIXED>(lf, gr + row0 + k, gc + 2 * h + 1 - (k & 1)) * (bblk[k] + ((n + s) + (c + side)));
+            float v = wblk[k] * (bblk[k] + ((n + s) + (c + side)));
             v = ((on_blk >> k) & 1) ? v : 0.f;
             B[sb + k * S] = v;
             vblk[k] = v;
@@ -318,7 +337,7 @@ __global__ void __launch_bounds__(RB_HP * RB_UP_NG) k_rb_up(Level lf, Level lc, 
         for (int k = 0; k < RG; ++k) {
             float s = p[(k + 1) * S];
             float side = p[k * S + ((k & 1) ? 1 : -1)];
-            float v = rb_winv<FIXED>(lf, gr + row0 + k, gc + 2 * h + (k & 1)) * (bred[k] + ((n + s) + (c + side)));
+            float v = wred[k] * (bred[k] + ((n + s) + (c + side)));
             v = ((own_red >> k) & 1) ? v : 0.f;
             if (DOT)
                 acc += bred[k] * v;
@@ -376,7 +395,7 @@ __global__ void __launch_bounds__(1024) k_rb_coarsest(Level lv, const float* __r
             int64_t idx = r * lv.pitch + c;
             if (((r + c) & 1) == colour && lv.umask[idx]) {
                 float nb = (xb[idx - lv.pitch] + xb[idx + lv.pitch]) + (xb[idx - 1] + xb[idx + 1]);
-                xb[idx] = rb_winv<FIXED>(lv, r, c) * (bb[idx] + nb);
+                xb[idx] = (lv.winv ? lv.winv[idx] : rb_winv<FIXED>(lv, r, c)) * (bb[idx] + nb);
             }
         }
         __syncthreads();
@@ -420,10 +439,12 @@ struct RBLevel {
 int launch_down(sa_ctx* ctx, const RBLevel& F, const RBLevel& C, int nb, const BandScalars* scal)
 {
     dim3 grid((unsigned)F.lv.n_tiles, (unsigned)nb);
-    if (F.lv.fixed_diag)
-        SA_LAUNCH(ctx, k_rb_down<true>, grid, RB_HP * RB_DOWN_NG, 0, F.lv, C.lv, F.b, F.xr, C.b, scal);
+    if (F.lv.winv)
+        SA_LAUNCH(ctx, (k_rb_down<true, true>), grid, RB_HP * RB_DOWN_NG, 0, F.lv, C.lv, F.b, F.xr, C.b, scal);
+    else if (F.lv.fixed_diag)
+        SA_LAUNCH(ctx, (k_rb_down<true, false>), grid, RB_HP * RB_DOWN_NG, 0, F.lv, C.lv, F.b, F.xr, C.b, scal);
     else
-        SA_LAUNCH(ctx, k_rb_down<false>, grid, RB_HP * RB_DOWN_NG, 0, F.lv, C.lv, F.b, F.xr, C.b, scal);
+        SA_LAUNCH(ctx, (k_rb_down<false, false>), grid, RB_HP * RB_DOWN_NG, 0, F.lv, C.lv, F.b, F.xr, C.b, scal);
     return SA_OK;
 }
 
@@ -431,10 +452,12 @@ template <bool DOT>
 int launch_up(sa_ctx* ctx, const RBLevel& F, const RBLevel& C, int nb, BandScalars* scal, int slot)
 {
     dim3 grid((unsigned)F.lv.n_tiles, (unsigned)nb);
-    if (F.lv.fixed_diag)
-        SA_LAUNCH(ctx, (k_rb_up<true, DOT>), grid, RB_HP * RB_UP_NG, 0, F.lv, C.lv, F.xr, F.b, C.x, F.x, scal, slot);
+    if (F.lv.winv)
+        SA_LAUNCH(ctx, (k_rb_up<true, DOT, true>), grid, RB_HP * RB_UP_NG, 0, F.lv, C.lv, F.xr, F.b, C.x, F.x, scal, slot);
+    else if (F.lv.fixed_diag)
+        SA_LAUNCH(ctx, (k_rb_up<true, DOT, false>), grid, RB_HP * RB_UP_NG, 0, F.lv, C.lv, F.xr, F.b, C.x, F.x, scal, slot);
     else
-        SA_LAUNCH(ctx, (k_rb_up<false, DOT>), grid, RB_HP * RB_UP_NG, 0, F.lv, C.lv, F.xr, F.b, C.x, F.x, scal, slot);
+        SA_LAUNCH(ctx, (k_rb_up<false, DOT, false>), grid, RB_HP * RB_UP_NG, 0, F.lv, C.lv, F.xr, F.b, C.x, F.x, scal, slot);
     return SA_OK;
 }
 

@@ -249,8 +249,10 @@ def test_resident_scene_device_buffers(ctx, port):
     sc = ctx.scene(sab.LAPLACE, rows, cols, 2)
     sc.set_mask(torch.from_numpy(mask.view(np.uint8)).cuda())
     d_img = torch.from_numpy(img).cuda()
+    d_img2 = d_img * 2.0
+    torch.cuda.synchronize()  # the library runs on its own stream: torch's kernels must have finished
     sc.set_band(0, d_img)
-    sc.set_band(1, d_img * 2.0)
+    sc.set_band(1, d_img2)
     st = sc.solve(tolerance=1e-12)
     assert all(s["status"] == sab.SA_OK for s in st) and st[0]["unknowns"] == int(mask.sum())
     out = torch.empty_like(d_img)
@@ -371,7 +373,8 @@ def _prototype():
 @pytest.mark.parametrize("shape", [(96, 128), (391, 517), (40, 33)])
 def test_rb_preconditioner_matches_numpy_prototype_and_is_symmetric(ctx, shape):
     """One application z = M^-1 r of the CUDA V-cycle against the numpy statement of the same algorithm
-    (tools/mg_prototype.py: red-black Gauss-Seidel V(1,1), float, mask injection, full weighting / bilinear), and
+    (tools/mg_prototype.py: red-black Gauss-Seidel V(1,1), float, mask injection, boundary-corrected coarse diagonals,
+    full weighting / bilinear), and
     <u, M^-1 v> = <v, M^-1 u>: CG needs a symmetric preconditioner."""
     proto = _prototype()
     rows, cols = shape
@@ -379,7 +382,7 @@ def test_rb_preconditioner_matches_numpy_prototype_and_is_symmetric(ctx, shape):
     rng = np.random.default_rng(3)
     sc = ctx.scene(sab.LAPLACE, rows, cols, 1)
     sc.set_mask(mask)
-    mg = proto.MG(mask, smoother="rb1", dtype=np.float32, coarse_sweeps=32)
+    mg = proto.MG(mask, smoother="rb1", dtype=np.float32, coarse_sweeps=32, corrected=True)
     zs, rs = [], []
     for _ in range(2):
         r = np.where(mask, rng.standard_normal(shape), 0.0)

@@ -7,6 +7,7 @@ rows = cols = 4096; nb = 4
 dev = torch.device("cuda", 0)
 mask = synth.torch_blob_mask(rows, cols, cover=0.3, cell=48, seed=2, device=dev)
 bands = [synth.torch_band(rows, cols, seed=100 + b, device=dev) for b in range(nb)]
+torch.cuda.synchronize()
 sc = ctx.scene(sab.LAPLACE, rows, cols, nb)
 for b in range(nb): sc.set_band(b, bands[b])
 sc.set_mask(mask)
