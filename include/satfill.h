@@ -177,6 +177,27 @@ int sa_scene_precondition(sa_scene* scene, const sa_options* opts, const double*
 /* Blocks until everything queued on the context's stream has finished. */
 int sa_synchronize(sa_ctx* ctx);
 
+/* ---- one system across several GPUs (a single very large hole, decomposed by rows) -------------------- */
+
+/* One process per GPU.  The host language moves 128 bytes: rank 0 calls sa_dist_unique_id, broadcasts the id by whatever
+ * it has (torch.distributed, MPI, a file), then every rank calls sa_dist_init on its context.  NCCL (libnccl.so.2) is
+ * resolved at run time; without it these calls return SA_NCCL_ERROR and everything else keeps working. */
+int sa_dist_unique_id(void* id128);
+int sa_dist_init(sa_ctx* ctx, const void* id128, int rank, int world);
+/* The row partition the solver uses (pure host logic): world + 1 row boundaries, aligned to 32 * 2^(levels - 1) rows so
+ * that `levels` multigrid levels split at the same places.  sa_dist_levels: the number of levels it splits for a scene
+ * of `rows` rows; coarser levels are replicated on every rank. */
+int sa_dist_partition(int64_t rows, int world, int levels, int64_t* row_begin);
+int sa_dist_levels(int64_t rows, int world);
+/* Mark a scene of a context that went through sa_dist_init as ONE system shared by all ranks: every rank sets the same
+ * mask and bands (only its own rows and one row around them are read), sa_scene_solve is collective, and afterwards
+ * each rank holds the solution on the rows sa_scene_owned_rows reports (axis: 0 = rows, 1 = columns of the caller's
+ * array -- the split runs along the slow axis of the memory layout).  sa_scene_allgather_band (collective) completes
+ * a band on every rank. */
+int sa_scene_set_distributed(sa_scene* scene, int on);
+int sa_scene_owned_rows(const sa_scene* scene, int64_t* lo, int64_t* hi, int* axis);
+int sa_scene_allgather_band(sa_scene* scene, int band);
+
 #ifdef __cplusplus
 }
 #endif

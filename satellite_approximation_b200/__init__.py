@@ -45,7 +45,7 @@ __all__ = [
     "LogLevel", "set_log_level", "filling_missing_portions_smooth_boundaries", "blend_images_poisson",
     "find_connected_components", "ConnectedComponents", "mask_scan", "unknown_numbering", "valid_neighbours",
     "Context", "Scene", "SolveStats", "default_context", "set_solver_defaults", "last_perf_info",
-    "LAPLACE", "POISSON", "JACOBI", "MULTIGRID", "MG_RB32", "MG_JACOBI64", "SatfillError",
+    "dist_partition", "dist_levels", "LAPLACE", "POISSON", "JACOBI", "MULTIGRID", "MG_RB32", "MG_JACOBI64", "SatfillError",
 ]  # fmt: skip
 
 _log = logging.getLogger("satellite_approximation_b200")
@@ -154,6 +154,27 @@ class Context:
 
     def synchronize(self) -> None:
         self._check(self._lib.sa_synchronize(self._h))
+
+    # ---- one system across several GPUs (sa_dist_*) --------------------------------------------------------------
+    def dist_init_torch(self) -> None:
+        """Join the ranks of the initialised torch.distributed process group into the library's own NCCL communicator:
+        rank 0 creates the id, torch.distributed broadcasts its 128 bytes (the only thing the host language moves)."""
+        import torch
+        import torch.distributed as dist
+
+        rank, world = dist.get_rank(), dist.get_world_size()
+        buf = (C.c_uint8 * 128)()
+        if rank == 0:
+            self._check(self._lib.sa_dist_unique_id(buf))
+        dev = torch.device("cuda", self.device) if dist.get_backend() == "nccl" else torch.device("cpu")
+        t = torch.tensor(list(bytes(buf)), dtype=torch.uint8, device=dev)
+        dist.broadcast(t, 0)
+        self.dist_init(bytes(t.cpu().tolist()), rank, world)
+
+    def dist_init(self, id128: bytes, rank: int, world: int) -> None:
+        buf = (C.c_uint8 * 128).from_buffer_copy(id128)
+        self._check(self._lib.sa_dist_init(self._h, buf, int(rank), int(world)))
+        self.rank, self.world = int(rank), int(world)
 
     def options(self, problem: int, tolerance=None, max_iterations=None, precond=None, check_every=None,
                 mg_levels=None, mg_smooth=None, profile=None, mg_unfused=None, mg_variant=None, cg_variant=None) -> _capi.Options:  # fmt: skip
@@ -321,10 +342,37 @@ class Scene:
         self.ctx._check(self.ctx._lib.sa_scene_precondition(self._h, C.byref(o), r.ctypes.data, z.ctypes.data, r.shape[1], 1))
         return z
 
+    def set_distributed(self, on: bool = True) -> None:
+        """One system shared by all ranks of the context's communicator, split by rows (sa_scene_set_distributed)."""
+        self.ctx._check(self.ctx._lib.sa_scene_set_distributed(self._h, int(bool(on))))
+
+    def owned_rows(self):
+        """(lo, hi, axis): the slice of the caller's array this rank holds the solution for after a distributed solve."""
+        lo, hi, axis = C.c_int64(), C.c_int64(), C.c_int()
+        self.ctx._check(self.ctx._lib.sa_scene_owned_rows(self._h, C.byref(lo), C.byref(hi), C.byref(axis)))
+        return lo.value, hi.value, axis.value
+
+    def allgather_band(self, band: int) -> None:
+        self.ctx._check(self.ctx._lib.sa_scene_allgather_band(self._h, int(band)))
+
     def info(self) -> dict:
         n, a, t = C.c_int64(), C.c_int32(), C.c_int32()
         self.ctx._lib.sa_scene_info(self._h, C.byref(n), C.byref(a), C.byref(t))
         return {"unknowns": n.value, "active_tiles": a.value, "total_tiles": t.value}
+
+
+def dist_partition(rows: int, world: int, levels: int) -> list[int]:
+    """Row boundaries (world + 1) of the row decomposition the distributed solver uses (sa_dist_partition)."""
+    lib = _capi.load()
+    out = (C.c_int64 * (world + 1))()
+    if lib.sa_dist_partition(int(rows), int(world), int(levels), out) != SA_OK:
+        raise ValueError("dist_partition: bad arguments")
+    return list(out)
+
+
+def dist_levels(rows: int, world: int) -> int:
+    """Number of multigrid levels the distributed solver splits by rows for a scene of `rows` rows (sa_dist_levels)."""
+    return int(_capi.load().sa_dist_levels(int(rows), int(world)))
 
 
 _default_ctx: Optional[Context] = None

@@ -31,6 +31,8 @@ EXPORTS = [
     "sa_mask_scan", "sa_unknown_numbering", "sa_label_components", "sa_laplace_fill", "sa_poisson_blend",
     "sa_scene_create", "sa_scene_destroy", "sa_scene_set_mask", "sa_scene_set_band", "sa_scene_set_guidance",
     "sa_scene_solve", "sa_scene_get_band", "sa_scene_info", "sa_scene_precondition", "sa_synchronize",
+    "sa_dist_unique_id", "sa_dist_init", "sa_dist_partition", "sa_dist_levels", "sa_scene_set_distributed",
+    "sa_scene_owned_rows", "sa_scene_allgather_band",
 ]  # fmt: skip
 
 
@@ -136,6 +138,20 @@ def load() -> C.CDLL:
     L.sa_scene_info.argtypes = [_vp, C.POINTER(_i64), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     L.sa_scene_precondition.restype = C.c_int
     L.sa_scene_precondition.argtypes = [_vp, C.POINTER(Options), _vp, _vp, _i64, _i64]
+    L.sa_dist_unique_id.restype = C.c_int
+    L.sa_dist_unique_id.argtypes = [_vp]
+    L.sa_dist_init.restype = C.c_int
+    L.sa_dist_init.argtypes = [_vp, _vp, C.c_int, C.c_int]
+    L.sa_dist_partition.restype = C.c_int
+    L.sa_dist_partition.argtypes = [_i64, C.c_int, C.c_int, C.POINTER(_i64)]
+    L.sa_dist_levels.restype = C.c_int
+    L.sa_dist_levels.argtypes = [_i64, C.c_int]
+    L.sa_scene_set_distributed.restype = C.c_int
+    L.sa_scene_set_distributed.argtypes = [_vp, C.c_int]
+    L.sa_scene_owned_rows.restype = C.c_int
+    L.sa_scene_owned_rows.argtypes = [_vp, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(C.c_int)]
+    L.sa_scene_allgather_band.restype = C.c_int
+    L.sa_scene_allgather_band.argtypes = [_vp, C.c_int]
     L.sa_synchronize.restype = C.c_int
     L.sa_synchronize.argtypes = [_vp]
     if L.sa_abi_version() != ABI_VERSION:

@@ -243,6 +243,7 @@ void sa_destroy(sa_ctx* ctx)
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     scene_free(cache_of(ctx)->scene);
+    dist_shutdown(ctx);
     for (auto& ev : ctx->ev)
         if (ev)
             cudaEventDestroy(ev);
@@ -508,6 +509,79 @@ int sa_scene_info(const sa_scene* s, int64_t* unknowns, int32_t* active_tiles, i
     if (total_tiles)
         *total_tiles = s->tiles_x * s->tiles_y;
     return SA_OK;
+}
+
+/* ---- row decomposition across GPUs ------------------------------------------------------------------------------------ */
+
+int sa_dist_unique_id(void* id128)
+{
+    if (!id128)
+        return SA_BAD_ARGUMENT;
+    return dist_unique_id(id128);
+}
+
+int sa_dist_init(sa_ctx* ctx, const void* id128, int rank, int world)
+{
+    SA_TRY(check_ctx(ctx));
+    if (!id128)
+        return fail(ctx, SA_BAD_ARGUMENT, "dist_init: null id");
+    if (ctx->comm)
+        return fail(ctx, SA_BAD_ARGUMENT, "dist_init: the context already has a communicator");
+    return dist_init(ctx, id128, rank, world);
+}
+
+int sa_dist_partition(int64_t rows, int world, int levels, int64_t* row_begin)
+{
+    if (rows < 0 || world < 1 || levels < 1 || levels > 8 || !row_begin)
+        return SA_BAD_ARGUMENT;
+    dist_partition(rows, world, levels, row_begin);
+    return SA_OK;
+}
+
+int sa_dist_levels(int64_t rows, int world)
+{
+    if (rows < 0 || world < 1)
+        return 0;
+    return dist_choose_levels(rows, world);
+}
+
+int sa_scene_set_distributed(sa_scene* s, int on)
+{
+    if (!s)
+        return SA_BAD_ARGUMENT;
+    if (on && !s->ctx->comm)
+        return fail(s->ctx, SA_BAD_ARGUMENT, "scene_set_distributed: the context has no communicator (sa_dist_init)");
+    s->distributed = on != 0;
+    s->dist_planned = false;
+    return SA_OK;
+}
+
+int sa_scene_owned_rows(const sa_scene* s, int64_t* lo, int64_t* hi, int* axis)
+{
+    if (!s)
+        return SA_BAD_ARGUMENT;
+    int64_t a = 0, b = s->rows;
+    if (s->distributed && s->dist_planned && !s->dl.empty()) {
+        a = s->dl[0].row_lo < s->rows ? s->dl[0].row_lo : s->rows;
+        b = s->dl[0].row_hi < s->rows ? s->dl[0].row_hi : s->rows;
+    }
+    if (lo)
+        *lo = a;
+    if (hi)
+        *hi = b;
+    if (axis)
+        *axis = s->transposed ? 1 : 0;
+    return SA_OK;
+}
+
+int sa_scene_allgather_band(sa_scene* s, int band)
+{
+    if (!s)
+        return SA_BAD_ARGUMENT;
+    SA_TRY(check_ctx(s->ctx));
+    if (band < 0 || band >= s->nbands)
+        return fail(s->ctx, SA_BAD_ARGUMENT, "scene_allgather_band: band out of range");
+    return dist_allgather_band(s, band);
 }
 
 /* ---- float path, host pointers ---------------------------------------------------------------------------------- */

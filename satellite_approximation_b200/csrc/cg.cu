@@ -334,6 +334,7 @@ int ensure_indexed(sa_scene* s)
     if (s->t)
         SA_CUDA(ctx, cudaMemsetAsync(s->t, 0, bytes, ctx->stream));
     s->hierarchy_built = false;
+    s->dist_planned = false;
     return SA_OK;
 }
 
@@ -432,21 +433,44 @@ int solve_scene(sa_scene* s, const sa_options& o, sa_stats* stats)
     }
     if (mg)
         SA_TRY(ensure_multigrid(s, o));
+    // one system split by rows across the ranks of the context's communicator (dist.cu)
+    const bool dist = s->distributed && ctx->world > 1;
+    if (dist) {
+        if (!strip || (mg && !rb))
+            return fail(ctx, SA_BAD_ARGUMENT, "distributed solve: needs the strip CG kernels and the red-black cycle");
+        if (!s->dist_planned || s->dist_mg != mg)
+            SA_TRY(dist_plan_scene(s, mg));
+    }
 
-    Level lv = fine_level(s);
-    dim3 grid((unsigned)lv.n_tiles, (unsigned)nb), block(CG_BLOCK_X, CG_BLOCK_Y);
+    Level lv = dist ? dist_level(s, 0, fine_level(s)) : fine_level(s);
+    const bool have_tiles = lv.n_tiles > 0;  // a rank's slice may hold no active tile
+    dim3 grid((unsigned)(have_tiles ? lv.n_tiles : 1), (unsigned)nb), block(CG_BLOCK_X, CG_BLOCK_Y);
     double* u0 = s->plane0(s->u, 0);
     double* g0 = poisson ? s->plane0(s->g, 0) : nullptr;
     double* r0 = s->plane0(s->r, 0);
     double* pbuf[2] = { s->plane0(s->p[0], 0), s->plane0(s->p[1], 0) };
 
     SA_CUDA(ctx, cudaMemsetAsync(s->scal, 0, sizeof(BandScalars) * nb, ctx->stream));
-    if (poisson) {
-        SA_LAUNCH(ctx, k_init_guess<true>, grid, block, 0, lv, u0, g0);
-        SA_LAUNCH(ctx, k_residual<true>, grid, block, 0, lv, u0, g0, r0, rb ? s->rb_rf() : nullptr, s->scal);
-    } else {
-        SA_LAUNCH(ctx, k_init_guess<false>, grid, block, 0, lv, u0, g0);
-        SA_LAUNCH(ctx, k_residual<false>, grid, block, 0, lv, u0, g0, r0, rb ? s->rb_rf() : nullptr, s->scal);
+    if (have_tiles) {
+        if (poisson)
+            SA_LAUNCH(ctx, k_init_guess<true>, grid, block, 0, lv, u0, g0);
+        else
+            SA_LAUNCH(ctx, k_init_guess<false>, grid, block, 0, lv, u0, g0);
+    }
+    if (dist)  // the residual's stencil reads the iterate one row beyond the slice
+        SA_TRY(dist_halo<double>(s, 0, u0, s->pitch, s->plane, 1, 1));
+    if (have_tiles) {
+        if (poisson)
+            SA_LAUNCH(ctx, k_residual<true>, grid, block, 0, lv, u0, g0, r0, rb ? s->rb_rf() : nullptr, s->scal);
+        else
+            SA_LAUNCH(ctx, k_residual<false>, grid, block, 0, lv, u0, g0, r0, rb ? s->rb_rf() : nullptr, s->scal);
+    }
+    if (dist) {
+        SA_TRY(dist_reduce(s, DIST_SETUP, 0, -1));
+        if (rb)
+            SA_TRY(dist_halo<float>(s, 0, s->rb_rf(), s->pitch, s->plane, 3, 3));
+        else
+            SA_TRY(dist_halo<double>(s, 0, r0, s->pitch, s->plane, 1, 1));
     }
     SA_LAUNCH(ctx, k_finalize_setup, (nb + 63) / 64, 64, 0, s->scal, nb, o.tolerance, mg ? 1 : 0);
     SA_CUDA(ctx, cudaGetLastError());
@@ -479,6 +503,8 @@ int solve_scene(sa_scene* s, const sa_options& o, sa_stats* stats)
                     z = s->plane0(s->z, 0);
                 }
                 float* rf = rb ? s->rb_rf() : nullptr;
+                if (dist)
+                    SA_TRY(dist_reduce(s, DIST_RZ, ki & 3, -1));
                 kt.begin(KC_DIRECTION, n * live);
                 if (strip)
                     SA_TRY(launch_direction2(ctx, lv, nb, false, z, rb, pin, pout, s->scal, ki));
@@ -487,6 +513,10 @@ int solve_scene(sa_scene* s, const sa_options& o, sa_stats* stats)
                 else
                     SA_LAUNCH(ctx, (k_direction<false, double>), grid, block, 0, lv, (const double*)z, pin, pout, s->scal, ki);
                 kt.end();
+                if (dist) {
+                    SA_TRY(dist_halo<double>(s, 0, pout, s->pitch, s->plane, 1, 1));
+                    SA_TRY(dist_reduce(s, DIST_PQ, ki & 3, (ki + 2) & 3));
+                }
                 kt.begin(KC_UPDATE, n * live);
                 if (strip)
                     SA_TRY(launch_update2(ctx, lv, nb, false, u0, pout, r0, rf, s->scal, ki));
@@ -495,6 +525,10 @@ int solve_scene(sa_scene* s, const sa_options& o, sa_stats* stats)
                 else
                     SA_LAUNCH(ctx, (k_update<false, false>), grid, block, 0, lv, u0, pout, r0, nullptr, s->scal, ki);
                 kt.end();
+                if (dist) {
+                    SA_TRY(dist_halo<float>(s, 0, rf, s->pitch, s->plane, 3, 3));
+                    SA_TRY(dist_reduce(s, DIST_RR, (ki + 1) & 3, -1));
+                }
                 SA_LAUNCH(ctx, k_check_converged, (nb + 63) / 64, 64, 0, s->scal, nb, ki + 1);
             } else {
                 kt.begin(KC_DIRECTION, n * live);
@@ -503,12 +537,21 @@ int solve_scene(sa_scene* s, const sa_options& o, sa_stats* stats)
                 else
                     SA_LAUNCH(ctx, (k_direction<true, double>), grid, block, 0, lv, r0, pin, pout, s->scal, ki);
                 kt.end();
+                if (dist) {
+                    SA_TRY(dist_halo<double>(s, 0, pout, s->pitch, s->plane, 1, 1));
+                    SA_TRY(dist_reduce(s, DIST_PQ, ki & 3, (ki + 2) & 3));
+                }
                 kt.begin(KC_UPDATE, n * live);
                 if (strip)
                     SA_TRY(launch_update2(ctx, lv, nb, true, u0, pout, r0, nullptr, s->scal, ki));
                 else
                     SA_LAUNCH(ctx, (k_update<true, false>), grid, block, 0, lv, u0, pout, r0, nullptr, s->scal, ki);
                 kt.end();
+                if (dist) {  // ranks must agree on the stop: test it from the reduced norm after every iteration
+                    SA_TRY(dist_halo<double>(s, 0, r0, s->pitch, s->plane, 1, 1));
+                    SA_TRY(dist_reduce(s, DIST_RR_RZ, (ki + 1) & 3, -1));
+                    SA_LAUNCH(ctx, k_check_converged, (nb + 63) / 64, 64, 0, s->scal, nb, ki + 1);
+                }
             }
         }
         SA_CUDA(ctx, cudaGetLastError());
@@ -521,7 +564,8 @@ int solve_scene(sa_scene* s, const sa_options& o, sa_stats* stats)
         all_done = live == 0;
     }
     SA_LAUNCH(ctx, k_final_check, (nb + 63) / 64, 64, 0, s->scal, nb, (int)(k & 0x3fffffff));
-    SA_LAUNCH(ctx, k_zero_unknowns, grid, block, 0, lv, u0, s->scal);
+    if (have_tiles)
+        SA_LAUNCH(ctx, k_zero_unknowns, grid, block, 0, lv, u0, s->scal);
     SA_CUDA(ctx, cudaGetLastError());
     SA_CUDA(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
     SA_CUDA(ctx, cudaMemcpyAsync(h_scal, s->scal, sizeof(BandScalars) * nb, cudaMemcpyDeviceToHost, ctx->stream));

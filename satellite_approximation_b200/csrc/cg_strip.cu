@@ -315,6 +315,8 @@ __global__ void __launch_bounds__(ST_THREADS) k_update2(Level lv, double* __rest
 int launch_direction2(sa_ctx* ctx, const Level& lv, int nbands, bool jacobi, const void* zin, bool z_is_float,
     const double* p_old, double* p_new, BandScalars* scal, int k)
 {
+    if (lv.n_tiles == 0)
+        return SA_OK;
     dim3 grid((unsigned)lv.n_tiles, (unsigned)nbands);
     if (jacobi) {
         if (lv.fixed_diag)
@@ -338,6 +340,8 @@ int launch_direction2(sa_ctx* ctx, const Level& lv, int nbands, bool jacobi, con
 int launch_update2(sa_ctx* ctx, const Level& lv, int nbands, bool jacobi, double* u, const double* p, double* r, float* rf,
     BandScalars* scal, int k)
 {
+    if (lv.n_tiles == 0)
+        return SA_OK;
     dim3 grid((unsigned)lv.n_tiles, (unsigned)nbands);
     if (jacobi) {
         if (lv.fixed_diag)

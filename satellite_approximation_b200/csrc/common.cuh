@@ -75,6 +75,10 @@ struct Level {
 }  // namespace satfill
 
 struct sa_ctx {
+    // row decomposition across GPUs (dist.cu): NCCL communicator (void*: nccl.h stays out of this header), rank, size
+    void* comm = nullptr;
+    int rank = 0, world = 1;
+    double* d_red = nullptr;  // packed per-band scalars for the all-reduce
     int device = 0;
     cudaStream_t stream = nullptr;
     bool owns_stream = false;
@@ -103,7 +107,19 @@ struct sa_level_store {
     int64_t n_unknowns = 0;
 };
 
+// One distributed multigrid level as a rank sees it: the rows it owns and its slice of the raster-ordered tile list.
+struct DistLevel {
+    int64_t row_lo = 0, row_hi = 0, rows = 0;
+    int tile_lo = 0, tile_hi = 0;
+    std::vector<int64_t> bounds;  // row boundaries of all ranks at this level (world + 1)
+};
+
 struct sa_scene {
+    // row decomposition (dist.cu)
+    bool distributed = false, dist_planned = false, dist_mg = false;
+    int dist_levels = 0;                      // multigrid levels that are split by rows; coarser ones are replicated
+    std::vector<DistLevel> dl;
+    std::vector<int64_t> dist_gather_rows;    // rows of the first replicated level each rank produces (world + 1)
     sa_ctx* ctx = nullptr;
     int problem = SA_LAPLACE;
     int64_t user_rows = 0, user_cols = 0;  // as given to sa_scene_create
@@ -268,6 +284,21 @@ int launch_direction2(sa_ctx* ctx, const Level& lv, int nbands, bool jacobi, con
     const double* p_old, double* p_new, BandScalars* scal, int k);
 int launch_update2(sa_ctx* ctx, const Level& lv, int nbands, bool jacobi, double* u, const double* p, double* r, float* rf,
     BandScalars* scal, int k);
+
+// ---- dist.cu: row decomposition of one system across GPUs -------------------------------------------------------------
+enum DistWhat { DIST_SETUP = 0, DIST_RZ = 1, DIST_PQ = 2, DIST_RR = 3, DIST_RR_RZ = 4 };
+void dist_partition(int64_t rows, int world, int levels, int64_t* row_begin);
+int dist_choose_levels(int64_t rows, int world);
+int dist_unique_id(void* out128);
+int dist_init(sa_ctx* ctx, const void* id128, int rank, int world);
+void dist_shutdown(sa_ctx* ctx);
+int dist_plan_scene(sa_scene* s, bool multigrid);
+Level dist_level(const sa_scene* s, int l, const Level& full);
+template <typename T>
+int dist_halo(sa_scene* s, int l, T* base, int64_t pitch, int64_t plane, int above, int below);
+int dist_gather(sa_scene* s, float* base, int64_t pitch, int64_t plane);
+int dist_reduce(sa_scene* s, int what, int slot, int clear_slot);
+int dist_allgather_band(sa_scene* s, int band);
 
 // ---- mg_fused.cu -------------------------------------------------------------------------------------------------
 int launch_mg_down(sa_ctx* ctx, const Level& lf, const Level& lc, int nbands, const double* b, double* x_out, double* bc,

@@ -438,6 +438,8 @@ struct RBLevel {
 
 int launch_down(sa_ctx* ctx, const RBLevel& F, const RBLevel& C, int nb, const BandScalars* scal)
 {
+    if (F.lv.n_tiles == 0)
+        return SA_OK;
     dim3 grid((unsigned)F.lv.n_tiles, (unsigned)nb);
     if (F.lv.winv)
         SA_LAUNCH(ctx, (k_rb_down<true, true>), grid, RB_HP * RB_DOWN_NG, 0, F.lv, C.lv, F.b, F.xr, C.b, scal);
@@ -451,6 +453,8 @@ int launch_down(sa_ctx* ctx, const RBLevel& F, const RBLevel& C, int nb, const B
 template <bool DOT>
 int launch_up(sa_ctx* ctx, const RBLevel& F, const RBLevel& C, int nb, BandScalars* scal, int slot)
 {
+    if (F.lv.n_tiles == 0)
+        return SA_OK;
     dim3 grid((unsigned)F.lv.n_tiles, (unsigned)nb);
     if (F.lv.winv)
         SA_LAUNCH(ctx, (k_rb_up<true, DOT, true>), grid, RB_HP * RB_UP_NG, 0, F.lv, C.lv, F.xr, F.b, C.x, F.x, scal, slot);
@@ -491,6 +495,12 @@ int apply_vcycle_rb(sa_scene* s, const sa_options& o, KernelTimer& kt, int rz_sl
     const int nl = (int)L.size();
     BandScalars* scal = s->scal;
     const int coarse_sweeps = 16;
+    // row decomposition (dist.cu): levels below dist_levels run on the rank's slice and exchange halo rows, the others
+    // are replicated on every rank
+    const bool dist = s->distributed && s->dist_planned && ctx->world > 1;
+    const int dlv = dist ? s->dist_levels : 0;
+    for (int l = 0; l < nl && l < dlv; ++l)
+        L[l].lv = dist_level(s, l, L[l].lv);
     if (nl == 1) {
         kt.begin(KC_SMOOTH, L[0].units);
         SA_TRY((launch_coarsest<true>(ctx, L[0], nb, scal, rz_slot, coarse_sweeps)));
@@ -502,6 +512,15 @@ int apply_vcycle_rb(sa_scene* s, const sa_options& o, KernelTimer& kt, int rz_sl
         kt.begin(l == 0 ? KC_MG_DOWN : KC_MG_DOWN_COARSE, L[l].units);
         SA_TRY(launch_down(ctx, L[l], L[l + 1], nb, scal));
         kt.end();
+        if (l < dlv) {
+            // the ascent reads the red half of the iterate 2 rows beyond the slice; the next level's descent reads
+            // its right-hand side 3 rows beyond -- or, if that level is replicated, everywhere
+            SA_TRY(dist_halo<float>(s, l, L[l].xr, L[l].lv.pitch >> 1, L[l].lv.plane >> 1, 2, 2));
+            if (l + 1 < dlv)
+                SA_TRY(dist_halo<float>(s, l + 1, L[l + 1].b, L[l + 1].lv.pitch, L[l + 1].lv.plane, 3, 3));
+            else
+                SA_TRY(dist_gather(s, L[l + 1].b, L[l + 1].lv.pitch, L[l + 1].lv.plane));
+        }
     }
     kt.begin(KC_SMOOTH, L[nl - 1].units);
     SA_TRY((launch_coarsest<false>(ctx, L[nl - 1], nb, scal, 0, coarse_sweeps)));
@@ -513,6 +532,8 @@ int apply_vcycle_rb(sa_scene* s, const sa_options& o, KernelTimer& kt, int rz_sl
         else
             SA_TRY((launch_up<false>(ctx, L[l], L[l + 1], nb, scal, 0)));
         kt.end();
+        if (l < dlv)  // the finer level's ascent interpolates from up to 2 coarse rows beyond; CG's direction needs 1 row of z
+            SA_TRY(dist_halo<float>(s, l, L[l].x, L[l].lv.pitch, L[l].lv.plane, l == 0 ? 1 : 2, l == 0 ? 1 : 2));
     }
     SA_CUDA(ctx, cudaGetLastError());
     return SA_OK;
