@@ -4,7 +4,10 @@
 // usable device.
 #include "common.cuh"
 
+#include <algorithm>
+#include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <new>
 
 using namespace satfill;
@@ -131,28 +134,34 @@ int64_t slow_stride(const sa_scene* s, int64_t rs, int64_t cs)
 }
 
 template <typename T>
-int copy_in(sa_scene* s, T* dst0, const T* src, int64_t rs, int64_t cs, int on_device, int64_t row_lo, int64_t row_hi)
+int copy_in(sa_scene* s, T* dst0, const T* src, int64_t rs, int64_t cs, int on_device, int64_t row_lo, int64_t row_hi,
+    cudaStream_t stream = nullptr)
 {
     sa_ctx* ctx = s->ctx;
+    if (!stream)
+        stream = ctx->stream;
     if (row_hi <= row_lo || s->cols == 0)
         return SA_OK;
     int64_t sp = slow_stride(s, rs, cs);
     SA_CUDA(ctx, cudaMemcpy2DAsync(dst0 + row_lo * s->pitch, (size_t)s->pitch * sizeof(T), src + row_lo * sp,
                      (size_t)sp * sizeof(T), (size_t)s->cols * sizeof(T), (size_t)(row_hi - row_lo),
-                     on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
+                     on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, stream));
     return SA_OK;
 }
 
 template <typename T>
-int copy_out(sa_scene* s, const T* src0, T* dst, int64_t rs, int64_t cs, int on_device, int64_t row_lo, int64_t row_hi)
+int copy_out(sa_scene* s, const T* src0, T* dst, int64_t rs, int64_t cs, int on_device, int64_t row_lo, int64_t row_hi,
+    cudaStream_t stream = nullptr)
 {
     sa_ctx* ctx = s->ctx;
+    if (!stream)
+        stream = ctx->stream;
     if (row_hi <= row_lo || s->cols == 0)
         return SA_OK;
     int64_t dp = slow_stride(s, rs, cs);
     SA_CUDA(ctx, cudaMemcpy2DAsync(dst + row_lo * dp, (size_t)dp * sizeof(T), src0 + row_lo * s->pitch,
                      (size_t)s->pitch * sizeof(T), (size_t)s->cols * sizeof(T), (size_t)(row_hi - row_lo),
-                     on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, ctx->stream));
+                     on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, stream));
     return SA_OK;
 }
 
@@ -244,6 +253,12 @@ void sa_destroy(sa_ctx* ctx)
     cudaStreamSynchronize(ctx->stream);
     scene_free(cache_of(ctx)->scene);
     dist_shutdown(ctx);
+    for (cudaEvent_t e : ctx->io_ev)
+        cudaEventDestroy(e);
+    if (ctx->io_in)
+        cudaStreamDestroy(ctx->io_in);
+    if (ctx->io_out)
+        cudaStreamDestroy(ctx->io_out);
     for (auto& ev : ctx->ev)
         if (ev)
             cudaEventDestroy(ev);
@@ -647,19 +662,79 @@ static int host_fill(sa_ctx* ctx, int problem, double* const* images, const doub
         row_lo = 0;
     if (row_hi > s->rows)
         row_hi = s->rows;
-    for (int b = 0; b < nbands; ++b) {
-        SA_TRY(copy_in<double>(s, s->plane0(s->u, b), images[b], rs, cs, 0, row_lo, row_hi));
-        if (problem == SA_POISSON)
-            SA_TRY(copy_in<double>(s, s->plane0(s->g, b), guidance[b], rs, cs, 0, row_lo, row_hi));
+    // 2. Bands cross PCIe and are solved in chunks: chunk c + 1 .. are on their way in (io_in) and chunk c - 1 is on
+    //    its way out (io_out) while chunk c is solved on the context's stream.  A chunk is at least ~256 MB of image so
+    //    that its transfer hides the solve's fixed costs; small scenes go through as one chunk.
+    const int64_t band_bytes = (row_hi - row_lo) * s->cols * (int64_t)sizeof(double);
+    int64_t chunk_bytes = (int64_t)256 << 20;
+    if (const char* e = std::getenv("SATFILL_CHUNK_BYTES"))  // tests force the chunked path on small scenes
+        chunk_bytes = std::max<int64_t>(1, std::atoll(e));
+    int per_chunk = (int)std::min<int64_t>(nbands, std::max<int64_t>(1, chunk_bytes / std::max<int64_t>(band_bytes, 1)));
+    const bool windows_ok = o.precond != SA_PRECOND_MULTIGRID || o.mg_variant == SA_MG_RB32;
+    if (per_chunk >= nbands || !windows_ok || std::getenv("SATFILL_NO_PIPELINE"))
+        per_chunk = nbands;
+    const int nch = (nbands + per_chunk - 1) / per_chunk;
+    if (nch > 1) {
+        if (!ctx->io_in) {
+            SA_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->io_in, cudaStreamNonBlocking));
+            SA_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->io_out, cudaStreamNonBlocking));
+        }
+        while ((int)ctx->io_ev.size() < nch) {
+            cudaEvent_t e;
+            SA_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            ctx->io_ev.push_back(e);
+        }
     }
-    int st = solve_scene(s, o, stats);
-    // Laplace never looks at the solver status (laplace.cpp:113-119); Poisson writes nothing unless every band
-    // converged (poisson.cpp:263-269).
-    if (st == SA_OK || (problem == SA_LAPLACE && st == SA_NOT_CONVERGED)) {
+    cudaStream_t sin = nch > 1 ? ctx->io_in : ctx->stream, sout = nch > 1 ? ctx->io_out : ctx->stream;
+    for (int c = 0; c < nch; ++c) {
+        for (int b = c * per_chunk; b < std::min(nbands, (c + 1) * per_chunk); ++b) {
+            SA_TRY(copy_in<double>(s, s->plane0(s->u, b), images[b], rs, cs, 0, row_lo, row_hi, sin));
+            if (problem == SA_POISSON)
+                SA_TRY(copy_in<double>(s, s->plane0(s->g, b), guidance[b], rs, cs, 0, row_lo, row_hi, sin));
+        }
+        if (nch > 1)
+            SA_CUDA(ctx, cudaEventRecord(ctx->io_ev[(size_t)c], sin));
+    }
+    // Laplace never looks at the solver status (laplace.cpp:113-119): a chunk leaves as soon as it is solved.  Poisson
+    // writes nothing unless every band converged (poisson.cpp:263-269): its bands leave after the last chunk.
+    int st = SA_OK;
+    const bool dbg = std::getenv("SATFILL_DEBUG_IO") != nullptr;
+    auto now_ms = [] { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; };
+    const double t_start = now_ms();
+    for (int c = 0; c < nch; ++c) {
+        const int b0 = c * per_chunk, b1 = std::min(nbands, (c + 1) * per_chunk);
+        if (dbg) {
+            cudaEventSynchronize(ctx->io_ev[(size_t)c]);
+            std::fprintf(stderr, "[satfill io] chunk %d: in at %.1f ms", c, now_ms() - t_start);
+        }
+        if (nch > 1)
+            SA_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->io_ev[(size_t)c], 0));
+        s->band0 = b0;
+        s->band_n = b1 - b0;
+        int stc = solve_scene(s, o, stats ? stats + b0 : nullptr);  // returns with the context's stream drained
+        s->band0 = 0;
+        s->band_n = -1;
+        if (dbg)
+            std::fprintf(stderr, ", solved at %.1f ms\n", now_ms() - t_start);
+        if (stc != SA_OK && stc != SA_NOT_CONVERGED) {
+            cudaStreamSynchronize(sin);
+            cudaStreamSynchronize(sout);
+            return stc;
+        }
+        if (stc != SA_OK)
+            st = stc;
+        if (problem == SA_LAPLACE)
+            for (int b = b0; b < b1; ++b)
+                SA_TRY(copy_out<double>(s, s->plane0(s->u, b), images[b], rs, cs, 0, row_lo, row_hi, sout));
+    }
+    if (problem == SA_POISSON && st == SA_OK)
         for (int b = 0; b < nbands; ++b)
-            SA_TRY(copy_out<double>(s, s->plane0(s->u, b), images[b], rs, cs, 0, row_lo, row_hi));
-        SA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    }
+            SA_TRY(copy_out<double>(s, s->plane0(s->u, b), images[b], rs, cs, 0, row_lo, row_hi, sout));
+    SA_CUDA(ctx, cudaStreamSynchronize(sout));
+    if (nch > 1)
+        SA_CUDA(ctx, cudaStreamSynchronize(sin));
+    if (dbg)
+        std::fprintf(stderr, "[satfill io] all out at %.1f ms\n", now_ms() - t_start);
     return st;
 }
 

@@ -277,6 +277,16 @@ __global__ void k_check_converged(BandScalars* scal, int nbands, int k)
     }
 }
 
+// The host polls the per-band scalars through pinned host memory that this kernel writes (cudaMallocHost memory is
+// device-addressable under unified addressing): no copy-engine transfer inside the loop, so the poll never queues
+// behind the band transfers that the host-pointer entry points keep in flight on the other streams (api.cu).
+__global__ void k_publish_scalars(const BandScalars* __restrict__ scal, int nbands, BandScalars* __restrict__ host)
+{
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < nbands)
+        host[b] = scal[b];
+}
+
 __global__ void k_final_check(BandScalars* scal, int nbands, int k_end)
 {
     int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -404,7 +414,9 @@ int precondition_scene(sa_scene* s, const sa_options& o)
 int solve_scene(sa_scene* s, const sa_options& o, sa_stats* stats)
 {
     sa_ctx* ctx = s->ctx;
-    const int nb = s->nbands;
+    // the band window [band0, band0 + nb): `stats` and every per-band base pointer below start at its first band
+    const int nb = s->win_n(), b0 = s->band0;
+    BandScalars* const scal = s->scal + b0;
     const bool poisson = s->problem == SA_POISSON;
     const bool mg = o.precond == SA_PRECOND_MULTIGRID;
     const bool rb = mg && o.mg_variant == SA_MG_RB32;
@@ -435,6 +447,10 @@ int solve_scene(sa_scene* s, const sa_options& o, sa_stats* stats)
         SA_TRY(ensure_multigrid(s, o));
     // one system split by rows across the ranks of the context's communicator (dist.cu)
     const bool dist = s->distributed && ctx->world > 1;
+    if (dist && (b0 != 0 || nb != s->nbands))
+        return fail(ctx, SA_BAD_ARGUMENT, "distributed solve: band windows are not supported");
+    if (mg && !rb && (b0 != 0 || nb != s->nbands))
+        return fail(ctx, SA_BAD_ARGUMENT, "band windows need the Jacobi or the red-black multigrid preconditioner");
     if (dist) {
         if (!strip || (mg && !rb))
             return fail(ctx, SA_BAD_ARGUMENT, "distributed solve: needs the strip CG kernels and the red-black cycle");
@@ -445,12 +461,12 @@ int solve_scene(sa_scene* s, const sa_options& o, sa_stats* stats)
     Level lv = dist ? dist_level(s, 0, fine_level(s)) : fine_level(s);
     const bool have_tiles = lv.n_tiles > 0;  // a rank's slice may hold no active tile
     dim3 grid((unsigned)(have_tiles ? lv.n_tiles : 1), (unsigned)nb), block(CG_BLOCK_X, CG_BLOCK_Y);
-    double* u0 = s->plane0(s->u, 0);
-    double* g0 = poisson ? s->plane0(s->g, 0) : nullptr;
-    double* r0 = s->plane0(s->r, 0);
-    double* pbuf[2] = { s->plane0(s->p[0], 0), s->plane0(s->p[1], 0) };
+    double* u0 = s->plane0(s->u, b0);
+    double* g0 = poisson ? s->plane0(s->g, b0) : nullptr;
+    double* r0 = s->plane0(s->r, b0);
+    double* pbuf[2] = { s->plane0(s->p[0], b0), s->plane0(s->p[1], b0) };
 
-    SA_CUDA(ctx, cudaMemsetAsync(s->scal, 0, sizeof(BandScalars) * nb, ctx->stream));
+    SA_CUDA(ctx, cudaMemsetAsync(scal, 0, sizeof(BandScalars) * nb, ctx->stream));
     if (have_tiles) {
         if (poisson)
             SA_LAUNCH(ctx, k_init_guess<true>, grid, block, 0, lv, u0, g0);
@@ -461,9 +477,9 @@ int solve_scene(sa_scene* s, const sa_options& o, sa_stats* stats)
         SA_TRY(dist_halo<double>(s, 0, u0, s->pitch, s->plane, 1, 1));
     if (have_tiles) {
         if (poisson)
-            SA_LAUNCH(ctx, k_residual<true>, grid, block, 0, lv, u0, g0, r0, rb ? s->rb_rf() : nullptr, s->scal);
+            SA_LAUNCH(ctx, k_residual<true>, grid, block, 0, lv, u0, g0, r0, rb ? s->rb_rf() : nullptr, scal);
         else
-            SA_LAUNCH(ctx, k_residual<false>, grid, block, 0, lv, u0, g0, r0, rb ? s->rb_rf() : nullptr, s->scal);
+            SA_LAUNCH(ctx, k_residual<false>, grid, block, 0, lv, u0, g0, r0, rb ? s->rb_rf() : nullptr, scal);
     }
     if (dist) {
         SA_TRY(dist_reduce(s, DIST_SETUP, 0, -1));
@@ -472,7 +488,7 @@ int solve_scene(sa_scene* s, const sa_options& o, sa_stats* stats)
         else
             SA_TRY(dist_halo<double>(s, 0, r0, s->pitch, s->plane, 1, 1));
     }
-    SA_LAUNCH(ctx, k_finalize_setup, (nb + 63) / 64, 64, 0, s->scal, nb, o.tolerance, mg ? 1 : 0);
+    SA_LAUNCH(ctx, k_finalize_setup, (nb + 63) / 64, 64, 0, scal, nb, o.tolerance, mg ? 1 : 0);
     SA_CUDA(ctx, cudaGetLastError());
     SA_CUDA(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
 
@@ -480,6 +496,8 @@ int solve_scene(sa_scene* s, const sa_options& o, sa_stats* stats)
     kt.ctx = ctx;
     kt.on = o.profile != 0;
     BandScalars* h_scal = (BandScalars*)ctx->pinned;
+    BandScalars* h_scal_dev = nullptr;  // the same memory as the device addresses it (k_publish_scalars)
+    SA_CUDA(ctx, cudaHostGetDevicePointer((void**)&h_scal_dev, h_scal, 0));
     // Jacobi iterations are short (two kernels): poll the flags every 32.  A multigrid iteration is a whole V-cycle:
     // poll every iteration, which also keeps the profile's per-class unit counts exact.
     const int check = o.check_every > 0 ? o.check_every : (mg ? 1 : 32);
@@ -500,18 +518,18 @@ int solve_scene(sa_scene* s, const sa_options& o, sa_stats* stats)
                     z = s->rb_z();
                 } else {
                     SA_TRY(apply_vcycle(s, o, kt, ki & 3, live));
-                    z = s->plane0(s->z, 0);
+                    z = s->plane0(s->z, b0);
                 }
                 float* rf = rb ? s->rb_rf() : nullptr;
                 if (dist)
                     SA_TRY(dist_reduce(s, DIST_RZ, ki & 3, -1));
                 kt.begin(KC_DIRECTION, n * live);
                 if (strip)
-                    SA_TRY(launch_direction2(ctx, lv, nb, false, z, rb, pin, pout, s->scal, ki));
+                    SA_TRY(launch_direction2(ctx, lv, nb, false, z, rb, pin, pout, scal, ki));
                 else if (rb)
-                    SA_LAUNCH(ctx, (k_direction<false, float>), grid, block, 0, lv, (const float*)z, pin, pout, s->scal, ki);
+                    SA_LAUNCH(ctx, (k_direction<false, float>), grid, block, 0, lv, (const float*)z, pin, pout, scal, ki);
                 else
-                    SA_LAUNCH(ctx, (k_direction<false, double>), grid, block, 0, lv, (const double*)z, pin, pout, s->scal, ki);
+                    SA_LAUNCH(ctx, (k_direction<false, double>), grid, block, 0, lv, (const double*)z, pin, pout, scal, ki);
                 kt.end();
                 if (dist) {
                     SA_TRY(dist_halo<double>(s, 0, pout, s->pitch, s->plane, 1, 1));
@@ -519,23 +537,23 @@ int solve_scene(sa_scene* s, const sa_options& o, sa_stats* stats)
                 }
                 kt.begin(KC_UPDATE, n * live);
                 if (strip)
-                    SA_TRY(launch_update2(ctx, lv, nb, false, u0, pout, r0, rf, s->scal, ki));
+                    SA_TRY(launch_update2(ctx, lv, nb, false, u0, pout, r0, rf, scal, ki));
                 else if (rb)
-                    SA_LAUNCH(ctx, (k_update<false, true>), grid, block, 0, lv, u0, pout, r0, rf, s->scal, ki);
+                    SA_LAUNCH(ctx, (k_update<false, true>), grid, block, 0, lv, u0, pout, r0, rf, scal, ki);
                 else
-                    SA_LAUNCH(ctx, (k_update<false, false>), grid, block, 0, lv, u0, pout, r0, nullptr, s->scal, ki);
+                    SA_LAUNCH(ctx, (k_update<false, false>), grid, block, 0, lv, u0, pout, r0, nullptr, scal, ki);
                 kt.end();
                 if (dist) {
                     SA_TRY(dist_halo<float>(s, 0, rf, s->pitch, s->plane, 3, 3));
                     SA_TRY(dist_reduce(s, DIST_RR, (ki + 1) & 3, -1));
                 }
-                SA_LAUNCH(ctx, k_check_converged, (nb + 63) / 64, 64, 0, s->scal, nb, ki + 1);
+                SA_LAUNCH(ctx, k_check_converged, (nb + 63) / 64, 64, 0, scal, nb, ki + 1);
             } else {
                 kt.begin(KC_DIRECTION, n * live);
                 if (strip)
-                    SA_TRY(launch_direction2(ctx, lv, nb, true, r0, false, pin, pout, s->scal, ki));
+                    SA_TRY(launch_direction2(ctx, lv, nb, true, r0, false, pin, pout, scal, ki));
                 else
-                    SA_LAUNCH(ctx, (k_direction<true, double>), grid, block, 0, lv, r0, pin, pout, s->scal, ki);
+                    SA_LAUNCH(ctx, (k_direction<true, double>), grid, block, 0, lv, r0, pin, pout, scal, ki);
                 kt.end();
                 if (dist) {
                     SA_TRY(dist_halo<double>(s, 0, pout, s->pitch, s->plane, 1, 1));
@@ -543,19 +561,19 @@ int solve_scene(sa_scene* s, const sa_options& o, sa_stats* stats)
                 }
                 kt.begin(KC_UPDATE, n * live);
                 if (strip)
-                    SA_TRY(launch_update2(ctx, lv, nb, true, u0, pout, r0, nullptr, s->scal, ki));
+                    SA_TRY(launch_update2(ctx, lv, nb, true, u0, pout, r0, nullptr, scal, ki));
                 else
-                    SA_LAUNCH(ctx, (k_update<true, false>), grid, block, 0, lv, u0, pout, r0, nullptr, s->scal, ki);
+                    SA_LAUNCH(ctx, (k_update<true, false>), grid, block, 0, lv, u0, pout, r0, nullptr, scal, ki);
                 kt.end();
                 if (dist) {  // ranks must agree on the stop: test it from the reduced norm after every iteration
                     SA_TRY(dist_halo<double>(s, 0, r0, s->pitch, s->plane, 1, 1));
                     SA_TRY(dist_reduce(s, DIST_RR_RZ, (ki + 1) & 3, -1));
-                    SA_LAUNCH(ctx, k_check_converged, (nb + 63) / 64, 64, 0, s->scal, nb, ki + 1);
+                    SA_LAUNCH(ctx, k_check_converged, (nb + 63) / 64, 64, 0, scal, nb, ki + 1);
                 }
             }
         }
         SA_CUDA(ctx, cudaGetLastError());
-        SA_CUDA(ctx, cudaMemcpyAsync(h_scal, s->scal, sizeof(BandScalars) * nb, cudaMemcpyDeviceToHost, ctx->stream));
+        SA_LAUNCH(ctx, k_publish_scalars, (nb + 63) / 64, 64, 0, scal, nb, h_scal_dev);
         SA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         kt.flush();
         live = 0;
@@ -563,12 +581,12 @@ int solve_scene(sa_scene* s, const sa_options& o, sa_stats* stats)
             live += h_scal[b].done ? 0 : 1;
         all_done = live == 0;
     }
-    SA_LAUNCH(ctx, k_final_check, (nb + 63) / 64, 64, 0, s->scal, nb, (int)(k & 0x3fffffff));
+    SA_LAUNCH(ctx, k_final_check, (nb + 63) / 64, 64, 0, scal, nb, (int)(k & 0x3fffffff));
     if (have_tiles)
-        SA_LAUNCH(ctx, k_zero_unknowns, grid, block, 0, lv, u0, s->scal);
+        SA_LAUNCH(ctx, k_zero_unknowns, grid, block, 0, lv, u0, scal);
     SA_CUDA(ctx, cudaGetLastError());
     SA_CUDA(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
-    SA_CUDA(ctx, cudaMemcpyAsync(h_scal, s->scal, sizeof(BandScalars) * nb, cudaMemcpyDeviceToHost, ctx->stream));
+    SA_LAUNCH(ctx, k_publish_scalars, (nb + 63) / 64, 64, 0, scal, nb, h_scal_dev);
     SA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     float setup_ms = 0.f, solve_ms = 0.f;
     cudaEventElapsedTime(&setup_ms, ctx->ev[0], ctx->ev[1]);

@@ -24,6 +24,23 @@ namespace {
 
 constexpr int ST_THREADS = 128;
 constexpr int ST_RG = 4;  // rows per thread
+// resident CTAs per SM the two kernels are compiled for (register budget) and launched with (persistent grids)
+#ifndef SATFILL_DIR_CTAS
+#define SATFILL_DIR_CTAS 6
+#endif
+#ifndef SATFILL_UPD_CTAS
+#define SATFILL_UPD_CTAS 5
+#endif
+#ifndef SATFILL_L2_PREFETCH
+#define SATFILL_L2_PREFETCH 0
+#endif
+#ifndef SATFILL_SECTOR_STORES
+#define SATFILL_SECTOR_STORES 1
+#endif
+constexpr int ST_DIR_CTAS = SATFILL_DIR_CTAS, ST_UPD_CTAS = SATFILL_UPD_CTAS;
+// a double z costs 12 more registers than a float one
+template <typename ZT>
+constexpr int dir_ctas() { return sizeof(ZT) == 8 && ST_DIR_CTAS > 6 ? 6 : ST_DIR_CTAS; }
 
 __device__ __forceinline__ double2 ldnc2_if(const double* p, unsigned pred)
 {
@@ -69,39 +86,42 @@ __device__ __forceinline__ double ldnc_if(const float* p, unsigned pred)
     return (double)v;
 }
 
-// Everything a thread needs to know about where it is.
-struct Strip {
-    int cx, row0;          // column pair index (0..15), first own row (tile-local)
-    int64_t gr, gc;        // global row of row0, global column of the pair's left cell
-    unsigned mL, mR;       // unknown bits of the two columns: bit j <=> tile row row0 - 1 + j, j = 0..5
-    int toff;              // element offset of (row0 - 1, left cell) from the tile's origin, in a plane of pitch `pitch`
-    int pitch;
+// What a thread needs to know about a tile: its coordinates and the unknown bits of the thread's two columns.
+struct TileBits {
+    int yx;      // ty << 16 | tx
+    unsigned m;  // mL | mR << 8: unknown bits of the two columns, bit j <=> tile row row0 - 1 + j, j = 0..5
+    __device__ __forceinline__ int ty() const { return yx >> 16; }
+    __device__ __forceinline__ int tx() const { return yx & 0xffff; }
+    __device__ __forceinline__ unsigned mL() const { return m & 63u; }
+    __device__ __forceinline__ unsigned mR() const { return m >> 8; }
+    __device__ __forceinline__ unsigned any() const { return (m | (m >> 8)) & 63u; }
+    // element offset of the tile's origin inside a band plane (fits 32 bits: a plane has < 2^31 elements)
+    __device__ __forceinline__ int origin(int pitch) const { return ty() * (TILE_H * pitch) + tx() * TILE_W; }
 };
 
-__device__ __forceinline__ Strip make_strip(const Level& lv, int tile_index, int& ty, int& tx)
+// Column masks of the thread's aligned column pair (2cx, 2cx + 1), rows row0 - 1 .. row0 + 4, from the transposed
+// per-tile bit words of the tile and of the tiles above and below it: three 8-byte loads that hit L2 (or L1).
+__device__ __forceinline__ TileBits load_tile_bits(const Level& lv, int yx, int cx, int row0)
 {
-    Strip s;
-    const int t = threadIdx.x;
-    const int yx = lv.tile_yx[tile_index];
-    ty = yx >> 16;
-    tx = yx & 0xffff;
-    s.cx = t & 15;
-    s.row0 = (t >> 4) * ST_RG;
-    s.pitch = (int)lv.pitch;
-    s.gr = (int64_t)ty * TILE_H + s.row0;
-    s.gc = (int64_t)tx * TILE_W + 2 * s.cx;
-    // frame column of tile column c is c + 1 (halo 1); bit (row + 1) of the mask <=> tile row `row`
-    unsigned long long cl = region_col_mask<1>(lv, ty, tx, 2 * s.cx + 1), cr = region_col_mask<1>(lv, ty, tx, 2 * s.cx + 2);
-    s.mL = (unsigned)(cl >> s.row0) & 63u;
-    s.mR = (unsigned)(cr >> s.row0) & 63u;
-    s.toff = (s.row0 - 1) * s.pitch + 2 * s.cx;
-    return s;
+    TileBits b;
+    b.yx = yx;
+    const uint32_t* w = lv.tbitsT + ((size_t)(b.ty() + 1) * lv.tb_stride + (b.tx() + 1)) * 32 + 2 * cx;
+    const size_t vs = (size_t)lv.tb_stride * 32;
+    const uint2 C = __ldg(reinterpret_cast<const uint2*>(w));
+    const uint2 N = __ldg(reinterpret_cast<const uint2*>(w - vs));
+    const uint2 S = __ldg(reinterpret_cast<const uint2*>(w + vs));
+    // bit (row + 1) of the 34-bit column <=> tile row `row`
+    unsigned long long cl = ((unsigned long long)N.x >> 31) | ((unsigned long long)C.x << 1) | ((unsigned long long)(S.x & 1u) << 33);
+    unsigned long long cr = ((unsigned long long)N.y >> 31) | ((unsigned long long)C.y << 1) | ((unsigned long long)(S.y & 1u) << 33);
+    b.m = ((unsigned)(cl >> row0) & 63u) | (((unsigned)(cr >> row0) & 63u) << 8);
+    return b;
 }
 
 __device__ __forceinline__ double block_sum4(double v, double* s_red /* 4 */)
 {
     for (int o = 16; o; o >>= 1)
         v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();  // s_red may still be read from the previous band
     if ((threadIdx.x & 31) == 0)
         s_red[threadIdx.x >> 5] = v;
     __syncthreads();
@@ -109,14 +129,9 @@ __device__ __forceinline__ double block_sum4(double v, double* s_red /* 4 */)
 }
 
 template <bool FIXED>
-__device__ __forceinline__ void diag_cols(const Level& lv, const Strip& s, int& dL, int& dR)
+__device__ __forceinline__ int diag_col(const Level& lv, int64_t c)
 {
-    if (FIXED) {
-        dL = dR = 2;
-    } else {
-        dL = (s.gc > 0) + (s.gc < lv.cols - 1);
-        dR = (s.gc + 1 > 0) + (s.gc + 1 < lv.cols - 1);
-    }
+    return FIXED ? 2 : (c > 0) + (c < lv.cols - 1);
 }
 template <bool FIXED>
 __device__ __forceinline__ int diag_row(const Level& lv, int64_t r)
@@ -125,109 +140,180 @@ __device__ __forceinline__ int diag_row(const Level& lv, int64_t r)
 }
 __device__ __forceinline__ double inv_of(int d) { return d == 4 ? 0.25 : (d == 3 ? (1.0 / 3.0) : (d == 2 ? 0.5 : 1.0)); }
 
+// The persistent tile loop shared by both kernels: CTA c visits tiles c, c + G, c + 2G, ... of the level's raster-ordered
+// list (neighbouring CTAs work on neighbouring tiles at the same time, so halo rows meet in L2).  Bytes in flight are
+// what bounds these kernels on cloud-like masks (half of a tile's loads are predicated off, and the register file caps
+// what a resident thread can have outstanding), so the loop runs a three-deep pipeline that costs no registers for
+// data: tile coordinates are fetched three visits ahead, the column masks two visits ahead, and `prefetch(tb)` asks L2
+// for the data of the NEXT visit (prefetch.global.L2, predicated like the loads) right after the current tile's loads
+// have been issued.  The dependent chain per tile is then  L2 -> arithmetic -> store  instead of
+// list -> masks -> HBM -> arithmetic -> store.
+template <typename Body, typename Prefetch>
+__device__ __forceinline__ void for_each_tile(const Level& lv, int cx, int row0, Body body, Prefetch prefetch)
+{
+    const int n = lv.n_tiles, G = (int)gridDim.x;
+    const int last = n - 1;
+    int i1 = (int)blockIdx.x + G, i2 = i1 + G;
+    TileBits tb = load_tile_bits(lv, lv.tile_yx[blockIdx.x], cx, row0);
+    TileBits tb1 = load_tile_bits(lv, lv.tile_yx[i1 < n ? i1 : last], cx, row0);
+    int yx2 = lv.tile_yx[i2 < n ? i2 : last];
+    while (true) {
+        const int i3 = i2 + G;
+        const int yx3 = lv.tile_yx[i3 < n ? i3 : last];
+        const TileBits tb2 = load_tile_bits(lv, yx2, cx, row0);
+        body(tb, tb1, i1 < n, prefetch);
+        if (i1 >= n)
+            break;
+        tb = tb1;
+        tb1 = tb2;
+        yx2 = yx3;
+        i1 = i2;
+        i2 = i3;
+    }
+}
+
+// OR of a row-bit mask over the lanes that share a 32-byte sector: two lanes for double pairs, four for float pairs
+__device__ __forceinline__ unsigned sector_or2(unsigned m)
+{
+    return SATFILL_SECTOR_STORES ? (m | __shfl_xor_sync(0xffffffffu, m, 1)) : m;
+}
+__device__ __forceinline__ unsigned sector_or4(unsigned m2)
+{
+    return SATFILL_SECTOR_STORES ? (m2 | __shfl_xor_sync(0xffffffffu, m2, 2)) : m2;
+}
+
+__device__ __forceinline__ void prefetch_l2_if(const void* p, unsigned pred)
+{
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %1, 0;\n\t@q prefetch.global.L2 [%0];\n\t}" ::"l"(p), "r"(pred));
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------------------------
 // k_direction2:  beta = rz_k / rz_{k-1};  p' = z + beta p  (halo cells recomputed);  pq = p'.Ap'
 //   JACOBI: z = r / d on the fly (zin = r).
+// Persistent: gridDim.x <= n_tiles CTAs, each walks all bands (a band that has converged costs one flag read).
 // ---------------------------------------------------------------------------------------------------------------
 template <bool JACOBI, bool FIXED, typename ZT>
-__global__ void __launch_bounds__(ST_THREADS) k_direction2(Level lv, const ZT* __restrict__ zin,
+__global__ void __launch_bounds__(ST_THREADS, dir_ctas<ZT>()) k_direction2(Level lv, int nbands, const ZT* __restrict__ zin,
     const double* __restrict__ p_old, double* __restrict__ p_new, BandScalars* __restrict__ scal, int k)
 {
     __shared__ double s_red[4];
-    BandScalars& sc = scal[blockIdx.y];
-    if (sc.done)
-        return;
     const int slot = k & 3;
     const bool lead = blockIdx.x == 0 && threadIdx.x == 0;
-    if (k > 0 && sc.rr[slot] < sc.thr) {  // ConjugateGradient.h:72-73 (strict <), tested one launch later
-        if (lead) {
-            sc.rr_exit = sc.rr[slot];
-            sc.iters = k - 1;
-            __threadfence();
-            sc.done = 1;
+    const int cx = threadIdx.x & 15, row0 = (threadIdx.x >> 4) * ST_RG;
+    const int pitch = (int)lv.pitch;
+    const int toff = (row0 - 1) * pitch + 2 * cx;  // (row0 - 1, left cell) from the tile's origin
+    const bool west = cx == 0, east = cx == 15;
+    for (int band = 0; band < nbands; ++band) {
+        BandScalars& sc = scal[band];
+        if (sc.done)
+            continue;
+        if (k > 0 && sc.rr[slot] < sc.thr) {  // ConjugateGradient.h:72-73 (strict <), tested one launch later
+            if (lead) {
+                sc.rr_exit = sc.rr[slot];
+                sc.iters = k - 1;
+                __threadfence();
+                sc.done = 1;
+            }
+            continue;
         }
-        return;
-    }
-    const double beta = k > 0 ? sc.rz[slot] / sc.rz[(k - 1) & 3] : 0.0;  // ConjugateGradient.h:77-79
-    if (lead) {  // recycle the slot two iterations ahead
-        int z2 = (k + 2) & 3;
-        sc.rz[z2] = 0.0;
-        sc.rr[z2] = 0.0;
-        sc.pq[z2] = 0.0;
-    }
-    int ty, tx;
-    const Strip s = make_strip(lv, blockIdx.x, ty, tx);
-    const int64_t origin = (int64_t)blockIdx.y * lv.plane + (int64_t)ty * TILE_H * lv.pitch + (int64_t)tx * TILE_W;
-    const ZT* zb = zin + origin;
-    const double* pb = p_old + origin;
-    const unsigned any = s.mL | s.mR;
-    const bool west = s.cx == 0, east = s.cx == 15;
-    // ---- all loads: pairs of rows row0-1 .. row0+4, and (edge lanes) the halo column of the own rows
-    double2 zv[6], pv[6];
-    double ze[ST_RG], pe[ST_RG];
-#pragma unroll
-    for (int j = 0; j < 6; ++j) {
-        zv[j] = ldnc2_if(zb + (s.toff + j * s.pitch), (any >> j) & 1);
-        pv[j] = ldnc2_if(pb + (s.toff + j * s.pitch), (any >> j) & 1);
-    }
-    {
-        // the halo cell can only matter if the own edge cell is an unknown
-        const int eoff = s.toff + (west ? -1 : 2);
-        const unsigned em = (west ? s.mL : (east ? s.mR : 0u)) >> 1;
-#pragma unroll
-        for (int j = 0; j < ST_RG; ++j) {
-            ze[j] = ldnc_if(zb + (eoff + (j + 1) * s.pitch), (em >> j) & 1);
-            pe[j] = ldnc_if(pb + (eoff + (j + 1) * s.pitch), (em >> j) & 1);
+        const double beta = k > 0 ? sc.rz[slot] / sc.rz[(k - 1) & 3] : 0.0;  // ConjugateGradient.h:77-79
+        if (lead) {  // recycle the slot two iterations ahead
+            int z2 = (k + 2) & 3;
+            sc.rz[z2] = 0.0;
+            sc.rr[z2] = 0.0;
+            sc.pq[z2] = 0.0;
         }
-    }
-    int dcL, dcR;
-    diag_cols<FIXED>(lv, s, dcL, dcR);
-    // ---- p' = z + beta p on the 6 x 2 cells and the edge column
-    double2 pn[6];
+        const int64_t band_off = (int64_t)band * lv.plane;
+        const ZT* zband = zin + band_off;
+        const double* pband = p_old + band_off;
+        double* poband = p_new + band_off;
+        double acc = 0.0;
+        // L2 prefetch of the next visit's tile: the own rows of z and p (the halo rows are other threads' own rows)
+        auto prefetch = [&](const TileBits& nx) {
+            const int o = nx.origin(pitch) + toff;
+            const unsigned any = nx.any();
 #pragma unroll
-    for (int j = 0; j < 6; ++j) {
-        double zl = zv[j].x, zr = zv[j].y;
-        if (JACOBI) {
-            int dr = diag_row<FIXED>(lv, s.gr - 1 + j);
-            zl *= inv_of(dr + dcL);
-            zr *= inv_of(dr + dcR);
-        }
-        pn[j].x = zl + beta * pv[j].x;  // ConjugateGradient.h:80
-        pn[j].y = zr + beta * pv[j].y;
-    }
-    double pedge[ST_RG];
+            for (int j = 1; j <= ST_RG; ++j) {
+                prefetch_l2_if(zband + (o + j * pitch), (any >> j) & 1);
+                prefetch_l2_if(pband + (o + j * pitch), (any >> j) & 1);
+            }
+        };
+        for_each_tile(lv, cx, row0, [&](const TileBits& tb, const TileBits& nx, bool has_next, auto& pf) {
+            const int origin = tb.origin(pitch);
+            const ZT* zb = zband + origin;
+            const double* pb = pband + origin;
+            const unsigned any = tb.any();
+            // ---- all loads: pairs of rows row0-1 .. row0+4, and (edge lanes) the halo column of the own rows
+            double2 zv[6], pv[6];
+            double ze[ST_RG], pe[ST_RG];
 #pragma unroll
-    for (int j = 0; j < ST_RG; ++j) {
-        double z = ze[j];
-        if (JACOBI) {
-            int64_t c = west ? s.gc - 1 : s.gc + 2;
-            z *= inv_of(diag_row<FIXED>(lv, s.gr + j) + (FIXED ? 2 : (c > 0) + (c < lv.cols - 1)));
-        }
-        pedge[j] = z + beta * pe[j];
-    }
-    // ---- store the own rows, accumulate p'.Ap'
-    double* po = p_new + origin;
-    double acc = 0.0;
+            for (int j = 0; j < 6; ++j) {
+                zv[j] = ldnc2_if(zb + (toff + j * pitch), (any >> j) & 1);
+                pv[j] = ldnc2_if(pb + (toff + j * pitch), (any >> j) & 1);
+            }
+            {
+                // the halo cell can only matter if the own edge cell is an unknown
+                const int eoff = toff + (west ? -1 : 2);
+                const unsigned em = (west ? tb.mL() : (east ? tb.mR() : 0u)) >> 1;
 #pragma unroll
-    for (int j = 1; j <= ST_RG; ++j) {
-        if ((any >> j) & 1)
-            *reinterpret_cast<double2*>(po + (s.toff + j * s.pitch)) = pn[j];
-        double wl = __shfl_up_sync(0xffffffffu, pn[j].y, 1);    // lane - 1's right cell
-        double er = __shfl_down_sync(0xffffffffu, pn[j].x, 1);  // lane + 1's left cell
-        if (west)
-            wl = pedge[j - 1];
-        if (east)
-            er = pedge[j - 1];
-        int dr = diag_row<FIXED>(lv, s.gr - 1 + j);
-        double ql = (double)(dr + dcL) * pn[j].x - ((pn[j - 1].x + pn[j + 1].x) + (wl + pn[j].y));
-        double qr = (double)(dr + dcR) * pn[j].y - ((pn[j - 1].y + pn[j + 1].y) + (pn[j].x + er));
-        acc += pn[j].x * ql + pn[j].y * qr;  // p' is zero outside the unknown set: no mask needed
+                for (int j = 0; j < ST_RG; ++j) {
+                    ze[j] = ldnc_if(zb + (eoff + (j + 1) * pitch), (em >> j) & 1);
+                    pe[j] = ldnc_if(pb + (eoff + (j + 1) * pitch), (em >> j) & 1);
+                }
+            }
+            if (SATFILL_L2_PREFETCH && has_next)
+                pf(nx);
+            const int64_t gr = (int64_t)tb.ty() * TILE_H + row0, gc = (int64_t)tb.tx() * TILE_W + 2 * cx;
+            const int dcL = diag_col<FIXED>(lv, gc), dcR = diag_col<FIXED>(lv, gc + 1);
+            // ---- p' = z + beta p on the 6 x 2 cells and the edge column
+            double2 pn[6];
+#pragma unroll
+            for (int j = 0; j < 6; ++j) {
+                double zl = zv[j].x, zr = zv[j].y;
+                if (JACOBI) {
+                    int dr = diag_row<FIXED>(lv, gr - 1 + j);
+                    zl *= inv_of(dr + dcL);
+                    zr *= inv_of(dr + dcR);
+                }
+                pn[j].x = zl + beta * pv[j].x;  // ConjugateGradient.h:80
+                pn[j].y = zr + beta * pv[j].y;
+            }
+            double pedge[ST_RG];
+#pragma unroll
+            for (int j = 0; j < ST_RG; ++j) {
+                double z = ze[j];
+                if (JACOBI)
+                    z *= inv_of(diag_row<FIXED>(lv, gr + j) + diag_col<FIXED>(lv, west ? gc - 1 : gc + 2));
+                pedge[j] = z + beta * pe[j];
+            }
+            // ---- store the own rows, accumulate p'.Ap'
+            // Stores cover whole 32-byte sectors (this pair and the other pair of the sector, a neighbouring lane): a
+            // partially written sector costs HBM a read-modify-write.  The extra cells are not unknowns: they get the
+            // zero the invariant demands.
+            double* po = poband + origin;
+            const unsigned st = sector_or2(any);
+#pragma unroll
+            for (int j = 1; j <= ST_RG; ++j) {
+                if ((st >> j) & 1)
+                    *reinterpret_cast<double2*>(po + (toff + j * pitch)) = pn[j];
+                double wl = __shfl_up_sync(0xffffffffu, pn[j].y, 1);    // lane - 1's right cell
+                double er = __shfl_down_sync(0xffffffffu, pn[j].x, 1);  // lane + 1's left cell
+                if (west)
+                    wl = pedge[j - 1];
+                if (east)
+                    er = pedge[j - 1];
+                int dr = diag_row<FIXED>(lv, gr - 1 + j);
+                double ql = (double)(dr + dcL) * pn[j].x - ((pn[j - 1].x + pn[j + 1].x) + (wl + pn[j].y));
+                double qr = (double)(dr + dcR) * pn[j].y - ((pn[j - 1].y + pn[j + 1].y) + (pn[j].x + er));
+                acc += pn[j].x * ql + pn[j].y * qr;  // p' is zero outside the unknown set: no mask needed
+            }
+        }, prefetch);
+        double tot = block_sum4(acc, s_red);
+        if (threadIdx.x == 0 && tot != 0.0)
+            atomicAdd(&sc.pq[slot], tot);
     }
-    double tot = block_sum4(acc, s_red);
-    if (threadIdx.x == 0 && tot != 0.0)
-        atomicAdd(&sc.pq[slot], tot);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -235,104 +321,137 @@ __global__ void __launch_bounds__(ST_THREADS) k_direction2(Level lv, const ZT* _
 //   RF: also write the residual as float for the red-black cycle.
 // ---------------------------------------------------------------------------------------------------------------
 template <bool JACOBI, bool FIXED, bool RF>
-__global__ void __launch_bounds__(ST_THREADS) k_update2(Level lv, double* __restrict__ u, const double* __restrict__ p,
-    double* __restrict__ rvec, float* __restrict__ rf, BandScalars* __restrict__ scal, int k)
+__global__ void __launch_bounds__(ST_THREADS, ST_UPD_CTAS) k_update2(Level lv, int nbands, double* __restrict__ u,
+    const double* __restrict__ p, double* __restrict__ rvec, float* __restrict__ rf, BandScalars* __restrict__ scal, int k)
 {
     __shared__ double s_red[4];
-    BandScalars& sc = scal[blockIdx.y];
-    if (sc.done)
-        return;
     const int slot = k & 3, next = (k + 1) & 3;
-    const double alpha = sc.rz[slot] / sc.pq[slot];  // ConjugateGradient.h:68
-    int ty, tx;
-    const Strip s = make_strip(lv, blockIdx.x, ty, tx);
-    const int64_t origin = (int64_t)blockIdx.y * lv.plane + (int64_t)ty * TILE_H * lv.pitch + (int64_t)tx * TILE_W;
-    const double* pb = p + origin;
-    double* ub = u + origin;
-    double* rb = rvec + origin;
-    const unsigned any = s.mL | s.mR;
-    const bool west = s.cx == 0, east = s.cx == 15;
-    double2 pv[6], xv[ST_RG], rv[ST_RG];
-    double pe[ST_RG];
+    const int cx = threadIdx.x & 15, row0 = (threadIdx.x >> 4) * ST_RG;
+    const int pitch = (int)lv.pitch;
+    const int toff = (row0 - 1) * pitch + 2 * cx;
+    const bool west = cx == 0, east = cx == 15;
+    for (int band = 0; band < nbands; ++band) {
+        BandScalars& sc = scal[band];
+        if (sc.done)
+            continue;
+        const double alpha = sc.rz[slot] / sc.pq[slot];  // ConjugateGradient.h:68
+        const int64_t band_off = (int64_t)band * lv.plane;
+        double r2 = 0.0, rz = 0.0;
+        const double* pband = p + band_off;
+        double* uband = u + band_off;
+        double* rband = rvec + band_off;
+        float* rfband = RF ? rf + band_off : nullptr;
+        auto prefetch = [&](const TileBits& nx) {
+            const int o = nx.origin(pitch) + toff;
+            const unsigned any = nx.any();
 #pragma unroll
-    for (int j = 0; j < 6; ++j)
-        pv[j] = ldnc2_if(pb + (s.toff + j * s.pitch), (any >> j) & 1);
+            for (int j = 1; j <= ST_RG; ++j) {
+                prefetch_l2_if(pband + (o + j * pitch), (any >> j) & 1);
+                prefetch_l2_if(uband + (o + j * pitch), (any >> j) & 1);
+                prefetch_l2_if(rband + (o + j * pitch), (any >> j) & 1);
+            }
+        };
+        for_each_tile(lv, cx, row0, [&](const TileBits& tb, const TileBits& nx, bool has_next, auto& pf) {
+            const int origin = tb.origin(pitch);
+            const double* pb = pband + origin;
+            double* ub = uband + origin;
+            double* rb = rband + origin;
+            const unsigned any = tb.any();
+            const unsigned mL = tb.mL(), mR = tb.mR();
+            // whole 32-byte sectors are written (see k_direction2): x of a cell that is not an unknown is written back as
+            // read, so x is loaded wherever its sector is stored (the sector travels anyway)
+            const unsigned st2 = sector_or2(any), st4 = RF ? sector_or4(st2) : 0u;
+            double2 pv[6], xv[ST_RG], rv[ST_RG];
+            double pe[ST_RG];
 #pragma unroll
-    for (int j = 0; j < ST_RG; ++j) {
-        xv[j] = ld2_if(ub + (s.toff + (j + 1) * s.pitch), (any >> (j + 1)) & 1);
-        rv[j] = ld2_if(rb + (s.toff + (j + 1) * s.pitch), (any >> (j + 1)) & 1);
-    }
-    {
-        const int eoff = s.toff + (west ? -1 : 2);
-        const unsigned em = (west ? s.mL : (east ? s.mR : 0u)) >> 1;
+            for (int j = 0; j < 6; ++j)
+                pv[j] = ldnc2_if(pb + (toff + j * pitch), (any >> j) & 1);
 #pragma unroll
-        for (int j = 0; j < ST_RG; ++j)
-            pe[j] = ldnc_if(pb + (eoff + (j + 1) * s.pitch), (em >> j) & 1);
-    }
-    int dcL, dcR;
-    diag_cols<FIXED>(lv, s, dcL, dcR);
-    double r2 = 0.0, rz = 0.0;
+            for (int j = 0; j < ST_RG; ++j) {
+                xv[j] = ld2_if(ub + (toff + (j + 1) * pitch), (st2 >> (j + 1)) & 1);
+                rv[j] = ld2_if(rb + (toff + (j + 1) * pitch), (any >> (j + 1)) & 1);
+            }
+            {
+                const int eoff = toff + (west ? -1 : 2);
+                const unsigned em = (west ? mL : (east ? mR : 0u)) >> 1;
 #pragma unroll
-    for (int j = 1; j <= ST_RG; ++j) {
-        double wl = __shfl_up_sync(0xffffffffu, pv[j].y, 1);
-        double er = __shfl_down_sync(0xffffffffu, pv[j].x, 1);
-        if (west)
-            wl = pe[j - 1];
-        if (east)
-            er = pe[j - 1];
-        int dr = diag_row<FIXED>(lv, s.gr - 1 + j);
-        double ql = (double)(dr + dcL) * pv[j].x - ((pv[j - 1].x + pv[j + 1].x) + (wl + pv[j].y));
-        double qr = (double)(dr + dcR) * pv[j].y - ((pv[j - 1].y + pv[j + 1].y) + (pv[j].x + er));
-        // a cell of the pair that is not an unknown keeps its value: p is zero there, and its r stays zero
-        double2 xn, rn;
-        xn.x = ((s.mL >> j) & 1) ? xv[j - 1].x + alpha * pv[j].x : xv[j - 1].x;                   // ConjugateGradient.h:69
-        xn.y = ((s.mR >> j) & 1) ? xv[j - 1].y + alpha * pv[j].y : xv[j - 1].y;
-        rn.x = ((s.mL >> j) & 1) ? rv[j - 1].x - alpha * ql : 0.0;                                // ConjugateGradient.h:70
-        rn.y = ((s.mR >> j) & 1) ? rv[j - 1].y - alpha * qr : 0.0;
-        if ((any >> j) & 1) {
-            const int off = s.toff + j * s.pitch;
-            *reinterpret_cast<double2*>(ub + off) = xn;
-            *reinterpret_cast<double2*>(rb + off) = rn;
-            if (RF)
-                *reinterpret_cast<float2*>(rf + origin + off) = make_float2((float)rn.x, (float)rn.y);
-        }
-        r2 += rn.x * rn.x + rn.y * rn.y;
-        if (JACOBI)
-            rz += rn.x * rn.x * inv_of(dr + dcL) + rn.y * rn.y * inv_of(dr + dcR);
-    }
-    double tot = block_sum4(r2, s_red);
-    if (threadIdx.x == 0 && tot != 0.0)
-        atomicAdd(&sc.rr[next], tot);
-    if (JACOBI) {
-        __syncthreads();
-        tot = block_sum4(rz, s_red);
+                for (int j = 0; j < ST_RG; ++j)
+                    pe[j] = ldnc_if(pb + (eoff + (j + 1) * pitch), (em >> j) & 1);
+            }
+            if (SATFILL_L2_PREFETCH && has_next)
+                pf(nx);
+            const int64_t gr = (int64_t)tb.ty() * TILE_H + row0, gc = (int64_t)tb.tx() * TILE_W + 2 * cx;
+            const int dcL = diag_col<FIXED>(lv, gc), dcR = diag_col<FIXED>(lv, gc + 1);
+#pragma unroll
+            for (int j = 1; j <= ST_RG; ++j) {
+                double wl = __shfl_up_sync(0xffffffffu, pv[j].y, 1);
+                double er = __shfl_down_sync(0xffffffffu, pv[j].x, 1);
+                if (west)
+                    wl = pe[j - 1];
+                if (east)
+                    er = pe[j - 1];
+                int dr = diag_row<FIXED>(lv, gr - 1 + j);
+                double ql = (double)(dr + dcL) * pv[j].x - ((pv[j - 1].x + pv[j + 1].x) + (wl + pv[j].y));
+                double qr = (double)(dr + dcR) * pv[j].y - ((pv[j - 1].y + pv[j + 1].y) + (pv[j].x + er));
+                // a cell of the pair that is not an unknown keeps its value: p is zero there, and its r stays zero
+                double2 xn, rn;
+                xn.x = ((mL >> j) & 1) ? xv[j - 1].x + alpha * pv[j].x : xv[j - 1].x;                   // ConjugateGradient.h:69
+                xn.y = ((mR >> j) & 1) ? xv[j - 1].y + alpha * pv[j].y : xv[j - 1].y;
+                rn.x = ((mL >> j) & 1) ? rv[j - 1].x - alpha * ql : 0.0;                                // ConjugateGradient.h:70
+                rn.y = ((mR >> j) & 1) ? rv[j - 1].y - alpha * qr : 0.0;
+                const int off = toff + j * pitch;
+                if ((st2 >> j) & 1) {
+                    *reinterpret_cast<double2*>(ub + off) = xn;
+                    *reinterpret_cast<double2*>(rb + off) = rn;
+                }
+                if (RF && ((st4 >> j) & 1))
+                    *reinterpret_cast<float2*>(rfband + origin + off) = make_float2((float)rn.x, (float)rn.y);
+                r2 += rn.x * rn.x + rn.y * rn.y;
+                if (JACOBI)
+                    rz += rn.x * rn.x * inv_of(dr + dcL) + rn.y * rn.y * inv_of(dr + dcR);
+            }
+        }, prefetch);
+        double tot = block_sum4(r2, s_red);
         if (threadIdx.x == 0 && tot != 0.0)
-            atomicAdd(&sc.rz[next], tot);
+            atomicAdd(&sc.rr[next], tot);
+        if (JACOBI) {
+            tot = block_sum4(rz, s_red);
+            if (threadIdx.x == 0 && tot != 0.0)
+                atomicAdd(&sc.rz[next], tot);
+        }
     }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Grid: as many CTAs as are resident at once (the occupancy the kernel was compiled for x the SM count), never more than
+// there are tiles, so that every CTA owns a tile of every band.
+static unsigned strip_grid(const sa_ctx* ctx, const Level& lv, int ctas_per_sm)
+{
+    int g = ctx->sm_count * ctas_per_sm;
+    return (unsigned)(g < lv.n_tiles ? g : lv.n_tiles);
+}
+
 int launch_direction2(sa_ctx* ctx, const Level& lv, int nbands, bool jacobi, const void* zin, bool z_is_float,
     const double* p_old, double* p_new, BandScalars* scal, int k)
 {
     if (lv.n_tiles == 0)
         return SA_OK;
-    dim3 grid((unsigned)lv.n_tiles, (unsigned)nbands);
+    const unsigned grid = strip_grid(ctx, lv, z_is_float ? dir_ctas<float>() : dir_ctas<double>());
     if (jacobi) {
         if (lv.fixed_diag)
-            SA_LAUNCH(ctx, (k_direction2<true, true, double>), grid, ST_THREADS, 0, lv, (const double*)zin, p_old, p_new, scal, k);
+            SA_LAUNCH(ctx, (k_direction2<true, true, double>), grid, ST_THREADS, 0, lv, nbands, (const double*)zin, p_old, p_new, scal, k);
         else
-            SA_LAUNCH(ctx, (k_direction2<true, false, double>), grid, ST_THREADS, 0, lv, (const double*)zin, p_old, p_new, scal, k);
+            SA_LAUNCH(ctx, (k_direction2<true, false, double>), grid, ST_THREADS, 0, lv, nbands, (const double*)zin, p_old, p_new, scal, k);
     } else if (z_is_float) {
         if (lv.fixed_diag)
-            SA_LAUNCH(ctx, (k_direction2<false, true, float>), grid, ST_THREADS, 0, lv, (const float*)zin, p_old, p_new, scal, k);
+            SA_LAUNCH(ctx, (k_direction2<false, true, float>), grid, ST_THREADS, 0, lv, nbands, (const float*)zin, p_old, p_new, scal, k);
         else
-            SA_LAUNCH(ctx, (k_direction2<false, false, float>), grid, ST_THREADS, 0, lv, (const float*)zin, p_old, p_new, scal, k);
+            SA_LAUNCH(ctx, (k_direction2<false, false, float>), grid, ST_THREADS, 0, lv, nbands, (const float*)zin, p_old, p_new, scal, k);
     } else {
         if (lv.fixed_diag)
-            SA_LAUNCH(ctx, (k_direction2<false, true, double>), grid, ST_THREADS, 0, lv, (const double*)zin, p_old, p_new, scal, k);
+            SA_LAUNCH(ctx, (k_direction2<false, true, double>), grid, ST_THREADS, 0, lv, nbands, (const double*)zin, p_old, p_new, scal, k);
         else
-            SA_LAUNCH(ctx, (k_direction2<false, false, double>), grid, ST_THREADS, 0, lv, (const double*)zin, p_old, p_new, scal, k);
+            SA_LAUNCH(ctx, (k_direction2<false, false, double>), grid, ST_THREADS, 0, lv, nbands, (const double*)zin, p_old, p_new, scal, k);
     }
     return SA_OK;
 }
@@ -342,22 +461,22 @@ int launch_update2(sa_ctx* ctx, const Level& lv, int nbands, bool jacobi, double
 {
     if (lv.n_tiles == 0)
         return SA_OK;
-    dim3 grid((unsigned)lv.n_tiles, (unsigned)nbands);
+    const unsigned grid = strip_grid(ctx, lv, ST_UPD_CTAS);
     if (jacobi) {
         if (lv.fixed_diag)
-            SA_LAUNCH(ctx, (k_update2<true, true, false>), grid, ST_THREADS, 0, lv, u, p, r, rf, scal, k);
+            SA_LAUNCH(ctx, (k_update2<true, true, false>), grid, ST_THREADS, 0, lv, nbands, u, p, r, rf, scal, k);
         else
-            SA_LAUNCH(ctx, (k_update2<true, false, false>), grid, ST_THREADS, 0, lv, u, p, r, rf, scal, k);
+            SA_LAUNCH(ctx, (k_update2<true, false, false>), grid, ST_THREADS, 0, lv, nbands, u, p, r, rf, scal, k);
     } else if (lv.fixed_diag) {
         if (rf)
-            SA_LAUNCH(ctx, (k_update2<false, true, true>), grid, ST_THREADS, 0, lv, u, p, r, rf, scal, k);
+            SA_LAUNCH(ctx, (k_update2<false, true, true>), grid, ST_THREADS, 0, lv, nbands, u, p, r, rf, scal, k);
         else
-            SA_LAUNCH(ctx, (k_update2<false, true, false>), grid, ST_THREADS, 0, lv, u, p, r, rf, scal, k);
+            SA_LAUNCH(ctx, (k_update2<false, true, false>), grid, ST_THREADS, 0, lv, nbands, u, p, r, rf, scal, k);
     } else {
         if (rf)
-            SA_LAUNCH(ctx, (k_update2<false, false, true>), grid, ST_THREADS, 0, lv, u, p, r, rf, scal, k);
+            SA_LAUNCH(ctx, (k_update2<false, false, true>), grid, ST_THREADS, 0, lv, nbands, u, p, r, rf, scal, k);
         else
-            SA_LAUNCH(ctx, (k_update2<false, false, false>), grid, ST_THREADS, 0, lv, u, p, r, rf, scal, k);
+            SA_LAUNCH(ctx, (k_update2<false, false, false>), grid, ST_THREADS, 0, lv, nbands, u, p, r, rf, scal, k);
     }
     return SA_OK;
 }

@@ -79,6 +79,9 @@ struct sa_ctx {
     void* comm = nullptr;
     int rank = 0, world = 1;
     double* d_red = nullptr;  // packed per-band scalars for the all-reduce
+    // host-pointer entry points: PCIe transfers of the other band chunks run on these while a chunk is solved
+    cudaStream_t io_in = nullptr, io_out = nullptr;
+    std::vector<cudaEvent_t> io_ev;
     int device = 0;
     cudaStream_t stream = nullptr;
     bool owns_stream = false;
@@ -153,11 +156,17 @@ struct sa_scene {
     std::vector<sa_level_store> coarse;  // multigrid hierarchy below level 0
     bool hierarchy_built = false;
 
+    // Band window of the next sa_scene_solve-like call: the host-pointer entry points (api.cu) solve a scene in chunks of
+    // bands so that PCIe transfers of the other chunks overlap the solve.  band_n < 0: all bands.
+    int band0 = 0, band_n = -1;
+    int win_n() const { return band_n < 0 ? nbands : band_n; }
+
     double* plane0(double* base, int band) const { return base + (int64_t)band * plane + pitch; }
     // float planes of the red-black cycle (mg_rb.cu) inside the z allocation: z itself, then the float copy of the
     // CG residual that k_update / k_residual write for it
-    float* rb_z() const { return (float*)z + pitch; }
-    float* rb_rf() const { return (float*)z + (int64_t)plane * nbands + pitch; }
+    // (both start at the first band of the window)
+    float* rb_z() const { return (float*)z + pitch + (int64_t)band0 * plane; }
+    float* rb_rf() const { return (float*)z + (int64_t)plane * nbands + pitch + (int64_t)band0 * plane; }
     uint8_t* mask0(uint8_t* base) const { return base + pitch; }
 };
 

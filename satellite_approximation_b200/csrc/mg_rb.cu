@@ -482,18 +482,18 @@ int launch_coarsest(sa_ctx* ctx, const RBLevel& L, int nb, BandScalars* scal, in
 int apply_vcycle_rb(sa_scene* s, const sa_options& o, KernelTimer& kt, int rz_slot, int live_bands)
 {
     sa_ctx* ctx = s->ctx;
-    const int nb = s->nbands;
+    const int nb = s->win_n(), b0 = s->band0;  // the band window (common.cuh): every base pointer starts at band b0
     std::vector<RBLevel> L;
     L.push_back({ fine_level(s), s->n_unknowns * live_bands, s->rb_rf(), s->rb_z(),
-        (float*)s->t + (s->pitch >> 1) });
+        (float*)s->t + (s->pitch >> 1) + (int64_t)b0 * (s->plane >> 1) });
     for (sa_level_store& c : s->coarse) {
         if (c.lv.n_tiles == 0)
             break;
-        L.push_back({ c.lv, c.n_unknowns * live_bands, (float*)c.b + c.lv.pitch, (float*)c.x + c.lv.pitch,
-            (float*)c.t + (c.lv.pitch >> 1) });
+        L.push_back({ c.lv, c.n_unknowns * live_bands, (float*)c.b + c.lv.pitch + (int64_t)b0 * c.lv.plane,
+            (float*)c.x + c.lv.pitch + (int64_t)b0 * c.lv.plane, (float*)c.t + (c.lv.pitch >> 1) + (int64_t)b0 * (c.lv.plane >> 1) });
     }
     const int nl = (int)L.size();
-    BandScalars* scal = s->scal;
+    BandScalars* scal = s->scal + b0;
     const int coarse_sweeps = 16;
     // row decomposition (dist.cu): levels below dist_levels run on the rank's slice and exchange halo rows, the others
     // are replicated on every rank

@@ -238,6 +238,46 @@ def test_multiband_matches_single_band(ctx):
         assert rel_max_abs(multi[b], single[0], mask) < 1e-9
 
 
+@pytest.mark.parametrize("precond", ["multigrid", "jacobi"])
+@pytest.mark.parametrize("chunk_bytes", [1, 400000])
+def test_host_fill_in_band_chunks_matches_one_chunk(ctx, monkeypatch, precond, chunk_bytes):
+    """sa_laplace_fill / sa_poisson_blend move and solve large scenes in chunks of bands (PCIe transfers of the other
+    chunks overlap the solve); SATFILL_CHUNK_BYTES forces that path on a small scene: 1 byte = one band per chunk,
+    400000 bytes = two bands per chunk with a ragged last chunk."""
+    rows, cols = 150, 170
+    mask = synth.blob_mask(rows, cols, cover=0.35, sigma=5.0, seed=21, clear_border=False)
+    lmask = mask.copy()
+    lmask[0, :] = lmask[-1, :] = False
+    lmask[:, 0] = lmask[:, -1] = False
+    bands = [synth.smooth_band(rows, cols, seed=30 + b) for b in range(5)]
+    guides = [synth.second_date(b, seed=3 + i) for i, b in enumerate(bands)]
+    pc = sab.MULTIGRID if precond == "multigrid" else sab.JACOBI
+    monkeypatch.setenv("SATFILL_NO_PIPELINE", "1")
+    one = [b.copy() for b in bands]
+    st_one = ctx.laplace_fill(one, lmask, tolerance=1e-11, precond=pc)
+    pone = [b.copy() for b in bands]
+    ctx.poisson_blend(pone, guides, mask, tolerance=1e-11, max_iterations=10**6, precond=pc)
+    monkeypatch.delenv("SATFILL_NO_PIPELINE")
+    monkeypatch.setenv("SATFILL_CHUNK_BYTES", str(chunk_bytes))
+    many = [b.copy() for b in bands]
+    st_many = ctx.laplace_fill(many, lmask, tolerance=1e-11, precond=pc)
+    pmany = [b.copy() for b in bands]
+    pst = ctx.poisson_blend(pmany, guides, mask, tolerance=1e-11, max_iterations=10**6, precond=pc)
+    assert all(s["status"] == sab.SA_OK for s in st_many + pst)
+    for b in range(5):
+        # the same kernels on the same data, up to the order of the atomic partial sums of the dot products
+        assert rel_max_abs(many[b], one[b], lmask) < 1e-8
+        assert rel_max_abs(pmany[b], pone[b], mask) < 1e-8
+        assert abs(st_many[b]["iterations"] - st_one[b]["iterations"]) <= 1
+        assert np.array_equal(many[b][~lmask], bands[b][~lmask])
+    # Poisson: one band that cannot converge -> nothing is written back, in any chunk (poisson.cpp:263-269)
+    pfail = [b.copy() for b in bands]
+    st = ctx.poisson_blend(pfail, guides, mask, tolerance=1e-13, max_iterations=2, precond=sab.JACOBI)
+    assert any(s["status"] == sab.SA_NOT_CONVERGED for s in st)
+    for b in range(5):
+        assert np.array_equal(pfail[b], bands[b])
+
+
 def test_resident_scene_device_buffers(ctx, port):
     """sa_scene_* with device-resident inputs (what bench.py times as `value`)."""
     import torch
