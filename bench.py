@@ -312,14 +312,9 @@ def run_b200(args, w):
     unknowns = st[0]["unknowns"]
     ok = all(s["status"] == sab.SA_OK for s in st)
     worst_err = max(s["error"] for s in st)
-    t = torch.tensor([ms], device=dev, dtype=torch.float64)
-    tot = torch.tensor([float(unknowns * nb)], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        if not one_system:  # independent scenes add up; one shared system is counted once
-            dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-    ms_max = float(t.item())
-    total_units = float(tot.item())
+    from satellite_approximation_b200 import multi
+
+    ms_max, total_units = multi.reduce_step(ms, float(unknowns * nb), one_system, dev)
     value = total_units * args.steps / (ms_max * 1e-3)
 
     # ---- roofline of the dominant kernel (by accumulated event time inside the timed region)
@@ -342,13 +337,27 @@ def run_b200(args, w):
         bytes_per_unknown = [25.0, 41.0, 25.0, 19.0, 18.0, 26.0, 18.0, 26.0]
     dom = max(range(NK), key=lambda c: kms[c])
     peak, peak_src = peaks()
+    # DRAM traffic of the dominant kernel: bytes per unknown-band measured by one `ncu --set full` capture of the same
+    # kernel on this workload (profiles/traffic.json, written by profiles/summarize.py traffic), scaled to this launch
+    traffic, traffic_src = None, None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        ent = tj.get(["k_direction2", "k_update2", None, None, "k_rb_down", "k_rb_up", None, None][dom] or "")
+        if ent and args.workload == tj.get("workload", "c3") and not args.mask:
+            traffic_src = ent
+    except Exception:
+        pass
     roof = None
     if kn[dom] > 0 and kms[dom] > 0:
         # per launch: algorithmic bytes = bytes/unknown x (unknown-bands the launches of this class processed / launches)
         units = ku[dom] / kn[dom]
         achieved = bytes_per_unknown[dom] * units / (kms[dom] / kn[dom] * 1e-3) / 1e9
         roof = {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak,
+                "traffic": traffic_src["dram_bytes_per_unit"] * units if traffic_src else None,
+                "traffic_source": (f"ncu dram__bytes_read+write of {traffic_src['kernel']}: {traffic_src['dram_bytes_per_unit']:.2f} B "
+                                   f"per unknown-band ({traffic_src['capture']}), scaled to this launch's units") if traffic_src else None,
+                "peak_source": peak_src,
                 "avg_launch_ms": kms[dom] / kn[dom], "launches": kn[dom],
                 "share_of_step": kms[dom] / ms if ms > 0 else None,
                 "algorithmic_bytes_per_launch": bytes_per_unknown[dom] * units,
@@ -377,6 +386,7 @@ def run_b200(args, w):
             "dtype": "f64" + (" (CG iterate, residual, operator and dot products; float inside the multigrid preconditioner)" if rb else ""),
             "data": "synthetic",
             "config": {"workload": w["desc"], "problem": w["problem"], "rows": rows, "cols": cols, "bands": nb,
+                       "setup_ms": st[0]["setup_ms"], "solve_ms": st[0]["solve_ms"],
                        "unknowns_per_band": unknowns, "tolerance": args.tol, "precond": args.precond,
                        "mg_variant": args.mg_variant if args.precond == "multigrid" else None,
                        "cg_iterations": iters, "cg_iterations_per_band": [s["iterations"] for s in st], "converged": ok, "worst_rel_residual": worst_err,

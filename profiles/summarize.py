@@ -70,5 +70,25 @@ def raw(path):
             print(f"  {'traffic = dram read + write':70s} {tot / 1e9:14.4f} GB  -> {tot / t / 1e9:.0f} GB/s under ncu")
 
 
+def traffic(path, units):
+    """dram bytes per unit of work (unknown x band) of the captured launch, as JSON: bench.py scales it to its own launches.
+        python profiles/summarize.py traffic rep.ncu-rep <unknown-bands the captured launch processed>"""
+    import json
+
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    hdr, units_row, r = rows[0], rows[1], rows[2]
+    scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    tot = 0.0
+    for w in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+        i = hdr.index(w)
+        tot += float(r[i].replace(",", "")) * scale[units_row[i]]
+    print(json.dumps({"kernel": re.sub(r"\(.*", "", r[hdr.index("Kernel Name")]).replace("void ", ""),
+                      "dram_bytes": tot, "units": float(units), "dram_bytes_per_unit": tot / float(units), "capture": path}))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "raw": raw}[sys.argv[1]](sys.argv[2])
+    if sys.argv[1] == "traffic":
+        traffic(sys.argv[2], sys.argv[3])
+    else:
+        {"launches": launches, "raw": raw}[sys.argv[1]](sys.argv[2])

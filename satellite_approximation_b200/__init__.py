@@ -162,14 +162,14 @@ class Context:
         import torch
         import torch.distributed as dist
 
+        from . import multi
+
         rank, world = dist.get_rank(), dist.get_world_size()
         buf = (C.c_uint8 * 128)()
         if rank == 0:
             self._check(self._lib.sa_dist_unique_id(buf))
         dev = torch.device("cuda", self.device) if dist.get_backend() == "nccl" else torch.device("cpu")
-        t = torch.tensor(list(bytes(buf)), dtype=torch.uint8, device=dev)
-        dist.broadcast(t, 0)
-        self.dist_init(bytes(t.cpu().tolist()), rank, world)
+        self.dist_init(multi.broadcast_bytes(bytes(buf) if rank == 0 else None, 128, 0, dev), rank, world)
 
     def dist_init(self, id128: bytes, rank: int, world: int) -> None:
         buf = (C.c_uint8 * 128).from_buffer_copy(id128)

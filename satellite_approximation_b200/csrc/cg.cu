@@ -328,21 +328,83 @@ Level fine_level(const sa_scene* s)
     return lv;
 }
 
+// Zero the work vectors at the unknowns of the mask they were last used with (the tile lists and bit masks of that mask
+// are still in place: sa_scene_set_mask only replaces the mask itself).
+static int scrub_work_vectors(sa_scene* s)
+{
+    sa_ctx* ctx = s->ctx;
+    const int nb = s->nbands;
+    ScrubPlanes P {};
+    P.d[P.nd++] = s->plane0(s->r, 0);
+    P.d[P.nd++] = s->plane0(s->p[0], 0);
+    P.d[P.nd++] = s->plane0(s->p[1], 0);
+    if ((s->work_dirty & WORK_J64) && s->z) {
+        P.d[P.nd++] = s->plane0(s->z, 0);
+        P.d[P.nd++] = s->plane0(s->t, 0);
+    }
+    if ((s->work_dirty & WORK_RB) && s->z) {
+        P.f[P.nf++] = (float*)s->z + s->pitch;                                   // z of the red-black cycle
+        P.f[P.nf++] = (float*)s->z + (int64_t)s->plane * nb + s->pitch;           // float copy of the residual
+        P.h[P.nh++] = (float*)s->t + (s->pitch >> 1);                             // red half of the iterate
+    }
+    SA_TRY(launch_scrub(ctx, fine_level(s), nb, P));
+    if (s->hierarchy_built)
+        for (sa_level_store& c : s->coarse) {
+            if (c.lv.n_tiles == 0)
+                break;
+            ScrubPlanes Q {};
+            if (s->work_dirty & WORK_J64) {
+                Q.d[Q.nd++] = c.x + c.lv.pitch;
+                Q.d[Q.nd++] = c.b + c.lv.pitch;
+                Q.d[Q.nd++] = c.t + c.lv.pitch;
+            }
+            if (s->work_dirty & WORK_RB) {
+                Q.f[Q.nf++] = (float*)c.x + c.lv.pitch;
+                Q.f[Q.nf++] = (float*)c.b + c.lv.pitch;
+                Q.h[Q.nh++] = (float*)c.t + (c.lv.pitch >> 1);
+            }
+            SA_TRY(launch_scrub(ctx, c.lv, nb, Q));
+        }
+    SA_CUDA(ctx, cudaGetLastError());
+    return SA_OK;
+}
+
+// Clear everything the multigrid cycles write (variant switch, or contents unknown).
+static int clear_multigrid_vectors(sa_scene* s)
+{
+    sa_ctx* ctx = s->ctx;
+    size_t bytes = (size_t)s->plane * s->nbands * sizeof(double);
+    if (s->z)
+        SA_CUDA(ctx, cudaMemsetAsync(s->z, 0, bytes, ctx->stream));
+    if (s->t)
+        SA_CUDA(ctx, cudaMemsetAsync(s->t, 0, bytes, ctx->stream));
+    for (sa_level_store& c : s->coarse) {
+        size_t vec = (size_t)c.lv.plane * s->nbands * sizeof(double);
+        SA_CUDA(ctx, cudaMemsetAsync(c.x, 0, vec, ctx->stream));
+        SA_CUDA(ctx, cudaMemsetAsync(c.b, 0, vec, ctx->stream));
+        SA_CUDA(ctx, cudaMemsetAsync(c.t, 0, vec, ctx->stream));
+    }
+    return SA_OK;
+}
+
 int ensure_indexed(sa_scene* s)
 {
     sa_ctx* ctx = s->ctx;
     if (s->indexed)
         return SA_OK;
-    SA_TRY(index_scene(s));
     // work vectors must be zero outside the unknown set (and in tiles that are never visited)
-    size_t bytes = (size_t)s->plane * s->nbands * sizeof(double);
-    SA_CUDA(ctx, cudaMemsetAsync(s->r, 0, bytes, ctx->stream));
-    SA_CUDA(ctx, cudaMemsetAsync(s->p[0], 0, bytes, ctx->stream));
-    SA_CUDA(ctx, cudaMemsetAsync(s->p[1], 0, bytes, ctx->stream));
-    if (s->z)
-        SA_CUDA(ctx, cudaMemsetAsync(s->z, 0, bytes, ctx->stream));
-    if (s->t)
-        SA_CUDA(ctx, cudaMemsetAsync(s->t, 0, bytes, ctx->stream));
+    if ((s->work_dirty & WORK_FULL) || !s->ever_indexed) {
+        size_t bytes = (size_t)s->plane * s->nbands * sizeof(double);
+        SA_CUDA(ctx, cudaMemsetAsync(s->r, 0, bytes, ctx->stream));
+        SA_CUDA(ctx, cudaMemsetAsync(s->p[0], 0, bytes, ctx->stream));
+        SA_CUDA(ctx, cudaMemsetAsync(s->p[1], 0, bytes, ctx->stream));
+        SA_TRY(clear_multigrid_vectors(s));
+    } else if (s->work_dirty != WORK_CLEAN) {
+        SA_TRY(scrub_work_vectors(s));  // before index_scene replaces the old tile lists
+    }
+    s->work_dirty = WORK_CLEAN;
+    SA_TRY(index_scene(s));
+    s->ever_indexed = true;
     s->hierarchy_built = false;
     s->dist_planned = false;
     return SA_OK;
@@ -389,6 +451,7 @@ int precondition_scene(sa_scene* s, const sa_options& o)
 {
     sa_ctx* ctx = s->ctx;
     SA_TRY(ensure_multigrid(s, o));
+    s->work_dirty = WORK_FULL;  // the caller's vector goes through r and p: clear everything before the next solve
     const int64_t n = (int64_t)s->rows_p * s->pitch;  // the plane without its guard rows
     const uint8_t* um = s->mask0(s->umask);
     SA_LAUNCH(ctx, k_mask_plane, 1024, 256, 0, s->plane0(s->r, 0), um, n);
@@ -445,6 +508,16 @@ int solve_scene(sa_scene* s, const sa_options& o, sa_stats* stats)
     }
     if (mg)
         SA_TRY(ensure_multigrid(s, o));
+    {
+        // the two multigrid variants lay the same allocations out differently: clear them when the variant changes
+        const int kind = !mg ? WORK_JACOBI : (rb ? WORK_RB : WORK_J64);
+        const int other = kind == WORK_RB ? WORK_J64 : (kind == WORK_J64 ? WORK_RB : 0);
+        if (s->work_dirty & other) {
+            SA_TRY(clear_multigrid_vectors(s));
+            s->work_dirty &= ~other;
+        }
+        s->work_dirty |= kind;
+    }
     // one system split by rows across the ranks of the context's communicator (dist.cu)
     const bool dist = s->distributed && ctx->world > 1;
     if (dist && (b0 != 0 || nb != s->nbands))

@@ -423,6 +423,41 @@ __global__ void __launch_bounds__(ST_THREADS, ST_UPD_CTAS) k_update2(Level lv, i
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// k_scrub: zero work vectors at the unknowns of a level (whole sectors).  Run through the tile list of the PREVIOUS
+// mask when the mask changes: a solve leaves its work vectors non-zero only at its own unknowns, so this restores the
+// "zero outside the unknown set" invariant for any new mask at a third of the bytes of clearing the planes.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(ST_THREADS) k_scrub(Level lv, ScrubPlanes P)
+{
+    const int cx = threadIdx.x & 15, row0 = (threadIdx.x >> 4) * ST_RG;
+    const int pitch = (int)lv.pitch, pitch2 = pitch >> 1;
+    const TileBits tb = load_tile_bits(lv, lv.tile_yx[blockIdx.x], cx, row0);
+    const unsigned any = tb.any(), st2 = any | __shfl_xor_sync(0xffffffffu, any, 1), st4 = st2 | __shfl_xor_sync(0xffffffffu, st2, 2);
+    const int64_t o = (int64_t)blockIdx.y * lv.plane + tb.origin(pitch) + (row0 - 1) * pitch + 2 * cx;
+    const int64_t o2 = (int64_t)blockIdx.y * (lv.plane >> 1) + tb.ty() * (TILE_H * pitch2) + tb.tx() * (TILE_W / 2) + (row0 - 1) * pitch2 + cx;
+#pragma unroll
+    for (int j = 1; j <= ST_RG; ++j) {
+        if ((st2 >> j) & 1)
+            for (int q = 0; q < P.nd; ++q)
+                *reinterpret_cast<double2*>(P.d[q] + o + j * pitch) = make_double2(0.0, 0.0);
+        if ((st4 >> j) & 1)
+            for (int q = 0; q < P.nf; ++q)
+                *reinterpret_cast<float2*>(P.f[q] + o + j * pitch) = make_float2(0.f, 0.f);
+        if ((any >> j) & 1)
+            for (int q = 0; q < P.nh; ++q)
+                P.h[q][o2 + j * pitch2] = 0.f;
+    }
+}
+
+int launch_scrub(sa_ctx* ctx, const Level& lv, int nbands, const ScrubPlanes& planes)
+{
+    if (lv.n_tiles == 0 || planes.nd + planes.nf + planes.nh == 0)
+        return SA_OK;
+    SA_LAUNCH(ctx, k_scrub, dim3((unsigned)lv.n_tiles, (unsigned)nbands), ST_THREADS, 0, lv, planes);
+    return SA_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // Grid: as many CTAs as are resident at once (the occupancy the kernel was compiled for x the SM count), never more than
 // there are tiles, so that every CTA owns a tile of every band.
 static unsigned strip_grid(const sa_ctx* ctx, const Level& lv, int ctas_per_sm)

@@ -155,6 +155,11 @@ struct sa_scene {
     bool indexed = false;
     std::vector<sa_level_store> coarse;  // multigrid hierarchy below level 0
     bool hierarchy_built = false;
+    // What has written the work vectors (r, p, z, t, coarse x / b / t) since they were last zero everywhere: a set of
+    // WORK_* bits.  A solve leaves them non-zero only at the unknowns of ITS mask, so when the mask changes they are
+    // scrubbed through the OLD tile lists (scrub_work_vectors) instead of being cleared plane by plane.
+    int work_dirty = 8;        // WORK_FULL until the first clear
+    bool ever_indexed = false;  // the tile lists / bit masks of a previous mask are valid
 
     // Band window of the next sa_scene_solve-like call: the host-pointer entry points (api.cu) solve a scene in chunks of
     // bands so that PCIe transfers of the other chunks overlap the solve.  band_n < 0: all bands.
@@ -293,6 +298,17 @@ int launch_direction2(sa_ctx* ctx, const Level& lv, int nbands, bool jacobi, con
     const double* p_old, double* p_new, BandScalars* scal, int k);
 int launch_update2(sa_ctx* ctx, const Level& lv, int nbands, bool jacobi, double* u, const double* p, double* r, float* rf,
     BandScalars* scal, int k);
+
+// work_dirty bits
+enum { WORK_CLEAN = 0, WORK_JACOBI = 1, WORK_RB = 2, WORK_J64 = 4, WORK_FULL = 8 };
+// cg_strip.cu: zero the given planes at the unknowns of `lv` (whole sectors)
+struct ScrubPlanes {
+    double* d[5];  // double planes, element (0, 0) of band 0
+    float* f[2];   // float planes
+    float* h[1];   // colour-split float half planes (mg_rb.cu: red cells)
+    int nd, nf, nh;
+};
+int launch_scrub(sa_ctx* ctx, const Level& lv, int nbands, const ScrubPlanes& planes);
 
 // ---- dist.cu: row decomposition of one system across GPUs -------------------------------------------------------------
 enum DistWhat { DIST_SETUP = 0, DIST_RZ = 1, DIST_PQ = 2, DIST_RR = 3, DIST_RR_RZ = 4 };

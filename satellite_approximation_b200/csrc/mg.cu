@@ -150,6 +150,10 @@ static int alloc_hierarchy(sa_scene* s, const sa_options& o)
         SA_CUDA(ctx, cudaMalloc(&L.x, vec));
         SA_CUDA(ctx, cudaMalloc(&L.b, vec));
         SA_CUDA(ctx, cudaMalloc(&L.t, vec));
+        // cleared once; afterwards a mask change scrubs them through the old tile lists (cg.cu: scrub_work_vectors)
+        SA_CUDA(ctx, cudaMemsetAsync(L.x, 0, vec, ctx->stream));
+        SA_CUDA(ctx, cudaMemsetAsync(L.b, 0, vec, ctx->stream));
+        SA_CUDA(ctx, cudaMemsetAsync(L.t, 0, vec, ctx->stream));
         SA_CUDA(ctx, cudaMalloc(&L.winv, (size_t)L.lv.plane * sizeof(float)));
         SA_CUDA(ctx, cudaMemsetAsync(L.winv, 0, (size_t)L.lv.plane * sizeof(float), ctx->stream));
         size_t words = (size_t)(L.lv.tiles_x + 2) * (L.lv.tiles_y + 2) * 32;
@@ -187,10 +191,6 @@ int build_hierarchy(sa_scene* s, const sa_options& o)
         SA_LAUNCH(ctx, k_coarsen_mask, n_tiles, block, 0, fmask, fpitch, frows, fcols, L.lv.fixed_diag, cmask, L.lv.rows,
             L.lv.cols, L.lv.pitch, L.lv.tiles_x, flags, count64, L.tbits, L.tbits + L.tb_words, L.winv + L.lv.pitch);
         SA_TRY(compact_tile_flags(ctx, flags, n_tiles, L.lv.tiles_x, L.tile_list, L.tile_list + 2 * n_tiles, L.d_counters));
-        size_t vec = (size_t)L.lv.plane * s->nbands * sizeof(double);
-        SA_CUDA(ctx, cudaMemsetAsync(L.x, 0, vec, ctx->stream));
-        SA_CUDA(ctx, cudaMemsetAsync(L.b, 0, vec, ctx->stream));
-        SA_CUDA(ctx, cudaMemsetAsync(L.t, 0, vec, ctx->stream));
         fmask = cmask;
         fpitch = L.lv.pitch;
         frows = L.lv.rows;

@@ -34,15 +34,15 @@ namespace {
 
 constexpr int RB_HP = 20;  // threads per row group (half columns): lane-linear shared-memory addressing
 #ifndef SATFILL_RB_DOWN_RG
-#define SATFILL_RB_DOWN_RG 10
+#define SATFILL_RB_DOWN_RG 14
 #endif
 #ifndef SATFILL_RB_UP_RG
-#define SATFILL_RB_UP_RG 6
+#define SATFILL_RB_UP_RG 12
 #endif
 // rows per thread: even, so that the row parity is the parity of the unrolled row index
 constexpr int RB_DOWN_RG = SATFILL_RB_DOWN_RG, RB_UP_RG = SATFILL_RB_UP_RG;
 // row stride S of the colour-split arrays with RG * S = 20 (mod 32): shared-memory bank = thread id + constant
-__host__ __device__ constexpr int rb_stride(int rg) { return rg == 4 ? 21 : (rg == 6 ? 30 : (rg == 10 ? 34 : (rg == 12 ? 23 : -1))); }
+__host__ __device__ constexpr int rb_stride(int rg) { return rg == 4 ? 21 : (rg == 6 ? 30 : (rg == 10 ? 34 : (rg == 12 ? 23 : (rg == 14 ? 22 : -1)))); }
 constexpr unsigned long long EVEN_ROWS = 0x5555555555555555ull;
 
 template <bool FIXED>
@@ -100,6 +100,28 @@ __device__ __forceinline__ float2 ldg2_if(const float* p, unsigned pred)
     return v;
 }
 
+// A row walker: a byte address advanced by the row pitch with one 64-bit add (the compiler otherwise keeps an element
+// index and re-derives the address -- four integer instructions per row and pointer)
+template <typename T>
+struct RowPtr {
+    unsigned long long a;
+    __device__ __forceinline__ RowPtr(const T* p) : a((unsigned long long)p) {}
+    __device__ __forceinline__ T* get() const { return (T*)a; }
+    __device__ __forceinline__ void step(unsigned long long bytes) { a += bytes; }
+};
+
+// predicated stores: one instruction, no branch
+__device__ __forceinline__ void stg_if(float* p, float v, unsigned pred)
+{
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q st.global.f32 [%0], %1;\n\t}" ::"l"(p), "f"(v), "r"(pred) : "memory");
+}
+__device__ __forceinline__ void stg2_if(float* p, float x, float y, unsigned pred)
+{
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %3, 0;\n\t@q st.global.v2.f32 [%0], {%1, %2};\n\t}" ::"l"(p), "f"(x), "f"(y),
+                 "r"(pred)
+                 : "memory");
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -134,20 +156,22 @@ __global__ void __launch_bounds__(RB_HP * RB_DOWN_NG) k_rb_down(Level lf, Level 
     const unsigned rm = (unsigned)(redm >> row0) & KM & rb_rows<RG>(row0, 1, W - 1) & rb_cols<RG>(h, 1, W - 1, true);
     const unsigned bm = (unsigned)(blkm >> row0) & KM & rb_rows<RG>(row0, 2, W - 2) & rb_cols<RG>(h, 2, W - 2, false);
     const int64_t gr = (int64_t)ty * TILE_H - H, gc = (int64_t)tx * TILE_W - H;  // global position of the frame origin
-    const int toff = row0 * pitch + 2 * h;                                       // the thread's (row0, column 2h) in it
+    // plane offset of the thread's (row0, column 2h); rows are walked by adding the pitch to a pointer (a fresh 64-bit
+    // address per row costs half a dozen integer instructions, and this kernel is bound by instruction issue)
+    const int64_t toff = (gr + row0) * lf.pitch + gc + 2 * h;
     // ---- global loads: the right-hand side at the thread's RG x 2 cells, one aligned pair per row
     float bred[RG], bblk[RG], wred[RG], wblk[RG];
     {
-        const float* bp = b + (int64_t)blockIdx.y * lf.plane + gr * lf.pitch + gc;
-        const float* wp = WINV ? lf.winv + gr * lf.pitch + gc : nullptr;
+        RowPtr<const float> bp(b + (int64_t)blockIdx.y * lf.plane + toff), wp(WINV ? lf.winv + toff : nullptr);
+        const unsigned long long pb = (unsigned long long)pitch * sizeof(float);
         const unsigned ld = rm | bm;
 #pragma unroll
-        for (int k = 0; k < RG; ++k) {
-            float2 v = ldg2_if(bp + (toff + k * pitch), (ld >> k) & 1);
+        for (int k = 0; k < RG; ++k, bp.step(pb), wp.step(pb)) {
+            float2 v = ldg2_if(bp.get(), (ld >> k) & 1);
             bred[k] = (k & 1) ? v.y : v.x;
             bblk[k] = (k & 1) ? v.x : v.y;
             if (WINV) {
-                float2 w = ldg2_if(wp + (toff + k * pitch), (ld >> k) & 1);
+                float2 w = ldg2_if(wp.get(), (ld >> k) & 1);
                 wred[k] = (k & 1) ? w.y : w.x;
                 wblk[k] = (k & 1) ? w.x : w.y;
             } else {
@@ -156,18 +180,29 @@ __global__ void __launch_bounds__(RB_HP * RB_DOWN_NG) k_rb_down(Level lf, Level 
             }
         }
     }
+    // mask injection for the restriction at the end (coarse unknown <=> fine (2I, 2J) unknown): the row words are
+    // fetched now, so that their latency is long gone when they are used
+    constexpr int NCOARSE = (TILE_H / 2) * (TILE_W / 2), CPT = (NCOARSE + THREADS - 1) / THREADS;
+    uint32_t crow[CPT];
+    {
+        const uint32_t* rowbits = lf.tbits + ((size_t)(ty + 1) * lf.tb_stride + (tx + 1)) * 32;
+#pragma unroll
+        for (int q = 0; q < CPT; ++q) {
+            int i = t + q * THREADS;
+            crow[q] = i < NCOARSE ? __ldg(rowbits + 2 * (i >> 4)) : 0u;
+        }
+    }
     const int sb = (row0 + 1) * S + h;  // shared index of (row0, h)
     // ---- red half-sweep from zero: x = b / d (pointwise); the tile's own red cells go to HBM colour-split
     {
-        float* xo = xr + (int64_t)blockIdx.y * (lf.plane >> 1) + gr * pitch2 + (gc >> 1);
-        const int toff2 = row0 * pitch2 + h;
+        RowPtr<float> xo(xr + (int64_t)blockIdx.y * (lf.plane >> 1) + (gr + row0) * pitch2 + (gc >> 1) + h);
+        const unsigned long long pb2 = (unsigned long long)pitch2 * sizeof(float);
         const unsigned own = rm & rb_rows<RG>(row0, H, H + TILE_H) & rb_cols<RG>(h, H, H + TILE_W, true);
 #pragma unroll
-        for (int k = 0; k < RG; ++k) {
+        for (int k = 0; k < RG; ++k, xo.step(pb2)) {
             float v = wred[k] * (((rm >> k) & 1) ? bred[k] : 0.f);
             R[sb + k * S] = v;
-            if ((own >> k) & 1)
-                xo[toff2 + k * pitch2] = v;
+            stg_if(xo.get(), v, (own >> k) & 1);
         }
     }
     __syncthreads();
@@ -208,12 +243,14 @@ __global__ void __launch_bounds__(RB_HP * RB_DOWN_NG) k_rb_down(Level lf, Level 
     {
         float* bco = bc + (int64_t)blockIdx.y * lc.plane + (int64_t)(ty * (TILE_H / 2)) * lc.pitch + tx * (TILE_W / 2);
         const int cpitch = (int)lc.pitch;
-        const uint32_t* rowbits = lf.tbits + ((size_t)(ty + 1) * lf.tb_stride + (tx + 1)) * 32;
-        for (int i = t; i < (TILE_H / 2) * (TILE_W / 2); i += THREADS) {
-            int ci = i >> 4, cj = i & 15;
-            if ((rowbits[2 * ci] >> (2 * cj)) & 1) {  // mask injection: coarse unknown <=> fine (2I, 2J) unknown
+#pragma unroll
+        for (int q = 0; q < CPT; ++q) {
+            const int i = t + q * THREADS;
+            const int ci = i >> 4, cj = i & 15;
+            if (i < NCOARSE) {
                 const float* p = R + (2 * ci + H + 1) * S + cj + 2;
-                bco[ci * cpitch + cj] = p[0] + 0.25f * ((p[-S - 1] + p[-S]) + (p[S - 1] + p[S]));
+                const float v = p[0] + 0.25f * ((p[-S - 1] + p[-S]) + (p[S - 1] + p[S]));
+                stg_if(bco + (ci * cpitch + cj), v, (crow[q] >> (2 * cj)) & 1);
             }
         }
     }
@@ -255,24 +292,24 @@ __global__ void __launch_bounds__(RB_HP * RB_UP_NG) k_rb_up(Level lf, Level lc, 
     const unsigned own_red = rm & own_rows & rb_cols<RG>(h, H, H + TILE_W, true);
     const unsigned own_blk = on_blk & own_rows & rb_cols<RG>(h, H, H + TILE_W, false);
     const int64_t gr = (int64_t)ty * TILE_H - H, gc = (int64_t)tx * TILE_W - H;
-    const int toff = row0 * pitch + 2 * h;
-    const int64_t goff = (int64_t)blockIdx.y * lf.plane + gr * lf.pitch + gc;
+    // plane offset of the thread's (row0, column 2h); rows are walked by pointer increments (see k_rb_down)
+    const int64_t toff = (gr + row0) * lf.pitch + gc + 2 * h;
+    const int64_t goff = (int64_t)blockIdx.y * lf.plane + toff;
     // ---- global loads first: red x on the whole region, b where an update needs it, the coarse correction
     float xv[RG], bred[RG], bblk[RG], wred[RG], wblk[RG];
     {
-        const float* xp = xr + (int64_t)blockIdx.y * (lf.plane >> 1) + gr * pitch2 + (gc >> 1);
-        const float* bp = b + goff;
-        const float* wp = WINV ? lf.winv + gr * lf.pitch + gc : nullptr;
-        const int toff2 = row0 * pitch2 + h;
+        RowPtr<const float> xp(xr + (int64_t)blockIdx.y * (lf.plane >> 1) + (gr + row0) * pitch2 + (gc >> 1) + h);
+        RowPtr<const float> bp(b + goff), wp(WINV ? lf.winv + toff : nullptr);
+        const unsigned long long pb = (unsigned long long)pitch * sizeof(float), pb2 = (unsigned long long)pitch2 * sizeof(float);
         const unsigned ld = own_red | on_blk;
 #pragma unroll
-        for (int k = 0; k < RG; ++k) {
-            xv[k] = ldg_if(xp + (toff2 + k * pitch2), (rm >> k) & 1);
-            float2 v = ldg2_if(bp + (toff + k * pitch), (ld >> k) & 1);
+        for (int k = 0; k < RG; ++k, xp.step(pb2), bp.step(pb), wp.step(pb)) {
+            xv[k] = ldg_if(xp.get(), (rm >> k) & 1);
+            float2 v = ldg2_if(bp.get(), (ld >> k) & 1);
             bred[k] = (k & 1) ? v.y : v.x;
             bblk[k] = (k & 1) ? v.x : v.y;
             if (WINV) {
-                float2 w = ldg2_if(wp + (toff + k * pitch), (ld >> k) & 1);
+                float2 w = ldg2_if(wp.get(), (ld >> k) & 1);
                 wred[k] = (k & 1) ? w.y : w.x;
                 wblk[k] = (k & 1) ? w.x : w.y;
             } else {
@@ -329,20 +366,20 @@ __global__ void __launch_bounds__(RB_HP * RB_UP_NG) k_rb_up(Level lf, Level lc, 
     // ---- red half-sweep on the tile itself; both cells of the half column leave as one aligned pair (a cell that
     //      is not an unknown is written as the zero it already holds)
     {
-        float* xo = x_out + goff;
+        RowPtr<float> xo(x_out + goff);
+        const unsigned long long pb = (unsigned long long)pitch * sizeof(float);
         const unsigned st = own_red | own_blk;
         const float* p = B + sb;
         float n = p[-S], c = p[0];
 #pragma unroll
-        for (int k = 0; k < RG; ++k) {
+        for (int k = 0; k < RG; ++k, xo.step(pb)) {
             float s = p[(k + 1) * S];
             float side = p[k * S + ((k & 1) ? 1 : -1)];
             float v = wred[k] * (bred[k] + ((n + s) + (c + side)));
             v = ((own_red >> k) & 1) ? v : 0.f;
             if (DOT)
                 acc += bred[k] * v;
-            if ((st >> k) & 1)
-                *reinterpret_cast<float2*>(xo + (toff + k * pitch)) = (k & 1) ? make_float2(vblk[k], v) : make_float2(v, vblk[k]);
+            stg2_if(xo.get(), (k & 1) ? vblk[k] : v, (k & 1) ? v : vblk[k], (st >> k) & 1);
             n = c;
             c = s;
         }

@@ -306,6 +306,39 @@ def test_resident_scene_device_buffers(ctx, port):
     sc.close()
 
 
+def test_mask_changes_on_a_resident_scene(ctx):
+    """The work vectors of a scene are non-zero only at the unknowns of the mask they were last used with; when the mask
+    changes they are scrubbed through the old tile lists (cg.cu: scrub_work_vectors).  A scene that goes through several
+    masks, preconditioners and multigrid variants must give what a fresh scene gives."""
+    rows, cols = 333, 290
+    bands = [synth.smooth_band(rows, cols, seed=60 + b) for b in range(2)]
+    masks = [synth.blob_mask(rows, cols, cover=c, sigma=sg, seed=sd) for c, sg, sd in
+             ((0.45, 9.0, 1), (0.2, 4.0, 2), (0.6, 14.0, 3), (0.3, 2.5, 4), (0.35, 7.0, 5))]
+    hole = np.zeros((rows, cols), bool)
+    hole[1:-1, 1:-1] = True
+    masks.insert(2, hole)
+    modes = [dict(precond=sab.MULTIGRID), dict(precond=sab.JACOBI), dict(precond=sab.MULTIGRID),
+             dict(precond=sab.MULTIGRID, mg_variant=sab.MG_JACOBI64), dict(precond=sab.MULTIGRID), dict(precond=sab.JACOBI)]
+    sc = ctx.scene(sab.LAPLACE, rows, cols, 2)
+    for mask, mode in zip(masks, modes):
+        sc.set_mask(mask)
+        for b in range(2):
+            sc.set_band(b, bands[b])
+        st = sc.solve(tolerance=1e-11, **mode)
+        fresh = ctx.scene(sab.LAPLACE, rows, cols, 2)
+        fresh.set_mask(mask)
+        for b in range(2):
+            fresh.set_band(b, bands[b])
+        st_f = fresh.solve(tolerance=1e-11, **mode)
+        for b in range(2):
+            assert st[b]["status"] == sab.SA_OK
+            assert abs(st[b]["iterations"] - st_f[b]["iterations"]) <= 1, (mode, st[b]["iterations"], st_f[b]["iterations"])
+            assert rel_max_abs(sc.get_band(b), fresh.get_band(b), mask) < 1e-8
+            assert np.array_equal(sc.get_band(b)[~mask], bands[b][~mask])
+        fresh.close()
+    sc.close()
+
+
 # ---- multigrid-preconditioned CG: same answers, far fewer iterations ------------------------------------------------
 @pytest.mark.parametrize("i", [0, 1, 2])
 def test_multigrid_laplace_vs_golden(ctx, small_cases, i):
