@@ -328,11 +328,12 @@ def run_b200(args, w):
     #   direction: R z 8 (4: the float cycle's z) + R p 8 + W p 8 + R mask 1;  update: R p, x, r 24 + W x, r 16 + mask 1
     #   single smoother sweep: R x 8 + R b 8 + W x 8 + R mask 1 = 25;  single transfers ~19
     #   double Jacobi cycle: down R b 8 + W x 8 + W b_c 8/4 = 18;  up R x 8 + R b 8 + R e_c 8/4 + W x 8 = 26
-    #   float red-black cycle (CG then also writes a float copy of r: update 41 + 4 = 45, direction reads a float z: 21):
+    #   float red-black cycle: CG keeps its search direction in float and writes a float copy of r for the cycle --
+    #     direction R z 4 + R p 4 + W p 4 + mask 1 = 13;  update R p 4 + R/W x 16 + R/W r 16 + W rf 4 + mask 1 = 41:
     #     down R b 4 + W x_red 4/2 + W b_c 4/4 = 7;  up R x_red 4/2 + R b 4 + R e_c 4/4 + W x 4 = 11;
     #     coarse levels also read the 1 / diagonal plane of the boundary-corrected operator: 11 and 15
     if rb:
-        bytes_per_unknown = [21.0, 45.0, 9.0, 19.0, 7.0, 11.0, 11.0, 15.0]
+        bytes_per_unknown = [13.0, 41.0, 9.0, 19.0, 7.0, 11.0, 11.0, 15.0]
     else:
         bytes_per_unknown = [25.0, 41.0, 25.0, 19.0, 18.0, 26.0, 18.0, 26.0]
     dom = max(range(NK), key=lambda c: kms[c])

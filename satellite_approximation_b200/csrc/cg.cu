@@ -336,8 +336,13 @@ static int scrub_work_vectors(sa_scene* s)
     const int nb = s->nbands;
     ScrubPlanes P {};
     P.d[P.nd++] = s->plane0(s->r, 0);
-    P.d[P.nd++] = s->plane0(s->p[0], 0);
-    P.d[P.nd++] = s->plane0(s->p[1], 0);
+    if (s->work_dirty & WORK_PF) {
+        P.f[P.nf++] = (float*)s->p[0] + s->pitch;
+        P.f[P.nf++] = (float*)s->p[1] + s->pitch;
+    } else {
+        P.d[P.nd++] = s->plane0(s->p[0], 0);
+        P.d[P.nd++] = s->plane0(s->p[1], 0);
+    }
     if ((s->work_dirty & WORK_J64) && s->z) {
         P.d[P.nd++] = s->plane0(s->z, 0);
         P.d[P.nd++] = s->plane0(s->t, 0);
@@ -516,7 +521,14 @@ int solve_scene(sa_scene* s, const sa_options& o, sa_stats* stats)
             SA_TRY(clear_multigrid_vectors(s));
             s->work_dirty &= ~other;
         }
-        s->work_dirty |= kind;
+        // ... and so do the two precisions of the search direction
+        const bool pf_now = o.cg_variant == 0 && rb;
+        if ((s->work_dirty & (WORK_JACOBI | WORK_RB | WORK_J64)) && ((s->work_dirty & WORK_PF) != 0) != pf_now) {
+            size_t bytes = (size_t)s->plane * s->nbands * sizeof(double);
+            SA_CUDA(ctx, cudaMemsetAsync(s->p[0], 0, bytes, ctx->stream));
+            SA_CUDA(ctx, cudaMemsetAsync(s->p[1], 0, bytes, ctx->stream));
+        }
+        s->work_dirty = (s->work_dirty & ~WORK_PF) | kind | (pf_now ? WORK_PF : 0);
     }
     // one system split by rows across the ranks of the context's communicator (dist.cu)
     const bool dist = s->distributed && ctx->world > 1;
@@ -537,7 +549,10 @@ int solve_scene(sa_scene* s, const sa_options& o, sa_stats* stats)
     double* u0 = s->plane0(s->u, b0);
     double* g0 = poisson ? s->plane0(s->g, b0) : nullptr;
     double* r0 = s->plane0(s->r, b0);
+    // the search direction: double planes, or (strip kernels + red-black cycle) float planes in the same allocations
+    const bool pf = strip && rb;
     double* pbuf[2] = { s->plane0(s->p[0], b0), s->plane0(s->p[1], b0) };
+    float* pbuf_f[2] = { (float*)s->p[0] + s->pitch + (int64_t)b0 * s->plane, (float*)s->p[1] + s->pitch + (int64_t)b0 * s->plane };
 
     SA_CUDA(ctx, cudaMemsetAsync(scal, 0, sizeof(BandScalars) * nb, ctx->stream));
     if (have_tiles) {
@@ -583,6 +598,8 @@ int solve_scene(sa_scene* s, const sa_options& o, sa_stats* stats)
             int ki = (int)(k & 0x3fffffff);  // only k == 0 and k & 3 matter to the kernels; iters is re-based below
             const double* pin = pbuf[k & 1];
             double* pout = pbuf[(k + 1) & 1];
+            const void* pin_v = pf ? (const void*)pbuf_f[k & 1] : (const void*)pin;
+            void* pout_v = pf ? (void*)pbuf_f[(k + 1) & 1] : (void*)pout;
             if (mg) {
                 // z = M^-1 r, rz[slot] accumulated by the cycle's last kernel
                 const void* z;
@@ -598,19 +615,22 @@ int solve_scene(sa_scene* s, const sa_options& o, sa_stats* stats)
                     SA_TRY(dist_reduce(s, DIST_RZ, ki & 3, -1));
                 kt.begin(KC_DIRECTION, n * live);
                 if (strip)
-                    SA_TRY(launch_direction2(ctx, lv, nb, false, z, rb, pin, pout, scal, ki));
+                    SA_TRY(launch_direction2(ctx, lv, nb, false, z, rb, pin_v, pout_v, pf, scal, ki));
                 else if (rb)
                     SA_LAUNCH(ctx, (k_direction<false, float>), grid, block, 0, lv, (const float*)z, pin, pout, scal, ki);
                 else
                     SA_LAUNCH(ctx, (k_direction<false, double>), grid, block, 0, lv, (const double*)z, pin, pout, scal, ki);
                 kt.end();
                 if (dist) {
-                    SA_TRY(dist_halo<double>(s, 0, pout, s->pitch, s->plane, 1, 1));
+                    if (pf)
+                        SA_TRY(dist_halo<float>(s, 0, (float*)pout_v, s->pitch, s->plane, 1, 1));
+                    else
+                        SA_TRY(dist_halo<double>(s, 0, pout, s->pitch, s->plane, 1, 1));
                     SA_TRY(dist_reduce(s, DIST_PQ, ki & 3, (ki + 2) & 3));
                 }
                 kt.begin(KC_UPDATE, n * live);
                 if (strip)
-                    SA_TRY(launch_update2(ctx, lv, nb, false, u0, pout, r0, rf, scal, ki));
+                    SA_TRY(launch_update2(ctx, lv, nb, false, u0, pout_v, pf, r0, rf, scal, ki));
                 else if (rb)
                     SA_LAUNCH(ctx, (k_update<false, true>), grid, block, 0, lv, u0, pout, r0, rf, scal, ki);
                 else
@@ -624,7 +644,7 @@ int solve_scene(sa_scene* s, const sa_options& o, sa_stats* stats)
             } else {
                 kt.begin(KC_DIRECTION, n * live);
                 if (strip)
-                    SA_TRY(launch_direction2(ctx, lv, nb, true, r0, false, pin, pout, scal, ki));
+                    SA_TRY(launch_direction2(ctx, lv, nb, true, r0, false, pin, pout, false, scal, ki));
                 else
                     SA_LAUNCH(ctx, (k_direction<true, double>), grid, block, 0, lv, r0, pin, pout, scal, ki);
                 kt.end();
@@ -634,7 +654,7 @@ int solve_scene(sa_scene* s, const sa_options& o, sa_stats* stats)
                 }
                 kt.begin(KC_UPDATE, n * live);
                 if (strip)
-                    SA_TRY(launch_update2(ctx, lv, nb, true, u0, pout, r0, nullptr, scal, ki));
+                    SA_TRY(launch_update2(ctx, lv, nb, true, u0, pout, false, r0, nullptr, scal, ki));
                 else
                     SA_LAUNCH(ctx, (k_update<true, false>), grid, block, 0, lv, u0, pout, r0, nullptr, scal, ki);
                 kt.end();

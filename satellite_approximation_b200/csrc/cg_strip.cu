@@ -77,6 +77,23 @@ __device__ __forceinline__ double2 ldnc2_if(const float* p, unsigned pred)  // f
         : "l"(p), "r"(pred));
     return make_double2((double)x, (double)y);
 }
+__device__ __forceinline__ float2 ldnc2f_if(const float* p, unsigned pred)  // float plane, as stored
+{
+    float2 v;
+    asm("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %3, 0;\n\tmov.f32 %0, 0f00000000;\n\tmov.f32 %1, 0f00000000;\n\t"
+        "@q ld.global.nc.v2.f32 {%0, %1}, [%2];\n\t}"
+        : "=f"(v.x), "=f"(v.y)
+        : "l"(p), "r"(pred));
+    return v;
+}
+__device__ __forceinline__ float ldncf_if(const float* p, unsigned pred)
+{
+    float v;
+    asm("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\tmov.f32 %0, 0f00000000;\n\t@q ld.global.nc.f32 %0, [%1];\n\t}"
+        : "=f"(v)
+        : "l"(p), "r"(pred));
+    return v;
+}
 __device__ __forceinline__ double ldnc_if(const float* p, unsigned pred)
 {
     float v;
@@ -85,6 +102,9 @@ __device__ __forceinline__ double ldnc_if(const float* p, unsigned pred)
         : "l"(p), "r"(pred));
     return (double)v;
 }
+
+__device__ __forceinline__ void store_pair(double* p, double2 v) { *reinterpret_cast<double2*>(p) = v; }
+__device__ __forceinline__ void store_pair(float* p, double2 v) { *reinterpret_cast<float2*>(p) = make_float2((float)v.x, (float)v.y); }
 
 // What a thread needs to know about a tile: its coordinates and the unknown bits of the thread's two columns.
 struct TileBits {
@@ -194,9 +214,13 @@ __device__ __forceinline__ void prefetch_l2_if(const void* p, unsigned pred)
 //   JACOBI: z = r / d on the fly (zin = r).
 // Persistent: gridDim.x <= n_tiles CTAs, each walks all bands (a band that has converged costs one flag read).
 // ---------------------------------------------------------------------------------------------------------------
-template <bool JACOBI, bool FIXED, typename ZT>
+//   PT = float: the search direction is STORED in single precision (the multigrid path, whose z is single precision
+//   anyway).  x, r, A p and every dot product stay double and use the rounded p, so r = b - A x holds as exactly as
+//   before; the rounding only perturbs the direction by 6e-8 relative, which CG does not notice
+//   (tools/mg_prototype.py: identical iteration counts down to a 1e-14 residual).
+template <bool JACOBI, bool FIXED, typename ZT, typename PT>
 __global__ void __launch_bounds__(ST_THREADS, dir_ctas<ZT>()) k_direction2(Level lv, int nbands, const ZT* __restrict__ zin,
-    const double* __restrict__ p_old, double* __restrict__ p_new, BandScalars* __restrict__ scal, int k)
+    const PT* __restrict__ p_old, PT* __restrict__ p_new, BandScalars* __restrict__ scal, int k)
 {
     __shared__ double s_red[4];
     const int slot = k & 3;
@@ -227,8 +251,8 @@ __global__ void __launch_bounds__(ST_THREADS, dir_ctas<ZT>()) k_direction2(Level
         }
         const int64_t band_off = (int64_t)band * lv.plane;
         const ZT* zband = zin + band_off;
-        const double* pband = p_old + band_off;
-        double* poband = p_new + band_off;
+        const PT* pband = p_old + band_off;
+        PT* poband = p_new + band_off;
         double acc = 0.0;
         // L2 prefetch of the next visit's tile: the own rows of z and p (the halo rows are other threads' own rows)
         auto prefetch = [&](const TileBits& nx) {
@@ -240,64 +264,101 @@ __global__ void __launch_bounds__(ST_THREADS, dir_ctas<ZT>()) k_direction2(Level
                 prefetch_l2_if(pband + (o + j * pitch), (any >> j) & 1);
             }
         };
-        for_each_tile(lv, cx, row0, [&](const TileBits& tb, const TileBits& nx, bool has_next, auto& pf) {
+        for_each_tile(lv, cx, row0, [&](const TileBits& tb, const TileBits& nx, bool has_next, auto& pf_next) {
             const int origin = tb.origin(pitch);
             const ZT* zb = zband + origin;
-            const double* pb = pband + origin;
+            const PT* pb = pband + origin;
             const unsigned any = tb.any();
-            // ---- all loads: pairs of rows row0-1 .. row0+4, and (edge lanes) the halo column of the own rows
-            double2 zv[6], pv[6];
-            double ze[ST_RG], pe[ST_RG];
+            const int64_t gr = (int64_t)tb.ty() * TILE_H + row0, gc = (int64_t)tb.tx() * TILE_W + 2 * cx;
+            const int dcL = diag_col<FIXED>(lv, gc), dcR = diag_col<FIXED>(lv, gc + 1);
+            const int eoff = toff + (west ? -1 : 2);
+            // the halo cell can only matter if the own edge cell is an unknown
+            const unsigned em = (west ? tb.mL() : (east ? tb.mR() : 0u)) >> 1;
+            double2 pn[6];
+            double pedge[ST_RG];
+            if constexpr (sizeof(PT) == 4 && sizeof(ZT) == 4 && !JACOBI) {
+                // float z, float p: p' = z + beta p in single precision, exactly as it is stored (conversions between
+                // float and double are a quarter-rate pipe: two per cell instead of eight); widened once for A p'
+                float2 zf[6], pf[6];
+                float zef[ST_RG], pef[ST_RG];
 #pragma unroll
-            for (int j = 0; j < 6; ++j) {
-                zv[j] = ldnc2_if(zb + (toff + j * pitch), (any >> j) & 1);
-                pv[j] = ldnc2_if(pb + (toff + j * pitch), (any >> j) & 1);
-            }
-            {
-                // the halo cell can only matter if the own edge cell is an unknown
-                const int eoff = toff + (west ? -1 : 2);
-                const unsigned em = (west ? tb.mL() : (east ? tb.mR() : 0u)) >> 1;
+                for (int j = 0; j < 6; ++j) {
+                    zf[j] = ldnc2f_if(zb + (toff + j * pitch), (any >> j) & 1);
+                    pf[j] = ldnc2f_if(pb + (toff + j * pitch), (any >> j) & 1);
+                }
+#pragma unroll
+                for (int j = 0; j < ST_RG; ++j) {
+                    zef[j] = ldncf_if(zb + (eoff + (j + 1) * pitch), (em >> j) & 1);
+                    pef[j] = ldncf_if(pb + (eoff + (j + 1) * pitch), (em >> j) & 1);
+                }
+                if (SATFILL_L2_PREFETCH && has_next)
+                    pf_next(nx);
+                const float bf = (float)beta;
+                const unsigned st = sector_or4(sector_or2(any));
+                PT* po = poband + origin;
+#pragma unroll
+                for (int j = 0; j < 6; ++j) {
+                    float2 v = make_float2(fmaf(bf, pf[j].x, zf[j].x), fmaf(bf, pf[j].y, zf[j].y));  // ConjugateGradient.h:80
+                    if (j >= 1 && j <= ST_RG && ((st >> j) & 1))
+                        *reinterpret_cast<float2*>(po + (toff + j * pitch)) = v;
+                    pn[j] = make_double2((double)v.x, (double)v.y);
+                }
+#pragma unroll
+                for (int j = 0; j < ST_RG; ++j)
+                    pedge[j] = (double)fmaf(bf, pef[j], zef[j]);
+            } else {
+                // ---- all loads: pairs of rows row0-1 .. row0+4, and (edge lanes) the halo column of the own rows
+                double2 zv[6], pv[6];
+                double ze[ST_RG], pe[ST_RG];
+#pragma unroll
+                for (int j = 0; j < 6; ++j) {
+                    zv[j] = ldnc2_if(zb + (toff + j * pitch), (any >> j) & 1);
+                    pv[j] = ldnc2_if(pb + (toff + j * pitch), (any >> j) & 1);
+                }
 #pragma unroll
                 for (int j = 0; j < ST_RG; ++j) {
                     ze[j] = ldnc_if(zb + (eoff + (j + 1) * pitch), (em >> j) & 1);
                     pe[j] = ldnc_if(pb + (eoff + (j + 1) * pitch), (em >> j) & 1);
                 }
-            }
-            if (SATFILL_L2_PREFETCH && has_next)
-                pf(nx);
-            const int64_t gr = (int64_t)tb.ty() * TILE_H + row0, gc = (int64_t)tb.tx() * TILE_W + 2 * cx;
-            const int dcL = diag_col<FIXED>(lv, gc), dcR = diag_col<FIXED>(lv, gc + 1);
-            // ---- p' = z + beta p on the 6 x 2 cells and the edge column
-            double2 pn[6];
+                if (SATFILL_L2_PREFETCH && has_next)
+                    pf_next(nx);
+                // ---- p' = z + beta p on the 6 x 2 cells and the edge column
 #pragma unroll
-            for (int j = 0; j < 6; ++j) {
-                double zl = zv[j].x, zr = zv[j].y;
-                if (JACOBI) {
-                    int dr = diag_row<FIXED>(lv, gr - 1 + j);
-                    zl *= inv_of(dr + dcL);
-                    zr *= inv_of(dr + dcR);
+                for (int j = 0; j < 6; ++j) {
+                    double zl = zv[j].x, zr = zv[j].y;
+                    if (JACOBI) {
+                        int dr = diag_row<FIXED>(lv, gr - 1 + j);
+                        zl *= inv_of(dr + dcL);
+                        zr *= inv_of(dr + dcR);
+                    }
+                    pn[j].x = zl + beta * pv[j].x;  // ConjugateGradient.h:80
+                    pn[j].y = zr + beta * pv[j].y;
+                    if (sizeof(PT) == 4) {  // p'.Ap' of the direction as it is stored
+                        pn[j].x = (double)(float)pn[j].x;
+                        pn[j].y = (double)(float)pn[j].y;
+                    }
                 }
-                pn[j].x = zl + beta * pv[j].x;  // ConjugateGradient.h:80
-                pn[j].y = zr + beta * pv[j].y;
-            }
-            double pedge[ST_RG];
 #pragma unroll
-            for (int j = 0; j < ST_RG; ++j) {
-                double z = ze[j];
-                if (JACOBI)
-                    z *= inv_of(diag_row<FIXED>(lv, gr + j) + diag_col<FIXED>(lv, west ? gc - 1 : gc + 2));
-                pedge[j] = z + beta * pe[j];
+                for (int j = 0; j < ST_RG; ++j) {
+                    double z = ze[j];
+                    if (JACOBI)
+                        z *= inv_of(diag_row<FIXED>(lv, gr + j) + diag_col<FIXED>(lv, west ? gc - 1 : gc + 2));
+                    pedge[j] = z + beta * pe[j];
+                    if (sizeof(PT) == 4)
+                        pedge[j] = (double)(float)pedge[j];
+                }
+                PT* po = poband + origin;
+                const unsigned st = sizeof(PT) == 4 ? sector_or4(sector_or2(any)) : sector_or2(any);
+#pragma unroll
+                for (int j = 1; j <= ST_RG; ++j)
+                    if ((st >> j) & 1)
+                        store_pair(po + (toff + j * pitch), pn[j]);
             }
-            // ---- store the own rows, accumulate p'.Ap'
-            // Stores cover whole 32-byte sectors (this pair and the other pair of the sector, a neighbouring lane): a
-            // partially written sector costs HBM a read-modify-write.  The extra cells are not unknowns: they get the
-            // zero the invariant demands.
-            double* po = poband + origin;
-            const unsigned st = sector_or2(any);
+            // ---- accumulate p'.Ap' over the own rows (whole 32-byte sectors were stored above: a partially written
+            //      sector costs HBM a read-modify-write; the extra cells are not unknowns and get the zero the invariant
+            //      demands)
 #pragma unroll
             for (int j = 1; j <= ST_RG; ++j) {
-                if ((st >> j) & 1)
-                    *reinterpret_cast<double2*>(po + (toff + j * pitch)) = pn[j];
                 double wl = __shfl_up_sync(0xffffffffu, pn[j].y, 1);    // lane - 1's right cell
                 double er = __shfl_down_sync(0xffffffffu, pn[j].x, 1);  // lane + 1's left cell
                 if (west)
@@ -320,9 +381,9 @@ __global__ void __launch_bounds__(ST_THREADS, dir_ctas<ZT>()) k_direction2(Level
 // k_update2:  alpha = rz / pq;  x += alpha p;  r -= alpha A p  (A p recomputed);  |r|^2 and (JACOBI) r.(r/d)
 //   RF: also write the residual as float for the red-black cycle.
 // ---------------------------------------------------------------------------------------------------------------
-template <bool JACOBI, bool FIXED, bool RF>
+template <bool JACOBI, bool FIXED, bool RF, typename PT>
 __global__ void __launch_bounds__(ST_THREADS, ST_UPD_CTAS) k_update2(Level lv, int nbands, double* __restrict__ u,
-    const double* __restrict__ p, double* __restrict__ rvec, float* __restrict__ rf, BandScalars* __restrict__ scal, int k)
+    const PT* __restrict__ p, double* __restrict__ rvec, float* __restrict__ rf, BandScalars* __restrict__ scal, int k)
 {
     __shared__ double s_red[4];
     const int slot = k & 3, next = (k + 1) & 3;
@@ -337,7 +398,7 @@ __global__ void __launch_bounds__(ST_THREADS, ST_UPD_CTAS) k_update2(Level lv, i
         const double alpha = sc.rz[slot] / sc.pq[slot];  // ConjugateGradient.h:68
         const int64_t band_off = (int64_t)band * lv.plane;
         double r2 = 0.0, rz = 0.0;
-        const double* pband = p + band_off;
+        const PT* pband = p + band_off;
         double* uband = u + band_off;
         double* rband = rvec + band_off;
         float* rfband = RF ? rf + band_off : nullptr;
@@ -353,7 +414,7 @@ __global__ void __launch_bounds__(ST_THREADS, ST_UPD_CTAS) k_update2(Level lv, i
         };
         for_each_tile(lv, cx, row0, [&](const TileBits& tb, const TileBits& nx, bool has_next, auto& pf) {
             const int origin = tb.origin(pitch);
-            const double* pb = pband + origin;
+            const PT* pb = pband + origin;
             double* ub = uband + origin;
             double* rb = rband + origin;
             const unsigned any = tb.any();
@@ -467,52 +528,88 @@ static unsigned strip_grid(const sa_ctx* ctx, const Level& lv, int ctas_per_sm)
 }
 
 int launch_direction2(sa_ctx* ctx, const Level& lv, int nbands, bool jacobi, const void* zin, bool z_is_float,
-    const double* p_old, double* p_new, BandScalars* scal, int k)
+    const void* p_old, void* p_new, bool p_is_float, BandScalars* scal, int k)
 {
     if (lv.n_tiles == 0)
         return SA_OK;
     const unsigned grid = strip_grid(ctx, lv, z_is_float ? dir_ctas<float>() : dir_ctas<double>());
+#define SA_DIR(J, F, ZT, PT)                                                                                      \
+    SA_LAUNCH(ctx, (k_direction2<J, F, ZT, PT>), grid, ST_THREADS, 0, lv, nbands, (const ZT*)zin, (const PT*)p_old, \
+        (PT*)p_new, scal, k)
+    const bool fixed = lv.fixed_diag != 0;
     if (jacobi) {
-        if (lv.fixed_diag)
-            SA_LAUNCH(ctx, (k_direction2<true, true, double>), grid, ST_THREADS, 0, lv, nbands, (const double*)zin, p_old, p_new, scal, k);
+        if (p_is_float)
+            return fail(ctx, SA_BAD_ARGUMENT, "direction: the Jacobi path keeps its search direction in double");
+        if (fixed)
+            SA_DIR(true, true, double, double);
         else
-            SA_LAUNCH(ctx, (k_direction2<true, false, double>), grid, ST_THREADS, 0, lv, nbands, (const double*)zin, p_old, p_new, scal, k);
+            SA_DIR(true, false, double, double);
     } else if (z_is_float) {
-        if (lv.fixed_diag)
-            SA_LAUNCH(ctx, (k_direction2<false, true, float>), grid, ST_THREADS, 0, lv, nbands, (const float*)zin, p_old, p_new, scal, k);
-        else
-            SA_LAUNCH(ctx, (k_direction2<false, false, float>), grid, ST_THREADS, 0, lv, nbands, (const float*)zin, p_old, p_new, scal, k);
+        if (p_is_float) {
+            if (fixed)
+                SA_DIR(false, true, float, float);
+            else
+                SA_DIR(false, false, float, float);
+        } else {
+            if (fixed)
+                SA_DIR(false, true, float, double);
+            else
+                SA_DIR(false, false, float, double);
+        }
     } else {
-        if (lv.fixed_diag)
-            SA_LAUNCH(ctx, (k_direction2<false, true, double>), grid, ST_THREADS, 0, lv, nbands, (const double*)zin, p_old, p_new, scal, k);
+        if (p_is_float)
+            return fail(ctx, SA_BAD_ARGUMENT, "direction: a double z goes with a double search direction");
+        if (fixed)
+            SA_DIR(false, true, double, double);
         else
-            SA_LAUNCH(ctx, (k_direction2<false, false, double>), grid, ST_THREADS, 0, lv, nbands, (const double*)zin, p_old, p_new, scal, k);
+            SA_DIR(false, false, double, double);
     }
+#undef SA_DIR
     return SA_OK;
 }
 
-int launch_update2(sa_ctx* ctx, const Level& lv, int nbands, bool jacobi, double* u, const double* p, double* r, float* rf,
-    BandScalars* scal, int k)
+int launch_update2(sa_ctx* ctx, const Level& lv, int nbands, bool jacobi, double* u, const void* p, bool p_is_float, double* r,
+    float* rf, BandScalars* scal, int k)
 {
     if (lv.n_tiles == 0)
         return SA_OK;
     const unsigned grid = strip_grid(ctx, lv, ST_UPD_CTAS);
+#define SA_UPD(J, F, R, PT) \
+    SA_LAUNCH(ctx, (k_update2<J, F, R, PT>), grid, ST_THREADS, 0, lv, nbands, u, (const PT*)p, r, rf, scal, k)
+    const bool fixed = lv.fixed_diag != 0;
     if (jacobi) {
-        if (lv.fixed_diag)
-            SA_LAUNCH(ctx, (k_update2<true, true, false>), grid, ST_THREADS, 0, lv, nbands, u, p, r, rf, scal, k);
+        if (p_is_float)
+            return fail(ctx, SA_BAD_ARGUMENT, "update: the Jacobi path keeps its search direction in double");
+        if (fixed)
+            SA_UPD(true, true, false, double);
         else
-            SA_LAUNCH(ctx, (k_update2<true, false, false>), grid, ST_THREADS, 0, lv, nbands, u, p, r, rf, scal, k);
-    } else if (lv.fixed_diag) {
-        if (rf)
-            SA_LAUNCH(ctx, (k_update2<false, true, true>), grid, ST_THREADS, 0, lv, nbands, u, p, r, rf, scal, k);
-        else
-            SA_LAUNCH(ctx, (k_update2<false, true, false>), grid, ST_THREADS, 0, lv, nbands, u, p, r, rf, scal, k);
+            SA_UPD(true, false, false, double);
+    } else if (p_is_float) {
+        if (fixed) {
+            if (rf)
+                SA_UPD(false, true, true, float);
+            else
+                SA_UPD(false, true, false, float);
+        } else {
+            if (rf)
+                SA_UPD(false, false, true, float);
+            else
+                SA_UPD(false, false, false, float);
+        }
     } else {
-        if (rf)
-            SA_LAUNCH(ctx, (k_update2<false, false, true>), grid, ST_THREADS, 0, lv, nbands, u, p, r, rf, scal, k);
-        else
-            SA_LAUNCH(ctx, (k_update2<false, false, false>), grid, ST_THREADS, 0, lv, nbands, u, p, r, rf, scal, k);
+        if (fixed) {
+            if (rf)
+                SA_UPD(false, true, true, double);
+            else
+                SA_UPD(false, true, false, double);
+        } else {
+            if (rf)
+                SA_UPD(false, false, true, double);
+            else
+                SA_UPD(false, false, false, double);
+        }
     }
+#undef SA_UPD
     return SA_OK;
 }
 

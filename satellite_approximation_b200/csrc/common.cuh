@@ -295,16 +295,16 @@ int precondition_scene(sa_scene* s, const sa_options& o);
 
 // ---- cg_strip.cu: the two kernels of a CG iteration, shared-memory-free generation ---------------------------------
 int launch_direction2(sa_ctx* ctx, const Level& lv, int nbands, bool jacobi, const void* zin, bool z_is_float,
-    const double* p_old, double* p_new, BandScalars* scal, int k);
-int launch_update2(sa_ctx* ctx, const Level& lv, int nbands, bool jacobi, double* u, const double* p, double* r, float* rf,
-    BandScalars* scal, int k);
+    const void* p_old, void* p_new, bool p_is_float, BandScalars* scal, int k);
+int launch_update2(sa_ctx* ctx, const Level& lv, int nbands, bool jacobi, double* u, const void* p, bool p_is_float, double* r,
+    float* rf, BandScalars* scal, int k);
 
 // work_dirty bits
-enum { WORK_CLEAN = 0, WORK_JACOBI = 1, WORK_RB = 2, WORK_J64 = 4, WORK_FULL = 8 };
+enum { WORK_CLEAN = 0, WORK_JACOBI = 1, WORK_RB = 2, WORK_J64 = 4, WORK_FULL = 8, WORK_PF = 16 /* p planes hold floats */ };
 // cg_strip.cu: zero the given planes at the unknowns of `lv` (whole sectors)
 struct ScrubPlanes {
     double* d[5];  // double planes, element (0, 0) of band 0
-    float* f[2];   // float planes
+    float* f[4];   // float planes
     float* h[1];   // colour-split float half planes (mg_rb.cu: red cells)
     int nd, nf, nh;
 };
