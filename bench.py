@@ -47,6 +47,11 @@ WORKLOADS = {
     # ONE system shared by all ranks: split by rows, halo rows + dot products over NCCL (strong scaling)
     "c5": dict(rows=20000, cols=20000, bands=1, cover=1.0, cell=0, problem="laplace", distributed=True,
                desc="single 20000x20000 contiguous hole, row-decomposed Laplace solve with halo exchange"),
+    # 64 scenes x ~156 regions as one 8 x 8 mosaic: every region is its own linear system, the block-sparse tile list
+    # batches them (only tiles that hold an unknown are ever visited)
+    "c4": dict(rows=16384, cols=16384, bands=4, cover=None, cell=0, problem="poisson", regions=10000,
+               desc="batched many-small-holes: 10k independent cloud regions across 64 2048x2048 scenes (one mosaic), "
+                    "4 bands, Poisson fill"),
     "small": dict(rows=2048, cols=2048, bands=4, cover=0.30, cell=48, problem="laplace",
                   desc="2048x2048 4-band tile, 30% cloud-like mask, Laplace fill"),
 }  # fmt: skip
@@ -137,7 +142,10 @@ def cpu_baseline(w, tol, crop, threads, steps=1):
     kind = "reference" if ref is not None else "port"
     eng = ref if ref is not None else oracle.port()
     n = min(crop, w["rows"], w["cols"])
-    mask = synth.blob_mask(n, n, cover=w["cover"], sigma=w["cell"] / 3.0, seed=2)
+    if w.get("regions"):  # the same density of regions as the workload
+        mask = synth.region_mask(n, n, max(1, int(w["regions"] * n * n / (w["rows"] * w["cols"]))), seed=3)
+    else:
+        mask = synth.blob_mask(n, n, cover=w["cover"], sigma=w["cell"] / 3.0, seed=2)
     nb = max(1, min(w["bands"], threads))
     bands = [synth.smooth_band(n, n, seed=100 + b) for b in range(nb)]
     poisson = w["problem"] == "poisson"
@@ -243,6 +251,10 @@ def run_b200(args, w):
         mask[:, 0] = 0
         mask[:, -1] = 0
         bands = [synth.torch_band(rows, cols, seed=100 + b, device=dev) for b in range(nb)]
+    elif w.get("regions"):
+        grid = 8
+        mask = torch.from_numpy(synth.scene_mosaic_mask(rows // grid, grid, w["regions"], seed=3 + 7 * rank).view(np.uint8)).to(dev)
+        bands = [synth.torch_band(rows, cols, seed=100 + b + 1000 * rank, device=dev) for b in range(nb)]
     else:
         # synthetic scene, built in HBM; every rank gets its own seed (independent scenes)
         mask = synth.torch_blob_mask(rows, cols, cover=w["cover"], cell=w["cell"], seed=2 + 17 * rank, device=dev)

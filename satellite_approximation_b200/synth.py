@@ -74,6 +74,8 @@ def region_mask(rows: int, cols: int, n_regions: int, area_lo: float = 1e2, area
         ratio = rng.uniform(0.5, 2.0)
         a = np.sqrt(area / np.pi * ratio)
         b = area / (np.pi * a)
+        if 2 * a + 6 >= rows or 2 * b + 6 >= cols:
+            continue
         cy = rng.uniform(a + 3, rows - a - 3)
         cx = rng.uniform(b + 3, cols - b - 3)
         y0, y1 = int(max(cy - a - 3, 0)), int(min(cy + a + 4, rows))
@@ -88,6 +90,19 @@ def region_mask(rows: int, cols: int, n_regions: int, area_lo: float = 1e2, area
         m[y0:y1, x0:x1] |= e
         occupied[y0:y1, x0:x1] |= grown
         placed += 1
+    return m
+
+
+def scene_mosaic_mask(scene: int = 2048, grid: int = 8, n_regions: int = 10000, seed: int = 3, area_lo: float = 1e2,
+                      area_hi: float = 5e4):
+    """BASELINE.json configs[3]: `n_regions` independent cloud regions across grid x grid scenes of scene x scene pixels,
+    laid out as one mosaic.  Regions keep >= 3 pixels from their scene's border, so the scenes stay independent linear
+    systems (4-connectivity) and the mosaic is solved exactly as the scenes would be one by one."""
+    per = [n_regions // (grid * grid) + (1 if i < n_regions % (grid * grid) else 0) for i in range(grid * grid)]
+    m = np.zeros((scene * grid, scene * grid), bool)
+    for i, n in enumerate(per):
+        y, x = divmod(i, grid)
+        m[y * scene : (y + 1) * scene, x * scene : (x + 1) * scene] = region_mask(scene, scene, n, area_lo, area_hi, seed=seed + 101 * i)
     return m
 
 

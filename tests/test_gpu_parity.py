@@ -306,6 +306,38 @@ def test_resident_scene_device_buffers(ctx, port):
     sc.close()
 
 
+def test_many_small_regions_mosaic_equals_scene_by_scene(ctx, port):
+    """BASELINE.json configs[3] in small: independent cloud regions across several scenes, solved as ONE mosaic (the
+    block-sparse tile list batches the regions), must equal the oracle run scene by scene -- regions are independent
+    linear systems (4-connectivity, approx/utils.h:38-44).  Also: one connected component per region, labelled in raster
+    order, bit-exact against the oracle."""
+    scene, grid, nreg, nb = 192, 2, 28, 2
+    mask = synth.scene_mosaic_mask(scene, grid, nreg, seed=11, area_lo=30.0, area_hi=1500.0)
+    n = scene * grid
+    bands = [synth.smooth_band(n, n, seed=70 + b) for b in range(nb)]
+    guides = [synth.second_date(b, seed=5 + i) for i, b in enumerate(bands)]
+    lab, k = ctx.label_components(mask)
+    wlab, wk = port.label_components(mask)
+    assert k == wk == nreg and np.array_equal(lab, wlab)
+    got = [b.copy() for b in bands]
+    st = ctx.poisson_blend(got, guides, mask, tolerance=1e-12, max_iterations=10**6, precond=sab.MULTIGRID)
+    assert all(s["status"] == sab.SA_OK for s in st)
+    lgot = [b.copy() for b in bands]
+    ctx.laplace_fill(lgot, mask, tolerance=1e-12, precond=sab.MULTIGRID)
+    for y in range(grid):
+        for x in range(grid):
+            sl = (slice(y * scene, (y + 1) * scene), slice(x * scene, (x + 1) * scene))
+            m = np.ascontiguousarray(mask[sl])
+            want, _ = port.poisson_blend([np.ascontiguousarray(b[sl]) for b in bands],
+                                         [np.ascontiguousarray(g[sl]) for g in guides], m, tol=1e-13, max_it=10**6)
+            for b in range(nb):
+                assert rel_max_abs(got[b][sl], want[b], m) < 1e-7
+                lwant, _ = port.laplace_fill(np.ascontiguousarray(bands[b][sl]), m, mode=1, tol=1e-13)
+                assert rel_max_abs(lgot[b][sl], lwant, m) < 1e-7
+    for b in range(nb):
+        assert np.array_equal(got[b][~mask], bands[b][~mask])
+
+
 def test_mask_changes_on_a_resident_scene(ctx):
     """The work vectors of a scene are non-zero only at the unknowns of the mask they were last used with; when the mask
     changes they are scrubbed through the old tile lists (cg.cu: scrub_work_vectors).  A scene that goes through several
