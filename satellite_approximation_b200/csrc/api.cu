@@ -643,7 +643,6 @@ static int host_fill(sa_ctx* ctx, int problem, double* const* images, const doub
     SA_TRY(copy_in<uint8_t>(s, s->mask0(s->mask), mask, rs, cs, 0, 0, s->rows));
     s->mask_set = true;
     s->indexed = false;
-    SA_TRY(ensure_indexed(s));
     sa_options o;
     if (opts)
         o = *opts;
@@ -651,6 +650,8 @@ static int host_fill(sa_ctx* ctx, int problem, double* const* images, const doub
         sa_default_options(&o, problem);
     if (!(o.tolerance > 0.0))
         o.tolerance = problem == SA_POISSON ? 1e-6 : DBL_EPSILON;
+    SA_TRY(ensure_indexed(s, o.precond != SA_PRECOND_MULTIGRID ? WORK_JACOBI
+                                 : (o.mg_variant == SA_MG_RB32 && o.cg_variant == 0 ? WORK_RB : WORK_J64)));
     if (s->n_unknowns == 0)
         return solve_scene(s, o, stats);  // fills stats, returns SA_EMPTY_MASK
     int32_t* h_cnt = (int32_t*)ctx->pinned;

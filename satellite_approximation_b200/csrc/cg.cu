@@ -330,12 +330,19 @@ Level fine_level(const sa_scene* s)
 
 // Zero the work vectors at the unknowns of the mask they were last used with (the tile lists and bit masks of that mask
 // are still in place: sa_scene_set_mask only replaces the mask itself).
-static int scrub_work_vectors(sa_scene* s)
+// `lean`: the solve that follows is the strip CG + red-black cycle again, which reads r, the float copy of r, the red
+// half-planes and the coarse right-hand sides only through the unknown bits (k_update2, k_rb_down, k_rb_up mask every
+// cell they use): only the vectors whose halos are read unmasked -- p, z, the coarse corrections -- have to be clean.
+// r is then marked stale for the day a Jacobi solve (which reads r with its halo) follows.
+static int scrub_work_vectors(sa_scene* s, bool lean)
 {
     sa_ctx* ctx = s->ctx;
     const int nb = s->nbands;
     ScrubPlanes P {};
-    P.d[P.nd++] = s->plane0(s->r, 0);
+    if (!lean)
+        P.d[P.nd++] = s->plane0(s->r, 0);
+    else
+        s->stale_r = s->stale_rb = true;
     if (s->work_dirty & WORK_PF) {
         P.f[P.nf++] = (float*)s->p[0] + s->pitch;
         P.f[P.nf++] = (float*)s->p[1] + s->pitch;
@@ -349,8 +356,10 @@ static int scrub_work_vectors(sa_scene* s)
     }
     if ((s->work_dirty & WORK_RB) && s->z) {
         P.f[P.nf++] = (float*)s->z + s->pitch;                                   // z of the red-black cycle
-        P.f[P.nf++] = (float*)s->z + (int64_t)s->plane * nb + s->pitch;           // float copy of the residual
-        P.h[P.nh++] = (float*)s->t + (s->pitch >> 1);                             // red half of the iterate
+        if (!lean) {
+            P.f[P.nf++] = (float*)s->z + (int64_t)s->plane * nb + s->pitch;       // float copy of the residual
+            P.h[P.nh++] = (float*)s->t + (s->pitch >> 1);                         // red half of the iterate
+        }
     }
     SA_TRY(launch_scrub(ctx, fine_level(s), nb, P));
     if (s->hierarchy_built)
@@ -364,9 +373,11 @@ static int scrub_work_vectors(sa_scene* s)
                 Q.d[Q.nd++] = c.t + c.lv.pitch;
             }
             if (s->work_dirty & WORK_RB) {
-                Q.f[Q.nf++] = (float*)c.x + c.lv.pitch;
-                Q.f[Q.nf++] = (float*)c.b + c.lv.pitch;
-                Q.h[Q.nh++] = (float*)c.t + (c.lv.pitch >> 1);
+                Q.f[Q.nf++] = (float*)c.x + c.lv.pitch;  // prolongation reads the coarse correction unmasked
+                if (!lean) {
+                    Q.f[Q.nf++] = (float*)c.b + c.lv.pitch;
+                    Q.h[Q.nh++] = (float*)c.t + (c.lv.pitch >> 1);
+                }
             }
             SA_TRY(launch_scrub(ctx, c.lv, nb, Q));
         }
@@ -392,7 +403,7 @@ static int clear_multigrid_vectors(sa_scene* s)
     return SA_OK;
 }
 
-int ensure_indexed(sa_scene* s)
+int ensure_indexed(sa_scene* s, int next_kind)
 {
     sa_ctx* ctx = s->ctx;
     if (s->indexed)
@@ -404,8 +415,11 @@ int ensure_indexed(sa_scene* s)
         SA_CUDA(ctx, cudaMemsetAsync(s->p[0], 0, bytes, ctx->stream));
         SA_CUDA(ctx, cudaMemsetAsync(s->p[1], 0, bytes, ctx->stream));
         SA_TRY(clear_multigrid_vectors(s));
+        s->stale_r = s->stale_rb = false;
     } else if (s->work_dirty != WORK_CLEAN) {
-        SA_TRY(scrub_work_vectors(s));  // before index_scene replaces the old tile lists
+        // before index_scene replaces the old tile lists
+        const bool lean = next_kind == WORK_RB && (s->work_dirty & ~WORK_PF) == WORK_RB && (s->work_dirty & WORK_PF);
+        SA_TRY(scrub_work_vectors(s, lean));
     }
     s->work_dirty = WORK_CLEAN;
     SA_TRY(index_scene(s));
@@ -490,7 +504,11 @@ int solve_scene(sa_scene* s, const sa_options& o, sa_stats* stats)
     const bool rb = mg && o.mg_variant == SA_MG_RB32;
     const bool strip = o.cg_variant == 0;
     SA_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
-    SA_TRY(ensure_indexed(s));
+    SA_TRY(ensure_indexed(s, !mg ? WORK_JACOBI : (rb && strip ? WORK_RB : WORK_J64)));
+    if (s->stale_r && !(rb && strip)) {  // Jacobi and the double cycle read r with its halo
+        SA_CUDA(ctx, cudaMemsetAsync(s->r, 0, (size_t)s->plane * s->nbands * sizeof(double), ctx->stream));
+        s->stale_r = false;
+    }
     const int64_t n = s->n_unknowns;
     // reference defaults: Laplace 2N (IterativeSolverBase.h:251), Poisson n/2 (poisson.cpp:207)
     int64_t max_it = o.max_iterations > 0 ? o.max_iterations : (poisson ? n / 2 : 2 * n);
@@ -517,9 +535,10 @@ int solve_scene(sa_scene* s, const sa_options& o, sa_stats* stats)
         // the two multigrid variants lay the same allocations out differently: clear them when the variant changes
         const int kind = !mg ? WORK_JACOBI : (rb ? WORK_RB : WORK_J64);
         const int other = kind == WORK_RB ? WORK_J64 : (kind == WORK_J64 ? WORK_RB : 0);
-        if (s->work_dirty & other) {
+        if ((s->work_dirty & other) || (kind == WORK_J64 && s->stale_rb)) {
             SA_TRY(clear_multigrid_vectors(s));
             s->work_dirty &= ~other;
+            s->stale_rb = false;
         }
         // ... and so do the two precisions of the search direction
         const bool pf_now = o.cg_variant == 0 && rb;

@@ -160,6 +160,8 @@ struct sa_scene {
     // scrubbed through the OLD tile lists (scrub_work_vectors) instead of being cleared plane by plane.
     int work_dirty = 8;        // WORK_FULL until the first clear
     bool ever_indexed = false;  // the tile lists / bit masks of a previous mask are valid
+    bool stale_r = false;       // r was left unscrubbed by a mask change (the red-black path never reads r unmasked)
+    bool stale_rb = false;      // ... and so were the cycle's masked-only vectors (float copy of r, red halves, coarse b)
 
     // Band window of the next sa_scene_solve-like call: the host-pointer entry points (api.cu) solve a scene in chunks of
     // bands so that PCIe transfers of the other chunks overlap the solve.  band_n < 0: all bands.
@@ -287,7 +289,7 @@ int device_label_components(sa_ctx* ctx, const uint8_t* mask, int64_t rows, int6
 
 // ---- cg.cu -----------------------------------------------------------------------------------------------------
 // index the mask if it changed and clear the work vectors (they must be zero outside the unknown set)
-int ensure_indexed(sa_scene* s);
+int ensure_indexed(sa_scene* s, int next_kind = 0);  // next_kind: WORK_* of the solve that follows (0: not known)
 int solve_scene(sa_scene* s, const sa_options& o, sa_stats* stats);
 Level fine_level(const sa_scene* s);
 // z = M^-1 r on band 0: r is taken from s->r (masked here), the result is left as doubles in s->p[0]

@@ -110,6 +110,32 @@ struct RowPtr {
     __device__ __forceinline__ void step(unsigned long long bytes) { a += bytes; }
 };
 
+// Accesses predicated on bit k of a row mask.  SATFILL_RB_CXX_PRED = 1 writes them as C++ conditionals, which the
+// compiler turns into one LOP3-to-predicate + a predicated access (5 % fewer instructions than the asm forms, which need
+// the bit as a 0 / 1 register first) -- and which measured 15 % SLOWER on the GPU: the compiler then orders each load
+// next to its use instead of issuing all of a thread's loads back to back.  Kept as a switch; the asm forms are used.
+#ifndef SATFILL_RB_CXX_PRED
+#define SATFILL_RB_CXX_PRED 0
+#endif
+__device__ __forceinline__ float ldg_bit(const float* p, unsigned mask, int k)
+{
+    if (!SATFILL_RB_CXX_PRED)
+        return ldg_if(p, (mask >> k) & 1);
+    float v = 0.f;
+    if (mask & (1u << k))
+        v = __ldg(p);
+    return v;
+}
+__device__ __forceinline__ float2 ldg2_bit(const float* p, unsigned mask, int k)
+{
+    if (!SATFILL_RB_CXX_PRED)
+        return ldg2_if(p, (mask >> k) & 1);
+    float2 v = make_float2(0.f, 0.f);
+    if (mask & (1u << k))
+        v = __ldg(reinterpret_cast<const float2*>(p));
+    return v;
+}
+
 // predicated stores: one instruction, no branch
 __device__ __forceinline__ void stg_if(float* p, float v, unsigned pred)
 {
@@ -120,6 +146,25 @@ __device__ __forceinline__ void stg2_if(float* p, float x, float y, unsigned pre
     asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %3, 0;\n\t@q st.global.v2.f32 [%0], {%1, %2};\n\t}" ::"l"(p), "f"(x), "f"(y),
                  "r"(pred)
                  : "memory");
+}
+
+__device__ __forceinline__ void stg_bit(float* p, float v, unsigned mask, int k)
+{
+    if (!SATFILL_RB_CXX_PRED) {
+        stg_if(p, v, (mask >> k) & 1);
+        return;
+    }
+    if (mask & (1u << k))
+        *p = v;
+}
+__device__ __forceinline__ void stg2_bit(float* p, float x, float y, unsigned mask, int k)
+{
+    if (!SATFILL_RB_CXX_PRED) {
+        stg2_if(p, x, y, (mask >> k) & 1);
+        return;
+    }
+    if (mask & (1u << k))
+        *reinterpret_cast<float2*>(p) = make_float2(x, y);
 }
 
 }  // namespace
@@ -167,11 +212,11 @@ __global__ void __launch_bounds__(RB_HP * RB_DOWN_NG) k_rb_down(Level lf, Level 
         const unsigned ld = rm | bm;
 #pragma unroll
         for (int k = 0; k < RG; ++k, bp.step(pb), wp.step(pb)) {
-            float2 v = ldg2_if(bp.get(), (ld >> k) & 1);
+            float2 v = ldg2_bit(bp.get(), ld, k);
             bred[k] = (k & 1) ? v.y : v.x;
             bblk[k] = (k & 1) ? v.x : v.y;
             if (WINV) {
-                float2 w = ldg2_if(wp.get(), (ld >> k) & 1);
+                float2 w = ldg2_bit(wp.get(), ld, k);
                 wred[k] = (k & 1) ? w.y : w.x;
                 wblk[k] = (k & 1) ? w.x : w.y;
             } else {
@@ -202,7 +247,7 @@ __global__ void __launch_bounds__(RB_HP * RB_DOWN_NG) k_rb_down(Level lf, Level 
         for (int k = 0; k < RG; ++k, xo.step(pb2)) {
             float v = wred[k] * (((rm >> k) & 1) ? bred[k] : 0.f);
             R[sb + k * S] = v;
-            stg_if(xo.get(), v, (own >> k) & 1);
+            stg_bit(xo.get(), v, own, k);
         }
     }
     __syncthreads();
@@ -304,12 +349,12 @@ __global__ void __launch_bounds__(RB_HP * RB_UP_NG) k_rb_up(Level lf, Level lc, 
         const unsigned ld = own_red | on_blk;
 #pragma unroll
         for (int k = 0; k < RG; ++k, xp.step(pb2), bp.step(pb), wp.step(pb)) {
-            xv[k] = ldg_if(xp.get(), (rm >> k) & 1);
-            float2 v = ldg2_if(bp.get(), (ld >> k) & 1);
+            xv[k] = ldg_bit(xp.get(), rm, k);
+            float2 v = ldg2_bit(bp.get(), ld, k);
             bred[k] = (k & 1) ? v.y : v.x;
             bblk[k] = (k & 1) ? v.x : v.y;
             if (WINV) {
-                float2 w = ldg2_if(wp.get(), (ld >> k) & 1);
+                float2 w = ldg2_bit(wp.get(), ld, k);
                 wred[k] = (k & 1) ? w.y : w.x;
                 wblk[k] = (k & 1) ? w.x : w.y;
             } else {
@@ -379,7 +424,7 @@ __global__ void __launch_bounds__(RB_HP * RB_UP_NG) k_rb_up(Level lf, Level lc, 
             v = ((own_red >> k) & 1) ? v : 0.f;
             if (DOT)
                 acc += bred[k] * v;
-            stg2_if(xo.get(), (k & 1) ? vblk[k] : v, (k & 1) ? v : vblk[k], (st >> k) & 1);
+            stg2_bit(xo.get(), (k & 1) ? vblk[k] : v, (k & 1) ? v : vblk[k], st, k);
             n = c;
             c = s;
         }
