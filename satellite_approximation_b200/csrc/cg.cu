@@ -574,19 +574,24 @@ int solve_scene(sa_scene* s, const sa_options& o, sa_stats* stats)
     float* pbuf_f[2] = { (float*)s->p[0] + s->pitch + (int64_t)b0 * s->plane, (float*)s->p[1] + s->pitch + (int64_t)b0 * s->plane };
 
     SA_CUDA(ctx, cudaMemsetAsync(scal, 0, sizeof(BandScalars) * nb, ctx->stream));
-    if (have_tiles) {
-        if (poisson)
-            SA_LAUNCH(ctx, k_init_guess<true>, grid, block, 0, lv, u0, g0);
-        else
-            SA_LAUNCH(ctx, k_init_guess<false>, grid, block, 0, lv, u0, g0);
-    }
-    if (dist)  // the residual's stencil reads the iterate one row beyond the slice
-        SA_TRY(dist_halo<double>(s, 0, u0, s->pitch, s->plane, 1, 1));
-    if (have_tiles) {
-        if (poisson)
-            SA_LAUNCH(ctx, k_residual<true>, grid, block, 0, lv, u0, g0, r0, rb ? s->rb_rf() : nullptr, scal);
-        else
-            SA_LAUNCH(ctx, k_residual<false>, grid, block, 0, lv, u0, g0, r0, rb ? s->rb_rf() : nullptr, scal);
+    if (strip) {
+        // one pass: x0, r0 = b - A x0 from the KNOWN neighbours only (so no halo of x0 is needed), the three norms
+        SA_TRY(launch_setup2(ctx, lv, nb, poisson, u0, g0, r0, rb ? s->rb_rf() : nullptr, scal));
+    } else {
+        if (have_tiles) {
+            if (poisson)
+                SA_LAUNCH(ctx, k_init_guess<true>, grid, block, 0, lv, u0, g0);
+            else
+                SA_LAUNCH(ctx, k_init_guess<false>, grid, block, 0, lv, u0, g0);
+        }
+        if (dist)  // the residual's stencil reads the iterate one row beyond the slice
+            SA_TRY(dist_halo<double>(s, 0, u0, s->pitch, s->plane, 1, 1));
+        if (have_tiles) {
+            if (poisson)
+                SA_LAUNCH(ctx, k_residual<true>, grid, block, 0, lv, u0, g0, r0, rb ? s->rb_rf() : nullptr, scal);
+            else
+                SA_LAUNCH(ctx, k_residual<false>, grid, block, 0, lv, u0, g0, r0, rb ? s->rb_rf() : nullptr, scal);
+        }
     }
     if (dist) {
         SA_TRY(dist_reduce(s, DIST_SETUP, 0, -1));

@@ -68,6 +68,14 @@ __device__ __forceinline__ double ldnc_if(const double* p, unsigned pred)
         : "l"(p), "r"(pred));
     return v;
 }
+__device__ __forceinline__ double ld_if(const double* p, unsigned pred)  // data this kernel also writes: no .nc
+{
+    double v;
+    asm("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\tmov.f64 %0, 0d0000000000000000;\n\t@q ld.global.f64 %0, [%1];\n\t}"
+        : "=d"(v)
+        : "l"(p), "r"(pred));
+    return v;
+}
 __device__ __forceinline__ double2 ldnc2_if(const float* p, unsigned pred)  // float plane, widened
 {
     float x, y;
@@ -484,6 +492,139 @@ __global__ void __launch_bounds__(ST_THREADS, ST_UPD_CTAS) k_update2(Level lv, i
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// k_setup2: the set-up of a solve in one pass over the active tiles (replaces k_init_guess + k_residual of cg.cu):
+//   x0 (Laplace: 0, IterativeSolverBase.h:357-360; Poisson: the replacement image, poisson.cpp:239,257) written into
+//   the unknown cells of u;  r0 = b - A x0;  |b|^2, |r0|^2, r0.(r0/d)  (laplace.cpp:71-94 / poisson.cpp:241-251 for b,
+//   ConjugateGradient.h:38-61 for the rest).  With x0 = g the residual collapses to a sum over the KNOWN neighbours:
+//       r0_p = sum_{q in N(p) known} (f_q - g_q)        (Laplace: g = 0, so r0 = b)
+//       b_p  = d_p g_p - sum_{q in N(p)} g_q + sum_{q in N(p) known} f_q
+//   A neighbour outside the image is a "known" cell holding zeros (guard rows / columns), so it drops out by itself.
+//   Unknown cells of u hold whatever the previous fill left there: they are only ever used through the known mask.
+// ---------------------------------------------------------------------------------------------------------------
+template <bool POISSON, bool RF>
+__global__ void __launch_bounds__(ST_THREADS, 4) k_setup2(Level lv, int nbands, double* __restrict__ u,
+    const double* __restrict__ g, double* __restrict__ rvec, float* __restrict__ rf, BandScalars* __restrict__ scal)
+{
+    constexpr bool FIXED = !POISSON;
+    __shared__ double s_red[4];
+    const int cx = threadIdx.x & 15, row0 = (threadIdx.x >> 4) * ST_RG;
+    const int pitch = (int)lv.pitch;
+    const int toff = (row0 - 1) * pitch + 2 * cx;
+    const bool west = cx == 0, east = cx == 15;
+    for (int band = 0; band < nbands; ++band) {
+        BandScalars& sc = scal[band];
+        const int64_t band_off = (int64_t)band * lv.plane;
+        double* uband = u + band_off;
+        const double* gband = POISSON ? g + band_off : nullptr;
+        double* rband = rvec + band_off;
+        float* rfband = RF ? rf + band_off : nullptr;
+        double b2 = 0.0, r2 = 0.0, rz = 0.0;
+        auto no_prefetch = [](const TileBits&) {};
+        for_each_tile(lv, cx, row0, [&](const TileBits& tb, const TileBits&, bool, auto&) {
+            const int origin = tb.origin(pitch);
+            const unsigned mL = tb.mL(), mR = tb.mR(), any = tb.any();
+            // unknown bits of the columns west of the pair's left cell and east of its right cell, own rows
+            unsigned mW = __shfl_up_sync(0xffffffffu, mR, 1), mE = __shfl_down_sync(0xffffffffu, mL, 1);
+            if (west || east) {
+                const uint32_t w = __ldg(lv.tbitsT + ((size_t)(tb.ty() + 1) * lv.tb_stride + (tb.tx() + (west ? 0 : 2))) * 32 + (west ? 31 : 0));
+                const unsigned e = ((w >> row0) & 15u) << 1;
+                if (west)
+                    mW = e;
+                else
+                    mE = e;
+            }
+            const unsigned own = any & 0x1eu;  // own rows that hold an unknown of the pair
+            // rows to load: those, the rows above / below them, and the rows an adjacent lane's unknowns look at (u and g
+            // hold real pixel values at known cells, unlike the solver's work vectors)
+            const unsigned ldm = (own | (own << 1) | (own >> 1) | __shfl_up_sync(0xffffffffu, own, 1) | __shfl_down_sync(0xffffffffu, own, 1)) & 63u;
+            double* ub = uband + origin;
+            double2 uv[6], gv[6];
+            double ue[ST_RG], ge[ST_RG];
+#pragma unroll
+            for (int j = 0; j < 6; ++j) {
+                uv[j] = ld2_if(ub + (toff + j * pitch), (ldm >> j) & 1);
+                gv[j] = POISSON ? ldnc2_if(gband + origin + (toff + j * pitch), (ldm >> j) & 1) : make_double2(0.0, 0.0);
+            }
+            {
+                const int eoff = toff + (west ? -1 : 2);
+                const unsigned em = (west ? mL : (east ? mR : 0u)) >> 1;
+#pragma unroll
+                for (int j = 0; j < ST_RG; ++j) {
+                    ue[j] = ld_if(ub + (eoff + (j + 1) * pitch), (em >> j) & 1);
+                    ge[j] = POISSON ? ldnc_if(gband + origin + (eoff + (j + 1) * pitch), (em >> j) & 1) : 0.0;
+                }
+            }
+            const int64_t gr = (int64_t)tb.ty() * TILE_H + row0, gc = (int64_t)tb.tx() * TILE_W + 2 * cx;
+            const int dcL = diag_col<FIXED>(lv, gc), dcR = diag_col<FIXED>(lv, gc + 1);
+            const unsigned st2 = sector_or2(own), st4 = RF ? sector_or4(st2) : 0u;
+#pragma unroll
+            for (int j = 1; j <= ST_RG; ++j) {
+                double uw = __shfl_up_sync(0xffffffffu, uv[j].y, 1), ueast = __shfl_down_sync(0xffffffffu, uv[j].x, 1);
+                double gw = 0.0, geast = 0.0;
+                if (POISSON) {
+                    gw = __shfl_up_sync(0xffffffffu, gv[j].y, 1);
+                    geast = __shfl_down_sync(0xffffffffu, gv[j].x, 1);
+                }
+                if (west) {
+                    uw = ue[j - 1];
+                    gw = ge[j - 1];
+                }
+                if (east) {
+                    ueast = ue[j - 1];
+                    geast = ge[j - 1];
+                }
+                const int dr = diag_row<FIXED>(lv, gr - 1 + j);
+                // known-neighbour sums of f and of (f - g): north, south, west, east
+                auto knownsum = [&](double n, double s_, double w, double e, unsigned kn, unsigned ks, unsigned kw, unsigned ke) {
+                    return ((kn ? 0.0 : n) + (ks ? 0.0 : s_)) + ((kw ? 0.0 : w) + (ke ? 0.0 : e));
+                };
+                const unsigned nL = (mL >> (j - 1)) & 1, sL = (mL >> (j + 1)) & 1, wL = (mW >> j) & 1, eL = (mR >> j) & 1;
+                const unsigned nR = (mR >> (j - 1)) & 1, sR = (mR >> (j + 1)) & 1, wR = (mL >> j) & 1, eR = (mE >> j) & 1;
+                const double fL = knownsum(uv[j - 1].x, uv[j + 1].x, uw, uv[j].y, nL, sL, wL, eL);
+                const double fR = knownsum(uv[j - 1].y, uv[j + 1].y, uv[j].x, ueast, nR, sR, wR, eR);
+                double bL = fL, bR = fR, resL = fL, resR = fR;
+                if (POISSON) {
+                    const double kgL = knownsum(gv[j - 1].x, gv[j + 1].x, gw, gv[j].y, nL, sL, wL, eL);
+                    const double kgR = knownsum(gv[j - 1].y, gv[j + 1].y, gv[j].x, geast, nR, sR, wR, eR);
+                    const double divL = (double)(dr + dcL) * gv[j].x - ((gv[j - 1].x + gv[j + 1].x) + (gw + gv[j].y));
+                    const double divR = (double)(dr + dcR) * gv[j].y - ((gv[j - 1].y + gv[j + 1].y) + (gv[j].x + geast));
+                    bL = divL + fL;
+                    bR = divR + fR;
+                    resL = fL - kgL;
+                    resR = fR - kgR;
+                }
+                const bool unkL = (mL >> j) & 1, unkR = (mR >> j) & 1;
+                if (!unkL)
+                    bL = resL = 0.0;
+                if (!unkR)
+                    bR = resR = 0.0;
+                b2 += bL * bL + bR * bR;
+                r2 += resL * resL + resR * resR;
+                rz += resL * resL * inv_of(dr + dcL) + resR * resR * inv_of(dr + dcR);
+                const int off = toff + j * pitch;
+                if ((st2 >> j) & 1) {
+                    // x0 into the unknown cells; a known cell of the sector is written back as read
+                    double2 xn = make_double2(unkL ? (POISSON ? gv[j].x : 0.0) : uv[j].x, unkR ? (POISSON ? gv[j].y : 0.0) : uv[j].y);
+                    *reinterpret_cast<double2*>(ub + off) = xn;
+                    *reinterpret_cast<double2*>(rband + origin + off) = make_double2(resL, resR);
+                }
+                if (RF && ((st4 >> j) & 1))
+                    *reinterpret_cast<float2*>(rfband + origin + off) = make_float2((float)resL, (float)resR);
+            }
+        }, no_prefetch);
+        double t = block_sum4(b2, s_red);
+        if (threadIdx.x == 0 && t != 0.0)
+            atomicAdd(&sc.bnorm2, t);
+        t = block_sum4(r2, s_red);
+        if (threadIdx.x == 0 && t != 0.0)
+            atomicAdd(&sc.rr[0], t);
+        t = block_sum4(rz, s_red);
+        if (threadIdx.x == 0 && t != 0.0)
+            atomicAdd(&sc.rz[0], t);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // k_scrub: zero work vectors at the unknowns of a level (whole sectors).  Run through the tile list of the PREVIOUS
 // mask when the mask changes: a solve leaves its work vectors non-zero only at its own unknowns, so this restores the
 // "zero outside the unknown set" invariant for any new mask at a third of the bytes of clearing the planes.
@@ -525,6 +666,26 @@ static unsigned strip_grid(const sa_ctx* ctx, const Level& lv, int ctas_per_sm)
 {
     int g = ctx->sm_count * ctas_per_sm;
     return (unsigned)(g < lv.n_tiles ? g : lv.n_tiles);
+}
+
+int launch_setup2(sa_ctx* ctx, const Level& lv, int nbands, bool poisson, double* u, const double* g, double* r, float* rf,
+    BandScalars* scal)
+{
+    if (lv.n_tiles == 0)
+        return SA_OK;
+    const unsigned grid = strip_grid(ctx, lv, 4);
+    if (poisson) {
+        if (rf)
+            SA_LAUNCH(ctx, (k_setup2<true, true>), grid, ST_THREADS, 0, lv, nbands, u, g, r, rf, scal);
+        else
+            SA_LAUNCH(ctx, (k_setup2<true, false>), grid, ST_THREADS, 0, lv, nbands, u, g, r, rf, scal);
+    } else {
+        if (rf)
+            SA_LAUNCH(ctx, (k_setup2<false, true>), grid, ST_THREADS, 0, lv, nbands, u, g, r, rf, scal);
+        else
+            SA_LAUNCH(ctx, (k_setup2<false, false>), grid, ST_THREADS, 0, lv, nbands, u, g, r, rf, scal);
+    }
+    return SA_OK;
 }
 
 int launch_direction2(sa_ctx* ctx, const Level& lv, int nbands, bool jacobi, const void* zin, bool z_is_float,

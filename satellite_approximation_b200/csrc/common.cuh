@@ -296,6 +296,8 @@ Level fine_level(const sa_scene* s);
 int precondition_scene(sa_scene* s, const sa_options& o);
 
 // ---- cg_strip.cu: the two kernels of a CG iteration, shared-memory-free generation ---------------------------------
+int launch_setup2(sa_ctx* ctx, const Level& lv, int nbands, bool poisson, double* u, const double* g, double* r, float* rf,
+    BandScalars* scal);
 int launch_direction2(sa_ctx* ctx, const Level& lv, int nbands, bool jacobi, const void* zin, bool z_is_float,
     const void* p_old, void* p_new, bool p_is_float, BandScalars* scal, int k);
 int launch_update2(sa_ctx* ctx, const Level& lv, int nbands, bool jacobi, double* u, const void* p, bool p_is_float, double* r,
