@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define SATFILL_ABI_VERSION 2
+#define SATFILL_ABI_VERSION 3
 
 typedef enum sa_status {
     SA_OK = 0,
@@ -197,6 +197,25 @@ int sa_dist_levels(int64_t rows, int world);
 int sa_scene_set_distributed(sa_scene* scene, int on);
 int sa_scene_owned_rows(const sa_scene* scene, int64_t* lo, int64_t* hi, int* axis);
 int sa_scene_allgather_band(sa_scene* scene, int band);
+
+/* ---- the steps either side of the path (next rows) ------------------------------------------------------- */
+
+/* approx::apply_laplace (lib/approx/source/laplace.cpp:134-168), the body of laplace_main
+ * (executables/laplace-main.cpp:34-40).  `image` and `invalid` are interleaved 8-bit images as cv::imread(IMREAD_COLOR)
+ * returns them: rows x cols x channels bytes, channel order B, G, R, channels == 3.  Invalid pixels are those of
+ * `invalid` with R >= red_threshold and G <= 150 (laplace.cpp:141-146); every channel of `image` is filled over that
+ * mask in one batched solve (the reference re-assembles and solves per channel, laplace.cpp:152-162).  `out` receives
+ * rows x cols x channels doubles, interleaved like the CV_64FC3 matrix the reference returns (laplace.cpp:159-167);
+ * `mask_out` (optional) rows x cols bytes.  stats: `channels` entries (optional).  Border semantics as sa_laplace_fill. */
+int sa_apply_laplace_u8(sa_ctx* ctx, const uint8_t* image, const uint8_t* invalid, int64_t rows, int64_t cols, int channels,
+    double red_threshold, double* out, uint8_t* mask_out, const sa_options* opts, sa_stats* stats);
+
+/* preprocess_cloud_band (executables/poisson-main.cpp:10-21): cv::morphologyEx(MORPH_CLOSE) of a float64 band with a
+ * (2 radius + 1)^2 rectangle (poisson_main: radius 5), then MatX<f64>::cast<bool>().  Dilation then erosion, windows
+ * clipped at the image border (OpenCV's default border value for morphology leaves outside pixels out of the max / min).
+ * mask_out has the band's layout (same element strides), one byte per pixel: 1 where the closed band is non-zero. */
+int sa_morph_close_mask(sa_ctx* ctx, const double* band, int64_t rows, int64_t cols, int64_t row_stride, int64_t col_stride,
+    int radius, uint8_t* mask_out);
 
 #ifdef __cplusplus
 }

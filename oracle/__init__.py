@@ -249,3 +249,54 @@ def ref() -> Ref | None:
     if _ref is None and os.path.exists(_REF_SO):
         _ref = Ref()
     return _ref
+
+
+# ---- the steps either side of the path ------------------------------------------------------------------
+def rgb_invalid_mask(invalid_bgr: np.ndarray, red_threshold: float = 220.0) -> np.ndarray:
+    """laplace.cpp:141-146: channels_cv[2] (red of a cv::imread BGR image) >= red_threshold and channels_cv[1]
+    (green) <= 150, compared as doubles."""
+    red = invalid_bgr[..., 2].astype(np.float64)
+    green = invalid_bgr[..., 1].astype(np.float64)
+    return (red >= red_threshold) & (green <= 150)
+
+
+def apply_laplace(image_bgr: np.ndarray, invalid_bgr: np.ndarray, red_threshold: float = 220.0, engine=None, **kw):
+    """Restatement of approx::apply_laplace (laplace.cpp:134-168): mask from the invalid image, every channel of the base
+    image widened to double (cv2eigen) and filled on its own (fill_missing_portion_smooth_boundary), channels merged
+    back (CV_64FC3).  `engine`: a Port (default, reduced system: border pixels are Dirichlet data) or a Ref."""
+    mask = rgb_invalid_mask(invalid_bgr, red_threshold)
+    eng = engine if engine is not None else port()
+    out = np.empty(image_bgr.shape, np.float64)
+    for k in range(image_bgr.shape[2]):
+        ch = np.ascontiguousarray(image_bgr[..., k].astype(np.float64))
+        if isinstance(eng, Port):
+            filled, _ = eng.laplace_fill(ch, mask, mode=1, **kw)
+        else:
+            filled, _ = eng.laplace_fill(ch, mask, **kw)
+        out[..., k] = filled
+    return out, mask
+
+
+def morph_close_mask(band: np.ndarray, radius: int = 5) -> np.ndarray:
+    """Restatement of preprocess_cloud_band (executables/poisson-main.cpp:10-21): cv::morphologyEx(MORPH_CLOSE) with a
+    (2 radius + 1)^2 MORPH_RECT element = dilation then erosion, both with OpenCV's default border for morphology
+    (pixels outside the image never win the max / min: the window is clipped), then MatX<f64>::cast<bool>().
+    Pinned against cv2 itself by tests/golden/prepost_cases.npz (oracle/make_golden.py)."""
+    a = np.asarray(band, np.float64)
+    rows, cols = a.shape
+
+    def run(x, axis, fn, fill):
+        pad = [(0, 0), (0, 0)]
+        pad[axis] = (radius, radius)
+        p = np.pad(x, pad, constant_values=fill)
+        out = None
+        for k in range(2 * radius + 1):
+            sl = [slice(None), slice(None)]
+            sl[axis] = slice(k, k + x.shape[axis])
+            v = p[tuple(sl)]
+            out = v.copy() if out is None else fn(out, v)
+        return out
+
+    d = run(run(a, 1, np.maximum, -np.inf), 0, np.maximum, -np.inf)
+    e = run(run(d, 1, np.minimum, np.inf), 0, np.minimum, np.inf)
+    return e != 0.0

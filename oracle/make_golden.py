@@ -97,6 +97,29 @@ def main() -> None:
         laplace_iters=np.int64(st.iterations),
         poisson_unknowns=np.stack([unknown_values(np.ascontiguousarray(o), crop_mask) for o in poi]),
     )
+    # ---- 4. the steps either side of the path: apply_laplace on a crop of the sample scene, and
+    #         preprocess_cloud_band's morphological close pinned against OpenCV itself (cv2 exists in this container only)
+    rng = np.random.default_rng(7)
+    pre = {}
+    inv = png[r0 : r0 + 256, c0 : c0 + 256, :3].copy()  # B, G, R as cv::imread(IMREAD_COLOR) returns them
+    inv[0, :] = inv[-1, :] = 0  # keep the marked region off the crop's border
+    inv[:, 0] = inv[:, -1] = 0
+    b02 = cv2.imread(os.path.join(SCENE, "B02.tif"), cv2.IMREAD_UNCHANGED)
+    b03 = cv2.imread(os.path.join(SCENE, "B03.tif"), cv2.IMREAD_UNCHANGED)
+    base = np.stack([np.clip(x[r0 : r0 + 256, c0 : c0 + 256] / 12.0, 0, 255).astype(np.uint8) for x in (b02, b03, b04)], axis=-1)
+    want, m = oracle.apply_laplace(base, inv, 220.0, engine=ref, tol=0.0, max_it=0)  # the reference's Eigen, per channel
+    pre["al_image"], pre["al_invalid"], pre["al_out"], pre["al_mask"] = base, inv, want, m
+    kernel = cv2.getStructuringElement(cv2.MORPH_RECT, (11, 11))  # poisson-main.cpp:13-16, dilation_size 5
+    cld = cv2.imread(os.path.join(SCENE, "CLD.tif"), cv2.IMREAD_UNCHANGED).astype(np.float64)
+    bands = [cld[400:700, 300:650].copy(), (rng.random((97, 130)) < 0.08).astype(np.float64) * rng.integers(1, 100, (97, 130)),
+             (rng.random((40, 33)) < 0.5).astype(np.float64), np.zeros((20, 20)), rng.standard_normal((64, 5)) * (rng.random((64, 5)) < 0.3)]
+    for i, bnd in enumerate(bands):
+        closed = cv2.morphologyEx(bnd, cv2.MORPH_CLOSE, kernel)
+        pre[f"mc{i}_band"] = bnd
+        pre[f"mc{i}_mask"] = closed != 0
+        assert np.array_equal(oracle.morph_close_mask(bnd, 5), closed != 0), i  # the restatement against OpenCV
+    np.savez_compressed(os.path.join(OUT, "prepost_cases.npz"), **pre)
+    print("apply_laplace crop: masked", int(m.sum()), "morph cases", len(bands))
     print("crop unknowns", int(crop_mask.sum()), "laplace iters", st.iterations, "poisson iters", pst[0].iterations)
     for fn in sorted(os.listdir(OUT)):
         print(fn, os.path.getsize(os.path.join(OUT, fn)))

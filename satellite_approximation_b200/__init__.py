@@ -45,7 +45,7 @@ __all__ = [
     "LogLevel", "set_log_level", "filling_missing_portions_smooth_boundaries", "blend_images_poisson",
     "find_connected_components", "ConnectedComponents", "mask_scan", "unknown_numbering", "valid_neighbours",
     "Context", "Scene", "SolveStats", "default_context", "set_solver_defaults", "last_perf_info",
-    "dist_partition", "dist_levels", "LAPLACE", "POISSON", "JACOBI", "MULTIGRID", "MG_RB32", "MG_JACOBI64", "SatfillError",
+    "dist_partition", "dist_levels", "apply_laplace", "preprocess_cloud_band", "LAPLACE", "POISSON", "JACOBI", "MULTIGRID", "MG_RB32", "MG_JACOBI64", "SatfillError",
 ]  # fmt: skip
 
 _log = logging.getLogger("satellite_approximation_b200")
@@ -273,6 +273,41 @@ class Context:
         self._check(st, ok=(SA_OK, SA_EMPTY_MASK, SA_NOT_CONVERGED))
         return [SolveStats(s.as_dict()) for s in stats]
 
+    def apply_laplace(self, image: np.ndarray, invalid_image: np.ndarray, red_threshold: float = 220.0, **opts):
+        """approx::apply_laplace (laplace.cpp:134-168): `image`, `invalid_image` uint8 H x W x 3 in cv::imread order
+        (B, G, R).  Returns (filled float64 H x W x 3, bool mask H x W, per-channel SolveStats)."""
+        if image.dtype != np.uint8 or invalid_image.dtype != np.uint8 or image.ndim != 3 or image.shape[2] != 3:
+            raise TypeError("apply_laplace: uint8 H x W x 3 images (cv::imread(IMREAD_COLOR))")
+        if image.shape != invalid_image.shape:
+            raise RuntimeError("Input image and mask are not the same size")  # laplace.cpp:124-127
+        img = np.ascontiguousarray(image)
+        inv = np.ascontiguousarray(invalid_image)
+        rows, cols, ch = img.shape
+        out = np.empty((rows, cols, ch), np.float64)
+        mask = np.empty((rows, cols), np.uint8)
+        stats = (_capi.Stats * ch)()
+        o = self.options(LAPLACE, **opts)
+        with self._lock:
+            st = self._lib.sa_apply_laplace_u8(self._h, img.ctypes.data, inv.ctypes.data, rows, cols, ch, float(red_threshold),
+                                               out.ctypes.data, mask.ctypes.data, C.byref(o), stats)  # fmt: skip
+        self._check(st, ok=(SA_OK, SA_EMPTY_MASK, SA_NOT_CONVERGED))
+        if st == SA_EMPTY_MASK:
+            out[...] = img
+            mask[...] = 0
+        return out, mask.astype(bool), [SolveStats(s.as_dict()) for s in stats]
+
+    def morph_close_mask(self, band: np.ndarray, radius: int = 5) -> np.ndarray:
+        """preprocess_cloud_band (poisson-main.cpp:10-21): MORPH_CLOSE with a (2 radius + 1)^2 rectangle, cast to bool."""
+        if band.dtype != np.float64 or band.ndim != 2:
+            raise TypeError("morph_close_mask: a 2-D float64 band")
+        rs, cs = _capi.element_strides(band)
+        rows, cols = band.shape
+        mask = np.empty(band.shape, np.uint8, order="F" if (rs == 1 and rows > 1) else "C")
+        with self._lock:
+            st = self._lib.sa_morph_close_mask(self._h, band.ctypes.data, rows, cols, rs, cs, int(radius), mask.ctypes.data)
+        self._check(st)
+        return mask.astype(bool)
+
     def scene(self, problem: int, rows: int, cols: int, nbands: int = 1) -> "Scene":
         return Scene(self, problem, rows, cols, nbands)
 
@@ -373,6 +408,23 @@ def dist_partition(rows: int, world: int, levels: int) -> list[int]:
 def dist_levels(rows: int, world: int) -> int:
     """Number of multigrid levels the distributed solver splits by rows for a scene of `rows` rows (sa_dist_levels)."""
     return int(_capi.load().sa_dist_levels(int(rows), int(world)))
+
+
+def apply_laplace(image: np.ndarray, invalid_image: np.ndarray, red_threshold: float = 220.0) -> np.ndarray:
+    """approx::apply_laplace (lib/approx/include/approx/laplace.h:31, laplace.cpp:134-168): the body of `laplace_main`.
+    uint8 H x W x 3 images in cv::imread order; returns the float64 H x W x 3 matrix the reference returns."""
+    opts = {}
+    if _defaults.get("laplace_tolerance") is not None:
+        opts["tolerance"] = _defaults["laplace_tolerance"]
+    if _defaults.get("precond") is not None:
+        opts["precond"] = _defaults["precond"]
+    return default_context().apply_laplace(image, invalid_image, red_threshold, **opts)[0]
+
+
+def preprocess_cloud_band(cloud_band: np.ndarray, dilation_size: int = 5) -> np.ndarray:
+    """preprocess_cloud_band of poisson_main (executables/poisson-main.cpp:10-21): 11 x 11 morphological close of the
+    cloud band, cast to bool -- the mask poisson_main hands to blend_images_poisson."""
+    return default_context().morph_close_mask(np.asarray(cloud_band), dilation_size)
 
 
 _default_ctx: Optional[Context] = None

@@ -752,4 +752,123 @@ int sa_poisson_blend(sa_ctx* ctx, double* const* inputs, const double* const* re
     return host_fill(ctx, SA_POISSON, inputs, replacements, nbands, mask, rows, cols, row_stride, col_stride, opts, stats);
 }
 
+/* ---- the steps either side of the path ------------------------------------------------------------------------------ */
+
+int sa_apply_laplace_u8(sa_ctx* ctx, const uint8_t* image, const uint8_t* invalid, int64_t rows, int64_t cols, int channels,
+    double red_threshold, double* out, uint8_t* mask_out, const sa_options* opts, sa_stats* stats)
+{
+    SA_TRY(check_ctx(ctx));
+    if (!image || !invalid || !out || rows < 0 || cols < 0)
+        return fail(ctx, SA_BAD_ARGUMENT, "apply_laplace: bad arguments");
+    if (channels != 3)
+        return fail(ctx, SA_BAD_ARGUMENT, "apply_laplace: cv::imread(IMREAD_COLOR) images have 3 channels");
+    if (rows * cols == 0)
+        return SA_EMPTY_MASK;
+    // the cached scene of the host-pointer entry points, row-major like cv::Mat
+    sa_ctx_cache* cache = cache_of(ctx);
+    sa_scene* s = cache->scene;
+    if (s && (s->problem != SA_LAPLACE || s->user_rows != rows || s->user_cols != cols || s->nbands != channels || s->transposed)) {
+        cudaStreamSynchronize(ctx->stream);
+        scene_free(s);
+        s = cache->scene = nullptr;
+    }
+    if (!s) {
+        SA_TRY(sa_scene_create(ctx, SA_LAPLACE, rows, cols, channels, &s));
+        int st = scene_alloc(s, false);
+        if (st != SA_OK) {
+            scene_free(s);
+            return st;
+        }
+        cache->scene = s;
+    }
+    const size_t nbytes = (size_t)rows * cols * channels;
+    uint8_t* d_u8 = nullptr;
+    double* d_out = nullptr;
+    SA_CUDA(ctx, cudaMalloc(&d_u8, 2 * nbytes));
+    if (cudaMalloc(&d_out, nbytes * sizeof(double)) != cudaSuccess) {
+        cudaFree(d_u8);
+        return fail(ctx, SA_OUT_OF_MEMORY, "apply_laplace: output staging");
+    }
+    auto cleanup = [&](int st) {
+        cudaStreamSynchronize(ctx->stream);
+        cudaFree(d_u8);
+        cudaFree(d_out);
+        return st;
+    };
+    if (cudaMemcpyAsync(d_u8, image, nbytes, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess
+        || cudaMemcpyAsync(d_u8 + nbytes, invalid, nbytes, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess)
+        return cleanup(fail(ctx, SA_CUDA_ERROR, "apply_laplace: upload"));
+    int st = split_u8_scene(s, d_u8, d_u8 + nbytes, channels, red_threshold);
+    if (st != SA_OK)
+        return cleanup(st);
+    s->mask_set = true;
+    s->indexed = false;
+    sa_options o;
+    if (opts)
+        o = *opts;
+    else
+        sa_default_options(&o, SA_LAPLACE);
+    if (!(o.tolerance > 0.0))
+        o.tolerance = DBL_EPSILON;
+    st = solve_scene(s, o, stats);
+    if (st != SA_OK && st != SA_NOT_CONVERGED && st != SA_EMPTY_MASK)  // Laplace never looks at the solver status
+        return cleanup(st);
+    int st2 = merge_f64_scene(s, channels, d_out);
+    if (st2 != SA_OK)
+        return cleanup(st2);
+    if (cudaMemcpyAsync(out, d_out, nbytes * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess)
+        return cleanup(fail(ctx, SA_CUDA_ERROR, "apply_laplace: download"));
+    if (mask_out
+        && cudaMemcpy2DAsync(mask_out, (size_t)cols, s->mask0(s->mask), (size_t)s->pitch, (size_t)cols, (size_t)rows,
+               cudaMemcpyDeviceToHost, ctx->stream)
+            != cudaSuccess)
+        return cleanup(fail(ctx, SA_CUDA_ERROR, "apply_laplace: mask download"));
+    return cleanup(st);
+}
+
+int sa_morph_close_mask(sa_ctx* ctx, const double* band, int64_t rows, int64_t cols, int64_t row_stride, int64_t col_stride,
+    int radius, uint8_t* mask_out)
+{
+    SA_TRY(check_ctx(ctx));
+    if (!band || !mask_out || rows < 0 || cols < 0 || radius < 0)
+        return fail(ctx, SA_BAD_ARGUMENT, "morph_close_mask: bad arguments");
+    if (rows * cols == 0)
+        return SA_OK;
+    Layout lay = classify(rows, cols, row_stride, col_stride);
+    if (lay == LAYOUT_BAD)
+        return fail(ctx, SA_BAD_ARGUMENT, "strides: one of row_stride / col_stride must be 1");
+    // a rectangle is transposition-symmetric: work on the buffer as it lies (slow x fast)
+    const bool col_major = lay == LAYOUT_COL_MAJOR;
+    const int64_t slow = col_major ? cols : rows, fast = col_major ? rows : cols;
+    const int64_t sp = col_major ? col_stride : row_stride;  // host elements between slow-axis neighbours
+    const size_t n = (size_t)slow * fast;
+    double *d_a = nullptr, *d_b = nullptr;
+    uint8_t* d_m = nullptr;
+    SA_CUDA(ctx, cudaMalloc(&d_a, n * sizeof(double)));
+    if (cudaMalloc(&d_b, n * sizeof(double)) != cudaSuccess || cudaMalloc(&d_m, n) != cudaSuccess) {
+        cudaFree(d_a);
+        cudaFree(d_b);
+        return fail(ctx, SA_OUT_OF_MEMORY, "morph_close_mask: staging");
+    }
+    auto cleanup = [&](int st) {
+        cudaStreamSynchronize(ctx->stream);
+        cudaFree(d_a);
+        cudaFree(d_b);
+        cudaFree(d_m);
+        return st;
+    };
+    if (cudaMemcpy2DAsync(d_a, (size_t)fast * sizeof(double), band, (size_t)(slow > 1 ? sp : fast) * sizeof(double),
+            (size_t)fast * sizeof(double), (size_t)slow, cudaMemcpyHostToDevice, ctx->stream)
+        != cudaSuccess)
+        return cleanup(fail(ctx, SA_CUDA_ERROR, "morph_close_mask: upload"));
+    int st = morph_close_mask(ctx, d_a, d_b, slow, fast, radius, d_m);
+    if (st != SA_OK)
+        return cleanup(st);
+    if (cudaMemcpy2DAsync(mask_out, (size_t)(slow > 1 ? sp : fast), d_m, (size_t)fast, (size_t)fast, (size_t)slow,
+            cudaMemcpyDeviceToHost, ctx->stream)
+        != cudaSuccess)
+        return cleanup(fail(ctx, SA_CUDA_ERROR, "morph_close_mask: download"));
+    return cleanup(SA_OK);
+}
+
 }  // extern "C"

@@ -314,6 +314,11 @@ struct ScrubPlanes {
 };
 int launch_scrub(sa_ctx* ctx, const Level& lv, int nbands, const ScrubPlanes& planes);
 
+// ---- prepost.cu: the steps either side of the path
+int split_u8_scene(sa_scene* s, const uint8_t* d_image, const uint8_t* d_invalid, int channels, double red_threshold);
+int merge_f64_scene(sa_scene* s, int channels, double* d_out);
+int morph_close_mask(sa_ctx* ctx, double* d_a, double* d_b, int64_t slow, int64_t fast, int radius, uint8_t* d_mask);
+
 // ---- dist.cu: row decomposition of one system across GPUs -------------------------------------------------------------
 enum DistWhat { DIST_SETUP = 0, DIST_RZ = 1, DIST_PQ = 2, DIST_RR = 3, DIST_RR_RZ = 4 };
 void dist_partition(int64_t rows, int world, int levels, int64_t* row_begin);

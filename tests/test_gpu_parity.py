@@ -538,3 +538,54 @@ def test_rb_multigrid_tiny_and_degenerate_scenes(ctx, port):
         st = ctx.poisson_blend(work, [g], mask, tolerance=1e-12, max_iterations=100000, precond=sab.MULTIGRID)
         if np.isfinite(want[0]).all() and st[0]["status"] == sab.SA_OK:
             assert rel_max_abs(work[0], want[0], mask) < 1e-6, shape
+
+
+# ---- the steps either side of the path --------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def prepost_cases():
+    import os
+
+    from conftest import GOLDEN
+
+    return dict(np.load(os.path.join(GOLDEN, "prepost_cases.npz")))
+
+
+def test_morph_close_mask_bit_exact(ctx, prepost_cases):
+    """preprocess_cloud_band (poisson-main.cpp:10-21): bit-exact against cv2.morphologyEx goldens, in both memory orders
+    (a rectangle is transposition-symmetric: the library works on the buffer as it lies), and against the oracle on a
+    large random band."""
+    import oracle
+
+    for i in range(5):
+        band, want = prepost_cases[f"mc{i}_band"], prepost_cases[f"mc{i}_mask"]
+        for order in ("C", "F"):
+            got = ctx.morph_close_mask(np.array(band, order=order, copy=True), 5)
+            assert got.dtype == bool and np.array_equal(got, want), (i, order)
+    rng = np.random.default_rng(1)
+    big = (rng.random((1500, 2100)) < 0.02) * rng.standard_normal((1500, 2100))
+    for radius in (0, 1, 5, 9):
+        assert np.array_equal(ctx.morph_close_mask(big, radius), oracle.morph_close_mask(big, radius)), radius
+    assert np.array_equal(sab.preprocess_cloud_band(prepost_cases["mc0_band"]), prepost_cases["mc0_mask"])
+    with pytest.raises(TypeError):
+        ctx.morph_close_mask(big.astype(np.float32))
+
+
+def test_apply_laplace_vs_reference_eigen(ctx, prepost_cases):
+    """approx::apply_laplace (laplace.cpp:134-168) on a crop of the reference's sample scene: mask bit-exact, the three
+    channels filled in one batched solve within the parity tolerance of the reference's per-channel Eigen solves."""
+    img, inv, want, mask = (prepost_cases[k] for k in ("al_image", "al_invalid", "al_out", "al_mask"))
+    out, got_mask, st = ctx.apply_laplace(img, inv, 220.0, tolerance=1e-6, precond=sab.MULTIGRID)
+    assert np.array_equal(got_mask, mask)
+    assert out.shape == img.shape and out.dtype == np.float64 and len(st) == 3
+    for k in range(3):
+        assert st[k]["status"] == sab.SA_OK and st[k]["unknowns"] == int(mask.sum())
+        assert rel_max_abs(out[..., k], want[..., k], mask) < PARITY_TOL  # at the benchmark's 1e-6 residual
+        assert np.array_equal(out[..., k][~mask], img[..., k][~mask].astype(np.float64))
+    tight, _, _ = ctx.apply_laplace(img, inv, 220.0, tolerance=1e-12, precond=sab.JACOBI)
+    for k in range(3):
+        assert rel_max_abs(tight[..., k], want[..., k], mask) < 1e-8
+    # a threshold nothing reaches: no invalid pixel, the image comes back widened (laplace.cpp:41-44)
+    same, m0, _ = ctx.apply_laplace(img, inv, 256.0)
+    assert not m0.any() and np.array_equal(same, img.astype(np.float64))
+    with pytest.raises(RuntimeError):
+        ctx.apply_laplace(img, inv[:-1], 220.0)
