@@ -18,6 +18,11 @@ struct PerfInfo {  // poisson.h:12-21
     void write(fs::path const& output) const;  // appends one CSV line (poisson.cpp:14-19)
 };
 
+// Offset / white-key overload (poisson.h:30-33, poisson.cpp:21-143): the replacement image is pasted at
+// (start_row, start_column); its unknowns are the pixels that are NOT the white key (MultiChannelImage::valid_pixel).
+// The reference solves with a direct factorisation; here the system goes through the same CG (tolerance 1e-12).
+void blend_images_poisson(MultiChannelImage& input_images, MultiChannelImage const& replacement_images, int start_row,
+    int start_column);
 void blend_images_poisson(MultiChannelImage& input_images, MultiChannelImage const& replacement_images,
     MatX<bool> const& invalid_mask, f64 tolerance = 1e-6, std::optional<int> max_iterations = {});
 std::vector<MatX<f64>> blend_images_poisson(std::vector<MatX<f64>> const& input_images,

@@ -5,6 +5,7 @@
 
 #include <satfill.h>
 
+#include <climits>
 #include <cstdio>
 #include <fstream>
 #include <mutex>
@@ -113,6 +114,47 @@ void blend_images_poisson(MultiChannelImage& input_images, MultiChannelImage con
         std::fprintf(stderr, "[approx] Failed to solve the linear system: no convergence\n");
     else if (rc != SA_OK && rc != SA_EMPTY_MASK)
         std::fprintf(stderr, "[approx] %s\n", sa_last_error(c.h));
+}
+
+void blend_images_poisson(MultiChannelImage& input_images, MultiChannelImage const& replacement_images, int start_row,
+    int start_column)
+{
+    // the three sanity checks of poisson.cpp:25-39: log and return
+    if (input_images.images.empty() || replacement_images.images.size() < 3
+        || replacement_images.images.size() < input_images.images.size())
+        return;
+    const Eigen::Index R = replacement_images.rows(), C = replacement_images.cols();
+    if (replacement_images.size() > input_images.size()) {
+        std::fprintf(stderr, "[approx] Cannot solve problem: replacement image is larger than the input image\n");
+        return;
+    }
+    if (start_row < 0 || start_column < 0 || start_row >= input_images.rows() || start_column >= input_images.cols()) {
+        std::fprintf(stderr, "[approx] Cannot solve problem: row/column is out of bounds\n");
+        return;
+    }
+    if (start_row + R > input_images.rows() || start_column + C > input_images.cols()) {
+        std::fprintf(stderr, "[approx] Cannot solve problem: replacement image goes beyond the bounds of the input image\n");
+        return;
+    }
+    // The system lives in the replacement's own rectangle (neighbours outside it are dropped, poisson.cpp:76,108), its
+    // unknowns are the non-key pixels, its boundary values come from the input at the offset: exactly the mask overload
+    // on the crop.
+    MatX<bool> unknown(R, C);
+    for (Eigen::Index col = 0; col < C; ++col)
+        for (Eigen::Index row = 0; row < R; ++row)
+            unknown(row, col) = replacement_images.valid_pixel(row, col);
+    const size_t nb = input_images.images.size();
+    MultiChannelImage crop, repl;
+    for (size_t b = 0; b < nb; ++b) {
+        crop.images.push_back(input_images.images[b].block(start_row, start_column, R, C));
+        repl.images.push_back(replacement_images.images[b]);
+    }
+    blend_images_poisson(crop, repl, unknown, 1e-12, std::optional<int>(INT_MAX / 2));
+    for (size_t b = 0; b < nb; ++b)  // poisson.cpp:126-139: only the unknowns are written
+        for (Eigen::Index col = 0; col < C; ++col)
+            for (Eigen::Index row = 0; row < R; ++row)
+                if (unknown(row, col))
+                    input_images.images[b](start_row + row, start_column + col) = crop.images[b](row, col);
 }
 
 std::vector<MatX<f64>> blend_images_poisson(std::vector<MatX<f64>> const& input_images,

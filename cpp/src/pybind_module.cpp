@@ -35,6 +35,25 @@ PYBIND11_MODULE(_core, m)
             std::optional<int>>(&approx::blend_images_poisson),
         "input_image"_a, "replacement_image"_a, "invalid_mask"_a, "tolerance"_a = 1e-6, "max_iterations"_a = std::nullopt,
         py::call_guard<py::gil_scoped_release>());
+    // not bound by the reference (its offset overload is only reachable from C++, poisson.h:30-33): exposed so that the
+    // parity tests can drive the C++ shim's implementation of it
+    m.def(
+        "blend_images_poisson_offset",
+        [](std::vector<MatX<f64>> input_images, std::vector<MatX<f64>> const& replacement_images, int start_row,
+            int start_column) {
+            py::gil_scoped_release release;
+            approx::MultiChannelImage input(std::move(input_images)), replacement(replacement_images);
+            approx::blend_images_poisson(input, replacement, start_row, start_column);
+            return input.images;
+        },
+        "input_image"_a, "replacement_image"_a, "start_row"_a, "start_column"_a);
+    m.def(
+        "find_connected_components",
+        [](MatX<bool> const& invalid) {
+            approx::ConnectedComponents cc = approx::find_connected_components(invalid);
+            return py::make_tuple(cc.matrix, cc.region_map.size());
+        },
+        py::arg("invalid_pixels").noconvert());
     m.def("set_laplace_options", [](double tolerance, long max_iterations, bool multigrid) {
         approx::set_laplace_options({ tolerance, max_iterations, multigrid });
     }, "tolerance"_a = 0.0, "max_iterations"_a = 0, "multigrid"_a = false);

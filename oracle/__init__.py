@@ -300,3 +300,47 @@ def morph_close_mask(band: np.ndarray, radius: int = 5) -> np.ndarray:
     d = run(run(a, 1, np.maximum, -np.inf), 0, np.maximum, -np.inf)
     e = run(run(d, 1, np.minimum, np.inf), 0, np.minimum, np.inf)
     return e != 0.0
+
+
+def poisson_offset_dense(inputs, replacements, start_row: int, start_column: int):
+    """Statement-for-statement restatement of the offset / white-key overload (poisson.cpp:21-143) for SMALL cases:
+    raster-order numbering of the valid (non-key) replacement pixels (:54-64), A with the in-replacement neighbour count
+    on the diagonal and -1 for valid neighbours (:70-91), b = sum of replacement gradients + input values at key
+    neighbours (:104-122), a dense direct solve in place of the reference's sparse factorisation (:93-95,125), write-back
+    of the unknowns only (:128-140).  Returns new input arrays."""
+    ins = [np.array(a, np.float64, copy=True) for a in inputs]
+    rep = [np.asarray(a, np.float64) for a in replacements]
+    R, Cc = rep[0].shape
+
+    def valid(r, c):  # MultiChannelImage::valid_pixel, approx/utils.h:101-105
+        return not (int(rep[0][r, c]) == 1 and int(rep[1][r, c]) == 1 and int(rep[2][r, c]) == 1)
+
+    def neighbours(r, c):  # valid_neighbours, approx/utils.h:35-50
+        return [(r + dr, c + dc) for dr, dc in ((-1, 0), (1, 0), (0, -1), (0, 1)) if 0 <= r + dr < R and 0 <= c + dc < Cc]
+
+    number = {}
+    for r in range(R):
+        for c in range(Cc):
+            if valid(r, c):
+                number[(r, c)] = len(number)
+    n = len(number)
+    if n == 0:
+        return ins
+    A = np.zeros((n, n))
+    for (r, c), k in number.items():
+        nb = neighbours(r, c)
+        A[k, k] = float(len(nb))
+        for q in nb:
+            if q in number:
+                A[k, number[q]] = -1.0
+    for ch in range(len(ins)):
+        b = np.zeros(n)
+        for (r, c), k in number.items():
+            for (nr, nc) in neighbours(r, c):
+                b[k] += rep[ch][r, c] - rep[ch][nr, nc]
+                if (nr, nc) not in number:
+                    b[k] += ins[ch][nr + start_row, nc + start_column]
+        x = np.linalg.solve(A, b)
+        for (r, c), k in number.items():
+            ins[ch][r + start_row, c + start_column] = x[k]
+    return ins

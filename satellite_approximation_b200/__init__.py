@@ -45,7 +45,7 @@ __all__ = [
     "LogLevel", "set_log_level", "filling_missing_portions_smooth_boundaries", "blend_images_poisson",
     "find_connected_components", "ConnectedComponents", "mask_scan", "unknown_numbering", "valid_neighbours",
     "Context", "Scene", "SolveStats", "default_context", "set_solver_defaults", "last_perf_info",
-    "dist_partition", "dist_levels", "apply_laplace", "preprocess_cloud_band", "LAPLACE", "POISSON", "JACOBI", "MULTIGRID", "MG_RB32", "MG_JACOBI64", "SatfillError",
+    "dist_partition", "dist_levels", "apply_laplace", "preprocess_cloud_band", "blend_images_poisson_offset", "valid_pixel_mask", "LAPLACE", "POISSON", "JACOBI", "MULTIGRID", "MG_RB32", "MG_JACOBI64", "SatfillError",
 ]  # fmt: skip
 
 _log = logging.getLogger("satellite_approximation_b200")
@@ -517,6 +517,53 @@ def blend_images_poisson(input_image: Sequence[np.ndarray], replacement_image: S
         _log.error("Failed to solve the linear system (no convergence)")  # poisson.cpp:263-269
         return outs
     return work
+
+
+def valid_pixel_mask(replacement_image: Sequence[np.ndarray]) -> np.ndarray:
+    """MultiChannelImage::valid_pixel over a whole image (approx/utils.h:101-105): a pixel whose first three channels
+    all truncate to 1 is the white key (invalid); everything else is part of the pasted region."""
+    a = [np.asarray(c) for c in replacement_image[:3]]
+    key = (a[0].astype(np.int64) == 1) & (a[1].astype(np.int64) == 1) & (a[2].astype(np.int64) == 1)
+    return ~key
+
+
+def blend_images_poisson_offset(input_image: Sequence[np.ndarray], replacement_image: Sequence[np.ndarray], start_row: int,
+                                start_column: int, tolerance: float = 1e-12) -> None:  # fmt: skip
+    """Offset / white-key overload of approx::blend_images_poisson (poisson.h:30-33, poisson.cpp:21-143; the README's
+    beach / chair demo): `replacement_image` is pasted into `input_image` at (start_row, start_column); its unknowns are
+    the pixels that are not the white key; the arrays of `input_image` are modified IN PLACE like the reference's
+    `MultiChannelImage&`.  The three bounds checks log and return (poisson.cpp:25-39).
+
+    The system lives in the replacement's own rectangle (neighbours outside it are dropped, poisson.cpp:76,108) and its
+    boundary values are the input pixels at the offset, so it is the mask overload on the crop.  The reference factorises
+    the matrix; here it goes through the same CG to `tolerance`."""
+    ins = list(input_image)
+    reps = [np.asarray(a, dtype=np.float64) for a in replacement_image]
+    if not ins or len(reps) < 3 or len(reps) < len(ins):
+        raise TypeError("blend_images_poisson_offset(): the replacement needs >= 3 channels and one per input channel")
+    rows, cols = ins[0].shape
+    R, C_ = reps[0].shape
+    if R * C_ > rows * cols:
+        _log.error("Cannot solve problem: replacement image is larger than the input image")
+        return
+    if start_row < 0 or start_column < 0 or start_row >= rows or start_column >= cols:
+        _log.error("Cannot solve problem: row/column is out of bounds")
+        return
+    if start_row + R > rows or start_column + C_ > cols:
+        _log.error("Cannot solve problem: replacement image goes beyond the bounds of the input image")
+        return
+    unknown = np.asfortranarray(valid_pixel_mask(reps))
+    sl = (slice(start_row, start_row + R), slice(start_column, start_column + C_))
+    work = [np.array(a[sl], dtype=np.float64, order="F", copy=True) for a in ins]
+    g = [np.asfortranarray(reps[b]) for b in range(len(ins))]
+    global _last_perf
+    _last_perf = default_context().poisson_blend(work, g, unknown, tolerance=tolerance, max_iterations=2**31 - 2,
+                                                 precond=_defaults["precond"])  # fmt: skip
+    if any(s["status"] == SA_NOT_CONVERGED for s in _last_perf):
+        _log.error("Failed to solve the linear system (no convergence)")
+        return
+    for a, w in zip(ins, work):  # poisson.cpp:126-139: only the unknowns are written
+        a[sl][unknown] = w[unknown]
 
 
 class ConnectedComponents:
