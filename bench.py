@@ -42,6 +42,9 @@ WORKLOADS = {
                desc="synthetic 10980x10980 13-band Sentinel-2 tile, 30% cloud-like mask, Laplace fill"),
     "c3-poisson": dict(rows=10980, cols=10980, bands=13, cover=0.30, cell=48, problem="poisson",
                        desc="synthetic 10980x10980 13-band tile, 30% cloud-like mask, Poisson blend"),
+    # the easy variant SURVEY.md 8d asks to report separately: iid Bernoulli(0.3) is sub-percolation (tiny components)
+    "c3-iid": dict(rows=10980, cols=10980, bands=13, cover=0.30, cell=0, problem="laplace", iid=True,
+                   desc="synthetic 10980x10980 13-band tile, 30% iid Bernoulli mask (tiny components), Laplace fill"),
     "c1": dict(rows=1697, cols=1284, bands=5, cover=0.29, cell=160, problem="laplace",
                desc="1697x1284 5-band scene (test_data/2019-05-22 shape), 29% mask, Laplace fill"),
     # ONE system shared by all ranks: split by rows, halo rows + dot products over NCCL (strong scaling)
@@ -121,6 +124,31 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(self.samples)}  # fmt: skip
 
 
+def bind_to_gpu_numa_node(local: int) -> str:
+    """Run this rank's host threads -- and so place its pinned buffers -- on the NUMA node its GPU hangs off, the way a
+    launcher would with numactl: with eight ranks moving 25 GB each per step, host memory on the wrong socket makes
+    every PCIe transfer cross the inter-socket link."""
+    try:
+        import torch
+
+        p = torch.cuda.get_device_properties(local)
+        bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+        if node < 0:
+            return "numa: single node"
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return f"numa node {node} ({len(cpus)} cpus)"
+    except Exception as e:  # noqa: BLE001 -- best effort: the bench runs unbound
+        return f"numa: unbound ({type(e).__name__})"
+    return "numa: unbound"
+
+
 def peaks():
     try:
         p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -142,7 +170,9 @@ def cpu_baseline(w, tol, crop, threads, steps=1):
     kind = "reference" if ref is not None else "port"
     eng = ref if ref is not None else oracle.port()
     n = min(crop, w["rows"], w["cols"])
-    if w.get("regions"):  # the same density of regions as the workload
+    if w.get("iid"):
+        mask = synth.bernoulli_mask(n, n, cover=w["cover"], seed=2)
+    elif w.get("regions"):  # the same density of regions as the workload
         mask = synth.region_mask(n, n, max(1, int(w["regions"] * n * n / (w["rows"] * w["cols"]))), seed=3)
     else:
         mask = synth.blob_mask(n, n, cover=w["cover"], sigma=w["cell"] / 3.0, seed=2)
@@ -221,6 +251,7 @@ def run_b200(args, w):
         raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = bind_to_gpu_numa_node(local) if world > 1 else "numa: not bound (one rank)"
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -251,6 +282,14 @@ def run_b200(args, w):
         mask[:, 0] = 0
         mask[:, -1] = 0
         bands = [synth.torch_band(rows, cols, seed=100 + b, device=dev) for b in range(nb)]
+    elif w.get("iid"):
+        gen = torch.Generator(device=dev).manual_seed(2 + 17 * rank)
+        mask = (torch.rand((rows, cols), generator=gen, device=dev) < w["cover"]).to(torch.uint8)
+        mask[0, :] = 0
+        mask[-1, :] = 0
+        mask[:, 0] = 0
+        mask[:, -1] = 0
+        bands = [synth.torch_band(rows, cols, seed=100 + b + 1000 * rank, device=dev) for b in range(nb)]
     elif w.get("regions"):
         grid = 8
         mask = torch.from_numpy(synth.scene_mosaic_mask(rows // grid, grid, w["regions"], seed=3 + 7 * rank).view(np.uint8)).to(dev)
@@ -384,7 +423,7 @@ def run_b200(args, w):
     scene.close()
     e2e = None
     if not args.no_e2e and not one_system:
-        e2e = run_e2e(args, w, ctx, sab, mask, bands, guides, world, dev, barrier)
+        e2e = run_e2e(args, w, ctx, sab, mask, bands, guides, world, dev, barrier, numa)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -415,7 +454,7 @@ def run_b200(args, w):
         dist.destroy_process_group()
 
 
-def run_e2e(args, w, ctx, sab, mask, bands, guides, world, dev, barrier):
+def run_e2e(args, w, ctx, sab, mask, bands, guides, world, dev, barrier, numa=""):
     import torch
 
     rows, cols, nb = w["rows"], w["cols"], w["bands"]
@@ -468,7 +507,7 @@ def run_e2e(args, w, ctx, sab, mask, bands, guides, world, dev, barrier):
     img_bytes = rows * cols * 8 * nb
     return {"value": unknowns * n_e2e / dt, "unit": UNIT, "h2d_bytes_per_step": rows * cols + img_bytes * (2 if poisson else 1),
             "d2h_bytes_per_step": img_bytes, "seconds_per_step": dt / n_e2e, "steps": n_e2e,
-            "api": "sa_poisson_blend" if poisson else "sa_laplace_fill", "host_buffers": "pinned"}  # fmt: skip
+            "api": "sa_poisson_blend" if poisson else "sa_laplace_fill", "host_buffers": "pinned", "host_placement": numa}  # fmt: skip
 
 
 def main():
