@@ -42,72 +42,72 @@ constexpr int ST_DIR_CTAS = SATFILL_DIR_CTAS, ST_UPD_CTAS = SATFILL_UPD_CTAS;
 template <typename ZT>
 constexpr int dir_ctas() { return sizeof(ZT) == 8 && ST_DIR_CTAS > 6 ? 6 : ST_DIR_CTAS; }
 
-__device__ __forceinline__ double2 ldnc2_if(const double* p, unsigned pred)
+__device__ __forceinline__ double2 ldnc2_if(const double* p, unsigned mask, unsigned bit)
 {
     double2 v;
-    asm("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %3, 0;\n\tmov.f64 %0, 0d0000000000000000;\n\tmov.f64 %1, 0d0000000000000000;\n\t"
+    asm("{\n\t.reg .pred q;\n\t.reg .b32 t;\n\tand.b32 t, %3, %4;\n\tsetp.ne.u32 q, t, 0;\n\tmov.f64 %0, 0d0000000000000000;\n\tmov.f64 %1, 0d0000000000000000;\n\t"
         "@q ld.global.nc.v2.f64 {%0, %1}, [%2];\n\t}"
         : "=d"(v.x), "=d"(v.y)
-        : "l"(p), "r"(pred));
+        : "l"(p), "r"(mask), "r"(bit));
     return v;
 }
-__device__ __forceinline__ double2 ld2_if(const double* p, unsigned pred)  // data this kernel also writes: no .nc
+__device__ __forceinline__ double2 ld2_if(const double* p, unsigned mask, unsigned bit)  // data this kernel also writes: no .nc
 {
     double2 v;
-    asm("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %3, 0;\n\tmov.f64 %0, 0d0000000000000000;\n\tmov.f64 %1, 0d0000000000000000;\n\t"
+    asm("{\n\t.reg .pred q;\n\t.reg .b32 t;\n\tand.b32 t, %3, %4;\n\tsetp.ne.u32 q, t, 0;\n\tmov.f64 %0, 0d0000000000000000;\n\tmov.f64 %1, 0d0000000000000000;\n\t"
         "@q ld.global.v2.f64 {%0, %1}, [%2];\n\t}"
         : "=d"(v.x), "=d"(v.y)
-        : "l"(p), "r"(pred));
+        : "l"(p), "r"(mask), "r"(bit));
     return v;
 }
-__device__ __forceinline__ double ldnc_if(const double* p, unsigned pred)
+__device__ __forceinline__ double ldnc_if(const double* p, unsigned mask, unsigned bit)
 {
     double v;
-    asm("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\tmov.f64 %0, 0d0000000000000000;\n\t@q ld.global.nc.f64 %0, [%1];\n\t}"
+    asm("{\n\t.reg .pred q;\n\t.reg .b32 t;\n\tand.b32 t, %2, %3;\n\tsetp.ne.u32 q, t, 0;\n\tmov.f64 %0, 0d0000000000000000;\n\t@q ld.global.nc.f64 %0, [%1];\n\t}"
         : "=d"(v)
-        : "l"(p), "r"(pred));
+        : "l"(p), "r"(mask), "r"(bit));
     return v;
 }
-__device__ __forceinline__ double ld_if(const double* p, unsigned pred)  // data this kernel also writes: no .nc
+__device__ __forceinline__ double ld_if(const double* p, unsigned mask, unsigned bit)  // data this kernel also writes: no .nc
 {
     double v;
-    asm("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\tmov.f64 %0, 0d0000000000000000;\n\t@q ld.global.f64 %0, [%1];\n\t}"
+    asm("{\n\t.reg .pred q;\n\t.reg .b32 t;\n\tand.b32 t, %2, %3;\n\tsetp.ne.u32 q, t, 0;\n\tmov.f64 %0, 0d0000000000000000;\n\t@q ld.global.f64 %0, [%1];\n\t}"
         : "=d"(v)
-        : "l"(p), "r"(pred));
+        : "l"(p), "r"(mask), "r"(bit));
     return v;
 }
-__device__ __forceinline__ double2 ldnc2_if(const float* p, unsigned pred)  // float plane, widened
+__device__ __forceinline__ double2 ldnc2_if(const float* p, unsigned mask, unsigned bit)  // float plane, widened
 {
     float x, y;
-    asm("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %3, 0;\n\tmov.f32 %0, 0f00000000;\n\tmov.f32 %1, 0f00000000;\n\t"
+    asm("{\n\t.reg .pred q;\n\t.reg .b32 t;\n\tand.b32 t, %3, %4;\n\tsetp.ne.u32 q, t, 0;\n\tmov.f32 %0, 0f00000000;\n\tmov.f32 %1, 0f00000000;\n\t"
         "@q ld.global.nc.v2.f32 {%0, %1}, [%2];\n\t}"
         : "=f"(x), "=f"(y)
-        : "l"(p), "r"(pred));
+        : "l"(p), "r"(mask), "r"(bit));
     return make_double2((double)x, (double)y);
 }
-__device__ __forceinline__ float2 ldnc2f_if(const float* p, unsigned pred)  // float plane, as stored
+__device__ __forceinline__ float2 ldnc2f_if(const float* p, unsigned mask, unsigned bit)  // float plane, as stored
 {
     float2 v;
-    asm("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %3, 0;\n\tmov.f32 %0, 0f00000000;\n\tmov.f32 %1, 0f00000000;\n\t"
+    asm("{\n\t.reg .pred q;\n\t.reg .b32 t;\n\tand.b32 t, %3, %4;\n\tsetp.ne.u32 q, t, 0;\n\tmov.f32 %0, 0f00000000;\n\tmov.f32 %1, 0f00000000;\n\t"
         "@q ld.global.nc.v2.f32 {%0, %1}, [%2];\n\t}"
         : "=f"(v.x), "=f"(v.y)
-        : "l"(p), "r"(pred));
+        : "l"(p), "r"(mask), "r"(bit));
     return v;
 }
-__device__ __forceinline__ float ldncf_if(const float* p, unsigned pred)
+__device__ __forceinline__ float ldncf_if(const float* p, unsigned mask, unsigned bit)
 {
     float v;
-    asm("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\tmov.f32 %0, 0f00000000;\n\t@q ld.global.nc.f32 %0, [%1];\n\t}"
+    asm("{\n\t.reg .pred q;\n\t.reg .b32 t;\n\tand.b32 t, %2, %3;\n\tsetp.ne.u32 q, t, 0;\n\tmov.f32 %0, 0f00000000;\n\t@q ld.global.nc.f32 %0, [%1];\n\t}"
         : "=f"(v)
-        : "l"(p), "r"(pred));
+        : "l"(p), "r"(mask), "r"(bit));
     return v;
 }
-__device__ __forceinline__ double ldnc_if(const float* p, unsigned pred)
+__device__ __forceinline__ double ldnc_if(const float* p, unsigned mask, unsigned bit)
 {
     float v;
-    asm("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\tmov.f32 %0, 0f00000000;\n\t@q ld.global.nc.f32 %0, [%1];\n\t}"
+    asm("{\n\t.reg .pred q;\n\t.reg .b32 t;\n\tand.b32 t, %2, %3;\n\tsetp.ne.u32 q, t, 0;\n\tmov.f32 %0, 0f00000000;\n\t@q ld.global.nc.f32 %0, [%1];\n\t}"
         : "=f"(v)
-        : "l"(p), "r"(pred));
+        : "l"(p), "r"(mask), "r"(bit));
     return (double)v;
 }
 
@@ -291,13 +291,13 @@ __global__ void __launch_bounds__(ST_THREADS, dir_ctas<ZT>()) k_direction2(Level
                 float zef[ST_RG], pef[ST_RG];
 #pragma unroll
                 for (int j = 0; j < 6; ++j) {
-                    zf[j] = ldnc2f_if(zb + (toff + j * pitch), (any >> j) & 1);
-                    pf[j] = ldnc2f_if(pb + (toff + j * pitch), (any >> j) & 1);
+                    zf[j] = ldnc2f_if(zb + (toff + j * pitch), any, 1u << j);
+                    pf[j] = ldnc2f_if(pb + (toff + j * pitch), any, 1u << j);
                 }
 #pragma unroll
                 for (int j = 0; j < ST_RG; ++j) {
-                    zef[j] = ldncf_if(zb + (eoff + (j + 1) * pitch), (em >> j) & 1);
-                    pef[j] = ldncf_if(pb + (eoff + (j + 1) * pitch), (em >> j) & 1);
+                    zef[j] = ldncf_if(zb + (eoff + (j + 1) * pitch), em, 1u << j);
+                    pef[j] = ldncf_if(pb + (eoff + (j + 1) * pitch), em, 1u << j);
                 }
                 if (SATFILL_L2_PREFETCH && has_next)
                     pf_next(nx);
@@ -320,13 +320,13 @@ __global__ void __launch_bounds__(ST_THREADS, dir_ctas<ZT>()) k_direction2(Level
                 double ze[ST_RG], pe[ST_RG];
 #pragma unroll
                 for (int j = 0; j < 6; ++j) {
-                    zv[j] = ldnc2_if(zb + (toff + j * pitch), (any >> j) & 1);
-                    pv[j] = ldnc2_if(pb + (toff + j * pitch), (any >> j) & 1);
+                    zv[j] = ldnc2_if(zb + (toff + j * pitch), any, 1u << j);
+                    pv[j] = ldnc2_if(pb + (toff + j * pitch), any, 1u << j);
                 }
 #pragma unroll
                 for (int j = 0; j < ST_RG; ++j) {
-                    ze[j] = ldnc_if(zb + (eoff + (j + 1) * pitch), (em >> j) & 1);
-                    pe[j] = ldnc_if(pb + (eoff + (j + 1) * pitch), (em >> j) & 1);
+                    ze[j] = ldnc_if(zb + (eoff + (j + 1) * pitch), em, 1u << j);
+                    pe[j] = ldnc_if(pb + (eoff + (j + 1) * pitch), em, 1u << j);
                 }
                 if (SATFILL_L2_PREFETCH && has_next)
                     pf_next(nx);
@@ -434,18 +434,18 @@ __global__ void __launch_bounds__(ST_THREADS, ST_UPD_CTAS) k_update2(Level lv, i
             double pe[ST_RG];
 #pragma unroll
             for (int j = 0; j < 6; ++j)
-                pv[j] = ldnc2_if(pb + (toff + j * pitch), (any >> j) & 1);
+                pv[j] = ldnc2_if(pb + (toff + j * pitch), any, 1u << j);
 #pragma unroll
             for (int j = 0; j < ST_RG; ++j) {
-                xv[j] = ld2_if(ub + (toff + (j + 1) * pitch), (st2 >> (j + 1)) & 1);
-                rv[j] = ld2_if(rb + (toff + (j + 1) * pitch), (any >> (j + 1)) & 1);
+                xv[j] = ld2_if(ub + (toff + (j + 1) * pitch), st2, 1u << (j + 1));
+                rv[j] = ld2_if(rb + (toff + (j + 1) * pitch), any, 1u << (j + 1));
             }
             {
                 const int eoff = toff + (west ? -1 : 2);
                 const unsigned em = (west ? mL : (east ? mR : 0u)) >> 1;
 #pragma unroll
                 for (int j = 0; j < ST_RG; ++j)
-                    pe[j] = ldnc_if(pb + (eoff + (j + 1) * pitch), (em >> j) & 1);
+                    pe[j] = ldnc_if(pb + (eoff + (j + 1) * pitch), em, 1u << j);
             }
             if (SATFILL_L2_PREFETCH && has_next)
                 pf(nx);
@@ -542,16 +542,16 @@ __global__ void __launch_bounds__(ST_THREADS, 4) k_setup2(Level lv, int nbands, 
             double ue[ST_RG], ge[ST_RG];
 #pragma unroll
             for (int j = 0; j < 6; ++j) {
-                uv[j] = ld2_if(ub + (toff + j * pitch), (ldm >> j) & 1);
-                gv[j] = POISSON ? ldnc2_if(gband + origin + (toff + j * pitch), (ldm >> j) & 1) : make_double2(0.0, 0.0);
+                uv[j] = ld2_if(ub + (toff + j * pitch), ldm, 1u << j);
+                gv[j] = POISSON ? ldnc2_if(gband + origin + (toff + j * pitch), ldm, 1u << j) : make_double2(0.0, 0.0);
             }
             {
                 const int eoff = toff + (west ? -1 : 2);
                 const unsigned em = (west ? mL : (east ? mR : 0u)) >> 1;
 #pragma unroll
                 for (int j = 0; j < ST_RG; ++j) {
-                    ue[j] = ld_if(ub + (eoff + (j + 1) * pitch), (em >> j) & 1);
-                    ge[j] = POISSON ? ldnc_if(gband + origin + (eoff + (j + 1) * pitch), (em >> j) & 1) : 0.0;
+                    ue[j] = ld_if(ub + (eoff + (j + 1) * pitch), em, 1u << j);
+                    ge[j] = POISSON ? ldnc_if(gband + origin + (eoff + (j + 1) * pitch), em, 1u << j) : 0.0;
                 }
             }
             const int64_t gr = (int64_t)tb.ty() * TILE_H + row0, gc = (int64_t)tb.tx() * TILE_W + 2 * cx;

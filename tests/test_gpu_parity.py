@@ -375,6 +375,54 @@ def test_mask_changes_on_a_resident_scene(ctx):
     sc.close()
 
 
+def test_full_tile_size_properties(ctx):
+    """BASELINE.json configs[2] at its full size (10980 x 10980, cloud-like 30 % mask) is far beyond what the oracle can
+    solve in a test, so the device-resident path is checked through size-independent properties: a discrete-harmonic
+    field is a fixed point of the fill, the fill is linear in the image, known pixels are bit-identical, and the filled
+    image satisfies the 5-point equations (true residual evaluated independently with torch, not the solver's
+    recurrence)."""
+    import torch
+
+    rows = cols = 10980
+    dev = torch.device("cuda", 0)
+    mask = synth.torch_blob_mask(rows, cols, cover=0.30, cell=48, seed=2, device=dev)
+    r = torch.arange(rows, device=dev, dtype=torch.float64)[:, None]
+    c = torch.arange(cols, device=dev, dtype=torch.float64)[None, :]
+    harmonic = (3.0 * r - 2.0 * c + 7.0).contiguous()                 # discrete harmonic: every cell is its neighbours' mean
+    smooth = synth.torch_band(rows, cols, seed=100, device=dev)
+    combo = (2.0 * harmonic - 3.0 * smooth).contiguous()
+    torch.cuda.synchronize()
+    sc = ctx.scene(sab.LAPLACE, rows, cols, 3)
+    sc.set_mask(mask)
+    for b, t in enumerate((harmonic, smooth, combo)):
+        sc.set_band(b, t)
+    st = sc.solve(tolerance=1e-9, precond=sab.MULTIGRID)
+    assert all(s["status"] == sab.SA_OK for s in st) and st[0]["unknowns"] == int(mask.sum().item())
+    assert max(s["iterations"] for s in st) <= 25
+    outs = []
+    for b in range(3):
+        o = torch.empty_like(harmonic)
+        sc.get_band(b, o)
+        outs.append(o)
+    ctx.synchronize()
+    sc.close()
+    m = mask.bool()
+    scale = float(harmonic.abs().max().item())
+    assert float((outs[0] - harmonic)[m].abs().max().item()) / scale < 1e-6                     # fixed point
+    lin = 2.0 * outs[0] - 3.0 * outs[1]
+    assert float((outs[2] - lin)[m].abs().max().item()) / float(lin[m].abs().max().item()) < 1e-6  # linearity
+    for o, t in zip(outs, (harmonic, smooth, combo)):
+        assert torch.equal(o[~m], t[~m])                                                         # known pixels untouched
+    # true relative residual of the reduced system: 4 x_p - sum of ALL neighbours (known ones carry the boundary values)
+    x = outs[1]
+    lap = 4.0 * x[1:-1, 1:-1] - (x[:-2, 1:-1] + x[2:, 1:-1] + x[1:-1, :-2] + x[1:-1, 2:])
+    mi = m[1:-1, 1:-1]
+    known = torch.where(m, torch.zeros_like(x), x)
+    bvec = (known[:-2, 1:-1] + known[2:, 1:-1] + known[1:-1, :-2] + known[1:-1, 2:])[mi]
+    res = float(lap[mi].norm().item()) / float(bvec.norm().item())
+    assert res < 1e-8, res
+
+
 # ---- multigrid-preconditioned CG: same answers, far fewer iterations ------------------------------------------------
 @pytest.mark.parametrize("i", [0, 1, 2])
 def test_multigrid_laplace_vs_golden(ctx, small_cases, i):
