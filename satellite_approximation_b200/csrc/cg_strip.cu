@@ -22,8 +22,16 @@ namespace satfill {
 
 namespace {
 
-constexpr int ST_THREADS = 128;
-constexpr int ST_RG = 4;  // rows per thread
+#ifndef SATFILL_ST_RG
+#define SATFILL_ST_RG 4
+#endif
+constexpr int ST_RG = SATFILL_ST_RG;  // rows per thread (4: 128-thread CTAs, 2: 256-thread CTAs with half the registers)
+constexpr int ST_THREADS = 16 * (TILE_H / ST_RG);
+constexpr int ST_WARPS = ST_THREADS / 32;
+constexpr int ST_NR = ST_RG + 2;                    // rows a thread looks at: its own and one above / below
+constexpr unsigned ST_NRM = (1u << ST_NR) - 1;      // ... as a bit mask (bit j <=> tile row row0 - 1 + j)
+constexpr unsigned ST_OWN = ((1u << ST_RG) - 1) << 1;  // the own rows among them
+static_assert(TILE_H % ST_RG == 0 && ST_THREADS % 32 == 0 && ST_NR <= 8, "unsupported rows per thread");
 // resident CTAs per SM the two kernels are compiled for (register budget) and launched with (persistent grids)
 #ifndef SATFILL_DIR_CTAS
 #define SATFILL_DIR_CTAS 6
@@ -120,9 +128,9 @@ struct TileBits {
     unsigned m;  // mL | mR << 8: unknown bits of the two columns, bit j <=> tile row row0 - 1 + j, j = 0..5
     __device__ __forceinline__ int ty() const { return yx >> 16; }
     __device__ __forceinline__ int tx() const { return yx & 0xffff; }
-    __device__ __forceinline__ unsigned mL() const { return m & 63u; }
+    __device__ __forceinline__ unsigned mL() const { return m & ST_NRM; }
     __device__ __forceinline__ unsigned mR() const { return m >> 8; }
-    __device__ __forceinline__ unsigned any() const { return (m | (m >> 8)) & 63u; }
+    __device__ __forceinline__ unsigned any() const { return (m | (m >> 8)) & ST_NRM; }
     // element offset of the tile's origin inside a band plane (fits 32 bits: a plane has < 2^31 elements)
     __device__ __forceinline__ int origin(int pitch) const { return ty() * (TILE_H * pitch) + tx() * TILE_W; }
 };
@@ -141,11 +149,11 @@ __device__ __forceinline__ TileBits load_tile_bits(const Level& lv, int yx, int 
     // bit (row + 1) of the 34-bit column <=> tile row `row`
     unsigned long long cl = ((unsigned long long)N.x >> 31) | ((unsigned long long)C.x << 1) | ((unsigned long long)(S.x & 1u) << 33);
     unsigned long long cr = ((unsigned long long)N.y >> 31) | ((unsigned long long)C.y << 1) | ((unsigned long long)(S.y & 1u) << 33);
-    b.m = ((unsigned)(cl >> row0) & 63u) | (((unsigned)(cr >> row0) & 63u) << 8);
+    b.m = ((unsigned)(cl >> row0) & ST_NRM) | (((unsigned)(cr >> row0) & ST_NRM) << 8);
     return b;
 }
 
-__device__ __forceinline__ double block_sum4(double v, double* s_red /* 4 */)
+__device__ __forceinline__ double block_sum4(double v, double* s_red /* ST_WARPS */)
 {
     for (int o = 16; o; o >>= 1)
         v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -153,7 +161,11 @@ __device__ __forceinline__ double block_sum4(double v, double* s_red /* 4 */)
     if ((threadIdx.x & 31) == 0)
         s_red[threadIdx.x >> 5] = v;
     __syncthreads();
-    return (s_red[0] + s_red[1]) + (s_red[2] + s_red[3]);  // valid everywhere
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < ST_WARPS; w += 2)
+        t += s_red[w] + s_red[w + 1];
+    return t;  // valid everywhere
 }
 
 template <bool FIXED>
@@ -230,7 +242,7 @@ template <bool JACOBI, bool FIXED, typename ZT, typename PT>
 __global__ void __launch_bounds__(ST_THREADS, dir_ctas<ZT>()) k_direction2(Level lv, int nbands, const ZT* __restrict__ zin,
     const PT* __restrict__ p_old, PT* __restrict__ p_new, BandScalars* __restrict__ scal, int k)
 {
-    __shared__ double s_red[4];
+    __shared__ double s_red[ST_WARPS];
     const int slot = k & 3;
     const bool lead = blockIdx.x == 0 && threadIdx.x == 0;
     const int cx = threadIdx.x & 15, row0 = (threadIdx.x >> 4) * ST_RG;
@@ -282,15 +294,15 @@ __global__ void __launch_bounds__(ST_THREADS, dir_ctas<ZT>()) k_direction2(Level
             const int eoff = toff + (west ? -1 : 2);
             // the halo cell can only matter if the own edge cell is an unknown
             const unsigned em = (west ? tb.mL() : (east ? tb.mR() : 0u)) >> 1;
-            double2 pn[6];
+            double2 pn[ST_NR];
             double pedge[ST_RG];
             if constexpr (sizeof(PT) == 4 && sizeof(ZT) == 4 && !JACOBI) {
                 // float z, float p: p' = z + beta p in single precision, exactly as it is stored (conversions between
                 // float and double are a quarter-rate pipe: two per cell instead of eight); widened once for A p'
-                float2 zf[6], pf[6];
+                float2 zf[ST_NR], pf[ST_NR];
                 float zef[ST_RG], pef[ST_RG];
 #pragma unroll
-                for (int j = 0; j < 6; ++j) {
+                for (int j = 0; j < ST_NR; ++j) {
                     zf[j] = ldnc2f_if(zb + (toff + j * pitch), any, 1u << j);
                     pf[j] = ldnc2f_if(pb + (toff + j * pitch), any, 1u << j);
                 }
@@ -305,7 +317,7 @@ __global__ void __launch_bounds__(ST_THREADS, dir_ctas<ZT>()) k_direction2(Level
                 const unsigned st = sector_or4(sector_or2(any));
                 PT* po = poband + origin;
 #pragma unroll
-                for (int j = 0; j < 6; ++j) {
+                for (int j = 0; j < ST_NR; ++j) {
                     float2 v = make_float2(fmaf(bf, pf[j].x, zf[j].x), fmaf(bf, pf[j].y, zf[j].y));  // ConjugateGradient.h:80
                     if (j >= 1 && j <= ST_RG && ((st >> j) & 1))
                         *reinterpret_cast<float2*>(po + (toff + j * pitch)) = v;
@@ -316,10 +328,10 @@ __global__ void __launch_bounds__(ST_THREADS, dir_ctas<ZT>()) k_direction2(Level
                     pedge[j] = (double)fmaf(bf, pef[j], zef[j]);
             } else {
                 // ---- all loads: pairs of rows row0-1 .. row0+4, and (edge lanes) the halo column of the own rows
-                double2 zv[6], pv[6];
+                double2 zv[ST_NR], pv[ST_NR];
                 double ze[ST_RG], pe[ST_RG];
 #pragma unroll
-                for (int j = 0; j < 6; ++j) {
+                for (int j = 0; j < ST_NR; ++j) {
                     zv[j] = ldnc2_if(zb + (toff + j * pitch), any, 1u << j);
                     pv[j] = ldnc2_if(pb + (toff + j * pitch), any, 1u << j);
                 }
@@ -332,7 +344,7 @@ __global__ void __launch_bounds__(ST_THREADS, dir_ctas<ZT>()) k_direction2(Level
                     pf_next(nx);
                 // ---- p' = z + beta p on the 6 x 2 cells and the edge column
 #pragma unroll
-                for (int j = 0; j < 6; ++j) {
+                for (int j = 0; j < ST_NR; ++j) {
                     double zl = zv[j].x, zr = zv[j].y;
                     if (JACOBI) {
                         int dr = diag_row<FIXED>(lv, gr - 1 + j);
@@ -393,7 +405,7 @@ template <bool JACOBI, bool FIXED, bool RF, typename PT>
 __global__ void __launch_bounds__(ST_THREADS, ST_UPD_CTAS) k_update2(Level lv, int nbands, double* __restrict__ u,
     const PT* __restrict__ p, double* __restrict__ rvec, float* __restrict__ rf, BandScalars* __restrict__ scal, int k)
 {
-    __shared__ double s_red[4];
+    __shared__ double s_red[ST_WARPS];
     const int slot = k & 3, next = (k + 1) & 3;
     const int cx = threadIdx.x & 15, row0 = (threadIdx.x >> 4) * ST_RG;
     const int pitch = (int)lv.pitch;
@@ -430,10 +442,10 @@ __global__ void __launch_bounds__(ST_THREADS, ST_UPD_CTAS) k_update2(Level lv, i
             // whole 32-byte sectors are written (see k_direction2): x of a cell that is not an unknown is written back as
             // read, so x is loaded wherever its sector is stored (the sector travels anyway)
             const unsigned st2 = sector_or2(any), st4 = RF ? sector_or4(st2) : 0u;
-            double2 pv[6], xv[ST_RG], rv[ST_RG];
+            double2 pv[ST_NR], xv[ST_RG], rv[ST_RG];
             double pe[ST_RG];
 #pragma unroll
-            for (int j = 0; j < 6; ++j)
+            for (int j = 0; j < ST_NR; ++j)
                 pv[j] = ldnc2_if(pb + (toff + j * pitch), any, 1u << j);
 #pragma unroll
             for (int j = 0; j < ST_RG; ++j) {
@@ -506,7 +518,7 @@ __global__ void __launch_bounds__(ST_THREADS, 4) k_setup2(Level lv, int nbands, 
     const double* __restrict__ g, double* __restrict__ rvec, float* __restrict__ rf, BandScalars* __restrict__ scal)
 {
     constexpr bool FIXED = !POISSON;
-    __shared__ double s_red[4];
+    __shared__ double s_red[ST_WARPS];
     const int cx = threadIdx.x & 15, row0 = (threadIdx.x >> 4) * ST_RG;
     const int pitch = (int)lv.pitch;
     const int toff = (row0 - 1) * pitch + 2 * cx;
@@ -527,21 +539,21 @@ __global__ void __launch_bounds__(ST_THREADS, 4) k_setup2(Level lv, int nbands, 
             unsigned mW = __shfl_up_sync(0xffffffffu, mR, 1), mE = __shfl_down_sync(0xffffffffu, mL, 1);
             if (west || east) {
                 const uint32_t w = __ldg(lv.tbitsT + ((size_t)(tb.ty() + 1) * lv.tb_stride + (tb.tx() + (west ? 0 : 2))) * 32 + (west ? 31 : 0));
-                const unsigned e = ((w >> row0) & 15u) << 1;
+                const unsigned e = ((w >> row0) & ((1u << ST_RG) - 1)) << 1;
                 if (west)
                     mW = e;
                 else
                     mE = e;
             }
-            const unsigned own = any & 0x1eu;  // own rows that hold an unknown of the pair
+            const unsigned own = any & ST_OWN;  // own rows that hold an unknown of the pair
             // rows to load: those, the rows above / below them, and the rows an adjacent lane's unknowns look at (u and g
             // hold real pixel values at known cells, unlike the solver's work vectors)
-            const unsigned ldm = (own | (own << 1) | (own >> 1) | __shfl_up_sync(0xffffffffu, own, 1) | __shfl_down_sync(0xffffffffu, own, 1)) & 63u;
+            const unsigned ldm = (own | (own << 1) | (own >> 1) | __shfl_up_sync(0xffffffffu, own, 1) | __shfl_down_sync(0xffffffffu, own, 1)) & ST_NRM;
             double* ub = uband + origin;
-            double2 uv[6], gv[6];
+            double2 uv[ST_NR], gv[ST_NR];
             double ue[ST_RG], ge[ST_RG];
 #pragma unroll
-            for (int j = 0; j < 6; ++j) {
+            for (int j = 0; j < ST_NR; ++j) {
                 uv[j] = ld2_if(ub + (toff + j * pitch), ldm, 1u << j);
                 gv[j] = POISSON ? ldnc2_if(gband + origin + (toff + j * pitch), ldm, 1u << j) : make_double2(0.0, 0.0);
             }

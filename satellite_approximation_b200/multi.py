@@ -79,3 +79,36 @@ def reduce_step(ms: float, units: float, one_system: bool, device=None) -> Tuple
     if not one_system:
         dist.all_reduce(u, op=dist.ReduceOp.SUM)
     return float(t.item()), float(u.item())
+
+
+def region_shard_mask(labels, num_labels: int, world: int, rank: int):
+    """Independent regions of ONE scene over several GPUs (second row): connected components are independent
+    linear systems, so rank `rank` fills the components that `pack_regions` deals to it and nothing else.  `labels` is
+    the label image of sa_label_components (0 = valid pixel).  Returns (this rank's invalid mask, its component labels).
+    The union of the ranks' fills is the fill of the whole mask; merging is a host-side gather of disjoint pixel sets
+    (`merge_region_fills`)."""
+    import numpy as np
+
+    lab = np.asarray(labels)
+    sizes = np.bincount(lab.ravel(), minlength=num_labels + 1)[1:]
+    mine = pack_regions(sizes, world)[rank]
+    keep = np.zeros(num_labels + 1, bool)
+    keep[[i + 1 for i in mine]] = True
+    return keep[lab], [i + 1 for i in mine]
+
+
+def merge_region_fills(filled, shard_mask):
+    """All ranks' fills of their own regions merged into every rank's `filled` arrays (a list of 2-D arrays, modified in
+    place): each rank contributes the pixels of its shard mask; the sets are disjoint, so the merge is an all-gather of
+    (mask, values) pairs and a scatter.  No collective touches the solve itself."""
+    import numpy as np
+    import torch.distributed as dist
+
+    world = dist.get_world_size()
+    mine = (np.asarray(shard_mask), [np.asarray(a)[shard_mask] for a in filled])
+    parts = [None] * world
+    dist.all_gather_object(parts, mine)
+    for m, vals in parts:
+        for a, v in zip(filled, vals):
+            a[m] = v
+    return filled

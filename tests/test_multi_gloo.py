@@ -26,6 +26,23 @@ def test_pack_regions_is_a_balanced_partition():
     assert multi.pack_regions([5], 2) == [[0], []]
 
 
+def test_region_shard_masks_partition_the_mask():
+    from scipy.ndimage import label
+
+    from satellite_approximation_b200 import synth
+
+    mask = synth.region_mask(300, 340, 30, area_lo=30.0, area_hi=3000.0, seed=4)
+    lab, k = label(mask)
+    for world in (1, 2, 3, 8):
+        shards = [multi.region_shard_mask(lab, k, world, r) for r in range(world)]
+        total = np.zeros(mask.shape, int)
+        for m, labels in shards:
+            total += m
+            assert set(np.unique(lab[m])) == set(labels)
+        assert np.array_equal(total, mask.astype(int))  # every invalid pixel in exactly one shard
+        assert sorted(l for _, ls in shards for l in ls) == list(range(1, k + 1))
+
+
 def test_round_robin_covers_every_item_once():
     for n, world in ((13, 8), (13, 2), (3, 8), (0, 4)):
         got = sorted(i for r in range(world) for i in multi.round_robin(n, world, r))
