@@ -505,9 +505,29 @@ def run_e2e(args, w, ctx, sab, mask, bands, guides, world, dev, barrier, numa=""
     dt = float(t.item())
     unknowns = st[0]["unknowns"] * nb * world
     img_bytes = rows * cols * 8 * nb
-    return {"value": unknowns * n_e2e / dt, "unit": UNIT, "h2d_bytes_per_step": rows * cols + img_bytes * (2 if poisson else 1),
-            "d2h_bytes_per_step": img_bytes, "seconds_per_step": dt / n_e2e, "steps": n_e2e,
-            "api": "sa_poisson_blend" if poisson else "sa_laplace_fill", "host_buffers": "pinned", "host_placement": numa}  # fmt: skip
+    out = {"value": unknowns * n_e2e / dt, "unit": UNIT, "seconds_per_step": dt / n_e2e, "steps": n_e2e,
+           "api": "sa_poisson_blend" if poisson else "sa_laplace_fill", "host_buffers": "pinned", "host_placement": numa,
+           "host_input_bytes": rows * cols + img_bytes * (2 if poisson else 1), "host_output_bytes": img_bytes}  # fmt: skip
+    if ctx.last_fill_direct:
+        # direct mode: kernels read / write the page-locked arrays in place.  What crosses PCIe per step: the mask, the
+        # known pixels that border the unknown set (Poisson: plus g on the unknown set and around it), and the unknown
+        # pixels on the way back -- counted here from the mask (the kernels move 16-byte pairs, so this is a lower bound)
+        m = torch.from_numpy(np_mask).to(dev).bool()
+        near = torch.zeros_like(m)
+        near[1:, :] |= m[:-1, :]
+        near[:-1, :] |= m[1:, :]
+        near[:, 1:] |= m[:, :-1]
+        near[:, :-1] |= m[:, 1:]
+        ring = int((near & ~m).sum().item())
+        unk = int(m.sum().item())
+        del m, near
+        out.update({"transfer": "direct (no image copies; set-up kernel reads, scatter kernel writes host memory)",
+                    "h2d_bytes_per_step": rows * cols + 8 * nb * (ring + ((unk + ring) if poisson else 0)),
+                    "d2h_bytes_per_step": 8 * nb * unk})  # fmt: skip
+    else:
+        out.update({"transfer": "copies (pipelined over three streams)", "h2d_bytes_per_step": out["host_input_bytes"],
+                    "d2h_bytes_per_step": img_bytes})  # fmt: skip
+    return out
 
 
 def main():

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define SATFILL_ABI_VERSION 3
+#define SATFILL_ABI_VERSION 4
 
 typedef enum sa_status {
     SA_OK = 0,
@@ -197,6 +197,12 @@ int sa_dist_levels(int64_t rows, int world);
 int sa_scene_set_distributed(sa_scene* scene, int on);
 int sa_scene_owned_rows(const sa_scene* scene, int64_t* lo, int64_t* hi, int* axis);
 int sa_scene_allgather_band(sa_scene* scene, int band);
+
+/* 1 if the last sa_laplace_fill / sa_poisson_blend of this context ran in direct mode: the caller's arrays were page-locked
+ * (device-addressable), so no image was copied -- the set-up kernel read the known pixels that border the unknown set (and
+ * the replacement image on the unknown set) straight from host memory and only the unknown pixels were stored back.
+ * 0 if the images were copied whole (pageable memory, an odd fast extent, SATFILL_NO_DIRECT). */
+int sa_last_fill_direct(const sa_ctx* ctx);
 
 /* ---- the steps either side of the path (next rows) ------------------------------------------------------- */
 

@@ -152,6 +152,12 @@ class Context:
     def kernel_launches(self) -> int:
         return int(self._lib.sa_kernel_launches(self._h))
 
+    @property
+    def last_fill_direct(self) -> bool:
+        """True if the last laplace_fill / poisson_blend read and wrote the caller's page-locked arrays in place over PCIe
+        (no image copies): sa_last_fill_direct."""
+        return bool(self._lib.sa_last_fill_direct(self._h))
+
     def synchronize(self) -> None:
         self._check(self._lib.sa_synchronize(self._h))
 

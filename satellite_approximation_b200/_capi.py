@@ -13,7 +13,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SATFILL_LIB") or os.path.join(_HERE, "lib", "libsatfill.so")  # SATFILL_LIB: tuning builds
-ABI_VERSION = 3  # SATFILL_ABI_VERSION of include/satfill.h
+ABI_VERSION = 4  # SATFILL_ABI_VERSION of include/satfill.h
 
 SA_OK, SA_EMPTY_MASK, SA_NOT_CONVERGED, SA_SIZE_MISMATCH, SA_BAD_ARGUMENT, SA_CUDA_ERROR, SA_NCCL_ERROR, SA_OOM = range(8)
 SA_LAPLACE, SA_POISSON = 0, 1
@@ -32,7 +32,7 @@ EXPORTS = [
     "sa_scene_create", "sa_scene_destroy", "sa_scene_set_mask", "sa_scene_set_band", "sa_scene_set_guidance",
     "sa_scene_solve", "sa_scene_get_band", "sa_scene_info", "sa_scene_precondition", "sa_synchronize",
     "sa_dist_unique_id", "sa_dist_init", "sa_dist_partition", "sa_dist_levels", "sa_scene_set_distributed",
-    "sa_scene_owned_rows", "sa_scene_allgather_band", "sa_apply_laplace_u8", "sa_morph_close_mask",
+    "sa_scene_owned_rows", "sa_scene_allgather_band", "sa_apply_laplace_u8", "sa_morph_close_mask", "sa_last_fill_direct",
 ]  # fmt: skip
 
 
@@ -156,6 +156,8 @@ def load() -> C.CDLL:
     L.sa_apply_laplace_u8.argtypes = [_vp, _vp, _vp, _i64, _i64, C.c_int, C.c_double, _vp, _vp, C.POINTER(Options), _vp]
     L.sa_morph_close_mask.restype = C.c_int
     L.sa_morph_close_mask.argtypes = [_vp, _vp, _i64, _i64, _i64, _i64, C.c_int, _vp]
+    L.sa_last_fill_direct.restype = C.c_int
+    L.sa_last_fill_direct.argtypes = [_vp]
     L.sa_synchronize.restype = C.c_int
     L.sa_synchronize.argtypes = [_vp]
     if L.sa_abi_version() != ABI_VERSION:

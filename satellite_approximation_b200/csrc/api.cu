@@ -654,6 +654,124 @@ static int host_fill(sa_ctx* ctx, int problem, double* const* images, const doub
                                  : (o.mg_variant == SA_MG_RB32 && o.cg_variant == 0 ? WORK_RB : WORK_J64)));
     if (s->n_unknowns == 0)
         return solve_scene(s, o, stats);  // fills stats, returns SA_EMPTY_MASK
+    // 2a. Direct mode: when the caller's arrays are page-locked (cudaMallocHost / cudaHostRegister / torch pin_memory) the
+    //     device can address them, and no image is copied at all: the set-up kernel reads, straight from host memory,
+    //     only the pixels the equations look at -- the ring of known pixels around the unknown set, plus g on the unknown
+    //     set for Poisson -- and a scatter kernel stores only the unknown pixels back.  Known pixels never cross PCIe.
+    {
+        bool direct = std::getenv("SATFILL_NO_DIRECT") == nullptr && o.cg_variant == 0
+            && (o.precond != SA_PRECOND_MULTIGRID || o.mg_variant == SA_MG_RB32) && s->cols % 2 == 0 && s->rows > 0;
+        const int64_t sp = slow_stride(s, rs, cs);
+        direct = direct && sp % 2 == 0;
+        std::vector<double*> dev_f((size_t)nbands, nullptr);
+        std::vector<const double*> dev_g((size_t)nbands, nullptr);
+        for (int b = 0; b < nbands && direct; ++b) {
+            cudaPointerAttributes at {};
+            if (cudaPointerGetAttributes(&at, images[b]) != cudaSuccess || at.type != cudaMemoryTypeHost || !at.devicePointer
+                || ((uintptr_t)at.devicePointer & 15)) {
+                direct = false;
+                break;
+            }
+            dev_f[(size_t)b] = (double*)at.devicePointer;
+            if (problem == SA_POISSON) {
+                cudaPointerAttributes ag {};
+                if (cudaPointerGetAttributes(&ag, guidance[b]) != cudaSuccess || ag.type != cudaMemoryTypeHost || !ag.devicePointer
+                    || ((uintptr_t)ag.devicePointer & 15)) {
+                    direct = false;
+                    break;
+                }
+                dev_g[(size_t)b] = (const double*)ag.devicePointer;
+            }
+        }
+        cudaGetLastError();  // cudaPointerGetAttributes on pageable memory may leave a sticky-free error behind
+        ctx->last_fill_direct = direct;
+        if (direct) {
+            // chunks: the scatter of chunk c (io_out) overlaps the solve of chunk c + 1
+            const int64_t band_bytes = s->rows * s->cols * (int64_t)sizeof(double);
+            int64_t chunk_bytes = (int64_t)256 << 20;
+            if (const char* e = std::getenv("SATFILL_CHUNK_BYTES"))
+                chunk_bytes = std::max<int64_t>(1, std::atoll(e));
+            int per_chunk = (int)std::min<int64_t>(std::min(nbands, HOST_BANDS_MAX), std::max<int64_t>(1, chunk_bytes / std::max<int64_t>(band_bytes, 1)));
+            if (per_chunk >= nbands && nbands <= HOST_BANDS_MAX)
+                per_chunk = nbands;
+            const int nch = (nbands + per_chunk - 1) / per_chunk;
+            if (!ctx->io_out) {
+                SA_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->io_in, cudaStreamNonBlocking));
+                SA_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->io_out, cudaStreamNonBlocking));
+            }
+            const Level lv = fine_level(s);
+            auto window = [&](int b0, int b1) {
+                HostBands hb {};
+                for (int b = b0; b < b1; ++b) {
+                    hb.f[b - b0] = dev_f[(size_t)b];
+                    hb.g[b - b0] = dev_g[(size_t)b];
+                }
+                hb.pitch = sp;
+                hb.rows = s->rows;
+                hb.cols = s->cols;
+                return hb;
+            };
+            int st = SA_OK;
+            const bool dbg = std::getenv("SATFILL_DEBUG_IO") != nullptr;
+            auto now_ms = [] { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; };
+            const double t_start = now_ms();
+            // While window c is solved on the context's stream, the set-up kernel of window c + 1 pulls its known ring over
+            // PCIe on io_in (two CTAs per SM, in the background) and io_out carries the unknowns of window c - 1 back.
+            SA_TRY(prepare_solve(s, o));
+            while ((int)ctx->io_ev.size() < nch) {
+                cudaEvent_t e;
+                SA_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+                ctx->io_ev.push_back(e);
+            }
+            if (nch > 1) {
+                // the housekeeping of prepare_solve (scrub, clears) must be complete before another stream touches the planes
+                SA_CUDA(ctx, cudaEventRecord(ctx->io_ev[0], ctx->stream));
+                SA_CUDA(ctx, cudaStreamWaitEvent(ctx->io_in, ctx->io_ev[0], 0));
+            }
+            for (int c = 0; c < nch; ++c) {
+                const int b0 = c * per_chunk, b1 = std::min(nbands, (c + 1) * per_chunk);
+                const HostBands hb = window(b0, b1);
+                s->band0 = b0;
+                s->band_n = b1 - b0;
+                s->direct = &hb;
+                if (c > 0) {
+                    s->window_ready = true;
+                    s->setup_ready = ctx->io_ev[(size_t)c];
+                }
+                if (c + 1 < nch) {  // the next window's set-up trickles in on io_in while this one is solved
+                    const int n0 = (c + 1) * per_chunk, n1 = std::min(nbands, (c + 2) * per_chunk);
+                    const HostBands hbn = window(n0, n1);
+                    SA_TRY(presetup_window(s, o, n0, n1 - n0, &hbn, ctx->io_in, ctx->io_ev[(size_t)c + 1]));
+                }
+                int stc = solve_scene(s, o, stats ? stats + b0 : nullptr);  // returns with the context's stream drained
+                s->direct = nullptr;
+                s->window_ready = false;
+                s->band0 = 0;
+                s->band_n = -1;
+                if (stc != SA_OK && stc != SA_NOT_CONVERGED) {
+                    cudaStreamSynchronize(ctx->io_in);
+                    cudaStreamSynchronize(ctx->io_out);
+                    return stc;
+                }
+                if (stc != SA_OK)
+                    st = stc;
+                if (dbg)
+                    std::fprintf(stderr, "[satfill io] direct chunk %d: solved at %.1f ms (set-up %.1f ms, solve %.1f ms)\n", c,
+                        now_ms() - t_start, stats ? stats[b0].setup_ms : 0.0, stats ? stats[b0].solve_ms : 0.0);
+                if (problem == SA_LAPLACE)  // never looks at the solver status (laplace.cpp:113-119)
+                    SA_TRY(launch_scatter_direct(ctx, ctx->io_out, lv, b1 - b0, s->plane0(s->u, b0), hb));
+            }
+            if (problem == SA_POISSON && st == SA_OK)  // nothing is written unless every band converged (poisson.cpp:263-269)
+                for (int c = 0; c < nch; ++c) {
+                    const int b0 = c * per_chunk, b1 = std::min(nbands, (c + 1) * per_chunk);
+                    SA_TRY(launch_scatter_direct(ctx, ctx->io_out, lv, b1 - b0, s->plane0(s->u, b0), window(b0, b1)));
+                }
+            SA_CUDA(ctx, cudaStreamSynchronize(ctx->io_out));
+            if (dbg)
+                std::fprintf(stderr, "[satfill io] direct: all out at %.1f ms\n", now_ms() - t_start);
+            return st;
+        }
+    }
     int32_t* h_cnt = (int32_t*)ctx->pinned;
     SA_CUDA(ctx, cudaMemcpyAsync(h_cnt, s->d_counters, 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
     SA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -663,7 +781,7 @@ static int host_fill(sa_ctx* ctx, int problem, double* const* images, const doub
         row_lo = 0;
     if (row_hi > s->rows)
         row_hi = s->rows;
-    // 2. Bands cross PCIe and are solved in chunks: chunk c + 1 .. are on their way in (io_in) and chunk c - 1 is on
+    // 2b. Pageable (or oddly laid out) host arrays: bands cross PCIe whole and are solved in chunks: chunk c + 1 .. are on their way in (io_in) and chunk c - 1 is on
     //    its way out (io_out) while chunk c is solved on the context's stream.  A chunk is at least ~256 MB of image so
     //    that its transfer hides the solve's fixed costs; small scenes go through as one chunk.
     const int64_t band_bytes = (row_hi - row_lo) * s->cols * (int64_t)sizeof(double);
@@ -751,6 +869,8 @@ int sa_poisson_blend(sa_ctx* ctx, double* const* inputs, const double* const* re
 {
     return host_fill(ctx, SA_POISSON, inputs, replacements, nbands, mask, rows, cols, row_stride, col_stride, opts, stats);
 }
+
+int sa_last_fill_direct(const sa_ctx* ctx) { return ctx && ctx->last_fill_direct ? 1 : 0; }
 
 /* ---- the steps either side of the path ------------------------------------------------------------------------------ */
 

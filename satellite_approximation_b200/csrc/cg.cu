@@ -493,42 +493,22 @@ int precondition_scene(sa_scene* s, const sa_options& o)
     return SA_OK;
 }
 
-int solve_scene(sa_scene* s, const sa_options& o, sa_stats* stats)
+// Everything a solve needs before its first kernel: the index of the mask, the multigrid hierarchy, and work vectors that
+// are clean for the preconditioner about to be used.  Idempotent, so the host-pointer entry points can call it once
+// before they start set-up kernels for several band windows on another stream.
+int prepare_solve(sa_scene* s, const sa_options& o)
 {
     sa_ctx* ctx = s->ctx;
-    // the band window [band0, band0 + nb): `stats` and every per-band base pointer below start at its first band
-    const int nb = s->win_n(), b0 = s->band0;
-    BandScalars* const scal = s->scal + b0;
-    const bool poisson = s->problem == SA_POISSON;
     const bool mg = o.precond == SA_PRECOND_MULTIGRID;
     const bool rb = mg && o.mg_variant == SA_MG_RB32;
     const bool strip = o.cg_variant == 0;
-    SA_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
     SA_TRY(ensure_indexed(s, !mg ? WORK_JACOBI : (rb && strip ? WORK_RB : WORK_J64)));
     if (s->stale_r && !(rb && strip)) {  // Jacobi and the double cycle read r with its halo
         SA_CUDA(ctx, cudaMemsetAsync(s->r, 0, (size_t)s->plane * s->nbands * sizeof(double), ctx->stream));
         s->stale_r = false;
     }
-    const int64_t n = s->n_unknowns;
-    // reference defaults: Laplace 2N (IterativeSolverBase.h:251), Poisson n/2 (poisson.cpp:207)
-    int64_t max_it = o.max_iterations > 0 ? o.max_iterations : (poisson ? n / 2 : 2 * n);
-    if (max_it > (int64_t)1 << 30)
-        max_it = (int64_t)1 << 30;
-    if (stats) {
-        for (int b = 0; b < nb; ++b) {
-            stats[b] = sa_stats {};
-            stats[b].unknowns = n;
-            stats[b].max_iterations = max_it;
-            stats[b].tolerance = o.tolerance;
-            stats[b].active_tiles = s->n_active_tiles;
-        }
-    }
-    if (n == 0) {  // laplace.cpp:41-44: nothing to do
-        if (stats)
-            for (int b = 0; b < nb; ++b)
-                stats[b].status = SA_EMPTY_MASK;
-        return SA_EMPTY_MASK;
-    }
+    if (s->n_unknowns == 0)
+        return SA_OK;
     if (mg)
         SA_TRY(ensure_multigrid(s, o));
     {
@@ -548,6 +528,69 @@ int solve_scene(sa_scene* s, const sa_options& o, sa_stats* stats)
             SA_CUDA(ctx, cudaMemsetAsync(s->p[1], 0, bytes, ctx->stream));
         }
         s->work_dirty = (s->work_dirty & ~WORK_PF) | kind | (pf_now ? WORK_PF : 0);
+    }
+    return SA_OK;
+}
+
+// The set-up of one band window on `stream` (strip kernels, not distributed): scalars cleared, x0 / r0 / norms, stop
+// threshold; `done` is recorded behind it.  solve_scene then skips its own set-up for that window (sa_scene::window_ready).
+int presetup_window(sa_scene* s, const sa_options& o, int b0, int nb, const HostBands* direct, cudaStream_t stream, cudaEvent_t done)
+{
+    sa_ctx* ctx = s->ctx;
+    const bool mg = o.precond == SA_PRECOND_MULTIGRID;
+    const bool rb = mg && o.mg_variant == SA_MG_RB32;
+    const bool poisson = s->problem == SA_POISSON;
+    BandScalars* scal = s->scal + b0;
+    cudaStream_t saved = ctx->stream;
+    ctx->stream = stream;  // every launch helper of the library issues on the context's stream
+    int st = SA_OK;
+    if (cudaMemsetAsync(scal, 0, sizeof(BandScalars) * nb, stream) != cudaSuccess)
+        st = fail(ctx, SA_CUDA_ERROR, "presetup: memset");
+    float* rf = rb ? (float*)s->z + (int64_t)s->plane * s->nbands + s->pitch + (int64_t)b0 * s->plane : nullptr;
+    if (st == SA_OK)
+        st = launch_setup2(ctx, fine_level(s), nb, poisson, s->plane0(s->u, b0), poisson ? s->plane0(s->g, b0) : nullptr,
+            s->plane0(s->r, b0), rf, scal, direct, /*background=*/true);
+    if (st == SA_OK) {
+        k_finalize_setup<<<(nb + 63) / 64, 64, 0, stream>>>(scal, nb, o.tolerance, mg ? 1 : 0);
+        ctx->launches += 1;
+        if (cudaGetLastError() != cudaSuccess || cudaEventRecord(done, stream) != cudaSuccess)
+            st = fail(ctx, SA_CUDA_ERROR, "presetup: launch");
+    }
+    ctx->stream = saved;
+    return st;
+}
+
+int solve_scene(sa_scene* s, const sa_options& o, sa_stats* stats)
+{
+    sa_ctx* ctx = s->ctx;
+    // the band window [band0, band0 + nb): `stats` and every per-band base pointer below start at its first band
+    const int nb = s->win_n(), b0 = s->band0;
+    BandScalars* const scal = s->scal + b0;
+    const bool poisson = s->problem == SA_POISSON;
+    const bool mg = o.precond == SA_PRECOND_MULTIGRID;
+    const bool rb = mg && o.mg_variant == SA_MG_RB32;
+    const bool strip = o.cg_variant == 0;
+    SA_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
+    SA_TRY(prepare_solve(s, o));
+    const int64_t n = s->n_unknowns;
+    // reference defaults: Laplace 2N (IterativeSolverBase.h:251), Poisson n/2 (poisson.cpp:207)
+    int64_t max_it = o.max_iterations > 0 ? o.max_iterations : (poisson ? n / 2 : 2 * n);
+    if (max_it > (int64_t)1 << 30)
+        max_it = (int64_t)1 << 30;
+    if (stats) {
+        for (int b = 0; b < nb; ++b) {
+            stats[b] = sa_stats {};
+            stats[b].unknowns = n;
+            stats[b].max_iterations = max_it;
+            stats[b].tolerance = o.tolerance;
+            stats[b].active_tiles = s->n_active_tiles;
+        }
+    }
+    if (n == 0) {  // laplace.cpp:41-44: nothing to do
+        if (stats)
+            for (int b = 0; b < nb; ++b)
+                stats[b].status = SA_EMPTY_MASK;
+        return SA_EMPTY_MASK;
     }
     // one system split by rows across the ranks of the context's communicator (dist.cu)
     const bool dist = s->distributed && ctx->world > 1;
@@ -573,10 +616,15 @@ int solve_scene(sa_scene* s, const sa_options& o, sa_stats* stats)
     double* pbuf[2] = { s->plane0(s->p[0], b0), s->plane0(s->p[1], b0) };
     float* pbuf_f[2] = { (float*)s->p[0] + s->pitch + (int64_t)b0 * s->plane, (float*)s->p[1] + s->pitch + (int64_t)b0 * s->plane };
 
+    if (s->window_ready) {
+        // the window's set-up was issued on another stream (presetup_window): wait for it instead of repeating it
+        s->window_ready = false;
+        SA_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, s->setup_ready, 0));
+    } else {
     SA_CUDA(ctx, cudaMemsetAsync(scal, 0, sizeof(BandScalars) * nb, ctx->stream));
     if (strip) {
         // one pass: x0, r0 = b - A x0 from the KNOWN neighbours only (so no halo of x0 is needed), the three norms
-        SA_TRY(launch_setup2(ctx, lv, nb, poisson, u0, g0, r0, rb ? s->rb_rf() : nullptr, scal));
+        SA_TRY(launch_setup2(ctx, lv, nb, poisson, u0, g0, r0, rb ? s->rb_rf() : nullptr, scal, s->direct));
     } else {
         if (have_tiles) {
             if (poisson)
@@ -601,6 +649,7 @@ int solve_scene(sa_scene* s, const sa_options& o, sa_stats* stats)
             SA_TRY(dist_halo<double>(s, 0, r0, s->pitch, s->plane, 1, 1));
     }
     SA_LAUNCH(ctx, k_finalize_setup, (nb + 63) / 64, 64, 0, scal, nb, o.tolerance, mg ? 1 : 0);
+    }
     SA_CUDA(ctx, cudaGetLastError());
     SA_CUDA(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
 

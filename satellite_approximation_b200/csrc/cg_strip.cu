@@ -18,6 +18,8 @@
 #include "common.cuh"
 #include "tile.cuh"
 
+#include <cstdlib>
+
 namespace satfill {
 
 namespace {
@@ -513,9 +515,14 @@ __global__ void __launch_bounds__(ST_THREADS, ST_UPD_CTAS) k_update2(Level lv, i
 //   A neighbour outside the image is a "known" cell holding zeros (guard rows / columns), so it drops out by itself.
 //   Unknown cells of u hold whatever the previous fill left there: they are only ever used through the known mask.
 // ---------------------------------------------------------------------------------------------------------------
-template <bool POISSON, bool RF>
+//   DIRECT: f (and g) are read straight from the CALLER'S host arrays (page-locked memory is device-addressable), and
+//   only where the equations look at them: a pair of cells that are both unknowns is never fetched, so what crosses PCIe
+//   on the way in is the ring of known pixels around the unknown set (and, for Poisson, g on the unknown set) instead of
+//   whole images.  The image plane u then only ever holds x: its known cells are never read by the solver.
+template <bool POISSON, bool RF, bool DIRECT>
 __global__ void __launch_bounds__(ST_THREADS, 4) k_setup2(Level lv, int nbands, double* __restrict__ u,
-    const double* __restrict__ g, double* __restrict__ rvec, float* __restrict__ rf, BandScalars* __restrict__ scal)
+    const double* __restrict__ g, double* __restrict__ rvec, float* __restrict__ rf, BandScalars* __restrict__ scal,
+    HostBands src)
 {
     constexpr bool FIXED = !POISSON;
     __shared__ double s_red[ST_WARPS];
@@ -527,13 +534,17 @@ __global__ void __launch_bounds__(ST_THREADS, 4) k_setup2(Level lv, int nbands, 
         BandScalars& sc = scal[band];
         const int64_t band_off = (int64_t)band * lv.plane;
         double* uband = u + band_off;
-        const double* gband = POISSON ? g + band_off : nullptr;
+        const double* gband = POISSON ? (DIRECT ? src.g[band] : g + band_off) : nullptr;
+        const double* fband = DIRECT ? src.f[band] : uband;
+        const int fpitch = DIRECT ? (int)src.pitch : pitch;           // elements per row of the f / g source
+        const int ftoff = (row0 - 1) * fpitch + 2 * cx;
         double* rband = rvec + band_off;
         float* rfband = RF ? rf + band_off : nullptr;
         double b2 = 0.0, r2 = 0.0, rz = 0.0;
         auto no_prefetch = [](const TileBits&) {};
         for_each_tile(lv, cx, row0, [&](const TileBits& tb, const TileBits&, bool, auto&) {
             const int origin = tb.origin(pitch);
+            const int forigin = DIRECT ? tb.origin(fpitch) : origin;
             const unsigned mL = tb.mL(), mR = tb.mR(), any = tb.any();
             // unknown bits of the columns west of the pair's left cell and east of its right cell, own rows
             unsigned mW = __shfl_up_sync(0xffffffffu, mR, 1), mE = __shfl_down_sync(0xffffffffu, mL, 1);
@@ -548,25 +559,41 @@ __global__ void __launch_bounds__(ST_THREADS, 4) k_setup2(Level lv, int nbands, 
             const unsigned own = any & ST_OWN;  // own rows that hold an unknown of the pair
             // rows to load: those, the rows above / below them, and the rows an adjacent lane's unknowns look at (u and g
             // hold real pixel values at known cells, unlike the solver's work vectors)
-            const unsigned ldm = (own | (own << 1) | (own >> 1) | __shfl_up_sync(0xffffffffu, own, 1) | __shfl_down_sync(0xffffffffu, own, 1)) & ST_NRM;
+            unsigned ldm = (own | (own << 1) | (own >> 1) | __shfl_up_sync(0xffffffffu, own, 1) | __shfl_down_sync(0xffffffffu, own, 1)) & ST_NRM;
+            const int64_t gr = (int64_t)tb.ty() * TILE_H + row0, gc = (int64_t)tb.tx() * TILE_W + 2 * cx;
+            unsigned em = (west ? mL : (east ? mR : 0u)) >> 1;  // own rows whose edge cell is an unknown
+            unsigned ldf = ldm, emf = em;
+            if (DIRECT) {
+                // the caller's array has no guard rows / padding columns: stay inside it (a cell outside is a known zero)
+                unsigned inside = 0;
+#pragma unroll
+                for (int j = 0; j < ST_NR; ++j)
+                    inside |= (gr - 1 + j >= 0 && gr - 1 + j < src.rows && gc + 1 < src.cols) ? (1u << j) : 0u;
+                ldm &= inside;
+                const int64_t ec = west ? gc - 1 : gc + 2;
+                if (ec < 0 || ec >= src.cols)
+                    em = 0;
+                em &= inside >> 1;
+                ldf = ldm & ~(mL & mR);                       // a pair of two unknowns holds nothing the equations read
+                emf = em & ~((west ? mW : mE) >> 1);          // nor does a halo cell that is an unknown itself
+            }
             double* ub = uband + origin;
+            const double* fb = fband + forigin;
             double2 uv[ST_NR], gv[ST_NR];
             double ue[ST_RG], ge[ST_RG];
 #pragma unroll
             for (int j = 0; j < ST_NR; ++j) {
-                uv[j] = ld2_if(ub + (toff + j * pitch), ldm, 1u << j);
-                gv[j] = POISSON ? ldnc2_if(gband + origin + (toff + j * pitch), ldm, 1u << j) : make_double2(0.0, 0.0);
+                uv[j] = ld2_if(fb + (ftoff + j * fpitch), ldf, 1u << j);
+                gv[j] = POISSON ? ldnc2_if(gband + forigin + (ftoff + j * fpitch), ldm, 1u << j) : make_double2(0.0, 0.0);
             }
             {
-                const int eoff = toff + (west ? -1 : 2);
-                const unsigned em = (west ? mL : (east ? mR : 0u)) >> 1;
+                const int eoff = ftoff + (west ? -1 : 2);
 #pragma unroll
                 for (int j = 0; j < ST_RG; ++j) {
-                    ue[j] = ld_if(ub + (eoff + (j + 1) * pitch), em, 1u << j);
-                    ge[j] = POISSON ? ldnc_if(gband + origin + (eoff + (j + 1) * pitch), em, 1u << j) : 0.0;
+                    ue[j] = ld_if(fb + (eoff + (j + 1) * fpitch), emf, 1u << j);
+                    ge[j] = POISSON ? ldnc_if(gband + forigin + (eoff + (j + 1) * fpitch), em, 1u << j) : 0.0;
                 }
             }
-            const int64_t gr = (int64_t)tb.ty() * TILE_H + row0, gc = (int64_t)tb.tx() * TILE_W + 2 * cx;
             const int dcL = diag_col<FIXED>(lv, gc), dcR = diag_col<FIXED>(lv, gc + 1);
             const unsigned st2 = sector_or2(own), st4 = RF ? sector_or4(st2) : 0u;
 #pragma unroll
@@ -681,22 +708,100 @@ static unsigned strip_grid(const sa_ctx* ctx, const Level& lv, int ctas_per_sm)
 }
 
 int launch_setup2(sa_ctx* ctx, const Level& lv, int nbands, bool poisson, double* u, const double* g, double* r, float* rf,
-    BandScalars* scal)
+    BandScalars* scal, const HostBands* direct, bool background)
 {
     if (lv.n_tiles == 0)
         return SA_OK;
-    const unsigned grid = strip_grid(ctx, lv, 4);
-    if (poisson) {
+    // background: issued beside a running solve (api.cu, direct mode) -- a few dozen CTAs keep PCIe busy with reads; more
+    // only slow the solve down (measured: 32 set-up + 16 scatter CTAs give the shortest call)
+    int bg = 32;
+    if (const char* e = std::getenv("SATFILL_PRESETUP_CTAS"))  // tuning knob
+        bg = std::atoi(e) > 0 ? std::atoi(e) : bg;
+    const unsigned grid = background ? (unsigned)(bg < lv.n_tiles ? bg : lv.n_tiles) : strip_grid(ctx, lv, 4);
+    const HostBands none {};
+#define SA_SETUP(P, R, D) \
+    SA_LAUNCH(ctx, (k_setup2<P, R, D>), grid, ST_THREADS, 0, lv, nbands, u, g, r, rf, scal, direct ? *direct : none)
+    if (direct) {
+        if (nbands > HOST_BANDS_MAX)
+            return fail(ctx, SA_BAD_ARGUMENT, "direct set-up: too many bands in one window");
+        if (poisson) {
+            if (rf)
+                SA_SETUP(true, true, true);
+            else
+                SA_SETUP(true, false, true);
+        } else {
+            if (rf)
+                SA_SETUP(false, true, true);
+            else
+                SA_SETUP(false, false, true);
+        }
+    } else if (poisson) {
         if (rf)
-            SA_LAUNCH(ctx, (k_setup2<true, true>), grid, ST_THREADS, 0, lv, nbands, u, g, r, rf, scal);
+            SA_SETUP(true, true, false);
         else
-            SA_LAUNCH(ctx, (k_setup2<true, false>), grid, ST_THREADS, 0, lv, nbands, u, g, r, rf, scal);
+            SA_SETUP(true, false, false);
     } else {
         if (rf)
-            SA_LAUNCH(ctx, (k_setup2<false, true>), grid, ST_THREADS, 0, lv, nbands, u, g, r, rf, scal);
+            SA_SETUP(false, true, false);
         else
-            SA_LAUNCH(ctx, (k_setup2<false, false>), grid, ST_THREADS, 0, lv, nbands, u, g, r, rf, scal);
+            SA_SETUP(false, false, false);
     }
+#undef SA_SETUP
+    return SA_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// k_scatter_direct: the way out of the direct mode.  The unknown pixels -- and nothing else -- are stored from the image
+// plane straight into the caller's page-locked arrays: 16 bytes where both cells of a pair are unknowns, 8 bytes where
+// one is.  Known pixels never cross PCIe in either direction (laplace.cpp:117-119 / poisson.cpp:273-283 only write the
+// invalid pixels too).
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(ST_THREADS) k_scatter_direct(Level lv, int nbands, const double* __restrict__ u, HostBands dst)
+{
+    const int cx = threadIdx.x & 15, row0 = (threadIdx.x >> 4) * ST_RG;
+    const int pitch = (int)lv.pitch, hpitch = (int)dst.pitch;
+    for (int i = blockIdx.x; i < lv.n_tiles; i += gridDim.x) {
+        const TileBits tb = load_tile_bits(lv, lv.tile_yx[i], cx, row0);
+        const unsigned mL = tb.mL(), mR = tb.mR();
+        if (((mL | mR) & ST_OWN) == 0)
+            continue;
+        const int o = tb.origin(pitch) + (row0 - 1) * pitch + 2 * cx;
+        const int ho = tb.origin(hpitch) + (row0 - 1) * hpitch + 2 * cx;
+        for (int band = 0; band < nbands; ++band) {
+            const double* ub = u + (int64_t)band * lv.plane;
+            double* hb = dst.f[band];
+#pragma unroll
+            for (int j = 1; j <= ST_RG; ++j) {
+                const bool l = (mL >> j) & 1, r = (mR >> j) & 1;
+                if (l | r) {
+                    const double2 v = *reinterpret_cast<const double2*>(ub + (o + j * pitch));
+                    double* h = hb + (ho + j * hpitch);
+                    if (l & r)
+                        *reinterpret_cast<double2*>(h) = v;
+                    else if (l)
+                        h[0] = v.x;
+                    else
+                        h[1] = v.y;
+                }
+            }
+        }
+    }
+}
+
+int launch_scatter_direct(sa_ctx* ctx, cudaStream_t stream, const Level& lv, int nbands, const double* u, const HostBands& dst)
+{
+    if (lv.n_tiles == 0 || nbands == 0)
+        return SA_OK;
+    if (nbands > HOST_BANDS_MAX)
+        return fail(ctx, SA_BAD_ARGUMENT, "direct scatter: too many bands in one window");
+    // a modest grid: the stores are bound by PCIe, and the next chunk's solve wants the SMs
+    int want = 16;  // the stores are bound by PCIe; more CTAs only take slots from the solve that runs beside them
+    if (const char* e = std::getenv("SATFILL_SCATTER_CTAS"))  // tuning knob
+        want = std::atoi(e) > 0 ? std::atoi(e) : want;
+    unsigned grid = (unsigned)(want < lv.n_tiles ? want : lv.n_tiles);
+    k_scatter_direct<<<grid, ST_THREADS, 0, stream>>>(lv, nbands, u, dst);
+    ctx->launches += 1;
+    SA_CUDA(ctx, cudaGetLastError());
     return SA_OK;
 }
 

@@ -637,3 +637,89 @@ def test_apply_laplace_vs_reference_eigen(ctx, prepost_cases):
     assert not m0.any() and np.array_equal(same, img.astype(np.float64))
     with pytest.raises(RuntimeError):
         ctx.apply_laplace(img, inv[:-1], 220.0)
+
+
+# ---- direct mode of the host-pointer entry points: page-locked caller arrays are read / written in place over PCIe ----------
+def _pinned(a: np.ndarray, order: str = "C") -> np.ndarray:
+    """A page-locked copy of `a` with the requested memory order (numpy view of a pinned torch tensor)."""
+    import torch
+
+    if order == "F":
+        t = torch.empty((a.shape[1], a.shape[0]), dtype=torch.from_numpy(np.zeros(1, a.dtype)).dtype).pin_memory()
+        v = t.numpy().T
+    else:
+        t = torch.empty(a.shape, dtype=torch.from_numpy(np.zeros(1, a.dtype)).dtype).pin_memory()
+        v = t.numpy()
+    v[...] = a
+    _pinned.keep.append(t)  # the numpy view does not own the page-locked storage
+    return v
+
+
+_pinned.keep = []
+
+
+@pytest.mark.parametrize("order", ["C", "F"])
+@pytest.mark.parametrize("precond", ["multigrid", "jacobi"])
+def test_direct_mode_on_page_locked_arrays(ctx, port, monkeypatch, order, precond):
+    """With page-locked caller arrays no image is copied: k_setup2<DIRECT> reads the known ring (and g) from host memory
+    and k_scatter_direct stores the unknown pixels back.  Must equal the copy path and the oracle; known pixels must
+    stay bit-identical; Poisson unknowns on the image border exercise the out-of-image neighbours."""
+    rows, cols, nb = 154, 172, 3
+    pc = sab.MULTIGRID if precond == "multigrid" else sab.JACOBI
+    lmask = synth.blob_mask(rows, cols, cover=0.4, sigma=5.0, seed=31)
+    pmask = synth.blob_mask(rows, cols, cover=0.4, sigma=5.0, seed=32, clear_border=False)
+    assert pmask[0].any() and pmask[:, -1].any()
+    bands = [synth.smooth_band(rows, cols, seed=80 + b) for b in range(nb)]
+    guides = [synth.second_date(b, seed=7 + i) for i, b in enumerate(bands)]
+    for chunk in (None, "1"):  # one window, or one band per window
+        if chunk:
+            monkeypatch.setenv("SATFILL_CHUNK_BYTES", chunk)
+        # Laplace
+        got = [_pinned(b, order) for b in bands]
+        m = np.array(lmask, order=order)
+        st = ctx.laplace_fill(got, m, tolerance=1e-12, precond=pc)
+        assert all(s["status"] == sab.SA_OK for s in st) and ctx.last_fill_direct
+        for b in range(nb):
+            want, _ = port.laplace_fill(bands[b], lmask, mode=1, tol=1e-13)
+            assert rel_max_abs(got[b], want, lmask) < 1e-8
+            assert np.array_equal(got[b][~lmask], bands[b][~lmask])
+        # Poisson
+        pgot = [_pinned(b, order) for b in bands]
+        pg = [_pinned(g, order) for g in guides]
+        pst = ctx.poisson_blend(pgot, pg, np.array(pmask, order=order), tolerance=1e-12, max_iterations=10**6, precond=pc)
+        assert all(s["status"] == sab.SA_OK for s in pst) and ctx.last_fill_direct
+        pwant, _ = port.poisson_blend(bands, guides, pmask, tol=1e-13, max_it=10**6)
+        for b in range(nb):
+            assert rel_max_abs(pgot[b], pwant[b], pmask) < 1e-7
+            assert np.array_equal(pgot[b][~pmask], bands[b][~pmask])
+        # a band that cannot converge: nothing is written (poisson.cpp:263-269)
+        pfail = [_pinned(b, order) for b in bands]
+        stf = ctx.poisson_blend(pfail, pg, np.array(pmask, order=order), tolerance=1e-13, max_iterations=2, precond=sab.JACOBI)
+        assert any(s["status"] == sab.SA_NOT_CONVERGED for s in stf)
+        assert all(np.array_equal(pfail[b], bands[b]) for b in range(nb))
+    # the copy path on the same page-locked arrays gives the same fill
+    monkeypatch.setenv("SATFILL_NO_DIRECT", "1")
+    ref = [_pinned(b, order) for b in bands]
+    ctx.laplace_fill(ref, np.array(lmask, order=order), tolerance=1e-12, precond=pc)
+    assert not ctx.last_fill_direct
+    monkeypatch.delenv("SATFILL_NO_DIRECT")
+    cur = [_pinned(b, order) for b in bands]
+    ctx.laplace_fill(cur, np.array(lmask, order=order), tolerance=1e-12, precond=pc)
+    for b in range(nb):
+        assert rel_max_abs(cur[b], ref[b], lmask) < 1e-8
+
+
+def test_direct_mode_falls_back_on_odd_widths(ctx, port):
+    """Pairs of cells are read 16 bytes at a time: arrays whose fast extent is odd take the copy path, same answers."""
+    rows, cols = 95, 131
+    mask = synth.blob_mask(rows, cols, cover=0.35, sigma=4.0, seed=41)
+    img = synth.smooth_band(rows, cols, seed=90)
+    want, _ = port.laplace_fill(img, mask, mode=1, tol=1e-13)
+    for order in ("C", "F"):
+        got = _pinned(img, order)
+        ctx.laplace_fill([got], np.array(mask, order=order), tolerance=1e-12, precond=sab.MULTIGRID)
+        assert not ctx.last_fill_direct
+        assert rel_max_abs(got, want, mask) < 1e-8 and np.array_equal(got[~mask], img[~mask])
+    pageable = img.copy()  # pageable memory: copied whole
+    ctx.laplace_fill([pageable], mask, tolerance=1e-12, precond=sab.MULTIGRID)
+    assert not ctx.last_fill_direct and rel_max_abs(pageable, want, mask) < 1e-8
