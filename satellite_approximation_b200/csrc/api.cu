@@ -715,37 +715,31 @@ static int host_fill(sa_ctx* ctx, int problem, double* const* images, const doub
             const bool dbg = std::getenv("SATFILL_DEBUG_IO") != nullptr;
             auto now_ms = [] { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; };
             const double t_start = now_ms();
-            // While window c is solved on the context's stream, the set-up kernel of window c + 1 pulls its known ring over
-            // PCIe on io_in (two CTAs per SM, in the background) and io_out carries the unknowns of window c - 1 back.
+            // While window c is solved on the context's stream, k_fetch_direct pulls the known ring of window c + 1 over PCIe
+            // on io_in and k_scatter_direct carries the unknowns of window c - 1 back on io_out (a few CTAs each).
             SA_TRY(prepare_solve(s, o));
             while ((int)ctx->io_ev.size() < nch) {
                 cudaEvent_t e;
                 SA_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
                 ctx->io_ev.push_back(e);
             }
-            if (nch > 1) {
-                // the housekeeping of prepare_solve (scrub, clears) must be complete before another stream touches the planes
-                SA_CUDA(ctx, cudaEventRecord(ctx->io_ev[0], ctx->stream));
-                SA_CUDA(ctx, cudaStreamWaitEvent(ctx->io_in, ctx->io_ev[0], 0));
-            }
+            auto fetch = [&](int c) {
+                const int b0 = c * per_chunk, b1 = std::min(nbands, (c + 1) * per_chunk);
+                SA_TRY(launch_fetch_direct(ctx, ctx->io_in, lv, b1 - b0, problem == SA_POISSON, s->plane0(s->u, b0),
+                    problem == SA_POISSON ? s->plane0(s->g, b0) : nullptr, window(b0, b1)));
+                SA_CUDA(ctx, cudaEventRecord(ctx->io_ev[(size_t)c], ctx->io_in));
+                return (int)SA_OK;
+            };
+            SA_TRY(fetch(0));
             for (int c = 0; c < nch; ++c) {
                 const int b0 = c * per_chunk, b1 = std::min(nbands, (c + 1) * per_chunk);
                 const HostBands hb = window(b0, b1);
                 s->band0 = b0;
                 s->band_n = b1 - b0;
-                s->direct = &hb;
-                if (c > 0) {
-                    s->window_ready = true;
-                    s->setup_ready = ctx->io_ev[(size_t)c];
-                }
-                if (c + 1 < nch) {  // the next window's set-up trickles in on io_in while this one is solved
-                    const int n0 = (c + 1) * per_chunk, n1 = std::min(nbands, (c + 2) * per_chunk);
-                    const HostBands hbn = window(n0, n1);
-                    SA_TRY(presetup_window(s, o, n0, n1 - n0, &hbn, ctx->io_in, ctx->io_ev[(size_t)c + 1]));
-                }
+                SA_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->io_ev[(size_t)c], 0));  // this window's ring has landed
+                if (c + 1 < nch)
+                    SA_TRY(fetch(c + 1));  // the next one trickles in while this window is solved
                 int stc = solve_scene(s, o, stats ? stats + b0 : nullptr);  // returns with the context's stream drained
-                s->direct = nullptr;
-                s->window_ready = false;
                 s->band0 = 0;
                 s->band_n = -1;
                 if (stc != SA_OK && stc != SA_NOT_CONVERGED) {

@@ -532,34 +532,6 @@ int prepare_solve(sa_scene* s, const sa_options& o)
     return SA_OK;
 }
 
-// The set-up of one band window on `stream` (strip kernels, not distributed): scalars cleared, x0 / r0 / norms, stop
-// threshold; `done` is recorded behind it.  solve_scene then skips its own set-up for that window (sa_scene::window_ready).
-int presetup_window(sa_scene* s, const sa_options& o, int b0, int nb, const HostBands* direct, cudaStream_t stream, cudaEvent_t done)
-{
-    sa_ctx* ctx = s->ctx;
-    const bool mg = o.precond == SA_PRECOND_MULTIGRID;
-    const bool rb = mg && o.mg_variant == SA_MG_RB32;
-    const bool poisson = s->problem == SA_POISSON;
-    BandScalars* scal = s->scal + b0;
-    cudaStream_t saved = ctx->stream;
-    ctx->stream = stream;  // every launch helper of the library issues on the context's stream
-    int st = SA_OK;
-    if (cudaMemsetAsync(scal, 0, sizeof(BandScalars) * nb, stream) != cudaSuccess)
-        st = fail(ctx, SA_CUDA_ERROR, "presetup: memset");
-    float* rf = rb ? (float*)s->z + (int64_t)s->plane * s->nbands + s->pitch + (int64_t)b0 * s->plane : nullptr;
-    if (st == SA_OK)
-        st = launch_setup2(ctx, fine_level(s), nb, poisson, s->plane0(s->u, b0), poisson ? s->plane0(s->g, b0) : nullptr,
-            s->plane0(s->r, b0), rf, scal, direct, /*background=*/true);
-    if (st == SA_OK) {
-        k_finalize_setup<<<(nb + 63) / 64, 64, 0, stream>>>(scal, nb, o.tolerance, mg ? 1 : 0);
-        ctx->launches += 1;
-        if (cudaGetLastError() != cudaSuccess || cudaEventRecord(done, stream) != cudaSuccess)
-            st = fail(ctx, SA_CUDA_ERROR, "presetup: launch");
-    }
-    ctx->stream = saved;
-    return st;
-}
-
 int solve_scene(sa_scene* s, const sa_options& o, sa_stats* stats)
 {
     sa_ctx* ctx = s->ctx;
@@ -616,15 +588,10 @@ int solve_scene(sa_scene* s, const sa_options& o, sa_stats* stats)
     double* pbuf[2] = { s->plane0(s->p[0], b0), s->plane0(s->p[1], b0) };
     float* pbuf_f[2] = { (float*)s->p[0] + s->pitch + (int64_t)b0 * s->plane, (float*)s->p[1] + s->pitch + (int64_t)b0 * s->plane };
 
-    if (s->window_ready) {
-        // the window's set-up was issued on another stream (presetup_window): wait for it instead of repeating it
-        s->window_ready = false;
-        SA_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, s->setup_ready, 0));
-    } else {
     SA_CUDA(ctx, cudaMemsetAsync(scal, 0, sizeof(BandScalars) * nb, ctx->stream));
     if (strip) {
         // one pass: x0, r0 = b - A x0 from the KNOWN neighbours only (so no halo of x0 is needed), the three norms
-        SA_TRY(launch_setup2(ctx, lv, nb, poisson, u0, g0, r0, rb ? s->rb_rf() : nullptr, scal, s->direct));
+        SA_TRY(launch_setup2(ctx, lv, nb, poisson, u0, g0, r0, rb ? s->rb_rf() : nullptr, scal));
     } else {
         if (have_tiles) {
             if (poisson)
@@ -649,7 +616,6 @@ int solve_scene(sa_scene* s, const sa_options& o, sa_stats* stats)
             SA_TRY(dist_halo<double>(s, 0, r0, s->pitch, s->plane, 1, 1));
     }
     SA_LAUNCH(ctx, k_finalize_setup, (nb + 63) / 64, 64, 0, scal, nb, o.tolerance, mg ? 1 : 0);
-    }
     SA_CUDA(ctx, cudaGetLastError());
     SA_CUDA(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
 

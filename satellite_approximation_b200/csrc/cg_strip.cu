@@ -515,14 +515,9 @@ __global__ void __launch_bounds__(ST_THREADS, ST_UPD_CTAS) k_update2(Level lv, i
 //   A neighbour outside the image is a "known" cell holding zeros (guard rows / columns), so it drops out by itself.
 //   Unknown cells of u hold whatever the previous fill left there: they are only ever used through the known mask.
 // ---------------------------------------------------------------------------------------------------------------
-//   DIRECT: f (and g) are read straight from the CALLER'S host arrays (page-locked memory is device-addressable), and
-//   only where the equations look at them: a pair of cells that are both unknowns is never fetched, so what crosses PCIe
-//   on the way in is the ring of known pixels around the unknown set (and, for Poisson, g on the unknown set) instead of
-//   whole images.  The image plane u then only ever holds x: its known cells are never read by the solver.
-template <bool POISSON, bool RF, bool DIRECT>
+template <bool POISSON, bool RF>
 __global__ void __launch_bounds__(ST_THREADS, 4) k_setup2(Level lv, int nbands, double* __restrict__ u,
-    const double* __restrict__ g, double* __restrict__ rvec, float* __restrict__ rf, BandScalars* __restrict__ scal,
-    HostBands src)
+    const double* __restrict__ g, double* __restrict__ rvec, float* __restrict__ rf, BandScalars* __restrict__ scal)
 {
     constexpr bool FIXED = !POISSON;
     __shared__ double s_red[ST_WARPS];
@@ -534,17 +529,13 @@ __global__ void __launch_bounds__(ST_THREADS, 4) k_setup2(Level lv, int nbands, 
         BandScalars& sc = scal[band];
         const int64_t band_off = (int64_t)band * lv.plane;
         double* uband = u + band_off;
-        const double* gband = POISSON ? (DIRECT ? src.g[band] : g + band_off) : nullptr;
-        const double* fband = DIRECT ? src.f[band] : uband;
-        const int fpitch = DIRECT ? (int)src.pitch : pitch;           // elements per row of the f / g source
-        const int ftoff = (row0 - 1) * fpitch + 2 * cx;
+        const double* gband = POISSON ? g + band_off : nullptr;
         double* rband = rvec + band_off;
         float* rfband = RF ? rf + band_off : nullptr;
         double b2 = 0.0, r2 = 0.0, rz = 0.0;
         auto no_prefetch = [](const TileBits&) {};
         for_each_tile(lv, cx, row0, [&](const TileBits& tb, const TileBits&, bool, auto&) {
             const int origin = tb.origin(pitch);
-            const int forigin = DIRECT ? tb.origin(fpitch) : origin;
             const unsigned mL = tb.mL(), mR = tb.mR(), any = tb.any();
             // unknown bits of the columns west of the pair's left cell and east of its right cell, own rows
             unsigned mW = __shfl_up_sync(0xffffffffu, mR, 1), mE = __shfl_down_sync(0xffffffffu, mL, 1);
@@ -559,39 +550,23 @@ __global__ void __launch_bounds__(ST_THREADS, 4) k_setup2(Level lv, int nbands, 
             const unsigned own = any & ST_OWN;  // own rows that hold an unknown of the pair
             // rows to load: those, the rows above / below them, and the rows an adjacent lane's unknowns look at (u and g
             // hold real pixel values at known cells, unlike the solver's work vectors)
-            unsigned ldm = (own | (own << 1) | (own >> 1) | __shfl_up_sync(0xffffffffu, own, 1) | __shfl_down_sync(0xffffffffu, own, 1)) & ST_NRM;
+            const unsigned ldm = (own | (own << 1) | (own >> 1) | __shfl_up_sync(0xffffffffu, own, 1) | __shfl_down_sync(0xffffffffu, own, 1)) & ST_NRM;
             const int64_t gr = (int64_t)tb.ty() * TILE_H + row0, gc = (int64_t)tb.tx() * TILE_W + 2 * cx;
-            unsigned em = (west ? mL : (east ? mR : 0u)) >> 1;  // own rows whose edge cell is an unknown
-            unsigned ldf = ldm, emf = em;
-            if (DIRECT) {
-                // the caller's array has no guard rows / padding columns: stay inside it (a cell outside is a known zero)
-                unsigned inside = 0;
-#pragma unroll
-                for (int j = 0; j < ST_NR; ++j)
-                    inside |= (gr - 1 + j >= 0 && gr - 1 + j < src.rows && gc + 1 < src.cols) ? (1u << j) : 0u;
-                ldm &= inside;
-                const int64_t ec = west ? gc - 1 : gc + 2;
-                if (ec < 0 || ec >= src.cols)
-                    em = 0;
-                em &= inside >> 1;
-                ldf = ldm & ~(mL & mR);                       // a pair of two unknowns holds nothing the equations read
-                emf = em & ~((west ? mW : mE) >> 1);          // nor does a halo cell that is an unknown itself
-            }
+            const unsigned em = (west ? mL : (east ? mR : 0u)) >> 1;  // own rows whose edge cell is an unknown
             double* ub = uband + origin;
-            const double* fb = fband + forigin;
             double2 uv[ST_NR], gv[ST_NR];
             double ue[ST_RG], ge[ST_RG];
 #pragma unroll
             for (int j = 0; j < ST_NR; ++j) {
-                uv[j] = ld2_if(fb + (ftoff + j * fpitch), ldf, 1u << j);
-                gv[j] = POISSON ? ldnc2_if(gband + forigin + (ftoff + j * fpitch), ldm, 1u << j) : make_double2(0.0, 0.0);
+                uv[j] = ld2_if(ub + (toff + j * pitch), ldm, 1u << j);
+                gv[j] = POISSON ? ldnc2_if(gband + origin + (toff + j * pitch), ldm, 1u << j) : make_double2(0.0, 0.0);
             }
             {
-                const int eoff = ftoff + (west ? -1 : 2);
+                const int eoff = toff + (west ? -1 : 2);
 #pragma unroll
                 for (int j = 0; j < ST_RG; ++j) {
-                    ue[j] = ld_if(fb + (eoff + (j + 1) * fpitch), emf, 1u << j);
-                    ge[j] = POISSON ? ldnc_if(gband + forigin + (eoff + (j + 1) * fpitch), em, 1u << j) : 0.0;
+                    ue[j] = ld_if(ub + (eoff + (j + 1) * pitch), em, 1u << j);
+                    ge[j] = POISSON ? ldnc_if(gband + origin + (eoff + (j + 1) * pitch), em, 1u << j) : 0.0;
                 }
             }
             const int dcL = diag_col<FIXED>(lv, gc), dcR = diag_col<FIXED>(lv, gc + 1);
@@ -708,45 +683,131 @@ static unsigned strip_grid(const sa_ctx* ctx, const Level& lv, int ctas_per_sm)
 }
 
 int launch_setup2(sa_ctx* ctx, const Level& lv, int nbands, bool poisson, double* u, const double* g, double* r, float* rf,
-    BandScalars* scal, const HostBands* direct, bool background)
+    BandScalars* scal)
 {
     if (lv.n_tiles == 0)
         return SA_OK;
-    // background: issued beside a running solve (api.cu, direct mode) -- a few dozen CTAs keep PCIe busy with reads; more
-    // only slow the solve down (measured: 32 set-up + 16 scatter CTAs give the shortest call)
-    int bg = 32;
-    if (const char* e = std::getenv("SATFILL_PRESETUP_CTAS"))  // tuning knob
-        bg = std::atoi(e) > 0 ? std::atoi(e) : bg;
-    const unsigned grid = background ? (unsigned)(bg < lv.n_tiles ? bg : lv.n_tiles) : strip_grid(ctx, lv, 4);
-    const HostBands none {};
-#define SA_SETUP(P, R, D) \
-    SA_LAUNCH(ctx, (k_setup2<P, R, D>), grid, ST_THREADS, 0, lv, nbands, u, g, r, rf, scal, direct ? *direct : none)
-    if (direct) {
-        if (nbands > HOST_BANDS_MAX)
-            return fail(ctx, SA_BAD_ARGUMENT, "direct set-up: too many bands in one window");
-        if (poisson) {
-            if (rf)
-                SA_SETUP(true, true, true);
-            else
-                SA_SETUP(true, false, true);
-        } else {
-            if (rf)
-                SA_SETUP(false, true, true);
-            else
-                SA_SETUP(false, false, true);
-        }
-    } else if (poisson) {
+    const unsigned grid = strip_grid(ctx, lv, 4);
+    if (poisson) {
         if (rf)
-            SA_SETUP(true, true, false);
+            SA_LAUNCH(ctx, (k_setup2<true, true>), grid, ST_THREADS, 0, lv, nbands, u, g, r, rf, scal);
         else
-            SA_SETUP(true, false, false);
+            SA_LAUNCH(ctx, (k_setup2<true, false>), grid, ST_THREADS, 0, lv, nbands, u, g, r, rf, scal);
     } else {
         if (rf)
-            SA_SETUP(false, true, false);
+            SA_LAUNCH(ctx, (k_setup2<false, true>), grid, ST_THREADS, 0, lv, nbands, u, g, r, rf, scal);
         else
-            SA_SETUP(false, false, false);
+            SA_LAUNCH(ctx, (k_setup2<false, false>), grid, ST_THREADS, 0, lv, nbands, u, g, r, rf, scal);
     }
-#undef SA_SETUP
+    return SA_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// k_fetch_direct: the way in of the direct mode (api.cu).  The caller's page-locked arrays are device-addressable, so
+// nothing is copied: this kernel reads, straight from host memory, exactly the pixels k_setup2 will look at -- a pair of
+// cells that are both unknowns is never fetched, so what crosses PCIe is the ring of known pixels around the unknown set
+// (and, for Poisson, g on the unknown set and around it) -- and drops them into the image (and guidance) planes.  It runs
+// on a few CTAs beside the solve of the previous band window: the volume is tiny (2 % of the image on cloud-like masks),
+// only PCIe latency has to be covered.  Known pixels elsewhere in the planes are stale and never read.
+// ---------------------------------------------------------------------------------------------------------------
+template <bool POISSON>
+__global__ void __launch_bounds__(ST_THREADS) k_fetch_direct(Level lv, int nbands, double* __restrict__ u, double* __restrict__ g,
+    HostBands src)
+{
+    const int cx = threadIdx.x & 15, row0 = (threadIdx.x >> 4) * ST_RG;
+    const int pitch = (int)lv.pitch, fpitch = (int)src.pitch;
+    const int toff = (row0 - 1) * pitch + 2 * cx, ftoff = (row0 - 1) * fpitch + 2 * cx;
+    const bool west = cx == 0, east = cx == 15;
+    for (int i = blockIdx.x; i < lv.n_tiles; i += gridDim.x) {  // trip count is uniform over the CTA: shuffles are safe
+        const TileBits tb = load_tile_bits(lv, lv.tile_yx[i], cx, row0);
+        const unsigned mL = tb.mL(), mR = tb.mR(), any = tb.any();
+        unsigned mW = __shfl_up_sync(0xffffffffu, mR, 1), mE = __shfl_down_sync(0xffffffffu, mL, 1);
+        if (west || east) {
+            const uint32_t w = __ldg(lv.tbitsT + ((size_t)(tb.ty() + 1) * lv.tb_stride + (tb.tx() + (west ? 0 : 2))) * 32 + (west ? 31 : 0));
+            const unsigned e = ((w >> row0) & ((1u << ST_RG) - 1)) << 1;
+            if (west)
+                mW = e;
+            else
+                mE = e;
+        }
+        const unsigned own = any & ST_OWN;
+        unsigned ldm = (own | (own << 1) | (own >> 1) | __shfl_up_sync(0xffffffffu, own, 1) | __shfl_down_sync(0xffffffffu, own, 1)) & ST_NRM;
+        const int64_t gr = (int64_t)tb.ty() * TILE_H + row0, gc = (int64_t)tb.tx() * TILE_W + 2 * cx;
+        // the caller's array has no guard rows / padding columns: stay inside it (the planes hold zeros out there)
+        unsigned inside = 0;
+#pragma unroll
+        for (int j = 0; j < ST_NR; ++j)
+            inside |= (gr - 1 + j >= 0 && gr - 1 + j < src.rows && gc + 1 < src.cols) ? (1u << j) : 0u;
+        ldm &= inside;
+        unsigned em = (west ? mL : (east ? mR : 0u)) >> 1;  // own rows whose edge cell is an unknown
+        const int64_t ec = west ? gc - 1 : gc + 2;
+        if (ec < 0 || ec >= src.cols)
+            em = 0;
+        em &= inside >> 1;
+        const unsigned ldf = ldm & ~(mL & mR);               // a pair of two unknowns holds nothing the equations read
+        const unsigned emf = em & ~((west ? mW : mE) >> 1);  // nor does a halo cell that is an unknown itself
+        if ((ldm | em) == 0)
+            continue;
+        const int origin = tb.origin(pitch), forigin = tb.origin(fpitch);
+        const int eoff = toff + (west ? -1 : 2), feoff = ftoff + (west ? -1 : 2);
+        for (int band = 0; band < nbands; ++band) {
+            double* ub = u + (int64_t)band * lv.plane + origin;
+            const double* fb = src.f[band] + forigin;
+            double2 v[ST_NR];
+            double e[ST_RG];
+#pragma unroll
+            for (int j = 0; j < ST_NR; ++j)
+                v[j] = ldnc2_if(fb + (ftoff + j * fpitch), ldf, 1u << j);
+#pragma unroll
+            for (int j = 0; j < ST_RG; ++j)
+                e[j] = ldnc_if(fb + (feoff + (j + 1) * fpitch), emf, 1u << j);
+#pragma unroll
+            for (int j = 0; j < ST_NR; ++j)
+                if ((ldf >> j) & 1)
+                    *reinterpret_cast<double2*>(ub + (toff + j * pitch)) = v[j];
+#pragma unroll
+            for (int j = 0; j < ST_RG; ++j)
+                if ((emf >> j) & 1)
+                    ub[eoff + (j + 1) * pitch] = e[j];
+            if (POISSON) {
+                double* gb = g + (int64_t)band * lv.plane + origin;
+                const double* hg = src.g[band] + forigin;
+#pragma unroll
+                for (int j = 0; j < ST_NR; ++j)
+                    v[j] = ldnc2_if(hg + (ftoff + j * fpitch), ldm, 1u << j);
+#pragma unroll
+                for (int j = 0; j < ST_RG; ++j)
+                    e[j] = ldnc_if(hg + (feoff + (j + 1) * fpitch), em, 1u << j);
+#pragma unroll
+                for (int j = 0; j < ST_NR; ++j)
+                    if ((ldm >> j) & 1)
+                        *reinterpret_cast<double2*>(gb + (toff + j * pitch)) = v[j];
+#pragma unroll
+                for (int j = 0; j < ST_RG; ++j)
+                    if ((em >> j) & 1)
+                        gb[eoff + (j + 1) * pitch] = e[j];
+            }
+        }
+    }
+}
+
+int launch_fetch_direct(sa_ctx* ctx, cudaStream_t stream, const Level& lv, int nbands, bool poisson, double* u, double* g,
+    const HostBands& src)
+{
+    if (lv.n_tiles == 0 || nbands == 0)
+        return SA_OK;
+    if (nbands > HOST_BANDS_MAX)
+        return fail(ctx, SA_BAD_ARGUMENT, "direct fetch: too many bands in one window");
+    int want = 64;  // a few dozen CTAs cover PCIe latency; more only take SM slots from the solve that runs beside them
+    if (const char* e = std::getenv("SATFILL_FETCH_CTAS"))  // tuning knob
+        want = std::atoi(e) > 0 ? std::atoi(e) : want;
+    const unsigned grid = (unsigned)(want < lv.n_tiles ? want : lv.n_tiles);
+    if (poisson)
+        k_fetch_direct<true><<<grid, ST_THREADS, 0, stream>>>(lv, nbands, u, g, src);
+    else
+        k_fetch_direct<false><<<grid, ST_THREADS, 0, stream>>>(lv, nbands, u, g, src);
+    ctx->launches += 1;
+    SA_CUDA(ctx, cudaGetLastError());
     return SA_OK;
 }
 

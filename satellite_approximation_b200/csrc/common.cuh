@@ -75,7 +75,7 @@ struct Level {
 // Direct mode of the host-pointer entry points: the caller's page-locked arrays as the device addresses them (api.cu).
 constexpr int HOST_BANDS_MAX = 16;
 struct HostBands {
-    double* f[HOST_BANDS_MAX];        // images: read by k_setup2<DIRECT>, written (unknown pixels only) by k_scatter_direct
+    double* f[HOST_BANDS_MAX];        // images: read by k_fetch_direct, written (unknown pixels only) by k_scatter_direct
     const double* g[HOST_BANDS_MAX];  // Poisson: replacement images
     int64_t pitch;                    // elements between rows of the caller's arrays (the slow-axis stride)
     int64_t rows, cols;               // resident extents
@@ -177,11 +177,6 @@ struct sa_scene {
     // bands so that PCIe transfers of the other chunks overlap the solve.  band_n < 0: all bands.
     int band0 = 0, band_n = -1;
     int win_n() const { return band_n < 0 ? nbands : band_n; }
-    // set by the host-pointer entry points for the window: read f / g straight from the caller's page-locked arrays
-    const satfill::HostBands* direct = nullptr;
-    // ... or that window's set-up has already been issued on another stream (cg.cu: presetup_window)
-    bool window_ready = false;
-    cudaEvent_t setup_ready = nullptr;
 
     double* plane0(double* base, int band) const { return base + (int64_t)band * plane + pitch; }
     // float planes of the red-black cycle (mg_rb.cu) inside the z allocation: z itself, then the float copy of the
@@ -312,9 +307,10 @@ int precondition_scene(sa_scene* s, const sa_options& o);
 
 // ---- cg_strip.cu: the two kernels of a CG iteration, shared-memory-free generation ---------------------------------
 int launch_setup2(sa_ctx* ctx, const Level& lv, int nbands, bool poisson, double* u, const double* g, double* r, float* rf,
-    BandScalars* scal, const HostBands* direct = nullptr, bool background = false);
+    BandScalars* scal);
 int prepare_solve(sa_scene* s, const sa_options& o);
-int presetup_window(sa_scene* s, const sa_options& o, int b0, int nb, const HostBands* direct, cudaStream_t stream, cudaEvent_t done);
+int launch_fetch_direct(sa_ctx* ctx, cudaStream_t stream, const Level& lv, int nbands, bool poisson, double* u, double* g,
+    const HostBands& src);
 int launch_scatter_direct(sa_ctx* ctx, cudaStream_t stream, const Level& lv, int nbands, const double* u, const HostBands& dst);
 int launch_direction2(sa_ctx* ctx, const Level& lv, int nbands, bool jacobi, const void* zin, bool z_is_float,
     const void* p_old, void* p_new, bool p_is_float, BandScalars* scal, int k);
