@@ -10,8 +10,11 @@ tile with a 30 % cloud-like mask, Laplace fill to a 1e-6 relative residual.  At 
 (scenes are independent: no data-path collective), `value` = all ranks' unknown pixels / max-over-ranks device time.
 
 `value`   : device-resident (inputs in HBM when the timed region starts), CUDA events on the launching stream.
-`e2e`     : the same metric through the host-pointer C-ABI call (sa_laplace_fill) from pinned host buffers, H2D and
-            D2H copies inside the timed region.
+`e2e`     : the same metric through the host-pointer C-ABI call (sa_laplace_fill / sa_poisson_blend) on pinned host
+            buffers; everything that crosses PCIe does so inside the timed region.  Pinned buffers put the library in
+            its direct mode (kernels read the known pixels bordering the unknown set from host memory and store the
+            unknown pixels back: no image copies); `e2e.transfer` says which way the call went and `h2d / d2h
+            _bytes_per_step` count what really moved.
 `roofline`: the dominant kernel's algorithmic bytes / its CUDA-event duration, accumulated inside the timed region
             (sa_options.profile), against MEASURED_PEAKS.json.
 `cpu_baseline`: the oracle (oracle/_ref = the reference's arithmetic on its vendored Eigen when that was built, else

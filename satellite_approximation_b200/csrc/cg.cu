@@ -7,11 +7,15 @@
 //     b_p = [Poisson: sum_{q in N4(p)} (g_p - g_q)] + sum_{q in N4(p) \ U} f_q
 // x lives in the image plane itself (known cells keep f, unknown cells hold the iterate); r, p are planes that are
 // zero outside U.  One CG iteration is two kernels over the active tiles of all bands (DESIGN.md "CG kernels"):
-//     k_direction:  beta = rz_k / rz_{k-1};  p' = z + beta p  (ping-pong buffer; z = r/d for Jacobi);  pq = p'.Ap'
-//     k_update:     alpha = rz_k / pq;  x += alpha p';  r -= alpha A p'  (A p' recomputed from the staged tile);
-//                   rr = |r|^2,  rz = r.(r/d)
-// 65 B per unknown per iteration instead of the 89 B of the textbook five-pass formulation: A p is never stored.
-// All scalars stay on the device (BandScalars); the host only polls the `done` flags every check_every iterations.
+//     direction:  beta = rz_k / rz_{k-1};  p' = z + beta p  (ping-pong buffer; z = r/d for Jacobi);  pq = p'.Ap'
+//     update:     alpha = rz_k / pq;  x += alpha p';  r -= alpha A p'  (A p' recomputed, never stored);
+//                 rr = |r|^2,  rz = r.(r/d)
+// A p is never stored (66 B per unknown and Jacobi iteration instead of the 89 B of the textbook five-pass formulation).
+// All scalars stay on the device (BandScalars); the host only polls the `done` flags through pinned memory.
+//
+// This file holds the solver driver (solve_scene, prepare_solve, the scrub of the work vectors) and the FIRST-GENERATION
+// kernels (k_init_guess, k_residual, k_direction, k_update: tile + halo staged through shared memory), kept as
+// cg_variant = 1, the reference the strip kernels of cg_strip.cu are tested against.  The product path is cg_strip.cu.
 #include "common.cuh"
 #include "tile.cuh"
 
