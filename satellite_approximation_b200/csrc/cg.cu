@@ -632,7 +632,14 @@ int solve_scene(sa_scene* s, const sa_options& o, sa_stats* stats)
     // Jacobi iterations are short (two kernels): poll the flags every 32.  A multigrid iteration is a whole V-cycle:
     // poll every iteration, which also keeps the profile's per-class unit counts exact.
     const int check = o.check_every > 0 ? o.check_every : (mg ? 1 : 32);
-    int64_t k = 0;
+    // The host reads the flags of batch i - 1 while batch i is already queued: the device never waits for the host to
+    // notice, enqueue and launch (for a one-band window that wait was 8 % of the solve).  A batch that turns out to be
+    // unnecessary costs a few dozen kernels that exit at their first instruction.  The profile's per-launch accounting
+    // and the row-decomposed solve (whose ranks must take every decision together) keep the in-step poll.
+    const bool lookahead = !kt.on && !dist && nb <= 512;
+    BandScalars* const h_slot[2] = { h_scal, h_scal + 512 };
+    BandScalars* const h_slot_dev[2] = { h_scal_dev, h_scal_dev + 512 };
+    int64_t k = 0, batch = 0;
     bool all_done = false;
     int live = nb;  // bands not done at the last poll
     while (k < max_it && !all_done) {
@@ -709,13 +716,27 @@ int solve_scene(sa_scene* s, const sa_options& o, sa_stats* stats)
             }
         }
         SA_CUDA(ctx, cudaGetLastError());
-        SA_LAUNCH(ctx, k_publish_scalars, (nb + 63) / 64, 64, 0, scal, nb, h_scal_dev);
-        SA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        kt.flush();
-        live = 0;
-        for (int b = 0; b < nb; ++b)
-            live += h_scal[b].done ? 0 : 1;
-        all_done = live == 0;
+        const int slot = lookahead ? (int)(batch & 1) : 0;
+        SA_LAUNCH(ctx, k_publish_scalars, (nb + 63) / 64, 64, 0, scal, nb, h_slot_dev[slot]);
+        const BandScalars* seen = nullptr;
+        if (lookahead) {
+            SA_CUDA(ctx, cudaEventRecord(ctx->ev[4 + slot], ctx->stream));
+            if (batch >= 1) {
+                SA_CUDA(ctx, cudaEventSynchronize(ctx->ev[4 + (1 - slot)]));
+                seen = h_slot[1 - slot];
+            }
+        } else {
+            SA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            kt.flush();
+            seen = h_slot[0];
+        }
+        if (seen) {
+            live = 0;
+            for (int b = 0; b < nb; ++b)
+                live += seen[b].done ? 0 : 1;
+            all_done = live == 0;
+        }
+        ++batch;
     }
     SA_LAUNCH(ctx, k_final_check, (nb + 63) / 64, 64, 0, scal, nb, (int)(k & 0x3fffffff));
     if (have_tiles)

@@ -101,7 +101,7 @@ struct sa_ctx {
     // pinned host scratch for polling convergence flags / small read-backs
     void* pinned = nullptr;
     size_t pinned_bytes = 0;
-    cudaEvent_t ev[4] = { nullptr, nullptr, nullptr, nullptr };
+    cudaEvent_t ev[6] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
     std::vector<cudaEvent_t> ev_pool;  // per-kernel timing (sa_options.profile)
 };
 
