@@ -45,7 +45,8 @@ __all__ = [
     "LogLevel", "set_log_level", "filling_missing_portions_smooth_boundaries", "blend_images_poisson",
     "find_connected_components", "ConnectedComponents", "mask_scan", "unknown_numbering", "valid_neighbours",
     "Context", "Scene", "SolveStats", "default_context", "set_solver_defaults", "last_perf_info",
-    "dist_partition", "dist_levels", "apply_laplace", "preprocess_cloud_band", "blend_images_poisson_offset", "valid_pixel_mask", "LAPLACE", "POISSON", "JACOBI", "MULTIGRID", "MG_RB32", "MG_JACOBI64", "SatfillError",
+    "dist_partition", "dist_levels", "apply_laplace", "preprocess_cloud_band", "blend_images_poisson_offset", "valid_pixel_mask", "image_to_channels", "channels_to_image",
+    "highlight_area_replaced", "LAPLACE", "POISSON", "JACOBI", "MULTIGRID", "MG_RB32", "MG_JACOBI64", "SatfillError",
 ]  # fmt: skip
 
 _log = logging.getLogger("satellite_approximation_b200")
@@ -570,6 +571,42 @@ def blend_images_poisson_offset(input_image: Sequence[np.ndarray], replacement_i
         return
     for a, w in zip(ins, work):  # poisson.cpp:126-139: only the unknowns are written
         a[sl][unknown] = w[unknown]
+
+
+GAMMA = 2.2  # approx/source/utils.cpp:8
+
+
+def image_to_channels(image_bgr_u8: np.ndarray) -> list[np.ndarray]:
+    """The arithmetic of approx::read_image (approx/source/utils.cpp:16-34) on an image that is already in memory
+    (uint8 H x W x 3 in cv::imread's B, G, R order): three float64 channels R, G, B, gamma-decoded pow(v / 255, 1 / 2.2).
+    File I/O itself (cv::imread) is outside the path."""
+    a = np.asarray(image_bgr_u8)
+    if a.dtype != np.uint8 or a.ndim != 3 or a.shape[2] != 3:
+        raise TypeError("image_to_channels(): uint8 H x W x 3")
+    return [np.power(a[..., k] / 255.0, 1.0 / GAMMA) for k in (2, 1, 0)]
+
+
+def channels_to_image(channels: Sequence[np.ndarray]) -> Optional[np.ndarray]:
+    """approx::image_list_to_cv (approx/source/utils.cpp:36-60): float64 channels R, G, B -> uint8 H x W x 3 in B, G, R
+    order, static_cast<uchar>(pow(v, 2.2) * 255) (truncation towards zero, wrap-around of out-of-range values like the
+    C++ cast).  Anything but three channels is logged and refused."""
+    if len(channels) != 3:
+        _log.warning("Image with less than 3 channels is not supported. (%d channels provided)", len(channels))
+        return None
+    out = np.empty(channels[0].shape + (3,), np.uint8)
+    for k, c in zip((2, 1, 0), channels):
+        out[..., k] = (np.power(np.asarray(c, np.float64), GAMMA) * 255.0).astype(np.int64).astype(np.uint8)
+    return out
+
+
+def highlight_area_replaced(input_image: Sequence[np.ndarray], replacement_image: Sequence[np.ndarray], start_row: int,
+                            start_column: int, color: Sequence[float]) -> None:  # fmt: skip
+    """approx::highlight_area_replaced (poisson.cpp:305-321): paints the pasted (non white-key) pixels of the replacement
+    at the offset with `color` in the first three channels of `input_image`, in place."""
+    m = valid_pixel_mask(replacement_image)
+    R, C_ = m.shape
+    for k in range(3):
+        input_image[k][start_row : start_row + R, start_column : start_column + C_][m] = color[k]
 
 
 class ConnectedComponents:

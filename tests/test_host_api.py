@@ -58,3 +58,36 @@ def test_stride_helpers():
     assert _capi.is_dense_2d(a[:, :5]) and _capi.is_dense_2d(a[1:4])
     assert not _capi.is_dense_2d(a[::2, ::2])
     assert _capi.element_strides(np.asfortranarray(a)) == (1, 6)
+
+
+def test_image_helpers_of_the_offset_demo():
+    """read_image / image_list_to_cv arithmetic (approx/source/utils.cpp:16-60), valid_pixel (approx/utils.h:101-105) and
+    highlight_area_replaced (poisson.cpp:305-321): host-side value helpers around the offset overload."""
+    rng = np.random.default_rng(0)
+    img = rng.integers(0, 256, (7, 9, 3), dtype=np.uint8)
+    ch = sab.image_to_channels(img)
+    assert len(ch) == 3 and ch[0].dtype == np.float64
+    assert np.allclose(ch[0], (img[..., 2] / 255.0) ** (1 / 2.2)) and np.allclose(ch[2], (img[..., 0] / 255.0) ** (1 / 2.2))
+    back = sab.channels_to_image(ch)
+    assert back.dtype == np.uint8 and np.max(np.abs(back.astype(int) - img.astype(int))) <= 1  # truncating cast
+    assert sab.channels_to_image(ch[:2]) is None
+    rep = [np.full((3, 4), 0.5) for _ in range(3)]
+    for c in rep:
+        c[0, :] = 1.0   # white key: truncates to 1 in all three channels
+    rep[1][0, 1] = 0.99  # one channel off the key -> a valid pixel
+    m = sab.valid_pixel_mask(rep)
+    assert m.tolist() == [[False, True, False, False], [True] * 4, [True] * 4]
+    big = [np.zeros((6, 8)) for _ in range(3)]
+    sab.highlight_area_replaced(big, rep, 2, 3, (0.1, 0.2, 0.3))
+    want = np.zeros((6, 8), bool)
+    want[2:5, 3:7] = m
+    for k, v in enumerate((0.1, 0.2, 0.3)):
+        assert np.array_equal(big[k] == v, want)
+
+
+def test_prepost_dtype_rules_before_any_device_work():
+    img = np.zeros((4, 5, 3), np.uint8)
+    with pytest.raises(TypeError):
+        sab.Context.apply_laplace(None, img.astype(np.float64), img)
+    with pytest.raises(TypeError):
+        sab.Context.morph_close_mask(None, np.zeros((4, 5), np.float32))
