@@ -709,6 +709,32 @@ def test_direct_mode_on_page_locked_arrays(ctx, port, monkeypatch, order, precon
         assert rel_max_abs(cur[b], ref[b], lmask) < 1e-8
 
 
+def test_direct_mode_tiny_and_degenerate_scenes(ctx, port):
+    """Page-locked arrays of a few pixels: all-valid, all-invalid, a single unknown, unknowns on every image border
+    (Poisson) -- the direct mode must agree with the oracle and never touch a known pixel."""
+    rng = np.random.default_rng(3)
+    for rows, cols in ((2, 2), (4, 6), (3, 8), (32, 32), (33, 34), (64, 2)):
+        img = rng.random((rows, cols)) * 100.0
+        g = rng.random((rows, cols)) * 100.0
+        for mask in (np.zeros((rows, cols), bool), np.ones((rows, cols), bool), rng.random((rows, cols)) < 0.5):
+            got = _pinned(img)
+            st = ctx.laplace_fill([got], mask, tolerance=1e-12, precond=sab.MULTIGRID)
+            want, _ = port.laplace_fill(img, mask, mode=1, tol=1e-13)
+            interior = mask.copy()
+            interior[0, :] = interior[-1, :] = False
+            interior[:, 0] = interior[:, -1] = False
+            if interior.any():
+                assert ctx.last_fill_direct and st[0]["status"] == sab.SA_OK
+                assert rel_max_abs(got, want, interior) < 1e-8
+            assert np.array_equal(got[~interior], img[~interior])
+            if mask.any() and not mask.all():  # all-invalid Poisson is singular (pure Neumann): the reference fails too
+                pgot, pg = _pinned(img), _pinned(g)
+                pst = ctx.poisson_blend([pgot], [pg], mask, tolerance=1e-12, max_iterations=10**6, precond=sab.MULTIGRID)
+                pwant, _ = port.poisson_blend([img], [g], mask, tol=1e-13, max_it=10**6)
+                assert pst[0]["status"] == sab.SA_OK and rel_max_abs(pgot, pwant[0], mask) < 1e-7
+                assert np.array_equal(pgot[~mask], img[~mask])
+
+
 def test_direct_mode_falls_back_on_odd_widths(ctx, port):
     """Pairs of cells are read 16 bytes at a time: arrays whose fast extent is odd take the copy path, same answers."""
     rows, cols = 95, 131
