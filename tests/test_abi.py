@@ -72,3 +72,38 @@ def test_product_never_imports_oracle():
             if fn.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
                 text = open(os.path.join(dirpath, fn)).read()
                 assert "import oracle" not in text and "liboracle" not in text and "libref_eigen" not in text, fn
+
+
+def _build_c_example(tmp_path):
+    from satellite_approximation_b200 import _capi
+
+    libdir = os.path.dirname(_capi.LIB_PATH)
+    exe = str(tmp_path / "fill_c_abi")
+    cmd = ["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "examples", "fill_c_abi.c"), "-L", libdir, "-lsatfill", f"-Wl,-rpath,{libdir}", "-lm", "-o", exe]  # fmt: skip
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return exe
+
+
+def test_header_is_plain_c_and_the_example_fails_loudly_without_a_gpu(tmp_path):
+    """include/satfill.h compiles as pedantic C99 (and as C++), and a plain-C caller of the C-ABI gets a clean error --
+    not a CPU fallback -- on a machine without a device."""
+    import torch
+
+    exe = _build_c_example(tmp_path)
+    r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-x", "c++", HEADER], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present: test_c_example_on_gpu runs it")
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 2 and "no CPU fallback" in r.stderr
+
+
+@pytest.mark.gpu
+def test_c_example_on_gpu(tmp_path):
+    """examples/fill_c_abi.c: sa_laplace_fill from plain C on a column-major image reproduces a discrete-harmonic field."""
+    exe = _build_c_example(tmp_path)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "max error" in r.stdout
