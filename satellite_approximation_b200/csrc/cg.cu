@@ -634,9 +634,11 @@ int solve_scene(sa_scene* s, const sa_options& o, sa_stats* stats)
     const int check = o.check_every > 0 ? o.check_every : (mg ? 1 : 32);
     // The host reads the flags of batch i - 1 while batch i is already queued: the device never waits for the host to
     // notice, enqueue and launch (for a one-band window that wait was 8 % of the solve).  A batch that turns out to be
-    // unnecessary costs a few dozen kernels that exit at their first instruction.  The profile's per-launch accounting
-    // and the row-decomposed solve (whose ranks must take every decision together) keep the in-step poll.
-    const bool lookahead = !kt.on && !dist && nb <= 512;
+    // unnecessary costs a few dozen kernels that exit at their first instruction.  Ranks of a row-decomposed solve see the
+    // same (all-reduced) flags for the same batch, so they still take every decision together.  The profile's
+    // per-launch accounting keeps the in-step poll when bands can finish at different iterations (its unit counts follow
+    // the live bands); with one band its events are simply read once the solve is over.
+    const bool lookahead = (!kt.on || nb == 1) && nb <= 512;
     BandScalars* const h_slot[2] = { h_scal, h_scal + 512 };
     BandScalars* const h_slot_dev[2] = { h_scal_dev, h_scal_dev + 512 };
     int64_t k = 0, batch = 0;
@@ -661,8 +663,15 @@ int solve_scene(sa_scene* s, const sa_options& o, sa_stats* stats)
                     z = s->plane0(s->z, b0);
                 }
                 float* rf = rb ? s->rb_rf() : nullptr;
-                if (dist)
-                    SA_TRY(dist_reduce(s, DIST_RZ, ki & 3, -1));
+                if (dist) {  // r.z summed over the ranks and the halo row of z, one NCCL launch
+                    SA_TRY(dist_reduce_pack(s, DIST_RZ, ki & 3));
+                    SA_TRY(dist_group_begin(s));
+                    SA_TRY(dist_reduce_issue(s));
+                    if (rb)
+                        SA_TRY(dist_halo<float>(s, 0, s->rb_z(), s->pitch, s->plane, 1, 1));
+                    SA_TRY(dist_group_end(s));
+                    SA_TRY(dist_reduce_unpack(s, DIST_RZ, ki & 3, -1));
+                }
                 kt.begin(KC_DIRECTION, n * live);
                 if (strip)
                     SA_TRY(launch_direction2(ctx, lv, nb, false, z, rb, pin_v, pout_v, pf, scal, ki));
@@ -671,12 +680,16 @@ int solve_scene(sa_scene* s, const sa_options& o, sa_stats* stats)
                 else
                     SA_LAUNCH(ctx, (k_direction<false, double>), grid, block, 0, lv, (const double*)z, pin, pout, scal, ki);
                 kt.end();
-                if (dist) {
+                if (dist) {  // the halo row of p' and p'.Ap' in one NCCL launch
+                    SA_TRY(dist_reduce_pack(s, DIST_PQ, ki & 3));
+                    SA_TRY(dist_group_begin(s));
+                    SA_TRY(dist_reduce_issue(s));
                     if (pf)
                         SA_TRY(dist_halo<float>(s, 0, (float*)pout_v, s->pitch, s->plane, 1, 1));
                     else
                         SA_TRY(dist_halo<double>(s, 0, pout, s->pitch, s->plane, 1, 1));
-                    SA_TRY(dist_reduce(s, DIST_PQ, ki & 3, (ki + 2) & 3));
+                    SA_TRY(dist_group_end(s));
+                    SA_TRY(dist_reduce_unpack(s, DIST_PQ, ki & 3, (ki + 2) & 3));
                 }
                 kt.begin(KC_UPDATE, n * live);
                 if (strip)
@@ -686,9 +699,13 @@ int solve_scene(sa_scene* s, const sa_options& o, sa_stats* stats)
                 else
                     SA_LAUNCH(ctx, (k_update<false, false>), grid, block, 0, lv, u0, pout, r0, nullptr, scal, ki);
                 kt.end();
-                if (dist) {
+                if (dist) {  // the halo rows of the cycle's residual copy and |r|^2 in one NCCL launch
+                    SA_TRY(dist_reduce_pack(s, DIST_RR, (ki + 1) & 3));
+                    SA_TRY(dist_group_begin(s));
+                    SA_TRY(dist_reduce_issue(s));
                     SA_TRY(dist_halo<float>(s, 0, rf, s->pitch, s->plane, 3, 3));
-                    SA_TRY(dist_reduce(s, DIST_RR, (ki + 1) & 3, -1));
+                    SA_TRY(dist_group_end(s));
+                    SA_TRY(dist_reduce_unpack(s, DIST_RR, (ki + 1) & 3, -1));
                 }
                 SA_LAUNCH(ctx, k_check_converged, (nb + 63) / 64, 64, 0, scal, nb, ki + 1);
             } else {
@@ -730,6 +747,7 @@ int solve_scene(sa_scene* s, const sa_options& o, sa_stats* stats)
             kt.flush();
             seen = h_slot[0];
         }
+
         if (seen) {
             live = 0;
             for (int b = 0; b < nb; ++b)
@@ -745,6 +763,7 @@ int solve_scene(sa_scene* s, const sa_options& o, sa_stats* stats)
     SA_CUDA(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
     SA_LAUNCH(ctx, k_publish_scalars, (nb + 63) / 64, 64, 0, scal, nb, h_scal_dev);
     SA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    kt.flush();  // the per-launch events of a one-band profile that polled one batch behind (everything else: empty)
     float setup_ms = 0.f, solve_ms = 0.f;
     cudaEventElapsedTime(&setup_ms, ctx->ev[0], ctx->ev[1]);
     cudaEventElapsedTime(&solve_ms, ctx->ev[1], ctx->ev[2]);

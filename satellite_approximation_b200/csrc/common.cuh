@@ -346,6 +346,11 @@ template <typename T>
 int dist_halo(sa_scene* s, int l, T* base, int64_t pitch, int64_t plane, int above, int below);
 int dist_gather(sa_scene* s, float* base, int64_t pitch, int64_t plane);
 int dist_reduce(sa_scene* s, int what, int slot, int clear_slot);
+int dist_reduce_pack(sa_scene* s, int what, int slot);
+int dist_reduce_issue(sa_scene* s);
+int dist_reduce_unpack(sa_scene* s, int what, int slot, int clear_slot);
+int dist_group_begin(sa_scene* s);
+int dist_group_end(sa_scene* s);
 int dist_allgather_band(sa_scene* s, int band);
 
 // ---- mg_fused.cu -------------------------------------------------------------------------------------------------

@@ -356,21 +356,61 @@ int dist_allgather_band(sa_scene* s, int band)
     return SA_OK;
 }
 
-// Sum of the per-rank partial scalars of one CG phase; clear_slot >= 0 also recycles that ring slot.
-int dist_reduce(sa_scene* s, int what, int slot, int clear_slot)
+// NCCL groups nest: a pair of these around several exchanges turns them into one launch (17 NCCL launches per CG
+// iteration are what separates the row-decomposed solve from linear scaling; grouped they are 10).
+int dist_group_begin(sa_scene* s)
 {
     sa_ctx* ctx = s->ctx;
     if (!s->dist_planned || ctx->world == 1)
         return SA_OK;
-    const int nb = s->nbands;
-    if (nb > 64)
+    SA_NCCL(ctx, nccl().GroupStart());
+    return SA_OK;
+}
+int dist_group_end(sa_scene* s)
+{
+    sa_ctx* ctx = s->ctx;
+    if (!s->dist_planned || ctx->world == 1)
+        return SA_OK;
+    SA_NCCL(ctx, nccl().GroupEnd());
+    return SA_OK;
+}
+
+// Sum of the per-rank partial scalars of one CG phase, in three steps so that the all-reduce can share a group with the
+// halo exchange of the same phase:  pack (kernel)  ->  issue (NCCL, may sit inside dist_group_begin / _end)  ->  unpack
+// (kernel; clear_slot >= 0 also recycles that ring slot).
+int dist_reduce_pack(sa_scene* s, int what, int slot)
+{
+    sa_ctx* ctx = s->ctx;
+    if (!s->dist_planned || ctx->world == 1)
+        return SA_OK;
+    if (s->nbands > 64)
         return fail(ctx, SA_BAD_ARGUMENT, "distributed solve: at most 64 bands");
-    SA_LAUNCH(ctx, k_pack, 1, 64, 0, s->scal, nb, what, slot, ctx->d_red);
-    SA_NCCL(ctx, nccl().AllReduce(ctx->d_red, ctx->d_red, (size_t)(3 * nb), ncclFloat64, ncclSum, (ncclComm_t)ctx->comm,
+    SA_LAUNCH(ctx, k_pack, 1, 64, 0, s->scal, s->nbands, what, slot, ctx->d_red);
+    return SA_OK;
+}
+int dist_reduce_issue(sa_scene* s)
+{
+    sa_ctx* ctx = s->ctx;
+    if (!s->dist_planned || ctx->world == 1)
+        return SA_OK;
+    SA_NCCL(ctx, nccl().AllReduce(ctx->d_red, ctx->d_red, (size_t)(3 * s->nbands), ncclFloat64, ncclSum, (ncclComm_t)ctx->comm,
                      ctx->stream));
-    SA_LAUNCH(ctx, k_unpack, 1, 64, 0, s->scal, nb, what, slot, ctx->d_red, clear_slot);
+    return SA_OK;
+}
+int dist_reduce_unpack(sa_scene* s, int what, int slot, int clear_slot)
+{
+    sa_ctx* ctx = s->ctx;
+    if (!s->dist_planned || ctx->world == 1)
+        return SA_OK;
+    SA_LAUNCH(ctx, k_unpack, 1, 64, 0, s->scal, s->nbands, what, slot, ctx->d_red, clear_slot);
     SA_CUDA(ctx, cudaGetLastError());
     return SA_OK;
+}
+int dist_reduce(sa_scene* s, int what, int slot, int clear_slot)
+{
+    SA_TRY(dist_reduce_pack(s, what, slot));
+    SA_TRY(dist_reduce_issue(s));
+    return dist_reduce_unpack(s, what, slot, clear_slot);
 }
 
 }  // namespace satfill

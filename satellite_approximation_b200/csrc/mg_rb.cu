@@ -597,11 +597,13 @@ int apply_vcycle_rb(sa_scene* s, const sa_options& o, KernelTimer& kt, int rz_sl
         if (l < dlv) {
             // the ascent reads the red half of the iterate 2 rows beyond the slice; the next level's descent reads
             // its right-hand side 3 rows beyond -- or, if that level is replicated, everywhere
+            SA_TRY(dist_group_begin(s));  // one NCCL launch for both exchanges
             SA_TRY(dist_halo<float>(s, l, L[l].xr, L[l].lv.pitch >> 1, L[l].lv.plane >> 1, 2, 2));
             if (l + 1 < dlv)
                 SA_TRY(dist_halo<float>(s, l + 1, L[l + 1].b, L[l + 1].lv.pitch, L[l + 1].lv.plane, 3, 3));
             else
                 SA_TRY(dist_gather(s, L[l + 1].b, L[l + 1].lv.pitch, L[l + 1].lv.plane));
+            SA_TRY(dist_group_end(s));
         }
     }
     kt.begin(KC_SMOOTH, L[nl - 1].units);
@@ -614,8 +616,10 @@ int apply_vcycle_rb(sa_scene* s, const sa_options& o, KernelTimer& kt, int rz_sl
         else
             SA_TRY((launch_up<false>(ctx, L[l], L[l + 1], nb, scal, 0)));
         kt.end();
-        if (l < dlv)  // the finer level's ascent interpolates from up to 2 coarse rows beyond; CG's direction needs 1 row of z
-            SA_TRY(dist_halo<float>(s, l, L[l].x, L[l].lv.pitch, L[l].lv.plane, l == 0 ? 1 : 2, l == 0 ? 1 : 2));
+        // the finer level's ascent interpolates from up to 2 coarse rows beyond.  (Level 0: CG's direction needs 1 row of z;
+        // the caller exchanges it in one group with the all-reduce of r.z -- cg.cu.)
+        if (l < dlv && l > 0)
+            SA_TRY(dist_halo<float>(s, l, L[l].x, L[l].lv.pitch, L[l].lv.plane, 2, 2));
     }
     SA_CUDA(ctx, cudaGetLastError());
     return SA_OK;
