@@ -1,0 +1,253 @@
+"""CPU: the GeoTIFF step either side of the Poisson path (satellite_approximation_b200/geotiff.py; reference
+lib/utils/include/utils/geotiff.h:98-263, executables/poisson-main.cpp:53-70).  Pinned against crops of the reference's
+sample scene re-encoded in the sample files' own flavour and decoded by OpenCV/libtiff (oracle/make_tiff_fixture.py),
+against Pillow/libtiff-written files where Pillow is importable, and by round trips."""
+from __future__ import annotations
+
+import hashlib
+import os
+import struct
+import zlib
+
+import numpy as np
+import pytest
+
+from satellite_approximation_b200 import geotiff as gt
+
+from conftest import GOLDEN
+
+SCENE = "/root/reference/test_data/2019-05-22"
+
+
+@pytest.fixture(scope="module")
+def expected():
+    return dict(np.load(os.path.join(GOLDEN, "scene_crop_expected.npz")))
+
+
+@pytest.mark.parametrize("name,dtype", [("B04", np.uint16), ("CLD", np.uint8), ("sunZenithAngles", np.float32)])
+def test_sample_scene_flavour_decodes_bit_exact(expected, name, dtype):
+    t = gt.TiffFile(os.path.join(GOLDEN, f"scene_crop_{name}.tif"))
+    assert (t.byteorder, t.compression, t.seg_h, t.tiled, t.samples_per_pixel) == (">", 32946, 8, False, 1)
+    a = t.read_band(1)
+    assert a.dtype == dtype and a.flags.c_contiguous
+    assert np.array_equal(a, expected[name])
+    assert np.allclose(t.geo_transform, expected["geo_transform"], rtol=0, atol=0)
+
+
+def test_full_sample_scene_digests(expected):
+    if not os.path.isdir(SCENE):
+        pytest.skip("reference sample scene not on this machine")
+    for line in expected["full_digests"]:
+        name, dtype, shape, digest = str(line).split()
+        a = gt.TiffFile(os.path.join(SCENE, name + ".tif")).read_band(1)
+        assert str(a.dtype) == dtype and f"{a.shape[0]}x{a.shape[1]}" == shape
+        assert hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest() == digest
+
+
+def test_geotiff_mirror_layouts_and_conversion(expected):
+    p = os.path.join(GOLDEN, "scene_crop_B04.tif")
+    g = gt.GeoTIFF(p, np.float64)
+    assert (g.height, g.width, g.raster_count) == (96, 80, 1)
+    a = g.read(1)
+    assert a.dtype == np.float64 and np.array_equal(a, expected["B04"].astype(np.float64))
+    assert [x.shape for x in g.read([1, 1])] == [(96, 80)] * 2 and len(g.read()) == 1
+    # the reference's matrix: column-major height x width over the row-major raster buffer (geotiff.h:234-253)
+    m = gt.GeoTIFF(p, np.float64, layout="reference").read(1)
+    assert m.shape == (96, 80) and m.flags.f_contiguous
+    flat = expected["B04"].astype(np.float64).ravel()
+    r, c = np.meshgrid(np.arange(96), np.arange(80), indexing="ij")
+    assert np.array_equal(m, flat[r + c * 96])
+    assert not np.array_equal(m, a)  # a non-square scene is index-scrambled there
+    x, y = g.pixel_to_geo(0, 0)
+    assert (x, y) == (expected["geo_transform"][0], expected["geo_transform"][3])
+    with pytest.raises(gt.TiffError):
+        g.read(2)
+
+
+def test_gdal_convert_rounds_and_clamps():
+    v = np.array([-3.7, -0.5, -0.49, 0.49, 0.5, 1.5, 2.5, 65534.5, 65535.4, 1e9, np.nan, np.inf, -np.inf])
+    assert gt.gdal_convert(v, np.uint16).tolist() == [0, 0, 0, 0, 1, 2, 3, 65535, 65535, 65535, 0, 65535, 0]
+    assert gt.gdal_convert(v[:7], np.int16).tolist() == [-4, -1, 0, 0, 1, 2, 3]
+    assert gt.gdal_convert(np.array([-5, 300], np.int32), np.uint8).tolist() == [0, 255]
+    assert gt.gdal_convert(np.array([70000], np.uint32), np.int16).tolist() == [32767]
+    assert gt.gdal_convert(np.array([1e30, -1e30]), np.int64).tolist() == [2**63 - 1, -(2**63)]
+    a = np.arange(5, dtype=np.uint16)
+    assert gt.gdal_convert(a, np.uint16) is a and gt.gdal_convert(a, np.float64).dtype == np.float64
+
+
+@pytest.mark.parametrize("dtype", [np.uint8, np.int8, np.uint16, np.int16, np.uint32, np.int32, np.float32, np.float64,
+                                   np.uint64, np.int64])  # fmt: skip
+@pytest.mark.parametrize("kw", [{}, {"tile": (16, 32)}, {"compress": True}, {"bigtiff": True}, {"rows_per_strip": 5},
+                                {"tile": (32, 16), "compress": True, "bigtiff": True}])  # fmt: skip
+def test_write_read_round_trip(tmp_path, dtype, kw):
+    rng = np.random.default_rng(7)
+    a = (rng.random((37, 53)) * 200 - (50 if np.dtype(dtype).kind != "u" else 0)).astype(dtype)
+    b = a[::-1].copy()
+    p = tmp_path / "x.tif"
+    gt.write_tiff(p, [a, b], **kw)
+    t = gt.TiffFile(p)
+    assert t.bigtiff == bool(kw.get("bigtiff")) and t.tiled == ("tile" in kw) and t.planar == 2
+    got = t.read_all()
+    assert got[0].dtype == np.dtype(dtype) and np.array_equal(got[0], a) and np.array_equal(got[1], b)
+    assert np.array_equal(t.read_band(2), b)
+
+
+def test_pillow_written_files(tmp_path):
+    Image = pytest.importorskip("PIL.Image")
+    rng = np.random.default_rng(3)
+    a = (rng.random((61, 47)) * 60000).astype(np.uint16)
+    rgb = (rng.random((61, 47, 3)) * 255).astype(np.uint8)
+    p = tmp_path / "p.tif"
+    for comp, code in [("raw", 1), ("tiff_lzw", 5), ("tiff_adobe_deflate", 8), ("packbits", 32773)]:
+        Image.fromarray(a).save(p, compression=comp)
+        t = gt.TiffFile(p)
+        assert t.compression == code and np.array_equal(t.read_band(1), a), comp
+        Image.fromarray(rgb).save(p, compression=comp)
+        t = gt.TiffFile(p)  # chunky RGB
+        assert t.planar == 1 and t.samples_per_pixel == 3
+        assert all(np.array_equal(t.read_band(i + 1), rgb[:, :, i]) for i in range(3)), comp
+        assert all(np.array_equal(x, rgb[:, :, i]) for i, x in enumerate(t.read_all())), comp
+    # and the other direction: libtiff reads what write_tiff makes (strips, tiles, deflate)
+    for kw in [{}, {"tile": (16, 16)}, {"compress": True}]:
+        gt.write_tiff(p, [a], **kw)
+        assert np.array_equal(np.array(Image.open(p)), a), kw
+
+
+def _encode(path, a, compression=1, predictor=1, byteorder="<", tile=None):
+    """A deliberately separate minimal encoder for the flavours no library here writes on demand (predictors 2 / 3,
+    big-endian, tiles): chunky samples, one strip or fixed tiles."""
+    bo = byteorder
+    h, w = a.shape[:2]
+    ns = 1 if a.ndim == 2 else a.shape[2]
+    a3 = a.reshape(h, w, ns)
+
+    def enc(block):
+        rows = block.shape[0]
+        if predictor == 2:
+            d = block.copy()
+            d[:, 1:] = block[:, 1:] - block[:, :-1]
+            raw = d.astype(d.dtype.newbyteorder(bo)).tobytes()
+        elif predictor == 3:
+            be = block.astype(block.dtype.newbyteorder(">")).view(np.uint8).reshape(rows, block.shape[1] * ns, -1)
+            planes = np.ascontiguousarray(be.transpose(0, 2, 1)).reshape(rows, -1)  # most significant bytes first
+            d = planes.copy()
+            d[:, ns:] = planes[:, ns:] - planes[:, :-ns]
+            raw = d.tobytes()
+        else:
+            raw = block.astype(block.dtype.newbyteorder(bo)).tobytes()
+        return zlib.compress(raw) if compression == 8 else raw
+
+    if tile:
+        th, tw = tile
+        segs = []
+        for r0 in range(0, h, th):
+            for c0 in range(0, w, tw):
+                t = np.zeros((th, tw, ns), a.dtype)
+                blk = a3[r0 : r0 + th, c0 : c0 + tw]
+                t[: blk.shape[0], : blk.shape[1]] = blk
+                segs.append(enc(t))
+    else:
+        segs = [enc(a3)]
+    blob = bytearray((b"II" if bo == "<" else b"MM") + struct.pack(bo + "HI", 42, 0))
+    offs = []
+    for s in segs:
+        offs.append(len(blob))
+        blob += s + (b"\0" if len(s) & 1 else b"")
+    n = len(segs)
+    o_offs, o_cnts = len(blob), len(blob) + 4 * n
+    blob += struct.pack(f"{bo}{n}I", *offs) + struct.pack(f"{bo}{n}I", *[len(s) for s in segs])
+    o_bits = len(blob)
+    blob += struct.pack(f"{bo}{ns}H", *[a.dtype.itemsize * 8] * ns) + struct.pack(f"{bo}{ns}H", *[{"u": 1, "i": 2, "f": 3}[a.dtype.kind]] * ns)
+    sh = lambda v: struct.pack(bo + "HH", v, 0)  # noqa: E731
+    lg = lambda v: struct.pack(bo + "I", v)  # noqa: E731
+    multi = ns > 2
+    ent = [(256, 4, 1, lg(w)), (257, 4, 1, lg(h)),
+           (258, 3, ns, lg(o_bits) if multi else struct.pack(f"{bo}{ns}H", *[a.dtype.itemsize * 8] * ns).ljust(4, b"\0")),
+           (259, 3, 1, sh(compression)), (262, 3, 1, sh(1)), (277, 3, 1, sh(ns)), (284, 3, 1, sh(1)), (317, 3, 1, sh(predictor)),
+           (339, 3, ns, lg(o_bits + 2 * ns) if multi else
+            struct.pack(f"{bo}{ns}H", *[{"u": 1, "i": 2, "f": 3}[a.dtype.kind]] * ns).ljust(4, b"\0"))]  # fmt: skip
+    one = lambda o, lst: lg(o) if n > 1 else lg(lst[0])  # noqa: E731
+    if tile:
+        ent += [(322, 4, 1, lg(tile[1])), (323, 4, 1, lg(tile[0])), (324, 4, n, one(o_offs, offs)),
+                (325, 4, n, one(o_cnts, [len(s) for s in segs]))]  # fmt: skip
+    else:
+        ent += [(273, 4, n, one(o_offs, offs)), (278, 4, 1, lg(h)), (279, 4, n, one(o_cnts, [len(s) for s in segs]))]
+    ent.sort()
+    ifd = len(blob)
+    blob += struct.pack(bo + "H", len(ent))
+    for tag, typ, cnt, val in ent:
+        blob += struct.pack(bo + "HHI", tag, typ, cnt) + val
+    blob += struct.pack(bo + "I", 0)
+    blob[4:8] = struct.pack(bo + "I", ifd)
+    with open(path, "wb") as f:
+        f.write(bytes(blob))
+
+
+@pytest.mark.parametrize("bo", ["<", ">"])
+def test_predictors_tiles_and_byte_orders(tmp_path, bo):
+    rng = np.random.default_rng(11)
+    p = tmp_path / "e.tif"
+    u = (rng.random((40, 50, 3)) * 65535).astype(np.uint16)
+    for tile in (None, (16, 32)):
+        for comp in (1, 8):
+            _encode(p, u, compression=comp, predictor=2, byteorder=bo, tile=tile)
+            t = gt.TiffFile(p)
+            assert t.predictor == 2 and t.samples_per_pixel == 3
+            assert all(np.array_equal(x, u[:, :, i]) for i, x in enumerate(t.read_all()))
+            assert np.array_equal(t.read_band(2), u[:, :, 1])
+    for dt in (np.float32, np.float64):
+        f = rng.standard_normal((33, 29)).astype(dt)
+        f2 = rng.standard_normal((33, 29, 2)).astype(dt)
+        for tile in (None, (16, 16)):
+            _encode(p, f, compression=8, predictor=3, byteorder=bo, tile=tile)
+            assert np.array_equal(gt.TiffFile(p).read_band(1), f)
+            _encode(p, f2, compression=1, predictor=3, byteorder=bo, tile=tile)
+            assert np.array_equal(gt.TiffFile(p).read_band(2), f2[:, :, 1])
+
+
+def test_writer_copies_template_and_overwrites_bands(tmp_path, expected):
+    # a 3-band u16 template with the sample scene's geo tags
+    src = gt.TiffFile(os.path.join(GOLDEN, "scene_crop_B04.tif"))
+    geo = {k: v for k, v in src.tags.items() if k in gt.GEO_TAGS}
+    b = expected["B04"]
+    tpl = tmp_path / "tpl.tif"
+    gt.write_tiff(tpl, [b, (b // 2).astype(np.uint16), (b // 3).astype(np.uint16)], extra_tags=geo)
+    vals = [b.astype(np.float64) + 0.5, b.astype(np.float64) * 100.0]  # the second saturates u16
+    out = tmp_path / "sub" / "out.tif"
+    gt.GeoTiffWriter(vals, tpl).write(out, start_index=2)  # poisson-main.cpp:68-69 writes from band 1; 2 tests the offset
+    t = gt.GeoTIFF(out, np.float64)
+    assert t.raster_count == 3 and t.file.dtype == np.uint16 and t.file.compression == 1
+    assert t.geo_transform == src.geo_transform and t.file.tags[gt.T_GEOASCII][1] == "WGS 84|"
+    got = t.read()
+    assert np.array_equal(got[0], b)  # untouched band keeps the template's pixels (CreateCopy)
+    assert np.array_equal(got[1], np.minimum(b.astype(np.float64) + 1.0, 65535.0))  # x.5 rounds away from zero
+    assert np.array_equal(got[2], np.minimum(b.astype(np.float64) * 100.0, 65535.0))
+    # single-band form always lands in band 1; reference layout round-trips through read -> write
+    m = gt.GeoTIFF(tpl, np.float64, layout="reference").read(2)
+    gt.GeoTiffWriter(m, tpl, layout="reference").write(out, start_index=3)
+    assert np.array_equal(gt.TiffFile(out).read_band(1), b // 2)
+    with pytest.raises(RuntimeError):
+        gt.GeoTiffWriter(vals, tpl).write(out, start_index=3)  # band 4 of 3
+    with pytest.raises(RuntimeError):
+        gt.GeoTiffWriter(vals[0][:10], tpl).write(out)
+
+
+def test_errors(tmp_path):
+    p = tmp_path / "bad.tif"
+    p.write_bytes(b"not a tiff at all")
+    with pytest.raises(gt.TiffError):
+        gt.TiffFile(p)
+    with pytest.raises(gt.TiffError):
+        gt.TiffFile(tmp_path / "missing.tif")
+    a = np.zeros((4, 4), np.uint8)
+    gt.write_tiff(p, [a])
+    with pytest.raises(gt.TiffError):  # no geo tags: the reference throws IOError (geotiff.h:220-222)
+        gt.GeoTIFF(p)
+    raw = bytearray(p.read_bytes())
+    with pytest.raises(ValueError):
+        gt.write_tiff(p, [a, np.zeros((4, 5), np.uint8)])
+    with pytest.raises(ValueError):
+        gt.write_tiff(p, [a], tile=(8, 8))
+    p.write_bytes(bytes(raw[:-20]))  # truncated directory
+    with pytest.raises(gt.TiffError):
+        gt.TiffFile(p)
