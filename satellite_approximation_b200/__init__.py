@@ -44,7 +44,7 @@ from ._capi import (  # noqa: F401  (re-exported)
 __all__ = [
     "LogLevel", "set_log_level", "filling_missing_portions_smooth_boundaries", "blend_images_poisson",
     "find_connected_components", "ConnectedComponents", "mask_scan", "unknown_numbering", "valid_neighbours",
-    "Context", "Scene", "SolveStats", "default_context", "set_solver_defaults", "last_perf_info",
+    "Context", "Scene", "SolveStats", "default_context", "set_solver_defaults", "last_perf_info", "write_perf_info",
     "dist_partition", "dist_levels", "apply_laplace", "preprocess_cloud_band", "blend_images_poisson_offset", "valid_pixel_mask", "image_to_channels", "channels_to_image",
     "highlight_area_replaced", "LAPLACE", "POISSON", "JACOBI", "MULTIGRID", "MG_RB32", "MG_JACOBI64", "SatfillError",
 ]  # fmt: skip
@@ -97,6 +97,19 @@ def set_solver_defaults(**kw) -> None:
 def last_perf_info() -> list[SolveStats]:
     """Records of the most recent fill (the reference appends PerfInfo to a hard-coded CSV, poisson.cpp:287-289)."""
     return list(_last_perf)
+
+
+def write_perf_info(output, records: Optional[Sequence[SolveStats]] = None) -> None:
+    """PerfInfo::write (poisson.cpp:13-18): append `region_size,tolerance,max_iterations,iterations,error,solve_time`
+    (seconds) to the CSV `output`, one line per record (default: the records of the most recent fill).  Opt-in: the
+    reference appends after every mask-overload blend to a path hard-coded to its author's home (poisson.cpp:285-289)."""
+    import os
+
+    rows = list(_last_perf if records is None else records)
+    with open(os.fspath(output), "a") as f:
+        for r in rows:
+            f.write(f"{int(r['unknowns'])},{r['tolerance']:g},{int(r['max_iterations'])},{int(r['iterations'])},"
+                    f"{r['error']:g},{r['solve_ms'] * 1e-3:g}\n")  # fmt: skip
 
 
 def _ptr(a) -> int:

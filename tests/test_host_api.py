@@ -91,3 +91,14 @@ def test_prepost_dtype_rules_before_any_device_work():
         sab.Context.apply_laplace(None, img.astype(np.float64), img)
     with pytest.raises(TypeError):
         sab.Context.morph_close_mask(None, np.zeros((4, 5), np.float32))
+
+
+def test_write_perf_info_csv(tmp_path):
+    """PerfInfo::write (poisson.cpp:13-18): region_size,tolerance,max_iterations,iterations,error,solve_time appended."""
+    recs = [sab.SolveStats(unknowns=633573, tolerance=1e-6, max_iterations=316786, iterations=989, error=9.96e-7,
+                           solve_ms=12500.0),
+            sab.SolveStats(unknowns=4, tolerance=0.5, max_iterations=2, iterations=1, error=0.0, solve_ms=0.25)]  # fmt: skip
+    p = tmp_path / "perf_info.csv"
+    sab.write_perf_info(p, recs[:1])
+    sab.write_perf_info(p, recs[1:])  # appends
+    assert p.read_text() == "633573,1e-06,316786,989,9.96e-07,12.5\n4,0.5,2,1,0,0.00025\n"  # operator<< on doubles = %g
