@@ -6,6 +6,9 @@
 
     python -m satellite_approximation_b200.drivers laplace_main  base.png marked.png out.png
     python -m satellite_approximation_b200.drivers poisson_main  input.tif replacement.tif [--reference-layout]
+    python -m satellite_approximation_b200.drivers fill_folder   base_folder --bands B02,B03,B04 [--poisson]
+        [--no-cache] [--skip-threshold 0.5] [--distance-weight 0.5]      (the commented-out fill_missing_data_folder,
+        lib/approx/source/laplace.cpp:170-244; under torchrun every rank takes every WORLD_SIZE-th date folder)
 
 Pixels go through the C-ABI on the GPU (apply_laplace -> sa_apply_laplace_u8, preprocess_cloud_band ->
 sa_morph_close_mask, blend_images_poisson -> sa_poisson_blend); there is no CPU solve here.  GeoTIFFs are read and
@@ -21,7 +24,7 @@ import numpy as np
 
 from . import geotiff
 
-__all__ = ["imread_color", "imwrite", "read_image", "write_image", "laplace_main", "poisson_main", "main"]
+__all__ = ["imread_color", "imwrite", "read_image", "write_image", "laplace_main", "poisson_main", "fill_folder_main", "main"]
 
 _log = logging.getLogger("approx")
 
@@ -158,6 +161,36 @@ def poisson_main(argv: Sequence[str]) -> int:
     return 0
 
 
+def fill_folder_main(argv: Sequence[str]) -> int:
+    import argparse
+
+    from . import scenes
+
+    ap = argparse.ArgumentParser(prog="fill_folder")
+    ap.add_argument("base_folder")
+    ap.add_argument("--bands", required=True, help="comma-separated band names (files <band>.tif in every date folder)")
+    ap.add_argument("--poisson", action="store_true", help="blend against the date find_good_close_image picks")
+    ap.add_argument("--no-cache", action="store_true")
+    ap.add_argument("--skip-threshold", type=float, default=0.5)
+    ap.add_argument("--distance-weight", type=float, default=0.5)
+    try:
+        a = ap.parse_args(list(argv))
+    except SystemExit:
+        return -1
+    bands = [b for b in a.bands.split(",") if b]
+    shard = scenes.shard_from_env()
+    if shard[1] > 1:
+        os.environ.setdefault("SATFILL_DEVICE", os.environ.get("LOCAL_RANK", "0"))
+    if a.poisson:
+        done = scenes.blend_missing_data_folder(a.base_folder, bands, not a.no_cache, a.skip_threshold, a.distance_weight,
+                                                shard=shard)  # fmt: skip
+    else:
+        done = scenes.fill_missing_data_folder(a.base_folder, bands, not a.no_cache, a.skip_threshold, shard=shard)
+    for name, ids in done.items():
+        _log.info("%s: %s", name, ", ".join(f"{b} -> id {i}" for b, i in ids.items()))
+    return 0
+
+
 def main(argv: Optional[Sequence[str]] = None) -> int:
     argv = list(sys.argv[1:] if argv is None else argv)
     logging.basicConfig(level=logging.INFO, format="%(levelname)s %(name)s: %(message)s")
@@ -165,6 +198,8 @@ def main(argv: Optional[Sequence[str]] = None) -> int:
         return laplace_main(argv[1:])
     if argv and argv[0] == "poisson_main":
         return poisson_main(argv[1:])
+    if argv and argv[0] == "fill_folder":
+        return fill_folder_main(argv[1:])
     print(__doc__)
     return -1
 

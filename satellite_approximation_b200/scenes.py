@@ -23,7 +23,7 @@ from typing import Callable, Optional, Sequence
 import numpy as np
 
 __all__ = ["Date", "parse_simple_date", "CloudShadowStatus", "DayInfo", "ApproxMethod", "DataBase", "GenericError",
-           "find_good_close_image", "DirectoryContents", "find_directory_contents", "fill_missing_data_folder",
+           "find_good_close_image", "DirectoryContents", "find_directory_contents", "fill_missing_data_folder", "shard_from_env",
            "blend_missing_data_folder"]  # fmt: skip
 
 _log = logging.getLogger("approx")
@@ -140,8 +140,9 @@ class DataBase:
 
     def __init__(self, base_path):
         self.path = os.path.join(os.fspath(base_path), "approximation.db")
-        # SQLite::OPEN_CREATE | OPEN_READWRITE (utils/source/db.cpp:10): the directory has to exist
-        self._db = sqlite3.connect(self.path, check_same_thread=False, isolation_level=None)
+        # SQLite::OPEN_CREATE | OPEN_READWRITE (utils/source/db.cpp:10): the directory has to exist.  Several ranks may share
+        # the file (one process per GPU, folders dealt out round-robin): SQLite's file lock serialises them, hence the timeout
+        self._db = sqlite3.connect(self.path, check_same_thread=False, isolation_level=None, timeout=60.0)
         self._lock = threading.Lock()
         self._db.execute(_CREATE_DATES)
 
@@ -272,6 +273,20 @@ def find_directory_contents(path) -> DirectoryContents:
     return DirectoryContents.MultiSpectral if os.path.exists(os.path.join(path, "B04.tif")) else DirectoryContents.Radar
 
 
+def shard_from_env() -> tuple[int, int]:
+    """(RANK, WORLD_SIZE) as torchrun exports them; (0, 1) for a plain process."""
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+
+
+def _my_folders(base_folder: str, shard: tuple[int, int]) -> list[str]:
+    rank, world = shard
+    if not (world >= 1 and 0 <= rank < world):
+        raise ValueError(f"shard: rank {rank} of {world}")
+    folders = sorted(e.path for e in os.scandir(base_folder)
+                     if e.is_dir() and find_directory_contents(e.path) == DirectoryContents.MultiSpectral)  # fmt: skip
+    return folders[rank::world]  # = multi.round_robin(len(folders), world, rank)
+
+
 def _read_scene_mask(folder: str, status: CloudShadowStatus) -> np.ndarray:
     from . import geotiff
 
@@ -293,7 +308,8 @@ def _gpu_laplace(bands: list[np.ndarray], mask: np.ndarray) -> None:
 
 def fill_missing_data_folder(base_folder, band_names: Sequence[str], use_cache: bool, skip_threshold: float,
                              write_outputs: bool = True,
-                             fill: Optional[Callable[[list[np.ndarray], np.ndarray], None]] = None) -> dict[str, dict[str, int]]:  # fmt: skip
+                             fill: Optional[Callable[[list[np.ndarray], np.ndarray], None]] = None,
+                             shard: tuple[int, int] = (0, 1)) -> dict[str, dict[str, int]]:  # fmt: skip
     """The folder driver the reference keeps commented out (laplace.cpp:170-244): for every multispectral date folder
     under `base_folder` whose cloud AND shadow masks exist and whose invalid fraction is at most `skip_threshold`, fill
     the invalid pixels (clouds | shadows) of each band `<folder>/<band>.tif` with the Laplace fill, record the result in
@@ -304,8 +320,9 @@ def fill_missing_data_folder(base_folder, band_names: Sequence[str], use_cache: 
     Differences by design: all bands of a folder share the mask, so they go to the GPU as ONE batched solve (the
     reference re-assembles per band); bands are read in raster layout (geotiff.py).  `fill(bands, mask)` fills float64
     C-ordered bands in place; the default is the GPU path and there is no other implementation in the product (the
-    parameter exists so that the host logic can be tested on a machine without a GPU).  Returns
-    {folder name: {band: id}} for what was filled."""
+    parameter exists so that the host logic can be tested on a machine without a GPU).  `shard=(rank, world)` makes this
+    process take every world-th folder (scenes are independent, one process per GPU, no collective; the
+    ranks share the database file).  Returns {folder name: {band: id}} for what was filled."""
     from . import geotiff
 
     base_folder = os.fspath(base_folder)
@@ -316,8 +333,7 @@ def fill_missing_data_folder(base_folder, band_names: Sequence[str], use_cache: 
         return done
     fill = fill or _gpu_laplace
     with DataBase(base_folder) as db:
-        folders = sorted(e.path for e in os.scandir(base_folder)
-                         if e.is_dir() and find_directory_contents(e.path) == DirectoryContents.MultiSpectral)  # fmt: skip
+        folders = _my_folders(base_folder, shard)
         for folder in folders:
             name = os.path.basename(folder)
             _log.debug("Starting folder: %s", folder)
@@ -364,7 +380,8 @@ def _gpu_poisson(bands: list[np.ndarray], guidance: list[np.ndarray], mask: np.n
 def blend_missing_data_folder(base_folder, band_names: Sequence[str], use_cache: bool, skip_threshold: float,
                               distance_weight: float = 0.5, write_outputs: bool = True,
                               blend: Optional[Callable[[list[np.ndarray], list[np.ndarray], np.ndarray], bool]] = None,
-                              fill: Optional[Callable[[list[np.ndarray], np.ndarray], None]] = None) -> dict[str, dict[str, int]]:  # fmt: skip
+                              fill: Optional[Callable[[list[np.ndarray], np.ndarray], None]] = None,
+                              shard: tuple[int, int] = (0, 1)) -> dict[str, dict[str, int]]:  # fmt: skip
     """The Poisson counterpart the reference's pieces imply (find_good_close_image + blend_images_poisson +
     ApproxMethod::Poisson, never wired together upstream): per date folder pick the guidance date with
     find_good_close_image; if it is another date, Poisson-blend each band against that date's band; if it is the date
@@ -380,8 +397,7 @@ def blend_missing_data_folder(base_folder, band_names: Sequence[str], use_cache:
     blend = blend or _gpu_poisson
     fill = fill or _gpu_laplace
     with DataBase(base_folder) as db:
-        folders = sorted(e.path for e in os.scandir(base_folder)
-                         if e.is_dir() and find_directory_contents(e.path) == DirectoryContents.MultiSpectral)  # fmt: skip
+        folders = _my_folders(base_folder, shard)
         for folder in folders:
             name = os.path.basename(folder)
             status = db.get_status(name)

@@ -109,3 +109,21 @@ def test_poisson_main_plumbing_with_oracle_pixels(tmp_path, monkeypatch, port, l
         assert np.array_equal(got[k][keep], bands_in[k][keep])
     if layout == "reference":  # and the two layouts really are different problems on a non-square scene
         assert not np.array_equal(back(mask), oracle.morph_close_mask(cloud.astype(np.float64), 5))
+
+
+def test_fill_folder_cli_arguments(tmp_path, monkeypatch):
+    from satellite_approximation_b200 import scenes
+
+    seen = {}
+    monkeypatch.setattr(scenes, "fill_missing_data_folder", lambda *a, **k: seen.update(laplace=(a, k)) or {})
+    monkeypatch.setattr(scenes, "blend_missing_data_folder", lambda *a, **k: seen.update(poisson=(a, k)) or {"d": {"B04": 1}})
+    monkeypatch.setenv("RANK", "1")
+    monkeypatch.setenv("WORLD_SIZE", "4")
+    monkeypatch.setenv("LOCAL_RANK", "1")
+    monkeypatch.delenv("SATFILL_DEVICE", raising=False)
+    assert drivers.main(["fill_folder", str(tmp_path), "--bands", "B04,B08", "--no-cache", "--skip-threshold", "0.7"]) == 0
+    assert seen["laplace"] == ((str(tmp_path), ["B04", "B08"], False, 0.7), {"shard": (1, 4)})
+    assert drivers.main(["fill_folder", str(tmp_path), "--bands", "B04", "--poisson", "--distance-weight", "0.25"]) == 0
+    assert seen["poisson"] == ((str(tmp_path), ["B04"], True, 0.5, 0.25), {"shard": (1, 4)})
+    assert os.environ.pop("SATFILL_DEVICE") == "1"  # one process per GPU: the default context follows LOCAL_RANK
+    assert drivers.main(["fill_folder", str(tmp_path)]) == -1  # --bands is required

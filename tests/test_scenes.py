@@ -224,3 +224,21 @@ def test_blend_missing_data_folder(tmp_path, port):
     # a solver failure leaves the folder unrecorded (poisson.cpp:263-269: log and leave the image alone)
     done = sc.blend_missing_data_folder(tmp_path, ["B04"], False, 0.9, 0.0, blend=lambda *a: False, fill=fill)
     assert set(done) == {"2019-05-12"}
+
+
+def test_folder_driver_shards_folders_over_ranks(tmp_path, port, monkeypatch):
+    """scenes are independent -> every world-th folder per rank, one shared database, no collective."""
+    truth = make_scene_tree(tmp_path)
+    with sc.DataBase(tmp_path) as db:
+        for name, (_, mask) in truth.items():
+            db.write_detection_result(name, True, True, 0.0, 0.0, float(mask.mean()))
+    fill = oracle_fill(port)
+    parts = [sc.fill_missing_data_folder(tmp_path, ["B04"], True, 1.0, fill=fill, shard=(r, 2)) for r in range(2)]
+    assert set(parts[0]) == {"2019-05-12", "2019-06-01"} and set(parts[1]) == {"2019-05-22"}  # sorted, every 2nd
+    ids = sorted(i for p in parts for d in p.values() for i in d.values())
+    assert ids == [1, 2, 3]  # one id sequence: the ranks share approximation.db
+    with pytest.raises(ValueError):
+        sc.fill_missing_data_folder(tmp_path, ["B04"], True, 1.0, fill=fill, shard=(2, 2))
+    monkeypatch.setenv("RANK", "3")
+    monkeypatch.setenv("WORLD_SIZE", "8")
+    assert sc.shard_from_env() == (3, 8)
