@@ -306,69 +306,6 @@ def _gpu_laplace(bands: list[np.ndarray], mask: np.ndarray) -> None:
                                        precond=sab._defaults["precond"], check_every=sab._defaults["check_every"])  # fmt: skip
 
 
-def fill_missing_data_folder(base_folder, band_names: Sequence[str], use_cache: bool, skip_threshold: float,
-                             write_outputs: bool = True,
-                             fill: Optional[Callable[[list[np.ndarray], np.ndarray], None]] = None,
-                             shard: tuple[int, int] = (0, 1)) -> dict[str, dict[str, int]]:  # fmt: skip
-    """The folder driver the reference keeps commented out (laplace.cpp:170-244): for every multispectral date folder
-    under `base_folder` whose cloud AND shadow masks exist and whose invalid fraction is at most `skip_threshold`, fill
-    the invalid pixels (clouds | shadows) of each band `<folder>/<band>.tif` with the Laplace fill, record the result in
-    `approximated_data`, and store it as `<folder>/approximated_data/<band>_<id>.tif` (the reference's write is commented
-    out inside the commented-out driver; `write_outputs=False` reproduces that).  With `use_cache`, bands that already
-    have a Laplace row for the date are skipped.
-
-    Differences by design: all bands of a folder share the mask, so they go to the GPU as ONE batched solve (the
-    reference re-assembles per band); bands are read in raster layout (geotiff.py).  `fill(bands, mask)` fills float64
-    C-ordered bands in place; the default is the GPU path and there is no other implementation in the product (the
-    parameter exists so that the host logic can be tested on a machine without a GPU).  `shard=(rank, world)` makes this
-    process take every world-th folder (scenes are independent, one process per GPU, no collective; the
-    ranks share the database file).  Returns {folder name: {band: id}} for what was filled."""
-    from . import geotiff
-
-    base_folder = os.fspath(base_folder)
-    _log.debug("Processing directory: %s", base_folder)
-    done: dict[str, dict[str, int]] = {}
-    if not os.path.isdir(base_folder):
-        _log.warning("Could not process: base folder is not a directory (%s)", base_folder)
-        return done
-    fill = fill or _gpu_laplace
-    with DataBase(base_folder) as db:
-        folders = _my_folders(base_folder, shard)
-        for folder in folders:
-            name = os.path.basename(folder)
-            _log.debug("Starting folder: %s", folder)
-            status = db.get_status(name)
-            if not (status.clouds_exist and status.shadows_exist):
-                _log.warning("Both clouds and shadows don't exist for folder %s. Skipping", folder)
-                continue
-            if status.percent_invalid > skip_threshold:
-                _log.info("Skipping %s because there is too little valid data (%.1f%% invalid)", folder,
-                          status.percent_invalid * 100.0)  # fmt: skip
-                continue
-            existing = db.get_approx_status(name, ApproxMethod.Laplace)
-            todo = [b for b in band_names if not (use_cache and b in existing)]
-            if not todo:
-                continue
-            mask = _read_scene_mask(folder, status)
-            bands = [np.ascontiguousarray(geotiff.GeoTIFF(os.path.join(folder, f"{b}.tif"), np.float64).read(1)) for b in todo]
-            if any(b.shape != mask.shape for b in bands):
-                raise RuntimeError("Input image and mask need to be the same size")  # laplace.cpp:124-127
-            fill(bands, mask)
-            out_dir = os.path.join(folder, "approximated_data")
-            if write_outputs and not os.path.exists(out_dir):
-                _log.info("Creating directory: %s", out_dir)
-                os.makedirs(out_dir)
-            done[name] = {}
-            for b, values in zip(todo, bands):
-                id_ = db.write_approx_results(name, b, ApproxMethod.Laplace)
-                done[name][b] = id_
-                if write_outputs:
-                    src = os.path.join(folder, f"{b}.tif")
-                    geotiff.GeoTiffWriter(values, src).write(os.path.join(out_dir, f"{b}_{id_}.tif"))
-            _log.info("Finished folder: %s", folder)
-    return done
-
-
 def _gpu_poisson(bands: list[np.ndarray], guidance: list[np.ndarray], mask: np.ndarray) -> bool:
     import satellite_approximation_b200 as sab
 
@@ -377,54 +314,54 @@ def _gpu_poisson(bands: list[np.ndarray], guidance: list[np.ndarray], mask: np.n
     return all(s["status"] != sab.SA_NOT_CONVERGED for s in stats)
 
 
-def blend_missing_data_folder(base_folder, band_names: Sequence[str], use_cache: bool, skip_threshold: float,
-                              distance_weight: float = 0.5, write_outputs: bool = True,
-                              blend: Optional[Callable[[list[np.ndarray], list[np.ndarray], np.ndarray], bool]] = None,
-                              fill: Optional[Callable[[list[np.ndarray], np.ndarray], None]] = None,
-                              shard: tuple[int, int] = (0, 1)) -> dict[str, dict[str, int]]:  # fmt: skip
-    """The Poisson counterpart the reference's pieces imply (find_good_close_image + blend_images_poisson +
-    ApproxMethod::Poisson, never wired together upstream): per date folder pick the guidance date with
-    find_good_close_image; if it is another date, Poisson-blend each band against that date's band; if it is the date
-    itself (it has fewer invalid pixels than any neighbour) or there is no neighbour, fall back to the Laplace fill and
-    record it as such.  Same skipping, caching, batching and output rules as fill_missing_data_folder."""
+@dataclass
+class _Job:
+    folder: str
+    name: str
+    status: CloudShadowStatus
+    todo: list
+    method: ApproxMethod
+    guide_dir: Optional[str] = None
+
+
+def _load_job(job: _Job):
+    """Decode one folder: mask, the bands to fill, and (Poisson) the guidance date's bands.  Runs on the reader thread
+    (zlib and numpy release the GIL, so this overlaps the GPU solve of the previous folder)."""
     from . import geotiff
 
-    base_folder = os.fspath(base_folder)
+    def band(folder, b):
+        return np.ascontiguousarray(geotiff.GeoTIFF(os.path.join(folder, f"{b}.tif"), np.float64).read(1))
+
+    mask = _read_scene_mask(job.folder, job.status)
+    bands = [band(job.folder, b) for b in job.todo]
+    guides = [band(job.guide_dir, b) for b in job.todo] if job.guide_dir is not None else None
+    return mask, bands, guides
+
+
+def _run_jobs(jobs: list, db: "DataBase", write_outputs: bool, prefetch: bool, blend, fill) -> dict[str, dict[str, int]]:
+    """Read -> solve -> record -> write, folder after folder.  With `prefetch` the next folder is decoded and the
+    previous folder's result files are encoded on two helper threads while the GPU solves the current one; the database
+    is only touched from the calling thread."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    from . import geotiff
+
     done: dict[str, dict[str, int]] = {}
-    if not os.path.isdir(base_folder):
-        _log.warning("Could not process: base folder is not a directory (%s)", base_folder)
+    if not jobs:
         return done
-    blend = blend or _gpu_poisson
-    fill = fill or _gpu_laplace
-    with DataBase(base_folder) as db:
-        folders = _my_folders(base_folder, shard)
-        for folder in folders:
-            name = os.path.basename(folder)
-            status = db.get_status(name)
-            if not (status.clouds_exist and status.shadows_exist):
-                _log.warning("Both clouds and shadows don't exist for folder %s. Skipping", folder)
-                continue
-            if status.percent_invalid > skip_threshold:
-                _log.info("Skipping %s because there is too little valid data (%.1f%% invalid)", folder,
-                          status.percent_invalid * 100.0)  # fmt: skip
-                continue
-            close = find_good_close_image(name, distance_weight, db)
-            guide_dir = os.path.join(base_folder, close) if close and close != name else None
-            if guide_dir is not None and not all(os.path.exists(os.path.join(guide_dir, f"{b}.tif")) for b in band_names):
-                _log.warning("Guidance date %s lacks some of the bands; using laplace approximation for %s", close, name)
-                guide_dir = None
-            method = ApproxMethod.Poisson if guide_dir is not None else ApproxMethod.Laplace
-            existing = db.get_approx_status(name, method)
-            todo = [b for b in band_names if not (use_cache and b in existing)]
-            if not todo:
-                continue
-            mask = _read_scene_mask(folder, status)
-            bands = [np.ascontiguousarray(geotiff.GeoTIFF(os.path.join(folder, f"{b}.tif"), np.float64).read(1)) for b in todo]
+    reader = ThreadPoolExecutor(1, thread_name_prefix="satfill-read") if prefetch else None
+    writer = ThreadPoolExecutor(1, thread_name_prefix="satfill-write") if prefetch else None
+    writes = []
+    try:
+        nxt = reader.submit(_load_job, jobs[0]) if reader else None
+        for i, job in enumerate(jobs):
+            _log.debug("Starting folder: %s", job.folder)
+            mask, bands, guides = nxt.result() if reader else _load_job(job)
+            if reader and i + 1 < len(jobs):
+                nxt = reader.submit(_load_job, jobs[i + 1])
             if any(b.shape != mask.shape for b in bands):
-                raise RuntimeError("Input image and mask need to be the same size")
-            if guide_dir is not None:
-                guides = [np.ascontiguousarray(geotiff.GeoTIFF(os.path.join(guide_dir, f"{b}.tif"), np.float64).read(1))
-                          for b in todo]  # fmt: skip
+                raise RuntimeError("Input image and mask need to be the same size")  # laplace.cpp:124-127
+            if guides is not None:
                 if any(g.shape != mask.shape for g in guides):
                     _log.error("Input and replacement images must have the same dimensions")  # poisson.cpp:154-157
                     continue
@@ -433,14 +370,110 @@ def blend_missing_data_folder(base_folder, band_names: Sequence[str], use_cache:
                     continue
             else:
                 fill(bands, mask)
-            out_dir = os.path.join(folder, "approximated_data")
-            if write_outputs:
+            out_dir = os.path.join(job.folder, "approximated_data")
+            if write_outputs and not os.path.exists(out_dir):
+                _log.info("Creating directory: %s", out_dir)
                 os.makedirs(out_dir, exist_ok=True)
-            done[name] = {}
-            for b, values in zip(todo, bands):
-                id_ = db.write_approx_results(name, b, method)
-                done[name][b] = id_
+            done[job.name] = {}
+            for b, values in zip(job.todo, bands):
+                id_ = db.write_approx_results(job.name, b, job.method)
+                done[job.name][b] = id_
                 if write_outputs:
-                    geotiff.GeoTiffWriter(values, os.path.join(folder, f"{b}.tif")).write(
-                        os.path.join(out_dir, f"{b}_{id_}.tif"))  # fmt: skip
+                    w = geotiff.GeoTiffWriter(values, os.path.join(job.folder, f"{b}.tif"))
+                    dest = os.path.join(out_dir, f"{b}_{id_}.tif")
+                    if writer:
+                        writes.append(writer.submit(w.write, dest))
+                    else:
+                        w.write(dest)
+            _log.info("Finished folder: %s", job.folder)
+        for f in writes:
+            f.result()  # re-raise what a write raised
+    finally:
+        for ex in (reader, writer):
+            if ex is not None:
+                ex.shutdown(wait=True, cancel_futures=True)
     return done
+
+
+def _eligible(db: "DataBase", folder: str, skip_threshold: float) -> Optional[CloudShadowStatus]:
+    status = db.get_status(os.path.basename(folder))
+    if not (status.clouds_exist and status.shadows_exist):
+        _log.warning("Both clouds and shadows don't exist for folder %s. Skipping", folder)
+        return None
+    if status.percent_invalid > skip_threshold:
+        _log.info("Skipping %s because there is too little valid data (%.1f%% invalid)", folder,
+                  status.percent_invalid * 100.0)  # fmt: skip
+        return None
+    return status
+
+
+def fill_missing_data_folder(base_folder, band_names: Sequence[str], use_cache: bool, skip_threshold: float,
+                             write_outputs: bool = True,
+                             fill: Optional[Callable[[list[np.ndarray], np.ndarray], None]] = None,
+                             shard: tuple[int, int] = (0, 1), prefetch: bool = True) -> dict[str, dict[str, int]]:  # fmt: skip
+    """The folder driver the reference keeps commented out (laplace.cpp:170-244): for every multispectral date folder
+    under `base_folder` whose cloud AND shadow masks exist and whose invalid fraction is at most `skip_threshold`, fill
+    the invalid pixels (clouds | shadows) of each band `<folder>/<band>.tif` with the Laplace fill, record the result in
+    `approximated_data`, and store it as `<folder>/approximated_data/<band>_<id>.tif` (the reference's write is commented
+    out inside the commented-out driver; `write_outputs=False` reproduces that).  With `use_cache`, bands that already
+    have a Laplace row for the date are skipped.
+
+    Differences by design: all bands of a folder share the mask, so they go to the GPU as ONE batched solve (the
+    reference re-assembles per band); bands are read in raster layout (geotiff.py); with `prefetch` the TIFF decode of
+    the next folder and the encode of the previous one overlap the solve (the reference's sketch is a serial
+    std::for_each under one mutex).  `fill(bands, mask)` fills float64 C-ordered bands in place; the default is the GPU
+    path and there is no other implementation in the product (the parameter exists so that the host logic can be tested
+    on a machine without a GPU).  `shard=(rank, world)` makes this process take every world-th folder (SURVEY.md §8e:
+    scenes are independent, one process per GPU, no collective; the ranks share the database file).  Returns
+    {folder name: {band: id}} for what was filled."""
+    base_folder = os.fspath(base_folder)
+    _log.debug("Processing directory: %s", base_folder)
+    if not os.path.isdir(base_folder):
+        _log.warning("Could not process: base folder is not a directory (%s)", base_folder)
+        return {}
+    with DataBase(base_folder) as db:
+        jobs = []
+        for folder in _my_folders(base_folder, shard):
+            status = _eligible(db, folder, skip_threshold)
+            if status is None:
+                continue
+            name = os.path.basename(folder)
+            existing = db.get_approx_status(name, ApproxMethod.Laplace)
+            todo = [b for b in band_names if not (use_cache and b in existing)]
+            if todo:
+                jobs.append(_Job(folder, name, status, todo, ApproxMethod.Laplace))
+        return _run_jobs(jobs, db, write_outputs, prefetch, None, fill or _gpu_laplace)
+
+
+def blend_missing_data_folder(base_folder, band_names: Sequence[str], use_cache: bool, skip_threshold: float,
+                              distance_weight: float = 0.5, write_outputs: bool = True,
+                              blend: Optional[Callable[[list[np.ndarray], list[np.ndarray], np.ndarray], bool]] = None,
+                              fill: Optional[Callable[[list[np.ndarray], np.ndarray], None]] = None,
+                              shard: tuple[int, int] = (0, 1), prefetch: bool = True) -> dict[str, dict[str, int]]:  # fmt: skip
+    """The Poisson counterpart the reference's pieces imply (find_good_close_image + blend_images_poisson +
+    ApproxMethod::Poisson, never wired together upstream): per date folder pick the guidance date with
+    find_good_close_image; if it is another date, Poisson-blend each band against that date's band; if it is the date
+    itself (it has fewer invalid pixels than any neighbour) or there is no neighbour, fall back to the Laplace fill and
+    record it as such.  Same skipping, caching, batching, prefetching and output rules as fill_missing_data_folder."""
+    base_folder = os.fspath(base_folder)
+    if not os.path.isdir(base_folder):
+        _log.warning("Could not process: base folder is not a directory (%s)", base_folder)
+        return {}
+    with DataBase(base_folder) as db:
+        jobs = []
+        for folder in _my_folders(base_folder, shard):
+            status = _eligible(db, folder, skip_threshold)
+            if status is None:
+                continue
+            name = os.path.basename(folder)
+            close = find_good_close_image(name, distance_weight, db)
+            guide_dir = os.path.join(base_folder, close) if close and close != name else None
+            if guide_dir is not None and not all(os.path.exists(os.path.join(guide_dir, f"{b}.tif")) for b in band_names):
+                _log.warning("Guidance date %s lacks some of the bands; using laplace approximation for %s", close, name)
+                guide_dir = None
+            method = ApproxMethod.Poisson if guide_dir is not None else ApproxMethod.Laplace
+            existing = db.get_approx_status(name, method)
+            todo = [b for b in band_names if not (use_cache and b in existing)]
+            if todo:
+                jobs.append(_Job(folder, name, status, todo, method, guide_dir))
+        return _run_jobs(jobs, db, write_outputs, prefetch, blend or _gpu_poisson, fill or _gpu_laplace)

@@ -242,3 +242,47 @@ def test_folder_driver_shards_folders_over_ranks(tmp_path, port, monkeypatch):
     monkeypatch.setenv("RANK", "3")
     monkeypatch.setenv("WORLD_SIZE", "8")
     assert sc.shard_from_env() == (3, 8)
+
+
+def test_folder_driver_prefetch_overlaps_and_matches_serial(tmp_path, port, monkeypatch):
+    import threading
+
+    truth = make_scene_tree(tmp_path)
+    with sc.DataBase(tmp_path) as db:
+        for name, (_, mask) in truth.items():
+            db.write_detection_result(name, True, True, 0.0, 0.0, float(mask.mean()))
+    fill = oracle_fill(port)
+    loading = {}
+    real_load = sc._load_job
+
+    def load(job):
+        loading.setdefault(job.name, threading.Event()).set()
+        return real_load(job), threading.current_thread().name
+
+    monkeypatch.setattr(sc, "_load_job", lambda job: load(job)[0])
+    overlapped = []
+
+    def slow_fill(bands, mask):
+        # while folder k is being solved, the reader thread must already be decoding folder k + 1
+        nxt = {"2019-05-12": "2019-05-22", "2019-05-22": "2019-06-01"}
+        cur = [n for n, (_, m) in truth.items() if m.shape == mask.shape and np.array_equal(m, mask)][0]
+        if cur in nxt:
+            overlapped.append(loading.setdefault(nxt[cur], threading.Event()).wait(timeout=20))
+        fill(bands, mask)
+
+    a = sc.fill_missing_data_folder(tmp_path, ["B04", "B08"], False, 1.0, fill=slow_fill, prefetch=True)
+    assert overlapped == [True, True]
+    b = sc.fill_missing_data_folder(tmp_path, ["B04", "B08"], False, 1.0, fill=fill, prefetch=False)
+    assert list(a) == list(b) == ["2019-05-12", "2019-05-22", "2019-06-01"]
+    for name in a:
+        for band in ("B04", "B08"):
+            x = gt.TiffFile(tmp_path / name / "approximated_data" / f"{band}_{a[name][band]}.tif").read_band(1)
+            y = gt.TiffFile(tmp_path / name / "approximated_data" / f"{band}_{b[name][band]}.tif").read_band(1)
+            assert np.array_equal(x, y)
+    # a folder that cannot be decoded: the error surfaces, earlier folders are recorded, helper threads are gone
+    (tmp_path / "2019-05-22" / "B08.tif").write_bytes(b"II*\0garbage")
+    with pytest.raises(gt.TiffError):
+        sc.fill_missing_data_folder(tmp_path, ["B04", "B08"], False, 1.0, fill=fill)
+    with sc.DataBase(tmp_path) as db:
+        assert len(db.get_approx_status("2019-05-12", sc.ApproxMethod.Laplace)) == 2
+    assert not [t for t in threading.enumerate() if t.name.startswith("satfill-")]
