@@ -4,6 +4,9 @@
 #include <pybind11/pybind11.h>
 #include <pybind11/stl.h>
 
+#include <filesystem>
+#include <string>
+
 #include <approx/laplace.h>
 #include <approx/poisson.h>
 
@@ -15,6 +18,11 @@ enum class LogLevel { Debug = 1, Info = 2, Warn = 3, Error = 4, Critical = 5 }; 
 PYBIND11_MODULE(_core, m)
 {
     m.doc() = "Data processing for sentinel satellite imagery (Laplace / Poisson fill path on B200)";
+    py::class_<std::filesystem::path>(m, "Path")  // src/main.cpp:20-22
+        .def(py::init<std::string>())
+        .def("__str__", [](std::filesystem::path const& p) { return p.string(); })
+        .def("__fspath__", [](std::filesystem::path const& p) { return p.string(); });
+    py::implicitly_convertible<std::string, std::filesystem::path>();
     py::enum_<LogLevel>(m, "LogLevel")
         .value("Debug", LogLevel::Debug)
         .value("Info", LogLevel::Info)

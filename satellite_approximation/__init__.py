@@ -5,12 +5,13 @@ C-ABI (libsatfill.so) and neither has a CPU fallback.  Cloud-detection symbols o
 from __future__ import annotations
 
 try:
-    from ._core import LogLevel, blend_images_poisson, filling_missing_portions_smooth_boundaries, set_log_level
+    from ._core import LogLevel, Path, blend_images_poisson, filling_missing_portions_smooth_boundaries, set_log_level
 
     BACKEND = "pybind11"
 except ImportError:
     from satellite_approximation_b200 import (
         LogLevel,
+        Path,
         blend_images_poisson,
         filling_missing_portions_smooth_boundaries,
         set_log_level,
@@ -18,7 +19,7 @@ except ImportError:
 
     BACKEND = "ctypes"
 
-__all__ = ["LogLevel", "set_log_level", "filling_missing_portions_smooth_boundaries", "blend_images_poisson"]
+__all__ = ["LogLevel", "Path", "set_log_level", "filling_missing_portions_smooth_boundaries", "blend_images_poisson"]
 
 
 def __getattr__(name):

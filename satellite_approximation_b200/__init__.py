@@ -42,7 +42,7 @@ from ._capi import (  # noqa: F401  (re-exported)
 )
 
 __all__ = [
-    "LogLevel", "set_log_level", "filling_missing_portions_smooth_boundaries", "blend_images_poisson",
+    "LogLevel", "Path", "set_log_level", "filling_missing_portions_smooth_boundaries", "blend_images_poisson",
     "find_connected_components", "ConnectedComponents", "mask_scan", "unknown_numbering", "valid_neighbours",
     "Context", "Scene", "SolveStats", "default_context", "set_solver_defaults", "last_perf_info", "write_perf_info",
     "dist_partition", "dist_levels", "apply_laplace", "preprocess_cloud_band", "blend_images_poisson_offset", "valid_pixel_mask", "image_to_channels", "channels_to_image",
@@ -66,6 +66,24 @@ _PY_LEVEL = {
     LogLevel.Debug: logging.DEBUG, LogLevel.Info: logging.INFO, LogLevel.Warn: logging.WARNING,
     LogLevel.Error: logging.ERROR, LogLevel.Critical: logging.CRITICAL,
 }  # fmt: skip
+
+
+class Path:
+    """`Path` of the reference's module (src/main.cpp:20-22): std::filesystem::path constructible from a str."""
+
+    def __init__(self, path: str):
+        if not isinstance(path, str):
+            raise TypeError("Path(): expected a str")
+        self._p = path
+
+    def __fspath__(self) -> str:
+        return self._p
+
+    def __str__(self) -> str:
+        return self._p
+
+    def __repr__(self) -> str:
+        return f"Path({self._p!r})"
 
 
 def set_log_level(level: LogLevel) -> None:

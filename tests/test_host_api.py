@@ -9,8 +9,17 @@ import satellite_approximation_b200 as sab
 
 
 def test_exports_match_reference_module():
-    for name in ("LogLevel", "set_log_level", "filling_missing_portions_smooth_boundaries", "blend_images_poisson"):
-        assert hasattr(sab, name)
+    import os
+
+    import satellite_approximation as sa  # the reference-named package: pybind11 _core when built, else the ctypes mirror
+
+    for mod in (sab, sa):
+        for name in ("LogLevel", "Path", "set_log_level", "filling_missing_portions_smooth_boundaries",
+                     "blend_images_poisson"):  # fmt: skip
+            assert hasattr(mod, name), (mod.__name__, name)
+        assert os.fspath(mod.Path("a/b.tif")) == "a/b.tif"  # src/main.cpp:20-22: constructible from a str
+    with pytest.raises(NotImplementedError):
+        sa.detect  # cloud / shadow detection is outside the path
     assert [m.name for m in sab.LogLevel] == ["Debug", "Info", "Warn", "Error", "Critical"]  # src/main.cpp:24-29
     sab.set_log_level(sab.LogLevel.Warn)
 
