@@ -3,7 +3,8 @@ and `utils::GeoTiffWriter<T>` (lib/utils/include/utils/geotiff.h:98-195 writer, 
 uses to fetch bands 1-5 + the cloud band and to store the blended bands (executables/poisson-main.cpp:53-70).
 
 The reference sits on GDAL, which this image does not have; SURVEY.md §8f-2 lists the GeoTIFF step as the data format next
-to the path.  This module is a self-contained TIFF codec for what Sentinel-2 exports use (numpy + zlib only):
+to the path.  This module is a self-contained TIFF codec for what Sentinel-2 exports use (numpy + zlib; the LZW and
+PackBits byte decoders are C, csrc/tiffcodec.c -> lib/libsattiff.so, with interpreter versions of the same as a stand-in):
 
   read   classic TIFF and BigTIFF, either byte order, strips or tiles, chunky or planar samples, 8/16/32/64-bit unsigned /
          signed / IEEE samples, compression none (1), deflate (8, 32946), LZW (5), PackBits (32773), predictor 1 / 2 / 3;
@@ -151,15 +152,50 @@ def _packbits_decode(data: bytes) -> bytes:
     return bytes(out)
 
 
-def _decompress(data: bytes, compression: int) -> bytes:
+_native = None
+
+
+def _native_codec():
+    """lib/libsattiff.so (csrc/tiffcodec.c): LZW / PackBits decoders in C.  Host-side I/O helper, optional: without it the
+    interpreter versions above decode the same bytes, only slowly.  False once loading has failed."""
+    global _native
+    if _native is None:
+        import ctypes as C
+
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libsattiff.so")
+        try:
+            lib = C.CDLL(path)
+            for fn in (lib.st_lzw_decode, lib.st_packbits_decode):
+                fn.argtypes = [C.c_char_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+                fn.restype = C.c_int
+            _native = lib
+        except (OSError, AttributeError):
+            _native = False
+    return _native
+
+
+def _decode_native(fn, data: bytes, expected: int) -> bytes:
+    import ctypes as C
+
+    out = C.create_string_buffer(max(expected, 1))
+    produced = C.c_size_t(0)
+    rc = fn(data, len(data), out, expected, C.byref(produced))
+    if rc != 0:
+        raise TiffError("corrupt LZW stream" if rc == -1 else "LZW stream does not start with a clear code")
+    return out.raw[: produced.value]
+
+
+def _decompress(data: bytes, compression: int, expected: int) -> bytes:
+    """`expected` = the decoded size of a full segment (an upper bound: the last strip may be shorter)."""
     if compression == 1:
         return data
     if compression in (8, 32946):
         return zlib.decompress(data)
-    if compression == 5:
-        return _lzw_decode(data)
-    if compression == 32773:
-        return _packbits_decode(data)
+    if compression in (5, 32773):
+        lib = _native_codec()
+        if lib:
+            return _decode_native(lib.st_lzw_decode if compression == 5 else lib.st_packbits_decode, data, expected)
+        return _lzw_decode(data) if compression == 5 else _packbits_decode(data)
     raise TiffError(f"unsupported TIFF compression {compression}")
 
 
@@ -308,9 +344,9 @@ class TiffFile:
         raw = self._buf[off : off + cnt]
         if len(raw) != cnt:
             raise TiffError(f"{self.path}: segment {index} points outside the file")
-        data = _decompress(raw, self.compression)
         isz = self.dtype.itemsize
         row_bytes = self.seg_w * nsamp * isz
+        data = _decompress(raw, self.compression, self.seg_h * row_bytes)
         rows = min(self.seg_h, len(data) // row_bytes) if row_bytes else 0
         if rows <= 0:
             raise TiffError(f"{self.path}: segment {index} is truncated")

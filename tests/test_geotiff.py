@@ -251,3 +251,36 @@ def test_errors(tmp_path):
     p.write_bytes(bytes(raw[:-20]))  # truncated directory
     with pytest.raises(gt.TiffError):
         gt.TiffFile(p)
+
+
+def test_native_and_interpreter_decoders_agree(tmp_path):
+    """csrc/tiffcodec.c (lib/libsattiff.so) against the pure-Python decoders on libtiff-written LZW / PackBits streams,
+    including streams long enough to reset the LZW table, and on corrupt input."""
+    Image = pytest.importorskip("PIL.Image")
+    lib = gt._native_codec()
+    assert lib, "libsattiff.so is not built (make -C satellite_approximation_b200/csrc)"
+    rng = np.random.default_rng(5)
+    noisy = (rng.random((300, 400)) * 65535).astype(np.uint16)  # incompressible: many table resets
+    smooth = (np.add.outer(np.arange(300), np.arange(400)) // 7).astype(np.uint16)  # long matches
+    flat = np.zeros((300, 400), np.uint8)
+    p = tmp_path / "n.tif"
+    for a in (noisy, smooth, flat):
+        for comp, fn, py in (("tiff_lzw", lib.st_lzw_decode, gt._lzw_decode), ("packbits", lib.st_packbits_decode, gt._packbits_decode)):
+            Image.fromarray(a).save(p, compression=comp)
+            t = gt.TiffFile(p)
+            assert np.array_equal(t.read_band(1), a)  # through the native decoder
+            for off, cnt in zip(t._offsets, t._counts):
+                raw = t._buf[int(off) : int(off) + int(cnt)]
+                want = py(raw)
+                cap = t.seg_h * t.seg_w * a.dtype.itemsize
+                assert gt._decode_native(fn, raw, cap) == want[:cap]
+                assert gt._decode_native(fn, raw, 10) == want[:10]  # clipped output
+    with pytest.raises(gt.TiffError):
+        gt._decode_native(lib.st_lzw_decode, b"\x00\x00\x00\x00", 16)  # no clear code first
+    with pytest.raises(gt.TiffError):
+        gt._lzw_decode(b"\x00\x00\x00\x00")
+    bad = bytes([0x80, 0x7F, 0xFF, 0xC0])  # clear, then code 0x1FF (>= next) as the first code
+    with pytest.raises(gt.TiffError):
+        gt._decode_native(lib.st_lzw_decode, bad, 16)
+    with pytest.raises(gt.TiffError):
+        gt._lzw_decode(bad)
