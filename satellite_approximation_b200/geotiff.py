@@ -190,7 +190,10 @@ def _decompress(data: bytes, compression: int, expected: int) -> bytes:
     if compression == 1:
         return data
     if compression in (8, 32946):
-        return zlib.decompress(data)
+        try:
+            return zlib.decompress(data)
+        except zlib.error as e:
+            raise TiffError(f"corrupt deflate stream: {e}") from e
     if compression in (5, 32773):
         lib = _native_codec()
         if lib:
@@ -205,6 +208,8 @@ def _decompress(data: bytes, compression: int, expected: int) -> bytes:
 
 class TiffFile:
     """First image file directory of a TIFF / BigTIFF: tags, geometry, and band decoding."""
+
+    decode_threads = min(8, os.cpu_count() or 1)  # segments decoded concurrently (class-wide knob)
 
     def __init__(self, path):
         self.path = os.fspath(path)
@@ -371,6 +376,33 @@ class TiffFile:
             raise TiffError(f"unsupported TIFF predictor {self.predictor}")
         return a
 
+    def _fill(self, out: np.ndarray, base: int, nsamp: int, pick: Optional[int]) -> None:
+        """Decode the segments of one plane into `out` ((H, W) with `pick`, (H, W, nsamp) without).  Segments are
+        independent, and zlib, the C decoders and numpy all release the GIL, so they are decoded on a small thread pool
+        when the file is big enough for that to pay."""
+
+        def one(k: int) -> None:
+            sy, sx = divmod(k, self._segs_x)
+            r0, c0 = sy * self.seg_h, sx * self.seg_w
+            seg = self._segment(base + k, nsamp)
+            h = min(self.seg_h, self.height - r0)
+            w = min(self.seg_w, self.width - c0)
+            if seg.shape[0] < h:
+                raise TiffError(f"{self.path}: segment {sy},{sx} is truncated")
+            out[r0 : r0 + h, c0 : c0 + w] = seg[:h, :w, pick] if pick is not None else seg[:h, :w]
+
+        n = self._segs_x * self._segs_y
+        workers = min(self.decode_threads, n)
+        if workers <= 1 or out.nbytes < (4 << 20):
+            for k in range(n):
+                one(k)
+            return
+        from concurrent.futures import ThreadPoolExecutor
+
+        with ThreadPoolExecutor(workers, thread_name_prefix="satfill-tiff") as pool:
+            for _ in pool.map(one, range(n), chunksize=max(1, n // (8 * workers))):
+                pass
+
     def read_band(self, band: int) -> np.ndarray:
         """Band `band` (1-based, GDAL numbering) as a C-ordered (height, width) array of the file's sample type."""
         spp = self.samples_per_pixel
@@ -378,19 +410,10 @@ class TiffFile:
             raise TiffError(f"{self.path}: band {band} out of range 1..{spp}")
         out = np.empty((self.height, self.width), dtype=self.dtype.newbyteorder("="))
         per_plane = self._segs_x * self._segs_y
-        base = (band - 1) * per_plane if self.planar == 2 else 0
-        nsamp = 1 if self.planar == 2 else spp
-        pick = 0 if self.planar == 2 else band - 1
-        for sy in range(self._segs_y):
-            r0 = sy * self.seg_h
-            for sx in range(self._segs_x):
-                c0 = sx * self.seg_w
-                seg = self._segment(base + sy * self._segs_x + sx, nsamp)
-                h = min(seg.shape[0], self.height - r0)
-                w = min(self.seg_w, self.width - c0)
-                if seg.shape[0] < h:
-                    raise TiffError(f"{self.path}: segment {sy},{sx} is truncated")
-                out[r0 : r0 + h, c0 : c0 + w] = seg[:h, :w, pick]
+        if self.planar == 2:
+            self._fill(out, (band - 1) * per_plane, 1, 0)
+        else:
+            self._fill(out, 0, spp, band - 1)
         return out
 
     def read_all(self) -> list[np.ndarray]:
@@ -399,14 +422,7 @@ class TiffFile:
         # chunky: decode every segment once
         spp = self.samples_per_pixel
         out = np.empty((self.height, self.width, spp), dtype=self.dtype.newbyteorder("="))
-        for sy in range(self._segs_y):
-            r0 = sy * self.seg_h
-            for sx in range(self._segs_x):
-                c0 = sx * self.seg_w
-                seg = self._segment(sy * self._segs_x + sx, spp)
-                h = min(seg.shape[0], self.height - r0)
-                w = min(self.seg_w, self.width - c0)
-                out[r0 : r0 + h, c0 : c0 + w] = seg[:h, :w]
+        self._fill(out, 0, spp, None)
         return [np.ascontiguousarray(out[:, :, b]) for b in range(spp)]
 
 

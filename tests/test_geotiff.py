@@ -284,3 +284,27 @@ def test_native_and_interpreter_decoders_agree(tmp_path):
         gt._decode_native(lib.st_lzw_decode, bad, 16)
     with pytest.raises(gt.TiffError):
         gt._lzw_decode(bad)
+
+
+def test_threaded_segment_decode_matches_serial(tmp_path, monkeypatch):
+    rng = np.random.default_rng(9)
+    a = (np.add.outer(np.arange(1300), np.arange(1700)) % 4096 + rng.integers(0, 40, (1300, 1700))).astype(np.uint16)
+    b = a[::-1].copy()
+    for kw in ({"rows_per_strip": 8}, {"tile": (256, 256)}):
+        p = tmp_path / "big.tif"
+        gt.write_tiff(p, [a, b], compress=True, **kw)
+        monkeypatch.setattr(gt.TiffFile, "decode_threads", 4)
+        par = gt.TiffFile(p).read_all()
+        monkeypatch.setattr(gt.TiffFile, "decode_threads", 1)
+        ser = gt.TiffFile(p).read_all()
+        assert np.array_equal(par[0], a) and np.array_equal(par[1], b)
+        assert all(np.array_equal(x, y) for x, y in zip(par, ser))
+    # an error inside a worker surfaces as the reader's error
+    raw = bytearray((tmp_path / "big.tif").read_bytes())
+    t = gt.TiffFile(tmp_path / "big.tif")
+    off = int(t._offsets[len(t._offsets) // 2])
+    raw[off : off + 8] = b"\xff" * 8  # corrupt one deflate stream
+    (tmp_path / "bad.tif").write_bytes(bytes(raw))
+    monkeypatch.setattr(gt.TiffFile, "decode_threads", 4)
+    with pytest.raises(gt.TiffError):
+        gt.TiffFile(tmp_path / "bad.tif").read_all()
