@@ -3,8 +3,11 @@
 #pragma once
 
 #include <optional>
+#include <string>
 
 #include "utils.h"
+#include "utils/date.h"
+#include "utils/error.h"
 
 namespace approx {
 
@@ -28,6 +31,28 @@ void blend_images_poisson(MultiChannelImage& input_images, MultiChannelImage con
 std::vector<MatX<f64>> blend_images_poisson(std::vector<MatX<f64>> const& input_images,
     std::vector<MatX<f64>> const& replacement_images, MatX<bool> const& invalid_mask, f64 tolerance = 1e-6,
     std::optional<int> max_iterations = {});
+
+// poisson.h:54, poisson.cpp:305-321: paint the pasted (non white-key) pixels of the replacement with `color` in the first
+// three channels of the input, at the offset.
+void highlight_area_replaced(MultiChannelImage& input_images, MultiChannelImage const& replacement_images, int start_row,
+    int start_col, Vec3<f64> const& color);
+
+// approx::DayInfo (lib/approx/include/approx/db.h:12-17) and the ranking rule of find_good_close_image
+// (poisson.cpp:323-349) on a list of candidates.  The reference pulls the candidates out of SQLite (approx::DataBase,
+// db.cpp:97-156); that side needs SQLiteCpp + Boost.date_time, which this image lacks, so the C++ shim takes the rows as
+// arguments and the database itself is mirrored in the Python package (satellite_approximation_b200/scenes.py).
+struct DayInfo {
+    utils::Date date;
+    f64 percent_invalid = 0.0;
+    [[nodiscard]] f64 distance(utils::Date const& other, f64 weight) const  // db.cpp:12-16
+    {
+        return weight * (f64)std::labs(other.days() - date.days()) + (1 - weight) * percent_invalid;
+    }
+};
+// Returns the ISO date of the best neighbour, `date_string` itself when the date has fewer invalid pixels than that
+// neighbour, "" when `close_images` is empty; throws utils::GenericError for a weight outside [0, 1].
+std::string find_good_close_image(std::string const& date_string, f64 distance_weight, std::vector<DayInfo> close_images,
+    f64 percent_invalid_of_date);
 
 // The record of the last blend (the reference appends it to a hard-coded path, poisson.cpp:287-289).
 PerfInfo const& last_perf_info();

@@ -8,7 +8,9 @@
 #include <climits>
 #include <cstdio>
 #include <fstream>
+#include <algorithm>
 #include <mutex>
+#include <sstream>
 #include <stdexcept>
 #include <string>
 
@@ -165,6 +167,34 @@ std::vector<MatX<f64>> blend_images_poisson(std::vector<MatX<f64>> const& input_
     MultiChannelImage replacement(replacement_images);
     blend_images_poisson(input, replacement, invalid_mask, tolerance, max_iterations);
     return input.images;
+}
+
+void highlight_area_replaced(MultiChannelImage& input_images, MultiChannelImage const& replacement_images, int start_row,
+    int start_col, Vec3<f64> const& color)
+{
+    for (Eigen::Index row = 0; row < replacement_images.rows(); ++row)  // poisson.cpp:305-321
+        for (Eigen::Index col = 0; col < replacement_images.cols(); ++col)
+            if (replacement_images.valid_pixel(row, col))
+                for (int c = 0; c < 3; ++c)
+                    input_images(c, row + start_row, col + start_col) = color[c];
+}
+
+std::string find_good_close_image(std::string const& date_string, f64 distance_weight, std::vector<DayInfo> close_images,
+    f64 percent_invalid_of_date)
+{
+    if (distance_weight < 0 || distance_weight > 1)  // poisson.cpp:325-327
+        throw utils::GenericError("Could not find close image: distance weight not between 0 and 1");
+    utils::Date date(date_string);
+    if (close_images.empty())  // poisson.cpp:331-334
+        return {};
+    std::stable_sort(close_images.begin(), close_images.end(), [&](DayInfo const& a, DayInfo const& b) {
+        return a.distance(date, distance_weight) < b.distance(date, distance_weight);
+    });
+    if (percent_invalid_of_date < close_images[0].percent_invalid)  // poisson.cpp:340-343: use the Laplace fill instead
+        return date_string;
+    std::ostringstream iso;  // to_iso_extended_string: YYYY-MM-DD
+    iso << close_images[0].date;
+    return iso.str();
 }
 
 ConnectedComponents find_connected_components(MatX<bool> const& invalid)

@@ -9,6 +9,9 @@
 
 #include <approx/laplace.h>
 #include <approx/poisson.h>
+#include <utils/filesystem.h>
+
+#include <array>
 
 namespace py = pybind11;
 using namespace py::literals;
@@ -55,6 +58,30 @@ PYBIND11_MODULE(_core, m)
             return input.images;
         },
         "input_image"_a, "replacement_image"_a, "start_row"_a, "start_column"_a);
+    // the dependency-free host pieces of the shim, exposed for the tests (tests/test_host_api.py)
+    m.def(
+        "highlight_area_replaced",
+        [](std::vector<MatX<f64>> input_images, std::vector<MatX<f64>> const& replacement_images, int start_row,
+            int start_column, std::array<double, 3> color) {
+            approx::MultiChannelImage input(std::move(input_images)), replacement(replacement_images);
+            approx::highlight_area_replaced(input, replacement, start_row, start_column,
+                Vec3<f64>(color[0], color[1], color[2]));
+            return input.images;
+        },
+        "input_image"_a, "replacement_image"_a, "start_row"_a, "start_column"_a, "color"_a);
+    m.def(
+        "find_good_close_image",
+        [](std::string const& date_string, double weight, std::vector<std::pair<std::string, double>> const& close,
+            double percent_invalid_of_date) {
+            std::vector<approx::DayInfo> info;
+            for (auto const& [d, p] : close)
+                info.push_back({ utils::Date(d), p });
+            return approx::find_good_close_image(date_string, weight, std::move(info), percent_invalid_of_date);
+        },
+        "date_string"_a, "distance_weight"_a, "close_images"_a, "percent_invalid_of_date"_a);
+    m.def("find_directory_contents", [](std::string const& path) { return (int)utils::find_directory_contents(path); });
+    m.def("date_days", [](std::string const& d) { return utils::Date(d).days(); });
+    py::register_exception<utils::GenericError>(m, "GenericError", PyExc_RuntimeError);
     m.def(
         "find_connected_components",
         [](MatX<bool> const& invalid) {

@@ -111,3 +111,54 @@ def test_write_perf_info_csv(tmp_path):
     sab.write_perf_info(p, recs[:1])
     sab.write_perf_info(p, recs[1:])  # appends
     assert p.read_text() == "633573,1e-06,316786,989,9.96e-07,12.5\n4,0.5,2,1,0,0.00025\n"  # operator<< on doubles = %g
+
+
+def _core_or_skip():
+    try:
+        from satellite_approximation import _core
+    except ImportError:
+        pytest.skip("satellite_approximation._core is not built (make -C cpp pybind needs Eigen headers)")
+    return _core
+
+
+def test_cpp_shim_host_pieces_match_the_python_mirror(tmp_path):
+    """The dependency-free host functions of the C++ `approx` shim (cpp/): highlight_area_replaced (poisson.cpp:305-321),
+    the ranking rule of find_good_close_image (poisson.cpp:323-349), utils::Date day arithmetic and
+    utils::find_directory_contents -- against the Python mirror and the datetime module."""
+    import datetime as dt
+
+    from satellite_approximation_b200 import scenes as sc
+
+    core = _core_or_skip()
+    rng = np.random.default_rng(2)
+    ins = [rng.random((12, 15)) for _ in range(3)]
+    rep = [rng.random((5, 6)) * 0.9 for _ in range(3)]
+    for ch in rep:
+        ch[1:3, 2:5] = 1.25  # the white key: truncates to 1 in all three channels
+    want = [a.copy() for a in ins]
+    sab.highlight_area_replaced(want, rep, 4, 7, (0.1, 0.2, 0.3))
+    got = core.highlight_area_replaced(ins, rep, 4, 7, (0.1, 0.2, 0.3))
+    assert all(np.array_equal(g, w) for g, w in zip(got, want)) and not np.array_equal(got[0], ins[0])
+    # Date: days since the epoch, validation
+    for s in ("1970-01-01", "2019-05-22", "2020-02-29", "2000-03-01", "1900-03-01", "2019-5-2", "2019/12/31"):
+        assert core.date_days(s) == (sc.parse_simple_date(s) - dt.date(1970, 1, 1)).days, s
+    for bad in ("2019-02-29", "2019-13-01", "2019-05", "2019-05-22x", "x"):
+        with pytest.raises(IndexError):  # std::out_of_range
+            core.date_days(bad)
+    # find_good_close_image on the rows of test_scenes.test_find_good_close_image
+    rows = [("2019-04-30", 0.0), ("2019-05-02", 0.05), ("2019-05-20", 0.90), ("2019-06-11", 0.10)]
+    with sc.DataBase(tmp_path) as db:
+        for d, p in rows + [("2019-05-22", 0.30)]:
+            db.write_detection_result(d, True, True, 0, 0, p)
+        for w in (0.0, 0.01, 0.05, 0.5, 1.0):
+            assert core.find_good_close_image("2019-05-22", w, rows, 0.30) == sc.find_good_close_image("2019-05-22", w, db), w
+    assert core.find_good_close_image("2019-05-22", 0.5, [], 0.3) == ""
+    assert core.find_good_close_image("2019-05-21", 1.0, rows, float("nan")) == "2019-05-20"
+    with pytest.raises(RuntimeError):
+        core.find_good_close_image("2019-05-22", 1.5, rows, 0.3)
+    # find_directory_contents
+    (tmp_path / "2019-05-22").mkdir()
+    (tmp_path / "2019-05-22" / "B04.tif").write_bytes(b"")
+    (tmp_path / "2019-05-23").mkdir()
+    for name in ("2019-05-22", "2019-05-23", "logs"):
+        assert core.find_directory_contents(str(tmp_path / name)) == sc.find_directory_contents(tmp_path / name).value
