@@ -483,6 +483,97 @@ class GeoTIFF:
         g = self.geo_transform
         return (g[0] + col * g[1] + row * g[2], g[3] + col * g[4] + row * g[5])
 
+    # -- geo-referencing helpers (geotiff.h:322-421; positions are LatLng = (north-south, east-west), north-up assumed) -----
+    def east_west_step(self) -> float:
+        return self.geo_transform[1]
+
+    def north_south_step(self) -> float:
+        return self.geo_transform[5]
+
+    def north(self) -> float:
+        return self.geo_transform[3]
+
+    def west(self) -> float:
+        return self.geo_transform[0]
+
+    def south(self) -> float:
+        return self.geo_transform[3] + self.height * self.north_south_step()
+
+    def east(self) -> float:
+        return self.geo_transform[0] + self.width * self.east_west_step()
+
+    def north_west(self) -> tuple[float, float]:
+        return (self.north(), self.west())
+
+    def north_east(self) -> tuple[float, float]:
+        return (self.north(), self.east())
+
+    def south_east(self) -> tuple[float, float]:
+        return (self.south(), self.east())
+
+    def south_west(self) -> tuple[float, float]:
+        return (self.south(), self.west())
+
+    def index_at(self, pos: Sequence[float]) -> tuple[int, int]:
+        """(x, y) = (column, row) of the pixel under `pos`, clamped to the image (geotiff.h:383-391; the C++ cast
+        truncates towards zero)."""
+        x = int((pos[1] - self.west()) / self.east_west_step())
+        y = int((pos[0] - self.north()) / self.north_south_step())
+        return (min(max(x, 0), self.width - 1), min(max(y, 0), self.height - 1))
+
+    def value_at(self, pos: Sequence[float], values: np.ndarray):
+        x, y = self.index_at(pos)
+        return values[y, x]
+
+    def uv_at(self, pos: Sequence[float]) -> tuple[float, float]:
+        x, y = self.index_at(pos)
+        return (x / self.width, y / self.height)
+
+    def mid_point_of_pixel(self, index: Sequence[int]) -> tuple[float, float]:
+        """geotiff.h:393-398, as written there: index[0] steps north-south, index[1] east-west."""
+        return (self.north() + self.north_south_step() * float(index[0]) + self.north_south_step() * 0.5,
+                self.west() + self.east_west_step() * float(index[1]) + self.east_west_step() * 0.5)  # fmt: skip
+
+    def bilinear_value_at(self, pos: Sequence[float], values: np.ndarray):
+        """geotiff.h:343-372.  On a pixel centre line (x or y integral) the reference divides by zero (inf * 0 = NaN for
+        floating samples); mirrored as is."""
+        x = (pos[1] - self.west()) / self.east_west_step()
+        y = (pos[0] - self.north()) / self.north_south_step()
+        x1, x2, y1, y2 = np.floor(x), np.ceil(x), np.floor(y), np.ceil(y)
+
+        def value(fx, fy):
+            xi = min(max(int(fx), 0), self.width - 1)
+            yi = min(max(int(fy), 0), self.height - 1)
+            return values[yi, xi]
+
+        m = np.array([[value(x1, y1), value(x1, y2)], [value(x2, y1), value(x2, y2)]], dtype=np.float64)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            s = np.float64(1.0) / np.float64((x2 - x1) * (y2 - y1))
+            r = s * (np.array([x2 - x, x - x1]) @ (m @ np.array([y2 - y, y - y1])))
+        return np.asarray(values).dtype.type(r) if np.asarray(values).dtype.kind == "f" else r
+
+    @staticmethod
+    def value_domain(values: np.ndarray, dtype=np.float64) -> tuple:
+        """geotiff.h:400-407: (min, max) of a band cast to `dtype`."""
+        t = np.dtype(dtype).type
+        return (t(np.min(values)), t(np.max(values)))
+
+    @staticmethod
+    def dem_value_domain(values: np.ndarray, dtype=np.float64) -> tuple:
+        """geotiff.h:409-421: as value_domain, ignoring the DEM no-data sentinel (<= -32767): those samples are lifted to
+        the maximum before the minimum is taken."""
+        v = np.asarray(values)
+        hi = np.max(v)
+        sel = (v <= -32767.0).astype(v.dtype)
+        tmp = v + 32767 * sel + hi * sel
+        t = np.dtype(dtype).type
+        return (t(np.min(tmp)), t(hi))
+
+    def write(self, matrix: np.ndarray, destination, band_index: int = 1) -> None:
+        """GeoTIFF::write(cv::Mat, path, bandIndex) (geotiff.h:276-320): a copy of this file with band `band_index`
+        replaced by the row-major `matrix`."""
+        GeoTiffWriter([np.asarray(matrix)], self.path).write(destination, start_index=band_index)
+
 
 # ---------------------------------------------------------------------------------------------------------------------
 # writer

@@ -308,3 +308,29 @@ def test_threaded_segment_decode_matches_serial(tmp_path, monkeypatch):
     monkeypatch.setattr(gt.TiffFile, "decode_threads", 4)
     with pytest.raises(gt.TiffError):
         gt.TiffFile(tmp_path / "bad.tif").read_all()
+
+
+def test_geo_referencing_helpers(tmp_path, expected):
+    """geotiff.h:322-421 on the sample-scene crop (north-up, lat/long degrees)."""
+    g = gt.GeoTIFF(os.path.join(GOLDEN, "scene_crop_B04.tif"), np.float64)
+    x0, dx, _, y0, _, dy = expected["geo_transform"]
+    assert (g.west(), g.north(), g.east_west_step(), g.north_south_step()) == (x0, y0, dx, dy)
+    assert g.east() == x0 + 80 * dx and g.south() == y0 + 96 * dy
+    assert g.north_west() == (y0, x0) and g.south_east() == (g.south(), g.east())
+    assert g.north_east() == (y0, g.east()) and g.south_west() == (g.south(), x0)
+    v = g.read(1)
+    pos = (y0 + 10.5 * dy, x0 + 20.5 * dx)  # the middle of pixel row 10, column 20
+    assert g.index_at(pos) == (20, 10) and g.value_at(pos, v) == v[10, 20]
+    assert g.uv_at(pos) == (20 / 80, 10 / 96)
+    assert np.allclose(g.mid_point_of_pixel((10, 20)), pos, rtol=0, atol=1e-12)
+    assert g.index_at((y0 + 1.0, x0 - 1.0)) == (0, 0) and g.index_at((y0 + 1e3 * dy, x0 + 1e3 * dx)) == (79, 95)  # clamped
+    # bilinear: between four pixel corners = the weighted mean of the four samples
+    q = (y0 + 10.25 * dy, x0 + 20.75 * dx)
+    want = (0.25 * 0.75) * v[10, 20] + (0.75 * 0.75) * v[10, 21] + (0.25 * 0.25) * v[11, 20] + (0.75 * 0.25) * v[11, 21]
+    assert np.isclose(g.bilinear_value_at(q, v), want, rtol=1e-9)
+    assert gt.GeoTIFF.value_domain(v) == (v.min(), v.max())
+    dem = np.array([[-32767.0, 5.0], [12.0, -32767.0]], np.float32)
+    assert gt.GeoTIFF.dem_value_domain(dem) == (5.0, 12.0) and gt.GeoTIFF.value_domain(dem, np.int32) == (-32767, 12)
+    # write(matrix, path, band): a copy with that band replaced
+    g.write(v[::-1] + 1.0, tmp_path / "w.tif", 1)
+    assert np.array_equal(gt.TiffFile(tmp_path / "w.tif").read_band(1), expected["B04"][::-1] + 1)
