@@ -74,13 +74,13 @@ def test_product_never_imports_oracle():
                 assert "import oracle" not in text and "liboracle" not in text and "libref_eigen" not in text, fn
 
 
-def _build_c_example(tmp_path):
+def _build_c_example(tmp_path, name="fill_c_abi"):
     from satellite_approximation_b200 import _capi
 
     libdir = os.path.dirname(_capi.LIB_PATH)
-    exe = str(tmp_path / "fill_c_abi")
+    exe = str(tmp_path / name)
     cmd = ["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
-           os.path.join(ROOT, "examples", "fill_c_abi.c"), "-L", libdir, "-lsatfill", f"-Wl,-rpath,{libdir}", "-lm", "-o", exe]  # fmt: skip
+           os.path.join(ROOT, "examples", name + ".c"), "-L", libdir, "-lsatfill", f"-Wl,-rpath,{libdir}", "-lm", "-o", exe]  # fmt: skip
     r = subprocess.run(cmd, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     return exe
@@ -96,8 +96,9 @@ def test_header_is_plain_c_and_the_example_fails_loudly_without_a_gpu(tmp_path):
     assert r.returncode == 0, r.stderr
     if torch.cuda.is_available():
         pytest.skip("a GPU is present: test_c_example_on_gpu runs it")
-    r = subprocess.run([exe], capture_output=True, text=True)
-    assert r.returncode == 2 and "no CPU fallback" in r.stderr
+    for exe in (exe, _build_c_example(tmp_path, "blend_c_abi")):
+        r = subprocess.run([exe], capture_output=True, text=True)
+        assert r.returncode == 2 and "no CPU fallback" in r.stderr
 
 
 @pytest.mark.gpu
@@ -107,3 +108,13 @@ def test_c_example_on_gpu(tmp_path):
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "max error" in r.stdout
+
+
+@pytest.mark.gpu
+def test_c_blend_example_on_gpu(tmp_path):
+    """examples/blend_c_abi.c: sa_unknown_numbering, sa_poisson_blend (replacement = input + constant returns the input)
+    and sa_label_components (the reference's own test case, tests/approximation.h:55-75) from plain C."""
+    exe = _build_c_example(tmp_path, "blend_c_abi")
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "components: 2 labels, sizes 4 and 8" in r.stdout
