@@ -286,3 +286,48 @@ def test_folder_driver_prefetch_overlaps_and_matches_serial(tmp_path, port, monk
     with sc.DataBase(tmp_path) as db:
         assert len(db.get_approx_status("2019-05-12", sc.ApproxMethod.Laplace)) == 2
     assert not [t for t in threading.enumerate() if t.name.startswith("satfill-")]
+
+
+def test_two_ranks_share_one_database(tmp_path):
+    """Two processes (RANK 0 / 1 of WORLD_SIZE 2, as torchrun would start them) run the folder driver at the same time on
+    one base folder: every folder is filled exactly once, and the ids they draw from the shared approximation.db are
+    distinct (SQLite's file lock serialises the writers)."""
+    import json
+    import subprocess
+    import sys
+
+    truth = {}
+    for k in range(6):
+        name = f"2019-05-{10 + k:02d}"
+        d = tmp_path / name
+        d.mkdir()
+        mask = synth.blob_mask(40, 48, cover=0.25, sigma=3.0, seed=70 + k)
+        for j, b in enumerate(("B04", "B08")):
+            gt.write_tiff(d / f"{b}.tif", [np.round(synth.smooth_band(40, 48, seed=80 + 2 * k + j)).astype(np.uint16)],
+                          extra_tags=GEO)  # fmt: skip
+        gt.write_tiff(d / "cloud_mask.tif", [mask.astype(np.uint8)], extra_tags=GEO)
+        gt.write_tiff(d / "shadow_mask.tif", [np.zeros((40, 48), np.uint8)], extra_tags=GEO)
+        truth[name] = mask
+    with sc.DataBase(tmp_path) as db:
+        for name, mask in truth.items():
+            db.write_detection_result(name, True, True, 0.0, 0.0, float(mask.mean()))
+    worker = os.path.join(os.path.dirname(os.path.abspath(__file__)), "folder_worker.py")
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", LOCAL_RANK=str(r))
+        procs.append(subprocess.Popen([sys.executable, worker, str(tmp_path), str(tmp_path / f"done{r}.json")], env=env,
+                                      stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))  # fmt: skip
+    for p in procs:
+        out, err = p.communicate(timeout=300)
+        assert p.returncode == 0, err[-2000:]
+    done = [json.load(open(tmp_path / f"done{r}.json")) for r in range(2)]
+    assert sorted(done[0]) == sorted(truth)[0::2] and sorted(done[1]) == sorted(truth)[1::2]
+    ids = sorted(i for d in done for f in d.values() for i in f.values())
+    assert ids == list(range(1, 13))
+    with sc.DataBase(tmp_path) as db:
+        for name in truth:
+            assert set(db.get_approx_status(name, sc.ApproxMethod.Laplace)) == {"B04", "B08"}
+    for d in done:
+        for name, bands in d.items():
+            for b, id_ in bands.items():
+                assert os.path.exists(tmp_path / name / "approximated_data" / f"{b}_{id_}.tif")
