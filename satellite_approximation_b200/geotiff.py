@@ -25,6 +25,7 @@ writer, which passes the same pointer back.  Both behaviours are here and the ca
 Pure host code: nothing here touches the GPU, and nothing here is a fallback for it."""
 from __future__ import annotations
 
+import mmap
 import os
 import struct
 import zlib
@@ -215,8 +216,10 @@ class TiffFile:
         self.path = os.fspath(path)
         try:
             with open(self.path, "rb") as f:
-                self._buf = f.read()
-        except OSError as e:
+                # mapped, not read: a 13-band Sentinel-2 tile is gigabytes, and only the segments of the bands asked for
+                # are ever touched
+                self._buf = mmap.mmap(f.fileno(), 0, access=mmap.ACCESS_READ) if os.fstat(f.fileno()).st_size else b""
+        except (OSError, ValueError) as e:
             raise TiffError(f"Failed to open {self.path}: {e}") from e
         b = self._buf
         if len(b) < 8 or b[:2] not in (b"II", b"MM"):
@@ -613,29 +616,40 @@ def write_tiff(path, bands: Sequence[np.ndarray], extra_tags: Optional[dict[int,
     if dt.kind not in "uif" or dt.itemsize not in (1, 2, 4, 8) or (dt.kind == "f" and dt.itemsize < 4):
         raise ValueError(f"unsupported sample type {dt}")
     le = dt.newbyteorder("<")
-    segments: list[bytes] = []
     if tile is not None:
         th, tw = tile
         if th % 16 or tw % 16 or th <= 0 or tw <= 0:
             raise ValueError("tile sides must be positive multiples of 16")
-        for b in bands:
-            for r0 in range(0, h, th):
-                for c0 in range(0, w, tw):
-                    t = np.zeros((th, tw), dtype=le)
-                    blk = b[r0 : r0 + th, c0 : c0 + tw]
-                    t[: blk.shape[0], : blk.shape[1]] = blk
-                    segments.append(t.tobytes())
+        raw_sizes = [th * tw * dt.itemsize] * (len(bands) * (-(-h // th)) * (-(-w // tw)))
     else:
         if rows_per_strip is None:
             rows_per_strip = max(1, min(h, (1 << 20) // max(1, w * dt.itemsize)))
+        raw_sizes = [min(rows_per_strip, h - r0) * w * dt.itemsize for _ in bands for r0 in range(0, h, rows_per_strip)]
+
+    def raw_segments():
+        """The uncompressed segments in file order, produced one at a time (a 13-band tile is never held twice)."""
         for b in bands:
-            for r0 in range(0, h, rows_per_strip):
-                segments.append(b[r0 : r0 + rows_per_strip].astype(le, copy=False).tobytes())
+            if tile is not None:
+                for r0 in range(0, h, th):
+                    for c0 in range(0, w, tw):
+                        t = np.zeros((th, tw), dtype=le)
+                        blk = b[r0 : r0 + th, c0 : c0 + tw]
+                        t[: blk.shape[0], : blk.shape[1]] = blk
+                        yield t.tobytes()
+            else:
+                for r0 in range(0, h, rows_per_strip):
+                    yield b[r0 : r0 + rows_per_strip].astype(le, copy=False).tobytes()
+
     if compress:
-        segments = [zlib.compress(s, 6) for s in segments]
-    payload = sum(len(s) + (len(s) & 1) for s in segments)
+        held = [zlib.compress(seg, 6) for seg in raw_segments()]  # sizes are only known afterwards: hold the compressed form
+        counts = [len(c) for c in held]
+        segments = lambda: iter(held)  # noqa: E731
+    else:
+        counts = raw_sizes
+        segments = raw_segments
+    payload = sum(c + (c & 1) for c in counts)
     if bigtiff is None:
-        bigtiff = payload + (1 << 20) + 16 * len(segments) >= (1 << 32)
+        bigtiff = payload + (1 << 20) + 16 * len(counts) >= (1 << 32)
     nb = len(bands)
     fmt = {"u": 1, "i": 2, "f": 3}[dt.kind]
     off_t = 16 if bigtiff else 4
@@ -651,10 +665,9 @@ def write_tiff(path, bands: Sequence[np.ndarray], extra_tags: Optional[dict[int,
             tags[t] = tv
     header = 16 if bigtiff else 8
     offsets, pos = [], header
-    for s in segments:
+    for c in counts:
         offsets.append(pos)
-        pos += len(s) + (len(s) & 1)
-    counts = [len(s) for s in segments]
+        pos += c + (c & 1)
     if tile is not None:
         tags[T_TILE_W], tags[T_TILE_L] = (4, tile[1]), (4, tile[0])
         tags[T_TILE_OFFSETS], tags[T_TILE_COUNTS] = (off_t, offsets), (off_t, counts)
@@ -687,9 +700,11 @@ def write_tiff(path, bands: Sequence[np.ndarray], extra_tags: Optional[dict[int,
             f.write(struct.pack("<2sHHHQ", b"II", 43, 8, 0, ifd_off))
         else:
             f.write(struct.pack("<2sHI", b"II", 42, ifd_off))
-        for s in segments:
-            f.write(s)
-            if len(s) & 1:
+        for seg, c in zip(segments(), counts):
+            if len(seg) != c:
+                raise RuntimeError("write_tiff: segment size does not match the directory")  # internal invariant
+            f.write(seg)
+            if c & 1:
                 f.write(b"\0")
         f.write(struct.pack("<Q" if bigtiff else "<H", n))
         f.write(entries)
@@ -719,11 +734,17 @@ class GeoTiffWriter:
             start_index = 1  # the single-band form always writes band 1 (geotiff.h:160-163)
         if start_index < 1 or start_index - 1 + len(self.values) > t.samples_per_pixel:
             raise RuntimeError("Unable to write raster image")  # GDAL: null band -> the reference crashes / throws
-        bands = t.read_all()
+        file_dtype = t.dtype.newbyteorder("=")
+        new = {}
         for i, v in enumerate(self.values):
             r = _from_layout(v, self.layout)
             if r.shape != (self.height, self.width):
                 raise RuntimeError("Unable to write raster image")
-            bands[start_index - 1 + i] = np.ascontiguousarray(gdal_convert(r, bands[0].dtype))
+            new[start_index - 1 + i] = np.ascontiguousarray(gdal_convert(r, file_dtype))
+        # the template's pixels are only needed for the bands that are not overwritten
+        kept = [b for b in range(t.samples_per_pixel) if b not in new]
+        old = dict(zip(range(t.samples_per_pixel), t.read_all())) if t.planar == 1 and len(kept) > 1 else {
+            b: t.read_band(b + 1) for b in kept}  # chunky samples: decode every segment once, not once per band
+        bands = [new[b] if b in new else old[b] for b in range(t.samples_per_pixel)]
         keep = {k: v for k, v in t.tags.items() if k in GEO_TAGS or k in (T_XRES, T_YRES, T_RESUNIT)}
         write_tiff(destination, bands, extra_tags=keep)
