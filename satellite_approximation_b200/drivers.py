@@ -132,8 +132,6 @@ def poisson_main(argv: Sequence[str]) -> int:
 
     `--reference-layout` reproduces the reference's buffer handling (geotiff.py: a column-major matrix over the row-major
     raster, i.e. an index-scrambled image for a non-square scene); the default treats the raster as the image it is."""
-    import satellite_approximation_b200 as sab
-
     args = [a for a in argv if a != "--reference-layout"]
     layout = "reference" if len(args) != len(argv) else "raster"
     if len(args) != 2:
@@ -149,16 +147,40 @@ def poisson_main(argv: Sequence[str]) -> int:
     tiff = geotiff.GeoTIFF(input_path, np.float64, layout=layout)
     input_bands = tiff.read(bands)
     cloud = tiff.read(cloud_band)
-    order = "F" if layout == "reference" else "C"
-    cloudmask = sab.preprocess_cloud_band(np.asarray(cloud, order=order))
+    cloudmask = _close_mask(cloud)
+    # one memory order for everything that goes to the C-ABI (the mask is a byte per pixel: cheap to re-lay if it differs)
+    cloudmask = np.asfortranarray(cloudmask) if layout == "reference" else np.ascontiguousarray(cloudmask)
     _log.info("Finished close + dilate")
     replacement_bands = geotiff.GeoTIFF(replacement_path, np.float64, layout=layout).read(bands)
     _log.info("Starting solver...")
-    res = sab.blend_images_poisson(input_bands, replacement_bands, cloudmask)
+    # blend_images_poisson's vector overload (poisson.cpp:292-303) returns the inputs unchanged when the sizes differ or a
+    # band does not converge; the same happens here, in place (the library writes nothing unless every band converged)
+    if any(a.shape != input_bands[0].shape for a in input_bands + replacement_bands):
+        _log.error("Input and replacement images must have the same dimensions")  # poisson.cpp:154-157
+    elif not _blend_in_place(input_bands, replacement_bands, cloudmask):
+        _log.error("Failed to solve the linear system (no convergence)")  # poisson.cpp:263-269
     _log.info("Finished solving. Writing results")
     dest = os.path.join(os.path.dirname(os.path.abspath(input_path)), "poisson_simple_replace", os.path.basename(input_path))
-    geotiff.GeoTiffWriter(res, input_path, layout=layout).write(dest)
+    geotiff.GeoTiffWriter(input_bands, input_path, layout=layout).write(dest)
     return 0
+
+
+def _close_mask(cloud: np.ndarray) -> np.ndarray:
+    """preprocess_cloud_band (poisson-main.cpp:10-21) on the GPU; the mask comes back in the band's memory order."""
+    import satellite_approximation_b200 as sab
+
+    return sab.preprocess_cloud_band(cloud)
+
+
+def _blend_in_place(bands: list, replacements: list, mask: np.ndarray) -> bool:
+    """approx::blend_images_poisson at its defaults (tolerance 1e-6, n / 2 iterations) on the GPU, in place on `bands`: the
+    decoded bands are handed to the C-ABI as they lie (either memory order), without the Fortran-ordered copies the
+    reference-shaped Python function makes.  False when a band did not converge (nothing was written then)."""
+    import satellite_approximation_b200 as sab
+
+    stats = sab.default_context().poisson_blend(bands, replacements, mask, tolerance=1e-6, max_iterations=None,
+                                                precond=sab._defaults["precond"], check_every=sab._defaults["check_every"])  # fmt: skip
+    return all(s["status"] != sab.SA_NOT_CONVERGED for s in stats)
 
 
 def fill_folder_main(argv: Sequence[str]) -> int:

@@ -79,16 +79,19 @@ def test_poisson_main_plumbing_with_oracle_pixels(tmp_path, monkeypatch, port, l
     a, b, bands_in, bands_rp, cloud = make_pair(tmp_path, rows, cols)
     seen = {}
 
-    def close(band, dilation_size=5):
+    def close(band):
         seen["band"] = band
-        return oracle.morph_close_mask(np.asarray(band), dilation_size)
+        return oracle.morph_close_mask(np.asarray(band), 5)
 
-    def blend(ins, reps, mask, tolerance=1e-6, max_iterations=None):
+    def blend(ins, reps, mask):
         seen["shapes"] = [x.shape for x in ins]
-        return port.poisson_blend(ins, reps, mask, tol=tolerance)[0]
+        seen["orders"] = {x.flags.f_contiguous and not x.flags.c_contiguous for x in ins + reps + [mask]}
+        for a, o in zip(ins, port.poisson_blend(ins, reps, mask, tol=1e-6)[0]):
+            a[...] = o
+        return True
 
-    monkeypatch.setattr(sab, "preprocess_cloud_band", close)
-    monkeypatch.setattr(sab, "blend_images_poisson", blend)
+    monkeypatch.setattr(drivers, "_close_mask", close)
+    monkeypatch.setattr(drivers, "_blend_in_place", blend)
     rc = drivers.poisson_main([str(a), str(b)] + (["--reference-layout"] if layout == "reference" else []))
     assert rc == 0
     out = tmp_path / "in" / "poisson_simple_replace" / "scene.tif"  # poisson-main.cpp:69
@@ -102,6 +105,7 @@ def test_poisson_main_plumbing_with_oracle_pixels(tmp_path, monkeypatch, port, l
     back = (lambda m: m) if layout == "raster" else (lambda m: m.reshape(-1, order="F").reshape(rows, cols))
     mask = oracle.morph_close_mask(to(cloud), 5)
     assert np.array_equal(np.asarray(seen["band"]), to(cloud)) and seen["shapes"] == [(rows, cols)] * 5
+    assert seen["orders"] == {layout == "reference"}  # every array reaches the C-ABI in one memory order, uncopied
     want = port.poisson_blend([to(x) for x in bands_in], [to(x) for x in bands_rp], mask, tol=1e-6)[0]
     for k in range(5):
         assert np.array_equal(got[k], gt.gdal_convert(back(want[k]), np.uint16)), k
@@ -127,3 +131,16 @@ def test_fill_folder_cli_arguments(tmp_path, monkeypatch):
     assert seen["poisson"] == ((str(tmp_path), ["B04"], True, 0.5, 0.25), {"shard": (1, 4)})
     assert os.environ.pop("SATFILL_DEVICE") == "1"  # one process per GPU: the default context follows LOCAL_RANK
     assert drivers.main(["fill_folder", str(tmp_path)]) == -1  # --bands is required
+
+
+def test_poisson_main_failed_solve_writes_the_inputs(tmp_path, monkeypatch):
+    """poisson.cpp:263-269 + 292-303: a band that does not converge leaves the images alone, and poisson_main still writes
+    its output file -- a copy of the input."""
+    import oracle
+
+    a, b, bands_in, _, cloud = make_pair(tmp_path, 40, 32)
+    monkeypatch.setattr(drivers, "_close_mask", lambda band: oracle.morph_close_mask(np.asarray(band), 5))
+    monkeypatch.setattr(drivers, "_blend_in_place", lambda *args: False)
+    assert drivers.poisson_main([str(a), str(b)]) == 0
+    got = gt.TiffFile(tmp_path / "in" / "poisson_simple_replace" / "scene.tif").read_all()
+    assert all(np.array_equal(g, w) for g, w in zip(got, bands_in + [cloud]))
