@@ -720,7 +720,21 @@ def write_tiff(path, bands: Sequence[np.ndarray], extra_tags: Optional[dict[int,
         entries += struct.pack("<HHQ" if bigtiff else "<HHI", t, typ, cnt) + field
     if not bigtiff and ifd_off + ifd_size + len(extra) >= (1 << 32):
         raise ValueError("file too large for classic TIFF; pass bigtiff=True")
-    os.makedirs(os.path.dirname(os.path.abspath(os.fspath(path))), exist_ok=True)
+    path = os.path.abspath(os.fspath(path))
+    os.makedirs(os.path.dirname(path), exist_ok=True)
+    # written next to the destination and renamed into place: a reader that has the old file mapped (the writer's own
+    # template, when source and destination are one path) keeps a valid mapping, and no half-written file is ever visible
+    tmp = f"{path}.part{os.getpid()}"
+    try:
+        _write_file(tmp, bigtiff, ifd_off, segments, counts, n, entries, extra)
+        os.replace(tmp, path)
+    except BaseException:
+        if os.path.exists(tmp):
+            os.remove(tmp)
+        raise
+
+
+def _write_file(path, bigtiff, ifd_off, segments, counts, n, entries, extra) -> None:
     with open(path, "wb") as f:
         if bigtiff:
             f.write(struct.pack("<2sHHHQ", b"II", 43, 8, 0, ifd_off))

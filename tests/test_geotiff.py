@@ -334,3 +334,51 @@ def test_geo_referencing_helpers(tmp_path, expected):
     # write(matrix, path, band): a copy with that band replaced
     g.write(v[::-1] + 1.0, tmp_path / "w.tif", 1)
     assert np.array_equal(gt.TiffFile(tmp_path / "w.tif").read_band(1), expected["B04"][::-1] + 1)
+
+
+def test_round_trip_property(tmp_path):
+    """Any shape / type / segmenting / band count survives write -> read (hypothesis; ragged last strips and tiles)."""
+    hyp = pytest.importorskip("hypothesis")
+    st = pytest.importorskip("hypothesis.strategies")
+    dtypes = [np.uint8, np.int8, np.uint16, np.int16, np.uint32, np.int32, np.float32, np.float64]
+
+    @hyp.settings(max_examples=60, deadline=None, suppress_health_check=list(hyp.HealthCheck))
+    @hyp.given(h=st.integers(1, 70), w=st.integers(1, 70), nb=st.integers(1, 4), dt=st.sampled_from(dtypes),
+               seg=st.one_of(st.none(), st.integers(1, 80), st.tuples(st.sampled_from([16, 32, 48]), st.sampled_from([16, 32]))),
+               compress=st.booleans(), big=st.booleans(), seed=st.integers(0, 2**31 - 1))  # fmt: skip
+    def run(h, w, nb, dt, seg, compress, big, seed):
+        rng = np.random.default_rng(seed)
+        bands = [(rng.random((h, w)) * 250 - (100 if np.dtype(dt).kind != "u" else 0)).astype(dt) for _ in range(nb)]
+        kw = {"tile": seg} if isinstance(seg, tuple) else {"rows_per_strip": seg}
+        p = tmp_path / "h.tif"
+        gt.write_tiff(p, bands, compress=compress, bigtiff=big, **kw)
+        t = gt.TiffFile(p)
+        assert (t.height, t.width, t.samples_per_pixel, t.bigtiff) == (h, w, nb, big)
+        for k, b in enumerate(bands):
+            assert np.array_equal(t.read_band(k + 1), b)
+        assert all(np.array_equal(x, y) for x, y in zip(t.read_all(), bands))
+        # both layouts of the GeoTIFF mirror invert through the writer
+        geo = {gt.T_PIXEL_SCALE: (12, [1.0, 1.0, 0.0]), gt.T_TIEPOINT: (12, [0.0] * 6)}
+        gt.write_tiff(p, bands, extra_tags=geo, compress=compress, **kw)
+        for layout in ("raster", "reference"):
+            g = gt.GeoTIFF(p, np.float64, layout=layout)
+            vals = g.read()
+            gt.GeoTiffWriter(vals, p, layout=layout).write(tmp_path / "h2.tif")
+            assert all(np.array_equal(x, y) for x, y in zip(gt.TiffFile(tmp_path / "h2.tif").read_all(), bands))
+
+    run()
+
+
+def test_writer_may_overwrite_its_own_template(tmp_path, expected):
+    """Destination == template: the template stays mapped while the new file is written beside it and renamed into place."""
+    geo = {k: v for k, v in gt.TiffFile(os.path.join(GOLDEN, "scene_crop_B04.tif")).tags.items() if k in gt.GEO_TAGS}
+    b = expected["B04"]
+    p = tmp_path / "scene.tif"
+    gt.write_tiff(p, [b, b // 2], extra_tags=geo, compress=True)
+    gt.GeoTiffWriter([b.astype(np.float64) + 3], p).write(p, start_index=1)
+    got = gt.TiffFile(p).read_all()
+    assert np.array_equal(got[0], b + 3) and np.array_equal(got[1], b // 2)
+    assert sorted(os.listdir(tmp_path)) == ["scene.tif"]  # no temporary left behind
+    with pytest.raises(ValueError):
+        gt.write_tiff(p, [b, b[:5]])
+    assert sorted(os.listdir(tmp_path)) == ["scene.tif"]
