@@ -307,6 +307,18 @@ class TiffFile:
         if len(self._offsets) < need or len(self._counts) < need:
             raise TiffError(f"{self.path}: {len(self._offsets)} segments listed, {need} needed")
 
+    def close(self) -> None:
+        """Drop the file mapping (it also goes with the object)."""
+        buf, self._buf = self._buf, b""
+        if isinstance(buf, mmap.mmap):
+            buf.close()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
     # -- tags ----------------------------------------------------------------------------------------------------------
     def _read_ifd(self, off: int) -> None:
         b, bo = self._buf, self.byteorder

@@ -382,3 +382,10 @@ def test_writer_may_overwrite_its_own_template(tmp_path, expected):
     with pytest.raises(ValueError):
         gt.write_tiff(p, [b, b[:5]])
     assert sorted(os.listdir(tmp_path)) == ["scene.tif"]
+
+
+def test_tiff_file_is_a_context_manager(expected):
+    with gt.TiffFile(os.path.join(GOLDEN, "scene_crop_CLD.tif")) as t:
+        assert np.array_equal(t.read_band(1), expected["CLD"])
+    with pytest.raises(gt.TiffError):
+        t.read_band(1)  # closed: the segments are gone
