@@ -61,6 +61,19 @@ def stats(mask: np.ndarray, th: int, tw: int) -> dict:
     }  # fmt: skip
 
 
+def granule_amplification(mask: np.ndarray, elem: int, granule: int) -> float:
+    """Bytes of the `granule`-byte DRAM units that hold at least one unknown / bytes of the unknowns, for a row-major plane
+    of `elem`-byte cells (rows padded to a multiple of the granule): what a run-following access pattern moves when DRAM
+    is filled `granule` bytes at a time."""
+    per = granule // elem
+    rows, cols = mask.shape
+    C = -(-cols // per) * per
+    m = np.zeros((rows, C), bool)
+    m[:, :cols] = mask
+    touched = m.reshape(rows, C // per, per).any(-1).sum()
+    return float(touched) * granule / (float(mask.sum()) * elem)
+
+
 def main() -> None:
     import torch
 
@@ -70,6 +83,10 @@ def main() -> None:
     cols = int(sys.argv[2]) if len(sys.argv) > 2 else rows
     mask = synth.torch_blob_mask(rows, cols, device="cpu").numpy().astype(bool)
     print(f"# synth.torch_blob_mask({rows}, {cols}): {mask.mean() * 100:.2f} % unknown ({int(mask.sum())} pixels)")
+    print("# DRAM bytes moved per byte of unknowns in a row-major plane, by fill granularity:")
+    for elem, name in ((8, "double"), (4, "float")):
+        print(f"#   {name:6s}  32 B sectors: {granule_amplification(mask, elem, 32):.3f}   64 B (sector pairs): "
+              f"{granule_amplification(mask, elem, 64):.3f}   128 B lines: {granule_amplification(mask, elem, 128):.3f}")
     print("# tile   active  fill   full-tiles  halo   runs/row  mean-run  sectors-touched  unknowns/sector-cell  "
           "frame-reads/unknown H=1  H=4")
     for th, tw in ((32, 32), (32, 64), (64, 32), (64, 64), (16, 64), (16, 128), (8, 128)):
