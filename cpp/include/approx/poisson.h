@@ -54,6 +54,11 @@ struct DayInfo {
 std::string find_good_close_image(std::string const& date_string, f64 distance_weight, std::vector<DayInfo> close_images,
     f64 percent_invalid_of_date);
 
+// preprocess_cloud_band of poisson_main (executables/poisson-main.cpp:10-21): (2 dilation_size + 1)^2 rectangular
+// morphological close of the cloud band, cast to bool -- on the GPU (sa_morph_close_mask), bit-exact against
+// cv::morphologyEx.  Lives in the executable upstream; here so that a poisson_main can be linked without OpenCV.
+MatX<bool> preprocess_cloud_band(MatX<f64> const& cloud_band, int dilation_size = 5);
+
 // The record of the last blend (the reference appends it to a hard-coded path, poisson.cpp:287-289).
 PerfInfo const& last_perf_info();
 

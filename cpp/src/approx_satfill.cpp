@@ -169,6 +169,21 @@ std::vector<MatX<f64>> blend_images_poisson(std::vector<MatX<f64>> const& input_
     return input.images;
 }
 
+MatX<bool> preprocess_cloud_band(MatX<f64> const& cloud_band, int dilation_size)
+{
+    MatX<bool> mask = MatX<bool>::Zero(cloud_band.rows(), cloud_band.cols());
+    if (cloud_band.size() == 0)
+        return mask;
+    Ctx& c = ctx();
+    std::lock_guard<std::mutex> guard(c.lock);
+    // column-major Eigen storage: row stride 1, column stride rows; the mask comes back in the same layout
+    int rc = sa_morph_close_mask(c.h, cloud_band.data(), cloud_band.rows(), cloud_band.cols(), 1, cloud_band.rows(),
+        dilation_size, reinterpret_cast<uint8_t*>(mask.data()));
+    if (rc != SA_OK)
+        throw std::runtime_error(std::string("preprocess_cloud_band: ") + sa_last_error(c.h));
+    return mask;
+}
+
 void highlight_area_replaced(MultiChannelImage& input_images, MultiChannelImage const& replacement_images, int start_row,
     int start_col, Vec3<f64> const& color)
 {

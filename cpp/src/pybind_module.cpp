@@ -10,6 +10,7 @@
 #include <approx/laplace.h>
 #include <approx/poisson.h>
 #include <utils/filesystem.h>
+#include <utils/geotiff.h>
 
 #include <array>
 
@@ -79,6 +80,35 @@ PYBIND11_MODULE(_core, m)
             return approx::find_good_close_image(date_string, weight, std::move(info), percent_invalid_of_date);
         },
         "date_string"_a, "distance_weight"_a, "close_images"_a, "percent_invalid_of_date"_a);
+    // utils/geotiff.h (the C++ twin of satellite_approximation_b200/geotiff.py), exposed for tests/test_geotiff.py
+    m.def(
+        "geotiff_read",
+        [](std::string const& path, int band, bool reference_layout) {
+            return utils::GeoTIFF<f64>(path, reference_layout ? utils::Layout::Reference : utils::Layout::Raster).read(band);
+        },
+        "path"_a, "band"_a, "reference_layout"_a = false);
+    m.def("geotiff_read_u8", [](std::string const& path, int band) { return utils::GeoTIFF<utils::u8>(path).read(band); });
+    m.def("geotiff_read_i16", [](std::string const& path, int band) { return utils::GeoTIFF<utils::i16>(path).read(band); });
+    m.def("geotiff_info", [](std::string const& path) {
+        utils::GeoTIFF<f64> t(path);
+        return py::make_tuple(t.height, t.width, t.raster_count(),
+            std::vector<double>(t.geoTransform, t.geoTransform + 6));
+    });
+    m.def(
+        "geotiff_write",
+        [](std::vector<MatX<f64>> values, std::string const& template_path, std::string const& destination, int start_index,
+            bool reference_layout, bool single) {
+            auto layout = reference_layout ? utils::Layout::Reference : utils::Layout::Raster;
+            if (single) {
+                utils::GeoTiffWriter<f64>(std::make_shared<MatX<f64>>(values.at(0)), template_path, layout)
+                    .write(destination, start_index);
+            } else {
+                utils::GeoTiffWriter<f64>(std::make_shared<std::vector<MatX<f64>>>(std::move(values)), template_path, layout)
+                    .write(destination, start_index);
+            }
+        },
+        "values"_a, "template_path"_a, "destination"_a, "start_index"_a = 1, "reference_layout"_a = false, "single"_a = false);
+    py::register_exception<utils::IOError>(m, "IOError", PyExc_OSError);
     m.def("find_directory_contents", [](std::string const& path) { return (int)utils::find_directory_contents(path); });
     m.def("date_days", [](std::string const& d) { return utils::Date(d).days(); });
     py::register_exception<utils::GenericError>(m, "GenericError", PyExc_RuntimeError);

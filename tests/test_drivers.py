@@ -144,3 +144,31 @@ def test_poisson_main_failed_solve_writes_the_inputs(tmp_path, monkeypatch):
     assert drivers.poisson_main([str(a), str(b)]) == 0
     got = gt.TiffFile(tmp_path / "in" / "poisson_simple_replace" / "scene.tif").read_all()
     assert all(np.array_equal(g, w) for g, w in zip(got, bands_in + [cloud]))
+
+
+def test_cpp_poisson_main_binary_without_a_gpu(tmp_path):
+    """cpp/src/poisson_main.cpp (the reference's executable on utils/geotiff.h + the `approx` shim): argument and file
+    checks, GeoTIFF decoding up to the first device call, and the loud failure -- exit code 2, no CPU fallback -- on a
+    machine without a GPU."""
+    import subprocess
+
+    import torch
+
+    from satellite_approximation_b200 import _capi
+
+    exe = os.path.join(os.path.dirname(_capi.LIB_PATH), "poisson_main")
+    if not os.path.exists(exe):
+        pytest.skip("poisson_main is not built (make -C cpp needs Eigen headers)")
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 255 and "Usage" in r.stderr  # return -1 (poisson-main.cpp:28-31)
+    r = subprocess.run([exe, str(tmp_path / "a.tif"), str(tmp_path / "b.tif")], capture_output=True, text=True)
+    assert r.returncode == 255 and "does not exist" in r.stderr
+    a, b, *_ = make_pair(tmp_path, 40, 32)
+    (tmp_path / "junk.tif").write_bytes(b"not a tiff")
+    r = subprocess.run([exe, str(tmp_path / "junk.tif"), str(b)], capture_output=True, text=True)
+    assert r.returncode == 1 and "not a TIFF" in r.stderr
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present: the device path of the binary is not part of the CPU suite")
+    r = subprocess.run([exe, str(a), str(b)], capture_output=True, text=True)
+    assert r.returncode == 2 and "no CPU fallback" in r.stderr, r.stderr
+    assert not os.path.exists(tmp_path / "in" / "poisson_simple_replace")

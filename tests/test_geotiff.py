@@ -113,7 +113,7 @@ def test_pillow_written_files(tmp_path):
         assert np.array_equal(np.array(Image.open(p)), a), kw
 
 
-def _encode(path, a, compression=1, predictor=1, byteorder="<", tile=None):
+def _encode(path, a, compression=1, predictor=1, byteorder="<", tile=None, geo=False):
     """A deliberately separate minimal encoder for the flavours no library here writes on demand (predictors 2 / 3,
     big-endian, tiles): chunky samples, one strip or fixed tiles."""
     bo = byteorder
@@ -172,6 +172,12 @@ def _encode(path, a, compression=1, predictor=1, byteorder="<", tile=None):
                 (325, 4, n, one(o_cnts, [len(s) for s in segs]))]  # fmt: skip
     else:
         ent += [(273, 4, n, one(o_offs, offs)), (278, 4, 1, lg(h)), (279, 4, n, one(o_cnts, [len(s) for s in segs]))]
+    if geo:  # ModelPixelScale + ModelTiepoint (type 12 = DOUBLE), values behind the segment tables
+        o_scale = len(blob)
+        blob += struct.pack(bo + "3d", 10.0, 10.0, 0.0)
+        o_tie = len(blob)
+        blob += struct.pack(bo + "6d", 0.0, 0.0, 0.0, 5e5, 6e6, 0.0)
+        ent += [(33550, 12, 3, lg(o_scale)), (33922, 12, 6, lg(o_tie))]
     ent.sort()
     ifd = len(blob)
     blob += struct.pack(bo + "H", len(ent))
@@ -389,3 +395,98 @@ def test_tiff_file_is_a_context_manager(expected):
         assert np.array_equal(t.read_band(1), expected["CLD"])
     with pytest.raises(gt.TiffError):
         t.read_band(1)  # closed: the segments are gone
+
+
+# ---- the C++ twin (cpp/include/utils/geotiff.h), through satellite_approximation._core ---------------------------------
+def _core_or_skip():
+    try:
+        from satellite_approximation import _core
+    except ImportError:
+        pytest.skip("satellite_approximation._core is not built (make -C cpp pybind needs Eigen headers)")
+    if not hasattr(_core, "geotiff_read"):
+        pytest.skip("stale _core without the GeoTIFF bindings")
+    return _core
+
+
+def test_cpp_geotiff_reads_what_the_python_reader_reads(tmp_path, expected):
+    core = _core_or_skip()
+    for name in ("B04", "CLD", "sunZenithAngles"):  # the sample scene's flavour: big-endian, deflate 32946, 8-row strips
+        p = os.path.join(GOLDEN, f"scene_crop_{name}.tif")
+        got = core.geotiff_read(p, 1)
+        assert got.dtype == np.float64 and got.flags.f_contiguous and np.array_equal(got, expected[name].astype(np.float64))
+        ref = core.geotiff_read(p, 1, True)  # the reference's matrix: column-major over the row-major raster
+        assert np.array_equal(ref, gt.GeoTIFF(p, np.float64, layout="reference").read(1))
+    h, w, n, g = core.geotiff_info(os.path.join(GOLDEN, "scene_crop_B04.tif"))
+    assert (h, w, n) == (96, 80, 1) and np.array_equal(g, expected["geo_transform"])
+    assert np.array_equal(core.geotiff_read_u8(os.path.join(GOLDEN, "scene_crop_B04.tif"), 1),
+                          np.minimum(expected["B04"], 255).astype(np.uint8))  # GDAL clamps on a narrowing read
+    # every flavour the Python writer and the test encoder produce
+    rng = np.random.default_rng(21)
+    a = (rng.random((45, 70)) * 60000).astype(np.uint16)
+    b = (rng.random((45, 70)) * 60000).astype(np.uint16)
+    geo = {gt.T_PIXEL_SCALE: (12, [10.0, 10.0, 0.0]), gt.T_TIEPOINT: (12, [0.0, 0.0, 0.0, 5e5, 6e6, 0.0])}
+    p = tmp_path / "x.tif"
+    for kw in ({}, {"tile": (16, 32)}, {"compress": True}, {"bigtiff": True, "tile": (32, 16), "compress": True},
+               {"rows_per_strip": 7}):  # fmt: skip
+        gt.write_tiff(p, [a, b], extra_tags=geo, **kw)
+        assert np.array_equal(core.geotiff_read(str(p), 1), a) and np.array_equal(core.geotiff_read(str(p), 2), b), kw
+    rgb = (rng.random((40, 50, 3)) * 65535).astype(np.uint16)
+    for bo in "<>":
+        for tile in (None, (16, 32)):
+            for comp in (1, 8):
+                _encode(p, rgb, compression=comp, predictor=2, byteorder=bo, tile=tile, geo=True)  # chunky + predictor
+                assert gt.TiffFile(p).geo_transform == (5e5, 10.0, 0.0, 6e6, 0.0, -10.0)
+                for k in range(3):
+                    assert np.array_equal(core.geotiff_read(str(p), k + 1), rgb[:, :, k]), (bo, tile, comp, k)
+            _encode(p, rgb, compression=8, predictor=2, byteorder=bo, tile=tile)
+            with pytest.raises(OSError):
+                core.geotiff_read(str(p), 2)  # no geo tags: IOError, like the reference's constructor (geotiff.h:220-222)
+    f = rng.standard_normal((33, 29))
+    gt.write_tiff(p, [f, -f], extra_tags=geo, compress=True)
+    assert np.array_equal(core.geotiff_read(str(p), 2), -f)
+    assert np.array_equal(core.geotiff_read_i16(str(p), 1), gt.gdal_convert(f, np.int16))
+    with pytest.raises(RuntimeError):
+        core.geotiff_read(str(p), 3)
+    with pytest.raises(OSError):
+        core.geotiff_read(str(tmp_path / "missing.tif"), 1)
+    (tmp_path / "junk.tif").write_bytes(b"II*\0\xff\xff\xff\x7f")
+    with pytest.raises(OSError):
+        core.geotiff_read(str(tmp_path / "junk.tif"), 1)
+    Image = pytest.importorskip("PIL.Image")
+    info = {33550: (10.0, 10.0, 0.0), 33922: (0.0, 0.0, 0.0, 5e5, 6e6, 0.0)}
+    smooth = (np.add.outer(np.arange(300), np.arange(400)) // 7).astype(np.uint16)  # long LZW matches, table resets
+    for img in (a, smooth):
+        for comp in ("tiff_lzw", "packbits", "tiff_adobe_deflate", "raw"):  # libtiff-written: csrc/tiffcodec.c and zlib
+            Image.fromarray(img).save(p, compression=comp, tiffinfo=info)
+            assert np.array_equal(core.geotiff_read(str(p), 1), img), comp
+
+
+def test_cpp_geotiff_writer_matches_the_python_writer(tmp_path, expected):
+    core = _core_or_skip()
+    src = gt.TiffFile(os.path.join(GOLDEN, "scene_crop_B04.tif"))
+    geo = {k: v for k, v in src.tags.items() if k in gt.GEO_TAGS}
+    b = expected["B04"]
+    tpl = tmp_path / "tpl.tif"
+    gt.write_tiff(tpl, [b, (b // 2).astype(np.uint16), (b // 3).astype(np.uint16)], extra_tags=geo, compress=True)
+    vals = [b.astype(np.float64) + 0.5, b.astype(np.float64) * 100.0 - 7e4]  # rounds half up; saturates both ways
+    for ref_layout in (False, True):
+        layout = "reference" if ref_layout else "raster"
+        py_out, cc_out = tmp_path / f"py_{layout}.tif", tmp_path / "sub" / f"cc_{layout}.tif"
+        send = [gt._to_layout(np.ascontiguousarray(v), layout) for v in vals]
+        gt.GeoTiffWriter(send, tpl, layout=layout).write(py_out, start_index=2)
+        core.geotiff_write([np.asfortranarray(v) for v in send], str(tpl), str(cc_out), 2, ref_layout)
+        a, c = gt.GeoTIFF(py_out, np.float64), gt.GeoTIFF(cc_out, np.float64)
+        assert c.raster_count == 3 and c.file.dtype == np.uint16 and c.geo_transform == a.geo_transform == src.geo_transform
+        assert c.file.tags[gt.T_GEOASCII][1] == "WGS 84|"
+        for x, y in zip(a.read(), c.read()):
+            assert np.array_equal(x, y)
+        assert np.array_equal(c.read(1), b)  # band 1 is the template's
+    # single-band form lands in band 1 whatever start_index says (geotiff.h:160-163)
+    core.geotiff_write([np.asfortranarray(vals[0])], str(tpl), str(tmp_path / "one.tif"), 3, False, True)
+    got = gt.TiffFile(tmp_path / "one.tif").read_all()
+    assert np.array_equal(got[0], gt.gdal_convert(vals[0], np.uint16)) and np.array_equal(got[2], b // 3)
+    with pytest.raises(RuntimeError):
+        core.geotiff_write([np.asfortranarray(v) for v in vals], str(tpl), str(tmp_path / "bad.tif"), 3)  # band 4 of 3
+    with pytest.raises(RuntimeError):
+        core.geotiff_write([np.asfortranarray(vals[0][:10])], str(tpl), str(tmp_path / "bad.tif"), 1)
+    assert not os.path.exists(tmp_path / "bad.tif")
