@@ -172,3 +172,49 @@ def test_cpp_poisson_main_binary_without_a_gpu(tmp_path):
     r = subprocess.run([exe, str(a), str(b)], capture_output=True, text=True)
     assert r.returncode == 2 and "no CPU fallback" in r.stderr, r.stderr
     assert not os.path.exists(tmp_path / "in" / "poisson_simple_replace")
+
+
+@pytest.mark.parametrize("layout", ["raster", "reference"])
+def test_cpp_poisson_main_binary_host_logic_with_oracle_pixels(tmp_path, port, layout):
+    """The whole C++ poisson_main (cpp/src/poisson_main.cpp: utils/geotiff.h decode, approx::preprocess_cloud_band,
+    approx::blend_images_poisson, GeoTiffWriter) run end to end on the CPU, with tests/fake_satfill.c -- the eight C-ABI
+    entry points the shim imports, answered by the ORACLE -- put in front of the real library through LD_LIBRARY_PATH.
+    Checks what surrounds the device calls: layouts, strides, band order, the output file; the expected file is the one
+    the Python driver's plumbing test demands."""
+    import subprocess
+
+    import oracle
+    from satellite_approximation_b200 import _capi
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    libdir = os.path.dirname(_capi.LIB_PATH)
+    exe = os.path.join(libdir, "poisson_main")
+    if not os.path.exists(exe):
+        pytest.skip("poisson_main is not built (make -C cpp needs Eigen headers)")
+    oracle.port()  # makes sure oracle/_build/liboracle.so exists
+    odir = os.path.join(root, "oracle", "_build")
+    fake = tmp_path / "fake"
+    fake.mkdir()
+    cmd = ["gcc", "-O2", "-std=c99", "-Wall", "-Wextra", "-fPIC", "-shared", "-I", os.path.join(root, "include"),
+           os.path.join(root, "tests", "fake_satfill.c"), "-o", str(fake / "libsatfill.so"), "-L", odir, "-loracle",
+           f"-Wl,-rpath,{odir}"]  # fmt: skip
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    rows, cols = 48, 36
+    a, b, bands_in, bands_rp, cloud = make_pair(tmp_path, rows, cols)
+    env = dict(os.environ, LD_LIBRARY_PATH=str(fake) + os.pathsep + os.environ.get("LD_LIBRARY_PATH", ""))
+    args = [exe, str(a), str(b)] + (["--reference-layout"] if layout == "reference" else [])
+    r = subprocess.run(args, capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stderr
+    got = gt.GeoTIFF(tmp_path / "in" / "poisson_simple_replace" / "scene.tif", np.float64)
+    assert got.raster_count == 6 and got.file.dtype == np.uint16 and got.geo_transform == (5e5, 10.0, 0.0, 6e6, 0.0, -10.0)
+    got = got.read()
+    assert np.array_equal(got[5], cloud)
+    to = (lambda x: x.astype(np.float64)) if layout == "raster" else (
+        lambda x: x.astype(np.float64).ravel().reshape((rows, cols), order="F"))  # fmt: skip
+    back = (lambda m: m) if layout == "raster" else (lambda m: m.reshape(-1, order="F").reshape(rows, cols))
+    mask = oracle.morph_close_mask(to(cloud), 5)
+    want = port.poisson_blend([to(x) for x in bands_in], [to(x) for x in bands_rp], mask, tol=1e-6)[0]
+    for k in range(5):
+        assert np.array_equal(got[k], gt.gdal_convert(back(want[k]), np.uint16)), k
+        assert np.array_equal(got[k][~back(mask)], bands_in[k][~back(mask)])
