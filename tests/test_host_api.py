@@ -162,3 +162,30 @@ def test_cpp_shim_host_pieces_match_the_python_mirror(tmp_path):
     (tmp_path / "2019-05-23").mkdir()
     for name in ("2019-05-22", "2019-05-23", "logs"):
         assert core.find_directory_contents(str(tmp_path / name)) == sc.find_directory_contents(tmp_path / name).value
+
+
+def test_cpp_shim_behaviour_on_the_cpu(tmp_path):
+    """The C++ `approx` shim behind satellite_approximation._core, exercised on the CPU: a libsatfill.so built from
+    tests/fake_satfill.c (the eight C-ABI entry points the shim imports, answered by the ORACLE) is put in front of the
+    real library through LD_LIBRARY_PATH in a child process.  What is checked is the shim's own host logic -- Eigen
+    casters and layouts, copies, defaults, the reference's error behaviours -- not the device code (tests -m gpu)."""
+    import os
+    import subprocess
+    import sys
+
+    import oracle
+
+    _core_or_skip()
+    oracle.port()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    odir = os.path.join(root, "oracle", "_build")
+    fake = tmp_path / "fake"
+    fake.mkdir()
+    r = subprocess.run(["gcc", "-O2", "-std=c99", "-Wall", "-Wextra", "-fPIC", "-shared", "-I", os.path.join(root, "include"),
+                        os.path.join(root, "tests", "fake_satfill.c"), "-o", str(fake / "libsatfill.so"), "-L", odir,
+                        "-loracle", f"-Wl,-rpath,{odir}"], capture_output=True, text=True)  # fmt: skip
+    assert r.returncode == 0, r.stderr
+    env = dict(os.environ, LD_LIBRARY_PATH=str(fake) + os.pathsep + os.environ.get("LD_LIBRARY_PATH", ""))
+    r = subprocess.run([sys.executable, os.path.join(root, "tests", "core_fake_worker.py")], env=env, capture_output=True,
+                       text=True, timeout=600)  # fmt: skip
+    assert r.returncode == 0 and "core-on-fake ok" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
