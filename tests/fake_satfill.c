@@ -1,7 +1,7 @@
 /* TEST INFRASTRUCTURE -- a stand-in `libsatfill.so` for CPU-only tests of host programs that link the C-ABI
- * (tests/test_drivers.py runs cpp/src/poisson_main.cpp against it through LD_LIBRARY_PATH).  It implements the eight entry
- * points the C++ `approx` shim imports by calling the ORACLE (oracle/_build/liboracle.so: the plain-C restatement of the
- * reference), so that everything around the device calls -- GeoTIFF decode, memory layouts, band order, status handling,
+ * (tests/test_drivers.py runs cpp/src/poisson_main.cpp against it through LD_LIBRARY_PATH).  It implements the entry points
+ * the C++ `approx` shim and the plain-C examples call, by calling the ORACLE (oracle/_build/liboracle.so: the plain-C
+ * restatement of the reference), so that everything around the device calls -- GeoTIFF decode, memory layouts, band order, status handling,
  * the output file -- can be checked end to end on a machine without a GPU.  It is never built into, shipped with or
  * loaded by the product: the product library fails loudly without a device. */
 #include <stdlib.h>
@@ -18,6 +18,7 @@ int so_laplace_fill(double* img, const uint8_t* mask, int64_t rows, int64_t cols
 int so_poisson_blend(double* const* inputs, const double* const* replacements, int nbands, const uint8_t* mask, int64_t rows,
     int64_t cols, int64_t rs, int64_t cs, double tol, int64_t max_it, so_stats* per_band);
 int32_t so_label_components(const uint8_t* mask, int64_t rows, int64_t cols, int64_t rs, int64_t cs, int32_t* labels);
+int64_t so_unknown_numbering(const uint8_t* mask, int64_t rows, int64_t cols, int64_t rs, int64_t cs, int32_t* number);
 
 struct sa_ctx {
     int dummy;
@@ -90,6 +91,14 @@ int sa_label_components(sa_ctx* ctx, const uint8_t* mask, int64_t rows, int64_t 
 {
     (void)ctx;
     *out_num_labels = so_label_components(mask, rows, cols, row_stride, col_stride, labels);
+    return SA_OK;
+}
+
+int sa_unknown_numbering(sa_ctx* ctx, const uint8_t* mask, int64_t rows, int64_t cols, int64_t row_stride, int64_t col_stride,
+    int32_t* numbering, int64_t* out_count)
+{
+    (void)ctx;
+    *out_count = so_unknown_numbering(mask, rows, cols, row_stride, col_stride, numbering);
     return SA_OK;
 }
 

@@ -118,3 +118,24 @@ def test_c_blend_example_on_gpu(tmp_path):
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "components: 2 labels, sizes 4 and 8" in r.stdout
+
+
+def test_c_examples_logic_on_the_cpu(tmp_path):
+    """examples/*.c run to completion on the CPU against tests/fake_satfill.c (the C-ABI answered by the ORACLE, put in
+    front of the real library through LD_LIBRARY_PATH): their own arithmetic and known answers are right, independently
+    of the device run (test_c_example_on_gpu, test_c_blend_example_on_gpu)."""
+    import oracle
+
+    oracle.port()
+    odir = os.path.join(ROOT, "oracle", "_build")
+    fake = tmp_path / "fake"
+    fake.mkdir()
+    r = subprocess.run(["gcc", "-O2", "-std=c99", "-Wall", "-Wextra", "-fPIC", "-shared", "-I", os.path.join(ROOT, "include"),
+                        os.path.join(ROOT, "tests", "fake_satfill.c"), "-o", str(fake / "libsatfill.so"), "-L", odir,
+                        "-loracle", f"-Wl,-rpath,{odir}"], capture_output=True, text=True)  # fmt: skip
+    assert r.returncode == 0, r.stderr
+    env = dict(os.environ, LD_LIBRARY_PATH=str(fake) + os.pathsep + os.environ.get("LD_LIBRARY_PATH", ""))
+    r = subprocess.run([_build_c_example(tmp_path)], capture_output=True, text=True, env=env)
+    assert r.returncode == 0 and "max error" in r.stdout, r.stdout + r.stderr
+    r = subprocess.run([_build_c_example(tmp_path, "blend_c_abi")], capture_output=True, text=True, env=env)
+    assert r.returncode == 0 and "components: 2 labels, sizes 4 and 8" in r.stdout, r.stdout + r.stderr
