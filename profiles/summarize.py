@@ -43,6 +43,13 @@ WANT = [
     "sm__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__t_sector_hit_rate.pct",
     "smsp__warp_issue_stalled_long_scoreboard_per_warp_active.pct", "smsp__warp_issue_stalled_barrier_per_warp_active.pct",
     "dram__cycles_elapsed.avg.per_second", "gpc__cycles_elapsed.avg.per_second",
+    # where the reads are served from (do the frame halos hit in L2? at which granularity is
+    # DRAM filled?)
+    "dram__sectors_read.sum", "dram__sectors_write.sum", "lts__t_sectors_srcunit_tex_op_read.sum",
+    "lts__t_sectors_srcunit_tex_op_read_lookup_hit.sum", "lts__t_sectors_srcunit_tex_op_read_lookup_miss.sum",
+    "lts__t_sectors_srcunit_tex_op_write.sum", "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum",
+    "l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum", "l1tex__t_sectors_pipe_lsu_mem_global_op_st.sum",
+    "lts__t_bytes.sum", "smsp__inst_executed.sum",
 ]  # fmt: skip
 
 

@@ -26,4 +26,14 @@ for ks in k_update2:2 k_direction2:2 k_rb_down:11 k_rb_up:21; do
         -f -o $out/${tag}_full_${k} python bench.py --steps 1 --warmup 0 --bands 4 --no-e2e --no-cpu > $out/${tag}_ncu_${k}.log 2>&1
     echo "ncu $k rc=$?"
 done
+# DENSE=1: the same two cycle kernels on a dense hole of the same size (bench.py --mask full): same halo factor, every DRAM
+# granule full -- the pair of captures that separates "halos miss in L2" from "short runs" 
+if [ "${DENSE:-0}" = "1" ]; then
+    for ks in k_rb_down:11 k_rb_up:21 k_update2:2; do
+        k=${ks%%:*}; skip=${ks##*:}
+        timeout 600 ncu --set full --clock-control none --import-source on -k regex:"^${k}\$" --launch-skip $skip --launch-count 1 \
+            -f -o $out/${tag}_dense_full_${k} python bench.py --steps 1 --warmup 0 --bands 4 --mask full --no-e2e --no-cpu > $out/${tag}_dense_ncu_${k}.log 2>&1
+        echo "ncu dense $k rc=$?"
+    done
+fi
 ls -la $out | tail -20
