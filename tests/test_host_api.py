@@ -189,3 +189,39 @@ def test_cpp_shim_behaviour_on_the_cpu(tmp_path):
     r = subprocess.run([sys.executable, os.path.join(root, "tests", "core_fake_worker.py")], env=env, capture_output=True,
                        text=True, timeout=600)  # fmt: skip
     assert r.returncode == 0 and "core-on-fake ok" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
+
+
+def test_find_good_close_image_cpp_and_python_agree_on_random_tables(tmp_path):
+    """The ranking rule of find_good_close_image (poisson.cpp:323-349) in both host languages on random `dates` tables
+    (hypothesis): same answer for every date, weight and invalid fraction, ties included."""
+    import datetime as dt
+
+    hyp = pytest.importorskip("hypothesis")
+    st = pytest.importorskip("hypothesis.strategies")
+    from satellite_approximation_b200 import scenes as sc
+
+    core = _core_or_skip()
+    days = st.integers(0, 200).map(lambda k: dt.date(2019, 11, 1) + dt.timedelta(days=k))  # crosses a year boundary
+    frac = st.sampled_from([0.0, 0.05, 0.1, 0.25, 0.25, 0.5, 0.9, 1.0])  # repeated values: ties
+    counter = [0]
+
+    @hyp.settings(max_examples=40, deadline=None, suppress_health_check=list(hyp.HealthCheck))
+    @hyp.given(rows=st.dictionaries(days, frac, min_size=1, max_size=12), date=days, own=st.one_of(st.none(), frac),
+               w=st.sampled_from([0.0, 0.01, 0.3, 0.5, 0.99, 1.0]))  # fmt: skip
+    def run(rows, date, own, w):
+        counter[0] += 1
+        base = tmp_path / f"t{counter[0]}"
+        base.mkdir()
+        rows = dict(rows)
+        rows.pop(date, None)
+        with sc.DataBase(base) as db:
+            for d, p in rows.items():
+                db.write_detection_result(d.isoformat(), True, True, 0.0, 0.0, p)
+            if own is not None:
+                db.write_detection_result(date.isoformat(), True, True, 0.0, 0.0, own)
+            want = sc.find_good_close_image(date.isoformat(), w, db)
+            close = [(i.date.isoformat(), i.percent_invalid) for i in db.select_close_images(date.isoformat())]
+        got = core.find_good_close_image(date.isoformat(), w, close, float("nan") if own is None else own)
+        assert got == want, (rows, date, own, w)
+
+    run()
