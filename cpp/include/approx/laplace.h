@@ -25,7 +25,7 @@ void fill_missing_portion_smooth_boundary(MatX<f64>& input_image, MatX<bool> con
 struct LaplaceOptions {
     f64 tolerance = 0.0;
     long max_iterations = 0;
-    bool multigrid = false;
+    bool multigrid = true;  // false: Eigen's DiagonalPreconditioner (the reference's own), ~50x more iterations
 };
 void set_laplace_options(LaplaceOptions const& options);
 

@@ -121,5 +121,5 @@ PYBIND11_MODULE(_core, m)
         py::arg("invalid_pixels").noconvert());
     m.def("set_laplace_options", [](double tolerance, long max_iterations, bool multigrid) {
         approx::set_laplace_options({ tolerance, max_iterations, multigrid });
-    }, "tolerance"_a = 0.0, "max_iterations"_a = 0, "multigrid"_a = false);
+    }, "tolerance"_a = 0.0, "max_iterations"_a = 0, "multigrid"_a = true);
 }

@@ -156,6 +156,12 @@ int sa_poisson_blend(sa_ctx* ctx, double* const* inputs, const double* const* re
  * is transpose-invariant, so a column-major source is solved as its transpose without a transposition). */
 int sa_scene_create(sa_ctx* ctx, int problem, int64_t rows, int64_t cols, int nbands, sa_scene** out);
 void sa_scene_destroy(sa_scene* scene);
+/* Limits of sa_scene_create (and of the host-pointer fills, which keep a scene).  The kernels address a band plane
+ * with 32-bit element offsets: sa_scene_plane_elements(rows, cols) -- the padded plane, in the larger of the two
+ * orientations a scene can be resident in; pure host arithmetic, needs no device -- must not exceed INT32_MAX
+ * (a 46000 x 46000 band; larger systems are split by rows across GPUs).  At most SA_MAX_BANDS bands per scene. */
+#define SA_MAX_BANDS 512
+int64_t sa_scene_plane_elements(int64_t rows, int64_t cols);
 /* src_on_device != 0: `src` is a device pointer (same strides convention).  Uploads are asynchronous on the
  * context's stream when the host memory is pinned. */
 int sa_scene_set_mask(sa_scene* scene, const uint8_t* src, int64_t row_stride, int64_t col_stride, int src_on_device);

@@ -100,7 +100,7 @@ class SolveStats(dict):
 
 # Solver knobs the reference does not expose on its Python surface.  `None` = the reference's own behaviour
 # (Laplace: Eigen defaults, epsilon tolerance / 2N iterations, laplace.cpp:113-114).
-_defaults = {"laplace_tolerance": None, "laplace_max_iterations": None, "precond": JACOBI, "check_every": None}
+_defaults = {"laplace_tolerance": None, "laplace_max_iterations": None, "precond": MULTIGRID, "check_every": None}
 _last_perf: list[SolveStats] = []
 
 
@@ -338,9 +338,17 @@ class Context:
         """preprocess_cloud_band (poisson-main.cpp:10-21): MORPH_CLOSE with a (2 radius + 1)^2 rectangle, cast to bool."""
         if band.dtype != np.float64 or band.ndim != 2:
             raise TypeError("morph_close_mask: a 2-D float64 band")
+        # The entry point writes the mask with the band's own pitch (satfill.h): a strided view (band[:, :k] of a wider
+        # array, negative strides ...) is densified first, so that the dense mask allocated here is what the library
+        # addresses -- a view's pitch would run past the end of it.
+        if not (band.flags.c_contiguous or band.flags.f_contiguous):
+            band = np.ascontiguousarray(band)
         rs, cs = _capi.element_strides(band)
         rows, cols = band.shape
-        mask = np.empty(band.shape, np.uint8, order="F" if (rs == 1 and rows > 1) else "C")
+        mask = np.empty(band.shape, np.uint8, order="F" if (band.flags.f_contiguous and not band.flags.c_contiguous) else "C")
+        mrs, mcs = _capi.element_strides(mask)
+        if rows * cols and (rows > 1 and cols > 1) and (mrs, mcs) != (rs, cs):
+            raise AssertionError("morph_close_mask: mask and band layouts differ")
         with self._lock:
             st = self._lib.sa_morph_close_mask(self._h, band.ctypes.data, rows, cols, rs, cs, int(radius), mask.ctypes.data)
         self._check(st)

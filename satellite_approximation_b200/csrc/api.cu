@@ -207,6 +207,20 @@ extern "C" {
 
 int sa_abi_version(void) { return SATFILL_ABI_VERSION; }
 
+int64_t sa_scene_plane_elements(int64_t rows, int64_t cols)
+{
+    if (rows < 0 || cols < 0)
+        return -1;
+    // the larger of the two orientations a scene can be resident in (scene_alloc)
+    auto plane = [](int64_t r, int64_t c) {
+        int64_t rp = round_up(r, TILE_H);
+        if (rp == 0)
+            rp = TILE_H;
+        return (rp + 2) * round_up(c + 1, TILE_W);
+    };
+    return std::max(plane(rows, cols), plane(cols, rows));
+}
+
 int sa_create(sa_ctx** out, int device, void* stream)
 {
     if (!out)
@@ -283,7 +297,11 @@ void sa_default_options(sa_options* o, int problem)
     // Laplace: Eigen's default tolerance is machine epsilon (IterativeSolverBase.h:367-368); Poisson: 1e-6 (poisson.h:45)
     o->tolerance = problem == SA_POISSON ? 1e-6 : DBL_EPSILON;
     o->max_iterations = 0;
-    o->precond = SA_PRECOND_JACOBI;
+    // The red-black multigrid V-cycle (mg_rb.cu) is the default preconditioner: the drop-in call takes the fast path.  It
+    // changes the path CG takes, not its fixed point or its stop rule, and the float cycle does not limit the attainable
+    // residual (tests: 1e-14).  SA_PRECOND_JACOBI -- Eigen's DiagonalPreconditioner, the reference's own -- is the opt-in.
+    o->precond = SA_PRECOND_MULTIGRID;
+    o->mg_variant = SA_MG_RB32;
     o->check_every = 0;
     o->mg_levels = 0;
     o->mg_smooth = 2;
@@ -398,8 +416,14 @@ int sa_scene_create(sa_ctx* ctx, int problem, int64_t rows, int64_t cols, int nb
     SA_TRY(check_ctx(ctx));
     if (!out || rows < 0 || cols < 0 || nbands < 1 || (problem != SA_LAPLACE && problem != SA_POISSON))
         return fail(ctx, SA_BAD_ARGUMENT, "scene_create: bad arguments");
-    if ((rows + 64) * (cols + 64) > (int64_t)INT32_MAX * 2 || rows > (1 << 20) || cols > (1 << 20))
-        return fail(ctx, SA_BAD_ARGUMENT, "scene_create: scene too large for one device plane");
+    // The strip kernels address a band plane with 32-bit element offsets (cg_strip.cu: TileBits::origin): the padded plane
+    // -- (rows rounded up to 32 + 2 guard rows) x (cols + 1 rounded up to 32), in either orientation -- must hold fewer
+    // than 2^31 elements (a 46000 x 46000 band; bigger holes are split by rows across GPUs, dist.cu).
+    if (sa_scene_plane_elements(rows, cols) > (int64_t)INT32_MAX || rows > (1 << 20) || cols > (1 << 20))
+        return fail(ctx, SA_BAD_ARGUMENT, "scene_create: scene too large for one device plane (32-bit plane offsets)");
+    // per-band scalars are published through a fixed page-locked buffer (cg.cu: k_publish_scalars, two look-ahead slots)
+    if (nbands > SA_MAX_BANDS)
+        return fail(ctx, SA_BAD_ARGUMENT, "scene_create: too many bands in one scene (SA_MAX_BANDS)");
     sa_scene* s = new (std::nothrow) sa_scene();
     if (!s)
         return fail(ctx, SA_OUT_OF_MEMORY, "scene_create: host allocation failed");
@@ -662,7 +686,8 @@ static int host_fill(sa_ctx* ctx, int problem, double* const* images, const doub
         bool direct = std::getenv("SATFILL_NO_DIRECT") == nullptr && o.cg_variant == 0
             && (o.precond != SA_PRECOND_MULTIGRID || o.mg_variant == SA_MG_RB32) && s->cols % 2 == 0 && s->rows > 0;
         const int64_t sp = slow_stride(s, rs, cs);
-        direct = direct && sp % 2 == 0;
+        // the fetch / scatter kernels address the caller's array with 32-bit element offsets as well
+        direct = direct && sp % 2 == 0 && (s->rows_p + 2) * sp <= (int64_t)INT32_MAX;
         std::vector<double*> dev_f((size_t)nbands, nullptr);
         std::vector<const double*> dev_g((size_t)nbands, nullptr);
         for (int b = 0; b < nbands && direct; ++b) {

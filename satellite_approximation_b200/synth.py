@@ -143,3 +143,126 @@ def torch_band(rows: int, cols: int, seed: int = 1, device="cuda"):
     f = f + 0.1 * torch.randn((rows, cols), generator=g, device=device, dtype=torch.float64)
     f = (f + 1.9) * (10000.0 / 3.8)
     return f.clamp_(0.0, 10000.0).contiguous()
+
+
+# ---- the benchmark scene of SURVEY.md 8d (configs[2]), window-reproducible ------------------------------------------------
+# "mask = threshold at the 70th percentile of Gaussian-filtered (sigma ~ 40 px) white noise, border ring cleared".  Both
+# bench arms must see the SAME scene: the B200 arm builds the whole 10980^2 tile in HBM, the CPU reference arm solves a
+# crop of it.  So the white noise is a counter-based hash of the GLOBAL pixel coordinates (any window can be generated on
+# its own, identically in numpy and torch), the Gaussian is truncated at 4 sigma (a window needs a halo of that many
+# noise pixels, nothing else), and the threshold is the analytic (1 - cover) quantile of the filtered field (a weighted sum
+# of ~4 pi sigma^2 = 20000 uniform variates is Gaussian to every digit that matters), not a quantile of the realisation.
+
+
+def _hash_uniform(r, c, seed: int):
+    """Uniform noise in [-0.5, 0.5) at global coordinates (r, c): int64 tensors / arrays (numpy or torch), broadcastable.
+    Plain 64-bit integer arithmetic that both libraries wrap identically; every intermediate is masked to 32 bits."""
+    m = 0xFFFFFFFF
+    h = (r * 0x9E3779B1 + c * 0x85EBCA77 + (int(seed) & m) * 0xC2B2AE3D + 0x27D4EB2F) & m
+    h = h ^ (h >> 15)
+    h = (h * 0x2C1B3C6D) & m
+    h = h ^ (h >> 12)
+    h = (h * 0x297A2D39) & m
+    h = h ^ (h >> 15)
+    return h, 1.0 / 4294967296.0
+
+
+def _gauss_kernel(sigma: float):
+    radius = int(np.ceil(4.0 * sigma))
+    x = np.arange(-radius, radius + 1, dtype=np.float64)
+    k = np.exp(-0.5 * (x / sigma) ** 2)
+    return k / k.sum(), radius
+
+
+def cloud_threshold(sigma: float, cover: float) -> float:
+    """Analytic (1 - cover) quantile of the filtered field: zero mean, std = sqrt(1 / 12) * sum(k^2) for the separable
+    kernel k (x) k applied to uniform noise of variance 1 / 12."""
+    from statistics import NormalDist
+
+    k, _ = _gauss_kernel(sigma)
+    return NormalDist().inv_cdf(1.0 - cover) * float(np.sqrt(1.0 / 12.0) * np.sum(k * k))
+
+
+def cloud_mask(rows: int, cols: int, cover: float = 0.3, sigma: float = 40.0, seed: int = 2, row0: int = 0, col0: int = 0,
+               clear_border: bool = True):
+    """numpy: the window [row0, row0 + rows) x [col0, col0 + cols) of the SURVEY 8d cloud mask with seed `seed` (bool).
+    clear_border clears the one-pixel ring of THIS window (a crop is its own image: Laplace unknowns never sit on the
+    image border, laplace.cpp:98-100)."""
+    from scipy.ndimage import correlate1d
+
+    k, R = _gauss_kernel(sigma)
+    r = np.arange(row0 - R, row0 + rows + R, dtype=np.int64)[:, None]
+    c = np.arange(col0 - R, col0 + cols + R, dtype=np.int64)[None, :]
+    h, scale = _hash_uniform(r, c, seed)
+    f = h.astype(np.float32) * np.float32(scale) - np.float32(0.5)
+    k32 = k.astype(np.float32)
+    f = correlate1d(f, k32, axis=0, mode="constant")[R:-R]
+    f = correlate1d(f, k32, axis=1, mode="constant")[:, R:-R]
+    m = f > np.float32(cloud_threshold(sigma, cover))
+    if clear_border:
+        m[0, :] = m[-1, :] = False
+        m[:, 0] = m[:, -1] = False
+    return m
+
+
+def torch_cloud_mask(rows: int, cols: int, cover: float = 0.3, sigma: float = 40.0, seed: int = 2, device="cuda",
+                     row0: int = 0, col0: int = 0, clear_border: bool = True):
+    """torch: the same window of the same mask as `cloud_mask`, built on `device` (uint8 0/1).  Float rounding of the
+    filter differs between the two, so a handful of pixels within 1e-6 of the threshold may differ; tests bound it."""
+    import torch
+
+    k, R = _gauss_kernel(sigma)
+    r = torch.arange(row0 - R, row0 + rows + R, device=device, dtype=torch.int64)[:, None]
+    c = torch.arange(col0 - R, col0 + cols + R, device=device, dtype=torch.int64)[None, :]
+    h, scale = _hash_uniform(r, c, seed)
+    f = h.to(torch.float32).mul_(scale).sub_(0.5)
+    del h
+    kt = torch.tensor(k, device=device, dtype=torch.float32)
+    f = torch.nn.functional.conv2d(f[None, None], kt.view(1, 1, -1, 1))
+    f = torch.nn.functional.conv2d(f, kt.view(1, 1, 1, -1))[0, 0]
+    m = (f > float(np.float32(cloud_threshold(sigma, cover)))).to(torch.uint8)
+    if clear_border:
+        m[0, :] = 0
+        m[-1, :] = 0
+        m[:, 0] = 0
+        m[:, -1] = 0
+    return m.contiguous()
+
+
+def _band_params(seed: int):
+    rng = np.random.default_rng(1000003 + int(seed))
+    return rng.uniform(1.0, 6.0, size=4), rng.uniform(0, 2 * np.pi, size=4)
+
+
+def scene_band(rows: int, cols: int, seed: int = 1, row0: int = 0, col0: int = 0, total_rows: int | None = None,
+               total_cols: int | None = None):
+    """numpy: window of the benchmark band `seed` (smooth field + hash noise in [0, 10000], float64) of a
+    total_rows x total_cols tile; any window of it comes out identically, and `torch_scene_band` builds the same values."""
+    tr, tc = total_rows or rows, total_cols or cols
+    k, ph = _band_params(seed)
+    ri = np.arange(row0, row0 + rows, dtype=np.int64)[:, None]
+    ci = np.arange(col0, col0 + cols, dtype=np.int64)[None, :]
+    r = ri.astype(np.float64) / max(tr - 1, 1)
+    c = ci.astype(np.float64) / max(tc - 1, 1)
+    tau = 2 * np.pi
+    f = np.sin(k[0] * tau * r + ph[0]) * np.cos(k[1] * tau * c + ph[1]) + 0.5 * np.sin(k[2] * tau * (r + c) + ph[2])
+    h, scale = _hash_uniform(ri, ci, 7919 + seed)
+    f = f + 0.35 * (h.astype(np.float64) * scale - 0.5)
+    return np.clip((f + 1.9) * (10000.0 / 3.8), 0.0, 10000.0)
+
+
+def torch_scene_band(rows: int, cols: int, seed: int = 1, device="cuda", row0: int = 0, col0: int = 0,
+                     total_rows: int | None = None, total_cols: int | None = None):
+    import torch
+
+    tr, tc = total_rows or rows, total_cols or cols
+    k, ph = _band_params(seed)
+    ri = torch.arange(row0, row0 + rows, device=device, dtype=torch.int64)[:, None]
+    ci = torch.arange(col0, col0 + cols, device=device, dtype=torch.int64)[None, :]
+    r = ri.to(torch.float64) / max(tr - 1, 1)
+    c = ci.to(torch.float64) / max(tc - 1, 1)
+    tau = 2 * np.pi
+    f = torch.sin(k[0] * tau * r + ph[0]) * torch.cos(k[1] * tau * c + ph[1]) + 0.5 * torch.sin(k[2] * tau * (r + c) + ph[2])
+    h, scale = _hash_uniform(ri, ci, 7919 + seed)
+    f = f + 0.35 * (h.to(torch.float64) * scale - 0.5)
+    return ((f + 1.9) * (10000.0 / 3.8)).clamp_(0.0, 10000.0).contiguous()

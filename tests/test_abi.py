@@ -48,7 +48,7 @@ def test_struct_layouts_match_header():
     lib = _capi.load()
     o = _capi.Options()
     lib.sa_default_options(ctypes.byref(o), _capi.SA_POISSON)
-    assert o.tolerance == 1e-6 and o.max_iterations == 0 and o.precond == _capi.SA_PRECOND_JACOBI
+    assert o.tolerance == 1e-6 and o.max_iterations == 0 and o.precond == _capi.SA_PRECOND_MULTIGRID  # the drop-in call takes the fast path
     lib.sa_default_options(ctypes.byref(o), _capi.SA_LAPLACE)
     assert o.tolerance == 2.220446049250313e-16  # Eigen default (IterativeSolverBase.h:367-368)
 

@@ -94,7 +94,13 @@ def test_pybind_module_is_a_drop_in(port):
         sa.filling_missing_portions_smooth_boundaries(img.astype(np.float32), mask)  # noconvert (src/main.cpp:49-54)
     with pytest.raises(RuntimeError):
         sa.filling_missing_portions_smooth_boundaries(img, np.asfortranarray(mask[:-1]))  # laplace.cpp:124-127
+    # the reference's own preconditioner as the opt-in, then back to the defaults: a plain drop-in call (no knobs:
+    # epsilon tolerance, 2N iterations, laplace.cpp:113-114) runs the multigrid path and lands on the same fill
     core.set_laplace_options(tolerance=0.0, max_iterations=0, multigrid=False)
+    gotj = sa.filling_missing_portions_smooth_boundaries(img, mask)
+    core.set_laplace_options(tolerance=0.0, max_iterations=0, multigrid=True)
+    gotd = sa.filling_missing_portions_smooth_boundaries(img, mask)
+    assert rel_max_abs(gotj, want, mask) < 1e-9 and rel_max_abs(gotd, want, mask) < 1e-9
     f = [synth.smooth_band(rows, cols, seed=5 + b) for b in range(2)]
     g = [synth.second_date(b, seed=3 + i) for i, b in enumerate(f)]
     pmask = synth.blob_mask(rows, cols, cover=0.3, sigma=4.0, seed=9, clear_border=False)

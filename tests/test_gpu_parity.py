@@ -146,7 +146,19 @@ def test_reference_default_tolerances(ctx, port):
     gotp = sab.blend_images_poisson([img], [g], mask)
     st = sab.last_perf_info()[0]
     assert st["status"] == sab.SA_OK and st["error"] <= 1e-6
-    # same algorithm, same stop rule: the iteration count matches Eigen's to within reduction-order rounding
+    assert st["iterations"] < wst[0].iterations  # the default preconditioner is the multigrid cycle
+    assert rel_max_abs(gotp[0], wantp[0], mask) < 1e-5
+    # the reference's own preconditioner (opt-in): same algorithm, same stop rule -- the iteration count matches Eigen's
+    # to within reduction-order rounding
+    sab.set_solver_defaults(precond=sab.JACOBI)
+    try:
+        gotj = sab.filling_missing_portions_smooth_boundaries(img, mask)
+        assert rel_max_abs(gotj, want, mask) < 1e-9
+        gotp = sab.blend_images_poisson([img], [g], mask)
+        st = sab.last_perf_info()[0]
+    finally:
+        sab.set_solver_defaults(precond=sab.MULTIGRID)
+    assert st["status"] == sab.SA_OK and st["error"] <= 1e-6
     assert abs(st["iterations"] - wst[0].iterations) <= 2
     assert rel_max_abs(gotp[0], wantp[0], mask) < 1e-5
 

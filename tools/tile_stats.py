@@ -1,5 +1,5 @@
 """CPU-side statistics of a workload mask under candidate tilings (no GPU): how much of what the tile kernels touch is
-algorithmic work.  For the default bench mask (synth.torch_blob_mask, 10980^2, 30 % cover) and a tile shape it prints
+algorithmic work.  For the default bench mask (synth.cloud_mask: SURVEY 8d, sigma = 40 px, 10980^2, 30 % cover; --bicubic: round 1's mask) and a tile shape it prints
 
   * the share of tiles that hold at least one unknown (the tile lists the kernels walk),
   * the fill of those tiles (unknowns / cells): the padding the dense-in-tile kernels pay,
@@ -79,10 +79,15 @@ def main() -> None:
 
     from satellite_approximation_b200 import synth
 
-    rows = int(sys.argv[1]) if len(sys.argv) > 1 else 10980
-    cols = int(sys.argv[2]) if len(sys.argv) > 2 else rows
-    mask = synth.torch_blob_mask(rows, cols, device="cpu").numpy().astype(bool)
-    print(f"# synth.torch_blob_mask({rows}, {cols}): {mask.mean() * 100:.2f} % unknown ({int(mask.sum())} pixels)")
+    args = [a for a in sys.argv[1:] if not a.startswith("--")]
+    rows = int(args[0]) if len(args) > 0 else 10980
+    cols = int(args[1]) if len(args) > 1 else rows
+    if "--bicubic" in sys.argv:  # round 1's bench mask: bicubically upsampled 48-pixel noise (blobs of about one tile)
+        mask = synth.torch_blob_mask(rows, cols, device="cpu").numpy().astype(bool)
+        print(f"# synth.torch_blob_mask({rows}, {cols}): {mask.mean() * 100:.2f} % unknown ({int(mask.sum())} pixels)")
+    else:  # the bench mask: SURVEY.md 8d, Gaussian-filtered (sigma = 40 px) white noise
+        mask = synth.cloud_mask(rows, cols)
+        print(f"# synth.cloud_mask({rows}, {cols}, sigma=40): {mask.mean() * 100:.2f} % unknown ({int(mask.sum())} pixels)")
     print("# DRAM bytes moved per byte of unknowns in a row-major plane, by fill granularity:")
     for elem, name in ((8, "double"), (4, "float")):
         print(f"#   {name:6s}  32 B sectors: {granule_amplification(mask, elem, 32):.3f}   64 B (sector pairs): "
