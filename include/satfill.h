@@ -56,8 +56,11 @@ typedef enum sa_precond {
 } sa_precond;
 
 typedef enum sa_mg_variant {
-    SA_MG_RB32 = 0,    /* red-black Gauss-Seidel V(1,1), float arithmetic inside the preconditioner (mg_rb.cu)      */
-    SA_MG_JACOBI64 = 1 /* damped-Jacobi V(nu,nu), double (mg_fused.cu / mg.cu)                                      */
+    SA_MG_RB32 = 0,     /* red-black Gauss-Seidel V(1,1), float arithmetic inside the preconditioner: one warp per tile,
+                         * neighbourhood in registers, coarse tail in one cooperative launch (mg_rbw.cu)              */
+    SA_MG_JACOBI64 = 1, /* damped-Jacobi V(nu,nu), double (mg_fused.cu / mg.cu)                                      */
+    SA_MG_RB32_CTA = 2  /* the same cycle as SA_MG_RB32 on its first-generation kernels (one CTA per tile and band,
+                         * neighbourhood in shared memory, one launch per level: mg_rb.cu); kept as the tested reference */
 } sa_mg_variant;
 
 /* Solver knobs.  The reference exposes tolerance / max_iterations on Poisson only (poisson.h:45-46); Laplace runs

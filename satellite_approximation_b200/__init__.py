@@ -38,6 +38,7 @@ from ._capi import (  # noqa: F401  (re-exported)
     SA_PRECOND_MULTIGRID as MULTIGRID,
     SA_MG_RB32 as MG_RB32,
     SA_MG_JACOBI64 as MG_JACOBI64,
+    SA_MG_RB32_CTA as MG_RB32_CTA,
     SatfillError,
 )
 
@@ -46,7 +47,7 @@ __all__ = [
     "find_connected_components", "ConnectedComponents", "mask_scan", "unknown_numbering", "valid_neighbours",
     "Context", "Scene", "SolveStats", "default_context", "set_solver_defaults", "last_perf_info", "write_perf_info",
     "dist_partition", "dist_levels", "apply_laplace", "preprocess_cloud_band", "blend_images_poisson_offset", "valid_pixel_mask", "image_to_channels", "channels_to_image",
-    "highlight_area_replaced", "LAPLACE", "POISSON", "JACOBI", "MULTIGRID", "MG_RB32", "MG_JACOBI64", "SatfillError",
+    "highlight_area_replaced", "LAPLACE", "POISSON", "JACOBI", "MULTIGRID", "MG_RB32", "MG_JACOBI64", "MG_RB32_CTA", "SatfillError",
 ]  # fmt: skip
 
 _log = logging.getLogger("satellite_approximation_b200")

@@ -18,7 +18,7 @@ ABI_VERSION = 4  # SATFILL_ABI_VERSION of include/satfill.h
 SA_OK, SA_EMPTY_MASK, SA_NOT_CONVERGED, SA_SIZE_MISMATCH, SA_BAD_ARGUMENT, SA_CUDA_ERROR, SA_NCCL_ERROR, SA_OOM = range(8)
 SA_LAPLACE, SA_POISSON = 0, 1
 SA_PRECOND_JACOBI, SA_PRECOND_MULTIGRID = 0, 1
-SA_MG_RB32, SA_MG_JACOBI64 = 0, 1
+SA_MG_RB32, SA_MG_JACOBI64, SA_MG_RB32_CTA = 0, 1, 2
 
 STATUS_NAMES = {
     0: "SA_OK", 1: "SA_EMPTY_MASK", 2: "SA_NOT_CONVERGED", 3: "SA_SIZE_MISMATCH", 4: "SA_BAD_ARGUMENT",

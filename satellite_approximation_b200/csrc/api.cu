@@ -280,6 +280,7 @@ void sa_destroy(sa_ctx* ctx)
         cudaEventDestroy(ev);
     if (ctx->pinned)
         cudaFreeHost(ctx->pinned);
+    cudaFree(ctx->d_barrier);
     if (ctx->owns_stream)
         cudaStreamDestroy(ctx->stream);
     delete static_cast<sa_ctx_full*>(ctx);
@@ -675,7 +676,7 @@ static int host_fill(sa_ctx* ctx, int problem, double* const* images, const doub
     if (!(o.tolerance > 0.0))
         o.tolerance = problem == SA_POISSON ? 1e-6 : DBL_EPSILON;
     SA_TRY(ensure_indexed(s, o.precond != SA_PRECOND_MULTIGRID ? WORK_JACOBI
-                                 : (o.mg_variant == SA_MG_RB32 && o.cg_variant == 0 ? WORK_RB : WORK_J64)));
+                                 : (o.mg_variant != SA_MG_JACOBI64 && o.cg_variant == 0 ? WORK_RB : WORK_J64)));
     if (s->n_unknowns == 0)
         return solve_scene(s, o, stats);  // fills stats, returns SA_EMPTY_MASK
     // 2a. Direct mode: when the caller's arrays are page-locked (cudaMallocHost / cudaHostRegister / torch pin_memory) the
@@ -684,7 +685,7 @@ static int host_fill(sa_ctx* ctx, int problem, double* const* images, const doub
     //     set for Poisson -- and a scatter kernel stores only the unknown pixels back.  Known pixels never cross PCIe.
     {
         bool direct = std::getenv("SATFILL_NO_DIRECT") == nullptr && o.cg_variant == 0
-            && (o.precond != SA_PRECOND_MULTIGRID || o.mg_variant == SA_MG_RB32) && s->cols % 2 == 0 && s->rows > 0;
+            && (o.precond != SA_PRECOND_MULTIGRID || o.mg_variant != SA_MG_JACOBI64) && s->cols % 2 == 0 && s->rows > 0;
         const int64_t sp = slow_stride(s, rs, cs);
         // the fetch / scatter kernels address the caller's array with 32-bit element offsets as well
         direct = direct && sp % 2 == 0 && (s->rows_p + 2) * sp <= (int64_t)INT32_MAX;
@@ -808,7 +809,7 @@ static int host_fill(sa_ctx* ctx, int problem, double* const* images, const doub
     if (const char* e = std::getenv("SATFILL_CHUNK_BYTES"))  // tests force the chunked path on small scenes
         chunk_bytes = std::max<int64_t>(1, std::atoll(e));
     int per_chunk = (int)std::min<int64_t>(nbands, std::max<int64_t>(1, chunk_bytes / std::max<int64_t>(band_bytes, 1)));
-    const bool windows_ok = o.precond != SA_PRECOND_MULTIGRID || o.mg_variant == SA_MG_RB32;
+    const bool windows_ok = o.precond != SA_PRECOND_MULTIGRID || o.mg_variant != SA_MG_JACOBI64;
     if (per_chunk >= nbands || !windows_ok || std::getenv("SATFILL_NO_PIPELINE"))
         per_chunk = nbands;
     const int nch = (nbands + per_chunk - 1) / per_chunk;

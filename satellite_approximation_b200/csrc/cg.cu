@@ -485,9 +485,12 @@ int precondition_scene(sa_scene* s, const sa_options& o)
     }
     KernelTimer kt;
     kt.ctx = ctx;
-    if (o.mg_variant == SA_MG_RB32) {
+    if (o.mg_variant != SA_MG_JACOBI64) {
         SA_LAUNCH(ctx, k_narrow_plane, 1024, 256, 0, s->plane0(s->r, 0), s->rb_rf(), n);
-        SA_TRY(apply_vcycle_rb(s, o, kt, 0, s->nbands));
+        if (o.mg_variant == SA_MG_RB32_CTA)
+            SA_TRY(apply_vcycle_rb(s, o, kt, 0, s->nbands));
+        else
+            SA_TRY(apply_vcycle_rbw(s, o, kt, 0, s->nbands));
         SA_LAUNCH(ctx, k_widen_plane<float>, 1024, 256, 0, s->rb_z(), um, s->plane0(s->p[0], 0), n);
     } else {
         SA_TRY(apply_vcycle(s, o, kt, 0, s->nbands));
@@ -504,7 +507,7 @@ int prepare_solve(sa_scene* s, const sa_options& o)
 {
     sa_ctx* ctx = s->ctx;
     const bool mg = o.precond == SA_PRECOND_MULTIGRID;
-    const bool rb = mg && o.mg_variant == SA_MG_RB32;
+    const bool rb = mg && o.mg_variant != SA_MG_JACOBI64;
     const bool strip = o.cg_variant == 0;
     SA_TRY(ensure_indexed(s, !mg ? WORK_JACOBI : (rb && strip ? WORK_RB : WORK_J64)));
     if (s->stale_r && !(rb && strip)) {  // Jacobi and the double cycle read r with its halo
@@ -544,7 +547,7 @@ int solve_scene(sa_scene* s, const sa_options& o, sa_stats* stats)
     BandScalars* const scal = s->scal + b0;
     const bool poisson = s->problem == SA_POISSON;
     const bool mg = o.precond == SA_PRECOND_MULTIGRID;
-    const bool rb = mg && o.mg_variant == SA_MG_RB32;
+    const bool rb = mg && o.mg_variant != SA_MG_JACOBI64;
     const bool strip = o.cg_variant == 0;
     SA_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
     SA_TRY(prepare_solve(s, o));
@@ -656,7 +659,10 @@ int solve_scene(sa_scene* s, const sa_options& o, sa_stats* stats)
                 // z = M^-1 r, rz[slot] accumulated by the cycle's last kernel
                 const void* z;
                 if (rb) {
-                    SA_TRY(apply_vcycle_rb(s, o, kt, ki & 3, live));
+                    if (o.mg_variant == SA_MG_RB32_CTA)
+                        SA_TRY(apply_vcycle_rb(s, o, kt, ki & 3, live));
+                    else
+                        SA_TRY(apply_vcycle_rbw(s, o, kt, ki & 3, live));
                     z = s->rb_z();
                 } else {
                     SA_TRY(apply_vcycle(s, o, kt, ki & 3, live));

@@ -88,6 +88,7 @@ struct sa_ctx {
     void* comm = nullptr;
     int rank = 0, world = 1;
     double* d_red = nullptr;  // packed per-band scalars for the all-reduce
+    unsigned* d_barrier = nullptr;  // arrival counter of the grid-wide barrier of the cooperative tail kernel (mg_rbw.cu)
     // host-pointer entry points: PCIe transfers of the other band chunks run on these while a chunk is solved
     cudaStream_t io_in = nullptr, io_out = nullptr;
     bool last_fill_direct = false;
@@ -368,5 +369,8 @@ int apply_vcycle(sa_scene* s, const sa_options& o, KernelTimer& kt, int rz_slot,
 // ---- mg_rb.cu ---------------------------------------------------------------------------------------------------
 // the same for the red-black float cycle: z is a FLOAT plane in s->z
 int apply_vcycle_rb(sa_scene* s, const sa_options& o, KernelTimer& kt, int rz_slot, int live_bands);
+
+// ---- mg_rbw.cu: the same cycle, one warp per tile with the neighbourhood in registers, coarse tail in one launch ------------
+int apply_vcycle_rbw(sa_scene* s, const sa_options& o, KernelTimer& kt, int rz_slot, int live_bands);
 
 }  // namespace satfill

@@ -49,6 +49,32 @@ def c1_scene():
 
 
 @pytest.fixture(scope="session")
+def c1_full(c1_scene):
+    """BASELINE.json configs[0] / [1] at full size: the reference's sample scene with the reference's own converged Eigen
+    solves (oracle/make_golden_full.py): unknown pixels only, 16.16 fixed point, delta-coded."""
+    z = np.load(os.path.join(GOLDEN, "c1_full.npz"))
+    scale = float(z["scale"])
+    shape = tuple(int(v) for v in z["shape"])
+
+    def unpack(planes):  # byte-transposed int32 second differences of 16.16 fixed point (oracle/make_golden_full.py)
+        d2 = np.ascontiguousarray(planes.T).view(np.int32).reshape(-1).astype(np.int64)
+        return np.cumsum(np.cumsum(d2)).astype(np.float64) / scale
+
+    def unpack_band(planes):  # byte-transposed int16 row deltas of the uint16 band
+        d = np.ascontiguousarray(planes.T).view(np.int16).reshape(shape).astype(np.int32)
+        return np.cumsum(d, axis=1).astype(np.uint16).astype(np.float64)  # deltas wrap modulo 2^16
+
+    full = c1_scene["full_mask"]
+    lmask = full.copy()
+    lmask[0, :] = lmask[-1, :] = False
+    lmask[:, 0] = lmask[:, -1] = False
+    return {"b04": unpack_band(z["b04_d"]), "b08": unpack_band(z["b08_d"]), "mask": full, "laplace_mask": lmask,
+            "laplace_unknowns": unpack(z["laplace_unknowns_d"]), "laplace_iters": int(z["laplace_iters"]),
+            "poisson_minus_guidance": [unpack(d) for d in z["poisson_minus_guidance_d"]], "poisson_iters": [int(i) for i in z["poisson_iters"]],
+            "storage_abs_error": 0.5 / scale}  # fmt: skip
+
+
+@pytest.fixture(scope="session")
 def ctx():
     """One library context per test session (GPU tests only)."""
     import satellite_approximation_b200 as sab

@@ -86,8 +86,6 @@ def test_folder_drivers_on_the_gpu(tmp_path, port):
         assert np.array_equal(got[~mask], bands["B04"][~mask].astype(np.float64))
 
 
-@pytest.mark.xfail(strict=False, reason="the C++ poisson_main binary was finished after round 1's GPU minutes were spent: "
-                   "its first run on a device is the round-end suite (XPASS = it works)")  # fmt: skip
 def test_cpp_poisson_main_binary_on_the_gpu(tmp_path, port):
     """cpp/src/poisson_main.cpp end to end: GeoTIFFs in (utils/geotiff.h), approx::preprocess_cloud_band +
     approx::blend_images_poisson on the GPU, GeoTIFF out -- against the oracle, as for the Python driver above."""
