@@ -34,42 +34,77 @@ namespace satfill {
 
 namespace {
 
-constexpr int RW_WARPS = 4;                 // warps per CTA; they never talk to each other
+constexpr int RW_WARPS = 4;                 // warps per CTA of the tail kernel (the per-level kernels run one-warp CTAs)
 constexpr int RW_THREADS = 32 * RW_WARPS;
+// resident one-warp CTAs per SM the per-level kernels are compiled for (= the register budget: 65536 / 32 / CTAs)
+#ifndef SATFILL_RBW_DOWN_CTAS
+#define SATFILL_RBW_DOWN_CTAS 20
+#endif
+#ifndef SATFILL_RBW_UP_CTAS
+#define SATFILL_RBW_UP_CTAS 16
+#endif
+#ifndef SATFILL_RBW_W_CTAS
+#define SATFILL_RBW_W_CTAS 12
+#endif
+// The kernels are bound by memory latency at the occupancy their registers allow (ncu: 5 of 16 warps per SM wait on a
+// long scoreboard per issue slot, issue slots 46 % busy, DRAM 45 - 64 %): while a band of a tile is computed, the rows of the
+// NEXT band of the same tile are already on their way into L2 (prefetch.global.L2, predicated like the loads; `next` =
+// the distance in elements to that band, 0 for the last band of the item).
+#ifndef SATFILL_RBW_PREFETCH
+#define SATFILL_RBW_PREFETCH 0  // measured: 1.6 - 2x SLOWER with the prefetches on (gpurun_out/r2f: 48 -> 80 ms descent, 54 -> 110 ms ascent)
+#endif
+constexpr int RBW_DOWN_CTAS = SATFILL_RBW_DOWN_CTAS, RBW_UP_CTAS = SATFILL_RBW_UP_CTAS, RBW_W_CTAS = SATFILL_RBW_W_CTAS;
 constexpr unsigned FULLW = 0xffffffffu;
 constexpr int DN_RG = 14, DN_HR = 4;        // descent: 3 x 14 = 42 >= 40 frame rows (halo 4: dependence cone 3, aligned)
 constexpr int UP_RG = 12, UP_HR = 2;        // ascent:  3 x 12 = 36 frame rows (halo 2)
 constexpr int HC = 4;                       // column halo of both frames: 40 columns = 10 quads
 
-__device__ __forceinline__ float4 ldg4_if(const float* p, unsigned pred)
+// Accesses predicated on (mask & bit) != 0: an AND with an immediate and a predicated access, no branch; loads give 0 when
+// the predicate is off.  (Written as asm so that all loads of a lane are issued back to back: a C++ conditional makes the
+// compiler order each load next to its use -- measured 15 % slower on the first generation.)
+__device__ __forceinline__ float4 ldg4_if(const float* p, unsigned mask, unsigned bit)
 {
     float4 v;
-    asm("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %5, 0;\n\tmov.f32 %0, 0f00000000;\n\tmov.f32 %1, 0f00000000;\n\t"
-        "mov.f32 %2, 0f00000000;\n\tmov.f32 %3, 0f00000000;\n\t@q ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];\n\t}"
+    asm("{\n\t.reg .pred q;\n\t.reg .b32 t;\n\tand.b32 t, %5, %6;\n\tsetp.ne.u32 q, t, 0;\n\tmov.f32 %0, 0f00000000;\n\t"
+        "mov.f32 %1, 0f00000000;\n\tmov.f32 %2, 0f00000000;\n\tmov.f32 %3, 0f00000000;\n\t"
+        "@q ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];\n\t}"
         : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-        : "l"(p), "r"(pred));
+        : "l"(p), "r"(mask), "r"(bit));
     return v;
 }
-__device__ __forceinline__ float2 ldg2_ifw(const float* p, unsigned pred)
+__device__ __forceinline__ float2 ldg2_ifw(const float* p, unsigned mask, unsigned bit)
 {
     float2 v;
-    asm("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %3, 0;\n\tmov.f32 %0, 0f00000000;\n\tmov.f32 %1, 0f00000000;\n\t"
-        "@q ld.global.nc.v2.f32 {%0, %1}, [%2];\n\t}"
+    asm("{\n\t.reg .pred q;\n\t.reg .b32 t;\n\tand.b32 t, %3, %4;\n\tsetp.ne.u32 q, t, 0;\n\tmov.f32 %0, 0f00000000;\n\t"
+        "mov.f32 %1, 0f00000000;\n\t@q ld.global.nc.v2.f32 {%0, %1}, [%2];\n\t}"
         : "=f"(v.x), "=f"(v.y)
-        : "l"(p), "r"(pred));
+        : "l"(p), "r"(mask), "r"(bit));
     return v;
 }
-__device__ __forceinline__ void stg4_if(float* p, float a, float b, float c, float d, unsigned pred)
+__device__ __forceinline__ void stg4_if(float* p, float a, float b, float c, float d, unsigned mask, unsigned bit)
 {
-    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %5, 0;\n\t@q st.global.v4.f32 [%0], {%1, %2, %3, %4};\n\t}" ::"l"(p), "f"(a),
-                 "f"(b), "f"(c), "f"(d), "r"(pred)
+    asm volatile("{\n\t.reg .pred q;\n\t.reg .b32 t;\n\tand.b32 t, %5, %6;\n\tsetp.ne.u32 q, t, 0;\n\t"
+                 "@q st.global.v4.f32 [%0], {%1, %2, %3, %4};\n\t}" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d), "r"(mask), "r"(bit)
                  : "memory");
 }
-__device__ __forceinline__ void stg2_ifw(float* p, float x, float y, unsigned pred)
+__device__ __forceinline__ void stg2_ifw(float* p, float x, float y, unsigned mask, unsigned bit)
 {
-    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %3, 0;\n\t@q st.global.v2.f32 [%0], {%1, %2};\n\t}" ::"l"(p), "f"(x), "f"(y),
-                 "r"(pred)
+    asm volatile("{\n\t.reg .pred q;\n\t.reg .b32 t;\n\tand.b32 t, %3, %4;\n\tsetp.ne.u32 q, t, 0;\n\t"
+                 "@q st.global.v2.f32 [%0], {%1, %2};\n\t}" ::"l"(p), "f"(x), "f"(y), "r"(mask), "r"(bit)
                  : "memory");
+}
+// the line holding p into L2, if (mask & bit) != 0
+__device__ __forceinline__ void prefetch_l2_if(const void* p, unsigned mask, unsigned bit)
+{
+    asm volatile("{\n\t.reg .pred q;\n\t.reg .b32 t;\n\tand.b32 t, %1, %2;\n\tsetp.ne.u32 q, t, 0;\n\t@q prefetch.global.L2 [%0];\n\t}" ::"l"(p),
+                 "r"(mask), "r"(bit));
+}
+// value if bit k of the mask is set, else 0.  ZW: the value already carries a factor 1 / d that is zero at every cell that
+// is not an unknown (the 1 / d plane of a coarse level): no select needed
+template <bool ZW>
+__device__ __forceinline__ float keep(unsigned mask, int k, float v)
+{
+    return ZW ? v : ((mask & (1u << k)) ? v : 0.f);
 }
 
 // Unknown bits of the four columns of quad q (frame columns 4q .. 4q + 3 <-> tile columns 4q - 4 ..) of the frame of tile
@@ -133,8 +168,8 @@ struct Par {
 // WMODE: 0 = 1/d is 1/4 everywhere, 1 = the level carries a 1/d plane (coarse levels), 2 = 1/d from the coordinates
 // ---------------------------------------------------------------------------------------------------------------
 template <int WMODE>
-__device__ __forceinline__ void rbw_down_tile(const Level& lf, int64_t cpitch, int ty, int tx, int lane,
-    const unsigned long long cm[4], const float* __restrict__ b, float* __restrict__ xr, float* __restrict__ bc)
+__device__ __forceinline__ void rbw_down_tile(const Level& lf, int64_t cpitch, int ty, int tx, int lane, unsigned alive,
+    const unsigned long long cm[4], const float* __restrict__ b, float* __restrict__ xr, float* __restrict__ bc, int64_t next)
 {
     constexpr int RG = DN_RG, HR = DN_HR;
     constexpr unsigned KM = Par<RG>::KM, EV = Par<RG>::EV, OD = Par<RG>::OD;
@@ -142,7 +177,9 @@ __device__ __forceinline__ void rbw_down_tile(const Level& lf, int64_t cpitch, i
     const int g = live ? lane / 10 : 2, q = live ? lane - 10 * g : 9;
     const int row0 = RG * g;
     // rows of the lane that lie inside the 40-row frame
-    const unsigned rows_in = live ? ((row0 + RG <= 32 + 2 * HR) ? KM : ((1u << (32 + 2 * HR - row0)) - 1)) : 0u;
+    // (alive = 0: the band has converged -- every access is predicated off and the arithmetic runs on zeros; a branch around
+    // the tile would make the warp shuffles below conditional, which costs a WARPSYNC / ENDCOLLECTIVE pair around each)
+    const unsigned rows_in = (live ? ((row0 + RG <= 32 + 2 * HR) ? KM : ((1u << (32 + 2 * HR - row0)) - 1)) : 0u) & alive;
     const unsigned c0 = (unsigned)(cm[0] >> row0) & rows_in, c1 = (unsigned)(cm[1] >> row0) & rows_in;
     const unsigned c2 = (unsigned)(cm[2] >> row0) & rows_in, c3 = (unsigned)(cm[3] >> row0) & rows_in;
     const unsigned anyq = c0 | c1 | c2 | c3;
@@ -160,12 +197,18 @@ __device__ __forceinline__ void rbw_down_tile(const Level& lf, int64_t cpitch, i
         unsigned long long bp = (unsigned long long)(b + toff), wp = (unsigned long long)(WMODE == 1 ? lf.winv + toff : nullptr);
 #pragma unroll
         for (int k = 0; k < RG; ++k, bp += pb, wp += pb) {
-            const float4 t = ldg4_if((const float*)bp, (anyq >> k) & 1);
+            const float4 t = ldg4_if((const float*)bp, anyq, 1u << k);
             v[k][0] = t.x, v[k][1] = t.y, v[k][2] = t.z, v[k][3] = t.w;
             if (WMODE == 1) {
-                const float4 w = ldg4_if((const float*)wp, (anyq >> k) & 1);
+                const float4 w = ldg4_if((const float*)wp, anyq, 1u << k);
                 wv[k][0] = w.x, wv[k][1] = w.y, wv[k][2] = w.z, wv[k][3] = w.w;
             }
+        }
+        if (SATFILL_RBW_PREFETCH && next) {
+            unsigned long long np = (unsigned long long)(b + toff + next);
+#pragma unroll
+            for (int k = 0; k < RG; ++k, np += pb)
+                prefetch_l2_if((const void*)np, anyq, 1u << k);
         }
     }
     // ---- red half-sweep from zero: x = b / d.  The tile's own red cells go to HBM colour-split: the two red cells of a
@@ -181,9 +224,9 @@ __device__ __forceinline__ void rbw_down_tile(const Level& lf, int64_t cpitch, i
             const int j0 = k & 1, j1 = 2 + (k & 1);
             // masked like every other cell update: the cycle's vectors are only ever trusted at the unknowns of the CURRENT
             // mask (a mask change leaves them unscrubbed: cg.cu, stale_rb)
-            v[k][j0] = ((rA >> k) & 1) ? v[k][j0] * W(k, j0) : 0.f;
-            v[k][j1] = ((rB >> k) & 1) ? v[k][j1] * W(k, j1) : 0.f;
-            stg2_ifw((float*)xo, v[k][j0], v[k][j1], (st >> k) & 1);
+            v[k][j0] = keep<WMODE == 1>(rA, k, v[k][j0] * W(k, j0));
+            v[k][j1] = keep<WMODE == 1>(rB, k, v[k][j1] * W(k, j1));
+            stg2_ifw((float*)xo, v[k][j0], v[k][j1], st, 1u << k);
         }
     }
     // ---- black half-sweep (in place: a black update reads red cells only)
@@ -199,16 +242,16 @@ __device__ __forceinline__ void rbw_down_tile(const Level& lf, int64_t cpitch, i
                 const float sa = v[k + 1][1], sb = v[k + 1][3];  // RG is even: row k + 1 exists
                 const float xa = W(k, 1) * (v[k][1] + ((na + sa) + (v[k][0] + v[k][2])));
                 const float xb = W(k, 3) * (v[k][3] + ((nb + sb) + (v[k][2] + e)));
-                v[k][1] = ((kA >> k) & 1) ? xa : 0.f;
-                v[k][3] = ((kB >> k) & 1) ? xb : 0.f;
+                v[k][1] = keep<WMODE == 1>(kA, k, xa);
+                v[k][3] = keep<WMODE == 1>(kB, k, xb);
             } else {  // black: columns 0 and 2; west of column 0 is the previous lane's column 3
                 const float w = __shfl_up_sync(FULLW, v[k][3], 1);
                 const float na = v[k - 1][0], nb = v[k - 1][2];
                 const float sa = k < RG - 1 ? v[k < RG - 1 ? k + 1 : k][0] : s0, sb = k < RG - 1 ? v[k < RG - 1 ? k + 1 : k][2] : s2;
                 const float xa = W(k, 0) * (v[k][0] + ((na + sa) + (w + v[k][1])));
                 const float xb = W(k, 2) * (v[k][2] + ((nb + sb) + (v[k][1] + v[k][3])));
-                v[k][0] = ((kA >> k) & 1) ? xa : 0.f;
-                v[k][2] = ((kB >> k) & 1) ? xb : 0.f;
+                v[k][0] = keep<WMODE == 1>(kA, k, xa);
+                v[k][2] = keep<WMODE == 1>(kB, k, xb);
             }
         }
     }
@@ -224,15 +267,15 @@ __device__ __forceinline__ void rbw_down_tile(const Level& lf, int64_t cpitch, i
                 const float na = k > 0 ? v[k > 0 ? k - 1 : 0][0] : n0, nb = k > 0 ? v[k > 0 ? k - 1 : 0][2] : n2;
                 const float ra = (na + v[k + 1][0]) + (w + v[k][1]);
                 const float rb = (nb + v[k + 1][2]) + (v[k][1] + v[k][3]);
-                v[k][0] = ((rA >> k) & 1) ? ra : 0.f;
-                v[k][2] = ((rB >> k) & 1) ? rb : 0.f;
+                v[k][0] = keep<false>(rA, k, ra);
+                v[k][2] = keep<false>(rB, k, rb);
             } else {  // red: columns 1 and 3; east of column 3 is the next lane's column 0
                 const float e = __shfl_down_sync(FULLW, v[k][0], 1);
                 const float sa = k < RG - 1 ? v[k < RG - 1 ? k + 1 : k][1] : s1, sb = k < RG - 1 ? v[k < RG - 1 ? k + 1 : k][3] : s3;
                 const float ra = (v[k - 1][1] + sa) + (v[k][0] + v[k][2]);
                 const float rb = (v[k - 1][3] + sb) + (v[k][2] + e);
-                v[k][1] = ((rA >> k) & 1) ? ra : 0.f;
-                v[k][3] = ((rB >> k) & 1) ? rb : 0.f;
+                v[k][1] = keep<false>(rA, k, ra);
+                v[k][3] = keep<false>(rB, k, rb);
             }
         }
     }
@@ -261,7 +304,7 @@ __device__ __forceinline__ void rbw_down_tile(const Level& lf, int64_t cpitch, i
             const float ca = v[k][0] + 0.25f * ((al + a1) + (left[m] + v[k + 1][1]));
             const float cb = v[k][2] + 0.25f * ((a1 + a3) + (v[k + 1][1] + v[k + 1][3]));
             // a coarse cell of the pair that is not an unknown gets the zero it already holds
-            stg2_ifw((float*)bo, ((c0 >> k) & 1) ? ca : 0.f, ((c2 >> k) & 1) ? cb : 0.f, (st >> k) & 1);
+            stg2_ifw((float*)bo, keep<false>(c0, k, ca), keep<false>(c2, k, cb), st, 1u << k);
         }
     }
 }
@@ -272,16 +315,16 @@ __device__ __forceinline__ void rbw_down_tile(const Level& lf, int64_t cpitch, i
 // Frame: rows ty*32 - 2 .., columns tx*32 - 4 ..; lane = 10 g + q owns rows [12 g, 12 g + 12) of quad q.
 // ---------------------------------------------------------------------------------------------------------------
 template <int WMODE, bool DOT>
-__device__ __forceinline__ float rbw_up_tile(const Level& lf, int64_t cpitch, int ty, int tx, int lane,
+__device__ __forceinline__ float rbw_up_tile(const Level& lf, int64_t cpitch, int ty, int tx, int lane, unsigned alive,
     const unsigned long long cm[4], const float* __restrict__ xr, const float* __restrict__ b, const float* __restrict__ ec,
-    float* __restrict__ x_out)
+    float* __restrict__ x_out, int64_t next)
 {
     constexpr int RG = UP_RG, HR = UP_HR;
     constexpr unsigned KM = Par<RG>::KM, EV = Par<RG>::EV, OD = Par<RG>::OD;
     const bool live = lane < 30;
     const int g = live ? lane / 10 : 2, q = live ? lane - 10 * g : 9;
     const int row0 = RG * g;
-    const unsigned liv = live ? KM : 0u;  // 3 x 12 rows are exactly the 36-row frame
+    const unsigned liv = (live ? KM : 0u) & alive;  // 3 x 12 rows are exactly the 36-row frame
     const unsigned c0 = (unsigned)(cm[0] >> row0) & liv, c1 = (unsigned)(cm[1] >> row0) & liv;
     const unsigned c2 = (unsigned)(cm[2] >> row0) & liv, c3 = (unsigned)(cm[3] >> row0) & liv;
     const unsigned anyq = c0 | c1 | c2 | c3;
@@ -289,7 +332,7 @@ __device__ __forceinline__ float rbw_up_tile(const Level& lf, int64_t cpitch, in
     const unsigned kA = (c1 & EV) | (c0 & OD), kB = (c3 & EV) | (c2 & OD);
     // unknown bits of the coarse cells the lane interpolates from: coarse row m (m = 0 .. RG / 2) <-> frame row row0 + 2 m,
     // coarse columns <-> quad columns 0 and 2
-    const unsigned cc = live ? (unsigned)(((cm[0] | cm[2]) >> row0) & ((1u << (RG + 1)) - 1)) : 0u;
+    const unsigned cc = (live ? (unsigned)(((cm[0] | cm[2]) >> row0) & ((1u << (RG + 1)) - 1)) : 0u) & alive;
     const int pitch = (int)lf.pitch;
     const int64_t gr = (int64_t)ty * TILE_H - HR, gc = (int64_t)tx * TILE_W - HC;
     const int64_t toff = (gr + row0) * lf.pitch + gc + 4 * q;
@@ -303,8 +346,8 @@ __device__ __forceinline__ float rbw_up_tile(const Level& lf, int64_t cpitch, in
         unsigned long long bp = (unsigned long long)(b + toff), wp = (unsigned long long)(WMODE == 1 ? lf.winv + toff : nullptr);
 #pragma unroll
         for (int k = 0; k < RG; ++k, xp += pb2, bp += pb, wp += pb) {
-            const float2 x2 = ldg2_ifw((const float*)xp, ((rA | rB) >> k) & 1);
-            const float4 t = ldg4_if((const float*)bp, (anyq >> k) & 1);
+            const float2 x2 = ldg2_ifw((const float*)xp, rA | rB, 1u << k);
+            const float4 t = ldg4_if((const float*)bp, anyq, 1u << k);
             bv[k][0] = t.x, bv[k][1] = t.y, bv[k][2] = t.z, bv[k][3] = t.w;
             // the red cells of the row: columns (k & 1) and 2 + (k & 1)
             v[k][k & 1] = x2.x;
@@ -312,7 +355,7 @@ __device__ __forceinline__ float rbw_up_tile(const Level& lf, int64_t cpitch, in
             v[k][1 - (k & 1)] = 0.f;
             v[k][3 - (k & 1)] = 0.f;
             if (WMODE == 1) {
-                const float4 w = ldg4_if((const float*)wp, (anyq >> k) & 1);
+                const float4 w = ldg4_if((const float*)wp, anyq, 1u << k);
                 wv[k][0] = w.x, wv[k][1] = w.y, wv[k][2] = w.z, wv[k][3] = w.w;
             }
         }
@@ -322,7 +365,16 @@ __device__ __forceinline__ float rbw_up_tile(const Level& lf, int64_t cpitch, in
         const unsigned long long cb2 = (unsigned long long)cpitch * sizeof(float);
 #pragma unroll
         for (int m = 0; m <= RG / 2; ++m, ep += cb2)
-            e[m] = ldg2_ifw((const float*)ep, (cc >> (2 * m)) & 1);
+            e[m] = ldg2_ifw((const float*)ep, cc, 1u << (2 * m));
+        if (SATFILL_RBW_PREFETCH && next) {
+            unsigned long long nb = (unsigned long long)(b + toff + next);
+            unsigned long long nx = (unsigned long long)(xr + (gr + row0) * (int64_t)(pitch >> 1) + (gc >> 1) + 2 * q + (next >> 1));
+#pragma unroll
+            for (int k = 0; k < RG; ++k, nb += pb, nx += pb2) {
+                prefetch_l2_if((const void*)nb, anyq, 1u << k);
+                prefetch_l2_if((const void*)nx, rA | rB, 1u << k);
+            }
+        }
     }
     // ---- x = x_red + P e at the red cells (the frame's row / column parity is the global one).  Even rows: the red cells
     //      sit on coarse points; odd rows: in the middle of four, the easternmost of them the next lane's first.
@@ -331,14 +383,14 @@ __device__ __forceinline__ float rbw_up_tile(const Level& lf, int64_t cpitch, in
         for (int k = 0; k < RG; ++k) {
             const int m = k >> 1;
             if ((k & 1) == 0) {
-                v[k][0] = ((rA >> k) & 1) ? v[k][0] + e[m].x : 0.f;
-                v[k][2] = ((rB >> k) & 1) ? v[k][2] + e[m].y : 0.f;
+                v[k][0] = keep<false>(rA, k, v[k][0] + e[m].x);
+                v[k][2] = keep<false>(rB, k, v[k][2] + e[m].y);
             } else {
                 const float ex0 = __shfl_down_sync(FULLW, e[m].x, 1), ex1 = __shfl_down_sync(FULLW, e[m + 1].x, 1);
                 const float pa = 0.25f * ((e[m].x + e[m].y) + (e[m + 1].x + e[m + 1].y));
                 const float pb_ = 0.25f * ((e[m].y + ex0) + (e[m + 1].y + ex1));
-                v[k][1] = ((rA >> k) & 1) ? v[k][1] + pa : 0.f;
-                v[k][3] = ((rB >> k) & 1) ? v[k][3] + pb_ : 0.f;
+                v[k][1] = keep<false>(rA, k, v[k][1] + pa);
+                v[k][3] = keep<false>(rB, k, v[k][3] + pb_);
             }
         }
     }
@@ -358,21 +410,17 @@ __device__ __forceinline__ float rbw_up_tile(const Level& lf, int64_t cpitch, in
                 const float na = k > 0 ? v[k > 0 ? k - 1 : 0][1] : n1, nb = k > 0 ? v[k > 0 ? k - 1 : 0][3] : n3;
                 xa = W(k, 1) * (bv[k][1] + ((na + v[k + 1][1]) + (v[k][0] + v[k][2])));
                 xb = W(k, 3) * (bv[k][3] + ((nb + v[k + 1][3]) + (v[k][2] + ee)));
-                xa = ((kA >> k) & 1) ? xa : 0.f;
-                xb = ((kB >> k) & 1) ? xb : 0.f;
+                xa = keep<WMODE == 1>(kA, k, xa);
+                xb = keep<WMODE == 1>(kB, k, xb);
                 v[k][1] = xa, v[k][3] = xb;
-                if (DOT)
-                    acc += ((own_rows >> k) & 1) ? fmaf(bv[k][1], xa, bv[k][3] * xb) : 0.f;
             } else {
                 const float ww = __shfl_up_sync(FULLW, v[k][3], 1);
                 const float sa = k < RG - 1 ? v[k < RG - 1 ? k + 1 : k][0] : s0, sb = k < RG - 1 ? v[k < RG - 1 ? k + 1 : k][2] : s2;
                 xa = W(k, 0) * (bv[k][0] + ((v[k - 1][0] + sa) + (ww + v[k][1])));
                 xb = W(k, 2) * (bv[k][2] + ((v[k - 1][2] + sb) + (v[k][1] + v[k][3])));
-                xa = ((kA >> k) & 1) ? xa : 0.f;
-                xb = ((kB >> k) & 1) ? xb : 0.f;
+                xa = keep<WMODE == 1>(kA, k, xa);
+                xb = keep<WMODE == 1>(kB, k, xb);
                 v[k][0] = xa, v[k][2] = xb;
-                if (DOT)
-                    acc += ((own_rows >> k) & 1) ? fmaf(bv[k][0], xa, bv[k][2] * xb) : 0.f;
             }
         }
     }
@@ -391,21 +439,21 @@ __device__ __forceinline__ float rbw_up_tile(const Level& lf, int64_t cpitch, in
                 const float na = k > 0 ? v[k > 0 ? k - 1 : 0][0] : n0, nb = k > 0 ? v[k > 0 ? k - 1 : 0][2] : n2;
                 xa = W(k, 0) * (bv[k][0] + ((na + v[k + 1][0]) + (ww + v[k][1])));
                 xb = W(k, 2) * (bv[k][2] + ((nb + v[k + 1][2]) + (v[k][1] + v[k][3])));
-                xa = ((rA >> k) & 1) ? xa : 0.f;
-                xb = ((rB >> k) & 1) ? xb : 0.f;
-                if (DOT)
-                    acc += ((own_rows >> k) & 1) ? fmaf(bv[k][0], xa, bv[k][2] * xb) : 0.f;
-                stg4_if((float*)xo, xa, v[k][1], xb, v[k][3], (st >> k) & 1);
+                xa = keep<WMODE == 1>(rA, k, xa);
+                xb = keep<WMODE == 1>(rB, k, xb);
+                if (DOT)  // b . x over the whole quad row: both colours are final here
+                    acc += keep<false>(own_rows, k, fmaf(bv[k][0], xa, bv[k][1] * v[k][1]) + fmaf(bv[k][2], xb, bv[k][3] * v[k][3]));
+                stg4_if((float*)xo, xa, v[k][1], xb, v[k][3], st, 1u << k);
             } else {
                 const float ee = __shfl_down_sync(FULLW, v[k][0], 1);
                 const float sa = k < RG - 1 ? v[k < RG - 1 ? k + 1 : k][1] : s1, sb = k < RG - 1 ? v[k < RG - 1 ? k + 1 : k][3] : s3;
                 xa = W(k, 1) * (bv[k][1] + ((v[k - 1][1] + sa) + (v[k][0] + v[k][2])));
                 xb = W(k, 3) * (bv[k][3] + ((v[k - 1][3] + sb) + (v[k][2] + ee)));
-                xa = ((rA >> k) & 1) ? xa : 0.f;
-                xb = ((rB >> k) & 1) ? xb : 0.f;
+                xa = keep<WMODE == 1>(rA, k, xa);
+                xb = keep<WMODE == 1>(rB, k, xb);
                 if (DOT)
-                    acc += ((own_rows >> k) & 1) ? fmaf(bv[k][1], xa, bv[k][3] * xb) : 0.f;
-                stg4_if((float*)xo, v[k][0], xa, v[k][2], xb, (st >> k) & 1);
+                    acc += keep<false>(own_rows, k, fmaf(bv[k][1], xa, bv[k][0] * v[k][0]) + fmaf(bv[k][3], xb, bv[k][2] * v[k][2]));
+                stg4_if((float*)xo, v[k][0], xa, v[k][2], xb, st, 1u << k);
             }
         }
     }
@@ -413,17 +461,33 @@ __device__ __forceinline__ float rbw_up_tile(const Level& lf, int64_t cpitch, in
 }
 
 // Work items of a level: (tile, chunk of bands), tile-major, so that consecutive warps work on neighbouring tiles.
+// band_major: item = (band, tile), band-major -- the whole GPU sweeps one band's planes at a time (a level-0 plane of the
+// benchmark tile is 0.5 GB: with the bands as the inner loop every warp touches a different 2 MB page per iteration and
+// array; the first-generation kernels, one CTA per tile and band with the band in blockIdx.y, had this order for free).
 struct Items {
-    int n_tiles, nbands, bchunk, nchunks;
-    __host__ __device__ int count() const { return n_tiles * nchunks; }
+    int n_tiles, nbands, bchunk, nchunks, band_major;
+    __host__ __device__ int count() const { return band_major ? n_tiles * nbands : n_tiles * nchunks; }
+    // item -> tile index and band range
+    __device__ __forceinline__ void at(int i, int& ti, int& b0, int& b1) const
+    {
+        if (band_major) {
+            b0 = i / n_tiles;
+            ti = i - b0 * n_tiles;
+            b1 = b0 + 1;
+        } else {
+            ti = i / nchunks;
+            b0 = (i - ti * nchunks) * bchunk;
+            b1 = min(nbands, b0 + bchunk);
+        }
+    }
 };
-inline Items make_items(int n_tiles, int nbands, int total_warps)
+inline Items make_items(int n_tiles, int nbands, int total_warps, bool band_major)
 {
     // as many bands per item as still leave every warp a few items (the column masks of a tile serve the whole chunk)
     int bchunk = nbands;
     while (bchunk > 1 && (int64_t)n_tiles * ((nbands + bchunk - 1) / bchunk) < 3 * (int64_t)total_warps)
         bchunk = (bchunk + 1) / 2;
-    return Items { n_tiles, nbands, bchunk, (nbands + bchunk - 1) / bchunk };
+    return Items { n_tiles, nbands, bchunk, (nbands + bchunk - 1) / bchunk, band_major ? 1 : 0 };
 }
 
 template <int WMODE>
@@ -432,27 +496,27 @@ __device__ __forceinline__ void rbw_down_items(const Level& lf, const Level& lc,
 {
     const int n = it.count();
     for (int i = first; i < n; i += stride) {
-        const int ti = i / it.nchunks, ch = i - ti * it.nchunks;
+        int ti, b0, b1;
+        it.at(i, ti, b0, b1);
         const int yx = lf.tile_yx[ti];
         const int ty = yx >> 16, tx = yx & 0xffff;
         unsigned long long cm[4];
         quad_col_masks<DN_HR>(lf, ty, tx, lane < 30 ? lane % 10 : 9, cm);
-        const int b1 = min(it.nbands, (ch + 1) * it.bchunk);
-        for (int band = ch * it.bchunk; band < b1; ++band) {
-            if (scal[band].done)
-                continue;
+        for (int band = b0; band < b1; ++band) {
+            const unsigned alive = scal[band].done ? 0u : ~0u;
+            const int64_t next = band + 1 < b1 ? lf.plane : 0;
             if (WMODE == 2) {
                 // 1 / d is 1 / 4 unless the frame touches the image border (warp-uniform)
                 const bool inner = ty > 0 && tx > 0 && (int64_t)(ty + 1) * TILE_H + DN_HR < lf.rows && (int64_t)(tx + 1) * TILE_W + HC < lf.cols;
                 if (inner)
-                    rbw_down_tile<0>(lf, lc.pitch, ty, tx, lane, cm, b + (int64_t)band * lf.plane, xr + (int64_t)band * (lf.plane >> 1),
-                        bc + (int64_t)band * lc.plane);
+                    rbw_down_tile<0>(lf, lc.pitch, ty, tx, lane, alive, cm, b + (int64_t)band * lf.plane, xr + (int64_t)band * (lf.plane >> 1),
+                        bc + (int64_t)band * lc.plane, next);
                 else
-                    rbw_down_tile<2>(lf, lc.pitch, ty, tx, lane, cm, b + (int64_t)band * lf.plane, xr + (int64_t)band * (lf.plane >> 1),
-                        bc + (int64_t)band * lc.plane);
+                    rbw_down_tile<2>(lf, lc.pitch, ty, tx, lane, alive, cm, b + (int64_t)band * lf.plane, xr + (int64_t)band * (lf.plane >> 1),
+                        bc + (int64_t)band * lc.plane, next);
             } else {
-                rbw_down_tile<WMODE>(lf, lc.pitch, ty, tx, lane, cm, b + (int64_t)band * lf.plane, xr + (int64_t)band * (lf.plane >> 1),
-                    bc + (int64_t)band * lc.plane);
+                rbw_down_tile<WMODE>(lf, lc.pitch, ty, tx, lane, alive, cm, b + (int64_t)band * lf.plane, xr + (int64_t)band * (lf.plane >> 1),
+                    bc + (int64_t)band * lc.plane, next);
             }
         }
     }
@@ -466,26 +530,26 @@ __device__ __forceinline__ void rbw_up_items(const Level& lf, const Level& lc, c
 {
     const int n = it.count();
     for (int i = first; i < n; i += stride) {
-        const int ti = i / it.nchunks, ch = i - ti * it.nchunks;
+        int ti, b0, b1;
+        it.at(i, ti, b0, b1);
         const int yx = lf.tile_yx[ti];
         const int ty = yx >> 16, tx = yx & 0xffff;
         unsigned long long cm[4];
         quad_col_masks<UP_HR>(lf, ty, tx, lane < 30 ? lane % 10 : 9, cm);
-        const int b1 = min(it.nbands, (ch + 1) * it.bchunk);
-        for (int band = ch * it.bchunk; band < b1; ++band) {
-            if (scal[band].done)
-                continue;
+        for (int band = b0; band < b1; ++band) {
+            const unsigned alive = scal[band].done ? 0u : ~0u;
             const float* xrb = xr + (int64_t)band * (lf.plane >> 1);
             const float* bb = b + (int64_t)band * lf.plane;
             const float* eb = ec + (int64_t)band * lc.plane;
             float* xb = x_out + (int64_t)band * lf.plane;
+            const int64_t next = band + 1 < b1 ? lf.plane : 0;
             float acc;
             if (WMODE == 2) {
                 const bool inner = ty > 0 && tx > 0 && (int64_t)(ty + 1) * TILE_H + UP_HR < lf.rows && (int64_t)(tx + 1) * TILE_W + HC < lf.cols;
-                acc = inner ? rbw_up_tile<0, DOT>(lf, lc.pitch, ty, tx, lane, cm, xrb, bb, eb, xb)
-                            : rbw_up_tile<2, DOT>(lf, lc.pitch, ty, tx, lane, cm, xrb, bb, eb, xb);
+                acc = inner ? rbw_up_tile<0, DOT>(lf, lc.pitch, ty, tx, lane, alive, cm, xrb, bb, eb, xb, next)
+                            : rbw_up_tile<2, DOT>(lf, lc.pitch, ty, tx, lane, alive, cm, xrb, bb, eb, xb, next);
             } else {
-                acc = rbw_up_tile<WMODE, DOT>(lf, lc.pitch, ty, tx, lane, cm, xrb, bb, eb, xb);
+                acc = rbw_up_tile<WMODE, DOT>(lf, lc.pitch, ty, tx, lane, alive, cm, xrb, bb, eb, xb, next);
             }
             if (DOT) {
                 // a few dozen products per lane in float, everything above that in double
@@ -505,27 +569,29 @@ __device__ __forceinline__ void rbw_up_items(const Level& lf, const Level& lc, c
 // ---------------------------------------------------------------------------------------------------------------
 // one level per launch (the levels that fill the GPU)
 // ---------------------------------------------------------------------------------------------------------------
+// CTAs of ONE warp: item indices then depend on blockIdx only, the compiler sees every loop as uniform and emits the warp
+// shuffles bare (with several warps per CTA the warp index comes from threadIdx and every shuffle gets a WARPSYNC /
+// ENDCOLLECTIVE pair: ~100 of 1700 instructions per tile).
 template <int WMODE>
-__global__ void __launch_bounds__(RW_THREADS, WMODE == 0 ? 4 : 3) k_rbw_down(Level lf, Level lc, Items it, const float* __restrict__ b,
-    float* __restrict__ xr, float* __restrict__ bc, const BandScalars* __restrict__ scal)
+__global__ void __launch_bounds__(32, WMODE == 0 ? RBW_DOWN_CTAS : RBW_W_CTAS) k_rbw_down(Level lf, Level lc, Items it,
+    const float* __restrict__ b, float* __restrict__ xr, float* __restrict__ bc, const BandScalars* __restrict__ scal)
 {
-    const int lane = threadIdx.x & 31, wg = (int)blockIdx.x * RW_WARPS + (threadIdx.x >> 5);
-    rbw_down_items<WMODE>(lf, lc, it, wg, (int)gridDim.x * RW_WARPS, lane, b, xr, bc, scal);
+    rbw_down_items<WMODE>(lf, lc, it, (int)blockIdx.x, (int)gridDim.x, (int)threadIdx.x, b, xr, bc, scal);
 }
 
 template <int WMODE, bool DOT>
-__global__ void __launch_bounds__(RW_THREADS, WMODE == 0 ? 4 : 3) k_rbw_up(Level lf, Level lc, Items it, const float* __restrict__ xr,
-    const float* __restrict__ b, const float* __restrict__ ec, float* __restrict__ x_out, BandScalars* __restrict__ scal, int slot)
+__global__ void __launch_bounds__(32, WMODE == 0 ? RBW_UP_CTAS : RBW_W_CTAS) k_rbw_up(Level lf, Level lc, Items it,
+    const float* __restrict__ xr, const float* __restrict__ b, const float* __restrict__ ec, float* __restrict__ x_out,
+    BandScalars* __restrict__ scal, int slot)
 {
-    extern __shared__ double s_acc_all[];  // RW_WARPS x nbands (DOT only)
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wg = (int)blockIdx.x * RW_WARPS + warp;
-    double* s_acc = s_acc_all + (size_t)warp * it.nbands;
+    extern __shared__ double s_acc[];  // nbands partial sums of b . x (DOT only)
+    const int lane = (int)threadIdx.x;
     if (DOT) {
         for (int i = lane; i < it.nbands; i += 32)
             s_acc[i] = 0.0;
         __syncwarp();
     }
-    rbw_up_items<WMODE, DOT>(lf, lc, it, wg, (int)gridDim.x * RW_WARPS, lane, xr, b, ec, x_out, scal, s_acc);
+    rbw_up_items<WMODE, DOT>(lf, lc, it, (int)blockIdx.x, (int)gridDim.x, lane, xr, b, ec, x_out, scal, s_acc);
     if (DOT) {
         __syncwarp();
         for (int i = lane; i < it.nbands; i += 32)
@@ -572,12 +638,61 @@ __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& epoch)
     __syncthreads();
 }
 
-// K forward (red, black) then K reverse (black, red) Gauss-Seidel sweeps from zero on the coarsest level, in place in
-// global memory: the CTA's own writes are visible to its threads after __syncthreads().
+// K forward (red, black) then K reverse (black, red) Gauss-Seidel sweeps from zero on the coarsest level.  One active tile
+// (every scene that is not extremely elongated): the tile lives in shared memory with a zero ring (`sm`: 3 x 34 x 34
+// floats), 1 / d zero at every cell that is not an unknown, so a half-sweep is branch free and costs one barrier instead
+// of a round trip to L2 per cell.  Otherwise in place in global memory: the CTA's own writes are visible to its threads
+// after __syncthreads().
+constexpr int CP = TILE_W + 2;
 template <bool DOT>
 __device__ void rbw_coarsest(const Level& lv, bool fixed, const float* __restrict__ bb, float* __restrict__ xb, int sweeps,
-    double* dot_out)
+    double* dot_out, float* sm)
 {
+    if (lv.n_tiles == 1) {
+        const int t = threadIdx.x, nt = blockDim.x;
+        float *sx = sm, *sb = sm + CP * CP, *sw = sm + 2 * CP * CP;
+        const int tile = lv.tile_list[0];
+        const int64_t r0 = (int64_t)(tile / lv.tiles_x) * TILE_H, c0 = (int64_t)(tile % lv.tiles_x) * TILE_W;
+        __syncthreads();  // the previous band's solve is over
+        for (int i = t; i < 3 * CP * CP; i += nt)
+            sm[i] = 0.f;
+        __syncthreads();
+        for (int i = t; i < TILE_H * TILE_W; i += nt) {
+            const int lr = i >> 5, lc = i & 31;
+            const int64_t idx = (r0 + lr) * lv.pitch + c0 + lc;
+            if (lv.umask[idx]) {
+                sb[(lr + 1) * CP + lc + 1] = bb[idx];
+                sw[(lr + 1) * CP + lc + 1] = lv.winv ? lv.winv[idx] : (fixed ? 0.25f : winv_of<false>(lv, r0 + lr, c0 + lc));
+            }
+        }
+        __syncthreads();
+        for (int hs = 0; hs < 4 * sweeps; ++hs) {
+            const int colour = hs < 2 * sweeps ? (hs & 1) : 1 - (hs & 1);  // 0 = red = (row + column) even
+            for (int i = t; i < TILE_H * TILE_W / 2; i += nt) {
+                const int lr = i >> 4, lc = 2 * (i & 15) + ((lr + colour) & 1);
+                const int p = (lr + 1) * CP + lc + 1;
+                sx[p] = sw[p] * (sb[p] + ((sx[p - CP] + sx[p + CP]) + (sx[p - 1] + sx[p + 1])));
+            }
+            __syncthreads();
+        }
+        double acc = 0.0;
+        for (int i = t; i < TILE_H * TILE_W; i += nt) {
+            const int lr = i >> 5, lc = i & 31;
+            const int64_t idx = (r0 + lr) * lv.pitch + c0 + lc;
+            const int p = (lr + 1) * CP + lc + 1;
+            if (sw[p] != 0.f) {
+                xb[idx] = sx[p];
+                acc += (double)sb[p] * (double)sx[p];
+            }
+        }
+        if (DOT) {
+            for (int o = 16; o; o >>= 1)
+                acc += __shfl_xor_sync(FULLW, acc, o);
+            if ((t & 31) == 0 && acc != 0.0)
+                atomicAdd(dot_out, acc);
+        }
+        return;
+    }
     const int t = threadIdx.x, nt = blockDim.x;
     const int cells = lv.n_tiles * (TILE_H * TILE_W);
     for (int i = t; i < cells; i += nt) {
@@ -620,6 +735,7 @@ __device__ void rbw_coarsest(const Level& lv, bool fixed, const float* __restric
 
 __global__ void __launch_bounds__(RW_THREADS, 3) k_rbw_tail(TailArgs A, BandScalars* __restrict__ scal, unsigned* __restrict__ barrier)
 {
+    __shared__ float s_coarsest[3 * CP * CP];
     const int lane = threadIdx.x & 31, wg = (int)blockIdx.x * RW_WARPS + (threadIdx.x >> 5);
     const int stride = (int)gridDim.x * RW_WARPS;
     unsigned epoch = 0;
@@ -632,7 +748,7 @@ __global__ void __launch_bounds__(RW_THREADS, 3) k_rbw_tail(TailArgs A, BandScal
         for (int band = blockIdx.x; band < A.nbands; band += gridDim.x)
             if (!scal[band].done)
                 rbw_coarsest<false>(C.lv, A.fixed != 0, C.b + (int64_t)band * C.lv.plane, C.x + (int64_t)band * C.lv.plane, A.sweeps,
-                    nullptr);
+                    nullptr, s_coarsest);
     }
     for (int l = A.n - 2; l >= 0; --l) {
         grid_barrier(barrier, epoch);
@@ -645,10 +761,11 @@ __global__ void __launch_bounds__(RW_THREADS, 3) k_rbw_tail(TailArgs A, BandScal
 __global__ void __launch_bounds__(RW_THREADS) k_rbw_coarsest_only(Level lv, int fixed, const float* __restrict__ b, float* __restrict__ x,
     BandScalars* __restrict__ scal, int slot, int sweeps)
 {
+    __shared__ float s_coarsest[3 * CP * CP];
     if (scal[blockIdx.x].done)
         return;
     rbw_coarsest<true>(lv, fixed != 0, b + (int64_t)blockIdx.x * lv.plane, x + (int64_t)blockIdx.x * lv.plane, sweeps,
-        &scal[blockIdx.x].rz[slot]);
+        &scal[blockIdx.x].rz[slot], s_coarsest);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -672,12 +789,19 @@ int env_int(const char* name, int dflt)
 
 int wmode_of(const Level& lv) { return lv.winv ? 1 : (lv.fixed_diag ? 0 : 2); }
 
+// band-major item order for levels whose band plane is larger than `SATFILL_RBW_BAND_MAJOR_MB` MB (default 256: level 0 of a 10980^2 tile)
+bool band_major_for(const Level& lv)
+{
+    static const int mb = env_int("SATFILL_RBW_BAND_MAJOR_MB", 256);
+    return mb >= 0 && (int64_t)lv.plane * (int64_t)sizeof(float) > (int64_t)mb << 20;
+}
+
 // resident CTAs per SM of a kernel (cached per kernel function)
 template <typename K>
-int ctas_per_sm(K kernel, size_t smem)
+int ctas_per_sm(K kernel, size_t smem, int threads)
 {
     int n = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, RW_THREADS, smem) != cudaSuccess || n < 1)
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, threads, smem) != cudaSuccess || n < 1)
         n = 1;
     return n;
 }
@@ -689,17 +813,16 @@ int launch_down_w(sa_ctx* ctx, const RWLevel& F, const RWLevel& C, int nb, const
     const int mode = wmode_of(F.lv);
     static int occ[3] = { 0, 0, 0 };
     if (!occ[mode])
-        occ[mode] = mode == 0 ? ctas_per_sm(k_rbw_down<0>, 0) : (mode == 1 ? ctas_per_sm(k_rbw_down<1>, 0) : ctas_per_sm(k_rbw_down<2>, 0));
-    const int max_ctas = ctx->sm_count * occ[mode];
-    const Items it = make_items(F.lv.n_tiles, nb, max_ctas * RW_WARPS);
-    const int want = (it.count() + RW_WARPS - 1) / RW_WARPS;
-    const unsigned grid = (unsigned)(want < max_ctas ? want : max_ctas);
+        occ[mode] = mode == 0 ? ctas_per_sm(k_rbw_down<0>, 0, 32) : (mode == 1 ? ctas_per_sm(k_rbw_down<1>, 0, 32) : ctas_per_sm(k_rbw_down<2>, 0, 32));
+    const int max_ctas = ctx->sm_count * occ[mode];  // one warp each
+    const Items it = make_items(F.lv.n_tiles, nb, max_ctas, band_major_for(F.lv));
+    const unsigned grid = (unsigned)(it.count() < max_ctas ? it.count() : max_ctas);
     if (mode == 0)
-        SA_LAUNCH(ctx, k_rbw_down<0>, grid, RW_THREADS, 0, F.lv, C.lv, it, F.b, F.xr, C.b, scal);
+        SA_LAUNCH(ctx, k_rbw_down<0>, grid, 32, 0, F.lv, C.lv, it, F.b, F.xr, C.b, scal);
     else if (mode == 1)
-        SA_LAUNCH(ctx, k_rbw_down<1>, grid, RW_THREADS, 0, F.lv, C.lv, it, F.b, F.xr, C.b, scal);
+        SA_LAUNCH(ctx, k_rbw_down<1>, grid, 32, 0, F.lv, C.lv, it, F.b, F.xr, C.b, scal);
     else
-        SA_LAUNCH(ctx, k_rbw_down<2>, grid, RW_THREADS, 0, F.lv, C.lv, it, F.b, F.xr, C.b, scal);
+        SA_LAUNCH(ctx, k_rbw_down<2>, grid, 32, 0, F.lv, C.lv, it, F.b, F.xr, C.b, scal);
     return SA_OK;
 }
 
@@ -709,23 +832,22 @@ int launch_up_w(sa_ctx* ctx, const RWLevel& F, const RWLevel& C, int nb, BandSca
     if (F.lv.n_tiles == 0)
         return SA_OK;
     const int mode = wmode_of(F.lv);
-    const size_t smem = DOT ? sizeof(double) * RW_WARPS * (size_t)nb : 0;
+    const size_t smem = DOT ? sizeof(double) * (size_t)nb : 0;
     static int occ[3] = { 0, 0, 0 };
     static size_t occ_smem[3] = { 0, 0, 0 };
     if (!occ[mode] || occ_smem[mode] != smem) {
-        occ[mode] = mode == 0 ? ctas_per_sm(k_rbw_up<0, DOT>, smem) : (mode == 1 ? ctas_per_sm(k_rbw_up<1, DOT>, smem) : ctas_per_sm(k_rbw_up<2, DOT>, smem));
+        occ[mode] = mode == 0 ? ctas_per_sm(k_rbw_up<0, DOT>, smem, 32) : (mode == 1 ? ctas_per_sm(k_rbw_up<1, DOT>, smem, 32) : ctas_per_sm(k_rbw_up<2, DOT>, smem, 32));
         occ_smem[mode] = smem;
     }
-    const int max_ctas = ctx->sm_count * occ[mode];
-    const Items it = make_items(F.lv.n_tiles, nb, max_ctas * RW_WARPS);
-    const int want = (it.count() + RW_WARPS - 1) / RW_WARPS;
-    const unsigned grid = (unsigned)(want < max_ctas ? want : max_ctas);
+    const int max_ctas = ctx->sm_count * occ[mode];  // one warp each
+    const Items it = make_items(F.lv.n_tiles, nb, max_ctas, band_major_for(F.lv));
+    const unsigned grid = (unsigned)(it.count() < max_ctas ? it.count() : max_ctas);
     if (mode == 0)
-        SA_LAUNCH(ctx, (k_rbw_up<0, DOT>), grid, RW_THREADS, smem, F.lv, C.lv, it, F.xr, F.b, C.x, F.x, scal, slot);
+        SA_LAUNCH(ctx, (k_rbw_up<0, DOT>), grid, 32, smem, F.lv, C.lv, it, F.xr, F.b, C.x, F.x, scal, slot);
     else if (mode == 1)
-        SA_LAUNCH(ctx, (k_rbw_up<1, DOT>), grid, RW_THREADS, smem, F.lv, C.lv, it, F.xr, F.b, C.x, F.x, scal, slot);
+        SA_LAUNCH(ctx, (k_rbw_up<1, DOT>), grid, 32, smem, F.lv, C.lv, it, F.xr, F.b, C.x, F.x, scal, slot);
     else
-        SA_LAUNCH(ctx, (k_rbw_up<2, DOT>), grid, RW_THREADS, smem, F.lv, C.lv, it, F.xr, F.b, C.x, F.x, scal, slot);
+        SA_LAUNCH(ctx, (k_rbw_up<2, DOT>), grid, 32, smem, F.lv, C.lv, it, F.xr, F.b, C.x, F.x, scal, slot);
     return SA_OK;
 }
 
@@ -734,7 +856,7 @@ int launch_tail(sa_ctx* ctx, const std::vector<RWLevel>& L, int first, int nb, B
 {
     static int occ = 0;
     if (!occ)
-        occ = ctas_per_sm(k_rbw_tail, 0);
+        occ = ctas_per_sm(k_rbw_tail, 0, RW_THREADS);
     int tail_ctas = env_int("SATFILL_TAIL_CTAS_PER_SM", 2);
     if (tail_ctas > occ)
         tail_ctas = occ;
@@ -748,7 +870,7 @@ int launch_tail(sa_ctx* ctx, const std::vector<RWLevel>& L, int first, int nb, B
     for (int l = first; l < (int)L.size(); ++l) {
         TailLevel& T = A.L[l - first];
         T.lv = L[(size_t)l].lv;
-        T.it = make_items(T.lv.n_tiles, nb, max_ctas * RW_WARPS);
+        T.it = make_items(T.lv.n_tiles, nb, max_ctas * RW_WARPS, false);
         T.b = L[(size_t)l].b;
         T.x = L[(size_t)l].x;
         T.xr = L[(size_t)l].xr;

@@ -1,18 +1,19 @@
 #!/bin/bash
-# Lean capture (1 GPU): `ncu --set full` of the two level-0 cycle kernels on the cloud-like bench mask and on a dense hole of
-# the same size -- the pair that separates "frame halos miss in L2" from "short DRAM runs" (DESIGN.md section 10, item 1).
-#   gpurun --timeout 1200 -- 'bash tools/gpu_cycle_capture.sh r2a'
-tag=${1:-run}
+# Lean capture (1 GPU): `ncu --set full` of the level-0 cycle kernels (second V-cycle of a solve) on the bench scene, 4 bands.
+#   gpurun --timeout 1200 -- 'bash tools/gpu_cycle_capture.sh r2d [mask]'
+#   mask: "" = the bench's cloud mask, "full" = a dense hole of the same size (every tile full)
+tag=${1:-run}; mask=${2:-}
 out=gpurun_out
 mkdir -p $out
-python bench.py --steps 1 --warmup 1 --bands 4 --no-e2e --no-cpu > $out/${tag}_plain.log 2>&1
+M=""; [ -n "$mask" ] && M="--mask $mask"
+B="--steps 1 --warmup 0 --bands 4 --no-e2e --no-cpu --no-dropin --no-multi $M"
+python bench.py --steps 1 --warmup 1 --bands 4 --no-e2e --no-cpu --no-dropin --no-multi $M > $out/${tag}_plain.log 2>&1
 echo "plain rc=$?"
-for ks in k_rb_down:11 k_rb_up:21; do
-    k=${ks%%:*}; skip=${ks##*:}
-    for m in blobs full; do
-        timeout 500 ncu --set full --clock-control none --import-source on -k regex:"^${k}\$" --launch-skip $skip --launch-count 1 \
-            -f -o $out/${tag}_${m}_full_${k} python bench.py --steps 1 --warmup 0 --bands 4 --mask $m --no-e2e --no-cpu > $out/${tag}_${m}_ncu_${k}.log 2>&1
-        echo "ncu $m $k rc=$?"
-    done
+# level-0 kernels by their template arguments (second launch = second V-cycle of the solve)
+for ks in "k_rbw_down<.int.0>:down0" "k_rbw_up<.int.0, .bool.1>:up0"; do
+    k=${ks%%:*}; name=${ks##*:}
+    timeout 500 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:"${k}" --launch-skip 1 --launch-count 1 \
+        -f -o $out/${tag}_full_${name} python bench.py $B > $out/${tag}_ncu_${name}.log 2>&1
+    echo "ncu $name rc=$?"
 done
-ls -la $out | tail -12
+ls -la $out | grep ${tag}_ | tail -12

@@ -1,20 +1,23 @@
 #!/bin/bash
-# gpurun: GPU tests on the product library, then the bench line of every tuning variant given
-#   gpurun -- 'bash tools/gpu_variants.sh tag "" _u4 _u6'
+# A/B of tuning builds of libsatfill (csrc/Makefile: VARIANT=_name EXTRA=-D...): one short bench line per library.
+#   gpurun -- 'bash tools/gpu_variants.sh r2f "" _nopf _w10 _c20'
 tag=$1; shift
 out=gpurun_out; mkdir -p $out
-python -m pytest tests -m gpu -x -q 2>&1 | tail -5
+B="--steps 4 --warmup 2 --no-e2e --no-cpu --no-dropin --no-multi"
+if [ "${PYTEST:-1}" = "1" ]; then
+  timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -k "rb_preconditioner or multigrid or tiny or mask_changes" > $out/${tag}_pytest.log 2>&1
+  echo "pytest rc=$?"; tail -3 $out/${tag}_pytest.log
+fi
 for v in "$@"; do
-  lib=$PWD/satellite_approximation_b200/lib/libsatfill$v.so
-  SATFILL_LIB=$lib python bench.py --steps 2 --warmup 2 --no-e2e --no-cpu > $out/${tag}_b$v.log 2>&1
-  python - $out/${tag}_b$v.log "$v" <<'P'
+  lib=satellite_approximation_b200/lib/libsatfill$v.so
+  SATFILL_LIB=$PWD/$lib timeout 300 python bench.py $B $EXTRA_ARGS > $out/${tag}_bench$v.json 2> $out/${tag}_bench$v.err
+  echo "== variant '$v' rc=$?"
+  python - "$out/${tag}_bench$v.json" <<'PY'
 import json,sys
-for l in open(sys.argv[1]):
-    if l.startswith("{"):
-        d=json.loads(l); r=d["roofline"]["all_kernels"]
-        print("variant[%s] ms/step %.1f it %s"%(sys.argv[2], d["ms_per_step"], d["config"]["cg_iterations"]), {k[:14]:(round(v["ms"]/d["steps"],1), round(v["GBps"] or 0)) for k,v in r.items() if v["ms"]})
-        break
-else:
-    print("variant[%s] FAILED"%sys.argv[2]); print(open(sys.argv[1]).read()[-2000:])
-P
+try:
+    d=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
+    print(" ms/step", round(d["ms_per_step"],2), "iters", d["config"]["cg_iterations"][:2], "step_frac", round(d["roofline"]["step_frac"],3))
+    for k,v in d["roofline"]["all_kernels"].items(): print("   %-45s %8.1f ms %5d  %6.0f GB/s  %.3f" % (k, v["ms"], v["launches"], v["GBps"] or 0, v["frac"] or 0))
+except Exception as e: print(" failed", e)
+PY
 done
