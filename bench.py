@@ -347,10 +347,12 @@ KERNEL_NAMES_J64 = ["cg_direction (k_direction)", "cg_update (k_update)", "mg_sw
 # algorithmic bytes per unknown of the level the launch runs on:
 #   float red-black cycle: CG keeps its search direction in float and writes a float copy of r for the cycle --
 #     direction R z 4 + R p 4 + W p 4 + mask 1 = 13;  update R p 4 + R/W x 16 + R/W r 16 + W rf 4 + mask 1 = 41;
-#     down R b 4 + W x_red 4/2 + W b_c 4/4 = 7;  up R x_red 4/2 + R b 4 + R e_c 4/4 + W x 4 = 11;
-#     coarse levels also read the 1 / diagonal plane of the boundary-corrected operator: 11 and 15
+#     down R b 4 + W b_c 4/4 = 5;  up R b 4 + R e_c 4/4 + W x 4 = 9  (the red half of the pre-smoothed iterate is
+#     recomputed from b in the ascent, not carried through HBM; the first-generation kernels, --mg-variant rb32_cta, write
+#     and read it: 7 and 11);  coarse levels also read the 1 / diagonal plane of the boundary-corrected operator: + 4
 #   double Jacobi cycle: direction 25, single sweep 25, single transfer ~19, down 18, up 26
-BYTES_RB = [13.0, 41.0, 26.0, 19.0, 7.0, 11.0, 11.0, 15.0]  # [2]: the coarse tail, descent 11 + ascent 15 per unknown of its levels
+BYTES_RB = [13.0, 41.0, 22.0, 19.0, 5.0, 9.0, 9.0, 13.0]  # [2]: the coarse tail, descent 9 + ascent 13 per unknown of its levels
+BYTES_RB_CTA = [13.0, 41.0, 9.0, 19.0, 7.0, 11.0, 11.0, 15.0]  # first-generation cycle kernels (the red half plane travels)
 BYTES_J64 = [25.0, 41.0, 25.0, 19.0, 18.0, 26.0, 18.0, 26.0]
 NK = 8
 
@@ -391,8 +393,8 @@ class Timed:
         return self.ms
 
 
-def kernel_table(t: Timed, rb: bool, unit_scale=1.0):
-    names, bpu = (KERNEL_NAMES_RB, BYTES_RB) if rb else (KERNEL_NAMES_J64, BYTES_J64)
+def kernel_table(t: Timed, rb, unit_scale=1.0):
+    names, bpu = (KERNEL_NAMES_RB, BYTES_RB_CTA if rb == "cta" else BYTES_RB) if rb else (KERNEL_NAMES_J64, BYTES_J64)
     tab = {}
     for c in range(NK):
         if t.kn[c]:
@@ -494,7 +496,9 @@ def run_b200(args, w):
 
     # ---- roofline of the dominant kernel (by accumulated event time inside the timed region)
     rb = args.precond == "multigrid" and args.mg_variant != "jacobi64"
-    names, bpu = (KERNEL_NAMES_RB, BYTES_RB) if rb else (KERNEL_NAMES_J64, BYTES_J64)
+    if rb and args.mg_variant == "rb32_cta":
+        rb = "cta"
+    names, bpu = (KERNEL_NAMES_RB, BYTES_RB_CTA if rb == "cta" else BYTES_RB) if rb else (KERNEL_NAMES_J64, BYTES_J64)
     kms, kn, ku = timed.kms, timed.kn, [u * unit_scale for u in timed.ku]
     dom = max(range(NK), key=lambda c: kms[c])
     peak, peak_src = peaks()

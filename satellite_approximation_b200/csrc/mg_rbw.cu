@@ -169,7 +169,7 @@ struct Par {
 // ---------------------------------------------------------------------------------------------------------------
 template <int WMODE>
 __device__ __forceinline__ void rbw_down_tile(const Level& lf, int64_t cpitch, int ty, int tx, int lane, unsigned alive,
-    const unsigned long long cm[4], const float* __restrict__ b, float* __restrict__ xr, float* __restrict__ bc, int64_t next)
+    const unsigned long long cm[4], const float* __restrict__ b, float* __restrict__ bc, int64_t next)
 {
     constexpr int RG = DN_RG, HR = DN_HR;
     constexpr unsigned KM = Par<RG>::KM, EV = Par<RG>::EV, OD = Par<RG>::OD;
@@ -211,22 +211,17 @@ __device__ __forceinline__ void rbw_down_tile(const Level& lf, int64_t cpitch, i
                 prefetch_l2_if((const void*)np, anyq, 1u << k);
         }
     }
-    // ---- red half-sweep from zero: x = b / d.  The tile's own red cells go to HBM colour-split: the two red cells of a
-    //      quad row are neighbours in the half plane.
+    // ---- red half-sweep from zero: x = b / d, pointwise.  Nothing of it is stored: the ascent recomputes it from the same
+    //      b with the same multiplication (the first generation carried the red half of the iterate through HBM: 2 B
+    //      written and 2 B read per unknown and level, a fifth of the cycle's traffic).
     {
-        const bool ownq = q >= 1 && q <= 8;
-        const unsigned own_rows = ((((1ull << (HR + TILE_H)) - 1) & ~((1ull << HR) - 1)) >> row0) & KM;
-        const unsigned st = ownq ? ((rA | rB) & own_rows) : 0u;
-        unsigned long long xo = (unsigned long long)(xr + (gr + row0) * (int64_t)(pitch >> 1) + (gc >> 1) + 2 * q);
-        const unsigned long long pb2 = pb >> 1;
 #pragma unroll
-        for (int k = 0; k < RG; ++k, xo += pb2) {
+        for (int k = 0; k < RG; ++k) {
             const int j0 = k & 1, j1 = 2 + (k & 1);
             // masked like every other cell update: the cycle's vectors are only ever trusted at the unknowns of the CURRENT
             // mask (a mask change leaves them unscrubbed: cg.cu, stale_rb)
             v[k][j0] = keep<WMODE == 1>(rA, k, v[k][j0] * W(k, j0));
             v[k][j1] = keep<WMODE == 1>(rB, k, v[k][j1] * W(k, j1));
-            stg2_ifw((float*)xo, v[k][j0], v[k][j1], st, 1u << k);
         }
     }
     // ---- black half-sweep (in place: a black update reads red cells only)
@@ -316,8 +311,7 @@ __device__ __forceinline__ void rbw_down_tile(const Level& lf, int64_t cpitch, i
 // ---------------------------------------------------------------------------------------------------------------
 template <int WMODE, bool DOT>
 __device__ __forceinline__ float rbw_up_tile(const Level& lf, int64_t cpitch, int ty, int tx, int lane, unsigned alive,
-    const unsigned long long cm[4], const float* __restrict__ xr, const float* __restrict__ b, const float* __restrict__ ec,
-    float* __restrict__ x_out, int64_t next)
+    const unsigned long long cm[4], const float* __restrict__ b, const float* __restrict__ ec, float* __restrict__ x_out, int64_t next)
 {
     constexpr int RG = UP_RG, HR = UP_HR;
     constexpr unsigned KM = Par<RG>::KM, EV = Par<RG>::EV, OD = Par<RG>::OD;
@@ -336,24 +330,17 @@ __device__ __forceinline__ float rbw_up_tile(const Level& lf, int64_t cpitch, in
     const int pitch = (int)lf.pitch;
     const int64_t gr = (int64_t)ty * TILE_H - HR, gc = (int64_t)tx * TILE_W - HC;
     const int64_t toff = (gr + row0) * lf.pitch + gc + 4 * q;
-    const unsigned long long pb = (unsigned long long)pitch * sizeof(float), pb2 = pb >> 1;
+    const unsigned long long pb = (unsigned long long)pitch * sizeof(float);
     float v[RG][4], bv[RG][4], wv[WMODE == 1 ? RG : 1][4];
     float2 e[RG / 2 + 1];
     const WCoord wc(lf, gr + row0, gc + 4 * q);
     auto W = [&](int k, int j) -> float { return WMODE == 0 ? 0.25f : (WMODE == 1 ? wv[WMODE == 1 ? k : 0][j] : wc.at(k, j)); };
     {
-        unsigned long long xp = (unsigned long long)(xr + (gr + row0) * (int64_t)(pitch >> 1) + (gc >> 1) + 2 * q);
         unsigned long long bp = (unsigned long long)(b + toff), wp = (unsigned long long)(WMODE == 1 ? lf.winv + toff : nullptr);
 #pragma unroll
-        for (int k = 0; k < RG; ++k, xp += pb2, bp += pb, wp += pb) {
-            const float2 x2 = ldg2_ifw((const float*)xp, rA | rB, 1u << k);
+        for (int k = 0; k < RG; ++k, bp += pb, wp += pb) {
             const float4 t = ldg4_if((const float*)bp, anyq, 1u << k);
             bv[k][0] = t.x, bv[k][1] = t.y, bv[k][2] = t.z, bv[k][3] = t.w;
-            // the red cells of the row: columns (k & 1) and 2 + (k & 1)
-            v[k][k & 1] = x2.x;
-            v[k][2 + (k & 1)] = x2.y;
-            v[k][1 - (k & 1)] = 0.f;
-            v[k][3 - (k & 1)] = 0.f;
             if (WMODE == 1) {
                 const float4 w = ldg4_if((const float*)wp, anyq, 1u << k);
                 wv[k][0] = w.x, wv[k][1] = w.y, wv[k][2] = w.z, wv[k][3] = w.w;
@@ -368,20 +355,22 @@ __device__ __forceinline__ float rbw_up_tile(const Level& lf, int64_t cpitch, in
             e[m] = ldg2_ifw((const float*)ep, cc, 1u << (2 * m));
         if (SATFILL_RBW_PREFETCH && next) {
             unsigned long long nb = (unsigned long long)(b + toff + next);
-            unsigned long long nx = (unsigned long long)(xr + (gr + row0) * (int64_t)(pitch >> 1) + (gc >> 1) + 2 * q + (next >> 1));
 #pragma unroll
-            for (int k = 0; k < RG; ++k, nb += pb, nx += pb2) {
+            for (int k = 0; k < RG; ++k, nb += pb)
                 prefetch_l2_if((const void*)nb, anyq, 1u << k);
-                prefetch_l2_if((const void*)nx, rA | rB, 1u << k);
-            }
         }
     }
-    // ---- x = x_red + P e at the red cells (the frame's row / column parity is the global one).  Even rows: the red cells
-    //      sit on coarse points; odd rows: in the middle of four, the easternmost of them the next lane's first.
+    // ---- x = x_red + P e at the red cells, x_red = b / d being the descent's red half-sweep from zero, recomputed (the
+    //      frame's row / column parity is the global one).  Even rows: the red cells sit on coarse points; odd rows: in
+    //      the middle of four, the easternmost of them the next lane's first.
     {
 #pragma unroll
         for (int k = 0; k < RG; ++k) {
             const int m = k >> 1;
+            v[k][k & 1] = bv[k][k & 1] * W(k, k & 1);
+            v[k][2 + (k & 1)] = bv[k][2 + (k & 1)] * W(k, 2 + (k & 1));
+            v[k][1 - (k & 1)] = 0.f;
+            v[k][3 - (k & 1)] = 0.f;
             if ((k & 1) == 0) {
                 v[k][0] = keep<false>(rA, k, v[k][0] + e[m].x);
                 v[k][2] = keep<false>(rB, k, v[k][2] + e[m].y);
@@ -492,7 +481,7 @@ inline Items make_items(int n_tiles, int nbands, int total_warps, bool band_majo
 
 template <int WMODE>
 __device__ __forceinline__ void rbw_down_items(const Level& lf, const Level& lc, const Items it, int first, int stride, int lane,
-    const float* __restrict__ b, float* __restrict__ xr, float* __restrict__ bc, const BandScalars* __restrict__ scal)
+    const float* __restrict__ b, float* __restrict__ bc, const BandScalars* __restrict__ scal)
 {
     const int n = it.count();
     for (int i = first; i < n; i += stride) {
@@ -509,14 +498,11 @@ __device__ __forceinline__ void rbw_down_items(const Level& lf, const Level& lc,
                 // 1 / d is 1 / 4 unless the frame touches the image border (warp-uniform)
                 const bool inner = ty > 0 && tx > 0 && (int64_t)(ty + 1) * TILE_H + DN_HR < lf.rows && (int64_t)(tx + 1) * TILE_W + HC < lf.cols;
                 if (inner)
-                    rbw_down_tile<0>(lf, lc.pitch, ty, tx, lane, alive, cm, b + (int64_t)band * lf.plane, xr + (int64_t)band * (lf.plane >> 1),
-                        bc + (int64_t)band * lc.plane, next);
+                    rbw_down_tile<0>(lf, lc.pitch, ty, tx, lane, alive, cm, b + (int64_t)band * lf.plane, bc + (int64_t)band * lc.plane, next);
                 else
-                    rbw_down_tile<2>(lf, lc.pitch, ty, tx, lane, alive, cm, b + (int64_t)band * lf.plane, xr + (int64_t)band * (lf.plane >> 1),
-                        bc + (int64_t)band * lc.plane, next);
+                    rbw_down_tile<2>(lf, lc.pitch, ty, tx, lane, alive, cm, b + (int64_t)band * lf.plane, bc + (int64_t)band * lc.plane, next);
             } else {
-                rbw_down_tile<WMODE>(lf, lc.pitch, ty, tx, lane, alive, cm, b + (int64_t)band * lf.plane, xr + (int64_t)band * (lf.plane >> 1),
-                    bc + (int64_t)band * lc.plane, next);
+                rbw_down_tile<WMODE>(lf, lc.pitch, ty, tx, lane, alive, cm, b + (int64_t)band * lf.plane, bc + (int64_t)band * lc.plane, next);
             }
         }
     }
@@ -525,8 +511,8 @@ __device__ __forceinline__ void rbw_down_items(const Level& lf, const Level& lc,
 // s_acc: per-warp, per-band partial sums of b . x (DOT), nbands doubles per warp
 template <int WMODE, bool DOT>
 __device__ __forceinline__ void rbw_up_items(const Level& lf, const Level& lc, const Items it, int first, int stride, int lane,
-    const float* __restrict__ xr, const float* __restrict__ b, const float* __restrict__ ec, float* __restrict__ x_out,
-    const BandScalars* __restrict__ scal, double* s_acc)
+    const float* __restrict__ b, const float* __restrict__ ec, float* __restrict__ x_out, const BandScalars* __restrict__ scal,
+    double* s_acc)
 {
     const int n = it.count();
     for (int i = first; i < n; i += stride) {
@@ -538,7 +524,6 @@ __device__ __forceinline__ void rbw_up_items(const Level& lf, const Level& lc, c
         quad_col_masks<UP_HR>(lf, ty, tx, lane < 30 ? lane % 10 : 9, cm);
         for (int band = b0; band < b1; ++band) {
             const unsigned alive = scal[band].done ? 0u : ~0u;
-            const float* xrb = xr + (int64_t)band * (lf.plane >> 1);
             const float* bb = b + (int64_t)band * lf.plane;
             const float* eb = ec + (int64_t)band * lc.plane;
             float* xb = x_out + (int64_t)band * lf.plane;
@@ -546,10 +531,10 @@ __device__ __forceinline__ void rbw_up_items(const Level& lf, const Level& lc, c
             float acc;
             if (WMODE == 2) {
                 const bool inner = ty > 0 && tx > 0 && (int64_t)(ty + 1) * TILE_H + UP_HR < lf.rows && (int64_t)(tx + 1) * TILE_W + HC < lf.cols;
-                acc = inner ? rbw_up_tile<0, DOT>(lf, lc.pitch, ty, tx, lane, alive, cm, xrb, bb, eb, xb, next)
-                            : rbw_up_tile<2, DOT>(lf, lc.pitch, ty, tx, lane, alive, cm, xrb, bb, eb, xb, next);
+                acc = inner ? rbw_up_tile<0, DOT>(lf, lc.pitch, ty, tx, lane, alive, cm, bb, eb, xb, next)
+                            : rbw_up_tile<2, DOT>(lf, lc.pitch, ty, tx, lane, alive, cm, bb, eb, xb, next);
             } else {
-                acc = rbw_up_tile<WMODE, DOT>(lf, lc.pitch, ty, tx, lane, alive, cm, xrb, bb, eb, xb, next);
+                acc = rbw_up_tile<WMODE, DOT>(lf, lc.pitch, ty, tx, lane, alive, cm, bb, eb, xb, next);
             }
             if (DOT) {
                 // a few dozen products per lane in float, everything above that in double
@@ -574,15 +559,14 @@ __device__ __forceinline__ void rbw_up_items(const Level& lf, const Level& lc, c
 // ENDCOLLECTIVE pair: ~100 of 1700 instructions per tile).
 template <int WMODE>
 __global__ void __launch_bounds__(32, WMODE == 0 ? RBW_DOWN_CTAS : RBW_W_CTAS) k_rbw_down(Level lf, Level lc, Items it,
-    const float* __restrict__ b, float* __restrict__ xr, float* __restrict__ bc, const BandScalars* __restrict__ scal)
+    const float* __restrict__ b, float* __restrict__ bc, const BandScalars* __restrict__ scal)
 {
-    rbw_down_items<WMODE>(lf, lc, it, (int)blockIdx.x, (int)gridDim.x, (int)threadIdx.x, b, xr, bc, scal);
+    rbw_down_items<WMODE>(lf, lc, it, (int)blockIdx.x, (int)gridDim.x, (int)threadIdx.x, b, bc, scal);
 }
 
 template <int WMODE, bool DOT>
 __global__ void __launch_bounds__(32, WMODE == 0 ? RBW_UP_CTAS : RBW_W_CTAS) k_rbw_up(Level lf, Level lc, Items it,
-    const float* __restrict__ xr, const float* __restrict__ b, const float* __restrict__ ec, float* __restrict__ x_out,
-    BandScalars* __restrict__ scal, int slot)
+    const float* __restrict__ b, const float* __restrict__ ec, float* __restrict__ x_out, BandScalars* __restrict__ scal, int slot)
 {
     extern __shared__ double s_acc[];  // nbands partial sums of b . x (DOT only)
     const int lane = (int)threadIdx.x;
@@ -591,7 +575,7 @@ __global__ void __launch_bounds__(32, WMODE == 0 ? RBW_UP_CTAS : RBW_W_CTAS) k_r
             s_acc[i] = 0.0;
         __syncwarp();
     }
-    rbw_up_items<WMODE, DOT>(lf, lc, it, (int)blockIdx.x, (int)gridDim.x, lane, xr, b, ec, x_out, scal, s_acc);
+    rbw_up_items<WMODE, DOT>(lf, lc, it, (int)blockIdx.x, (int)gridDim.x, lane, b, ec, x_out, scal, s_acc);
     if (DOT) {
         __syncwarp();
         for (int i = lane; i < it.nbands; i += 32)
@@ -608,7 +592,6 @@ struct TailLevel {
     Items it;
     float* b;
     float* x;
-    float* xr;
 };
 struct TailArgs {
     TailLevel L[MAX_LEVELS];
@@ -740,7 +723,7 @@ __global__ void __launch_bounds__(RW_THREADS, 3) k_rbw_tail(TailArgs A, BandScal
     const int stride = (int)gridDim.x * RW_WARPS;
     unsigned epoch = 0;
     for (int l = 0; l + 1 < A.n; ++l) {
-        rbw_down_items<1>(A.L[l].lv, A.L[l + 1].lv, A.L[l].it, wg, stride, lane, A.L[l].b, A.L[l].xr, A.L[l + 1].b, scal);
+        rbw_down_items<1>(A.L[l].lv, A.L[l + 1].lv, A.L[l].it, wg, stride, lane, A.L[l].b, A.L[l + 1].b, scal);
         grid_barrier(barrier, epoch);
     }
     {
@@ -752,7 +735,7 @@ __global__ void __launch_bounds__(RW_THREADS, 3) k_rbw_tail(TailArgs A, BandScal
     }
     for (int l = A.n - 2; l >= 0; --l) {
         grid_barrier(barrier, epoch);
-        rbw_up_items<1, false>(A.L[l].lv, A.L[l + 1].lv, A.L[l].it, wg, stride, lane, A.L[l].xr, A.L[l].b, A.L[l + 1].x, A.L[l].x, scal,
+        rbw_up_items<1, false>(A.L[l].lv, A.L[l + 1].lv, A.L[l].it, wg, stride, lane, A.L[l].b, A.L[l + 1].x, A.L[l].x, scal,
             nullptr);
     }
 }
@@ -778,7 +761,6 @@ struct RWLevel {
     int64_t units;
     float* b;   // level 0: the float copy of the CG residual
     float* x;   // full plane (level 0: z)
-    float* xr;  // colour-split half plane
 };
 
 int env_int(const char* name, int dflt)
@@ -818,11 +800,11 @@ int launch_down_w(sa_ctx* ctx, const RWLevel& F, const RWLevel& C, int nb, const
     const Items it = make_items(F.lv.n_tiles, nb, max_ctas, band_major_for(F.lv));
     const unsigned grid = (unsigned)(it.count() < max_ctas ? it.count() : max_ctas);
     if (mode == 0)
-        SA_LAUNCH(ctx, k_rbw_down<0>, grid, 32, 0, F.lv, C.lv, it, F.b, F.xr, C.b, scal);
+        SA_LAUNCH(ctx, k_rbw_down<0>, grid, 32, 0, F.lv, C.lv, it, F.b, C.b, scal);
     else if (mode == 1)
-        SA_LAUNCH(ctx, k_rbw_down<1>, grid, 32, 0, F.lv, C.lv, it, F.b, F.xr, C.b, scal);
+        SA_LAUNCH(ctx, k_rbw_down<1>, grid, 32, 0, F.lv, C.lv, it, F.b, C.b, scal);
     else
-        SA_LAUNCH(ctx, k_rbw_down<2>, grid, 32, 0, F.lv, C.lv, it, F.b, F.xr, C.b, scal);
+        SA_LAUNCH(ctx, k_rbw_down<2>, grid, 32, 0, F.lv, C.lv, it, F.b, C.b, scal);
     return SA_OK;
 }
 
@@ -843,11 +825,11 @@ int launch_up_w(sa_ctx* ctx, const RWLevel& F, const RWLevel& C, int nb, BandSca
     const Items it = make_items(F.lv.n_tiles, nb, max_ctas, band_major_for(F.lv));
     const unsigned grid = (unsigned)(it.count() < max_ctas ? it.count() : max_ctas);
     if (mode == 0)
-        SA_LAUNCH(ctx, (k_rbw_up<0, DOT>), grid, 32, smem, F.lv, C.lv, it, F.xr, F.b, C.x, F.x, scal, slot);
+        SA_LAUNCH(ctx, (k_rbw_up<0, DOT>), grid, 32, smem, F.lv, C.lv, it, F.b, C.x, F.x, scal, slot);
     else if (mode == 1)
-        SA_LAUNCH(ctx, (k_rbw_up<1, DOT>), grid, 32, smem, F.lv, C.lv, it, F.xr, F.b, C.x, F.x, scal, slot);
+        SA_LAUNCH(ctx, (k_rbw_up<1, DOT>), grid, 32, smem, F.lv, C.lv, it, F.b, C.x, F.x, scal, slot);
     else
-        SA_LAUNCH(ctx, (k_rbw_up<2, DOT>), grid, 32, smem, F.lv, C.lv, it, F.xr, F.b, C.x, F.x, scal, slot);
+        SA_LAUNCH(ctx, (k_rbw_up<2, DOT>), grid, 32, smem, F.lv, C.lv, it, F.b, C.x, F.x, scal, slot);
     return SA_OK;
 }
 
@@ -873,7 +855,6 @@ int launch_tail(sa_ctx* ctx, const std::vector<RWLevel>& L, int first, int nb, B
         T.it = make_items(T.lv.n_tiles, nb, max_ctas * RW_WARPS, false);
         T.b = L[(size_t)l].b;
         T.x = L[(size_t)l].x;
-        T.xr = L[(size_t)l].xr;
         if (l + 1 < (int)L.size())
             most = std::max(most, (T.it.count() + RW_WARPS - 1) / RW_WARPS);
     }
@@ -898,13 +879,12 @@ int apply_vcycle_rbw(sa_scene* s, const sa_options& o, KernelTimer& kt, int rz_s
     sa_ctx* ctx = s->ctx;
     const int nb = s->win_n(), b0 = s->band0;  // the band window (common.cuh): every base pointer starts at band b0
     std::vector<RWLevel> L;
-    L.push_back({ fine_level(s), s->n_unknowns * live_bands, s->rb_rf(), s->rb_z(),
-        (float*)s->t + (s->pitch >> 1) + (int64_t)b0 * (s->plane >> 1) });
+    L.push_back({ fine_level(s), s->n_unknowns * live_bands, s->rb_rf(), s->rb_z() });
     for (sa_level_store& c : s->coarse) {
         if (c.lv.n_tiles == 0)
             break;
         L.push_back({ c.lv, c.n_unknowns * live_bands, (float*)c.b + c.lv.pitch + (int64_t)b0 * c.lv.plane,
-            (float*)c.x + c.lv.pitch + (int64_t)b0 * c.lv.plane, (float*)c.t + (c.lv.pitch >> 1) + (int64_t)b0 * (c.lv.plane >> 1) });
+            (float*)c.x + c.lv.pitch + (int64_t)b0 * c.lv.plane });
     }
     const int nl = (int)L.size();
     BandScalars* scal = s->scal + b0;
@@ -933,15 +913,13 @@ int apply_vcycle_rbw(sa_scene* s, const sa_options& o, KernelTimer& kt, int rz_s
         SA_TRY(launch_down_w(ctx, L[(size_t)l], L[(size_t)l + 1], nb, scal));
         kt.end();
         if (l < dlv) {
-            // the ascent reads the red half of the iterate 2 rows beyond the slice; the next level's descent reads
-            // its right-hand side 3 rows beyond -- or, if that level is replicated, everywhere
-            SA_TRY(dist_group_begin(s));  // one NCCL launch for both exchanges
-            SA_TRY(dist_halo<float>(s, l, L[(size_t)l].xr, L[(size_t)l].lv.pitch >> 1, L[(size_t)l].lv.plane >> 1, 2, 2));
+            // the next level's descent reads its right-hand side 3 rows beyond the slice -- or, if that level is replicated,
+            // everywhere (nothing of this level travels: the ascent recomputes the red half of the iterate from b, whose halo
+            // rows it already holds)
             if (l + 1 < dlv)
                 SA_TRY(dist_halo<float>(s, l + 1, L[(size_t)l + 1].b, L[(size_t)l + 1].lv.pitch, L[(size_t)l + 1].lv.plane, 3, 3));
             else
                 SA_TRY(dist_gather(s, L[(size_t)l + 1].b, L[(size_t)l + 1].lv.pitch, L[(size_t)l + 1].lv.plane));
-            SA_TRY(dist_group_end(s));
         }
     }
     {
