@@ -596,6 +596,7 @@ struct TailLevel {
 struct TailArgs {
     TailLevel L[MAX_LEVELS];
     int n;        // levels in the tail; the last one is the coarsest (solved by relaxation, one CTA per band)
+    int n_grid;   // the first n_grid of them are worked by the whole grid, the rest per band inside one CTA
     int nbands;
     int sweeps;
     int fixed;    // coarsest level only: 1 / d = 1 / 4 where the level has no 1 / d plane (a one-level hierarchy)
@@ -716,27 +717,60 @@ __device__ void rbw_coarsest(const Level& lv, bool fixed, const float* __restric
 
 }  // namespace
 
+// Levels [0, n_grid) of the tail are worked by the whole grid with a grid-wide barrier after each; the DEEP levels
+// [n_grid, n) -- a handful of tiles each -- are worked per band by ONE CTA, whose warps only need __syncthreads between
+// levels: a grid barrier costs ~4 us (one atomic per CTA and a round trip to L2 per poll), a CTA barrier nothing, and on a
+// scene-sized problem (1697 x 1284: the reference's sample scene) ten of the seventeen phases of the tail are deep.
 __global__ void __launch_bounds__(RW_THREADS, 3) k_rbw_tail(TailArgs A, BandScalars* __restrict__ scal, unsigned* __restrict__ barrier)
 {
     __shared__ float s_coarsest[3 * CP * CP];
-    const int lane = threadIdx.x & 31, wg = (int)blockIdx.x * RW_WARPS + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wg = (int)blockIdx.x * RW_WARPS + warp;
     const int stride = (int)gridDim.x * RW_WARPS;
     unsigned epoch = 0;
-    for (int l = 0; l + 1 < A.n; ++l) {
+    for (int l = 0; l < A.n_grid; ++l) {
         rbw_down_items<1>(A.L[l].lv, A.L[l + 1].lv, A.L[l].it, wg, stride, lane, A.L[l].b, A.L[l + 1].b, scal);
         grid_barrier(barrier, epoch);
     }
-    {
-        const TailLevel& C = A.L[A.n - 1];
-        for (int band = blockIdx.x; band < A.nbands; band += gridDim.x)
-            if (!scal[band].done)
-                rbw_coarsest<false>(C.lv, A.fixed != 0, C.b + (int64_t)band * C.lv.plane, C.x + (int64_t)band * C.lv.plane, A.sweeps,
-                    nullptr, s_coarsest);
+    for (int band = blockIdx.x; band < A.nbands; band += gridDim.x) {
+        if (scal[band].done)
+            continue;
+        for (int l = A.n_grid; l + 1 < A.n; ++l) {
+            const Level& lf = A.L[l].lv;
+            const Level& lc = A.L[l + 1].lv;
+            for (int ti = warp; ti < lf.n_tiles; ti += RW_WARPS) {
+                const int yx = lf.tile_yx[ti];
+                unsigned long long cm[4];
+                quad_col_masks<DN_HR>(lf, yx >> 16, yx & 0xffff, lane < 30 ? lane % 10 : 9, cm);
+                rbw_down_tile<1>(lf, lc.pitch, yx >> 16, yx & 0xffff, lane, ~0u, cm, A.L[l].b + (int64_t)band * lf.plane,
+                    A.L[l + 1].b + (int64_t)band * lc.plane, 0);
+            }
+            __threadfence();
+            __syncthreads();
+        }
+        {
+            const TailLevel& C = A.L[A.n - 1];
+            rbw_coarsest<false>(C.lv, A.fixed != 0, C.b + (int64_t)band * C.lv.plane, C.x + (int64_t)band * C.lv.plane, A.sweeps, nullptr,
+                s_coarsest);
+            __threadfence();
+            __syncthreads();
+        }
+        for (int l = A.n - 2; l >= A.n_grid; --l) {
+            const Level& lf = A.L[l].lv;
+            const Level& lc = A.L[l + 1].lv;
+            for (int ti = warp; ti < lf.n_tiles; ti += RW_WARPS) {
+                const int yx = lf.tile_yx[ti];
+                unsigned long long cm[4];
+                quad_col_masks<UP_HR>(lf, yx >> 16, yx & 0xffff, lane < 30 ? lane % 10 : 9, cm);
+                rbw_up_tile<1, false>(lf, lc.pitch, yx >> 16, yx & 0xffff, lane, ~0u, cm, A.L[l].b + (int64_t)band * lf.plane,
+                    A.L[l + 1].x + (int64_t)band * lc.plane, A.L[l].x + (int64_t)band * lf.plane, 0);
+            }
+            __threadfence();
+            __syncthreads();
+        }
     }
-    for (int l = A.n - 2; l >= 0; --l) {
+    for (int l = A.n_grid - 1; l >= 0; --l) {
         grid_barrier(barrier, epoch);
-        rbw_up_items<1, false>(A.L[l].lv, A.L[l + 1].lv, A.L[l].it, wg, stride, lane, A.L[l].b, A.L[l + 1].x, A.L[l].x, scal,
-            nullptr);
+        rbw_up_items<1, false>(A.L[l].lv, A.L[l + 1].lv, A.L[l].it, wg, stride, lane, A.L[l].b, A.L[l + 1].x, A.L[l].x, scal, nullptr);
     }
 }
 
@@ -849,13 +883,18 @@ int launch_tail(sa_ctx* ctx, const std::vector<RWLevel>& L, int first, int nb, B
     A.sweeps = sweeps;
     A.fixed = fixed ? 1 : 0;
     int most = nb;
+    const int deep_tiles = env_int("SATFILL_TAIL_DEEP_TILES", 8);
+    A.n_grid = 0;
+    for (int l = first; l + 1 < (int)L.size(); ++l)
+        if (L[(size_t)l].lv.n_tiles > deep_tiles)
+            A.n_grid = l - first + 1;
     for (int l = first; l < (int)L.size(); ++l) {
         TailLevel& T = A.L[l - first];
         T.lv = L[(size_t)l].lv;
         T.it = make_items(T.lv.n_tiles, nb, max_ctas * RW_WARPS, false);
         T.b = L[(size_t)l].b;
         T.x = L[(size_t)l].x;
-        if (l + 1 < (int)L.size())
+        if (l - first < A.n_grid)
             most = std::max(most, (T.it.count() + RW_WARPS - 1) / RW_WARPS);
     }
     unsigned grid = (unsigned)std::min(most, max_ctas);
