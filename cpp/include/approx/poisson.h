@@ -2,6 +2,8 @@
 // 12-52); implemented in cpp/src/approx_satfill.cpp on top of libsatfill.so.
 #pragma once
 
+#include <type_traits>
+
 #include <optional>
 #include <string>
 
@@ -53,6 +55,37 @@ struct DayInfo {
 // neighbour, "" when `close_images` is empty; throws utils::GenericError for a weight outside [0, 1].
 std::string find_good_close_image(std::string const& date_string, f64 distance_weight, std::vector<DayInfo> close_images,
     f64 percent_invalid_of_date);
+
+// The reference's own signature (lib/approx/include/approx/poisson.h:63, poisson.cpp:323-349):
+//     std::string find_good_close_image(std::string const& date_string, f64 distance_weight, DataBase& db);
+// as a template over the database type, so that the header needs neither SQLiteCpp nor Boost: any type with the two
+// queries of approx::DataBase (db.h:30-31) fits -- the reference's own class compiled from its own db.cpp, or a stand-in
+// (tests).  The rows' `date` is a utils::Date or anything with year() / month() / day() (boost::gregorian::date).  Same
+// order of effects as upstream: the weight is checked before the database is touched, and the second query only runs
+// when a neighbour exists.
+namespace detail {
+template <class D>
+utils::Date to_date(D const& d)
+{
+    if constexpr (std::is_same_v<std::decay_t<D>, utils::Date>)
+        return d;
+    else
+        return utils::Date((int)d.year(), (int)d.month(), (int)d.day());
+}
+}  // namespace detail
+template <class DataBaseT>
+std::string find_good_close_image(std::string const& date_string, f64 distance_weight, DataBaseT& db)
+{
+    if (distance_weight < 0 || distance_weight > 1)  // poisson.cpp:325-327
+        throw utils::GenericError("Could not find close image: distance weight not between 0 and 1");
+    std::vector<DayInfo> rows;
+    for (auto const& r : db.select_close_images(date_string))
+        rows.push_back(DayInfo { detail::to_date(r.date), (f64)r.percent_invalid });
+    if (rows.empty())  // poisson.cpp:331-334
+        return {};
+    return find_good_close_image(date_string, distance_weight, std::move(rows),
+        (f64)db.select_info_about_date(date_string).percent_invalid);
+}
 
 // preprocess_cloud_band of poisson_main (executables/poisson-main.cpp:10-21): (2 dilation_size + 1)^2 rectangular
 // morphological close of the cloud band, cast to bool -- on the GPU (sa_morph_close_mask), bit-exact against

@@ -2,6 +2,7 @@
 // C-ABI of libsatfill.so.  No arithmetic happens here -- Eigen is only the container type of the signatures.
 #include <approx/laplace.h>
 #include <approx/poisson.h>
+#include <utils/log.h>
 
 #include <satfill.h>
 
@@ -45,6 +46,7 @@ static_assert(sizeof(bool) == 1, "MatX<bool> is passed to the C-ABI as a byte ma
 }  // namespace
 
 void set_laplace_options(LaplaceOptions const& options) { g_laplace = options; }
+LaplaceOptions const& laplace_options() { return g_laplace; }
 PerfInfo const& last_perf_info() { return g_perf; }
 
 void PerfInfo::write(fs::path const& output) const
@@ -76,6 +78,38 @@ void fill_missing_portion_smooth_boundary(MatX<f64>& input_image, MatX<bool> con
         input_image.cols(), 1, input_image.rows(), &o, &st);
     if (rc != SA_OK && rc != SA_EMPTY_MASK && rc != SA_NOT_CONVERGED)  // the reference never checks info() here
         throw std::runtime_error(std::string("satfill: ") + sa_last_error(c.h));
+    g_perf = PerfInfo { (long)st.unknowns, st.tolerance, (long)st.max_iterations, (long)st.iterations, st.error, st.solve_ms * 1e-3 };
+    if (rc == SA_EMPTY_MASK)  // laplace.cpp:41-44
+        utils::log(utils::LogLevel::info, "approx", "No invalid pixels found: nothing to do");
+    else  // laplace.cpp:129-131 logs the elapsed time of the call
+        utils::log(utils::LogLevel::info, "approx", "Laplace fill: %lld unknowns, %lld iterations, residual %.3e, %.3f ms on the device",
+            (long long)st.unknowns, (long long)st.iterations, st.error, st.setup_ms + st.solve_ms);
+}
+
+void apply_laplace(const unsigned char* image, const unsigned char* invalid_image, Eigen::Index rows, Eigen::Index cols,
+    f64 red_threshold, f64* out)
+{
+    if (rows <= 0 || cols <= 0)
+        return;
+    if (!image || !invalid_image || !out)
+        throw std::runtime_error("apply_laplace: null buffer");
+    Ctx& c = ctx();
+    std::lock_guard<std::mutex> guard(c.lock);
+    sa_options o;
+    sa_default_options(&o, SA_LAPLACE);
+    if (g_laplace.tolerance > 0)
+        o.tolerance = g_laplace.tolerance;
+    if (g_laplace.max_iterations > 0)
+        o.max_iterations = g_laplace.max_iterations;
+    o.precond = g_laplace.multigrid ? SA_PRECOND_MULTIGRID : SA_PRECOND_JACOBI;
+    sa_stats st[3] {};
+    int rc = sa_apply_laplace_u8(c.h, image, invalid_image, rows, cols, 3, red_threshold, out, nullptr, &o, st);
+    if (rc != SA_OK && rc != SA_EMPTY_MASK && rc != SA_NOT_CONVERGED)  // the reference never checks info() here
+        throw std::runtime_error(std::string("satfill: ") + sa_last_error(c.h));
+    if (rc == SA_EMPTY_MASK) {  // laplace.cpp:41-44 per channel: nothing to fill, the image comes back as doubles
+        for (Eigen::Index i = 0; i < rows * cols * 3; ++i)
+            out[i] = (f64)image[i];
+    }
 }
 
 void blend_images_poisson(MultiChannelImage& input_images, MultiChannelImage const& replacement_images,
@@ -85,12 +119,12 @@ void blend_images_poisson(MultiChannelImage& input_images, MultiChannelImage con
         return;
     if (input_images.images.size() != replacement_images.images.size() || input_images.rows() != replacement_images.rows()
         || input_images.cols() != replacement_images.cols()) {  // poisson.cpp:154-157: log and return
-        std::fprintf(stderr, "[approx] Input and replacement images must have the same dimensions\n");
+        utils::log(utils::LogLevel::err, "approx", "Input and replacement images must have the same dimensions");
         return;
     }
     if (invalid_mask.rows() != input_images.rows() || invalid_mask.cols() != input_images.cols()) {
         // poisson.cpp:158-160 logs and continues (out-of-bounds reads); return instead
-        std::fprintf(stderr, "[approx] Invalid mask must match the image dimensions\n");
+        utils::log(utils::LogLevel::err, "approx", "Invalid mask must match the image dimensions");
         return;
     }
     Ctx& c = ctx();
@@ -113,9 +147,9 @@ void blend_images_poisson(MultiChannelImage& input_images, MultiChannelImage con
     g_perf = PerfInfo { (long)last.unknowns, last.tolerance, (long)last.max_iterations, (long)last.iterations, last.error,
         last.solve_ms * 1e-3 };
     if (rc == SA_NOT_CONVERGED)  // poisson.cpp:263-269: nothing was written
-        std::fprintf(stderr, "[approx] Failed to solve the linear system: no convergence\n");
+        utils::log(utils::LogLevel::err, "approx", "Failed to solve the linear system: no convergence");
     else if (rc != SA_OK && rc != SA_EMPTY_MASK)
-        std::fprintf(stderr, "[approx] %s\n", sa_last_error(c.h));
+        utils::log(utils::LogLevel::err, "approx", "%s", sa_last_error(c.h));
 }
 
 void blend_images_poisson(MultiChannelImage& input_images, MultiChannelImage const& replacement_images, int start_row,
@@ -127,15 +161,15 @@ void blend_images_poisson(MultiChannelImage& input_images, MultiChannelImage con
         return;
     const Eigen::Index R = replacement_images.rows(), C = replacement_images.cols();
     if (replacement_images.size() > input_images.size()) {
-        std::fprintf(stderr, "[approx] Cannot solve problem: replacement image is larger than the input image\n");
+        utils::log(utils::LogLevel::err, "approx", "Cannot solve problem: replacement image is larger than the input image");
         return;
     }
     if (start_row < 0 || start_column < 0 || start_row >= input_images.rows() || start_column >= input_images.cols()) {
-        std::fprintf(stderr, "[approx] Cannot solve problem: row/column is out of bounds\n");
+        utils::log(utils::LogLevel::err, "approx", "Cannot solve problem: row/column is out of bounds");
         return;
     }
     if (start_row + R > input_images.rows() || start_column + C > input_images.cols()) {
-        std::fprintf(stderr, "[approx] Cannot solve problem: replacement image goes beyond the bounds of the input image\n");
+        utils::log(utils::LogLevel::err, "approx", "Cannot solve problem: replacement image goes beyond the bounds of the input image");
         return;
     }
     // The system lives in the replacement's own rectangle (neighbours outside it are dropped, poisson.cpp:76,108), its

@@ -1,6 +1,7 @@
 // satellite_approximation._core -- the fill-path functions of the reference's pybind11 module (src/main.cpp:16-58)
 // bound to the B200 implementation.  Same names, argument names, noconvert rules and defaults.
 #include <pybind11/eigen.h>
+#include <pybind11/numpy.h>
 #include <pybind11/pybind11.h>
 #include <pybind11/stl.h>
 
@@ -11,13 +12,16 @@
 #include <approx/poisson.h>
 #include <utils/filesystem.h>
 #include <utils/geotiff.h>
+#include <utils/log.h>
+
+#include <algorithm>
 
 #include <array>
 
 namespace py = pybind11;
 using namespace py::literals;
 
-enum class LogLevel { Debug = 1, Info = 2, Warn = 3, Error = 4, Critical = 5 };  // spdlog values (src/main.cpp:24-29)
+enum class PyLogLevel { Debug = 1, Info = 2, Warn = 3, Error = 4, Critical = 5 };  // spdlog values (src/main.cpp:24-29)
 
 PYBIND11_MODULE(_core, m)
 {
@@ -27,19 +31,45 @@ PYBIND11_MODULE(_core, m)
         .def("__str__", [](std::filesystem::path const& p) { return p.string(); })
         .def("__fspath__", [](std::filesystem::path const& p) { return p.string(); });
     py::implicitly_convertible<std::string, std::filesystem::path>();
-    py::enum_<LogLevel>(m, "LogLevel")
-        .value("Debug", LogLevel::Debug)
-        .value("Info", LogLevel::Info)
-        .value("Warn", LogLevel::Warn)
-        .value("Error", LogLevel::Error)
-        .value("Critical", LogLevel::Critical);
-    m.def("set_log_level", [](LogLevel) {});
+    py::enum_<PyLogLevel>(m, "LogLevel")
+        .value("Debug", PyLogLevel::Debug)
+        .value("Info", PyLogLevel::Info)
+        .value("Warn", PyLogLevel::Warn)
+        .value("Error", PyLogLevel::Error)
+        .value("Critical", PyLogLevel::Critical);
+    // src/main.cpp:30-34 sets the level of the reference's spdlog loggers; here: of the shim's stderr log (utils/log.h)
+    m.def("set_log_level", [](PyLogLevel level) { utils::set_log_level((utils::LogLevel)(int)level); });
+    // the record of the last fill (approx::PerfInfo, poisson.h:12-21; the reference appends it to a hard-coded CSV)
+    m.def("last_perf_info", []() {
+        approx::PerfInfo const& p = approx::last_perf_info();
+        return py::dict("region_size"_a = p.region_size, "tolerance"_a = p.tolerance, "max_iterations"_a = p.max_iterations,
+            "iterations"_a = p.iterations, "error"_a = p.error, "solve_time"_a = p.solve_time);
+    });
+    // apply_laplace on numpy arrays (laplace.h:31 takes cv::Mat: uint8 H x W x 3 in cv::imread order)
+    m.def(
+        "apply_laplace",
+        [](py::array_t<unsigned char, py::array::c_style | py::array::forcecast> image,
+            py::array_t<unsigned char, py::array::c_style | py::array::forcecast> invalid_image, double red_threshold) {
+            if (image.ndim() != 3 || image.shape(2) != 3 || invalid_image.ndim() != 3 || invalid_image.shape(2) != 3)
+                throw std::runtime_error("apply_laplace: uint8 H x W x 3 images");
+            if (image.shape(0) != invalid_image.shape(0) || image.shape(1) != invalid_image.shape(1))
+                throw std::runtime_error("Input image and mask need to be the same size");  // laplace.cpp:124-127
+            py::array_t<double> out({ image.shape(0), image.shape(1), (py::ssize_t)3 });
+            {
+                py::gil_scoped_release release;
+                approx::apply_laplace(image.data(), invalid_image.data(), image.shape(0), image.shape(1), red_threshold,
+                    out.mutable_data());
+            }
+            return out;
+        },
+        "image"_a, "invalid_image"_a, "red_threshold"_a = 220.0);
+    m.def("get_log_level", []() { return (PyLogLevel)std::min(std::max((int)utils::log_level(), 1), 5); });
     m.def(
         "filling_missing_portions_smooth_boundaries",
         [](MatX<f64>& input_image, MatX<bool> const& invalid_pixels) {
             py::gil_scoped_release release;
             approx::fill_missing_portion_smooth_boundary(input_image, invalid_pixels);
-            return input_image;
+            return std::move(input_image);  // the caster's own copy of the caller's array: hand it back without another copy
         },
         py::arg("input_image").noconvert(), py::arg("invalid_pixels").noconvert());
     m.def("blend_images_poisson",

@@ -53,6 +53,21 @@ def main() -> None:
     assert all(np.array_equal(o, x) for o, x in zip(out, f))
     out = core.blend_images_poisson(f, [x[:, :-1] for x in g], mask)  # poisson.cpp:154-157: log and return
     assert all(np.array_equal(o, x) for o, x in zip(out, f))
+    # set_log_level is wired (src/main.cpp:30-34), the record of the last fill is readable, apply_laplace runs on numpy images
+    assert core.get_log_level() == core.LogLevel.Warn
+    core.set_log_level(core.LogLevel.Critical)
+    assert core.get_log_level() == core.LogLevel.Critical
+    core.set_log_level(core.LogLevel.Warn)
+    core.blend_images_poisson(f, g, mask)
+    info = core.last_perf_info()
+    assert info["region_size"] == int(mask.sum()) and info["iterations"] >= 1 and info["tolerance"] == 1e-6, info
+    rng = np.random.default_rng(11)
+    bgr = rng.integers(0, 256, (40, 36, 3), dtype=np.uint8)
+    marked = np.zeros_like(bgr)
+    marked[5:20, 8:30, 2] = 255  # red, green stays 0: (R >= 220) & (G <= 150)
+    al = core.apply_laplace(bgr, marked, 220.0)
+    wal, wmask = oracle.apply_laplace(bgr, marked, 220.0, tol=1e-13)
+    assert al.shape == (40, 36, 3) and wmask.sum() == 15 * 22 and np.max(np.abs(al - wal)) < 1e-6
     # connected components: the reference's own case (tests/approximation.h:55-75)
     m = np.zeros((10, 10), bool)
     m[1:3, 1:3] = True

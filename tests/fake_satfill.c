@@ -86,6 +86,37 @@ int sa_poisson_blend(sa_ctx* ctx, double* const* inputs, const double* const* re
     return rc;
 }
 
+/* approx::apply_laplace (laplace.cpp:134-168): mask from the marked image, every channel filled with it */
+int sa_apply_laplace_u8(sa_ctx* ctx, const uint8_t* image, const uint8_t* invalid, int64_t rows, int64_t cols, int channels,
+    double red_threshold, double* out, uint8_t* mask_out, const sa_options* opts, sa_stats* stats)
+{
+    (void)ctx;
+    const int64_t n = rows * cols;
+    uint8_t* mask = (uint8_t*)malloc((size_t)(n > 0 ? n : 1));
+    double* plane = (double*)malloc(sizeof(double) * (size_t)(n > 0 ? n : 1));
+    if (!mask || !plane)
+        return SA_OUT_OF_MEMORY;
+    for (int64_t i = 0; i < n; ++i)
+        mask[i] = invalid[i * channels + 2] >= red_threshold && invalid[i * channels + 1] <= 150;
+    int worst = SA_OK;
+    for (int ch = 0; ch < channels; ++ch) {
+        for (int64_t i = 0; i < n; ++i)
+            plane[i] = image[i * channels + ch];
+        so_stats st;
+        int rc = so_laplace_fill(plane, mask, rows, cols, cols, 1, 1, opts ? opts->tolerance : 0.0, opts ? opts->max_iterations : 0, &st);
+        fill_stats(stats ? stats + ch : NULL, &st, 1, rc, opts);
+        if (rc > worst)
+            worst = rc;
+        for (int64_t i = 0; i < n; ++i)
+            out[i * channels + ch] = plane[i];
+    }
+    if (mask_out)
+        memcpy(mask_out, mask, (size_t)n);
+    free(mask);
+    free(plane);
+    return worst;
+}
+
 int sa_label_components(sa_ctx* ctx, const uint8_t* mask, int64_t rows, int64_t cols, int64_t row_stride, int64_t col_stride,
     int32_t* labels, int32_t* out_num_labels)
 {

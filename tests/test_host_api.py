@@ -191,6 +191,54 @@ def test_cpp_shim_behaviour_on_the_cpu(tmp_path):
     assert r.returncode == 0 and "core-on-fake ok" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
 
 
+def test_cpp_api_gated_on_opencv_and_the_database(tmp_path):
+    """cv::Mat apply_laplace(cv::Mat const&, cv::Mat const&, f64) (laplace.h:31) and find_good_close_image(std::string
+    const&, f64, DataBase&) (poisson.h:63) with the reference's signatures: compiled against tests/fake_opencv (a minimal
+    cv::Mat: this image has no OpenCV C++ headers) and a stand-in database, run on the CPU against the fake C-ABI, checked
+    against the oracle's restatement of laplace.cpp:134-168 and the Python mirror of the picker."""
+    import os
+    import subprocess
+
+    import oracle
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    eigen = os.environ.get("EIGEN_DIR", "/root/reference/thirdparty/eigen-master")
+    shim = os.path.join(root, "satellite_approximation_b200", "lib", "libapprox_satfill.so")
+    if not os.path.isdir(eigen) or not os.path.exists(shim):
+        pytest.skip("needs Eigen headers and the built C++ shim (make -C cpp)")
+    oracle.port()
+    odir = os.path.join(root, "oracle", "_build")
+    fake = tmp_path / "fake"
+    fake.mkdir()
+    r = subprocess.run(["gcc", "-O2", "-std=c99", "-Wall", "-Wextra", "-fPIC", "-shared", "-I", os.path.join(root, "include"),
+                        os.path.join(root, "tests", "fake_satfill.c"), "-o", str(fake / "libsatfill.so"), "-L", odir,
+                        "-loracle", f"-Wl,-rpath,{odir}"], capture_output=True, text=True)  # fmt: skip
+    assert r.returncode == 0, r.stderr
+    exe = tmp_path / "cpp_gated_api"
+    r = subprocess.run(["g++", "-O1", "-std=c++20", "-Wall", "-I", os.path.join(root, "tests", "fake_opencv"), "-I",
+                        os.path.join(root, "cpp", "include"), "-I", os.path.join(root, "include"), "-I", eigen,
+                        os.path.join(root, "tests", "cpp_gated_api.cpp"), "-o", str(exe), "-L", os.path.dirname(shim),
+                        "-lapprox_satfill", "-L", str(fake), "-lsatfill", f"-Wl,-rpath,{os.path.dirname(shim)}"],
+                       capture_output=True, text=True)  # fmt: skip
+    assert r.returncode == 0, r.stderr[-3000:]
+    rows, cols = 37, 45
+    env = dict(os.environ, LD_LIBRARY_PATH=str(fake) + os.pathsep + os.environ.get("LD_LIBRARY_PATH", ""))
+    r = subprocess.run([str(exe), str(rows), str(cols)], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = r.stdout.strip().splitlines()
+    assert lines[0] == f"image {rows} {cols}"
+    vals = np.array([[float(x) for x in ln.split()] for ln in lines[1 : 1 + rows * cols * 3]])
+    image = vals[:, 0].astype(np.uint8).reshape(rows, cols, 3)
+    invalid = vals[:, 1].astype(np.uint8).reshape(rows, cols, 3)
+    got = vals[:, 2].reshape(rows, cols, 3)
+    want, mask = oracle.apply_laplace(image, invalid, 220.0, tol=1e-13)
+    assert mask.any() and np.max(np.abs(got - want)) < 1e-6
+    assert np.array_equal(got[~mask], image[~mask].astype(np.float64))
+    # the picker: nearest date for weight 1, cleanest date for weight 0, the date itself when it is cleaner than its best
+    # neighbour, "" (and only ONE query) without neighbours, and the weight check before any query
+    assert lines[-1] == "picker 1 2019-05-20 2019-06-01 2019-05-22 [] 1 weight-error 0", lines[-1]
+
+
 def test_find_good_close_image_cpp_and_python_agree_on_random_tables(tmp_path):
     """The ranking rule of find_good_close_image (poisson.cpp:323-349) in both host languages on random `dates` tables
     (hypothesis): same answer for every date, weight and invalid fraction, ties included."""
