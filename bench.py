@@ -737,7 +737,7 @@ def run_dropin(args, w, ctx, h_arrays):
         from satellite_approximation import _core  # type: ignore
 
         p = _core.last_perf_info() if hasattr(_core, "last_perf_info") else None
-        info = {"iterations": int(p.iterations), "error": float(p.error)} if p is not None else None
+        info = {"iterations": int(p["iterations"]), "error": float(p["error"]), "tolerance": float(p["tolerance"])} if p is not None else None
     except Exception:  # noqa: BLE001
         pass
     return {"value": unknowns * n_bands_timed / dt, "unit": UNIT, "seconds_per_step": dt, "steps": steps,

@@ -615,12 +615,11 @@ int solve_scene(sa_scene* s, const sa_options& o, sa_stats* stats)
                 SA_LAUNCH(ctx, k_residual<false>, grid, block, 0, lv, u0, g0, r0, rb ? s->rb_rf() : nullptr, scal);
         }
     }
-    if (dist) {
-        SA_TRY(dist_reduce(s, DIST_SETUP, 0, -1));
+    if (dist) {  // |b|^2, |r0|^2, r0.z0 summed over the ranks, and the halo rows of the residual the first kernel reads
         if (rb)
-            SA_TRY(dist_halo<float>(s, 0, s->rb_rf(), s->pitch, s->plane, 3, 3));
+            SA_TRY(dist_step(s, 0, DIST_VEC_RHS, s->rb_rf(), 4, s->pitch, s->plane, 3, 3, DIST_SETUP, 0, -1));
         else
-            SA_TRY(dist_halo<double>(s, 0, r0, s->pitch, s->plane, 1, 1));
+            SA_TRY(dist_step(s, 0, DIST_VEC_RHS, r0, 8, s->pitch, s->plane, 1, 1, DIST_SETUP, 0, -1));
     }
     SA_LAUNCH(ctx, k_finalize_setup, (nb + 63) / 64, 64, 0, scal, nb, o.tolerance, mg ? 1 : 0);
     SA_CUDA(ctx, cudaGetLastError());
@@ -669,15 +668,8 @@ int solve_scene(sa_scene* s, const sa_options& o, sa_stats* stats)
                     z = s->plane0(s->z, b0);
                 }
                 float* rf = rb ? s->rb_rf() : nullptr;
-                if (dist) {  // r.z summed over the ranks and the halo row of z, one NCCL launch
-                    SA_TRY(dist_reduce_pack(s, DIST_RZ, ki & 3));
-                    SA_TRY(dist_group_begin(s));
-                    SA_TRY(dist_reduce_issue(s));
-                    if (rb)
-                        SA_TRY(dist_halo<float>(s, 0, s->rb_z(), s->pitch, s->plane, 1, 1));
-                    SA_TRY(dist_group_end(s));
-                    SA_TRY(dist_reduce_unpack(s, DIST_RZ, ki & 3, -1));
-                }
+                if (dist)  // r.z summed over the ranks and the halo row of z, one exchange
+                    SA_TRY(dist_step(s, 0, DIST_VEC_SOL, rb ? (void*)s->rb_z() : nullptr, 4, s->pitch, s->plane, 1, 1, DIST_RZ, ki & 3, -1));
                 kt.begin(KC_DIRECTION, n * live);
                 if (strip)
                     SA_TRY(launch_direction2(ctx, lv, nb, false, z, rb, pin_v, pout_v, pf, scal, ki));
@@ -686,17 +678,9 @@ int solve_scene(sa_scene* s, const sa_options& o, sa_stats* stats)
                 else
                     SA_LAUNCH(ctx, (k_direction<false, double>), grid, block, 0, lv, (const double*)z, pin, pout, scal, ki);
                 kt.end();
-                if (dist) {  // the halo row of p' and p'.Ap' in one NCCL launch
-                    SA_TRY(dist_reduce_pack(s, DIST_PQ, ki & 3));
-                    SA_TRY(dist_group_begin(s));
-                    SA_TRY(dist_reduce_issue(s));
-                    if (pf)
-                        SA_TRY(dist_halo<float>(s, 0, (float*)pout_v, s->pitch, s->plane, 1, 1));
-                    else
-                        SA_TRY(dist_halo<double>(s, 0, pout, s->pitch, s->plane, 1, 1));
-                    SA_TRY(dist_group_end(s));
-                    SA_TRY(dist_reduce_unpack(s, DIST_PQ, ki & 3, (ki + 2) & 3));
-                }
+                if (dist)  // the halo row of p' and p'.Ap' in one exchange
+                    SA_TRY(dist_step(s, 0, DIST_VEC_DIR, pf ? pout_v : (void*)pout, pf ? 4 : 8, s->pitch, s->plane, 1, 1, DIST_PQ, ki & 3,
+                        (ki + 2) & 3));
                 kt.begin(KC_UPDATE, n * live);
                 if (strip)
                     SA_TRY(launch_update2(ctx, lv, nb, false, u0, pout_v, pf, r0, rf, scal, ki));
@@ -705,14 +689,8 @@ int solve_scene(sa_scene* s, const sa_options& o, sa_stats* stats)
                 else
                     SA_LAUNCH(ctx, (k_update<false, false>), grid, block, 0, lv, u0, pout, r0, nullptr, scal, ki);
                 kt.end();
-                if (dist) {  // the halo rows of the cycle's residual copy and |r|^2 in one NCCL launch
-                    SA_TRY(dist_reduce_pack(s, DIST_RR, (ki + 1) & 3));
-                    SA_TRY(dist_group_begin(s));
-                    SA_TRY(dist_reduce_issue(s));
-                    SA_TRY(dist_halo<float>(s, 0, rf, s->pitch, s->plane, 3, 3));
-                    SA_TRY(dist_group_end(s));
-                    SA_TRY(dist_reduce_unpack(s, DIST_RR, (ki + 1) & 3, -1));
-                }
+                if (dist)  // the halo rows of the cycle's residual copy and |r|^2 in one exchange
+                    SA_TRY(dist_step(s, 0, DIST_VEC_RHS, rf, 4, s->pitch, s->plane, 3, 3, DIST_RR, (ki + 1) & 3, -1));
                 SA_LAUNCH(ctx, k_check_converged, (nb + 63) / 64, 64, 0, scal, nb, ki + 1);
             } else {
                 kt.begin(KC_DIRECTION, n * live);
@@ -721,10 +699,8 @@ int solve_scene(sa_scene* s, const sa_options& o, sa_stats* stats)
                 else
                     SA_LAUNCH(ctx, (k_direction<true, double>), grid, block, 0, lv, r0, pin, pout, scal, ki);
                 kt.end();
-                if (dist) {
-                    SA_TRY(dist_halo<double>(s, 0, pout, s->pitch, s->plane, 1, 1));
-                    SA_TRY(dist_reduce(s, DIST_PQ, ki & 3, (ki + 2) & 3));
-                }
+                if (dist)
+                    SA_TRY(dist_step(s, 0, DIST_VEC_DIR, pout, 8, s->pitch, s->plane, 1, 1, DIST_PQ, ki & 3, (ki + 2) & 3));
                 kt.begin(KC_UPDATE, n * live);
                 if (strip)
                     SA_TRY(launch_update2(ctx, lv, nb, true, u0, pout, false, r0, nullptr, scal, ki));
@@ -732,8 +708,7 @@ int solve_scene(sa_scene* s, const sa_options& o, sa_stats* stats)
                     SA_LAUNCH(ctx, (k_update<true, false>), grid, block, 0, lv, u0, pout, r0, nullptr, scal, ki);
                 kt.end();
                 if (dist) {  // ranks must agree on the stop: test it from the reduced norm after every iteration
-                    SA_TRY(dist_halo<double>(s, 0, r0, s->pitch, s->plane, 1, 1));
-                    SA_TRY(dist_reduce(s, DIST_RR_RZ, (ki + 1) & 3, -1));
+                    SA_TRY(dist_step(s, 0, DIST_VEC_RHS, r0, 8, s->pitch, s->plane, 1, 1, DIST_RR_RZ, (ki + 1) & 3, -1));
                     SA_LAUNCH(ctx, k_check_converged, (nb + 63) / 64, 64, 0, scal, nb, ki + 1);
                 }
             }

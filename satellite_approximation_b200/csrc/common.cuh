@@ -88,6 +88,7 @@ struct sa_ctx {
     void* comm = nullptr;
     int rank = 0, world = 1;
     double* d_red = nullptr;  // packed per-band scalars for the all-reduce
+    void* peer = nullptr;  // peer-memory arena of the row decomposition (dist.cu: PeerState)
     unsigned* d_barrier = nullptr;  // arrival counter of the grid-wide barrier of the cooperative tail kernel (mg_rbw.cu)
     // host-pointer entry points: PCIe transfers of the other band chunks run on these while a chunk is solved
     cudaStream_t io_in = nullptr, io_out = nullptr;
@@ -353,6 +354,11 @@ int dist_reduce_unpack(sa_scene* s, int what, int slot, int clear_slot);
 int dist_group_begin(sa_scene* s);
 int dist_group_end(sa_scene* s);
 int dist_allgather_band(sa_scene* s, int band);
+// one exchange step (halo rows of a vector and / or the sum of a group of per-band scalars), over peer memory or NCCL
+int dist_step(sa_scene* s, int level, int vec, void* base, int elem_bytes, int64_t pitch, int64_t plane, int above, int below, int what,
+    int slot, int clear_slot);
+int dist_uses_peer_memory(const sa_ctx* ctx);
+enum DistVec { DIST_VEC_RHS = 0, DIST_VEC_SOL = 1, DIST_VEC_DIR = 2 };
 
 // ---- mg_fused.cu -------------------------------------------------------------------------------------------------
 int launch_mg_down(sa_ctx* ctx, const Level& lf, const Level& lc, int nbands, const double* b, double* x_out, double* bc,

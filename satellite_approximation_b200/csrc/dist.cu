@@ -37,6 +37,7 @@ struct NcclApi {
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
@@ -61,18 +62,28 @@ NcclApi& nccl()
         SA_SYM(CommDestroy);
         SA_SYM(AllReduce);
         SA_SYM(Broadcast);
+        SA_SYM(AllGather);
         SA_SYM(Send);
         SA_SYM(Recv);
         SA_SYM(GroupStart);
         SA_SYM(GroupEnd);
         SA_SYM(GetErrorString);
 #undef SA_SYM
-        a.ok = a.GetUniqueId && a.CommInitRank && a.CommDestroy && a.AllReduce && a.Broadcast && a.Send && a.Recv
+        a.ok = a.GetUniqueId && a.CommInitRank && a.CommDestroy && a.AllReduce && a.Broadcast && a.AllGather && a.Send && a.Recv
             && a.GroupStart && a.GroupEnd && a.GetErrorString;
         return a;
     }();
     return api;
 }
+
+// Inside a GroupStart / GroupEnd pair: remember the first failure, keep going to the GroupEnd (a return from inside an open
+// group would leave it open and the peers blocked in their half of the exchange).
+#define SA_NCCL_IN_GROUP(first_error, expr)                                     \
+    do {                                                                        \
+        ncclResult_t r__ = (expr);                                              \
+        if (r__ != ncclSuccess && (first_error) == ncclSuccess)                 \
+            (first_error) = r__;                                                \
+    } while (0)
 
 #define SA_NCCL(ctx, expr)                                                                                        \
     do {                                                                                                          \
@@ -135,6 +146,184 @@ __global__ void k_unpack(BandScalars* __restrict__ scal, int nbands, int what, i
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// Peer-memory exchange (NVLink / NVSwitch, CUDA IPC): the exchanges of the iteration loop without a collective library.
+//
+// Inside the CG loop every exchange is tiny -- one to three halo rows per neighbour (3 to 240 KB) and 3 doubles per band --
+// so what it costs is launch and protocol latency, not bandwidth: ten NCCL launches per iteration were half a millisecond
+// against 0.9 ms of arithmetic at 8 GPUs.  Here every rank owns an ARENA in its HBM that all ranks of the node map (CUDA
+// IPC handles, all-gathered once per plan over the NCCL communicator), and one exchange is two small kernels on the
+// solver's stream:
+//   k_peer_push   stores my boundary rows straight into the neighbours' arenas and my partial sums into every peer's
+//                 arena (remote stores over NVLink), fences (system scope), and raises one flag per receiver to the epoch
+//                 of this exchange;
+//   k_peer_pull   waits (acquire, system scope) until the flags of my senders have reached the epoch, moves the rows from
+//                 my arena into the halo rows of my plane and adds the partial sums of all ranks IN RANK ORDER -- every
+//                 rank computes bit-identical sums, so all ranks take every decision of the solve together.
+// No rank ever waits inside a push, so the pushes of all ranks always complete and the pulls cannot deadlock.  A slot of
+// the arena is reused one CG iteration later; between two uses of a slot lies at least one all-rank reduction, which no
+// rank can leave before every rank has pushed for it -- i.e. before every rank has, in stream order, drained the slot.
+// The reduction slots themselves alternate between two buffers for the same reason.
+// ---------------------------------------------------------------------------------------------------------------------------
+constexpr int PEER_MAX_WORLD = 64, PEER_MAX_BANDS = 64, PEER_KINDS = 3 * 8;
+constexpr size_t PEER_FLAG_BYTES = 4096;                                                 // halo flags [kind][2], then reduction flags [rank]
+constexpr size_t PEER_AR_BYTES = sizeof(double) * 2 * PEER_MAX_WORLD * 3 * PEER_MAX_BANDS;  // [parity][rank][3 * band]
+constexpr size_t PEER_HALO_OFF = ((PEER_FLAG_BYTES + PEER_AR_BYTES + 255) / 256) * 256;
+
+struct PeerState {
+    bool ok = false;
+    char* arena = nullptr;  // my arena (device memory of this rank)
+    size_t arena_bytes = 0;
+    std::vector<char*> peer;  // every rank's arena as this process maps it ([rank] = arena)
+    size_t slot_off[PEER_KINDS][2] = {};    // byte offset of the (kind, direction) staging slot in a rank's arena
+    size_t slot_bytes[PEER_KINDS] = {};
+    unsigned long long halo_epoch[PEER_KINDS] = {};
+    unsigned long long ar_epoch = 0;
+    unsigned* d_ticket = nullptr;
+    size_t refused_bytes = 0;  // an arena of this size could not be shared (or sharing is switched off): stay on NCCL
+};
+
+struct PeerHalo {       // one exchange as the kernels see it
+    char* base;         // element (0, 0) of band 0 of my plane
+    int64_t row_bytes, plane_bytes;
+    int nbands;
+    int64_t send_up_row, send_up_rows;      // my first rows -> the rank above (its halo below)
+    int64_t send_down_row, send_down_rows;  // my last rows -> the rank below (its halo above)
+    int64_t recv_up_row, recv_up_rows;      // the rows above my slice <- the rank above
+    int64_t recv_down_row, recv_down_rows;  // the rows below my slice <- the rank below
+    char* up_slot;      // the slot in the arena of the rank above that receives from below
+    char* down_slot;    // the slot in the arena of the rank below that receives from above
+    char* my_from_up;   // my own slots
+    char* my_from_down;
+    unsigned long long* up_flag;    // flags to raise (in the neighbours' arenas) and to wait for (in mine)
+    unsigned long long* down_flag;
+    unsigned long long* my_up_flag;
+    unsigned long long* my_down_flag;
+    unsigned long long epoch;
+};
+struct PeerReduce {
+    int on, what, slot, clear_slot, nbands, rank, world, parity;
+    unsigned long long epoch;
+    char* peer[PEER_MAX_WORLD];  // arenas
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// rows [row, row + rows) of every band, packed band after band
+__device__ __forceinline__ void copy_rows(char* dst, bool dst_packed, const char* src, bool src_packed, int64_t rows, int64_t row_bytes,
+    int64_t plane_bytes, int nbands, int t, int nt)
+{
+    const int64_t per_band = rows * row_bytes, n16 = per_band >> 4;  // rows are multiples of 128 bytes
+    for (int b = 0; b < nbands; ++b) {
+        const uint4* sp = reinterpret_cast<const uint4*>(src + (src_packed ? b * per_band : b * plane_bytes));
+        uint4* dp = reinterpret_cast<uint4*>(dst + (dst_packed ? b * per_band : b * plane_bytes));
+        for (int64_t i = t; i < n16; i += nt)
+            dp[i] = sp[i];
+    }
+}
+
+__global__ void __launch_bounds__(256) k_peer_push(PeerHalo H, PeerReduce R, const BandScalars* __restrict__ scal, unsigned* __restrict__ ticket)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+    if (H.send_up_rows > 0)
+        copy_rows(H.up_slot, true, H.base + H.send_up_row * H.row_bytes, false, H.send_up_rows, H.row_bytes, H.plane_bytes, H.nbands, t, nt);
+    if (H.send_down_rows > 0)
+        copy_rows(H.down_slot, true, H.base + H.send_down_row * H.row_bytes, false, H.send_down_rows, H.row_bytes, H.plane_bytes, H.nbands, t, nt);
+    if (R.on && blockIdx.x == 0) {
+        // my partial sums into slot [parity][my rank] of every rank's arena (my own included)
+        for (int i = threadIdx.x; i < R.world * R.nbands; i += blockDim.x) {
+            const int peer = i / R.nbands, b = i - peer * R.nbands;
+            const BandScalars& sc = scal[b];
+            double v0, v1 = 0.0, v2 = 0.0;
+            if (R.what == DIST_SETUP)
+                v0 = sc.bnorm2, v1 = sc.rr[0], v2 = sc.rz[0];
+            else if (R.what == DIST_RZ)
+                v0 = sc.rz[R.slot];
+            else if (R.what == DIST_PQ)
+                v0 = sc.pq[R.slot];
+            else
+                v0 = sc.rr[R.slot], v1 = sc.rz[R.slot];
+            double* o = reinterpret_cast<double*>(R.peer[peer] + PEER_FLAG_BYTES) + ((size_t)(R.parity * PEER_MAX_WORLD + R.rank) * PEER_MAX_BANDS + b) * 3;
+            o[0] = v0, o[1] = v1, o[2] = v2;
+        }
+    }
+    // the last CTA to get here raises the flags: everything every CTA stored is then visible system-wide
+    __threadfence_system();
+    __syncthreads();
+    __shared__ unsigned last;
+    if (threadIdx.x == 0)
+        last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (last) {
+        __threadfence_system();
+        if (threadIdx.x == 0) {
+            *ticket = 0;
+            if (H.send_up_rows > 0)
+                st_release_sys(H.up_flag, H.epoch);
+            if (H.send_down_rows > 0)
+                st_release_sys(H.down_flag, H.epoch);
+        }
+        if (R.on)
+            for (int peer = threadIdx.x; peer < R.world; peer += blockDim.x)
+                st_release_sys(reinterpret_cast<unsigned long long*>(R.peer[peer] + 2048) + R.rank, R.epoch);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_peer_pull(PeerHalo H, PeerReduce R, BandScalars* __restrict__ scal)
+{
+    if (threadIdx.x == 0) {
+        if (H.recv_up_rows > 0)
+            while (ld_acquire_sys(H.my_up_flag) < H.epoch) { }
+        if (H.recv_down_rows > 0)
+            while (ld_acquire_sys(H.my_down_flag) < H.epoch) { }
+    }
+    if (R.on && blockIdx.x == 0 && threadIdx.x < R.world)
+        while (ld_acquire_sys(reinterpret_cast<const unsigned long long*>(R.peer[R.rank] + 2048) + threadIdx.x) < R.epoch) { }
+    __syncthreads();
+    const int t = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+    if (H.recv_up_rows > 0)
+        copy_rows(H.base + H.recv_up_row * H.row_bytes, false, H.my_from_up, true, H.recv_up_rows, H.row_bytes, H.plane_bytes, H.nbands, t, nt);
+    if (H.recv_down_rows > 0)
+        copy_rows(H.base + H.recv_down_row * H.row_bytes, false, H.my_from_down, true, H.recv_down_rows, H.row_bytes, H.plane_bytes, H.nbands, t, nt);
+    if (R.on && blockIdx.x == 0) {
+        for (int b = threadIdx.x; b < R.nbands; b += blockDim.x) {
+            const double* base = reinterpret_cast<const double*>(R.peer[R.rank] + PEER_FLAG_BYTES) + (size_t)R.parity * PEER_MAX_WORLD * PEER_MAX_BANDS * 3;
+            double v0 = 0.0, v1 = 0.0, v2 = 0.0;
+            for (int r = 0; r < R.world; ++r) {  // rank order: the same sum, bit for bit, on every rank
+                const double* o = base + ((size_t)r * PEER_MAX_BANDS + b) * 3;
+                v0 += o[0], v1 += o[1], v2 += o[2];
+            }
+            BandScalars& sc = scal[b];
+            if (R.what == DIST_SETUP)
+                sc.bnorm2 = v0, sc.rr[0] = v1, sc.rz[0] = v2;
+            else if (R.what == DIST_RZ)
+                sc.rz[R.slot] = v0;
+            else if (R.what == DIST_PQ)
+                sc.pq[R.slot] = v0;
+            else {
+                sc.rr[R.slot] = v0;
+                if (R.what == DIST_RR_RZ)
+                    sc.rz[R.slot] = v1;
+            }
+            if (R.clear_slot >= 0) {  // see k_unpack
+                sc.rz[R.clear_slot] = 0.0;
+                sc.rr[R.clear_slot] = 0.0;
+                sc.pq[R.clear_slot] = 0.0;
+            }
+        }
+    }
+}
+
 }  // namespace
 
 // ---- partition (host logic; also exported through the C-ABI so that it can be tested without a GPU) ---------------
@@ -194,8 +383,25 @@ int dist_init(sa_ctx* ctx, const void* id128, int rank, int world)
     return SA_OK;
 }
 
+static void peer_release(sa_ctx* ctx)
+{
+    PeerState* P = (PeerState*)ctx->peer;
+    if (!P)
+        return;
+    for (size_t r = 0; r < P->peer.size(); ++r)
+        if (P->peer[r] && (int)r != ctx->rank)
+            cudaIpcCloseMemHandle(P->peer[r]);
+    cudaFree(P->arena);
+    cudaFree(P->d_ticket);
+    delete P;
+    ctx->peer = nullptr;
+}
+
 void dist_shutdown(sa_ctx* ctx)
 {
+    if (ctx->comm)
+        cudaStreamSynchronize(ctx->stream);
+    peer_release(ctx);
     if (ctx->comm && nccl().ok)
         nccl().CommDestroy((ncclComm_t)ctx->comm);
     ctx->comm = nullptr;
@@ -216,6 +422,8 @@ static int slice_tiles(sa_ctx* ctx, const int32_t* d_list, int n_tiles, int tile
     *hi = (int)(std::lower_bound(h.begin(), h.end(), (int32_t)((int64_t)ty_hi * tiles_x)) - h.begin());
     return SA_OK;
 }
+
+static int peer_plan(sa_scene* s);
 
 int dist_plan_scene(sa_scene* s, bool multigrid)
 {
@@ -265,6 +473,191 @@ int dist_plan_scene(sa_scene* s, bool multigrid)
             s->dist_gather_rows[(size_t)k] = std::min(rb[(size_t)k] >> levels, (int64_t)R.lv.tiles_y * TILE_H);
     }
     s->dist_planned = true;
+    SA_TRY(peer_plan(s));
+    return SA_OK;
+}
+
+
+// ---- peer-memory arena: layout for a scene, allocation, exchange of the IPC handles ----------------------------------------
+// Collective: every rank calls it with the same scene shape (dist_plan_scene).  Falls back to NCCL for the whole
+// communicator (P->ok = false on every rank) when any rank cannot map a peer's arena, or when SATFILL_DIST_NCCL_ONLY is set.
+static int peer_plan(sa_scene* s)
+{
+    sa_ctx* ctx = s->ctx;
+    const int world = ctx->world, rank = ctx->rank;
+    if (world > PEER_MAX_WORLD || s->nbands > PEER_MAX_BANDS || s->dist_levels > PEER_KINDS / 3)
+        return SA_OK;  // stays on NCCL
+    PeerState* P = (PeerState*)ctx->peer;
+    if (!P) {
+        P = new PeerState();
+        ctx->peer = P;
+        SA_CUDA(ctx, cudaMalloc(&P->d_ticket, sizeof(unsigned)));
+        SA_CUDA(ctx, cudaMemsetAsync(P->d_ticket, 0, sizeof(unsigned), ctx->stream));
+    }
+    // staging slots: (level, vector) x (from above, from below), up to 3 rows of doubles per band
+    size_t off = PEER_HALO_OFF;
+    for (int k = 0; k < PEER_KINDS; ++k)
+        P->slot_bytes[k] = 0;
+    for (int l = 0; l < s->dist_levels; ++l) {
+        const int64_t pitch = l == 0 ? s->pitch : s->coarse[(size_t)l - 1].lv.pitch;
+        for (int v = 0; v < 3; ++v) {
+            const int k = l * 3 + v;
+            P->slot_bytes[k] = (size_t)(3 * pitch * (int64_t)sizeof(double)) * (size_t)s->nbands;
+            for (int d = 0; d < 2; ++d) {
+                P->slot_off[k][d] = off;
+                off += (P->slot_bytes[k] + 255) / 256 * 256;
+            }
+        }
+    }
+    if (off <= P->arena_bytes || off <= P->refused_bytes)
+        return SA_OK;  // the arena of an earlier plan is large enough (every rank sees the same history of shapes)
+    const bool forced_off = std::getenv("SATFILL_DIST_NCCL_ONLY") != nullptr;
+    // a new, larger arena: allocate, all-gather the handles over the NCCL communicator, map the peers, then drop the old one
+    // (the all-gather orders this after everything any rank still had in flight on the old arena)
+    char* fresh = nullptr;
+    const size_t bytes = off + (off >> 2);
+    SA_CUDA(ctx, cudaMalloc(&fresh, bytes));
+    SA_CUDA(ctx, cudaMemsetAsync(fresh, 0, bytes, ctx->stream));
+    cudaIpcMemHandle_t mine {};
+    int ok = forced_off ? 0 : (cudaIpcGetMemHandle(&mine, fresh) == cudaSuccess ? 1 : 0);
+    cudaGetLastError();
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    char* d_h = nullptr;
+    SA_CUDA(ctx, cudaMalloc(&d_h, (size_t)world * 64 + sizeof(int)));
+    SA_CUDA(ctx, cudaMemcpyAsync(d_h + (size_t)rank * 64, &mine, 64, cudaMemcpyHostToDevice, ctx->stream));
+    SA_NCCL(ctx, nccl().AllGather(d_h + (size_t)rank * 64, d_h, 64, ncclChar, (ncclComm_t)ctx->comm, ctx->stream));
+    std::vector<cudaIpcMemHandle_t> all((size_t)world);
+    SA_CUDA(ctx, cudaMemcpyAsync(all.data(), d_h, (size_t)world * 64, cudaMemcpyDeviceToHost, ctx->stream));
+    SA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    std::vector<char*> mapped((size_t)world, nullptr);
+    mapped[(size_t)rank] = fresh;
+    for (int r = 0; r < world && ok; ++r) {
+        if (r == rank)
+            continue;
+        void* q = nullptr;
+        if (cudaIpcOpenMemHandle(&q, all[(size_t)r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+            ok = 0;
+            cudaGetLastError();
+        }
+        mapped[(size_t)r] = (char*)q;
+    }
+    // every rank must agree
+    int* d_ok = reinterpret_cast<int*>(d_h + (size_t)world * 64);
+    SA_CUDA(ctx, cudaMemcpyAsync(d_ok, &ok, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    SA_NCCL(ctx, nccl().AllReduce(d_ok, d_ok, 1, ncclInt, ncclMin, (ncclComm_t)ctx->comm, ctx->stream));
+    SA_CUDA(ctx, cudaMemcpyAsync(&ok, d_ok, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    SA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(d_h);
+    // the old arena and its mappings
+    for (size_t r = 0; r < P->peer.size(); ++r)
+        if (P->peer[r] && (int)r != rank)
+            cudaIpcCloseMemHandle(P->peer[r]);
+    cudaFree(P->arena);
+    if (!ok) {
+        for (int r = 0; r < world; ++r)
+            if (r != rank && mapped[(size_t)r])
+                cudaIpcCloseMemHandle(mapped[(size_t)r]);
+        cudaFree(fresh);
+        P->arena = nullptr;
+        P->arena_bytes = 0;
+        P->peer.clear();
+        P->ok = false;
+        P->refused_bytes = off;
+        return SA_OK;
+    }
+    P->arena = fresh;
+    P->arena_bytes = bytes;
+    P->peer = mapped;
+    for (int k = 0; k < PEER_KINDS; ++k)
+        P->halo_epoch[k] = 0;
+    P->ar_epoch = 0;
+    P->ok = true;
+    return SA_OK;
+}
+
+int dist_uses_peer_memory(const sa_ctx* ctx)
+{
+    const PeerState* P = (const PeerState*)ctx->peer;
+    return P && P->ok ? 1 : 0;
+}
+
+// One exchange step of the row-decomposed solve on the solver's stream: the halo rows of one vector of level `level`
+// (base != nullptr: `above` rows wanted above the slice, `below` rows below it; vec 0 = right-hand side / residual,
+// 1 = iterate / correction, 2 = search direction) and / or the sum over the ranks of one group of per-band scalars
+// (what >= 0: DistWhat; clear_slot as in dist_reduce_unpack).  Over peer memory when the arena is mapped, else over NCCL.
+int dist_step(sa_scene* s, int level, int vec, void* base, int elem_bytes, int64_t pitch, int64_t plane, int above, int below, int what,
+    int slot, int clear_slot)
+{
+    sa_ctx* ctx = s->ctx;
+    if (!s->dist_planned || ctx->world == 1)
+        return SA_OK;
+    PeerState* P = (PeerState*)ctx->peer;
+    if (!P || !P->ok) {
+        if (what >= 0)
+            SA_TRY(dist_reduce_pack(s, what, slot));
+        SA_TRY(dist_group_begin(s));
+        int st = SA_OK;
+        if (what >= 0)
+            st = dist_reduce_issue(s);
+        if (st == SA_OK && base)
+            st = elem_bytes == 8 ? dist_halo<double>(s, level, (double*)base, pitch, plane, above, below)
+                                 : dist_halo<float>(s, level, (float*)base, pitch, plane, above, below);
+        int st2 = dist_group_end(s);  // always closes the group, also on an error inside it
+        if (st != SA_OK)
+            return st;
+        SA_TRY(st2);
+        if (what >= 0)
+            SA_TRY(dist_reduce_unpack(s, what, slot, clear_slot));
+        return SA_OK;
+    }
+    const int rank = ctx->rank, world = ctx->world;
+    const DistLevel& d = s->dl[(size_t)level];
+    const bool mine = d.row_hi > d.row_lo;
+    const int up = rank - 1, down = rank + 1;
+    const bool has_up = base && mine && up >= 0 && d.row_lo > 0;
+    const bool has_down = base && mine && down < world && d.bounds[(size_t)down + 1] > d.bounds[(size_t)down];
+    const int kind = level * 3 + vec;
+    PeerHalo H {};
+    H.base = (char*)base;
+    H.row_bytes = pitch * elem_bytes;
+    H.plane_bytes = plane * elem_bytes;
+    H.nbands = s->nbands;
+    if (base) {
+        if ((size_t)(std::max(above, below) * H.row_bytes) * (size_t)s->nbands > P->slot_bytes[kind])
+            return fail(ctx, SA_BAD_ARGUMENT, "distributed solve: halo rows do not fit their staging slot");
+        H.epoch = ++P->halo_epoch[kind];
+        unsigned long long* my_flags = reinterpret_cast<unsigned long long*>(P->arena);
+        H.my_up_flag = my_flags + kind * 2 + 0;
+        H.my_down_flag = my_flags + kind * 2 + 1;
+        H.my_from_up = P->arena + P->slot_off[kind][0];
+        H.my_from_down = P->arena + P->slot_off[kind][1];
+        if (has_up) {  // the rank above receives my first rows as its halo BELOW
+            H.send_up_row = d.row_lo, H.send_up_rows = below;
+            H.recv_up_row = d.row_lo - above, H.recv_up_rows = above;
+            H.up_slot = P->peer[(size_t)up] + P->slot_off[kind][1];
+            H.up_flag = reinterpret_cast<unsigned long long*>(P->peer[(size_t)up]) + kind * 2 + 1;
+        }
+        if (has_down) {  // the rank below receives my last rows as its halo ABOVE
+            H.send_down_row = d.row_hi - above, H.send_down_rows = above;
+            H.recv_down_row = d.row_hi, H.recv_down_rows = below;
+            H.down_slot = P->peer[(size_t)down] + P->slot_off[kind][0];
+            H.down_flag = reinterpret_cast<unsigned long long*>(P->peer[(size_t)down]) + kind * 2 + 0;
+        }
+    }
+    PeerReduce R {};
+    R.on = what >= 0 ? 1 : 0;
+    if (R.on) {
+        R.what = what, R.slot = slot, R.clear_slot = clear_slot, R.nbands = s->nbands, R.rank = rank, R.world = world;
+        R.epoch = ++P->ar_epoch;
+        R.parity = (int)(R.epoch & 1);
+        for (int r = 0; r < world; ++r)
+            R.peer[r] = P->peer[(size_t)r];
+    }
+    const int64_t bytes = (int64_t)std::max(above, below) * H.row_bytes * s->nbands;
+    const unsigned grid = !base ? 1u : (bytes > (1 << 20) ? 32u : (bytes > (64 << 10) ? 8u : 2u));
+    SA_LAUNCH(ctx, k_peer_push, grid, 256, 0, H, R, s->scal, P->d_ticket);
+    SA_LAUNCH(ctx, k_peer_pull, grid, 256, 0, H, R, s->scal);
+    SA_CUDA(ctx, cudaGetLastError());
     return SA_OK;
 }
 
@@ -298,20 +691,22 @@ int dist_halo(sa_scene* s, int l, T* base, int64_t pitch, int64_t plane, int abo
     // ranks whose slice is empty at this level (row_lo == row_hi) neither own nor need rows; the partition hands out
     // whole blocks to the leading ranks, so empty slices only occur at the tail and never sit between two non-empty ones
     const bool mine = d.row_hi > d.row_lo;
+    ncclResult_t bad = ncclSuccess;
     SA_NCCL(ctx, nccl().GroupStart());
     for (int b = 0; b < s->nbands; ++b) {
         T* p = base + (int64_t)b * plane;
         if (mine && up >= 0 && d.row_lo > 0) {
             // the rank above needs `below` rows from my top; I need `above` rows from its bottom
-            SA_NCCL(ctx, nccl().Send(p + d.row_lo * pitch, (size_t)(below * pitch), dt, up, comm, ctx->stream));
-            SA_NCCL(ctx, nccl().Recv(p + (d.row_lo - above) * pitch, (size_t)(above * pitch), dt, up, comm, ctx->stream));
+            SA_NCCL_IN_GROUP(bad, nccl().Send(p + d.row_lo * pitch, (size_t)(below * pitch), dt, up, comm, ctx->stream));
+            SA_NCCL_IN_GROUP(bad, nccl().Recv(p + (d.row_lo - above) * pitch, (size_t)(above * pitch), dt, up, comm, ctx->stream));
         }
         if (mine && down < ctx->world && d.bounds[(size_t)down + 1] > d.bounds[(size_t)down]) {
-            SA_NCCL(ctx, nccl().Send(p + (d.row_hi - above) * pitch, (size_t)(above * pitch), dt, down, comm, ctx->stream));
-            SA_NCCL(ctx, nccl().Recv(p + d.row_hi * pitch, (size_t)(below * pitch), dt, down, comm, ctx->stream));
+            SA_NCCL_IN_GROUP(bad, nccl().Send(p + (d.row_hi - above) * pitch, (size_t)(above * pitch), dt, down, comm, ctx->stream));
+            SA_NCCL_IN_GROUP(bad, nccl().Recv(p + d.row_hi * pitch, (size_t)(below * pitch), dt, down, comm, ctx->stream));
         }
     }
-    SA_NCCL(ctx, nccl().GroupEnd());
+    SA_NCCL_IN_GROUP(bad, nccl().GroupEnd());
+    SA_NCCL(ctx, bad);
     return SA_OK;
 }
 template int dist_halo<double>(sa_scene*, int, double*, int64_t, int64_t, int, int);
@@ -324,6 +719,7 @@ int dist_gather(sa_scene* s, float* base, int64_t pitch, int64_t plane)
     if (!s->dist_planned || ctx->world == 1)
         return SA_OK;
     const ncclComm_t comm = (ncclComm_t)ctx->comm;
+    ncclResult_t bad = ncclSuccess;
     SA_NCCL(ctx, nccl().GroupStart());
     for (int b = 0; b < s->nbands; ++b)
         for (int k = 0; k < ctx->world; ++k) {
@@ -331,9 +727,10 @@ int dist_gather(sa_scene* s, float* base, int64_t pitch, int64_t plane)
             if (hi <= lo)
                 continue;
             float* p = base + (int64_t)b * plane + lo * pitch;
-            SA_NCCL(ctx, nccl().Broadcast(p, p, (size_t)((hi - lo) * pitch), ncclFloat32, k, comm, ctx->stream));
+            SA_NCCL_IN_GROUP(bad, nccl().Broadcast(p, p, (size_t)((hi - lo) * pitch), ncclFloat32, k, comm, ctx->stream));
         }
-    SA_NCCL(ctx, nccl().GroupEnd());
+    SA_NCCL_IN_GROUP(bad, nccl().GroupEnd());
+    SA_NCCL(ctx, bad);
     return SA_OK;
 }
 
@@ -344,15 +741,17 @@ int dist_allgather_band(sa_scene* s, int band)
     if (!s->dist_planned || ctx->world == 1)
         return SA_OK;
     const DistLevel& d = s->dl[0];
+    ncclResult_t bad = ncclSuccess;
     SA_NCCL(ctx, nccl().GroupStart());
     for (int k = 0; k < ctx->world; ++k) {
         int64_t lo = d.bounds[(size_t)k], hi = std::min(d.bounds[(size_t)k + 1], s->rows_p);
         if (hi <= lo)
             continue;
         double* p = s->plane0(s->u, band) + lo * s->pitch;
-        SA_NCCL(ctx, nccl().Broadcast(p, p, (size_t)((hi - lo) * s->pitch), ncclFloat64, k, (ncclComm_t)ctx->comm, ctx->stream));
+        SA_NCCL_IN_GROUP(bad, nccl().Broadcast(p, p, (size_t)((hi - lo) * s->pitch), ncclFloat64, k, (ncclComm_t)ctx->comm, ctx->stream));
     }
-    SA_NCCL(ctx, nccl().GroupEnd());
+    SA_NCCL_IN_GROUP(bad, nccl().GroupEnd());
+    SA_NCCL(ctx, bad);
     return SA_OK;
 }
 

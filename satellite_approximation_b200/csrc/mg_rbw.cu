@@ -956,7 +956,8 @@ int apply_vcycle_rbw(sa_scene* s, const sa_options& o, KernelTimer& kt, int rz_s
             // everywhere (nothing of this level travels: the ascent recomputes the red half of the iterate from b, whose halo
             // rows it already holds)
             if (l + 1 < dlv)
-                SA_TRY(dist_halo<float>(s, l + 1, L[(size_t)l + 1].b, L[(size_t)l + 1].lv.pitch, L[(size_t)l + 1].lv.plane, 3, 3));
+                SA_TRY(dist_step(s, l + 1, DIST_VEC_RHS, L[(size_t)l + 1].b, 4, L[(size_t)l + 1].lv.pitch, L[(size_t)l + 1].lv.plane, 3, 3, -1,
+                    0, -1));
             else
                 SA_TRY(dist_gather(s, L[(size_t)l + 1].b, L[(size_t)l + 1].lv.pitch, L[(size_t)l + 1].lv.plane));
         }
@@ -979,7 +980,7 @@ int apply_vcycle_rbw(sa_scene* s, const sa_options& o, KernelTimer& kt, int rz_s
         // the finer level's ascent interpolates from up to 2 coarse rows beyond.  (Level 0: CG's direction needs 1 row of z;
         // the caller exchanges it in one group with the all-reduce of r.z -- cg.cu.)
         if (l < dlv && l > 0)
-            SA_TRY(dist_halo<float>(s, l, L[(size_t)l].x, L[(size_t)l].lv.pitch, L[(size_t)l].lv.plane, 2, 2));
+            SA_TRY(dist_step(s, l, DIST_VEC_SOL, L[(size_t)l].x, 4, L[(size_t)l].lv.pitch, L[(size_t)l].lv.plane, 2, 2, -1, 0, -1));
     }
     SA_CUDA(ctx, cudaGetLastError());
     return SA_OK;
