@@ -477,11 +477,7 @@ def run_b200(args, w):
     clocks = sampler.stop()
     launches = timed.launches
     st = timed.st
-    unit_scale = 1.0
-    if one_system and world > 1:
-        # the library counts a launch's units as the whole system's unknowns: a rank processes its share of the rows
-        lo, hi, _ = scene.owned_rows()
-        unit_scale = (hi - lo) / rows
+    unit_scale = 1.0  # the library's per-launch units are the unknowns THIS rank processed (row-decomposed solves included)
     unknowns = st[0]["unknowns"]
     ok = all(s["status"] == sab.SA_OK for s in st)
     worst_err = max(s["error"] for s in st)
@@ -818,7 +814,7 @@ def run_row_decomposed(args, ctx, sab, rank, world, dev, stream, barrier, multi,
     del mask
     torch.cuda.empty_cache()
     ms_max, _ = multi.reduce_step(ms, 0.0, True, dev)
-    tab = kernel_table(t, True, (hi - lo) / n)
+    tab = kernel_table(t, True)
     for v in tab.values():
         v["frac"] = v["GBps"] / peak if v["GBps"] else None
     return {"what": f"single {n}x{n} contiguous hole, one system split by rows over {world} GPU(s)"

@@ -591,8 +591,14 @@ int sa_scene_set_distributed(sa_scene* s, int on)
         return SA_BAD_ARGUMENT;
     if (on && !s->ctx->comm)
         return fail(s->ctx, SA_BAD_ARGUMENT, "scene_set_distributed: the context has no communicator (sa_dist_init)");
+    if (s->distributed != (on != 0)) {
+        // a split scene only ever scrubs its own rows: switching modes clears the work vectors wholesale and re-indexes
+        s->work_dirty |= 8;  // WORK_FULL
+        s->indexed = false;
+    }
     s->distributed = on != 0;
     s->dist_planned = false;
+    s->dist_no_window = false;
     return SA_OK;
 }
 

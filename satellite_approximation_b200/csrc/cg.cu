@@ -426,6 +426,8 @@ int ensure_indexed(sa_scene* s, int next_kind)
         SA_TRY(scrub_work_vectors(s, lean));
     }
     s->work_dirty = WORK_CLEAN;
+    // a row-decomposed scene indexes only its own rows (dist.cu)
+    SA_TRY(dist_prepare_window(s, next_kind != WORK_JACOBI));
     SA_TRY(index_scene(s));
     s->ever_indexed = true;
     s->hierarchy_built = false;
@@ -580,8 +582,19 @@ int solve_scene(sa_scene* s, const sa_options& o, sa_stats* stats)
     if (dist) {
         if (!strip || (mg && !rb))
             return fail(ctx, SA_BAD_ARGUMENT, "distributed solve: needs the strip CG kernels and the red-black cycle");
-        if (!s->dist_planned || s->dist_mg != mg)
-            SA_TRY(dist_plan_scene(s, mg));
+        if (!s->dist_planned || s->dist_mg != mg) {
+            int pst = dist_plan_scene(s, mg);
+            if (pst == SA_RETRY_UNWINDOWED) {
+                // too small for the windowed set-up (or the preconditioner changed under the same mask): index the whole
+                // mask on every rank, as a scene that is not split does, and slice the tile lists
+                s->dist_no_window = true;
+                s->indexed = false;
+                s->work_dirty |= WORK_FULL;
+                SA_TRY(prepare_solve(s, o));
+                pst = dist_plan_scene(s, mg);
+            }
+            SA_TRY(pst);
+        }
     }
 
     Level lv = dist ? dist_level(s, 0, fine_level(s)) : fine_level(s);
@@ -628,6 +641,8 @@ int solve_scene(sa_scene* s, const sa_options& o, sa_stats* stats)
     KernelTimer kt;
     kt.ctx = ctx;
     kt.on = o.profile != 0;
+    // what the profile counts per launch: the unknowns THIS rank processes
+    const int64_t n_units = dist ? (int64_t)((double)n * s->dist_unit_frac) : n;
     BandScalars* h_scal = (BandScalars*)ctx->pinned;
     BandScalars* h_scal_dev = nullptr;  // the same memory as the device addresses it (k_publish_scalars)
     SA_CUDA(ctx, cudaHostGetDevicePointer((void**)&h_scal_dev, h_scal, 0));
@@ -670,7 +685,7 @@ int solve_scene(sa_scene* s, const sa_options& o, sa_stats* stats)
                 float* rf = rb ? s->rb_rf() : nullptr;
                 if (dist)  // r.z summed over the ranks and the halo row of z, one exchange
                     SA_TRY(dist_step(s, 0, DIST_VEC_SOL, rb ? (void*)s->rb_z() : nullptr, 4, s->pitch, s->plane, 1, 1, DIST_RZ, ki & 3, -1));
-                kt.begin(KC_DIRECTION, n * live);
+                kt.begin(KC_DIRECTION, n_units * live);
                 if (strip)
                     SA_TRY(launch_direction2(ctx, lv, nb, false, z, rb, pin_v, pout_v, pf, scal, ki));
                 else if (rb)
@@ -681,7 +696,7 @@ int solve_scene(sa_scene* s, const sa_options& o, sa_stats* stats)
                 if (dist)  // the halo row of p' and p'.Ap' in one exchange
                     SA_TRY(dist_step(s, 0, DIST_VEC_DIR, pf ? pout_v : (void*)pout, pf ? 4 : 8, s->pitch, s->plane, 1, 1, DIST_PQ, ki & 3,
                         (ki + 2) & 3));
-                kt.begin(KC_UPDATE, n * live);
+                kt.begin(KC_UPDATE, n_units * live);
                 if (strip)
                     SA_TRY(launch_update2(ctx, lv, nb, false, u0, pout_v, pf, r0, rf, scal, ki));
                 else if (rb)
@@ -693,7 +708,7 @@ int solve_scene(sa_scene* s, const sa_options& o, sa_stats* stats)
                     SA_TRY(dist_step(s, 0, DIST_VEC_RHS, rf, 4, s->pitch, s->plane, 3, 3, DIST_RR, (ki + 1) & 3, -1));
                 SA_LAUNCH(ctx, k_check_converged, (nb + 63) / 64, 64, 0, scal, nb, ki + 1);
             } else {
-                kt.begin(KC_DIRECTION, n * live);
+                kt.begin(KC_DIRECTION, n_units * live);
                 if (strip)
                     SA_TRY(launch_direction2(ctx, lv, nb, true, r0, false, pin, pout, false, scal, ki));
                 else
@@ -701,7 +716,7 @@ int solve_scene(sa_scene* s, const sa_options& o, sa_stats* stats)
                 kt.end();
                 if (dist)
                     SA_TRY(dist_step(s, 0, DIST_VEC_DIR, pout, 8, s->pitch, s->plane, 1, 1, DIST_PQ, ki & 3, (ki + 2) & 3));
-                kt.begin(KC_UPDATE, n * live);
+                kt.begin(KC_UPDATE, n_units * live);
                 if (strip)
                     SA_TRY(launch_update2(ctx, lv, nb, true, u0, pout, false, r0, nullptr, scal, ki));
                 else

@@ -132,6 +132,11 @@ struct DistLevel {
 struct sa_scene {
     // row decomposition (dist.cu)
     bool distributed = false, dist_planned = false, dist_mg = false;
+    // The mask is indexed -- unknown set, tile lists, bit words, coarse levels that are split by rows -- only on the rank's own
+    // tile rows (+ one tile row either side), so that the set-up of a row-decomposed solve scales with the ranks: see
+    // dist_prepare_window (dist.cu).  dist_no_window: the scene turned out too small for that (fewer usable levels than planned).
+    bool dist_windowed = false, dist_no_window = false, dist_mg_window = false;
+    double dist_unit_frac = 1.0;  // share of the rows this rank owns: the profile counts the unknowns a rank processes
     int dist_levels = 0;                      // multigrid levels that are split by rows; coarser ones are replicated
     std::vector<DistLevel> dl;
     std::vector<int64_t> dist_gather_rows;    // rows of the first replicated level each rank produces (world + 1)
@@ -285,13 +290,15 @@ int transpose_i32(sa_ctx* ctx, const int32_t* src, int64_t src_rows, int64_t src
     int64_t dst_pitch);
 // normalise to 0/1, build umask + active tile list + unknown count for a scene
 int index_scene(sa_scene* s);
+// number of unknowns of the whole mask (row-decomposed scenes index only their own rows)
+int count_unknowns(sa_scene* s, int64_t* out);
 // raster-order numbering / pixel list / bbox of a device mask (pitch bytes per row, non-zero = invalid)
 int device_numbering(sa_ctx* ctx, const uint8_t* mask, int64_t rows, int64_t cols, int64_t pitch, int32_t* numbering,
     int64_t* out_pixels, int64_t capacity, int64_t* out_count, int64_t bbox[4]);
 // flags[n_tiles] -> raster-ordered list of the flagged tiles; d_n_active (device, 4 ints) receives
 // {count, first tile, last tile}
 int compact_tile_flags(sa_ctx* ctx, const int32_t* flags, int n_tiles, int tiles_x, int32_t* tile_list, int32_t* tile_yx,
-    int32_t* d_n_active);
+    int32_t* d_n_active, int first_tile = 0);
 // exclusive scan helper shared with ccl.cu: in place over `n` 64-bit counters, total written to *total
 int device_scan_u64(sa_ctx* ctx, unsigned long long* data, int64_t n, unsigned long long* total);
 
@@ -343,6 +350,8 @@ int dist_unique_id(void* out128);
 int dist_init(sa_ctx* ctx, const void* id128, int rank, int world);
 void dist_shutdown(sa_ctx* ctx);
 int dist_plan_scene(sa_scene* s, bool multigrid);
+int dist_prepare_window(sa_scene* s, bool multigrid);  // before index_scene: the rows of every split level this rank owns
+constexpr int SA_RETRY_UNWINDOWED = -77;               // dist_plan_scene: index the whole mask and plan again
 Level dist_level(const sa_scene* s, int l, const Level& full);
 template <typename T>
 int dist_halo(sa_scene* s, int l, T* base, int64_t pitch, int64_t plane, int above, int below);

@@ -425,58 +425,124 @@ static int slice_tiles(sa_ctx* ctx, const int32_t* d_list, int n_tiles, int tile
 
 static int peer_plan(sa_scene* s);
 
-int dist_plan_scene(sa_scene* s, bool multigrid)
+// extents of level l of the hierarchy of a rows-high grid (mg.cu: alloc_hierarchy)
+static void level_rows(int64_t rows, int l, int64_t* lrows, int* ltiles_y)
 {
-    sa_ctx* ctx = s->ctx;
-    const int world = ctx->world, rank = ctx->rank;
-    int levels = 1;
-    if (multigrid) {
-        const int nl = 1 + (int)s->coarse.size();
-        levels = dist_choose_levels(s->rows, world);
-        // the coarsest level of the hierarchy is always replicated (its solver is one CTA per band)
-        int usable = 0;
-        for (int l = 1; l < nl; ++l)
-            if (s->coarse[l - 1].lv.n_tiles > 0)
-                usable = l;
-        if (levels > usable)
-            levels = usable;
-        if (levels < 1)
-            return fail(ctx, SA_BAD_ARGUMENT, "distributed solve: the scene is too small to be split by rows");
-    }
-    if ((s->rows + TILE_H - 1) / TILE_H < world)
-        return fail(ctx, SA_BAD_ARGUMENT, "distributed solve: fewer tile rows than ranks");
-    s->dist_levels = levels;
-    s->dist_mg = multigrid;
+    for (int i = 0; i < l; ++i)
+        rows = (rows + 1) / 2;
+    *lrows = rows;
+    int64_t rp = round_up(rows, TILE_H);
+    *ltiles_y = (int)((rp == 0 ? TILE_H : rp) / TILE_H);
+}
+
+// row boundaries of every split level and of the first replicated one
+static void fill_bounds(sa_scene* s, int levels)
+{
+    const int world = s->ctx->world, rank = s->ctx->rank;
     std::vector<int64_t> rb((size_t)world + 1);
     dist_partition(s->rows, world, levels, rb.data());
     s->dl.assign((size_t)levels, DistLevel {});
     for (int l = 0; l < levels; ++l) {
         DistLevel& d = s->dl[(size_t)l];
-        const int64_t lrows = l == 0 ? s->rows : s->coarse[l - 1].lv.rows;
-        const int lty = l == 0 ? s->tiles_y : s->coarse[l - 1].lv.tiles_y;
-        const int ltx = l == 0 ? s->tiles_x : s->coarse[l - 1].lv.tiles_x;
+        int64_t lrows;
+        int lty;
+        level_rows(s->rows, l, &lrows, &lty);
         d.bounds.resize((size_t)world + 1);
         for (int k = 0; k <= world; ++k)
             d.bounds[(size_t)k] = std::min(rb[(size_t)k] >> l, (int64_t)lty * TILE_H);
         d.row_lo = d.bounds[(size_t)rank];
         d.row_hi = d.bounds[(size_t)rank + 1];
         d.rows = lrows;
-        const int32_t* list = l == 0 ? s->tile_list : s->coarse[l - 1].tile_list;
-        const int n = l == 0 ? s->n_active_tiles : s->coarse[l - 1].lv.n_tiles;
-        SA_TRY(slice_tiles(ctx, list, n, ltx, (int)(d.row_lo / TILE_H), (int)(d.row_hi / TILE_H), &d.tile_lo, &d.tile_hi));
     }
     // the rows of the first replicated level that every rank produces (for the gather)
     s->dist_gather_rows.assign((size_t)world + 1, 0);
-    if (multigrid) {
-        const sa_level_store& R = s->coarse[(size_t)levels - 1];  // level `levels`
-        for (int k = 0; k <= world; ++k)
-            s->dist_gather_rows[(size_t)k] = std::min(rb[(size_t)k] >> levels, (int64_t)R.lv.tiles_y * TILE_H);
-    }
-    s->dist_planned = true;
-    SA_TRY(peer_plan(s));
+    int64_t rrows;
+    int rty;
+    level_rows(s->rows, levels, &rrows, &rty);
+    for (int k = 0; k <= world; ++k)
+        s->dist_gather_rows[(size_t)k] = std::min(rb[(size_t)k] >> levels, (int64_t)rty * TILE_H);
+}
+
+// Called BEFORE the mask is indexed: fixes the rows of every split level this rank owns, so that index_scene and
+// build_hierarchy only have to look at those rows (+ one tile row either side) -- the set-up of the row-decomposed solve
+// then scales with the ranks instead of being repeated by every rank on the whole mask.  The number of split levels is the
+// one dist_choose_levels wants; dist_plan_scene checks it against the hierarchy that came out and, for scenes too small
+// for it, asks for the unwindowed path (SA_RETRY_UNWINDOWED).
+int dist_prepare_window(sa_scene* s, bool multigrid)
+{
+    sa_ctx* ctx = s->ctx;
+    s->dist_windowed = false;
+    if (!s->distributed || ctx->world <= 1 || s->dist_no_window || std::getenv("SATFILL_DIST_NO_WINDOW"))
+        return SA_OK;
+    if ((s->rows + TILE_H - 1) / TILE_H < ctx->world)
+        return SA_OK;  // dist_plan_scene reports it
+    const int levels = multigrid ? dist_choose_levels(s->rows, ctx->world) : 1;
+    fill_bounds(s, levels);
+    s->dist_levels = levels;
+    s->dist_mg_window = multigrid;
+    s->dist_windowed = true;
     return SA_OK;
 }
 
+int dist_plan_scene(sa_scene* s, bool multigrid)
+{
+    sa_ctx* ctx = s->ctx;
+    const int world = ctx->world;
+    if ((s->rows + TILE_H - 1) / TILE_H < world)
+        return fail(ctx, SA_BAD_ARGUMENT, "distributed solve: fewer tile rows than ranks");
+    const int nl = 1 + (int)s->coarse.size();
+    if (s->dist_windowed) {
+        if (s->dist_mg_window != multigrid)
+            return SA_RETRY_UNWINDOWED;
+        if (multigrid) {
+            // the hierarchy must reach below the split levels: a replicated level with tiles (the replicated levels are the
+            // same on every rank, so every rank comes to the same conclusion; a split level's own list may well be empty)
+            bool deep_enough = false;
+            for (int l = s->dist_levels; l < nl; ++l)
+                if (s->coarse[(size_t)l - 1].lv.n_tiles > 0)
+                    deep_enough = true;
+            if (!deep_enough)
+                return SA_RETRY_UNWINDOWED;
+        }
+        // the tile lists ARE the rank's slices
+        for (int l = 0; l < s->dist_levels; ++l) {
+            s->dl[(size_t)l].tile_lo = 0;
+            s->dl[(size_t)l].tile_hi = l == 0 ? s->n_active_tiles : s->coarse[(size_t)l - 1].lv.n_tiles;
+        }
+        s->dist_mg = multigrid;
+        s->dist_planned = true;
+        s->dist_unit_frac = s->rows > 0 ? (double)(std::min(s->dl[0].row_hi, s->rows) - std::min(s->dl[0].row_lo, s->rows)) / (double)s->rows : 1.0;
+        SA_TRY(peer_plan(s));
+        return SA_OK;
+    }
+    int levels = 1;
+    if (multigrid) {
+        levels = dist_choose_levels(s->rows, world);
+        // the coarsest level of the hierarchy is always replicated (its solver is one CTA per band)
+        int usable = 0;
+        for (int l = 1; l < nl; ++l)
+            if (s->coarse[(size_t)l - 1].lv.n_tiles > 0)
+                usable = l;
+        if (levels > usable)
+            levels = usable;
+        if (levels < 1)
+            return fail(ctx, SA_BAD_ARGUMENT, "distributed solve: the scene is too small to be split by rows");
+    }
+    s->dist_levels = levels;
+    s->dist_mg = multigrid;
+    fill_bounds(s, levels);
+    for (int l = 0; l < levels; ++l) {
+        DistLevel& d = s->dl[(size_t)l];
+        const int ltx = l == 0 ? s->tiles_x : s->coarse[(size_t)l - 1].lv.tiles_x;
+        const int32_t* list = l == 0 ? s->tile_list : s->coarse[(size_t)l - 1].tile_list;
+        const int n = l == 0 ? s->n_active_tiles : s->coarse[(size_t)l - 1].lv.n_tiles;
+        SA_TRY(slice_tiles(ctx, list, n, ltx, (int)(d.row_lo / TILE_H), (int)(d.row_hi / TILE_H), &d.tile_lo, &d.tile_hi));
+    }
+    s->dist_planned = true;
+    s->dist_unit_frac = s->rows > 0 ? (double)(std::min(s->dl[0].row_hi, s->rows) - std::min(s->dl[0].row_lo, s->rows)) / (double)s->rows : 1.0;
+    SA_TRY(peer_plan(s));
+    return SA_OK;
+}
 
 // ---- peer-memory arena: layout for a scene, allocation, exchange of the IPC handles ----------------------------------------
 // Collective: every rank calls it with the same scene shape (dist_plan_scene).  Falls back to NCCL for the whole

@@ -4,6 +4,8 @@
 // poisson.cpp:162-177.  HBM-bound byte work: one coalesced read of the mask, one coalesced write of the table.
 #include "common.cuh"
 
+#include <algorithm>
+
 namespace satfill {
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -57,9 +59,12 @@ int transpose_i32(sa_ctx* ctx, const int32_t* s, int64_t r, int64_t c, int64_t s
 // to 0/1 in place on the way.  Each CTA records whether its tile holds an unknown; a single-CTA ballot scan then
 // lists the active tiles in raster order (reproducible work order, neighbouring CTAs touch neighbouring memory).
 // ---------------------------------------------------------------------------------------------------------------
+// A row-decomposed scene (dist.cu) launches it on its own tile rows plus one either side (first_tile = the first tile of
+// that window); only tiles of rows [own_lo, own_hi) are flagged, i.e. listed.
 __global__ void __launch_bounds__(CG_THREADS) k_build_unknown_set(uint8_t* __restrict__ mask, uint8_t* __restrict__ umask,
     int64_t rows, int64_t cols, int64_t pitch, int tiles_x, int laplace, int32_t* __restrict__ tile_flags,
-    unsigned long long* __restrict__ count64, uint32_t* __restrict__ tbits, uint32_t* __restrict__ tbitsT)
+    unsigned long long* __restrict__ count64, uint32_t* __restrict__ tbits, uint32_t* __restrict__ tbitsT, int first_tile, int own_lo,
+    int own_hi)
 {
     __shared__ int warp_cnt[CG_BLOCK_Y];
     __shared__ unsigned scol[TILE_W];
@@ -67,7 +72,8 @@ __global__ void __launch_bounds__(CG_THREADS) k_build_unknown_set(uint8_t* __res
         scol[threadIdx.x] = 0;
     __syncthreads();
     unsigned colbits = 0;
-    int tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x;
+    const int tile = first_tile + (int)blockIdx.x;
+    int tx = tile % tiles_x, ty = tile / tiles_x;
     int64_t c = (int64_t)tx * TILE_W + threadIdx.x;
     int cnt = 0;
 #pragma unroll
@@ -100,14 +106,30 @@ __global__ void __launch_bounds__(CG_THREADS) k_build_unknown_set(uint8_t* __res
         int total = 0;
         for (int w = 0; w < CG_BLOCK_Y; ++w)
             total += warp_cnt[w];
-        tile_flags[blockIdx.x] = total > 0;
-        if (total > 0)
+        const bool own = ty >= own_lo && ty < own_hi;
+        tile_flags[tile] = own && total > 0;
+        if (own && total > 0)
             atomicAdd(count64, (unsigned long long)total);
     }
 }
 
+// unknowns of the whole mask (a row-decomposed scene indexes only its own rows, but every rank needs the size of the system)
+__global__ void __launch_bounds__(256) k_count_unknowns(const uint8_t* __restrict__ mask, int64_t rows, int64_t cols, int64_t pitch,
+    int laplace, unsigned long long* __restrict__ count64)
+{
+    unsigned long long n = 0;
+    const int64_t r_lo = laplace ? 1 : 0, r_hi = laplace ? rows - 1 : rows, c_lo = laplace ? 1 : 0, c_hi = laplace ? cols - 1 : cols;
+    for (int64_t r = r_lo + blockIdx.x; r < r_hi; r += gridDim.x)
+        for (int64_t c = c_lo + threadIdx.x; c < c_hi; c += blockDim.x)
+            n += mask[r * pitch + c] != 0;
+    for (int o = 16; o; o >>= 1)
+        n += __shfl_xor_sync(0xffffffffu, n, o);
+    if ((threadIdx.x & 31) == 0 && n)
+        atomicAdd(count64, n);
+}
+
 __global__ void __launch_bounds__(1024) k_compact_flags(const int32_t* __restrict__ flags, int n_tiles, int tiles_x,
-    int32_t* __restrict__ tile_list, int32_t* __restrict__ tile_yx, int32_t* __restrict__ n_active)
+    int32_t* __restrict__ tile_list, int32_t* __restrict__ tile_yx, int32_t* __restrict__ n_active, int first_tile)
 {
     // single CTA, raster order: running offset + block-wide ballot scan
     __shared__ int warp_tot[32];
@@ -116,9 +138,10 @@ __global__ void __launch_bounds__(1024) k_compact_flags(const int32_t* __restric
         base = 0;
     __syncthreads();
     int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int start = 0; start < n_tiles; start += 1024) {
+    // tiles [first_tile, first_tile + n_tiles) of the grid
+    for (int start = first_tile; start < first_tile + n_tiles; start += 1024) {
         int i = start + threadIdx.x;
-        int f = (i < n_tiles) ? flags[i] : 0;
+        int f = (i < first_tile + n_tiles) ? flags[i] : 0;
         unsigned b = __ballot_sync(0xffffffffu, f);
         int pre = __popc(b & ((1u << lane) - 1));
         if (lane == 0)
@@ -149,9 +172,9 @@ __global__ void __launch_bounds__(1024) k_compact_flags(const int32_t* __restric
 
 // Shared by the fine level (index_scene) and the multigrid coarse levels: flags -> raster-ordered list + count.
 int compact_tile_flags(sa_ctx* ctx, const int32_t* flags, int n_tiles, int tiles_x, int32_t* tile_list, int32_t* tile_yx,
-    int32_t* d_n_active)
+    int32_t* d_n_active, int first_tile)
 {
-    SA_LAUNCH(ctx, k_compact_flags, 1, 1024, 0, flags, n_tiles, tiles_x, tile_list, tile_yx, d_n_active);
+    SA_LAUNCH(ctx, k_compact_flags, 1, 1024, 0, flags, n_tiles, tiles_x, tile_list, tile_yx, d_n_active, first_tile);
     SA_CUDA(ctx, cudaGetLastError());
     return SA_OK;
 }
@@ -164,10 +187,22 @@ int index_scene(sa_scene* s)
     SA_CUDA(ctx, cudaMemsetAsync(s->d_counters, 0, 4 * sizeof(int32_t), ctx->stream));
     SA_CUDA(ctx, cudaMemsetAsync(s->d_count64, 0, sizeof(unsigned long long), ctx->stream));
     dim3 block(CG_BLOCK_X, CG_BLOCK_Y);
-    SA_LAUNCH(ctx, k_build_unknown_set, n_tiles, block, 0, s->mask0(s->mask), s->mask0(s->umask), s->rows, s->cols,
-        s->pitch, s->tiles_x, s->problem == SA_LAPLACE ? 1 : 0, flags, s->d_count64, s->tbits, s->tbits + s->tb_words);
+    // a row-decomposed scene: its own tile rows (+ one either side for the neighbourhoods of its edge tiles)
+    int own_lo = 0, own_hi = s->tiles_y, win_lo = 0, win_hi = s->tiles_y;
+    if (s->dist_windowed && !s->dl.empty()) {
+        own_lo = (int)(s->dl[0].row_lo / TILE_H);
+        own_hi = (int)(s->dl[0].row_hi / TILE_H);
+        win_lo = std::max(own_lo - 1, 0);
+        win_hi = std::min(own_hi + 1, s->tiles_y);
+        if (win_hi < win_lo)
+            win_hi = win_lo;
+    }
+    const int first = win_lo * s->tiles_x, count = (win_hi - win_lo) * s->tiles_x;
+    if (count > 0)
+        SA_LAUNCH(ctx, k_build_unknown_set, count, block, 0, s->mask0(s->mask), s->mask0(s->umask), s->rows, s->cols, s->pitch,
+            s->tiles_x, s->problem == SA_LAPLACE ? 1 : 0, flags, s->d_count64, s->tbits, s->tbits + s->tb_words, first, own_lo, own_hi);
     SA_CUDA(ctx, cudaGetLastError());
-    SA_TRY(compact_tile_flags(ctx, flags, n_tiles, s->tiles_x, s->tile_list, s->tile_list + 2 * n_tiles, s->d_counters));
+    SA_TRY(compact_tile_flags(ctx, flags, count, s->tiles_x, s->tile_list, s->tile_list + 2 * n_tiles, s->d_counters, first));
     struct readback {
         int32_t counters[4];
         unsigned long long n;
@@ -177,7 +212,22 @@ int index_scene(sa_scene* s)
     SA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     s->n_active_tiles = h->counters[0];
     s->n_unknowns = (int64_t)h->n;
+    if (s->dist_windowed)  // the size of the whole system, not of this rank's rows
+        SA_TRY(count_unknowns(s, &s->n_unknowns));
     s->indexed = true;
+    return SA_OK;
+}
+
+int count_unknowns(sa_scene* s, int64_t* out)
+{
+    sa_ctx* ctx = s->ctx;
+    SA_CUDA(ctx, cudaMemsetAsync(s->d_count64, 0, sizeof(unsigned long long), ctx->stream));
+    SA_LAUNCH(ctx, k_count_unknowns, 4 * ctx->sm_count, 256, 0, s->mask0(s->mask), s->rows, s->cols, s->pitch,
+        s->problem == SA_LAPLACE ? 1 : 0, s->d_count64);
+    unsigned long long* h = (unsigned long long*)ctx->pinned;
+    SA_CUDA(ctx, cudaMemcpyAsync(h, s->d_count64, sizeof(*h), cudaMemcpyDeviceToHost, ctx->stream));
+    SA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *out = (int64_t)*h;
     return SA_OK;
 }
 

@@ -17,6 +17,8 @@
 #include "common.cuh"
 #include "tile.cuh"
 
+#include <algorithm>
+
 namespace satfill {
 
 constexpr double MG_OMEGA = 0.8;  // damped Jacobi: optimal smoothing factor 0.6 for the 5-point operator
@@ -39,18 +41,35 @@ __device__ __forceinline__ double lv_diag(const Level& lv, int64_t r, int64_t c)
 //                                                           a full coarse spacing away);
 //     it is known: the boundary sits at half the spacing -> 2;
 //     it lies outside the image (Poisson only: no neighbour there, poisson.cpp:187-190), or the arm's end does: 0.
+//
+// shift > 0 (row-decomposed scenes, dist.cu): `fmask` is the RAW level-0 mask (non-zero = invalid) and the level is built
+// from it directly -- coarse (I, J) <-> level-0 (I << shift, J << shift), a cell of the next finer level (i, j) <-> level-0
+// (i << (shift - 1), j << (shift - 1)) -- which is the same mask injection, but needs no finer level to exist beyond the
+// rows this rank owns.  laplace: the border rule of the unknown set (k_build_unknown_set).  The grid covers the tiles
+// [first_tile, first_tile + gridDim.x); only tiles of rows [own_lo, own_hi) are flagged / counted.
 __global__ void __launch_bounds__(CG_THREADS) k_coarsen_mask(const uint8_t* __restrict__ fmask, int64_t fpitch,
     int64_t frows, int64_t fcols, int fixed, uint8_t* __restrict__ cmask, int64_t crows, int64_t ccols, int64_t cpitch,
     int tiles_x, int32_t* __restrict__ tile_flags, unsigned long long* __restrict__ count64, uint32_t* __restrict__ tbits,
-    uint32_t* __restrict__ tbitsT, float* __restrict__ winv)
+    uint32_t* __restrict__ tbitsT, float* __restrict__ winv, int shift, int64_t rows0, int64_t cols0, int laplace, int first_tile,
+    int own_lo, int own_hi)
 {
+    // unknown of the next finer level at (i, j) (in range by construction of the callers' tests)
+    auto fine_unknown = [&](int64_t i, int64_t j) -> bool {
+        if (shift == 0)
+            return fmask[i * fpitch + j] != 0;
+        const int64_t R = i << (shift - 1), C = j << (shift - 1);
+        if (R >= rows0 || C >= cols0 || !fmask[R * fpitch + C])
+            return false;
+        return !(laplace && (R == 0 || R == rows0 - 1 || C == 0 || C == cols0 - 1));
+    };
     __shared__ int warp_cnt[CG_BLOCK_Y];
     __shared__ unsigned scol[TILE_W];
     if (threadIdx.y == 0)
         scol[threadIdx.x] = 0;
     __syncthreads();
     unsigned colbits = 0;
-    int tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x;
+    const int tile = first_tile + (int)blockIdx.x;
+    int tx = tile % tiles_x, ty = tile / tiles_x;
     int64_t c = (int64_t)tx * TILE_W + threadIdx.x;
     int cnt = 0;
 #pragma unroll
@@ -58,7 +77,7 @@ __global__ void __launch_bounds__(CG_THREADS) k_coarsen_mask(const uint8_t* __re
         int64_t r = (int64_t)ty * TILE_H + threadIdx.y + j * CG_BLOCK_Y;
         uint8_t m = 0;
         if (r < crows && c < ccols)
-            m = fmask[2 * r * fpitch + 2 * c];
+            m = fine_unknown(2 * r, 2 * c) ? 1 : 0;
         cmask[r * cpitch + c] = m;
         {
             float d = 0.f;
@@ -72,7 +91,7 @@ __global__ void __launch_bounds__(CG_THREADS) k_coarsen_mask(const uint8_t* __re
                     bool end_in = er >= 0 && er < frows && ec >= 0 && ec < fcols;
                     if (!mid_in)
                         d += fixed ? 2.f : 0.f;
-                    else if (!fmask[mr * fpitch + mc])
+                    else if (!fine_unknown(mr, mc))
                         d += 2.f;
                     else
                         d += (end_in || fixed) ? 1.f : 0.f;
@@ -99,8 +118,9 @@ __global__ void __launch_bounds__(CG_THREADS) k_coarsen_mask(const uint8_t* __re
         int total = 0;
         for (int w = 0; w < CG_BLOCK_Y; ++w)
             total += warp_cnt[w];
-        tile_flags[blockIdx.x] = total > 0;
-        if (total > 0)
+        const bool own = ty >= own_lo && ty < own_hi;
+        tile_flags[tile] = own && total > 0;
+        if (own && total > 0)
             atomicAdd(count64, (unsigned long long)total);
     }
 }
@@ -182,15 +202,36 @@ int build_hierarchy(sa_scene* s, const sa_options& o)
     const uint8_t* fmask = s->mask0(s->umask);
     int64_t fpitch = s->pitch, frows = s->rows, fcols = s->cols;
     dim3 block(CG_BLOCK_X, CG_BLOCK_Y);
+    // A row-decomposed scene that indexes only its own rows (dist.cu: dist_prepare_window) builds every level straight from
+    // the raw mask: the split levels on the rank's rows (+ one tile row either side), the replicated ones everywhere.
+    const bool windowed = s->dist_windowed;
+    int level = 0;
     for (sa_level_store& L : s->coarse) {
+        ++level;
         int n_tiles = L.lv.tiles_x * L.lv.tiles_y;
         int32_t* flags = L.tile_list + n_tiles;
         unsigned long long* count64 = reinterpret_cast<unsigned long long*>(L.d_counters + 4);
         SA_CUDA(ctx, cudaMemsetAsync(L.d_counters, 0, sizeof(int32_t) * 4 + sizeof(unsigned long long), ctx->stream));
         uint8_t* cmask = L.umask_alloc + L.lv.pitch;
-        SA_LAUNCH(ctx, k_coarsen_mask, n_tiles, block, 0, fmask, fpitch, frows, fcols, L.lv.fixed_diag, cmask, L.lv.rows,
-            L.lv.cols, L.lv.pitch, L.lv.tiles_x, flags, count64, L.tbits, L.tbits + L.tb_words, L.winv + L.lv.pitch);
-        SA_TRY(compact_tile_flags(ctx, flags, n_tiles, L.lv.tiles_x, L.tile_list, L.tile_list + 2 * n_tiles, L.d_counters));
+        int own_lo = 0, own_hi = L.lv.tiles_y, win_lo = 0, win_hi = L.lv.tiles_y;
+        if (windowed && level < (int)s->dl.size()) {
+            own_lo = (int)(s->dl[(size_t)level].row_lo / TILE_H);
+            own_hi = (int)(s->dl[(size_t)level].row_hi / TILE_H);
+            win_lo = std::max(own_lo - 1, 0);
+            win_hi = std::max(std::min(own_hi + 1, L.lv.tiles_y), win_lo);
+        }
+        const int first = win_lo * L.lv.tiles_x, count = (win_hi - win_lo) * L.lv.tiles_x;
+        if (count > 0) {
+            if (windowed)
+                SA_LAUNCH(ctx, k_coarsen_mask, count, block, 0, s->mask0(s->mask), s->pitch, frows, fcols, L.lv.fixed_diag, cmask,
+                    L.lv.rows, L.lv.cols, L.lv.pitch, L.lv.tiles_x, flags, count64, L.tbits, L.tbits + L.tb_words, L.winv + L.lv.pitch,
+                    level, s->rows, s->cols, s->problem == SA_LAPLACE ? 1 : 0, first, own_lo, own_hi);
+            else
+                SA_LAUNCH(ctx, k_coarsen_mask, count, block, 0, fmask, fpitch, frows, fcols, L.lv.fixed_diag, cmask, L.lv.rows,
+                    L.lv.cols, L.lv.pitch, L.lv.tiles_x, flags, count64, L.tbits, L.tbits + L.tb_words, L.winv + L.lv.pitch, 0,
+                    s->rows, s->cols, 0, first, own_lo, own_hi);
+        }
+        SA_TRY(compact_tile_flags(ctx, flags, count, L.lv.tiles_x, L.tile_list, L.tile_list + 2 * n_tiles, L.d_counters, first));
         fmask = cmask;
         fpitch = L.lv.pitch;
         frows = L.lv.rows;

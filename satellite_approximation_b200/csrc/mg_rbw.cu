@@ -933,8 +933,12 @@ int apply_vcycle_rbw(sa_scene* s, const sa_options& o, KernelTimer& kt, int rz_s
     // are replicated on every rank
     const bool dist = s->distributed && s->dist_planned && ctx->world > 1;
     const int dlv = dist ? s->dist_levels : 0;
-    for (int l = 0; l < nl && l < dlv; ++l)
+    for (int l = 0; l < nl && l < dlv; ++l) {
         L[(size_t)l].lv = dist_level(s, l, L[(size_t)l].lv);
+        // the profile counts what THIS rank processes (a windowed scene counted only its own unknowns on the split coarse levels)
+        if (l == 0 || !s->dist_windowed)
+            L[(size_t)l].units = (int64_t)((double)L[(size_t)l].units * s->dist_unit_frac);
+    }
     if (nl == 1) {
         kt.begin(KC_SMOOTH, L[0].units);
         SA_LAUNCH(ctx, k_rbw_coarsest_only, nb, RW_THREADS, 0, L[0].lv, fixed ? 1 : 0, L[0].b, L[0].x, scal, rz_slot, coarse_sweeps);
