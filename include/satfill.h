@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define SATFILL_ABI_VERSION 4
+#define SATFILL_ABI_VERSION 5
 
 typedef enum sa_status {
     SA_OK = 0,
@@ -112,6 +112,10 @@ int sa_create(sa_ctx** out, int device, void* stream);
 void sa_destroy(sa_ctx* ctx);
 const char* sa_last_error(const sa_ctx* ctx);
 int sa_abi_version(void);
+/* 1 when the library also holds the first-generation kernels (built with SATFILL_LEGACY_VARIANTS: cg_variant = 1,
+ * SA_MG_JACOBI64, SA_MG_RB32_CTA -- the tested references of the product kernels); the product library returns 0 and
+ * refuses those variants with SA_BAD_ARGUMENT. */
+int sa_has_legacy_variants(void);
 void sa_default_options(sa_options* opts, int problem);
 /* number of kernels of this library launched through ctx since creation (bench.py's gpu_launches) */
 int64_t sa_kernel_launches(const sa_ctx* ctx);

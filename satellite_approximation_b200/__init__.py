@@ -182,6 +182,12 @@ class Context:
         return st
 
     @property
+    def has_legacy_variants(self) -> bool:
+        """True when the loaded library also holds the first-generation kernels (cg_variant = 1, MG_JACOBI64, MG_RB32_CTA):
+        lib/libsatfill_legacy.so, built with SATFILL_LEGACY_VARIANTS.  The product library refuses those variants."""
+        return bool(self._lib.sa_has_legacy_variants())
+
+    @property
     def kernel_launches(self) -> int:
         return int(self._lib.sa_kernel_launches(self._h))
 

@@ -13,7 +13,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SATFILL_LIB") or os.path.join(_HERE, "lib", "libsatfill.so")  # SATFILL_LIB: tuning builds
-ABI_VERSION = 4  # SATFILL_ABI_VERSION of include/satfill.h
+ABI_VERSION = 5  # SATFILL_ABI_VERSION of include/satfill.h
 
 SA_OK, SA_EMPTY_MASK, SA_NOT_CONVERGED, SA_SIZE_MISMATCH, SA_BAD_ARGUMENT, SA_CUDA_ERROR, SA_NCCL_ERROR, SA_OOM = range(8)
 SA_LAPLACE, SA_POISSON = 0, 1
@@ -33,7 +33,7 @@ EXPORTS = [
     "sa_scene_solve", "sa_scene_get_band", "sa_scene_info", "sa_scene_precondition", "sa_synchronize",
     "sa_dist_unique_id", "sa_dist_init", "sa_dist_partition", "sa_dist_levels", "sa_scene_set_distributed",
     "sa_scene_owned_rows", "sa_scene_allgather_band", "sa_apply_laplace_u8", "sa_morph_close_mask", "sa_last_fill_direct",
-    "sa_scene_plane_elements",
+    "sa_scene_plane_elements", "sa_has_legacy_variants",
 ]  # fmt: skip
 
 
@@ -161,6 +161,8 @@ def load() -> C.CDLL:
     L.sa_last_fill_direct.argtypes = [_vp]
     L.sa_scene_plane_elements.restype = _i64
     L.sa_scene_plane_elements.argtypes = [_i64, _i64]
+    L.sa_has_legacy_variants.restype = C.c_int
+    L.sa_has_legacy_variants.argtypes = []
     L.sa_synchronize.restype = C.c_int
     L.sa_synchronize.argtypes = [_vp]
     if L.sa_abi_version() != ABI_VERSION:

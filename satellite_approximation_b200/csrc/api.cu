@@ -207,6 +207,8 @@ extern "C" {
 
 int sa_abi_version(void) { return SATFILL_ABI_VERSION; }
 
+int sa_has_legacy_variants(void) { return SATFILL_LEGACY_VARIANTS ? 1 : 0; }
+
 int64_t sa_scene_plane_elements(int64_t rows, int64_t cols)
 {
     if (rows < 0 || cols < 0)

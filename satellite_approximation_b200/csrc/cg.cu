@@ -29,6 +29,7 @@ namespace satfill {
 
 // x0: Laplace solve() starts from zero (IterativeSolverBase.h:357-360); Poisson from the replacement image
 // (poisson.cpp:239, 257).
+#if SATFILL_LEGACY_VARIANTS
 template <bool POISSON>
 __global__ void __launch_bounds__(CG_THREADS) k_init_guess(Level lv, double* __restrict__ u, const double* __restrict__ g)
 {
@@ -90,6 +91,8 @@ __global__ void __launch_bounds__(CG_THREADS) k_residual(Level lv, const double*
         atomicAdd(&scal[blockIdx.y].rz[0], t);
 }
 
+#endif  // SATFILL_LEGACY_VARIANTS
+
 __global__ void k_finalize_setup(BandScalars* scal, int nbands, double tol, int mg)
 {
     int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -135,6 +138,7 @@ __global__ void __launch_bounds__(CG_THREADS) k_zero_unknowns(Level lv, double* 
 // The two kernels of one CG iteration.
 // ---------------------------------------------------------------------------------------------------------------
 
+#if SATFILL_LEGACY_VARIANTS
 // k_direction: p' = z + beta p, pq = p'.Ap'.   JACOBI: z = r / d computed on the fly (zin = r).  Otherwise zin = z.
 template <bool JACOBI, typename ZT>
 __global__ void __launch_bounds__(CG_THREADS, 8) k_direction(Level lv, const ZT* __restrict__ zin,
@@ -265,6 +269,8 @@ __global__ void __launch_bounds__(CG_THREADS, 8) k_update(Level lv, double* __re
             atomicAdd(&sc.rz[next], t);
     }
 }
+
+#endif  // SATFILL_LEGACY_VARIANTS
 
 // Multigrid loop: test the stop rule right after the update of iteration k - 1 (one thread per band), so that a band
 // that has converged does not pay for another V-cycle before k_direction would notice.
@@ -475,6 +481,10 @@ static int ensure_multigrid(sa_scene* s, const sa_options& o)
 int precondition_scene(sa_scene* s, const sa_options& o)
 {
     sa_ctx* ctx = s->ctx;
+#if !SATFILL_LEGACY_VARIANTS
+    if (o.mg_variant != SA_MG_RB32)
+        return fail(ctx, SA_BAD_ARGUMENT, "this libsatfill holds the product kernels only (SATFILL_LEGACY_VARIANTS)");
+#endif
     SA_TRY(ensure_multigrid(s, o));
     s->work_dirty = WORK_FULL;  // the caller's vector goes through r and p: clear everything before the next solve
     const int64_t n = (int64_t)s->rows_p * s->pitch;  // the plane without its guard rows
@@ -551,6 +561,11 @@ int solve_scene(sa_scene* s, const sa_options& o, sa_stats* stats)
     const bool mg = o.precond == SA_PRECOND_MULTIGRID;
     const bool rb = mg && o.mg_variant != SA_MG_JACOBI64;
     const bool strip = o.cg_variant == 0;
+#if !SATFILL_LEGACY_VARIANTS
+    if (!strip || (mg && o.mg_variant != SA_MG_RB32))
+        return fail(ctx, SA_BAD_ARGUMENT, "this libsatfill holds the product kernels only: cg_variant = 1, SA_MG_JACOBI64 and SA_MG_RB32_CTA "
+                                          "need the library built with SATFILL_LEGACY_VARIANTS (lib/libsatfill_legacy.so)");
+#endif
     SA_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
     SA_TRY(prepare_solve(s, o));
     const int64_t n = s->n_unknowns;
@@ -615,17 +630,17 @@ int solve_scene(sa_scene* s, const sa_options& o, sa_stats* stats)
     } else {
         if (have_tiles) {
             if (poisson)
-                SA_LAUNCH(ctx, k_init_guess<true>, grid, block, 0, lv, u0, g0);
+                SA_LAUNCH_LEGACY(ctx, k_init_guess<true>, grid, block, 0, lv, u0, g0);
             else
-                SA_LAUNCH(ctx, k_init_guess<false>, grid, block, 0, lv, u0, g0);
+                SA_LAUNCH_LEGACY(ctx, k_init_guess<false>, grid, block, 0, lv, u0, g0);
         }
         if (dist)  // the residual's stencil reads the iterate one row beyond the slice
             SA_TRY(dist_halo<double>(s, 0, u0, s->pitch, s->plane, 1, 1));
         if (have_tiles) {
             if (poisson)
-                SA_LAUNCH(ctx, k_residual<true>, grid, block, 0, lv, u0, g0, r0, rb ? s->rb_rf() : nullptr, scal);
+                SA_LAUNCH_LEGACY(ctx, k_residual<true>, grid, block, 0, lv, u0, g0, r0, rb ? s->rb_rf() : nullptr, scal);
             else
-                SA_LAUNCH(ctx, k_residual<false>, grid, block, 0, lv, u0, g0, r0, rb ? s->rb_rf() : nullptr, scal);
+                SA_LAUNCH_LEGACY(ctx, k_residual<false>, grid, block, 0, lv, u0, g0, r0, rb ? s->rb_rf() : nullptr, scal);
         }
     }
     if (dist) {  // |b|^2, |r0|^2, r0.z0 summed over the ranks, and the halo rows of the residual the first kernel reads
@@ -689,9 +704,9 @@ int solve_scene(sa_scene* s, const sa_options& o, sa_stats* stats)
                 if (strip)
                     SA_TRY(launch_direction2(ctx, lv, nb, false, z, rb, pin_v, pout_v, pf, scal, ki));
                 else if (rb)
-                    SA_LAUNCH(ctx, (k_direction<false, float>), grid, block, 0, lv, (const float*)z, pin, pout, scal, ki);
+                    SA_LAUNCH_LEGACY(ctx, (k_direction<false, float>), grid, block, 0, lv, (const float*)z, pin, pout, scal, ki);
                 else
-                    SA_LAUNCH(ctx, (k_direction<false, double>), grid, block, 0, lv, (const double*)z, pin, pout, scal, ki);
+                    SA_LAUNCH_LEGACY(ctx, (k_direction<false, double>), grid, block, 0, lv, (const double*)z, pin, pout, scal, ki);
                 kt.end();
                 if (dist)  // the halo row of p' and p'.Ap' in one exchange
                     SA_TRY(dist_step(s, 0, DIST_VEC_DIR, pf ? pout_v : (void*)pout, pf ? 4 : 8, s->pitch, s->plane, 1, 1, DIST_PQ, ki & 3,
@@ -700,9 +715,9 @@ int solve_scene(sa_scene* s, const sa_options& o, sa_stats* stats)
                 if (strip)
                     SA_TRY(launch_update2(ctx, lv, nb, false, u0, pout_v, pf, r0, rf, scal, ki));
                 else if (rb)
-                    SA_LAUNCH(ctx, (k_update<false, true>), grid, block, 0, lv, u0, pout, r0, rf, scal, ki);
+                    SA_LAUNCH_LEGACY(ctx, (k_update<false, true>), grid, block, 0, lv, u0, pout, r0, rf, scal, ki);
                 else
-                    SA_LAUNCH(ctx, (k_update<false, false>), grid, block, 0, lv, u0, pout, r0, nullptr, scal, ki);
+                    SA_LAUNCH_LEGACY(ctx, (k_update<false, false>), grid, block, 0, lv, u0, pout, r0, nullptr, scal, ki);
                 kt.end();
                 if (dist)  // the halo rows of the cycle's residual copy and |r|^2 in one exchange
                     SA_TRY(dist_step(s, 0, DIST_VEC_RHS, rf, 4, s->pitch, s->plane, 3, 3, DIST_RR, (ki + 1) & 3, -1));
@@ -712,7 +727,7 @@ int solve_scene(sa_scene* s, const sa_options& o, sa_stats* stats)
                 if (strip)
                     SA_TRY(launch_direction2(ctx, lv, nb, true, r0, false, pin, pout, false, scal, ki));
                 else
-                    SA_LAUNCH(ctx, (k_direction<true, double>), grid, block, 0, lv, r0, pin, pout, scal, ki);
+                    SA_LAUNCH_LEGACY(ctx, (k_direction<true, double>), grid, block, 0, lv, r0, pin, pout, scal, ki);
                 kt.end();
                 if (dist)
                     SA_TRY(dist_step(s, 0, DIST_VEC_DIR, pout, 8, s->pitch, s->plane, 1, 1, DIST_PQ, ki & 3, (ki + 2) & 3));
@@ -720,7 +735,7 @@ int solve_scene(sa_scene* s, const sa_options& o, sa_stats* stats)
                 if (strip)
                     SA_TRY(launch_update2(ctx, lv, nb, true, u0, pout, false, r0, nullptr, scal, ki));
                 else
-                    SA_LAUNCH(ctx, (k_update<true, false>), grid, block, 0, lv, u0, pout, r0, nullptr, scal, ki);
+                    SA_LAUNCH_LEGACY(ctx, (k_update<true, false>), grid, block, 0, lv, u0, pout, r0, nullptr, scal, ki);
                 kt.end();
                 if (dist) {  // ranks must agree on the stop: test it from the reduced norm after every iteration
                     SA_TRY(dist_step(s, 0, DIST_VEC_RHS, r0, 8, s->pitch, s->plane, 1, 1, DIST_RR_RZ, (ki + 1) & 3, -1));

@@ -19,6 +19,13 @@
 
 #include "../../include/satfill.h"
 
+// SATFILL_LEGACY_VARIANTS = 1 also builds the first-generation kernels -- cg_variant = 1 (cg.cu: tile + halo staged through
+// shared memory), SA_MG_JACOBI64 (mg.cu, mg_fused.cu) and SA_MG_RB32_CTA (mg_rb.cu) -- the references the product kernels
+// are tested against (lib/libsatfill_legacy.so, tests/test_gpu_legacy.py).  The product library ships the hot path only.
+#ifndef SATFILL_LEGACY_VARIANTS
+#define SATFILL_LEGACY_VARIANTS 0
+#endif
+
 namespace satfill {
 
 constexpr int TILE_W = 32;
@@ -225,6 +232,14 @@ inline int fail(sa_ctx* ctx, int status, const std::string& msg)
         kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);   \
         (ctx)->launches += 1;                                              \
     } while (0)
+// a launch of a first-generation kernel: compiled away in the product build (the request is refused before it gets there)
+#if SATFILL_LEGACY_VARIANTS
+#define SA_LAUNCH_LEGACY(...) SA_LAUNCH(__VA_ARGS__)
+#else
+#define SA_LAUNCH_LEGACY(...) \
+    do {                      \
+    } while (0)
+#endif
 
 inline int64_t round_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
 

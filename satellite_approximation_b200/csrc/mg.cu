@@ -255,6 +255,7 @@ int build_hierarchy(sa_scene* s, const sa_options& o)
     return SA_OK;
 }
 
+#if SATFILL_LEGACY_VARIANTS
 // ---- cycle kernels -------------------------------------------------------------------------------------------------
 
 // FIRST: x_out = omega * b / d (one damped-Jacobi sweep from a zero iterate, pointwise).
@@ -524,5 +525,12 @@ int apply_vcycle(sa_scene* s, const sa_options& o, KernelTimer& kt, int rz_slot,
     }
     return SA_OK;
 }
+
+#else
+int apply_vcycle(sa_scene* s, const sa_options&, KernelTimer&, int, int)
+{
+    return fail(s->ctx, SA_BAD_ARGUMENT, "SA_MG_JACOBI64 needs a library built with SATFILL_LEGACY_VARIANTS");
+}
+#endif  // SATFILL_LEGACY_VARIANTS
 
 }  // namespace satfill

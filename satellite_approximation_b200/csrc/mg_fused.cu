@@ -28,6 +28,7 @@
 #include "common.cuh"
 #include "tile.cuh"
 
+#if SATFILL_LEGACY_VARIANTS
 namespace satfill {
 
 constexpr double FW = 0.8;  // damped-Jacobi weight, same as mg.cu
@@ -285,3 +286,4 @@ int launch_mg_up(sa_ctx* ctx, const Level& lf, const Level& lc, int nbands, cons
 }
 
 }  // namespace satfill
+#endif  // SATFILL_LEGACY_VARIANTS

@@ -28,6 +28,7 @@
 #include "common.cuh"
 #include "tile.cuh"
 
+#if SATFILL_LEGACY_VARIANTS
 namespace satfill {
 
 namespace {
@@ -626,3 +627,11 @@ int apply_vcycle_rb(sa_scene* s, const sa_options& o, KernelTimer& kt, int rz_sl
 }
 
 }  // namespace satfill
+#else
+namespace satfill {
+int apply_vcycle_rb(sa_scene* s, const sa_options&, KernelTimer&, int, int)
+{
+    return fail(s->ctx, SA_BAD_ARGUMENT, "SA_MG_RB32_CTA needs a library built with SATFILL_LEGACY_VARIANTS");
+}
+}  // namespace satfill
+#endif  // SATFILL_LEGACY_VARIANTS

@@ -37,7 +37,7 @@ def test_library_exports_every_declared_symbol():
     out = subprocess.run(["nm", "-D", "--defined-only", _capi.LIB_PATH], capture_output=True, text=True, check=True).stdout
     exported = {line.split()[-1] for line in out.splitlines() if " T " in line}
     assert set(header_symbols()) <= exported
-    assert lib.sa_abi_version() == 4
+    assert lib.sa_abi_version() == 5
 
 
 def test_struct_layouts_match_header():

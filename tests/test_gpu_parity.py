@@ -15,6 +15,13 @@ pytestmark = pytest.mark.gpu
 PARITY_TOL = 1e-4  # BASELINE.json: "filled pixels within 1e-4 relative max-abs difference"
 
 
+def _needs_legacy(ctx):
+    """The first-generation kernels (cg_variant = 1, MG_JACOBI64, MG_RB32_CTA) live in lib/libsatfill_legacy.so only; the
+    product library refuses them.  tests/test_gpu_legacy.py re-runs this file against the legacy library."""
+    if not ctx.has_legacy_variants:
+        pytest.skip("needs lib/libsatfill_legacy.so (SATFILL_LIB): run through tests/test_gpu_legacy.py")
+
+
 # ---- integer path: bit-exact ---------------------------------------------------------------------------------------
 def _masks():
     rng = np.random.default_rng(7)
@@ -408,6 +415,8 @@ def test_mask_changes_on_a_resident_scene(ctx):
     masks.insert(2, hole)
     mg, jac, j64 = dict(precond=sab.MULTIGRID), dict(precond=sab.JACOBI), dict(precond=sab.MULTIGRID, mg_variant=sab.MG_JACOBI64)
     legacy = dict(precond=sab.MULTIGRID, cg_variant=1)
+    if not ctx.has_legacy_variants:  # the product library: the same walk through masks on its own two preconditioners
+        j64, legacy = jac, mg        # (tests/test_gpu_legacy.py runs this file against lib/libsatfill_legacy.so)
     # consecutive red-black solves take the lean scrub (r and the cycle's masked-only vectors stay stale), which the
     # other preconditioners must then not trip over
     modes = [mg, jac, mg, j64, mg, jac, mg, mg, mg, j64, mg, mg, jac, mg, mg, legacy, mg, legacy, j64]
@@ -584,6 +593,7 @@ def test_multigrid_poisson_border_touching_large(ctx):
 
 
 def test_fused_multigrid_kernels_match_single_sweep_kernels(ctx):
+    _needs_legacy(ctx)
     """k_mg_down / k_mg_up (temporal blocking in shared memory) against the one-sweep-per-kernel V-cycle: the same
     arithmetic in a different schedule, so iteration counts agree and the fills agree to rounding.  Odd sizes, a mask
     touching the border and two bands exercise tile edges, the coarse-grid edges and the band stride."""
@@ -623,6 +633,8 @@ def _prototype():
 @pytest.mark.parametrize("variant", ["rb32", "rb32_cta"])
 @pytest.mark.parametrize("shape", [(96, 128), (391, 517), (40, 33), (1100, 700)])
 def test_rb_preconditioner_matches_numpy_prototype_and_is_symmetric(ctx, shape, variant):
+    if variant != "rb32":
+        _needs_legacy(ctx)
     """One application z = M^-1 r of the CUDA V-cycle against the numpy statement of the same algorithm
     (tools/mg_prototype.py: red-black Gauss-Seidel V(1,1), float, mask injection, boundary-corrected coarse diagonals,
     full weighting / bilinear), and
@@ -651,6 +663,8 @@ def test_rb_preconditioner_matches_numpy_prototype_and_is_symmetric(ctx, shape, 
 
 @pytest.mark.parametrize("variant", ["rb32", "jacobi64", "rb32_cta"])
 def test_multigrid_variants_reach_the_same_fill(ctx, variant):
+    if variant != "rb32":
+        _needs_legacy(ctx)
     """The preconditioner only changes the path of CG, not its fixed point: both variants meet a tight tolerance and
     agree with the Jacobi-preconditioned solve; the float cycle does not limit the attainable accuracy."""
     rows, cols = 300, 413
