@@ -29,6 +29,7 @@ import numpy as np
 
 from . import _capi
 from ._capi import (  # noqa: F401  (re-exported)
+    SA_BAD_ARGUMENT,
     SA_EMPTY_MASK,
     SA_LAPLACE as LAPLACE,
     SA_NOT_CONVERGED,
