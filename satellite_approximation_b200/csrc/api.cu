@@ -684,7 +684,7 @@ static int host_fill(sa_ctx* ctx, int problem, double* const* images, const doub
     if (!(o.tolerance > 0.0))
         o.tolerance = problem == SA_POISSON ? 1e-6 : DBL_EPSILON;
     SA_TRY(ensure_indexed(s, o.precond != SA_PRECOND_MULTIGRID ? WORK_JACOBI
-                                 : (o.mg_variant != SA_MG_JACOBI64 && o.cg_variant == 0 ? WORK_RB : WORK_J64)));
+                                 : (o.mg_variant != SA_MG_JACOBI64 && o.cg_variant == 0 ? (WORK_RB | (o.mg_variant == SA_MG_RB32 ? WORK_RBW : 0)) : WORK_J64)));
     if (s->n_unknowns == 0)
         return solve_scene(s, o, stats);  // fills stats, returns SA_EMPTY_MASK
     // 2a. Direct mode: when the caller's arrays are page-locked (cudaMallocHost / cudaHostRegister / torch pin_memory) the

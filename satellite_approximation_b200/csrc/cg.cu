@@ -413,6 +413,21 @@ static int clear_multigrid_vectors(sa_scene* s)
     return SA_OK;
 }
 
+// Work vectors left unscrubbed by mask changes between solves of the warp-kernel red-black path (stale_all): any other
+// path reads some of them unmasked, so it gets them cleared wholesale first.
+static int clear_stale_vectors(sa_scene* s)
+{
+    sa_ctx* ctx = s->ctx;
+    size_t bytes = (size_t)s->plane * s->nbands * sizeof(double);
+    SA_CUDA(ctx, cudaMemsetAsync(s->r, 0, bytes, ctx->stream));
+    SA_CUDA(ctx, cudaMemsetAsync(s->p[0], 0, bytes, ctx->stream));
+    SA_CUDA(ctx, cudaMemsetAsync(s->p[1], 0, bytes, ctx->stream));
+    SA_TRY(clear_multigrid_vectors(s));
+    s->stale_r = s->stale_rb = s->stale_all = false;
+    s->work_dirty &= ~(WORK_JACOBI | WORK_RB | WORK_J64 | WORK_PF | WORK_RBW);
+    return SA_OK;
+}
+
 int ensure_indexed(sa_scene* s, int next_kind)
 {
     sa_ctx* ctx = s->ctx;
@@ -425,11 +440,20 @@ int ensure_indexed(sa_scene* s, int next_kind)
         SA_CUDA(ctx, cudaMemsetAsync(s->p[0], 0, bytes, ctx->stream));
         SA_CUDA(ctx, cudaMemsetAsync(s->p[1], 0, bytes, ctx->stream));
         SA_TRY(clear_multigrid_vectors(s));
-        s->stale_r = s->stale_rb = false;
+        s->stale_r = s->stale_rb = s->stale_all = false;
     } else if (s->work_dirty != WORK_CLEAN) {
         // before index_scene replaces the old tile lists
-        const bool lean = next_kind == WORK_RB && (s->work_dirty & ~WORK_PF) == WORK_RB && (s->work_dirty & WORK_PF);
-        SA_TRY(scrub_work_vectors(s, lean));
+        const bool rb_again = (next_kind & ~WORK_RBW) == WORK_RB && (s->work_dirty & ~(WORK_PF | WORK_RBW)) == WORK_RB && (s->work_dirty & WORK_PF);
+        if (rb_again && (next_kind & WORK_RBW) && (s->work_dirty & WORK_RBW)) {
+            // strip CG + warp-per-tile cycle on both sides of the mask change: NOTHING has to be scrubbed.  Every kernel of
+            // that path loads a work vector only where the current mask has an unknown in the loaded piece (pair, quad,
+            // halo cell), every such piece has been rewritten by the current solve before it is read (whole sectors /
+            // quads, zeros at the cells that are not unknowns), and the one place that multiplies an old value by zero
+            // (p at iteration 0) only needs it to be finite.  Everything is then "stale" for any other path.
+            s->stale_r = s->stale_rb = s->stale_all = true;
+        } else {
+            SA_TRY(scrub_work_vectors(s, rb_again));
+        }
     }
     s->work_dirty = WORK_CLEAN;
     // a row-decomposed scene indexes only its own rows (dist.cu)
@@ -486,6 +510,8 @@ int precondition_scene(sa_scene* s, const sa_options& o)
         return fail(ctx, SA_BAD_ARGUMENT, "this libsatfill holds the product kernels only (SATFILL_LEGACY_VARIANTS)");
 #endif
     SA_TRY(ensure_multigrid(s, o));
+    if (s->stale_all && o.mg_variant != SA_MG_RB32)
+        SA_TRY(clear_stale_vectors(s));
     s->work_dirty = WORK_FULL;  // the caller's vector goes through r and p: clear everything before the next solve
     const int64_t n = (int64_t)s->rows_p * s->pitch;  // the plane without its guard rows
     const uint8_t* um = s->mask0(s->umask);
@@ -521,7 +547,10 @@ int prepare_solve(sa_scene* s, const sa_options& o)
     const bool mg = o.precond == SA_PRECOND_MULTIGRID;
     const bool rb = mg && o.mg_variant != SA_MG_JACOBI64;
     const bool strip = o.cg_variant == 0;
-    SA_TRY(ensure_indexed(s, !mg ? WORK_JACOBI : (rb && strip ? WORK_RB : WORK_J64)));
+    const bool rbw = rb && strip && o.mg_variant == SA_MG_RB32;
+    SA_TRY(ensure_indexed(s, !mg ? WORK_JACOBI : (rb && strip ? (WORK_RB | (rbw ? WORK_RBW : 0)) : WORK_J64)));
+    if (s->stale_all && !rbw)
+        SA_TRY(clear_stale_vectors(s));
     if (s->stale_r && !(rb && strip)) {  // Jacobi and the double cycle read r with its halo
         SA_CUDA(ctx, cudaMemsetAsync(s->r, 0, (size_t)s->plane * s->nbands * sizeof(double), ctx->stream));
         s->stale_r = false;
@@ -546,7 +575,7 @@ int prepare_solve(sa_scene* s, const sa_options& o)
             SA_CUDA(ctx, cudaMemsetAsync(s->p[0], 0, bytes, ctx->stream));
             SA_CUDA(ctx, cudaMemsetAsync(s->p[1], 0, bytes, ctx->stream));
         }
-        s->work_dirty = (s->work_dirty & ~WORK_PF) | kind | (pf_now ? WORK_PF : 0);
+        s->work_dirty = (s->work_dirty & ~(WORK_PF | WORK_RBW)) | kind | (pf_now ? WORK_PF : 0) | (rbw ? WORK_RBW : 0);
     }
     return SA_OK;
 }

@@ -127,12 +127,17 @@ __device__ __forceinline__ void store_pair(float* p, double2 v) { *reinterpret_c
 // What a thread needs to know about a tile: its coordinates and the unknown bits of the thread's two columns.
 struct TileBits {
     int yx;      // ty << 16 | tx
-    unsigned m;  // mL | mR << 8: unknown bits of the two columns, bit j <=> tile row row0 - 1 + j, j = 0..5
+    unsigned m;  // mL | mR << 8: unknown bits of the two columns, bit j <=> tile row row0 - 1 + j, j = 0..5;
+                 // bits 16 .. 16 + ST_RG - 1 (edge lanes): the halo column's cell of own row j is an unknown
     __device__ __forceinline__ int ty() const { return yx >> 16; }
     __device__ __forceinline__ int tx() const { return yx & 0xffff; }
     __device__ __forceinline__ unsigned mL() const { return m & ST_NRM; }
-    __device__ __forceinline__ unsigned mR() const { return m >> 8; }
+    __device__ __forceinline__ unsigned mR() const { return (m >> 8) & ST_NRM; }
     __device__ __forceinline__ unsigned any() const { return (m | (m >> 8)) & ST_NRM; }
+    // own rows (bit j <=> row0 + j) whose halo-column neighbour -- column -1 for the west lane, column 32 for the east lane --
+    // is an unknown: a halo value is only ever loaded where it is one (the vectors are zero elsewhere BY DEFINITION, but
+    // after a mask change only the sectors that hold an unknown of the new mask have been rewritten: cg.cu, stale_all)
+    __device__ __forceinline__ unsigned halo() const { return (m >> 16) & ((1u << ST_RG) - 1); }
     // element offset of the tile's origin inside a band plane (fits 32 bits: a plane has < 2^31 elements)
     __device__ __forceinline__ int origin(int pitch) const { return ty() * (TILE_H * pitch) + tx() * TILE_W; }
 };
@@ -152,6 +157,10 @@ __device__ __forceinline__ TileBits load_tile_bits(const Level& lv, int yx, int 
     unsigned long long cl = ((unsigned long long)N.x >> 31) | ((unsigned long long)C.x << 1) | ((unsigned long long)(S.x & 1u) << 33);
     unsigned long long cr = ((unsigned long long)N.y >> 31) | ((unsigned long long)C.y << 1) | ((unsigned long long)(S.y & 1u) << 33);
     b.m = ((unsigned)(cl >> row0) & ST_NRM) | (((unsigned)(cr >> row0) & ST_NRM) << 8);
+    if (cx == 0 || cx == 15) {  // the halo column: column 31 of the tile to the west, column 0 of the tile to the east
+        const uint32_t h = __ldg(lv.tbitsT + ((size_t)(b.ty() + 1) * lv.tb_stride + (b.tx() + (cx == 0 ? 0 : 2))) * 32 + (cx == 0 ? 31 : 0));
+        b.m |= ((h >> row0) & ((1u << ST_RG) - 1)) << 16;
+    }
     return b;
 }
 
@@ -294,8 +303,8 @@ __global__ void __launch_bounds__(ST_THREADS, dir_ctas<ZT>()) k_direction2(Level
             const int64_t gr = (int64_t)tb.ty() * TILE_H + row0, gc = (int64_t)tb.tx() * TILE_W + 2 * cx;
             const int dcL = diag_col<FIXED>(lv, gc), dcR = diag_col<FIXED>(lv, gc + 1);
             const int eoff = toff + (west ? -1 : 2);
-            // the halo cell can only matter if the own edge cell is an unknown
-            const unsigned em = (west ? tb.mL() : (east ? tb.mR() : 0u)) >> 1;
+            // the halo cell can only matter if the own edge cell is an unknown -- and holds a value only if it is one itself
+            const unsigned em = ((west ? tb.mL() : (east ? tb.mR() : 0u)) >> 1) & tb.halo();
             double2 pn[ST_NR];
             double pedge[ST_RG];
             if constexpr (sizeof(PT) == 4 && sizeof(ZT) == 4 && !JACOBI) {
@@ -456,7 +465,7 @@ __global__ void __launch_bounds__(ST_THREADS, ST_UPD_CTAS) k_update2(Level lv, i
             }
             {
                 const int eoff = toff + (west ? -1 : 2);
-                const unsigned em = (west ? mL : (east ? mR : 0u)) >> 1;
+                const unsigned em = ((west ? mL : (east ? mR : 0u)) >> 1) & tb.halo();
 #pragma unroll
                 for (int j = 0; j < ST_RG; ++j)
                     pe[j] = ldnc_if(pb + (eoff + (j + 1) * pitch), em, 1u << j);

@@ -186,6 +186,7 @@ struct sa_scene {
     bool ever_indexed = false;  // the tile lists / bit masks of a previous mask are valid
     bool stale_r = false;       // r was left unscrubbed by a mask change (the red-black path never reads r unmasked)
     bool stale_rb = false;      // ... and so were the cycle's masked-only vectors (float copy of r, red halves, coarse b)
+    bool stale_all = false;     // ... and so was everything else (strip CG + warp-per-tile cycle before and after the change)
 
     // Band window of the next sa_scene_solve-like call: the host-pointer entry points (api.cu) solve a scene in chunks of
     // bands so that PCIe transfers of the other chunks overlap the solve.  band_n < 0: all bands.
@@ -342,7 +343,8 @@ int launch_update2(sa_ctx* ctx, const Level& lv, int nbands, bool jacobi, double
     float* rf, BandScalars* scal, int k);
 
 // work_dirty bits
-enum { WORK_CLEAN = 0, WORK_JACOBI = 1, WORK_RB = 2, WORK_J64 = 4, WORK_FULL = 8, WORK_PF = 16 /* p planes hold floats */ };
+enum { WORK_CLEAN = 0, WORK_JACOBI = 1, WORK_RB = 2, WORK_J64 = 4, WORK_FULL = 8, WORK_PF = 16 /* p planes hold floats */,
+    WORK_RBW = 32 /* the red-black cycle ran on the warp-per-tile kernels (mg_rbw.cu) */ };
 // cg_strip.cu: zero the given planes at the unknowns of `lv` (whole sectors)
 struct ScrubPlanes {
     double* d[5];  // double planes, element (0, 0) of band 0

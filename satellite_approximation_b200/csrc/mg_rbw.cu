@@ -664,10 +664,8 @@ __device__ void rbw_coarsest(const Level& lv, bool fixed, const float* __restric
             const int lr = i >> 5, lc = i & 31;
             const int64_t idx = (r0 + lr) * lv.pitch + c0 + lc;
             const int p = (lr + 1) * CP + lc + 1;
-            if (sw[p] != 0.f) {
-                xb[idx] = sx[p];
-                acc += (double)sb[p] * (double)sx[p];
-            }
+            xb[idx] = sx[p];  // the whole tile: zero at every cell that is not an unknown (1 / d is zero there)
+            acc += (double)sb[p] * (double)sx[p];
         }
         if (DOT) {
             for (int o = 16; o; o >>= 1)
@@ -682,8 +680,7 @@ __device__ void rbw_coarsest(const Level& lv, bool fixed, const float* __restric
     for (int i = t; i < cells; i += nt) {
         const int tile = lv.tile_list[i >> 10], lr = (i >> 5) & 31, lc = i & 31;
         const int64_t idx = ((int64_t)(tile / lv.tiles_x) * TILE_H + lr) * lv.pitch + (int64_t)(tile % lv.tiles_x) * TILE_W + lc;
-        if (lv.umask[idx])
-            xb[idx] = 0.f;
+        xb[idx] = 0.f;  // every cell of the active tiles: the readers of x take whole pairs / quads of it
     }
     __syncthreads();
     for (int hs = 0; hs < 4 * sweeps; ++hs) {
@@ -693,7 +690,9 @@ __device__ void rbw_coarsest(const Level& lv, bool fixed, const float* __restric
             const int64_t r = (int64_t)(tile / lv.tiles_x) * TILE_H + lr, c = (int64_t)(tile % lv.tiles_x) * TILE_W + lc;
             const int64_t idx = r * lv.pitch + c;
             if (((r + c) & 1) == colour && lv.umask[idx]) {
-                const float nb = (xb[idx - lv.pitch] + xb[idx + lv.pitch]) + (xb[idx - 1] + xb[idx + 1]);
+                // neighbours through the mask: the plane is only trusted at the unknowns of the current mask (cg.cu: stale_all)
+                const float nb = ((lv.umask[idx - lv.pitch] ? xb[idx - lv.pitch] : 0.f) + (lv.umask[idx + lv.pitch] ? xb[idx + lv.pitch] : 0.f))
+                    + ((lv.umask[idx - 1] ? xb[idx - 1] : 0.f) + (lv.umask[idx + 1] ? xb[idx + 1] : 0.f));
                 const float w = lv.winv ? lv.winv[idx] : (fixed ? 0.25f : winv_of<false>(lv, r, c));
                 xb[idx] = w * (bb[idx] + nb);
             }
