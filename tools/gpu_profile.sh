@@ -1,39 +1,26 @@
 #!/bin/bash
-# One gpurun call (1 GPU): GPU parity tests, the default bench (both arms), the ncu launch list of the same command and
-# one `ncu --set full` capture per hot kernel.  Everything lands in gpurun_out/<tag>_*; profiles/summarize.py turns the
-# ncu outputs into the text files committed under profiles/.
-#   gpurun --timeout 1500 -- 'bash tools/gpu_profile.sh r1b'
+# One gpurun call (1 GPU): the default bench (both arms), the ncu launch list of the same workload and one `ncu --set full`
+# capture per hot kernel (4 bands: ncu saves and restores device memory around each of its ~40 replays).  Everything lands in
+# gpurun_out/<tag>_*; tools/collect_profiles.sh turns the ncu outputs into the text files committed under profiles/.
+#   gpurun --timeout 2400 -- 'bash tools/gpu_profile.sh r2z'
 tag=${1:-run}
 out=gpurun_out
 mkdir -p $out
-python -m pytest tests -m gpu -x -q > $out/${tag}_pytest.log 2>&1
-echo "pytest rc=$?" | tee -a $out/${tag}_pytest.log
-tail -3 $out/${tag}_pytest.log
-python bench.py > $out/${tag}_bench.log 2> $out/${tag}_bench.err
-echo "bench rc=$?"
-python bench.py --impl reference > $out/${tag}_bench_reference.log 2> $out/${tag}_bench_reference.err
-echo "bench reference rc=$?"
+python bench.py --steps ${STEPS:-20} --warmup 5 > $out/${tag}_bench.json 2> $out/${tag}_bench.err; echo "bench rc=$?"
+python bench.py --impl reference --steps 3 --warmup 1 > $out/${tag}_bench_reference.json 2> $out/${tag}_bench_reference.err; echo "bench reference rc=$?"
 # launch list: the default workload, one warm-up + one timed step (shares must agree with the bench's own event times)
-python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu > $out/${tag}_plain.log 2>&1 &&
+A="--steps 1 --warmup 1 --no-e2e --no-cpu --no-dropin --no-multi"
+python bench.py $A > $out/${tag}_plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file $out/${tag}_launches.csv \
-    python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu > $out/${tag}_ncu_launches.log 2>&1
+    python bench.py $A > $out/${tag}_ncu_launches.log 2>&1
 echo "launch list rc=$?"
-# full captures, 4 bands (ncu saves and restores device memory around each of its ~40 replays)
-# (a V-cycle launches k_rb_down on levels 0..10 and k_rb_up on levels 10..0: skip to a level-0 launch of the 2nd cycle)
-for ks in k_update2:2 k_direction2:2 k_rb_down:11 k_rb_up:21; do
-    k=${ks%%:*}; skip=${ks##*:}
-    timeout 600 ncu --set full --clock-control none --import-source on -k regex:"^${k}\$" --launch-skip $skip --launch-count 1 \
-        -f -o $out/${tag}_full_${k} python bench.py --steps 1 --warmup 0 --bands 4 --no-e2e --no-cpu > $out/${tag}_ncu_${k}.log 2>&1
-    echo "ncu $k rc=$?"
+# full captures of the level-0 kernels of the second CG iteration (template arguments select the level-0 instantiations)
+B="--steps 1 --warmup 0 --bands 4 --no-e2e --no-cpu --no-dropin --no-multi"
+for ks in "k_update2<:update2" "k_direction2<:direction2" "k_rbw_down<.int.0>:rbw_down_L0" "k_rbw_up<.int.0, .bool.1>:rbw_up_L0" "k_rbw_down<.int.1>:rbw_down_L1" "k_rbw_up<.int.1, .bool.0>:rbw_up_L1"; do
+    k=${ks%%:*}; name=${ks##*:}
+    timeout 600 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:"${k}" --launch-skip 1 --launch-count 1 \
+        -f -o $out/${tag}_full_${name} python bench.py $B > $out/${tag}_ncu_${name}.log 2>&1
+    echo "ncu $name rc=$?"
 done
-# DENSE=1: the same two cycle kernels on a dense hole of the same size (bench.py --mask full): same halo factor, every DRAM
-# granule full -- the pair of captures that separates "halos miss in L2" from "short runs" 
-if [ "${DENSE:-0}" = "1" ]; then
-    for ks in k_rb_down:11 k_rb_up:21 k_update2:2; do
-        k=${ks%%:*}; skip=${ks##*:}
-        timeout 600 ncu --set full --clock-control none --import-source on -k regex:"^${k}\$" --launch-skip $skip --launch-count 1 \
-            -f -o $out/${tag}_dense_full_${k} python bench.py --steps 1 --warmup 0 --bands 4 --mask full --no-e2e --no-cpu > $out/${tag}_dense_ncu_${k}.log 2>&1
-        echo "ncu dense $k rc=$?"
-    done
-fi
-ls -la $out | tail -20
+grep -o '"unknowns_per_band": [0-9]*' $out/${tag}_ncu_update2.log | head -1 > $out/${tag}_units.txt
+ls -la $out | grep ${tag}_ | tail -20
