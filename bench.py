@@ -100,6 +100,9 @@ def parse_args():
     ap.add_argument("--no-multi", action="store_true", help="N > 1: skip the row-decomposed / one-tile / parity sub-records")
     ap.add_argument("--cpu-crop", type=int, default=768, help="edge of the crop the CPU baseline solves")
     ap.add_argument("--hole", type=int, default=20000, help="edge of the row-decomposed hole (configs[4]: 20000)")
+    ap.add_argument("--rank-seeds", action="store_true",
+                    help="N > 1: every rank builds a scene of its own (seed 2 + 17 rank) instead of its own copy of THE benchmark tile; "
+                         "the masks then need 9 or 10 CG iterations and the slowest rank sets the step (config.per_rank shows it)")
     return ap.parse_args()
 
 
@@ -440,8 +443,11 @@ def run_b200(args, w):
     if world > 1:
         ctx.dist_init_torch()  # the library's own NCCL communicator (row decomposition: csrc/dist.cu)
 
-    mask = device_inputs(w, rank, dev)
-    bands = [device_band(w, b, 0 if one_system else rank, dev) for b in range(nb)]
+    # weak scaling: every rank fills its own copy of the benchmark tile (configs[2] names ONE tile: seed 2), so that the
+    # per-N values differ by what running N GPUs at once costs and not by which masks the other ranks drew
+    scene_rank = rank if args.rank_seeds else 0
+    mask = device_inputs(w, scene_rank, dev)
+    bands = [device_band(w, b, 0 if one_system else scene_rank, dev) for b in range(nb)]
     guides = [0.9 * bands[(b + 1) % nb] + 37.0 for b in range(nb)] if poisson else None
     if args.mask:  # diagnostic patterns: how the kernels' throughput depends on the shape of the unknown set
         rr = torch.arange(rows, device=dev)[:, None]
@@ -575,7 +581,7 @@ def run_b200(args, w):
     if rank == 0:
         cfg = {"workload": w["desc"], "problem": w["problem"], "rows": rows, "cols": cols, "bands": nb,
                "mask": ("SURVEY 8d: Gaussian-filtered (sigma = %g px) white noise thresholded at the analytic %g quantile, border ring "
-                        "cleared (synth.torch_cloud_mask, seed 2 + 17 rank)" % (w["sigma"], 1 - w["cover"])) if w.get("sigma") and not args.mask else (args.mask or "see workload"),
+                        "cleared (synth.torch_cloud_mask, seed %s)" % (w["sigma"], 1 - w["cover"], "2 + 17 rank" if args.rank_seeds else "2 on every rank")) if w.get("sigma") and not args.mask else (args.mask or "see workload"),
                "setup_ms": st[0]["setup_ms"], "solve_ms": st[0]["solve_ms"],
                "unknowns_per_band": unknowns, "tolerance": args.tol, "precond": args.precond,
                "mg_variant": args.mg_variant if args.precond == "multigrid" else None,
@@ -585,7 +591,7 @@ def run_b200(args, w):
                      "scene fits L2; mask re-upload + re-index between steps, no explicit flush",
                "parallelism": (f"one system split by rows over {world} GPU(s): NCCL halo rows + packed all-reduce of "
                                "the dot products, coarse multigrid levels replicated") if one_system else
-                              f"{world} independent scene(s), one per GPU, no collective"}  # fmt: skip
+                              f"{world} independent scene(s), one per GPU ({'own seeds' if args.rank_seeds else 'every rank its own copy of the benchmark tile'}), no collective"}  # fmt: skip
         for k in ("one_tile_strong", "row_decomposed"):
             if k in extra:
                 cfg[k] = extra[k]
