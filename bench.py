@@ -816,6 +816,7 @@ def run_row_decomposed(args, ctx, sab, rank, world, dev, stream, barrier, multi,
     launches = t.launches
     lo, hi, _ = scene.owned_rows() if world > 1 else (0, n, 0)
     st = t.st
+    peer = ctx.dist_uses_peer_memory if world > 1 else False
     scene.close()
     del mask
     torch.cuda.empty_cache()
@@ -824,7 +825,10 @@ def run_row_decomposed(args, ctx, sab, rank, world, dev, stream, barrier, multi,
     for v in tab.values():
         v["frac"] = v["GBps"] / peak if v["GBps"] else None
     return {"what": f"single {n}x{n} contiguous hole, one system split by rows over {world} GPU(s)"
-                    + (": halo rows and dot products over the library's NCCL communicator" if world > 1 else " (no exchange)"),
+                    + ((": halo rows and dot products over peer memory (CUDA IPC arenas, two kernels per exchange); NCCL for the plan "
+                        "and the gather of the first replicated level" if peer else
+                        ": halo rows and dot products over the library's NCCL communicator") if world > 1 else " (no exchange)"),
+            "exchange": ("peer memory" if peer else "nccl") if world > 1 else None,
             "ms_per_solve": ms_max, "value": st[0]["unknowns"] / (ms_max * 1e-3), "unit": UNIT, "unknowns": st[0]["unknowns"],
             "cg_iterations": t.iters, "converged": all(s["status"] == sab.SA_OK for s in st),
             "worst_rel_residual": max(s["error"] for s in st), "setup_ms": st[0]["setup_ms"], "solve_ms": st[0]["solve_ms"],

@@ -210,6 +210,10 @@ int sa_dist_levels(int64_t rows, int world);
 int sa_scene_set_distributed(sa_scene* scene, int on);
 int sa_scene_owned_rows(const sa_scene* scene, int64_t* lo, int64_t* hi, int* axis);
 int sa_scene_allgather_band(sa_scene* scene, int band);
+/* 1 when the exchanges inside the iteration loop of a row-decomposed solve go over peer memory -- every rank's arena mapped by
+ * all ranks of the node through CUDA IPC, two small kernels per exchange -- and 0 when they go over NCCL (the fallback: peers
+ * that cannot map each other, or SATFILL_DIST_NCCL_ONLY in the environment).  Valid after the first distributed solve. */
+int sa_dist_uses_peer_memory(const sa_ctx* ctx);
 
 /* 1 if the last sa_laplace_fill / sa_poisson_blend of this context ran in direct mode: the caller's arrays were page-locked
  * (device-addressable), so no image was copied -- the set-up kernel read the known pixels that border the unknown set (and

@@ -183,6 +183,11 @@ class Context:
         return st
 
     @property
+    def dist_uses_peer_memory(self) -> bool:
+        """True when the exchanges of a row-decomposed solve go over peer memory (CUDA IPC) rather than NCCL."""
+        return bool(self._lib.sa_dist_uses_peer_memory(self._h))
+
+    @property
     def has_legacy_variants(self) -> bool:
         """True when the loaded library also holds the first-generation kernels (cg_variant = 1, MG_JACOBI64, MG_RB32_CTA):
         lib/libsatfill_legacy.so, built with SATFILL_LEGACY_VARIANTS.  The product library refuses those variants."""

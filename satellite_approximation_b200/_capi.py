@@ -33,7 +33,7 @@ EXPORTS = [
     "sa_scene_solve", "sa_scene_get_band", "sa_scene_info", "sa_scene_precondition", "sa_synchronize",
     "sa_dist_unique_id", "sa_dist_init", "sa_dist_partition", "sa_dist_levels", "sa_scene_set_distributed",
     "sa_scene_owned_rows", "sa_scene_allgather_band", "sa_apply_laplace_u8", "sa_morph_close_mask", "sa_last_fill_direct",
-    "sa_scene_plane_elements", "sa_has_legacy_variants",
+    "sa_scene_plane_elements", "sa_has_legacy_variants", "sa_dist_uses_peer_memory",
 ]  # fmt: skip
 
 
@@ -161,6 +161,8 @@ def load() -> C.CDLL:
     L.sa_last_fill_direct.argtypes = [_vp]
     L.sa_scene_plane_elements.restype = _i64
     L.sa_scene_plane_elements.argtypes = [_i64, _i64]
+    L.sa_dist_uses_peer_memory.restype = C.c_int
+    L.sa_dist_uses_peer_memory.argtypes = [_vp]
     L.sa_has_legacy_variants.restype = C.c_int
     L.sa_has_legacy_variants.argtypes = []
     L.sa_synchronize.restype = C.c_int

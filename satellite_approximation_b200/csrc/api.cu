@@ -622,6 +622,8 @@ int sa_scene_owned_rows(const sa_scene* s, int64_t* lo, int64_t* hi, int* axis)
     return SA_OK;
 }
 
+int sa_dist_uses_peer_memory(const sa_ctx* ctx) { return ctx ? dist_uses_peer_memory(ctx) : 0; }
+
 int sa_scene_allgather_band(sa_scene* s, int band)
 {
     if (!s)

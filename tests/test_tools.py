@@ -35,3 +35,28 @@ def test_tile_stats_known_answers():
     r[0, 3:8] = True
     assert ts.granule_amplification(r, 8, 32) == 2 * 32 / 40 and ts.granule_amplification(r, 8, 64) == 64 / 40
     assert ts.granule_amplification(r, 4, 32) == 32 / 20 and ts.granule_amplification(r, 4, 128) == 128 / 20
+
+
+def test_bench_scene_is_window_reproducible():
+    """bench.py's scene (Gaussian-filtered sigma = 40 px white noise, analytic threshold; synth.cloud_mask /
+    scene_band): any window can be built on its own and equals the same pixels of a larger window, and the numpy and torch
+    generators agree -- that is what lets the CPU reference arm solve a crop of the VERY SAME scene the B200 arm fills."""
+    import torch
+
+    from satellite_approximation_b200 import synth
+
+    big = synth.cloud_mask(500, 620, seed=2, row0=4000, col0=3900, clear_border=False)
+    sub = synth.cloud_mask(300, 256, seed=2, row0=4096, col0=4100, clear_border=False)
+    assert np.array_equal(big[96:396, 200:456], sub)
+    assert 0.05 < big.mean() < 0.65  # 30 % cover over the tile; a window a few blobs wide fluctuates widely
+    t = synth.torch_cloud_mask(300, 256, seed=2, device="cpu", row0=4096, col0=4100, clear_border=False).numpy().astype(bool)
+    assert (t != sub).mean() < 1e-4  # float rounding of the two filters: at most a handful of pixels at the threshold
+    cleared = synth.cloud_mask(300, 256, seed=2, row0=4096, col0=4100)
+    assert not cleared[0].any() and not cleared[-1].any() and not cleared[:, 0].any() and not cleared[:, -1].any()
+    assert not np.array_equal(synth.cloud_mask(64, 64, seed=2, row0=4096, col0=4100), synth.cloud_mask(64, 64, seed=19, row0=4096, col0=4100))
+    b = synth.scene_band(120, 90, seed=5, row0=100, col0=50, total_rows=10980, total_cols=10980)
+    whole = synth.scene_band(400, 300, seed=5, row0=0, col0=0, total_rows=10980, total_cols=10980)
+    assert np.array_equal(whole[100:220, 50:140], b)
+    bt = synth.torch_scene_band(120, 90, seed=5, device="cpu", row0=100, col0=50, total_rows=10980, total_cols=10980).numpy()
+    assert np.max(np.abs(b - bt)) < 1e-9 and b.min() >= 0.0 and b.max() <= 10000.0
+    assert abs(synth.cloud_threshold(40.0, 0.5)) < 1e-12 and synth.cloud_threshold(40.0, 0.3) > 0
