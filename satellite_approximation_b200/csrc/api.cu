@@ -248,6 +248,7 @@ int sa_create(sa_ctx** out, int device, void* stream)
         ctx->owns_stream = true;
     }
     cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+    ctx->grid_sms = ctx->sm_count;
     ctx->pinned_bytes = 1 << 20;
     if (cudaMallocHost(&ctx->pinned, ctx->pinned_bytes) != cudaSuccess) {
         if (ctx->owns_stream)
@@ -722,7 +723,9 @@ static int host_fill(sa_ctx* ctx, int problem, double* const* images, const doub
         cudaGetLastError();  // cudaPointerGetAttributes on pageable memory may leave a sticky-free error behind
         ctx->last_fill_direct = direct;
         if (direct) {
-            // chunks: the scatter of chunk c (io_out) overlaps the solve of chunk c + 1
+            // Band windows: the unknowns of window c travel home (k_scatter_direct on io_out, a few CTAs) while window
+            // c + 1 is solved.  A solve costs a few milliseconds whatever its size and a window's scatter has to hide
+            // under the next solve, so a tile is cut into about five windows -- one when its bands are small.
             const int64_t band_bytes = s->rows * s->cols * (int64_t)sizeof(double);
             int64_t chunk_bytes = (int64_t)256 << 20;
             if (const char* e = std::getenv("SATFILL_CHUNK_BYTES"))
@@ -730,7 +733,14 @@ static int host_fill(sa_ctx* ctx, int problem, double* const* images, const doub
             int per_chunk = (int)std::min<int64_t>(std::min(nbands, HOST_BANDS_MAX), std::max<int64_t>(1, chunk_bytes / std::max<int64_t>(band_bytes, 1)));
             if (per_chunk >= nbands && nbands <= HOST_BANDS_MAX)
                 per_chunk = nbands;
-            const int nch = (nbands + per_chunk - 1) / per_chunk;
+            else if (!std::getenv("SATFILL_CHUNK_BYTES"))
+                per_chunk = std::min(HOST_BANDS_MAX, std::max(per_chunk, (nbands + 4) / 5));
+            if (const char* e = std::getenv("SATFILL_CHUNK_BANDS"))  // tuning knob
+                per_chunk = std::min(std::min(nbands, HOST_BANDS_MAX), std::max(1, std::atoi(e)));
+            std::vector<int> edge { 0 };  // window c holds the bands [edge[c], edge[c + 1])
+            while (edge.back() < nbands)
+                edge.push_back(std::min(nbands, edge.back() + per_chunk));
+            const int nch = (int)edge.size() - 1;
             if (!ctx->io_out) {
                 SA_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->io_in, cudaStreamNonBlocking));
                 SA_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->io_out, cudaStreamNonBlocking));
@@ -751,24 +761,39 @@ static int host_fill(sa_ctx* ctx, int problem, double* const* images, const doub
             const bool dbg = std::getenv("SATFILL_DEBUG_IO") != nullptr;
             auto now_ms = [] { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; };
             const double t_start = now_ms();
-            // While window c is solved on the context's stream, k_fetch_direct pulls the known ring of window c + 1 over PCIe
-            // on io_in and k_scatter_direct carries the unknowns of window c - 1 back on io_out (a few CTAs each).
             SA_TRY(prepare_solve(s, o));
+            // The way in: while window c is solved on the context's stream, k_fetch_direct pulls the ring of known pixels
+            // of window c + 1 over PCIe on io_in.  Every read of host memory is a PCIe round trip and the bus takes only
+            // so many at a time (measured: 4.6 GB/s with 64 CTAs, less with more), so the rings of a 13-band tile need
+            // ~45 ms however they are fetched: they have to travel beside the solves, not in front of them.
             while ((int)ctx->io_ev.size() < nch) {
                 cudaEvent_t e;
                 SA_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
                 ctx->io_ev.push_back(e);
             }
             auto fetch = [&](int c) {
-                const int b0 = c * per_chunk, b1 = std::min(nbands, (c + 1) * per_chunk);
+                const int b0 = edge[(size_t)c], b1 = edge[(size_t)c + 1];
                 SA_TRY(launch_fetch_direct(ctx, ctx->io_in, lv, b1 - b0, problem == SA_POISSON, s->plane0(s->u, b0),
                     problem == SA_POISSON ? s->plane0(s->g, b0) : nullptr, window(b0, b1)));
                 SA_CUDA(ctx, cudaEventRecord(ctx->io_ev[(size_t)c], ctx->io_in));
                 return (int)SA_OK;
             };
+            // The io kernels hold a few SMs for themselves (cg_strip.cu: io_ctas); the solve kernels size their grids --
+            // CTAs that each walk a fixed share of the tiles -- for the SMs that are left, so that every solve CTA is
+            // resident at once.
+            struct GridGuard {
+                sa_ctx* c;
+                ~GridGuard() { c->grid_sms = c->sm_count; }
+            } grid_guard { ctx };
+            if (nch > 1) {
+                int reserve = io_ctas(false) + io_ctas(true);
+                if (const char* e = std::getenv("SATFILL_IO_RESERVE_SMS"))  // tuning knob
+                    reserve = std::atoi(e);
+                ctx->grid_sms = std::max(ctx->sm_count / 2, ctx->sm_count - std::max(0, reserve));
+            }
             SA_TRY(fetch(0));
             for (int c = 0; c < nch; ++c) {
-                const int b0 = c * per_chunk, b1 = std::min(nbands, (c + 1) * per_chunk);
+                const int b0 = edge[(size_t)c], b1 = edge[(size_t)c + 1];
                 const HostBands hb = window(b0, b1);
                 s->band0 = b0;
                 s->band_n = b1 - b0;
@@ -793,7 +818,7 @@ static int host_fill(sa_ctx* ctx, int problem, double* const* images, const doub
             }
             if (problem == SA_POISSON && st == SA_OK)  // nothing is written unless every band converged (poisson.cpp:263-269)
                 for (int c = 0; c < nch; ++c) {
-                    const int b0 = c * per_chunk, b1 = std::min(nbands, (c + 1) * per_chunk);
+                    const int b0 = edge[(size_t)c], b1 = edge[(size_t)c + 1];
                     SA_TRY(launch_scatter_direct(ctx, ctx->io_out, lv, b1 - b0, s->plane0(s->u, b0), window(b0, b1)));
                 }
             SA_CUDA(ctx, cudaStreamSynchronize(ctx->io_out));

@@ -687,7 +687,7 @@ int launch_scrub(sa_ctx* ctx, const Level& lv, int nbands, const ScrubPlanes& pl
 // there are tiles, so that every CTA owns a tile of every band.
 static unsigned strip_grid(const sa_ctx* ctx, const Level& lv, int ctas_per_sm)
 {
-    int g = ctx->sm_count * ctas_per_sm;
+    int g = ctx->grid_sms * ctas_per_sm;
     return (unsigned)(g < lv.n_tiles ? g : lv.n_tiles);
 }
 
@@ -712,22 +712,43 @@ int launch_setup2(sa_ctx* ctx, const Level& lv, int nbands, bool poisson, double
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// The io kernels of the direct mode run beside the solves (api.cu).  Both are bound by PCIe latency, not by anything an SM
+// does, so each is a handful of 1024-thread CTAs: an io CTA has an SM to itself and the solve kernels, whose grids are
+// sized for the SMs that are left (sa_ctx::grid_sms), never wait for a slot it holds.  (io CTAs sprinkled over many SMs
+// cost every one of those SMs a solve CTA, and a solve CTA that does not fit runs as a second wave: measured +50 % on the
+// solve with 16 x 256 threads of scatter beside it.)
+//   fetch: reads of host memory, ~3 ms per band of a 10980^2 tile with 6 x 1024 threads, slower with fewer AND with many more;
+//   scatter: posted writes, 64 warps keep PCIe busy (38 GB/s of unknown pixels alone, the same as tools/probe measures).
+// ---------------------------------------------------------------------------------------------------------------
+int io_ctas(bool scatter)
+{
+    static const int f = [] { const char* e = std::getenv("SATFILL_FETCH_CTAS"); return e && std::atoi(e) > 0 ? std::atoi(e) : 6; }();
+    static const int sc = [] { const char* e = std::getenv("SATFILL_SCATTER_CTAS"); return e && std::atoi(e) > 0 ? std::atoi(e) : 2; }();
+    return scatter ? sc : f;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // k_fetch_direct: the way in of the direct mode (api.cu).  The caller's page-locked arrays are device-addressable, so
 // nothing is copied: this kernel reads, straight from host memory, exactly the pixels k_setup2 will look at -- a pair of
 // cells that are both unknowns is never fetched, so what crosses PCIe is the ring of known pixels around the unknown set
 // (and, for Poisson, g on the unknown set and around it) -- and drops them into the image (and guidance) planes.  It runs
-// on a few CTAs beside the solve of the previous band window: the volume is tiny (2 % of the image on cloud-like masks),
-// only PCIe latency has to be covered.  Known pixels elsewhere in the planes are stale and never read.
+// on a few CTAs beside the solve of the previous band window: the volume is tiny (2 % of the image on cloud-like masks)
+// but every read is a PCIe round trip.  Known pixels elsewhere in the planes are stale and never read.
 // ---------------------------------------------------------------------------------------------------------------
+constexpr int IO_THREADS = 1024;  // an io CTA takes a whole SM (see io_ctas below)
 template <bool POISSON>
-__global__ void __launch_bounds__(ST_THREADS) k_fetch_direct(Level lv, int nbands, double* __restrict__ u, double* __restrict__ g,
+__global__ void __launch_bounds__(IO_THREADS, 1) k_fetch_direct(Level lv, int nbands, double* __restrict__ u, double* __restrict__ g,
     HostBands src)
 {
-    const int cx = threadIdx.x & 15, row0 = (threadIdx.x >> 4) * ST_RG;
+    // groups of ST_THREADS threads walk the tiles independently (no CTA-wide barrier; the shuffles stay inside a warp)
+    constexpr int GROUPS = IO_THREADS / ST_THREADS;
+    const int tid = threadIdx.x % ST_THREADS;
+    const int cx = tid & 15, row0 = (tid >> 4) * ST_RG;
     const int pitch = (int)lv.pitch, fpitch = (int)src.pitch;
     const int toff = (row0 - 1) * pitch + 2 * cx, ftoff = (row0 - 1) * fpitch + 2 * cx;
     const bool west = cx == 0, east = cx == 15;
-    for (int i = blockIdx.x; i < lv.n_tiles; i += gridDim.x) {  // trip count is uniform over the CTA: shuffles are safe
+    // trip count is uniform over a group (and a warp lies inside one group): shuffles are safe
+    for (int i = blockIdx.x * GROUPS + threadIdx.x / ST_THREADS; i < lv.n_tiles; i += gridDim.x * GROUPS) {
         const TileBits tb = load_tile_bits(lv, lv.tile_yx[i], cx, row0);
         const unsigned mL = tb.mL(), mR = tb.mR(), any = tb.any();
         unsigned mW = __shfl_up_sync(0xffffffffu, mR, 1), mE = __shfl_down_sync(0xffffffffu, mL, 1);
@@ -807,14 +828,11 @@ int launch_fetch_direct(sa_ctx* ctx, cudaStream_t stream, const Level& lv, int n
         return SA_OK;
     if (nbands > HOST_BANDS_MAX)
         return fail(ctx, SA_BAD_ARGUMENT, "direct fetch: too many bands in one window");
-    int want = 64;  // a few dozen CTAs cover PCIe latency; more only take SM slots from the solve that runs beside them
-    if (const char* e = std::getenv("SATFILL_FETCH_CTAS"))  // tuning knob
-        want = std::atoi(e) > 0 ? std::atoi(e) : want;
-    const unsigned grid = (unsigned)(want < lv.n_tiles ? want : lv.n_tiles);
+    const unsigned grid = (unsigned)io_ctas(false);
     if (poisson)
-        k_fetch_direct<true><<<grid, ST_THREADS, 0, stream>>>(lv, nbands, u, g, src);
+        k_fetch_direct<true><<<grid, IO_THREADS, 0, stream>>>(lv, nbands, u, g, src);
     else
-        k_fetch_direct<false><<<grid, ST_THREADS, 0, stream>>>(lv, nbands, u, g, src);
+        k_fetch_direct<false><<<grid, IO_THREADS, 0, stream>>>(lv, nbands, u, g, src);
     ctx->launches += 1;
     SA_CUDA(ctx, cudaGetLastError());
     return SA_OK;
@@ -825,34 +843,50 @@ int launch_fetch_direct(sa_ctx* ctx, cudaStream_t stream, const Level& lv, int n
 // plane straight into the caller's page-locked arrays: 16 bytes where both cells of a pair are unknowns, 8 bytes where
 // one is.  Known pixels never cross PCIe in either direction (laplace.cpp:117-119 / poisson.cpp:273-283 only write the
 // invalid pixels too).
+// The stores go out in raster order of the caller's array: the warps of the grid walk the image row by row, each taking K
+// consecutive 64-column segments (K x 512 bytes) of one row at a time, a lane per aligned column pair; the K loads are in
+// flight together.  At any moment the whole grid writes into a few neighbouring rows, i.e. a few pages of host memory.
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(ST_THREADS) k_scatter_direct(Level lv, int nbands, const double* __restrict__ u, HostBands dst)
+template <int K>
+__global__ void __launch_bounds__(IO_THREADS, 1) k_scatter_direct(Level lv, int nbands, const double* __restrict__ u, HostBands dst)
 {
-    const int cx = threadIdx.x & 15, row0 = (threadIdx.x >> 4) * ST_RG;
+    const int lane = threadIdx.x & 31;
+    const int warp = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), nwarps = (int)((gridDim.x * blockDim.x) >> 5);
+    const int pairs_x = (lv.tiles_x + 1) >> 1, groups_x = (pairs_x + K - 1) / K;
     const int pitch = (int)lv.pitch, hpitch = (int)dst.pitch;
-    for (int i = blockIdx.x; i < lv.n_tiles; i += gridDim.x) {
-        const TileBits tb = load_tile_bits(lv, lv.tile_yx[i], cx, row0);
-        const unsigned mL = tb.mL(), mR = tb.mR();
-        if (((mL | mR) & ST_OWN) == 0)
-            continue;
-        const int o = tb.origin(pitch) + (row0 - 1) * pitch + 2 * cx;
-        const int ho = tb.origin(hpitch) + (row0 - 1) * hpitch + 2 * cx;
-        for (int band = 0; band < nbands; ++band) {
-            const double* ub = u + (int64_t)band * lv.plane;
-            double* hb = dst.f[band];
+    const int n_groups = (int)dst.rows * groups_x;
+    const int sh = (2 * lane) & 31;
+    for (int g = warp; g < n_groups; g += nwarps) {
+        const int r = g / groups_x, tp0 = (g - r * groups_x) * K;
+        // the row's 32-column words of the tiles of the K segments: lanes 0..15 hold the left tile's, 16..31 the right one's
+        const uint32_t* w = lv.tbits + ((size_t)((r >> 5) + 1) * lv.tb_stride + (2 * tp0 + (lane >> 4) + 1)) * 32 + (r & 31);
+        unsigned bits[K];
+        bool any = false;
 #pragma unroll
-            for (int j = 1; j <= ST_RG; ++j) {
-                const bool l = (mL >> j) & 1, r = (mR >> j) & 1;
-                if (l | r) {
-                    const double2 v = *reinterpret_cast<const double2*>(ub + (o + j * pitch));
-                    double* h = hb + (ho + j * hpitch);
-                    if (l & r)
-                        *reinterpret_cast<double2*>(h) = v;
-                    else if (l)
-                        h[0] = v.x;
-                    else
-                        h[1] = v.y;
-                }
+        for (int k = 0; k < K; ++k) {
+            bits[k] = tp0 + k < pairs_x ? (__ldg(w + (size_t)k * 64) >> sh) & 3u : 0u;
+            any |= bits[k] != 0;
+        }
+        if (!__any_sync(0xffffffffu, any))
+            continue;
+        const int o = r * pitch + tp0 * (2 * TILE_W) + 2 * lane, ho = r * hpitch + tp0 * (2 * TILE_W) + 2 * lane;
+        for (int band = 0; band < nbands; ++band) {
+            const double* ub = u + (int64_t)band * lv.plane + o;
+            double* hb = dst.f[band] + ho;
+            double2 v[K];
+#pragma unroll
+            for (int k = 0; k < K; ++k)
+                if (bits[k])
+                    v[k] = *reinterpret_cast<const double2*>(ub + k * (2 * TILE_W));
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                double* h = hb + k * (2 * TILE_W);
+                if (bits[k] == 3u)
+                    *reinterpret_cast<double2*>(h) = v[k];
+                else if (bits[k] == 1u)
+                    h[0] = v[k].x;
+                else if (bits[k] == 2u)
+                    h[1] = v[k].y;
             }
         }
     }
@@ -864,12 +898,7 @@ int launch_scatter_direct(sa_ctx* ctx, cudaStream_t stream, const Level& lv, int
         return SA_OK;
     if (nbands > HOST_BANDS_MAX)
         return fail(ctx, SA_BAD_ARGUMENT, "direct scatter: too many bands in one window");
-    // a modest grid: the stores are bound by PCIe, and the next chunk's solve wants the SMs
-    int want = 16;  // the stores are bound by PCIe; more CTAs only take slots from the solve that runs beside them
-    if (const char* e = std::getenv("SATFILL_SCATTER_CTAS"))  // tuning knob
-        want = std::atoi(e) > 0 ? std::atoi(e) : want;
-    unsigned grid = (unsigned)(want < lv.n_tiles ? want : lv.n_tiles);
-    k_scatter_direct<<<grid, ST_THREADS, 0, stream>>>(lv, nbands, u, dst);
+    k_scatter_direct<8><<<(unsigned)io_ctas(true), IO_THREADS, 0, stream>>>(lv, nbands, u, dst);
     ctx->launches += 1;
     SA_CUDA(ctx, cudaGetLastError());
     return SA_OK;

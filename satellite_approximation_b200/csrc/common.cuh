@@ -107,6 +107,7 @@ struct sa_ctx {
     int64_t launches = 0;
     std::string error;
     int sm_count = 148;
+    int grid_sms = 148;  // the SMs the solve kernels size their grids for (api.cu: fewer while io kernels run beside them)
     // pinned host scratch for polling convergence flags / small read-backs
     void* pinned = nullptr;
     size_t pinned_bytes = 0;
@@ -337,6 +338,7 @@ int prepare_solve(sa_scene* s, const sa_options& o);
 int launch_fetch_direct(sa_ctx* ctx, cudaStream_t stream, const Level& lv, int nbands, bool poisson, double* u, double* g,
     const HostBands& src);
 int launch_scatter_direct(sa_ctx* ctx, cudaStream_t stream, const Level& lv, int nbands, const double* u, const HostBands& dst);
+int io_ctas(bool scatter);  // CTAs (one SM each) of the fetch / scatter kernel
 int launch_direction2(sa_ctx* ctx, const Level& lv, int nbands, bool jacobi, const void* zin, bool z_is_float,
     const void* p_old, void* p_new, bool p_is_float, BandScalars* scal, int k);
 int launch_update2(sa_ctx* ctx, const Level& lv, int nbands, bool jacobi, double* u, const void* p, bool p_is_float, double* r,

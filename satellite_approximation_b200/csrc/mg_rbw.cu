@@ -829,7 +829,7 @@ int launch_down_w(sa_ctx* ctx, const RWLevel& F, const RWLevel& C, int nb, const
     static int occ[3] = { 0, 0, 0 };
     if (!occ[mode])
         occ[mode] = mode == 0 ? ctas_per_sm(k_rbw_down<0>, 0, 32) : (mode == 1 ? ctas_per_sm(k_rbw_down<1>, 0, 32) : ctas_per_sm(k_rbw_down<2>, 0, 32));
-    const int max_ctas = ctx->sm_count * occ[mode];  // one warp each
+    const int max_ctas = ctx->grid_sms * occ[mode];  // one warp each
     const Items it = make_items(F.lv.n_tiles, nb, max_ctas, band_major_for(F.lv));
     const unsigned grid = (unsigned)(it.count() < max_ctas ? it.count() : max_ctas);
     if (mode == 0)
@@ -854,7 +854,7 @@ int launch_up_w(sa_ctx* ctx, const RWLevel& F, const RWLevel& C, int nb, BandSca
         occ[mode] = mode == 0 ? ctas_per_sm(k_rbw_up<0, DOT>, smem, 32) : (mode == 1 ? ctas_per_sm(k_rbw_up<1, DOT>, smem, 32) : ctas_per_sm(k_rbw_up<2, DOT>, smem, 32));
         occ_smem[mode] = smem;
     }
-    const int max_ctas = ctx->sm_count * occ[mode];  // one warp each
+    const int max_ctas = ctx->grid_sms * occ[mode];  // one warp each
     const Items it = make_items(F.lv.n_tiles, nb, max_ctas, band_major_for(F.lv));
     const unsigned grid = (unsigned)(it.count() < max_ctas ? it.count() : max_ctas);
     if (mode == 0)
@@ -875,7 +875,7 @@ int launch_tail(sa_ctx* ctx, const std::vector<RWLevel>& L, int first, int nb, B
     int tail_ctas = env_int("SATFILL_TAIL_CTAS_PER_SM", 2);
     if (tail_ctas > occ)
         tail_ctas = occ;
-    const int max_ctas = ctx->sm_count * tail_ctas;
+    const int max_ctas = ctx->grid_sms * tail_ctas;
     TailArgs A {};
     A.n = (int)L.size() - first;
     A.nbands = nb;
