@@ -121,16 +121,18 @@ __global__ void k_finalize_setup(BandScalars* scal, int nbands, double tol, int 
 __global__ void __launch_bounds__(CG_THREADS) k_zero_unknowns(Level lv, double* __restrict__ u,
     const BandScalars* __restrict__ scal)
 {
-    if (!scal[blockIdx.y].zero_rhs)
+    if (!scal[blockIdx.y].zero_rhs)  // (almost always: the grid is a few CTAs per band that walk the tile list)
         return;
-    int tile = lv.tile_list[blockIdx.x];
-    int64_t r0 = (int64_t)(tile / lv.tiles_x) * TILE_H, c0 = (int64_t)(tile % lv.tiles_x) * TILE_W;
-    int64_t boff = (int64_t)blockIdx.y * lv.plane;
+    const int64_t boff = (int64_t)blockIdx.y * lv.plane;
+    for (int i = blockIdx.x; i < lv.n_tiles; i += gridDim.x) {
+        const int tile = lv.tile_list[i];
+        const int64_t r0 = (int64_t)(tile / lv.tiles_x) * TILE_H, c0 = (int64_t)(tile % lv.tiles_x) * TILE_W;
 #pragma unroll
-    for (int j = 0; j < ROWS_PER_THREAD; ++j) {
-        int64_t idx = (r0 + threadIdx.y + j * CG_BLOCK_Y) * lv.pitch + c0 + threadIdx.x;
-        if (lv.umask[idx])
-            u[boff + idx] = 0.0;
+        for (int j = 0; j < ROWS_PER_THREAD; ++j) {
+            const int64_t idx = (r0 + threadIdx.y + j * CG_BLOCK_Y) * lv.pitch + c0 + threadIdx.x;
+            if (lv.umask[idx])
+                u[boff + idx] = 0.0;
+        }
     }
 }
 
@@ -798,7 +800,7 @@ int solve_scene(sa_scene* s, const sa_options& o, sa_stats* stats)
     }
     SA_LAUNCH(ctx, k_final_check, (nb + 63) / 64, 64, 0, scal, nb, (int)(k & 0x3fffffff));
     if (have_tiles)
-        SA_LAUNCH(ctx, k_zero_unknowns, grid, block, 0, lv, u0, scal);
+        SA_LAUNCH(ctx, k_zero_unknowns, dim3(std::min(grid.x, 4u * (unsigned)ctx->sm_count), grid.y), block, 0, lv, u0, scal);
     SA_CUDA(ctx, cudaGetLastError());
     SA_CUDA(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
     SA_LAUNCH(ctx, k_publish_scalars, (nb + 63) / 64, 64, 0, scal, nb, h_scal_dev);

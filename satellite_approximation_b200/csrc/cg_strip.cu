@@ -562,19 +562,22 @@ __global__ void __launch_bounds__(ST_THREADS, 4) k_setup2(Level lv, int nbands, 
             const unsigned ldm = (own | (own << 1) | (own >> 1) | __shfl_up_sync(0xffffffffu, own, 1) | __shfl_down_sync(0xffffffffu, own, 1)) & ST_NRM;
             const int64_t gr = (int64_t)tb.ty() * TILE_H + row0, gc = (int64_t)tb.tx() * TILE_W + 2 * cx;
             const unsigned em = (west ? mL : (east ? mR : 0u)) >> 1;  // own rows whose edge cell is an unknown
+            // of the image only KNOWN values are looked at (x0 replaces the unknown cells): a pair of two unknowns, or a
+            // halo cell that is an unknown itself, is not loaded -- inside a hole that is every load of u
+            const unsigned ldu = ldm & ~(mL & mR), emu = em & ~((west ? mW : mE) >> 1);
             double* ub = uband + origin;
             double2 uv[ST_NR], gv[ST_NR];
             double ue[ST_RG], ge[ST_RG];
 #pragma unroll
             for (int j = 0; j < ST_NR; ++j) {
-                uv[j] = ld2_if(ub + (toff + j * pitch), ldm, 1u << j);
+                uv[j] = ld2_if(ub + (toff + j * pitch), ldu, 1u << j);
                 gv[j] = POISSON ? ldnc2_if(gband + origin + (toff + j * pitch), ldm, 1u << j) : make_double2(0.0, 0.0);
             }
             {
                 const int eoff = toff + (west ? -1 : 2);
 #pragma unroll
                 for (int j = 0; j < ST_RG; ++j) {
-                    ue[j] = ld_if(ub + (eoff + (j + 1) * pitch), em, 1u << j);
+                    ue[j] = ld_if(ub + (eoff + (j + 1) * pitch), emu, 1u << j);
                     ge[j] = POISSON ? ldnc_if(gband + origin + (eoff + (j + 1) * pitch), em, 1u << j) : 0.0;
                 }
             }
