@@ -360,6 +360,17 @@ BYTES_J64 = [25.0, 41.0, 25.0, 19.0, 18.0, 26.0, 18.0, 26.0]
 NK = 8
 
 
+def rb_tables(rb):
+    """Names and algorithmic bytes per unknown of the kernel classes of the red-black path.  The strip CG applies x += alpha p
+    every other pass (k_update2, XM; SATFILL_DEFER_X=0 switches it off): the even passes leave x alone (41 - 16 = 25 B, class
+    3), the odd ones add the steps of both (41 + R p_prev 4 = 45 B, class 1)."""
+    names, bpu = list(KERNEL_NAMES_RB), list(BYTES_RB_CTA if rb == "cta" else BYTES_RB)
+    if os.environ.get("SATFILL_DEFER_X", "1") != "0":
+        names[1], bpu[1] = "cg_update, two steps into x (k_update2 XM=2)", 45.0
+        names[3], bpu[3] = "cg_update, x left alone (k_update2 XM=1)", 25.0
+    return names, bpu
+
+
 class Timed:
     """K steps of a resident scene, timed with CUDA events on the launching stream; per-class kernel times accumulated
     from sa_options.profile."""
@@ -397,7 +408,7 @@ class Timed:
 
 
 def kernel_table(t: Timed, rb, unit_scale=1.0):
-    names, bpu = (KERNEL_NAMES_RB, BYTES_RB_CTA if rb == "cta" else BYTES_RB) if rb else (KERNEL_NAMES_J64, BYTES_J64)
+    names, bpu = rb_tables(rb) if rb else (KERNEL_NAMES_J64, BYTES_J64)
     tab = {}
     for c in range(NK):
         if t.kn[c]:
@@ -500,7 +511,7 @@ def run_b200(args, w):
     rb = args.precond == "multigrid" and args.mg_variant != "jacobi64"
     if rb and args.mg_variant == "rb32_cta":
         rb = "cta"
-    names, bpu = (KERNEL_NAMES_RB, BYTES_RB_CTA if rb == "cta" else BYTES_RB) if rb else (KERNEL_NAMES_J64, BYTES_J64)
+    names, bpu = rb_tables(rb) if rb else (KERNEL_NAMES_J64, BYTES_J64)
     kms, kn, ku = timed.kms, timed.kn, [u * unit_scale for u in timed.ku]
     dom = max(range(NK), key=lambda c: kms[c])
     peak, peak_src = peaks()
@@ -509,7 +520,9 @@ def run_b200(args, w):
     traffic_src = None
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        ent = tj.get(["k_direction2", "k_update2", None, None, "k_rb_down", "k_rb_up", None, None][dom] or "")
+        ent = tj.get(["k_direction2", "k_update2", None, "k_update2_x_left_alone" if rb else None, "k_rb_down", "k_rb_up", None, None][dom] or "")
+        if ent and dom == 1 and rb and names[1] != KERNEL_NAMES_RB[1] and "float, 2>" not in ent.get("kernel", ""):
+            ent = None  # a capture of the undeferred kernel does not describe this one
         if ent and args.workload == tj.get("workload", "c3") and not args.mask:
             traffic_src = ent
     except Exception:

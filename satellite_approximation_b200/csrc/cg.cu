@@ -707,6 +707,9 @@ int solve_scene(sa_scene* s, const sa_options& o, sa_stats* stats)
     int64_t k = 0, batch = 0;
     bool all_done = false;
     int live = nb;  // bands not done at the last poll
+    // strip CG with the float search direction: x += alpha p every other pass (SATFILL_DEFER_X=0 switches it off)
+    static const bool defer_env = [] { const char* e = std::getenv("SATFILL_DEFER_X"); return !e || std::atoi(e) != 0; }();
+    const bool defer_x = defer_env && strip && mg && rb && pf;
     while (k < max_it && !all_done) {
         int64_t k_stop = k + check < max_it ? k + check : max_it;
         for (; k < k_stop; ++k) {
@@ -742,9 +745,11 @@ int solve_scene(sa_scene* s, const sa_options& o, sa_stats* stats)
                 if (dist)  // the halo row of p' and p'.Ap' in one exchange
                     SA_TRY(dist_step(s, 0, DIST_VEC_DIR, pf ? pout_v : (void*)pout, pf ? 4 : 8, s->pitch, s->plane, 1, 1, DIST_PQ, ki & 3,
                         (ki + 2) & 3));
-                kt.begin(KC_UPDATE, n_units * live);
+                // x travels every other pass (k_update2, XM): even passes leave it alone, odd ones add both steps
+                const int xm = defer_x ? ((k & 1) ? 2 : 1) : 0;
+                kt.begin(xm == 1 ? KC_UPDATE_DEFERRED : KC_UPDATE, n_units * live);
                 if (strip)
-                    SA_TRY(launch_update2(ctx, lv, nb, false, u0, pout_v, pf, r0, rf, scal, ki));
+                    SA_TRY(launch_update2(ctx, lv, nb, false, u0, pout_v, pf, r0, rf, scal, ki, xm, pin_v));
                 else if (rb)
                     SA_LAUNCH_LEGACY(ctx, (k_update<false, true>), grid, block, 0, lv, u0, pout, r0, rf, scal, ki);
                 else
@@ -798,6 +803,8 @@ int solve_scene(sa_scene* s, const sa_options& o, sa_stats* stats)
         }
         ++batch;
     }
+    if (defer_x)  // the step a band's last pass left behind
+        SA_TRY(launch_flush_x(ctx, lv, nb, u0, pbuf_f[0], pbuf_f[1], scal));
     SA_LAUNCH(ctx, k_final_check, (nb + 63) / 64, 64, 0, scal, nb, (int)(k & 0x3fffffff));
     if (have_tiles)
         SA_LAUNCH(ctx, k_zero_unknowns, dim3(std::min(grid.x, 4u * (unsigned)ctx->sm_count), grid.y), block, 0, lv, u0, scal);

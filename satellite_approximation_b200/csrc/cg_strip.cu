@@ -412,9 +412,15 @@ __global__ void __launch_bounds__(ST_THREADS, dir_ctas<ZT>()) k_direction2(Level
 // k_update2:  alpha = rz / pq;  x += alpha p;  r -= alpha A p  (A p recomputed);  |r|^2 and (JACOBI) r.(r/d)
 //   RF: also write the residual as float for the red-black cycle.
 // ---------------------------------------------------------------------------------------------------------------
-template <bool JACOBI, bool FIXED, bool RF, typename PT>
+//   XM (the float-direction path): x is only ever accumulated, so its 16 bytes per unknown travel every OTHER pass.
+//     XM = 1 (even passes): x is neither loaded nor stored; alpha stays in alpha_hist[k & 1], the direction in its buffer
+//     (the next k_direction2 writes the OTHER buffer), pend is raised.
+//     XM = 2 (odd passes): x += alpha_{k-1} p_{k-1} + alpha_k p_k (4 more bytes: p_{k-1}), pend is lowered.
+//     A band whose last pass was an XM = 1 pass gets its step from k_flush_x after the loop.
+template <bool JACOBI, bool FIXED, bool RF, typename PT, int XM = 0>
 __global__ void __launch_bounds__(ST_THREADS, ST_UPD_CTAS) k_update2(Level lv, int nbands, double* __restrict__ u,
-    const PT* __restrict__ p, double* __restrict__ rvec, float* __restrict__ rf, BandScalars* __restrict__ scal, int k)
+    const PT* __restrict__ p, double* __restrict__ rvec, float* __restrict__ rf, BandScalars* __restrict__ scal, int k,
+    const PT* __restrict__ p_prev = nullptr)
 {
     __shared__ double s_red[ST_WARPS];
     const int slot = k & 3, next = (k + 1) & 3;
@@ -427,9 +433,16 @@ __global__ void __launch_bounds__(ST_THREADS, ST_UPD_CTAS) k_update2(Level lv, i
         if (sc.done)
             continue;
         const double alpha = sc.rz[slot] / sc.pq[slot];  // ConjugateGradient.h:68
+        const double alpha_prev = XM == 2 ? sc.alpha_hist[(k + 1) & 1] : 0.0;  // written by the previous launch
+        if (XM != 0 && blockIdx.x == 0 && threadIdx.x == 0) {  // every CTA visits every live band: one writer
+            sc.alpha_hist[k & 1] = alpha;
+            sc.pend = XM == 1 ? 1 : 0;
+            sc.pend_buf = (k + 1) & 1;  // cg.cu: pass k's direction lives in p buffer (k + 1) & 1
+        }
         const int64_t band_off = (int64_t)band * lv.plane;
         double r2 = 0.0, rz = 0.0;
         const PT* pband = p + band_off;
+        const PT* qband = XM == 2 ? p_prev + band_off : nullptr;
         double* uband = u + band_off;
         double* rband = rvec + band_off;
         float* rfband = RF ? rf + band_off : nullptr;
@@ -453,14 +466,17 @@ __global__ void __launch_bounds__(ST_THREADS, ST_UPD_CTAS) k_update2(Level lv, i
             // whole 32-byte sectors are written (see k_direction2): x of a cell that is not an unknown is written back as
             // read, so x is loaded wherever its sector is stored (the sector travels anyway)
             const unsigned st2 = sector_or2(any), st4 = RF ? sector_or4(st2) : 0u;
-            double2 pv[ST_NR], xv[ST_RG], rv[ST_RG];
+            double2 pv[ST_NR], xv[ST_RG], rv[ST_RG], qv[ST_RG];
             double pe[ST_RG];
 #pragma unroll
             for (int j = 0; j < ST_NR; ++j)
                 pv[j] = ldnc2_if(pb + (toff + j * pitch), any, 1u << j);
 #pragma unroll
             for (int j = 0; j < ST_RG; ++j) {
-                xv[j] = ld2_if(ub + (toff + (j + 1) * pitch), st2, 1u << (j + 1));
+                if (XM != 1)
+                    xv[j] = ld2_if(ub + (toff + (j + 1) * pitch), st2, 1u << (j + 1));
+                if (XM == 2)
+                    qv[j] = ldnc2_if(qband + origin + (toff + (j + 1) * pitch), any, 1u << (j + 1));
                 rv[j] = ld2_if(rb + (toff + (j + 1) * pitch), any, 1u << (j + 1));
             }
             {
@@ -487,13 +503,19 @@ __global__ void __launch_bounds__(ST_THREADS, ST_UPD_CTAS) k_update2(Level lv, i
                 double qr = (double)(dr + dcR) * pv[j].y - ((pv[j - 1].y + pv[j + 1].y) + (pv[j].x + er));
                 // a cell of the pair that is not an unknown keeps its value: p is zero there, and its r stays zero
                 double2 xn, rn;
-                xn.x = ((mL >> j) & 1) ? xv[j - 1].x + alpha * pv[j].x : xv[j - 1].x;                   // ConjugateGradient.h:69
-                xn.y = ((mR >> j) & 1) ? xv[j - 1].y + alpha * pv[j].y : xv[j - 1].y;
+                if (XM != 1) {
+                    // XM = 2: the step of the previous pass first, as if it had been added then
+                    const double2 x0 = XM == 2 ? make_double2(xv[j - 1].x + alpha_prev * qv[j - 1].x, xv[j - 1].y + alpha_prev * qv[j - 1].y)
+                                               : xv[j - 1];
+                    xn.x = ((mL >> j) & 1) ? x0.x + alpha * pv[j].x : xv[j - 1].x;                      // ConjugateGradient.h:69
+                    xn.y = ((mR >> j) & 1) ? x0.y + alpha * pv[j].y : xv[j - 1].y;
+                }
                 rn.x = ((mL >> j) & 1) ? rv[j - 1].x - alpha * ql : 0.0;                                // ConjugateGradient.h:70
                 rn.y = ((mR >> j) & 1) ? rv[j - 1].y - alpha * qr : 0.0;
                 const int off = toff + j * pitch;
                 if ((st2 >> j) & 1) {
-                    *reinterpret_cast<double2*>(ub + off) = xn;
+                    if (XM != 1)
+                        *reinterpret_cast<double2*>(ub + off) = xn;
                     *reinterpret_cast<double2*>(rb + off) = rn;
                 }
                 if (RF && ((st4 >> j) & 1))
@@ -948,14 +970,86 @@ int launch_direction2(sa_ctx* ctx, const Level& lv, int nbands, bool jacobi, con
     return SA_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// k_flush_x: the step a band's last pass left behind (k_update2, XM = 1): x += alpha p at the unknowns of the bands whose
+// pend flag is up.  Runs once after the loop; costs nothing for bands whose last pass was an XM = 2 pass.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(ST_THREADS) k_flush_x(Level lv, int nbands, double* __restrict__ u, const float* __restrict__ p0,
+    const float* __restrict__ p1, const BandScalars* __restrict__ scal)
+{
+    const int cx = threadIdx.x & 15, row0 = (threadIdx.x >> 4) * ST_RG;
+    const int pitch = (int)lv.pitch;
+    for (int band = 0; band < nbands; ++band) {
+        const BandScalars& sc = scal[band];
+        if (!sc.pend)
+            continue;
+        const int buf = sc.pend_buf;
+        const double alpha = sc.alpha_hist[(buf + 1) & 1];  // pass k: slot k & 1, buffer (k + 1) & 1
+        const float* pband = (buf ? p1 : p0) + (int64_t)band * lv.plane;
+        double* uband = u + (int64_t)band * lv.plane;
+        for (int i = blockIdx.x; i < lv.n_tiles; i += gridDim.x) {
+            const TileBits tb = load_tile_bits(lv, lv.tile_yx[i], cx, row0);
+            const unsigned mL = tb.mL(), mR = tb.mR(), any = tb.any() & ST_OWN;
+            if (!any)
+                continue;
+            const int o = tb.origin(pitch) + (row0 - 1) * pitch + 2 * cx;
+            double2 xv[ST_RG], pv[ST_RG];
+#pragma unroll
+            for (int j = 1; j <= ST_RG; ++j) {
+                xv[j - 1] = ld2_if(uband + (o + j * pitch), any, 1u << j);
+                pv[j - 1] = ldnc2_if(pband + (o + j * pitch), any, 1u << j);
+            }
+#pragma unroll
+            for (int j = 1; j <= ST_RG; ++j)
+                if ((any >> j) & 1) {
+                    double2 xn = xv[j - 1];
+                    if ((mL >> j) & 1)
+                        xn.x += alpha * pv[j - 1].x;
+                    if ((mR >> j) & 1)
+                        xn.y += alpha * pv[j - 1].y;
+                    *reinterpret_cast<double2*>(uband + (o + j * pitch)) = xn;
+                }
+        }
+    }
+}
+
+int launch_flush_x(sa_ctx* ctx, const Level& lv, int nbands, double* u, const float* p0, const float* p1, const BandScalars* scal)
+{
+    if (lv.n_tiles == 0 || nbands == 0)
+        return SA_OK;
+    SA_LAUNCH(ctx, k_flush_x, strip_grid(ctx, lv, 8), ST_THREADS, 0, lv, nbands, u, p0, p1, scal);
+    return SA_OK;
+}
+
 int launch_update2(sa_ctx* ctx, const Level& lv, int nbands, bool jacobi, double* u, const void* p, bool p_is_float, double* r,
-    float* rf, BandScalars* scal, int k)
+    float* rf, BandScalars* scal, int k, int xm, const void* p_prev)
 {
     if (lv.n_tiles == 0)
         return SA_OK;
     const unsigned grid = strip_grid(ctx, lv, ST_UPD_CTAS);
+    if (xm != 0) {  // the product path only: float direction, float copy of the residual
+        if (jacobi || !p_is_float || !rf || (xm == 2 && !p_prev))
+            return fail(ctx, SA_BAD_ARGUMENT, "update: deferred x is for the float-direction path");
+#define SA_UPDX(F, X)                                                                                                   \
+    SA_LAUNCH(ctx, (k_update2<false, F, true, float, X>), grid, ST_THREADS, 0, lv, nbands, u, (const float*)p, r, rf, scal, k, \
+        (const float*)p_prev)
+        const bool fx = lv.fixed_diag != 0;
+        if (xm == 1) {
+            if (fx)
+                SA_UPDX(true, 1);
+            else
+                SA_UPDX(false, 1);
+        } else {
+            if (fx)
+                SA_UPDX(true, 2);
+            else
+                SA_UPDX(false, 2);
+        }
+#undef SA_UPDX
+        return SA_OK;
+    }
 #define SA_UPD(J, F, R, PT) \
-    SA_LAUNCH(ctx, (k_update2<J, F, R, PT>), grid, ST_THREADS, 0, lv, nbands, u, (const PT*)p, r, rf, scal, k)
+    SA_LAUNCH(ctx, (k_update2<J, F, R, PT>), grid, ST_THREADS, 0, lv, nbands, u, (const PT*)p, r, rf, scal, k, (const PT*)nullptr)
     const bool fixed = lv.fixed_diag != 0;
     if (jacobi) {
         if (p_is_float)

@@ -54,6 +54,12 @@ struct BandScalars {
     int done;       // sticky: band has met thr (or had a zero right-hand side)
     int iters;      // Eigen-style iteration count at exit (ConjugateGradient.h:65-82)
     int zero_rhs;   // ConjugateGradient.h:43-49: x is set to zero
+    // x += alpha p applied every other pass (k_update2, XM): the band's last pass left alpha_hist[pend_buf ^ 1 ...] -- see
+    // k_flush_x.  pend != 0: the step of the band's last pass (alpha_hist[pend_pass & 1], direction in p buffer pend_buf)
+    // has not been added to x yet.
+    int pend;
+    double alpha_hist[2];  // alpha of pass k in slot k & 1
+    int pend_buf;
     int pad;
 };
 
@@ -248,7 +254,8 @@ inline int64_t round_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
 // Kernel classes reported in sa_stats.kernel_ms / kernel_launches when sa_options.profile is set.
 enum KernelClass {
     KC_DIRECTION = 0, KC_UPDATE = 1, KC_SMOOTH = 2, KC_TRANSFER = 3, KC_MG_DOWN = 4, KC_MG_UP = 5, KC_MG_DOWN_COARSE = 6,
-    KC_MG_UP_COARSE = 7, KC_COUNT = 8
+    KC_MG_UP_COARSE = 7, KC_COUNT = 8,
+    KC_UPDATE_DEFERRED = KC_TRANSFER  // strip CG + red-black cycle: the passes of k_update2 that leave x alone (the slot is free there)
 };
 
 // Brackets individual launches with CUDA events on the launching stream; the pairs are resolved after the next
@@ -341,8 +348,11 @@ int launch_scatter_direct(sa_ctx* ctx, cudaStream_t stream, const Level& lv, int
 int io_ctas(bool scatter);  // CTAs (one SM each) of the fetch / scatter kernel
 int launch_direction2(sa_ctx* ctx, const Level& lv, int nbands, bool jacobi, const void* zin, bool z_is_float,
     const void* p_old, void* p_new, bool p_is_float, BandScalars* scal, int k);
+// xm: 0 = x += alpha p;  1 = x is left alone (alpha and the direction stay behind for the next pass);  2 = x += the step of
+// the previous pass (direction p_prev) and this one
 int launch_update2(sa_ctx* ctx, const Level& lv, int nbands, bool jacobi, double* u, const void* p, bool p_is_float, double* r,
-    float* rf, BandScalars* scal, int k);
+    float* rf, BandScalars* scal, int k, int xm = 0, const void* p_prev = nullptr);
+int launch_flush_x(sa_ctx* ctx, const Level& lv, int nbands, double* u, const float* p0, const float* p1, const BandScalars* scal);
 
 // work_dirty bits
 enum { WORK_CLEAN = 0, WORK_JACOBI = 1, WORK_RB = 2, WORK_J64 = 4, WORK_FULL = 8, WORK_PF = 16 /* p planes hold floats */,

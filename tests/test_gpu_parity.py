@@ -857,3 +857,36 @@ def test_direct_mode_falls_back_on_odd_widths(ctx, port):
     pageable = img.copy()  # pageable memory: copied whole
     ctx.laplace_fill([pageable], mask, tolerance=1e-12, precond=sab.MULTIGRID)
     assert not ctx.last_fill_direct and rel_max_abs(pageable, want, mask) < 1e-8
+
+
+def test_deferred_x_update_equals_the_plain_update(tmp_path):
+    """k_update2 adds alpha p to x every other pass (XM = 1 / 2) and k_flush_x adds the step a band's last pass left behind
+    (cg_strip.cu).  The same solves with SATFILL_DEFER_X=0 -- the plain update of ConjugateGradient.h:69 -- must give the same
+    iterate: after a FIXED number of passes of either parity (iteration limit), and when bands stop at different passes."""
+    import os
+    import subprocess
+    import sys
+
+    here = os.path.dirname(os.path.abspath(__file__))
+    root, worker = os.path.dirname(here), os.path.join(here, "defer_x_worker.py")
+    out = {}
+    for flag in ("1", "0"):
+        path = str(tmp_path / ("defer%s.npz" % flag))
+        r = subprocess.run([sys.executable, worker, path], env=dict(os.environ, SATFILL_DEFER_X=flag, PYTHONPATH=root),
+                           capture_output=True, text=True, timeout=600, cwd=root)  # fmt: skip
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        out[flag] = np.load(path)
+    keys = sorted(out["1"].files)
+    assert keys == sorted(out["0"].files) and len(keys) > 40
+    stops = set()
+    for k in keys:
+        a, b = out["1"][k], out["0"][k]
+        if k.endswith("/iters"):
+            assert np.array_equal(a, b), (k, a, b)
+            stops.update(int(v) & 1 for v in a)
+            continue
+        # not bit-identical: the dot products are atomic sums, so two runs of EITHER mode differ in the last bits of alpha
+        # (1e-12 after seven passes); a step left out is 1e-2 .. 1e-7 of the iterate in these cases
+        scale = np.max(np.abs(b))
+        assert np.max(np.abs(a - b)) <= 1e-10 * scale, (k, float(np.max(np.abs(a - b)) / scale))
+    assert stops == {0, 1}  # bands stopped after odd and after even numbers of passes
