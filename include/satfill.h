@@ -92,8 +92,10 @@ typedef struct sa_stats {
     int32_t status;         /* sa_status of this band                                                           */
     int32_t active_tiles;   /* tiles of the block-sparse layout that contain an unknown                         */
     /* sa_options.profile: summed CUDA-event durations and launch counts of the solver kernels of the whole batch,
-     * by class: 0 = CG direction (p update + p.Ap), 1 = CG update (x, r, norms), 2 = multigrid single sweeps,
-     * 3 = multigrid single transfers (residual, restriction, prolongation), 4 = fused multigrid descent
+     * by class: 0 = CG direction (p update + p.Ap), 1 = CG update (x, r, norms), 2 = multigrid single sweeps (the
+     * default red-black path: its cooperative tail kernel), 3 = multigrid single transfers (residual, restriction,
+     * prolongation; the default red-black path has none and counts here the passes of the CG update that leave x alone --
+     * it adds alpha p to x every other pass, class 1 then holds the passes that add two steps), 4 = fused multigrid descent
      * (pre-smoothing + residual + restriction) on level 0, 5 = fused multigrid ascent (prolongation + post-smoothing)
      * on level 0, 6 / 7 = the same two on the coarse levels */
     double kernel_ms[8];

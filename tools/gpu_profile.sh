@@ -16,9 +16,10 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-fi
 echo "launch list rc=$?"
 # full captures of the level-0 kernels of the second CG iteration (template arguments select the level-0 instantiations)
 B="--steps 1 --warmup 0 --bands 4 --no-e2e --no-cpu --no-dropin --no-multi"
-for ks in "k_update2<:update2" "k_direction2<:direction2" "k_rbw_down<.int.0>:rbw_down_L0" "k_rbw_up<.int.0, .bool.1>:rbw_up_L0" "k_rbw_down<.int.1>:rbw_down_L1" "k_rbw_up<.int.1, .bool.0>:rbw_up_L1"; do
-    k=${ks%%:*}; name=${ks##*:}
-    timeout 600 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:"${k}" --launch-skip 1 --launch-count 1 \
+# (k_update2: launch 1 = the second pass, XM = 2, x takes two steps; launch 2 = the third pass, XM = 1, x left alone)
+for ks in "k_update2<|update2|1" "k_update2<|update2_x_left_alone|2" "k_direction2<|direction2|1" "k_rbw_down<.int.0>|rbw_down_L0|1" "k_rbw_up<.int.0, .bool.1>|rbw_up_L0|1" "k_rbw_down<.int.1>|rbw_down_L1|1" "k_rbw_up<.int.1, .bool.0>|rbw_up_L1|1"; do
+    IFS='|' read -r k name skip <<< "$ks"
+    timeout 600 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:"${k}" --launch-skip $skip --launch-count 1 \
         -f -o $out/${tag}_full_${name} python bench.py $B > $out/${tag}_ncu_${name}.log 2>&1
     echo "ncu $name rc=$?"
 done
