@@ -877,7 +877,7 @@ def test_deferred_x_update_equals_the_plain_update(tmp_path):
         assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
         out[flag] = np.load(path)
     keys = sorted(out["1"].files)
-    assert keys == sorted(out["0"].files) and len(keys) > 40
+    assert keys == sorted(out["0"].files) and len(keys) > 40, len(keys)
     stops = set()
     for k in keys:
         a, b = out["1"][k], out["0"][k]
@@ -885,8 +885,9 @@ def test_deferred_x_update_equals_the_plain_update(tmp_path):
             assert np.array_equal(a, b), (k, a, b)
             stops.update(int(v) & 1 for v in a)
             continue
-        # not bit-identical: the dot products are atomic sums, so two runs of EITHER mode differ in the last bits of alpha
-        # (1e-12 after seven passes); a step left out is 1e-2 .. 1e-7 of the iterate in these cases
+        # not bit-identical: the dot products are atomic sums, so two runs of EITHER mode differ in the last bits of alpha, and
+        # CG amplifies that pass by pass (seen: 1e-12 .. 3e-10 after seven passes); a step left out is 1e-1 .. 1e-5 of the
+        # iterate in these cases (few passes, loose tolerances)
         scale = np.max(np.abs(b))
-        assert np.max(np.abs(a - b)) <= 1e-10 * scale, (k, float(np.max(np.abs(a - b)) / scale))
+        assert np.max(np.abs(a - b)) <= 1e-8 * scale, (k, float(np.max(np.abs(a - b)) / scale))
     assert stops == {0, 1}  # bands stopped after odd and after even numbers of passes
