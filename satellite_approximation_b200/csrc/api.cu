@@ -764,8 +764,9 @@ static int host_fill(sa_ctx* ctx, int problem, double* const* images, const doub
             SA_TRY(prepare_solve(s, o));
             // The way in: while window c is solved on the context's stream, k_fetch_direct pulls the ring of known pixels
             // of window c + 1 over PCIe on io_in.  Every read of host memory is a PCIe round trip and the bus takes only
-            // so many at a time (measured: 4.6 GB/s with 64 CTAs, less with more), so the rings of a 13-band tile need
-            // ~45 ms however they are fetched: they have to travel beside the solves, not in front of them.
+            // so many at a time (measured: 5 - 7 GB/s with ~6000 threads, less with fewer AND with more), so the rings of
+            // a 13-band tile need 30 - 45 ms however they are fetched: they have to travel beside the solves, not in
+            // front of them.
             while ((int)ctx->io_ev.size() < nch) {
                 cudaEvent_t e;
                 SA_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
