@@ -66,3 +66,63 @@ struct MultiChannelImage {  // utils.h:52-106
 };
 
 }  // namespace approx
+
+// read_image / image_list_to_cv / write_image (utils.h:108-110, utils.cpp:16-68): the 8-bit image files either side of the
+// fill.  Only with OpenCV's C++ headers (this image has none; tests/fake_opencv/ holds the few members used here so that the
+// block is compiled and run by tests/test_host_api.py).  Channels are R, G, B in [0, 1], gamma 2.2 decoded on the way in and
+// encoded (truncating, like the reference's static_cast<uchar>) on the way out; files hold B, G, R.
+#if __has_include(<opencv2/imgcodecs.hpp>)
+#include <cmath>
+#include <opencv2/core.hpp>
+#include <opencv2/imgcodecs.hpp>
+
+#include "utils/error.h"
+#include "utils/log.h"
+
+namespace approx {
+
+inline constexpr f64 image_gamma = 2.2;  // utils.cpp:9
+
+inline MultiChannelImage read_image(fs::path path)  // utils.cpp:16-35
+{
+    cv::Mat const file = cv::imread(path.string(), cv::IMREAD_COLOR);
+    if (file.empty())
+        throw utils::IOError("Failed to open image", path);
+    MultiChannelImage out(3, (Eigen::Index)file.rows, (Eigen::Index)file.cols);
+    f64 decode[256];  // 256 possible values: one pow each instead of three per pixel
+    for (int v = 0; v < 256; ++v)
+        decode[v] = std::pow(v / 255.0, 1.0 / image_gamma);
+    for (int r = 0; r < file.rows; ++r)
+        for (int c = 0; c < file.cols; ++c) {
+            cv::Vec3b const bgr = file.at<cv::Vec3b>(r, c);
+            for (int ch = 0; ch < 3; ++ch)
+                out[(size_t)ch](r, c) = decode[bgr[2 - ch]];
+        }
+    return out;
+}
+
+inline std::optional<cv::Mat> image_list_to_cv(std::vector<MatX<f64>> const& channels)  // utils.cpp:37-59
+{
+    if (channels.size() != 3) {
+        utils::log(utils::LogLevel::warn, "approx", "Image with less than 3 channels is not supported. (%zu channels provided)", channels.size());
+        return {};
+    }
+    cv::Mat file((int)channels[0].rows(), (int)channels[0].cols(), CV_8UC3);
+    for (int r = 0; r < file.rows; ++r)
+        for (int c = 0; c < file.cols; ++c) {
+            cv::Vec3b bgr;
+            for (int ch = 0; ch < 3; ++ch)
+                bgr[2 - ch] = static_cast<unsigned char>(std::pow(channels[(size_t)ch](r, c), image_gamma) * 255.0);
+            file.at<cv::Vec3b>(r, c) = bgr;
+        }
+    return file;
+}
+
+inline void write_image(std::vector<MatX<f64>> const& channels, fs::path const& output_path)  // utils.cpp:61-68
+{
+    if (auto const file = image_list_to_cv(channels))
+        cv::imwrite(output_path.string(), *file);
+}
+
+}  // namespace approx
+#endif

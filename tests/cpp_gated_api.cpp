@@ -2,12 +2,17 @@
 // fake C-ABI: the parts of the reference's C++ API that are gated on headers this image lacks --
 //   cv::Mat approx::apply_laplace(cv::Mat const&, cv::Mat const&, f64)                          (laplace.h:31)
 //   std::string approx::find_good_close_image(std::string const&, f64, DataBase&)               (poisson.h:63)
+//   approx::read_image / image_list_to_cv / write_image                                         (utils.h:108-110)
 // Prints the filled image (doubles, one per line) after a header line, and the picker's answers.
 #include <approx/laplace.h>
 #include <approx/poisson.h>
+#include <approx/utils.h>
 
+#include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <string>
 #include <vector>
 
 struct FakeRow {
@@ -69,5 +74,43 @@ int main(int argc, char** argv)
         std::printf(" weight-error %d", db.queries - q0);
     }
     std::printf("\n");
+    // image files (argv[3]: a directory to write into): a 256-level ramp survives write -> read bit for bit except where
+    // the truncating encode lands one level low; the channel order is R, G, B on the C++ side and B, G, R in the file
+    if (argc > 3) {
+        const std::string dir = argv[3];
+        approx::MultiChannelImage ramp(3, 4, 256);
+        for (int r = 0; r < 4; ++r)
+            for (int c = 0; c < 256; ++c) {
+                ramp[0](r, c) = std::pow(c / 255.0, 1.0 / approx::image_gamma);
+                ramp[1](r, c) = std::pow((255 - c) / 255.0, 1.0 / approx::image_gamma);
+                ramp[2](r, c) = r == 0 ? 0.0 : 1.0;
+            }
+        approx::write_image(ramp.images, dir + "/ramp.ppm");
+        approx::MultiChannelImage back = approx::read_image(dir + "/ramp.ppm");
+        int worst = 0, exact = 0;
+        for (int ch = 0; ch < 3; ++ch)
+            for (int r = 0; r < 4; ++r)
+                for (int c = 0; c < 256; ++c) {
+                    const int want = (int)std::lround(std::pow(ramp[(size_t)ch](r, c), approx::image_gamma) * 255.0);
+                    const int got = (int)std::lround(std::pow(back[(size_t)ch](r, c), approx::image_gamma) * 255.0);
+                    worst = std::max(worst, std::abs(want - got));
+                    exact += want == got;
+                }
+        auto const mat = approx::image_list_to_cv(ramp.images);
+        const cv::Vec3b px = mat->at<cv::Vec3b>(2, 255);  // R = 1, G = 0, B = 1  ->  B G R = 255 0 255
+        bool threw_io = false;
+        try {
+            approx::read_image(dir + "/missing.ppm");
+        } catch (utils::IOError const&) {  // utils.cpp:19-21
+            threw_io = true;
+        }
+        std::vector<MatX<f64>> two(2, MatX<f64>::Zero(2, 2));
+        approx::write_image(two, dir + "/two.ppm");  // logged, nothing written (utils.cpp:39-42, 64-66)
+        std::FILE* f = std::fopen((dir + "/two.ppm").c_str(), "rb");
+        std::printf("images %d %d %d %d %d %d %d %d %d\n", (int)back.rows(), (int)back.cols(), worst, exact, (int)px[0], (int)px[1], (int)px[2],
+            threw_io ? 1 : 0, f ? 1 : 0);
+        if (f)
+            std::fclose(f);
+    }
     return 0;
 }

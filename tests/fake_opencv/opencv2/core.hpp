@@ -1,5 +1,6 @@
-// TEST INFRASTRUCTURE -- a minimal cv::Mat (the members approx::apply_laplace(cv::Mat ...) touches), so that the
-// OpenCV-gated part of cpp/include/approx/laplace.h compiles and runs in an image without OpenCV's C++ headers.
+// TEST INFRASTRUCTURE -- a minimal cv::Mat (the members approx::apply_laplace(cv::Mat ...) and approx::read_image /
+// image_list_to_cv touch), so that the OpenCV-gated parts of cpp/include/approx/{laplace,utils}.h compile and run in an image
+// without OpenCV's C++ headers.
 #pragma once
 #include <cstring>
 #include <memory>
@@ -9,6 +10,11 @@
 #define CV_8UC3 CV_MAKETYPE(CV_8U, 3)
 #define CV_64FC3 CV_MAKETYPE(CV_64F, 3)
 namespace cv {
+struct Vec3b {
+    unsigned char v[3] = { 0, 0, 0 };
+    unsigned char& operator[](int i) { return v[i]; }
+    unsigned char const& operator[](int i) const { return v[i]; }
+};
 class Mat {
 public:
     int rows = 0, cols = 0;
@@ -17,6 +23,11 @@ public:
     Mat(int r, int c, int type) : rows(r), cols(c), type_(type), store_(new unsigned char[(size_t)r * c * elem()]) { data = store_.get(); }
     int type() const { return type_; }
     bool isContinuous() const { return true; }
+    bool empty() const { return data == nullptr || rows * cols == 0; }
+    template <typename T>
+    T& at(int r, int c) { return reinterpret_cast<T*>(data)[(size_t)r * cols + c]; }
+    template <typename T>
+    T const& at(int r, int c) const { return reinterpret_cast<T const*>(data)[(size_t)r * cols + c]; }
     Mat clone() const
     {
         Mat m(rows, cols, type_);

@@ -223,9 +223,16 @@ def test_cpp_api_gated_on_opencv_and_the_database(tmp_path):
     assert r.returncode == 0, r.stderr[-3000:]
     rows, cols = 37, 45
     env = dict(os.environ, LD_LIBRARY_PATH=str(fake) + os.pathsep + os.environ.get("LD_LIBRARY_PATH", ""))
-    r = subprocess.run([str(exe), str(rows), str(cols)], env=env, capture_output=True, text=True, timeout=300)
+    r = subprocess.run([str(exe), str(rows), str(cols), str(tmp_path)], env=env, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr[-2000:]
     lines = r.stdout.strip().splitlines()
+    # read_image / image_list_to_cv / write_image (utils.cpp:16-68): size, worst level error of a write -> read round trip of
+    # a ramp (the reference's truncating encode lands one level low wherever pow(pow(v, 1/2.2), 2.2) * 255 comes out a hair under
+    # the integer: about a third of the levels), B G R order in the file, IOError, nothing written for 2 channels
+    img = lines.pop().split()
+    assert img[0] == "images" and [int(v) for v in img[1:3]] == [4, 256] and int(img[3]) <= 1 and int(img[4]) > 3 * 4 * 256 * 0.5
+    assert [int(v) for v in img[5:]] == [255, 0, 255, 1, 0], img
+    assert "less than 3 channels" in r.stderr
     assert lines[0] == f"image {rows} {cols}"
     vals = np.array([[float(x) for x in ln.split()] for ln in lines[1 : 1 + rows * cols * 3]])
     image = vals[:, 0].astype(np.uint8).reshape(rows, cols, 3)
