@@ -494,6 +494,9 @@ def run_b200(args, w):
     clocks = sampler.stop()
     launches = timed.launches
     st = timed.st
+    # HBM held by this process while the resident scene exists (the library's planes + the bench's own copies of the inputs)
+    free_b, total_b = torch.cuda.mem_get_info(dev)
+    hbm_used_gb = (total_b - free_b) / 1e9
     unit_scale = 1.0  # the library's per-launch units are the unknowns THIS rank processed (row-decomposed solves included)
     unknowns = st[0]["unknowns"]
     ok = all(s["status"] == sab.SA_OK for s in st)
@@ -595,7 +598,7 @@ def run_b200(args, w):
         cfg = {"workload": w["desc"], "problem": w["problem"], "rows": rows, "cols": cols, "bands": nb,
                "mask": ("SURVEY 8d: Gaussian-filtered (sigma = %g px) white noise thresholded at the analytic %g quantile, border ring "
                         "cleared (synth.torch_cloud_mask, seed %s)" % (w["sigma"], 1 - w["cover"], "2 + 17 rank" if args.rank_seeds else "2 on every rank")) if w.get("sigma") and not args.mask else (args.mask or "see workload"),
-               "setup_ms": st[0]["setup_ms"], "solve_ms": st[0]["solve_ms"],
+               "setup_ms": st[0]["setup_ms"], "solve_ms": st[0]["solve_ms"], "hbm_used_gb": hbm_used_gb,
                "unknowns_per_band": unknowns, "tolerance": args.tol, "precond": args.precond,
                "mg_variant": args.mg_variant if args.precond == "multigrid" else None,
                "cg_iterations": timed.iters, "cg_iterations_per_band": [s["iterations"] for s in st], "converged": ok,

@@ -362,7 +362,7 @@ static int scrub_work_vectors(sa_scene* s, bool lean)
         P.d[P.nd++] = s->plane0(s->p[0], 0);
         P.d[P.nd++] = s->plane0(s->p[1], 0);
     }
-    if ((s->work_dirty & WORK_J64) && s->z) {
+    if ((s->work_dirty & WORK_J64) && s->z && s->t) {
         P.d[P.nd++] = s->plane0(s->z, 0);
         P.d[P.nd++] = s->plane0(s->t, 0);
     }
@@ -370,7 +370,8 @@ static int scrub_work_vectors(sa_scene* s, bool lean)
         P.f[P.nf++] = (float*)s->z + s->pitch;                                   // z of the red-black cycle
         if (!lean) {
             P.f[P.nf++] = (float*)s->z + (int64_t)s->plane * nb + s->pitch;       // float copy of the residual
-            P.h[P.nh++] = (float*)s->t + (s->pitch >> 1);                         // red half of the iterate
+            if (s->t)  // (first-generation cycle only: the product library does not allocate it)
+                P.h[P.nh++] = (float*)s->t + (s->pitch >> 1);                     // red half of the iterate
         }
     }
     SA_TRY(launch_scrub(ctx, fine_level(s), nb, P));
@@ -379,7 +380,7 @@ static int scrub_work_vectors(sa_scene* s, bool lean)
             if (c.lv.n_tiles == 0)
                 break;
             ScrubPlanes Q {};
-            if (s->work_dirty & WORK_J64) {
+            if ((s->work_dirty & WORK_J64) && c.t) {
                 Q.d[Q.nd++] = c.x + c.lv.pitch;
                 Q.d[Q.nd++] = c.b + c.lv.pitch;
                 Q.d[Q.nd++] = c.t + c.lv.pitch;
@@ -388,7 +389,8 @@ static int scrub_work_vectors(sa_scene* s, bool lean)
                 Q.f[Q.nf++] = (float*)c.x + c.lv.pitch;  // prolongation reads the coarse correction unmasked
                 if (!lean) {
                     Q.f[Q.nf++] = (float*)c.b + c.lv.pitch;
-                    Q.h[Q.nh++] = (float*)c.t + (c.lv.pitch >> 1);
+                    if (c.t)
+                        Q.h[Q.nh++] = (float*)c.t + (c.lv.pitch >> 1);
                 }
             }
             SA_TRY(launch_scrub(ctx, c.lv, nb, Q));
@@ -410,7 +412,8 @@ static int clear_multigrid_vectors(sa_scene* s)
         size_t vec = (size_t)c.lv.plane * s->nbands * sizeof(double);
         SA_CUDA(ctx, cudaMemsetAsync(c.x, 0, vec, ctx->stream));
         SA_CUDA(ctx, cudaMemsetAsync(c.b, 0, vec, ctx->stream));
-        SA_CUDA(ctx, cudaMemsetAsync(c.t, 0, vec, ctx->stream));
+        if (c.t)
+            SA_CUDA(ctx, cudaMemsetAsync(c.t, 0, vec, ctx->stream));
     }
     return SA_OK;
 }
@@ -494,10 +497,12 @@ static int ensure_multigrid(sa_scene* s, const sa_options& o)
     sa_ctx* ctx = s->ctx;
     if (!s->z) {
         size_t bytes = (size_t)s->plane * s->nbands * sizeof(double);
-        SA_CUDA(ctx, cudaMalloc(&s->z, bytes));
-        SA_CUDA(ctx, cudaMalloc(&s->t, bytes));
+        SA_CUDA(ctx, cudaMalloc(&s->z, bytes));  // the red-black cycle: z (float) in the first half, the float copy of r in the second
         SA_CUDA(ctx, cudaMemsetAsync(s->z, 0, bytes, ctx->stream));
+#if SATFILL_LEGACY_VARIANTS  // the second plane of the first-generation cycles (ping-pong partner / red half of the iterate)
+        SA_CUDA(ctx, cudaMalloc(&s->t, bytes));
         SA_CUDA(ctx, cudaMemsetAsync(s->t, 0, bytes, ctx->stream));
+#endif
     }
     if (!s->hierarchy_built)
         SA_TRY(build_hierarchy(s, o));

@@ -169,11 +169,13 @@ static int alloc_hierarchy(sa_scene* s, const sa_options& o)
         SA_CUDA(ctx, cudaMalloc(&L.d_counters, sizeof(int32_t) * 4 + sizeof(unsigned long long)));
         SA_CUDA(ctx, cudaMalloc(&L.x, vec));
         SA_CUDA(ctx, cudaMalloc(&L.b, vec));
+#if SATFILL_LEGACY_VARIANTS  // the first-generation cycles' third vector; the product cycle keeps x and b only
         SA_CUDA(ctx, cudaMalloc(&L.t, vec));
+        SA_CUDA(ctx, cudaMemsetAsync(L.t, 0, vec, ctx->stream));
+#endif
         // cleared once; afterwards a mask change scrubs them through the old tile lists (cg.cu: scrub_work_vectors)
         SA_CUDA(ctx, cudaMemsetAsync(L.x, 0, vec, ctx->stream));
         SA_CUDA(ctx, cudaMemsetAsync(L.b, 0, vec, ctx->stream));
-        SA_CUDA(ctx, cudaMemsetAsync(L.t, 0, vec, ctx->stream));
         SA_CUDA(ctx, cudaMalloc(&L.winv, (size_t)L.lv.plane * sizeof(float)));
         SA_CUDA(ctx, cudaMemsetAsync(L.winv, 0, (size_t)L.lv.plane * sizeof(float), ctx->stream));
         size_t words = (size_t)(L.lv.tiles_x + 2) * (L.lv.tiles_y + 2) * 32;
