@@ -80,8 +80,6 @@ int scene_alloc(sa_scene* s, bool transposed)
     size_t vec = (size_t)s->plane * s->nbands * sizeof(double);
     SA_CUDA(ctx, cudaMalloc(&s->u, vec));
     SA_CUDA(ctx, cudaMalloc(&s->r, vec));
-    SA_CUDA(ctx, cudaMalloc(&s->p[0], vec));
-    SA_CUDA(ctx, cudaMalloc(&s->p[1], vec));
     SA_CUDA(ctx, cudaMemsetAsync(s->u, 0, vec, ctx->stream));
     if (s->problem == SA_POISSON) {
         SA_CUDA(ctx, cudaMalloc(&s->g, vec));

@@ -399,6 +399,39 @@ static int scrub_work_vectors(sa_scene* s, bool lean)
     return SA_OK;
 }
 
+// The two buffers of the search direction (ping-pong).  The product path keeps p in float, so they are sized for float
+// planes -- half of what round 1 allocated, 12.6 GB of a C3 scene -- and grow (contents dropped: they are only ever needed
+// zero outside the unknown set) the first time a path wants double planes (Jacobi, the first-generation CG).  Never less
+// than one double plane: precondition_scene hands its result back through p[0].
+int ensure_p(sa_scene* s, size_t elem_bytes)
+{
+    sa_ctx* ctx = s->ctx;
+    const size_t need = std::max((size_t)s->plane * s->nbands * elem_bytes, (size_t)s->plane * sizeof(double));
+    if (s->p_bytes >= need)
+        return SA_OK;
+    if (s->p[0] || s->p[1])
+        SA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(s->p[0]);
+    cudaFree(s->p[1]);
+    s->p[0] = s->p[1] = nullptr;
+    s->p_bytes = 0;
+    SA_CUDA(ctx, cudaMalloc(&s->p[0], need));
+    SA_CUDA(ctx, cudaMalloc(&s->p[1], need));
+    SA_CUDA(ctx, cudaMemsetAsync(s->p[0], 0, need, ctx->stream));
+    SA_CUDA(ctx, cudaMemsetAsync(s->p[1], 0, need, ctx->stream));
+    s->p_bytes = need;
+    return SA_OK;
+}
+
+static int clear_p(sa_scene* s)
+{
+    if (s->p_bytes) {
+        SA_CUDA(s->ctx, cudaMemsetAsync(s->p[0], 0, s->p_bytes, s->ctx->stream));
+        SA_CUDA(s->ctx, cudaMemsetAsync(s->p[1], 0, s->p_bytes, s->ctx->stream));
+    }
+    return SA_OK;
+}
+
 // Clear everything the multigrid cycles write (variant switch, or contents unknown).
 static int clear_multigrid_vectors(sa_scene* s)
 {
@@ -425,8 +458,7 @@ static int clear_stale_vectors(sa_scene* s)
     sa_ctx* ctx = s->ctx;
     size_t bytes = (size_t)s->plane * s->nbands * sizeof(double);
     SA_CUDA(ctx, cudaMemsetAsync(s->r, 0, bytes, ctx->stream));
-    SA_CUDA(ctx, cudaMemsetAsync(s->p[0], 0, bytes, ctx->stream));
-    SA_CUDA(ctx, cudaMemsetAsync(s->p[1], 0, bytes, ctx->stream));
+    SA_TRY(clear_p(s));
     SA_TRY(clear_multigrid_vectors(s));
     s->stale_r = s->stale_rb = s->stale_all = false;
     s->work_dirty &= ~(WORK_JACOBI | WORK_RB | WORK_J64 | WORK_PF | WORK_RBW);
@@ -442,8 +474,7 @@ int ensure_indexed(sa_scene* s, int next_kind)
     if ((s->work_dirty & WORK_FULL) || !s->ever_indexed) {
         size_t bytes = (size_t)s->plane * s->nbands * sizeof(double);
         SA_CUDA(ctx, cudaMemsetAsync(s->r, 0, bytes, ctx->stream));
-        SA_CUDA(ctx, cudaMemsetAsync(s->p[0], 0, bytes, ctx->stream));
-        SA_CUDA(ctx, cudaMemsetAsync(s->p[1], 0, bytes, ctx->stream));
+        SA_TRY(clear_p(s));
         SA_TRY(clear_multigrid_vectors(s));
         s->stale_r = s->stale_rb = s->stale_all = false;
     } else if (s->work_dirty != WORK_CLEAN) {
@@ -517,6 +548,7 @@ int precondition_scene(sa_scene* s, const sa_options& o)
         return fail(ctx, SA_BAD_ARGUMENT, "this libsatfill holds the product kernels only (SATFILL_LEGACY_VARIANTS)");
 #endif
     SA_TRY(ensure_multigrid(s, o));
+    SA_TRY(ensure_p(s, sizeof(float)));  // (at least one double plane: the result goes out through p[0])
     if (s->stale_all && o.mg_variant != SA_MG_RB32)
         SA_TRY(clear_stale_vectors(s));
     s->work_dirty = WORK_FULL;  // the caller's vector goes through r and p: clear everything before the next solve
@@ -555,6 +587,7 @@ int prepare_solve(sa_scene* s, const sa_options& o)
     const bool rb = mg && o.mg_variant != SA_MG_JACOBI64;
     const bool strip = o.cg_variant == 0;
     const bool rbw = rb && strip && o.mg_variant == SA_MG_RB32;
+    SA_TRY(ensure_p(s, strip && rb ? sizeof(float) : sizeof(double)));  // (grows before anything below touches p)
     SA_TRY(ensure_indexed(s, !mg ? WORK_JACOBI : (rb && strip ? (WORK_RB | (rbw ? WORK_RBW : 0)) : WORK_J64)));
     if (s->stale_all && !rbw)
         SA_TRY(clear_stale_vectors(s));
@@ -578,9 +611,7 @@ int prepare_solve(sa_scene* s, const sa_options& o)
         // ... and so do the two precisions of the search direction
         const bool pf_now = o.cg_variant == 0 && rb;
         if ((s->work_dirty & (WORK_JACOBI | WORK_RB | WORK_J64)) && ((s->work_dirty & WORK_PF) != 0) != pf_now) {
-            size_t bytes = (size_t)s->plane * s->nbands * sizeof(double);
-            SA_CUDA(ctx, cudaMemsetAsync(s->p[0], 0, bytes, ctx->stream));
-            SA_CUDA(ctx, cudaMemsetAsync(s->p[1], 0, bytes, ctx->stream));
+            SA_TRY(clear_p(s));
         }
         s->work_dirty = (s->work_dirty & ~(WORK_PF | WORK_RBW)) | kind | (pf_now ? WORK_PF : 0) | (rbw ? WORK_RBW : 0);
     }

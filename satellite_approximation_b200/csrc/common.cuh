@@ -172,6 +172,7 @@ struct sa_scene {
     double* p[2] = { nullptr, nullptr };
     double* z = nullptr;   // multigrid only: preconditioned residual
     double* t = nullptr;   // multigrid only: fine-level scratch (smoother ping-pong, residual)
+    size_t p_bytes = 0;    // bytes of each of p[0], p[1]: float planes for the product path, double planes once a path needs them (cg.cu: ensure_p)
     uint8_t* mask = nullptr;   // normalised 0/1 invalid mask (allocation base)
     uint8_t* umask = nullptr;  // unknown set (allocation base)
     int32_t* tile_list = nullptr;
@@ -345,6 +346,7 @@ int prepare_solve(sa_scene* s, const sa_options& o);
 int launch_fetch_direct(sa_ctx* ctx, cudaStream_t stream, const Level& lv, int nbands, bool poisson, double* u, double* g,
     const HostBands& src);
 int launch_scatter_direct(sa_ctx* ctx, cudaStream_t stream, const Level& lv, int nbands, const double* u, const HostBands& dst);
+int ensure_p(sa_scene* s, size_t elem_bytes);  // cg.cu: the two search-direction buffers, sized for float or double planes
 int io_ctas(bool scatter);  // CTAs (one SM each) of the fetch / scatter kernel
 int launch_direction2(sa_ctx* ctx, const Level& lv, int nbands, bool jacobi, const void* zin, bool z_is_float,
     const void* p_old, void* p_new, bool p_is_float, BandScalars* scal, int k);
