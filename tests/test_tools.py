@@ -60,3 +60,17 @@ def test_bench_scene_is_window_reproducible():
     bt = synth.torch_scene_band(120, 90, seed=5, device="cpu", row0=100, col0=50, total_rows=10980, total_cols=10980).numpy()
     assert np.max(np.abs(b - bt)) < 1e-9 and b.min() >= 0.0 and b.max() <= 10000.0
     assert abs(synth.cloud_threshold(40.0, 0.5)) < 1e-12 and synth.cloud_threshold(40.0, 0.3) > 0
+
+
+def test_every_runtime_switch_of_the_library_is_documented():
+    """INTEGRATION.md section 6 lists the environment variables libsatfill reads: no switch without a line there."""
+    import glob
+    import re
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    read = set()
+    for path in glob.glob(os.path.join(root, "satellite_approximation_b200", "csrc", "*.cu*")):
+        read.update(re.findall(r'(?:getenv|env_int)\("(SATFILL_[A-Z0-9_]+)"', open(path).read()))
+    doc = open(os.path.join(root, "INTEGRATION.md")).read()
+    assert len(read) >= 10
+    assert not [v for v in sorted(read) if v not in doc]
