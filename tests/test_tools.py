@@ -74,3 +74,21 @@ def test_every_runtime_switch_of_the_library_is_documented():
     doc = open(os.path.join(root, "INTEGRATION.md")).read()
     assert len(read) >= 10
     assert not [v for v in sorted(read) if v not in doc]
+
+
+def test_bench_kernel_classes_follow_the_update_mode(monkeypatch):
+    """bench.py accounts the CG update per class: with the deferred x update (default) the passes that leave x alone are
+    class 3 at 25 B per unknown and the two-step passes class 1 at 45 B -- 35 on average against the plain update's 41, which
+    SATFILL_DEFER_X=0 selects in the library and in the table alike."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_under_test", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    monkeypatch.delenv("SATFILL_DEFER_X", raising=False)
+    names, bpu = bench.rb_tables(True)
+    assert (bpu[1], bpu[3]) == (45.0, 25.0) and "XM=2" in names[1] and "XM=1" in names[3]
+    assert (bpu[1] + bpu[3]) / 2 == 35.0 and len(names) == len(bpu) == bench.NK
+    monkeypatch.setenv("SATFILL_DEFER_X", "0")
+    names, bpu = bench.rb_tables(True)
+    assert bpu[1] == 41.0 and names[1] == bench.KERNEL_NAMES_RB[1] and bpu == bench.BYTES_RB
+    assert bench.rb_tables("cta")[1] == bench.BYTES_RB_CTA
